@@ -1,0 +1,219 @@
+"""ctypes binding of libdd_b200.so (include/dd_b200.h).
+
+This is the *only* way the Python host reaches the GPU kernels: plain pointers and sizes, PyTorch tensors
+are nothing more than the device-memory container (``tensor.data_ptr()``).  There is no CPU fallback:
+if the shared library is missing, or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+DD_F32, DD_F16 = 0, 1
+DD_CONV_RELU, DD_CONV_RELU_COPY = 1, 2
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdd_b200.so")
+
+
+class DDError(RuntimeError):
+  pass
+
+
+class dd_tensor(ctypes.Structure):
+  _fields_ = [("ptr", ctypes.c_void_p), ("dtype", ctypes.c_int32), ("n", ctypes.c_int32), ("h", ctypes.c_int32),
+              ("w", ctypes.c_int32), ("c", ctypes.c_int32), ("cstride", ctypes.c_int32), ("coff", ctypes.c_int32)]
+
+
+class dd_standardize_params(ctypes.Structure):
+  _fields_ = [("use_log1p", ctypes.c_int32), ("mean", ctypes.c_float), ("variance", ctypes.c_float),
+              ("use_variance", ctypes.c_int32), ("variance_mode", ctypes.c_int32),
+              ("relative_variance", ctypes.c_int32), ("compute_before_standardization", ctypes.c_int32),
+              ("compress_to_one_channel", ctypes.c_int32), ("epsilon", ctypes.c_float)]
+
+
+class dd_invert_params(ctypes.Structure):
+  _fields_ = [("use_log1p", ctypes.c_int32), ("mean", ctypes.c_float), ("variance", ctypes.c_float)]
+
+
+class dd_gather_entry(ctypes.Structure):
+  _fields_ = [("ptr", ctypes.c_void_p), ("cstride", ctypes.c_int32), ("cidx", ctypes.c_int32),
+              ("constant", ctypes.c_float), ("pad_", ctypes.c_int32)]
+
+
+_P = ctypes.POINTER
+_vp, _i, _u32, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_size_t
+_T = _P(dd_tensor)
+
+# name -> (restype, argtypes); mirrors include/dd_b200.h declaration by declaration
+SIGNATURES = {
+    "dd_abi_version": (_i, []),
+    "dd_last_error": (ctypes.c_char_p, []),
+    "dd_ctx_create": (_i, [_i, _P(_vp)]),
+    "dd_ctx_destroy": (_i, [_vp]),
+    "dd_ctx_sm_count": (_i, [_vp]),
+    "dd_ctx_set_option": (_i, [_vp, ctypes.c_char_p, _i]),
+    "dd_ctx_launch_count": (ctypes.c_int64, [_vp]),
+    "dd_conv2d_packed_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "dd_conv2d_pack_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "dd_conv2d_fwd": (_i, [_vp, _T, _vp, _vp, _i, _u32, _T, _T, _T, _vp]),
+    "dd_conv2d_transpose2x2_fwd": (_i, [_vp, _T, _vp, _vp, _u32, _T, _vp]),
+    "dd_maxpool_s2_fwd": (_i, [_vp, _T, _i, _T, _vp]),
+    "dd_avgpool_fwd": (_i, [_vp, _T, _i, _T, _vp]),
+    "dd_standardize_variance": (_i, [_vp, _T, _P(dd_standardize_params), _T, _T, _vp]),
+    "dd_assemble_input": (_i, [_vp, _vp, _i, _i, _T, _vp]),
+    "dd_kernel_predict_fwd": (_i, [_vp, _T, _T, _i, _i, _T, _vp]),
+    "dd_compose_head_fwd": (_i, [_vp, _T, _T, _vp, _vp, _i, _T, _vp]),
+    "dd_compose_tail_fwd": (_i, [_vp, _T, _vp, _vp, _i, _T, _T, _P(dd_invert_params), _T, _vp]),
+    "dd_invert_standardization": (_i, [_vp, _T, _P(dd_invert_params), _T, _vp]),
+    "dd_cast_copy": (_i, [_vp, _T, _T, _vp]),
+    "dd_l2_flush": (_i, [_vp, _vp, _sz, _vp]),
+}
+
+_lib = None
+
+
+def load_library(path=None):
+  """Loads libdd_b200.so and installs the prototypes.  Raises DDError when it is not built."""
+  global _lib
+  if _lib is not None and path is None:
+    return _lib
+  path = path or _LIB_PATH
+  if not os.path.exists(path):
+    raise DDError("%s not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                  "(there is no CPU fallback)" % path)
+  lib = ctypes.CDLL(path)
+  for name, (restype, argtypes) in SIGNATURES.items():
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = argtypes
+  if lib.dd_abi_version() != 1:
+    raise DDError("libdd_b200 ABI version mismatch")
+  _lib = lib
+  return lib
+
+
+def _dtype_code(t):
+  if t.dtype == torch.float32:
+    return DD_F32
+  if t.dtype == torch.float16:
+    return DD_F16
+  raise DDError("unsupported tensor dtype %s" % t.dtype)
+
+
+def desc(t, c=None, coff=0):
+  """dd_tensor view of channels [coff, coff+c) of a contiguous NHWC torch tensor."""
+  assert t.dim() == 4 and t.is_contiguous(), "NHWC contiguous tensor expected"
+  n, h, w, cs = t.shape
+  if c is None:
+    c = cs - coff
+  assert 0 <= coff and coff + c <= cs
+  return dd_tensor(t.data_ptr(), _dtype_code(t), n, h, w, c, cs, coff)
+
+
+class Context:
+  """Owns a dd_ctx for one CUDA device and wraps every entry point with error checking."""
+
+  def __init__(self, device=0):
+    self.lib = load_library()
+    if not torch.cuda.is_available():
+      raise DDError("no CUDA device: deepdenoiser_b200 has no CPU fallback")
+    self.device = torch.device("cuda", device)
+    handle = ctypes.c_void_p()
+    self._check(self.lib.dd_ctx_create(device, ctypes.byref(handle)))
+    self.handle = handle
+
+  def __del__(self):
+    try:
+      if getattr(self, "handle", None):
+        self.lib.dd_ctx_destroy(self.handle)
+        self.handle = None
+    except Exception:
+      pass
+
+  def _check(self, rc):
+    if rc != 0:
+      raise DDError("libdd_b200 error %d: %s" % (rc, self.lib.dd_last_error().decode()))
+
+  @staticmethod
+  def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+  # -- context
+  def sm_count(self):
+    return self.lib.dd_ctx_sm_count(self.handle)
+
+  def launch_count(self):
+    return int(self.lib.dd_ctx_launch_count(self.handle))
+
+  def set_option(self, name, value):
+    self._check(self.lib.dd_ctx_set_option(self.handle, name.encode(), int(value)))
+
+  # -- conv
+  def pack_conv_weights(self, w, dtype, transposed=False):
+    """w: CPU float32 tensor in TF layout [kh,kw,cin,cout] ([kh,kw,cout,cin] if transposed).
+    Returns (packed device uint8 tensor)."""
+    w = w.detach().to(torch.float32).contiguous().cpu()
+    ks = w.shape[0]
+    cin, cout = (w.shape[3], w.shape[2]) if transposed else (w.shape[2], w.shape[3])
+    code = DD_F16 if dtype == torch.float16 else DD_F32
+    nbytes = self.lib.dd_conv2d_packed_bytes(ks, cin, cout, code, int(transposed))
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+    self._check(self.lib.dd_conv2d_pack_weights(self.handle, w.data_ptr(), ks, cin, cout, code, int(transposed),
+                                                packed.data_ptr(), self._stream()))
+    return packed
+
+  def conv2d(self, x, w_packed, bias, ksize, y, relu=False, residual=None, y_relu=None):
+    flags = (DD_CONV_RELU if relu else 0) | (DD_CONV_RELU_COPY if y_relu is not None else 0)
+    self._check(self.lib.dd_conv2d_fwd(
+        self.handle, ctypes.byref(x), w_packed.data_ptr(), bias.data_ptr() if bias is not None else None, ksize,
+        flags, ctypes.byref(residual) if residual is not None else None, ctypes.byref(y),
+        ctypes.byref(y_relu) if y_relu is not None else None, self._stream()))
+
+  def conv2d_transpose2x2(self, x, w_packed, bias, y, relu=False):
+    self._check(self.lib.dd_conv2d_transpose2x2_fwd(
+        self.handle, ctypes.byref(x), w_packed.data_ptr(), bias.data_ptr() if bias is not None else None,
+        DD_CONV_RELU if relu else 0, ctypes.byref(y), self._stream()))
+
+  # -- pooling
+  def maxpool_s2(self, x, ksize, y):
+    self._check(self.lib.dd_maxpool_s2_fwd(self.handle, ctypes.byref(x), ksize, ctypes.byref(y), self._stream()))
+
+  def avgpool(self, x, factor, y):
+    self._check(self.lib.dd_avgpool_fwd(self.handle, ctypes.byref(x), factor, ctypes.byref(y), self._stream()))
+
+  # -- encoder
+  def standardize_variance(self, src, params, std_out, var_out):
+    self._check(self.lib.dd_standardize_variance(
+        self.handle, ctypes.byref(src), ctypes.byref(params), ctypes.byref(std_out) if std_out is not None else None,
+        ctypes.byref(var_out) if var_out is not None else None, self._stream()))
+
+  def assemble_input(self, table_dev, tuples, n, out):
+    self._check(self.lib.dd_assemble_input(self.handle, table_dev.data_ptr(), tuples, n, ctypes.byref(out),
+                                           self._stream()))
+
+  # -- kernel prediction / multi-scale
+  def kernel_predict(self, src, logits, ksize, features, out):
+    self._check(self.lib.dd_kernel_predict_fwd(self.handle, ctypes.byref(src), ctypes.byref(logits), ksize, features,
+                                               ctypes.byref(out), self._stream()))
+
+  def compose_head(self, small, large, w_host, b_host, c_mid, y):
+    self._check(self.lib.dd_compose_head_fwd(self.handle, ctypes.byref(small), ctypes.byref(large),
+                                             w_host.data_ptr(), b_host.data_ptr(), c_mid, ctypes.byref(y),
+                                             self._stream()))
+
+  def compose_tail(self, t, w_host, b_host, c_mid, small, large, inv, out):
+    self._check(self.lib.dd_compose_tail_fwd(self.handle, ctypes.byref(t), w_host.data_ptr(), b_host.data_ptr(), c_mid,
+                                             ctypes.byref(small), ctypes.byref(large),
+                                             ctypes.byref(inv) if inv is not None else None, ctypes.byref(out),
+                                             self._stream()))
+
+  def invert_standardization(self, x, inv, y):
+    self._check(self.lib.dd_invert_standardization(self.handle, ctypes.byref(x), ctypes.byref(inv), ctypes.byref(y),
+                                                   self._stream()))
+
+  def cast_copy(self, x, y):
+    self._check(self.lib.dd_cast_copy(self.handle, ctypes.byref(x), ctypes.byref(y), self._stream()))
+
+  def l2_flush(self, scratch):
+    self._check(self.lib.dd_l2_flush(self.handle, scratch.data_ptr(), scratch.numel() * scratch.element_size(),
+                                     self._stream()))

@@ -1,0 +1,540 @@
+// C-ABI: HBM-bound kernels around the convolution stack — pooling, source standardisation + local
+// variance, network-input assembly, the kernel-prediction apply and the multi-scale composition.
+#include <string.h>
+
+#include "dd_internal.h"
+
+namespace dd {
+
+__device__ __forceinline__ float signed_log1p(float v) { return copysignf(log1pf(fabsf(v)), v) * (v != 0.f); }
+__device__ __forceinline__ float signed_expm1(float v) { return copysignf(expm1f(fabsf(v)), v) * (v != 0.f); }
+// np.pad(mode='symmetric'): mirror including the edge sample (Conv2dUtilities.py:77-95)
+__device__ __forceinline__ int sym_index(int i, int n) {
+  // valid for -n <= i < 2n, iterate for tiny images
+  while (i < 0 || i >= n) i = (i < 0) ? (-i - 1) : (2 * n - i - 1);
+  return i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// max pooling, stride 2, TF 'SAME' (pad_total = max((out-1)*2 + k - n, 0), pad_before = pad_total / 2)
+struct PoolParams {
+  View x, y;
+  int ksize, pad_y, pad_x;
+};
+
+__global__ void __launch_bounds__(256) maxpool_generic_kernel(const PoolParams p) {
+  const size_t total = static_cast<size_t>(p.y.n) * p.y.h * p.y.w * p.y.c;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % p.y.c);
+  const size_t opix = idx / p.y.c;
+  const int ox = static_cast<int>(opix % p.y.w);
+  const int oy = static_cast<int>((opix / p.y.w) % p.y.h);
+  const int n = static_cast<int>(opix / (static_cast<size_t>(p.y.w) * p.y.h));
+  float m = -INFINITY;
+  for (int r = 0; r < p.ksize; ++r) {
+    const int yy = 2 * oy - p.pad_y + r;
+    if (yy < 0 || yy >= p.x.h) continue;
+    for (int s = 0; s < p.ksize; ++s) {
+      const int xx = 2 * ox - p.pad_x + s;
+      if (xx < 0 || xx >= p.x.w) continue;
+      m = fmaxf(m, p.x.load(p.x.pix(n, yy, xx), c));
+    }
+  }
+  p.y.store(opix, c, m);
+}
+
+// fp16, 8 channels (16 bytes) per thread
+__global__ void __launch_bounds__(256) maxpool_h8_kernel(const PoolParams p) {
+  const int cv = p.y.c / 8;
+  const size_t total = static_cast<size_t>(p.y.n) * p.y.h * p.y.w * cv;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % cv) * 8;
+  const size_t opix = idx / cv;
+  const int ox = static_cast<int>(opix % p.y.w);
+  const int oy = static_cast<int>((opix / p.y.w) % p.y.h);
+  const int n = static_cast<int>(opix / (static_cast<size_t>(p.y.w) * p.y.h));
+  const __half* xin = reinterpret_cast<const __half*>(p.x.ptr);
+  __half2 m[4];
+  const __half2 ninf = __float2half2_rn(-INFINITY);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) m[i] = ninf;
+  for (int r = 0; r < p.ksize; ++r) {
+    const int yy = 2 * oy - p.pad_y + r;
+    if (yy < 0 || yy >= p.x.h) continue;
+    for (int s = 0; s < p.ksize; ++s) {
+      const int xx = 2 * ox - p.pad_x + s;
+      if (xx < 0 || xx >= p.x.w) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(xin + p.x.pix(n, yy, xx) * p.x.cstride + p.x.coff + c));
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m[i] = __hmax2(m[i], h[i]);
+    }
+  }
+  uint4 o;
+  __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) oh[i] = m[i];
+  *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.y.ptr) + opix * p.y.cstride + p.y.coff + c) = o;
+}
+
+// average pooling factor x factor, stride factor, TF 'SAME' (padded cells excluded from the divisor)
+struct AvgPoolParams {
+  View x, y;
+  int f, pad_y, pad_x;
+};
+__global__ void __launch_bounds__(256) avgpool_kernel(const AvgPoolParams p) {
+  const size_t total = static_cast<size_t>(p.y.n) * p.y.h * p.y.w;
+  const size_t opix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (opix >= total) return;
+  const int ox = static_cast<int>(opix % p.y.w);
+  const int oy = static_cast<int>((opix / p.y.w) % p.y.h);
+  const int n = static_cast<int>(opix / (static_cast<size_t>(p.y.w) * p.y.h));
+  for (int c = 0; c < p.y.c; ++c) {
+    float acc = 0.f;
+    int cnt = 0;
+    for (int r = 0; r < p.f; ++r) {
+      const int yy = oy * p.f - p.pad_y + r;
+      if (yy < 0 || yy >= p.x.h) continue;
+      for (int s = 0; s < p.f; ++s) {
+        const int xx = ox * p.f - p.pad_x + s;
+        if (xx < 0 || xx >= p.x.w) continue;
+        acc += p.x.load(p.x.pix(n, yy, xx), c);
+        ++cnt;
+      }
+    }
+    p.y.store(opix, c, acc / static_cast<float>(cnt));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct StdParams {
+  View src, sout, vout;
+  dd_standardize_params q;
+  int has_s, has_v;
+  float inv_sqrt_var;
+};
+
+__device__ __forceinline__ float standardize_value(float v, const dd_standardize_params& q, float inv_sqrt_var) {
+  if (q.use_log1p) v = signed_log1p(v);
+  if (q.mean != 0.f) v -= q.mean;
+  if (q.variance != 1.f) v *= inv_sqrt_var;
+  return v;
+}
+
+__global__ void __launch_bounds__(256) standardize_variance_kernel(const StdParams p) {
+  const size_t total = static_cast<size_t>(p.src.n) * p.src.h * p.src.w;
+  const size_t pixel = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pixel >= total) return;
+  const int x0 = static_cast<int>(pixel % p.src.w);
+  const int y0 = static_cast<int>((pixel / p.src.w) % p.src.h);
+  const int n = static_cast<int>(pixel / (static_cast<size_t>(p.src.w) * p.src.h));
+  const int C = p.src.c;
+  float var_sum = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float centre = standardize_value(p.src.load(pixel, c), p.q, p.inv_sqrt_var);
+    if (p.has_s) {
+      if (C == 1) { p.sout.store(pixel, 0, centre); p.sout.store(pixel, 1, centre); p.sout.store(pixel, 2, centre); }
+      else p.sout.store(pixel, c, centre);
+    }
+    if (p.has_v) {
+      float m = 0.f, m2 = 0.f;
+      for (int r = -1; r <= 1; ++r) {
+        const int yy = sym_index(y0 + r, p.src.h);
+        for (int s = -1; s <= 1; ++s) {
+          if (p.q.variance_mode == 1 && r != 0 && s != 0) continue;  // 'neighbor': plus-shaped stencil
+          const int xx = sym_index(x0 + s, p.src.w);
+          float v = p.src.load(p.src.pix(n, yy, xx), c);
+          if (!p.q.compute_before_standardization) v = standardize_value(v, p.q, p.inv_sqrt_var);
+          m += v;
+          m2 += v * v;
+        }
+      }
+      const float inv_cnt = (p.q.variance_mode == 1) ? (1.f / 5.f) : (1.f / 9.f);
+      m *= inv_cnt; m2 *= inv_cnt;
+      const float msq = m * m;
+      float var = m2 - msq;
+      if (p.q.relative_variance) var = var / fmaxf(msq, p.q.epsilon);
+      if (p.q.compress_to_one_channel) var_sum += var;
+      else p.vout.store(pixel, c, var);
+    }
+  }
+  if (p.has_v && p.q.compress_to_one_channel) p.vout.store(pixel, 0, var_sum / static_cast<float>(C));
+}
+
+// ------------------------------------------------------------------------------------------------
+struct AssembleParams {
+  const dd_gather_entry* table;
+  View out;
+  int tuples, n;
+};
+__global__ void __launch_bounds__(256) assemble_kernel(const AssembleParams p) {
+  const size_t img_pix = static_cast<size_t>(p.out.h) * p.out.w;
+  const size_t total = static_cast<size_t>(p.tuples) * p.n * img_pix;
+  const size_t opix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (opix >= total) return;
+  const size_t b = opix / img_pix;         // output image = t * n + i
+  const int t = static_cast<int>(b / p.n);
+  const size_t spix = (b % p.n) * img_pix + (opix % img_pix);  // pixel index inside the [n,h,w] source
+  const dd_gather_entry* row = p.table + static_cast<size_t>(t) * p.out.c;
+  if (p.out.f16 && (p.out.c % 8 == 0) && (p.out.coff % 8 == 0) && (p.out.cstride % 8 == 0)) {
+    __half* o = reinterpret_cast<__half*>(p.out.ptr) + opix * p.out.cstride + p.out.coff;
+    for (int c0 = 0; c0 < p.out.c; c0 += 8) {
+      uint4 pk;
+      __half* ph = reinterpret_cast<__half*>(&pk);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const dd_gather_entry e = row[c0 + i];
+        const float v = e.ptr ? __ldg(e.ptr + spix * e.cstride + e.cidx) : e.constant;
+        ph[i] = __float2half_rn(v);
+      }
+      *reinterpret_cast<uint4*>(o + c0) = pk;
+    }
+  } else {
+    for (int c = 0; c < p.out.c; ++c) {
+      const dd_gather_entry e = row[c];
+      p.out.store(opix, c, e.ptr ? __ldg(e.ptr + spix * e.cstride + e.cidx) : e.constant);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel-prediction apply.  LANES threads cooperate on one pixel (LANES = 32 for large K so that the
+// K*K logits of a pixel are read as one coalesced run; 4 for small K).  The symmetric-padded source
+// tile lives in shared memory as float4 (rgb + pad) so a tap is one LDS.128.
+constexpr int kKpTileH = 8, kKpTileW = 32, kKpThreads = 256;
+struct KpParams {
+  View src, logits, out;
+  int K, F;          // kernel size, features per logits tensor
+  int tiles_x, tiles_y;
+};
+
+template <int LANES>
+__global__ void __launch_bounds__(kKpThreads) kernel_predict_kernel(const KpParams p) {
+  extern __shared__ float4 s_src[];
+  const int K = p.K, K2 = K * K, pad = (K - 1) / 2;
+  const int TW = kKpTileW + 2 * pad, TH = kKpTileH + 2 * pad;
+  const int img = blockIdx.z;                       // f * B + b
+  const int B = p.logits.n;
+  const int f = img / B, b = img % B;
+  const int ty0 = blockIdx.y * kKpTileH, tx0 = blockIdx.x * kKpTileW;
+  const int h = p.src.h, w = p.src.w;
+  for (int i = threadIdx.x; i < TW * TH; i += kKpThreads) {
+    const int ly = i / TW, lx = i % TW;
+    const int yy = sym_index(ty0 + ly - pad, h), xx = sym_index(tx0 + lx - pad, w);
+    const size_t sp = p.src.pix(img, yy, xx);
+    s_src[i] = make_float4(p.src.load(sp, 0), p.src.load(sp, 1), p.src.load(sp, 2), 0.f);
+  }
+  __syncthreads();
+  constexpr int PIX_PER_PASS = kKpThreads / LANES;
+  const int sub = threadIdx.x % LANES;
+  const int grp = threadIdx.x / LANES;
+  const int coff = f * K2;
+  for (int pp = grp; pp < kKpTileH * kKpTileW; pp += PIX_PER_PASS) {
+    const int ly = pp / kKpTileW, lx = pp % kKpTileW;
+    const int y = ty0 + ly, x = tx0 + lx;
+    const bool valid = (y < h) && (x < w);   // uniform across the LANES of a pixel
+    const size_t lpix = valid ? p.logits.pix(b, y, x) : 0;
+    // pass 1: max
+    float mx = -INFINITY;
+    if (valid) for (int t = sub; t < K2; t += LANES) mx = fmaxf(mx, p.logits.load(lpix, coff + t));
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // pass 2: exp, sum, weighted source
+    float sum = 0.f, r = 0.f, g = 0.f, bl = 0.f;
+    if (valid) {
+      for (int t = sub; t < K2; t += LANES) {
+        const float e = __expf(p.logits.load(lpix, coff + t) - mx);
+        const int i = t / K, j = t - i * K;
+        const float4 sv = s_src[(ly + i) * TW + lx + j];
+        sum += e;
+        r = fmaf(e, sv.x, r); g = fmaf(e, sv.y, g); bl = fmaf(e, sv.z, bl);
+      }
+    }
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      r += __shfl_xor_sync(0xffffffffu, r, o);
+      g += __shfl_xor_sync(0xffffffffu, g, o);
+      bl += __shfl_xor_sync(0xffffffffu, bl, o);
+    }
+    if (valid && sub == 0) {
+      const float inv = 1.f / sum;
+      const size_t op = p.out.pix(img, y, x);
+      p.out.store(op, 0, r * inv); p.out.store(op, 1, g * inv); p.out.store(op, 2, bl * inv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int kComposeMaxC = 32;
+struct ComposeHeadParams {
+  View small, large, y;
+  float w[6 * kComposeMaxC];
+  float b[kComposeMaxC];
+  int c_mid;
+};
+__global__ void __launch_bounds__(256) compose_head_kernel(const ComposeHeadParams p) {
+  const size_t total = static_cast<size_t>(p.large.n) * p.large.h * p.large.w;
+  const size_t pixel = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pixel >= total) return;
+  const int x0 = static_cast<int>(pixel % p.large.w);
+  const int y0 = static_cast<int>((pixel / p.large.w) % p.large.h);
+  const int n = static_cast<int>(pixel / (static_cast<size_t>(p.large.w) * p.large.h));
+  const size_t spix = p.small.pix(n, y0 >> 1, x0 >> 1);
+  float in[6];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { in[c] = p.small.load(spix, c); in[3 + c] = p.large.load(pixel, c); }
+  for (int c = 0; c < p.y.c; ++c) {
+    float v = 0.f;
+    if (c < p.c_mid) {
+      v = p.b[c];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v = fmaf(in[k], p.w[k * p.c_mid + c], v);
+      v = fmaxf(v, 0.f);
+    }
+    p.y.store(pixel, c, v);
+  }
+}
+
+struct ComposeTailParams {
+  View t, small, large, out;
+  float w[kComposeMaxC];
+  float b;
+  int c_mid;
+  int has_inv;
+  dd_invert_params inv;
+  float sqrt_var;
+};
+__device__ __forceinline__ float invert_value(float v, const dd_invert_params& q, float sqrt_var) {
+  if (q.variance != 1.f) v *= sqrt_var;
+  if (q.mean != 0.f) v += q.mean;
+  if (q.use_log1p) v = signed_expm1(v);
+  return v;
+}
+__global__ void __launch_bounds__(256) compose_tail_kernel(const ComposeTailParams p) {
+  const size_t total = static_cast<size_t>(p.large.n) * p.large.h * p.large.w;
+  const size_t pixel = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pixel >= total) return;
+  const int x0 = static_cast<int>(pixel % p.large.w);
+  const int y0 = static_cast<int>((pixel / p.large.w) % p.large.h);
+  const int n = static_cast<int>(pixel / (static_cast<size_t>(p.large.w) * p.large.h));
+  float a = p.b;
+  for (int c = 0; c < p.c_mid; ++c) a = fmaf(p.t.load(pixel, c), p.w[c], a);
+  a = fmaxf(a, 0.f);
+  const float wgt = 1.f / (1.f + __expf(-a));
+  const size_t spix = p.small.pix(n, y0 >> 1, x0 >> 1);
+  const int yb = y0 & ~1, xb = x0 & ~1;
+  for (int c = 0; c < 3; ++c) {
+    const float low = 0.25f * (p.large.load(p.large.pix(n, yb, xb), c) + p.large.load(p.large.pix(n, yb, xb + 1), c) +
+                               p.large.load(p.large.pix(n, yb + 1, xb), c) + p.large.load(p.large.pix(n, yb + 1, xb + 1), c));
+    float v = p.large.load(pixel, c) - wgt * low + wgt * p.small.load(spix, c);
+    if (p.has_inv) v = invert_value(v, p.inv, p.sqrt_var);
+    p.out.store(pixel, c, v);
+  }
+}
+
+struct InvertParams {
+  View x, y;
+  dd_invert_params inv;
+  float sqrt_var;
+};
+__global__ void __launch_bounds__(256) invert_kernel(const InvertParams p) {
+  const size_t total = static_cast<size_t>(p.x.n) * p.x.h * p.x.w;
+  const size_t pixel = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pixel >= total) return;
+  for (int c = 0; c < p.x.c; ++c) p.y.store(pixel, c, invert_value(p.x.load(pixel, c), p.inv, p.sqrt_var));
+}
+
+struct CastParams { View x, y; };
+__global__ void __launch_bounds__(256) cast_copy_kernel(const CastParams p) {
+  const size_t total = static_cast<size_t>(p.x.n) * p.x.h * p.x.w * p.x.c;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % p.x.c);
+  const size_t pixel = idx / p.x.c;
+  p.y.store(pixel, c, p.x.load(pixel, c));
+}
+
+__global__ void __launch_bounds__(256) l2_flush_kernel(uint4* buf, size_t n16, uint32_t tag) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride)
+    buf[i] = make_uint4(tag, tag + 1, tag + 2, static_cast<uint32_t>(i));
+}
+
+inline unsigned blocks_for(size_t total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
+inline bool same_spatial(const dd_tensor* a, const dd_tensor* b) { return a->n == b->n && a->h == b->h && a->w == b->w; }
+
+}  // namespace dd
+
+using namespace dd;
+
+extern "C" {
+
+int dd_maxpool_s2_fwd(dd_ctx* ctx, const dd_tensor* x, int ksize, const dd_tensor* y, void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(x) && tensor_ok(y), "bad argument");
+  DD_CHECK_ARG(ksize == 2 || ksize == 3, "maxpool ksize must be 2 or 3");
+  const int oh = (x->h + 1) / 2, ow = (x->w + 1) / 2;
+  DD_CHECK_ARG(y->n == x->n && y->h == oh && y->w == ow && y->c == x->c, "maxpool: bad output dims");
+  PoolParams p;
+  p.x = make_view(x); p.y = make_view(y); p.ksize = ksize;
+  const int pty = (oh - 1) * 2 + ksize - x->h, ptx = (ow - 1) * 2 + ksize - x->w;
+  p.pad_y = (pty > 0 ? pty : 0) / 2; p.pad_x = (ptx > 0 ? ptx : 0) / 2;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool vec = x->dtype == DD_F16 && y->dtype == DD_F16 && x->c % 8 == 0 && x->coff % 8 == 0 &&
+                   x->cstride % 8 == 0 && y->coff % 8 == 0 && y->cstride % 8 == 0;
+  if (vec) {
+    const size_t total = static_cast<size_t>(y->n) * y->h * y->w * (y->c / 8);
+    maxpool_h8_kernel<<<blocks_for(total, 256), 256, 0, s>>>(p);
+  } else {
+    const size_t total = static_cast<size_t>(y->n) * y->h * y->w * y->c;
+    maxpool_generic_kernel<<<blocks_for(total, 256), 256, 0, s>>>(p);
+  }
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_avgpool_fwd(dd_ctx* ctx, const dd_tensor* x, int factor, const dd_tensor* y, void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(x) && tensor_ok(y), "bad argument");
+  DD_CHECK_ARG(factor >= 1 && factor <= 16, "avgpool factor out of range");
+  const int oh = (x->h + factor - 1) / factor, ow = (x->w + factor - 1) / factor;
+  DD_CHECK_ARG(y->n == x->n && y->h == oh && y->w == ow && y->c == x->c, "avgpool: bad output dims");
+  AvgPoolParams p;
+  p.x = make_view(x); p.y = make_view(y); p.f = factor;
+  p.pad_y = (oh * factor - x->h) / 2; p.pad_x = (ow * factor - x->w) / 2;
+  const size_t total = static_cast<size_t>(y->n) * y->h * y->w;
+  avgpool_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_standardize_variance(dd_ctx* ctx, const dd_tensor* src, const dd_standardize_params* prm,
+                            const dd_tensor* std_out, const dd_tensor* var_out, void* stream) {
+  DD_CHECK_ARG(ctx && prm && tensor_ok(src), "bad argument");
+  DD_CHECK_ARG(src->c == 1 || src->c == 3, "source must have 1 or 3 channels");
+  DD_CHECK_ARG(std_out || var_out, "nothing to compute");
+  StdParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = make_view(src); p.q = *prm;
+  p.inv_sqrt_var = 1.f / sqrtf(prm->variance);
+  if (std_out) {
+    DD_CHECK_ARG(tensor_ok(std_out) && same_spatial(src, std_out) && std_out->c == 3, "std_out must be [n,h,w,3]");
+    p.sout = make_view(std_out); p.has_s = 1;
+  }
+  if (var_out && prm->use_variance) {
+    const int vc = prm->compress_to_one_channel ? 1 : src->c;
+    DD_CHECK_ARG(tensor_ok(var_out) && same_spatial(src, var_out) && var_out->c == vc, "var_out has wrong dims");
+    p.vout = make_view(var_out); p.has_v = 1;
+  }
+  const size_t total = static_cast<size_t>(src->n) * src->h * src->w;
+  standardize_variance_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_assemble_input(dd_ctx* ctx, const dd_gather_entry* table_dev, int tuples, int n, const dd_tensor* out,
+                      void* stream) {
+  DD_CHECK_ARG(ctx && table_dev && tensor_ok(out), "bad argument");
+  DD_CHECK_ARG(tuples > 0 && n > 0 && out->n == tuples * n, "assemble: out.n must be tuples*n");
+  AssembleParams p;
+  p.table = table_dev; p.out = make_view(out); p.tuples = tuples; p.n = n;
+  const size_t total = static_cast<size_t>(out->n) * out->h * out->w;
+  assemble_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_kernel_predict_fwd(dd_ctx* ctx, const dd_tensor* src, const dd_tensor* logits, int ksize, int features,
+                          const dd_tensor* out, void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(src) && tensor_ok(logits) && tensor_ok(out), "bad argument");
+  DD_CHECK_ARG(ksize >= 1 && (ksize & 1) && ksize <= 31, "kernel size must be odd and <= 31");
+  DD_CHECK_ARG(features >= 1 && logits->c == features * ksize * ksize, "logits must have features*K*K channels");
+  DD_CHECK_ARG(src->c == 3 && out->c == 3 && src->dtype == DD_F32 && out->dtype == DD_F32, "src/out must be fp32 rgb");
+  DD_CHECK_ARG(src->n == logits->n * features && out->n == src->n, "src/out batch must be logits.n * features");
+  DD_CHECK_ARG(src->h == logits->h && src->w == logits->w && same_spatial(src, out), "spatial dims differ");
+  KpParams p;
+  p.src = make_view(src); p.logits = make_view(logits); p.out = make_view(out);
+  p.K = ksize; p.F = features;
+  p.tiles_x = (src->w + kKpTileW - 1) / kKpTileW; p.tiles_y = (src->h + kKpTileH - 1) / kKpTileH;
+  const int pad = (ksize - 1) / 2;
+  const size_t smem = static_cast<size_t>(kKpTileW + 2 * pad) * (kKpTileH + 2 * pad) * sizeof(float4);
+  dim3 grid(p.tiles_x, p.tiles_y, src->n);
+  DD_CHECK_ARG(src->n <= 65535 && p.tiles_y <= 65535, "kernel_predict grid too large");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ksize * ksize >= 64) kernel_predict_kernel<32><<<grid, kKpThreads, smem, s>>>(p);
+  else kernel_predict_kernel<4><<<grid, kKpThreads, smem, s>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_compose_head_fwd(dd_ctx* ctx, const dd_tensor* small, const dd_tensor* large, const float* w, const float* b,
+                        int c_mid, const dd_tensor* y, void* stream) {
+  DD_CHECK_ARG(ctx && w && b && tensor_ok(small) && tensor_ok(large) && tensor_ok(y), "bad argument");
+  DD_CHECK_ARG(c_mid > 0 && c_mid <= kComposeMaxC && y->c >= c_mid, "compose width unsupported");
+  DD_CHECK_ARG(small->c == 3 && large->c == 3 && large->h == 2 * small->h && large->w == 2 * small->w &&
+                   small->n == large->n && same_spatial(large, y), "compose_head: dims");
+  ComposeHeadParams p;
+  memset(&p, 0, sizeof(p));
+  p.small = make_view(small); p.large = make_view(large); p.y = make_view(y); p.c_mid = c_mid;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // weights are tiny: stage them through the kernel parameter block (host pointers expected)
+  memcpy(p.w, w, sizeof(float) * 6 * c_mid);
+  memcpy(p.b, b, sizeof(float) * c_mid);
+  const size_t total = static_cast<size_t>(large->n) * large->h * large->w;
+  compose_head_kernel<<<blocks_for(total, 256), 256, 0, s>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_compose_tail_fwd(dd_ctx* ctx, const dd_tensor* t, const float* w, const float* b, int c_mid,
+                        const dd_tensor* small, const dd_tensor* large, const dd_invert_params* inv,
+                        const dd_tensor* out, void* stream) {
+  DD_CHECK_ARG(ctx && w && b && tensor_ok(t) && tensor_ok(small) && tensor_ok(large) && tensor_ok(out), "bad argument");
+  DD_CHECK_ARG(c_mid > 0 && c_mid <= kComposeMaxC && t->c >= c_mid, "compose width unsupported");
+  DD_CHECK_ARG(small->c == 3 && large->c == 3 && out->c == 3 && large->h == 2 * small->h && large->w == 2 * small->w &&
+                   small->n == large->n && same_spatial(large, t) && same_spatial(large, out), "compose_tail: dims");
+  ComposeTailParams p;
+  memset(&p, 0, sizeof(p));
+  p.t = make_view(t); p.small = make_view(small); p.large = make_view(large); p.out = make_view(out);
+  p.c_mid = c_mid;
+  memcpy(p.w, w, sizeof(float) * c_mid);
+  p.b = b[0];
+  if (inv) { p.has_inv = 1; p.inv = *inv; p.sqrt_var = sqrtf(inv->variance); }
+  const size_t total = static_cast<size_t>(large->n) * large->h * large->w;
+  compose_tail_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_invert_standardization(dd_ctx* ctx, const dd_tensor* x, const dd_invert_params* inv, const dd_tensor* y,
+                              void* stream) {
+  DD_CHECK_ARG(ctx && inv && tensor_ok(x) && tensor_ok(y) && same_spatial(x, y) && x->c == y->c, "bad argument");
+  InvertParams p;
+  p.x = make_view(x); p.y = make_view(y); p.inv = *inv; p.sqrt_var = sqrtf(inv->variance);
+  const size_t total = static_cast<size_t>(x->n) * x->h * x->w;
+  invert_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_cast_copy(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(x) && tensor_ok(y) && same_spatial(x, y) && x->c == y->c, "bad argument");
+  CastParams p;
+  p.x = make_view(x); p.y = make_view(y);
+  const size_t total = static_cast<size_t>(x->n) * x->h * x->w * x->c;
+  cast_copy_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_l2_flush(dd_ctx* ctx, void* scratch, size_t bytes, void* stream) {
+  DD_CHECK_ARG(ctx && scratch && bytes >= 16, "bad argument");
+  static uint32_t tag = 0;
+  l2_flush_kernel<<<ctx->sm_count * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<uint4*>(scratch),
+                                                                                    bytes / 16, ++tag);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+}  // extern "C"

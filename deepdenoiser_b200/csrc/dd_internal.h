@@ -1,0 +1,90 @@
+// Internal helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/dd_b200.h"
+
+struct dd_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t max_smem_optin = 0;
+  void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime
+  int conv_shift_mode = 0;       // see conv_tc.cuh (validated on hardware; 2 is the all-aligned fallback)
+  int conv_rows = 0;             // 0 = auto
+  int conv_b_stages = 0;         // 0 = auto
+  std::atomic<int64_t> launches{0};
+};
+
+namespace dd {
+
+void set_error(const char* fmt, ...);
+
+#define DD_CHECK_ARG(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      ::dd::set_error(__VA_ARGS__);             \
+      return DD_ERR_INVALID;                    \
+    }                                           \
+  } while (0)
+
+#define DD_CUDA(call)                                                                        \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      ::dd::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return DD_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+#define DD_LAUNCH_CHECK(ctx)                                                                  \
+  do {                                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ != cudaSuccess) {                                                                 \
+      ::dd::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return DD_ERR_CUDA;                                                                     \
+    }                                                                                         \
+    (ctx)->launches.fetch_add(1, std::memory_order_relaxed);                                  \
+  } while (0)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline size_t elem_size(int dtype) { return dtype == DD_F16 ? 2 : 4; }
+
+inline bool tensor_ok(const dd_tensor* t) {
+  return t && t->ptr && t->n > 0 && t->h > 0 && t->w > 0 && t->c > 0 && t->coff >= 0 &&
+         t->coff + t->c <= t->cstride && (t->dtype == DD_F32 || t->dtype == DD_F16);
+}
+
+// Device-side view with typed element access (fp16 or fp32 storage, fp32 math).
+struct View {
+  void* ptr;
+  int f16;
+  int n, h, w, c, cstride, coff;
+  __host__ __device__ size_t pix(int in, int y, int x) const {
+    return (static_cast<size_t>(in) * h + y) * w + x;
+  }
+  __device__ float load(size_t pixel, int ch) const {
+    const size_t i = pixel * cstride + coff + ch;
+    return f16 ? __half2float(reinterpret_cast<const __half*>(ptr)[i]) : reinterpret_cast<const float*>(ptr)[i];
+  }
+  __device__ void store(size_t pixel, int ch, float v) const {
+    const size_t i = pixel * cstride + coff + ch;
+    if (f16) reinterpret_cast<__half*>(ptr)[i] = __float2half_rn(v);
+    else reinterpret_cast<float*>(ptr)[i] = v;
+  }
+};
+
+inline View make_view(const dd_tensor* t) {
+  View v;
+  v.ptr = t->ptr; v.f16 = (t->dtype == DD_F16);
+  v.n = t->n; v.h = t->h; v.w = t->w; v.c = t->c; v.cstride = t->cstride; v.coff = t->coff;
+  return v;
+}
+
+}  // namespace dd

@@ -1,0 +1,174 @@
+/* dd_b200.h — C ABI of libdd_b200.so, the B200 (sm_100a) replacement for the TensorFlow ops on the
+ * DeepDenoiser hot path.  The reference has no FFI: its only seam is the Python method
+ * Architecture.predict(features, mode) (TensorFlow/Architecture.py:537-617), which builds the graph out
+ * of tf.layers.* / tf.nn.* calls.  Every entry point below replaces one family of those calls; the
+ * reference call sites are cited on each declaration.  A maintainer binds them with ctypes
+ * (INTEGRATION.md); deepdenoiser_b200/_lib.py is that binding.
+ *
+ * Conventions
+ *   - all tensors are NHWC, described by dd_tensor: a device pointer to the START OF THE UNDERLYING
+ *     BUFFER, logical dims n,h,w,c, the buffer's channel stride `cstride` (elements per pixel) and the
+ *     view's first channel `coff`.  concat == writing at a channel offset of a wider buffer.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing,
+ *     never synchronises, and returns 0 on success or a negative dd_status; dd_last_error() returns a
+ *     thread-local message.
+ *   - dtype: activations are DD_F16 (tensor-core path, fp32 accumulate) or DD_F32 (exact path);
+ *     images (sources, predictions, weights of the per-pixel filter) are DD_F32.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef DD_B200_H_
+#define DD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DD_B200_ABI_VERSION 1
+
+typedef enum dd_status {
+  DD_OK = 0,
+  DD_ERR_INVALID = -1,     /* bad argument (shape / alignment / dtype) */
+  DD_ERR_CUDA = -2,        /* CUDA runtime / driver error */
+  DD_ERR_UNSUPPORTED = -3, /* combination not implemented */
+  DD_ERR_NO_DEVICE = -4
+} dd_status;
+
+typedef enum dd_dtype { DD_F32 = 0, DD_F16 = 1 } dd_dtype;
+
+typedef struct dd_tensor {
+  void* ptr;
+  int32_t dtype; /* dd_dtype */
+  int32_t n, h, w, c;
+  int32_t cstride;
+  int32_t coff;
+} dd_tensor;
+
+typedef struct dd_ctx dd_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int dd_abi_version(void);
+const char* dd_last_error(void);
+int dd_ctx_create(int device, dd_ctx** out);
+int dd_ctx_destroy(dd_ctx* ctx);
+int dd_ctx_sm_count(const dd_ctx* ctx);
+/* Tuning / experiment knobs ("conv_shift_mode", "conv_rows", ...). Returns DD_ERR_INVALID if unknown. */
+int dd_ctx_set_option(dd_ctx* ctx, const char* name, int value);
+/* Number of kernels this library has launched through `ctx` (bench.py's gpu_launches). */
+int64_t dd_ctx_launch_count(const dd_ctx* ctx);
+
+/* ---- convolution weights -------------------------------------------------------------------- */
+/* Packs TF-layout weights for dd_conv2d_fwd.
+ *   w_hwio   host fp32, tf.layers.conv2d kernel layout [kh,kw,Cin,Cout], or for
+ *            transposed convs tf.layers.conv2d_transpose layout [kh,kw,Cout,Cin] (A.5) with
+ *            transposed != 0
+ *   dtype    DD_F16: [tap][round16(Cout*groups)][round64(Cin)] fp16 (tcgen05 B operand)
+ *            DD_F32: [tap][Cout][Cin] fp32 (exact SIMT path)
+ * dd_conv2d_packed_bytes() gives the size of `packed` (device memory, written on `stream` from a
+ * staging copy the function makes). */
+size_t dd_conv2d_packed_bytes(int ksize, int cin, int cout, int dtype, int transposed);
+int dd_conv2d_pack_weights(dd_ctx* ctx, const float* w_host, int ksize, int cin, int cout, int dtype,
+                           int transposed, void* packed_dev, void* stream);
+
+/* flags for dd_conv2d_fwd */
+#define DD_CONV_RELU 1u        /* activation=tf.nn.relu on the output */
+#define DD_CONV_RELU_COPY 2u   /* additionally write relu(output) to y_relu (dense-block inputs) */
+
+/* y = conv2d(x, W) + b, stride 1, padding 'same', ksize 3 or 1; optional residual add and ReLU.
+ * Replaces tf.layers.conv2d at UNet.py:29-31, Tiramisu.py:35-37,50-52,77-79, Architecture.py:238-243,
+ * MultiScalePrediction.py:88-90.  x.dtype selects the path (F16: tcgen05, F32: SIMT); y may be F16 or
+ * F32 on the F16 path.  bias: device fp32, round_up(cout,16) entries (zero padded), or NULL.
+ * residual / y_relu may be NULL.  On the F16 path channels [cout, round_up(cout,8)) of y are written
+ * as zeros, so y needs that much room after coff. */
+int dd_conv2d_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const float* bias, int ksize,
+                  uint32_t flags, const dd_tensor* residual, const dd_tensor* y, const dd_tensor* y_relu,
+                  void* stream);
+
+/* y = relu?(conv2d_transpose(x, W, k=2, stride=2, 'same') + b): y[2i+a,2j+b,o] = sum_c x[i,j,c] W[a,b,o,c].
+ * Replaces tf.layers.conv2d_transpose at UNet.py:56-58. */
+int dd_conv2d_transpose2x2_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const float* bias,
+                               uint32_t flags, const dd_tensor* y, void* stream);
+
+/* ---- pooling / resampling ------------------------------------------------------------------- */
+/* tf.layers.max_pooling2d(pool=ksize, strides=2, 'same'): ksize 3 (UNet.py:42-44, pad bottom/right only)
+ * or 2 (Tiramisu.py:55-57).  y dims = ceil(x dims / 2). */
+int dd_maxpool_s2_fwd(dd_ctx* ctx, const dd_tensor* x, int ksize, const dd_tensor* y, void* stream);
+/* tf.layers.average_pooling2d(factor, factor, 'same') (MultiScalePrediction.py:11-13); fp32 images. */
+int dd_avgpool_fwd(dd_ctx* ctx, const dd_tensor* x, int factor, const dd_tensor* y, void* stream);
+
+/* ---- source encoder ------------------------------------------------------------------------- */
+/* FeatureStandardization.standardize + FeatureEngineering.variance for one render pass
+ * (Architecture.py:39-46,114-132; FeatureEngineering.py:11-70; Utilities.py:3-4).
+ *   src       fp32 [n,h,w,c] c in {1,3};      std_out fp32 [n,h,w,3] (1 channel replicated to 3,
+ *             SourceEncoder.py:49-51) or NULL; var_out fp32 [n,h,w,1|3] or NULL
+ *   variance_mode 0 'uniform' 1 'neighbor'; variance computed on the raw (before != 0) or standardised
+ *   values; relative => / max(mean^2, epsilon); compress => mean over channels. */
+typedef struct dd_standardize_params {
+  int32_t use_log1p;
+  float mean;
+  float variance; /* divide by sqrt(variance) iff != 1 */
+  int32_t use_variance;
+  int32_t variance_mode;
+  int32_t relative_variance;
+  int32_t compute_before_standardization;
+  int32_t compress_to_one_channel;
+  float epsilon;
+} dd_standardize_params;
+int dd_standardize_variance(dd_ctx* ctx, const dd_tensor* src, const dd_standardize_params* prm,
+                            const dd_tensor* std_out, const dd_tensor* var_out, void* stream);
+
+/* SourceEncoder.prepare_neural_network_input (SourceEncoder.py:29-79) for ALL tuples at once:
+ * out[t*n + i, y, x, ch] = table[t][ch].ptr ? ptr[((i*h + y)*w + x)*cstride + cidx] : table[t][ch].constant
+ * table: device array of tuples*out.c entries. */
+typedef struct dd_gather_entry {
+  const float* ptr;
+  int32_t cstride;
+  int32_t cidx;
+  float constant;
+  int32_t pad_;
+} dd_gather_entry;
+int dd_assemble_input(dd_ctx* ctx, const dd_gather_entry* table_dev, int tuples, int n, const dd_tensor* out,
+                      void* stream);
+
+/* ---- kernel prediction ---------------------------------------------------------------------- */
+/* KernelPrediction.kernel_prediction (KernelPrediction.py:11-63) with use_softmax=True, mode='symmetric':
+ *   out[b,y,x,c] = sum_{i,j} sym(src)[b,y+i-p,x+j-p,c] * softmax_k(logits[b',y,x,f*K*K + k])[i*K+j]
+ * src/out fp32 [features*B,h,w,3] with B = logits.n; image f*B + b uses logits channels
+ * [f*K*K, (f+1)*K*K) of logits image b (the tf.split of Architecture.py:581-587). logits F16 or F32. */
+int dd_kernel_predict_fwd(dd_ctx* ctx, const dd_tensor* src, const dd_tensor* logits, int ksize, int features,
+                          const dd_tensor* out, void* stream);
+
+/* ---- multi-scale composition ---------------------------------------------------------------- */
+/* First layer of the compose weight net: relu(conv1x1_{6->C}(concat[up2(small), large]))
+ * (MultiScalePrediction.py:16-33,57-66).  small fp32 [B,h/2,w/2,3], large fp32 [B,h,w,3],
+ * w HOST fp32 [6][C] (TF [1,1,6,C]), b HOST fp32 [C] (copied into the launch parameters);
+ * y F16/F32 [B,h,w,C..] (channels >= C zero-filled to y.c). */
+int dd_compose_head_fwd(dd_ctx* ctx, const dd_tensor* small, const dd_tensor* large, const float* w,
+                        const float* b, int c_mid, const dd_tensor* y, void* stream);
+/* Tail: wgt = sigmoid(relu(conv1x1_{C->1}(t) + b)); out = large - wgt*up2(down2(large)) + wgt*up2(small)
+ * (MultiScalePrediction.py:36-54,73-77), optionally followed by the inverse standardisation
+ * (Architecture.py:48-55) when inv != NULL.  w HOST fp32 [C], b HOST fp32 [1]. */
+typedef struct dd_invert_params {
+  int32_t use_log1p;
+  float mean;
+  float variance;
+} dd_invert_params;
+int dd_compose_tail_fwd(dd_ctx* ctx, const dd_tensor* t, const float* w, const float* b, int c_mid,
+                        const dd_tensor* small, const dd_tensor* large, const dd_invert_params* inv,
+                        const dd_tensor* out, void* stream);
+/* FeatureStandardization.invert_standardization on an fp32 image (Architecture.py:48-55). */
+int dd_invert_standardization(dd_ctx* ctx, const dd_tensor* x, const dd_invert_params* inv, const dd_tensor* y,
+                              void* stream);
+
+/* ---- utilities ------------------------------------------------------------------------------ */
+/* dtype / channel-view conversion copy y = cast(x) (c channels). */
+int dd_cast_copy(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, void* stream);
+/* Writes `bytes` of a scratch buffer (L2 flush between timed iterations in bench.py). */
+int dd_l2_flush(dd_ctx* ctx, void* scratch, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DD_B200_H_ */
