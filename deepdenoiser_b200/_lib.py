@@ -57,11 +57,12 @@ SIGNATURES = {
     "dd_conv2d_pack_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "dd_conv2d_fwd": (_i, [_vp, _T, _vp, _vp, _i, _u32, _T, _T, _T, _vp]),
     "dd_conv2d_transpose2x2_fwd": (_i, [_vp, _T, _vp, _vp, _u32, _T, _vp]),
+    "dd_conv2d_transpose3x3_fwd": (_i, [_vp, _T, _P(_vp), _vp, _u32, _T, _T, _vp]),
     "dd_maxpool_s2_fwd": (_i, [_vp, _T, _i, _T, _vp]),
     "dd_avgpool_fwd": (_i, [_vp, _T, _i, _T, _vp]),
     "dd_standardize_variance": (_i, [_vp, _T, _P(dd_standardize_params), _T, _T, _vp]),
     "dd_assemble_input": (_i, [_vp, _vp, _i, _i, _T, _vp]),
-    "dd_kernel_predict_fwd": (_i, [_vp, _T, _T, _i, _i, _T, _vp]),
+    "dd_kernel_predict_fwd": (_i, [_vp, _T, _T, _i, _i, _i, _T, _vp]),
     "dd_compose_head_fwd": (_i, [_vp, _T, _T, _vp, _vp, _i, _T, _vp]),
     "dd_compose_tail_fwd": (_i, [_vp, _T, _vp, _vp, _i, _T, _T, _P(dd_invert_params), _T, _vp]),
     "dd_invert_standardization": (_i, [_vp, _T, _P(dd_invert_params), _T, _vp]),
@@ -174,6 +175,13 @@ class Context:
         self.handle, ctypes.byref(x), w_packed.data_ptr(), bias.data_ptr() if bias is not None else None,
         DD_CONV_RELU if relu else 0, ctypes.byref(y), self._stream()))
 
+  def conv2d_transpose3x3(self, x, w_phases, bias, y, y_relu=None, relu=False):
+    arr = (ctypes.c_void_p * 4)(*[w.data_ptr() for w in w_phases])
+    flags = (DD_CONV_RELU if relu else 0) | (DD_CONV_RELU_COPY if y_relu is not None else 0)
+    self._check(self.lib.dd_conv2d_transpose3x3_fwd(
+        self.handle, ctypes.byref(x), arr, bias.data_ptr() if bias is not None else None, flags, ctypes.byref(y),
+        ctypes.byref(y_relu) if y_relu is not None else None, self._stream()))
+
   # -- pooling
   def maxpool_s2(self, x, ksize, y):
     self._check(self.lib.dd_maxpool_s2_fwd(self.handle, ctypes.byref(x), ksize, ctypes.byref(y), self._stream()))
@@ -192,9 +200,9 @@ class Context:
                                            self._stream()))
 
   # -- kernel prediction / multi-scale
-  def kernel_predict(self, src, logits, ksize, features, out):
+  def kernel_predict(self, src, logits, ksize, features, images_per_tuple, out):
     self._check(self.lib.dd_kernel_predict_fwd(self.handle, ctypes.byref(src), ctypes.byref(logits), ksize, features,
-                                               ctypes.byref(out), self._stream()))
+                                               images_per_tuple, ctypes.byref(out), self._stream()))
 
   def compose_head(self, small, large, w_host, b_host, c_mid, y):
     self._check(self.lib.dd_compose_head_fwd(self.handle, ctypes.byref(small), ctypes.byref(large),

@@ -116,6 +116,7 @@ struct TcLaunch {
   const dd_tensor* y;
   const dd_tensor* y_relu;
   int ups, sp0;
+  uint32_t tap_mask;        // 0 = all taps
 };
 
 static int launch_conv_tc(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream) {
@@ -138,6 +139,7 @@ static int launch_conv_tc(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream) {
   p.n_umma = L.n_umma;
   p.acc_stride = round_up(L.n_umma, 32);
   p.taps = L.ksize * L.ksize;
+  p.tap_mask = L.tap_mask ? L.tap_mask : (p.taps == 9 ? 0x1FFu : 1u);
   p.n_chunks = (p.Cin + kConvCH - 1) / kConvCH;
   p.shift_mode = (p.taps == 9) ? ctx->conv_shift_mode : 0;
 
@@ -409,6 +411,46 @@ int dd_conv2d_transpose2x2_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_pa
     L.ngroups = per; L.group_c = c16; L.cout_store = round_up(cout, 8);
     L.ksize = 1; L.bias = bias; L.flags = flags; L.residual = nullptr; L.y = y; L.y_relu = nullptr;
     L.ups = 2; L.sp0 = sp0;
+    int rc = launch_conv_tc(ctx, L, s);
+    if (rc) return rc;
+  }
+  return DD_OK;
+}
+
+
+int dd_conv2d_transpose3x3_fwd(dd_ctx* ctx, const dd_tensor* x, const void* const* w_phase, const float* bias,
+                               uint32_t flags, const dd_tensor* y, const dd_tensor* y_relu, void* stream) {
+  DD_CHECK_ARG(ctx && w_phase && w_phase[0] && w_phase[1] && w_phase[2] && w_phase[3], "NULL argument");
+  DD_CHECK_ARG(tensor_ok(x) && tensor_ok(y), "bad tensor descriptor");
+  DD_CHECK_ARG(y->n == x->n && y->h == 2 * x->h && y->w == 2 * x->w, "transpose3x3: output must be 2x input");
+  DD_CHECK_ARG(!y_relu || (tensor_ok(y_relu) && y_relu->c == y->c && y_relu->h == y->h && y_relu->w == y->w),
+               "bad y_relu");
+  DD_CHECK_ARG(((flags & DD_CONV_RELU_COPY) != 0) == (y_relu != nullptr), "DD_CONV_RELU_COPY needs y_relu");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int cout = y->c;
+  for (int ph = 0; ph < 4; ++ph) {
+    const int py = ph >> 1, px = ph & 1;
+    if (x->dtype == DD_F32) {
+      DD_CHECK_ARG(y->dtype == DD_F32, "exact path writes fp32");
+      int rc = launch_conv_simt(ctx, x, reinterpret_cast<const float*>(w_phase[ph]), bias, 3, cout, flags, nullptr, y,
+                                y_relu, 2, py, px, s);
+      if (rc) return rc;
+      continue;
+    }
+    // taps of the phase kernel sit at slab offsets (dy+1, dx+1), dy,dx in {0,-1}; W index py-2dy must be <= 2
+    uint32_t mask = 0;
+    for (int dy = 0; dy >= -1; --dy)
+      for (int dx = 0; dx >= -1; --dx)
+        if (py - 2 * dy <= 2 && px - 2 * dx <= 2) mask |= 1u << ((dy + 1) * 3 + (dx + 1));
+    const int c16 = round_up(cout, 16);
+    DD_CHECK_ARG(c16 <= 256, "cout %d > 256", cout);
+    TcLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.x = x; L.w_packed = w_phase[ph]; L.rows_total = c16; L.row0 = 0; L.n_umma = c16;
+    L.ngroups = 1; L.group_c = c16; L.cout_store = round_up(cout, 8);
+    L.ksize = 3; L.bias = bias; L.flags = flags; L.residual = nullptr; L.y = y; L.y_relu = y_relu;
+    L.ups = 2; L.sp0 = ph; L.tap_mask = mask;
+    DD_CHECK_ARG(ctx->conv_shift_mode == 0, "tap subsets need conv_shift_mode 0");
     int rc = launch_conv_tc(ctx, L, s);
     if (rc) return rc;
   }

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(const AssembleParams p) {
 constexpr int kKpTileH = 8, kKpTileW = 32, kKpThreads = 256;
 struct KpParams {
   View src, logits, out;
-  int K, F;          // kernel size, features per logits tensor
+  int K, F, ipt;     // kernel size, features per logits tensor, images per tuple
   int tiles_x, tiles_y;
 };
 
@@ -215,9 +215,9 @@ __global__ void __launch_bounds__(kKpThreads) kernel_predict_kernel(const KpPara
   extern __shared__ float4 s_src[];
   const int K = p.K, K2 = K * K, pad = (K - 1) / 2;
   const int TW = kKpTileW + 2 * pad, TH = kKpTileH + 2 * pad;
-  const int img = blockIdx.z;                       // f * B + b
-  const int B = p.logits.n;
-  const int f = img / B, b = img % B;
+  // logits image b = tuple * ipt + n, feature f  ->  src/out image (tuple * F + f) * ipt + n
+  const int b = blockIdx.z / p.F, f = blockIdx.z % p.F;
+  const int img = ((b / p.ipt) * p.F + f) * p.ipt + (b % p.ipt);
   const int ty0 = blockIdx.y * kKpTileH, tx0 = blockIdx.x * kKpTileW;
   const int h = p.src.h, w = p.src.w;
   for (int i = threadIdx.x; i < TW * TH; i += kKpThreads) {
@@ -446,7 +446,7 @@ int dd_assemble_input(dd_ctx* ctx, const dd_gather_entry* table_dev, int tuples,
 }
 
 int dd_kernel_predict_fwd(dd_ctx* ctx, const dd_tensor* src, const dd_tensor* logits, int ksize, int features,
-                          const dd_tensor* out, void* stream) {
+                          int images_per_tuple, const dd_tensor* out, void* stream) {
   DD_CHECK_ARG(ctx && tensor_ok(src) && tensor_ok(logits) && tensor_ok(out), "bad argument");
   DD_CHECK_ARG(ksize >= 1 && (ksize & 1) && ksize <= 31, "kernel size must be odd and <= 31");
   DD_CHECK_ARG(features >= 1 && logits->c == features * ksize * ksize, "logits must have features*K*K channels");
@@ -455,7 +455,8 @@ int dd_kernel_predict_fwd(dd_ctx* ctx, const dd_tensor* src, const dd_tensor* lo
   DD_CHECK_ARG(src->h == logits->h && src->w == logits->w && same_spatial(src, out), "spatial dims differ");
   KpParams p;
   p.src = make_view(src); p.logits = make_view(logits); p.out = make_view(out);
-  p.K = ksize; p.F = features;
+  DD_CHECK_ARG(images_per_tuple >= 1 && logits->n % images_per_tuple == 0, "logits.n must be a multiple of images_per_tuple");
+  p.K = ksize; p.F = features; p.ipt = images_per_tuple;
   p.tiles_x = (src->w + kKpTileW - 1) / kKpTileW; p.tiles_y = (src->h + kKpTileH - 1) / kKpTileH;
   const int pad = (ksize - 1) / 2;
   const size_t smem = static_cast<size_t>(kKpTileW + 2 * pad) * (kKpTileH + 2 * pad) * sizeof(float4);

@@ -35,6 +35,7 @@ struct ConvTcParams {
   int n_umma;             // UMMA N (multiple of 16, <= 256) = ngroups * group_c
   int acc_stride;         // TMEM columns between accumulators (n_umma rounded up to 32)
   int taps;               // 9 or 1
+  uint32_t tap_mask;      // bit (r*3+s) set: tap is computed (conv2d_transpose 3x3 phases use tap subsets)
   int R;                  // rows per tile
   int strips, bands, num_tiles;
   int n_chunks;           // ceil(Cin / 64)
@@ -142,6 +143,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int s = (n_sgroups == 3) ? g : si;
               for (int r = 0; r < n_r; ++r) {
                 const int tap = (p.taps == 9) ? (r * 3 + s) : 0;
+                if (!((p.tap_mask >> tap) & 1u)) continue;
                 mbar_wait(&b_empty[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&b_full[stage], p.b_tx_bytes);
                 tma_load_3d(b_smem + static_cast<size_t>(stage) * p.b_stage_bytes, &tmB, &b_full[stage],
@@ -159,6 +161,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t idesc = make_idesc_f16(kConvTileW, p.n_umma);
       const uint32_t a_base = smem_u32(a_smem);
       const uint32_t b_base = smem_u32(b_smem);
+      const uint64_t desc_tmpl = make_desc_sw128(0, 0);
+      const uint32_t a_row_pitch = static_cast<uint32_t>(p.a_box_w) * 128u;
       int as = 0; uint32_t aphase = 0;
       int bs = 0; uint32_t bphase = 0;
       int it = 0;
@@ -179,18 +183,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int si = 0; si < s_per_group; ++si) {
               const int s_off = (n_sgroups == 3) ? 0 : si;
               for (int r = 0; r < n_r; ++r) {
+                const int s_tap = (n_sgroups == 3) ? g : si;
+                if (!((p.tap_mask >> ((p.taps == 9) ? (r * 3 + s_tap) : 0)) & 1u)) continue;
                 mbar_wait(&b_full[bs], bphase);
                 tc_fence_after();
                 const uint32_t b_stage = b_base + static_cast<uint32_t>(bs) * p.b_stage_bytes;
+                // descriptors differ only in the 14-bit (address >> 4) field: plain 64-bit adds
+                const uint64_t bdesc0 = desc_tmpl + (b_stage >> 4);
+                const uint32_t a_tap = a_stage + static_cast<uint32_t>((r * p.a_box_w + s_off) * 128);
+                const uint32_t acc0 = first ? 0u : 1u;
                 for (int j = 0; j < p.R; ++j) {
-                  const uint32_t a_row = a_stage + static_cast<uint32_t>(((j + r) * p.a_box_w + s_off) * 128);
-                  const uint32_t boff = (p.shift_mode == 1) ? ((a_row >> 7) & 7u) : 0u;
+                  const uint64_t adesc0 = desc_tmpl + ((a_tap + static_cast<uint32_t>(j) * a_row_pitch) >> 4);
                   const uint32_t d_tmem = tmem_acc + static_cast<uint32_t>(j * p.acc_stride);
-                  for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t adesc = make_desc_sw128(a_row + k * 32, boff);
-                    const uint64_t bdesc = make_desc_sw128(b_stage + k * 32, 0);
-                    umma_f16(d_tmem, adesc, bdesc, idesc, (first && k == 0) ? 0u : 1u);
-                  }
+                  umma_f16(d_tmem, adesc0, bdesc0, idesc, acc0);
+                  if (ksteps > 1) umma_f16(d_tmem, adesc0 + 2, bdesc0 + 2, idesc, 1u);
+                  if (ksteps > 2) umma_f16(d_tmem, adesc0 + 4, bdesc0 + 4, idesc, 1u);
+                  if (ksteps > 3) umma_f16(d_tmem, adesc0 + 6, bdesc0 + 6, idesc, 1u);
                 }
                 first = false;
                 umma_commit(&b_empty[bs]);

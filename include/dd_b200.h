@@ -91,6 +91,14 @@ int dd_conv2d_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const f
 int dd_conv2d_transpose2x2_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const float* bias,
                                uint32_t flags, const dd_tensor* y, void* stream);
 
+/* y = relu?(conv2d_transpose(x, W, k=3, stride=2, 'same') + b) (Tiramisu.py:62-64; SURVEY A.5: full 2n+1
+ * output cropped at the tail).  Computed as 4 output phases, each a stride-1 conv of x with the taps that
+ * land on that phase: w_phase[py*2+px] is an ordinary packed 3x3 kernel (dd_conv2d_pack_weights,
+ * transposed = 0) holding W[py-2dy, px-2dx]^T at tap (dy+1, dx+1), dy,dx in {0,-1}, zeros elsewhere.
+ * y_relu (optional, with DD_CONV_RELU_COPY) receives relu(y). */
+int dd_conv2d_transpose3x3_fwd(dd_ctx* ctx, const dd_tensor* x, const void* const* w_phase, const float* bias,
+                               uint32_t flags, const dd_tensor* y, const dd_tensor* y_relu, void* stream);
+
 /* ---- pooling / resampling ------------------------------------------------------------------- */
 /* tf.layers.max_pooling2d(pool=ksize, strides=2, 'same'): ksize 3 (UNet.py:42-44, pad bottom/right only)
  * or 2 (Tiramisu.py:55-57).  y dims = ceil(x dims / 2). */
@@ -133,12 +141,15 @@ int dd_assemble_input(dd_ctx* ctx, const dd_gather_entry* table_dev, int tuples,
                       void* stream);
 
 /* ---- kernel prediction ---------------------------------------------------------------------- */
-/* KernelPrediction.kernel_prediction (KernelPrediction.py:11-63) with use_softmax=True, mode='symmetric':
- *   out[b,y,x,c] = sum_{i,j} sym(src)[b,y+i-p,x+j-p,c] * softmax_k(logits[b',y,x,f*K*K + k])[i*K+j]
- * src/out fp32 [features*B,h,w,3] with B = logits.n; image f*B + b uses logits channels
- * [f*K*K, (f+1)*K*K) of logits image b (the tf.split of Architecture.py:581-587). logits F16 or F32. */
+/* KernelPrediction.kernel_prediction (KernelPrediction.py:11-63) with use_softmax=True, mode='symmetric',
+ * including the tf.split of the post-processed tensor into one K*K slab per feature of the tuple
+ * (Architecture.py:581-587) and the per-feature KernelPredictor loop (Architecture.py:260-289):
+ *   out[o,y,x,c] = sum_{i,j} sym(src)[o,y+i-p,x+j-p,c] * softmax_k(logits[b,y,x,f*K*K + k])[i*K+j]
+ * logits F16/F32 [B,h,w,features*K*K]; src/out fp32 [features*B,h,w,3].  Logits image b = tuple*ipt + n
+ * (ipt = images_per_tuple) and feature f use src/out image o = (tuple*features + f)*ipt + n, i.e. the
+ * images of the passes of one tuple are adjacent ("pass-major bank"). */
 int dd_kernel_predict_fwd(dd_ctx* ctx, const dd_tensor* src, const dd_tensor* logits, int ksize, int features,
-                          const dd_tensor* out, void* stream);
+                          int images_per_tuple, const dd_tensor* out, void* stream);
 
 /* ---- multi-scale composition ---------------------------------------------------------------- */
 /* First layer of the compose weight net: relu(conv1x1_{6->C}(concat[up2(small), large]))

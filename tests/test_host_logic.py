@@ -1,0 +1,133 @@
+"""Host-side logic of the product (no GPU): feature layout, tuples, variable lists, work counts, naming, and that
+the C-ABI library loads and exports every symbol include/dd_b200.h declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+from deepdenoiser_b200 import _lib, synthetic
+from deepdenoiser_b200.Architecture import Architecture, FeaturePredictionTupleType, FeaturePredictionType
+from deepdenoiser_b200.FeatureFlags import FeatureFlagMode
+from deepdenoiser_b200.Naming import Naming
+from deepdenoiser_b200.RenderPasses import RenderPasses, RenderPassesUsage
+from oracle import reference_model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+  header = open(os.path.join(ROOT, "include", "dd_b200.h")).read()
+  declared = set(re.findall(r"\b(dd_[a-z0-9_]+)\s*\(", header))
+  declared -= {"dd_ctx"}
+  assert len(declared) >= 20
+  assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+  lib = _lib.load_library()          # raises if the .so is not built
+  for name in declared:
+    assert hasattr(lib, name), name
+  assert lib.dd_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip("GPU present")
+  with pytest.raises(_lib.DDError):
+    _lib.Context(0)
+  lib = _lib.load_library()
+  handle = ctypes.c_void_p()
+  assert lib.dd_ctx_create(0, ctypes.byref(handle)) == -4      # DD_ERR_NO_DEVICE
+  assert b"no CPU fallback" in lib.dd_last_error()
+  arch = Architecture(synthetic.example_architecture_json())
+  with pytest.raises(_lib.DDError):
+    arch.predict(synthetic.synthetic_features(arch, 1, 16, 16))
+
+
+def test_example_json_feature_layout():
+  a = Architecture(synthetic.example_architecture_json())
+  assert a.feature_prediction_tuple_type == FeaturePredictionTupleType.SINGLE
+  names = [fp.name for fp in a.feature_predictions]
+  # sorted combined names x [Color, Direct, Indirect], empty names skipped (Architecture.py:420-473)
+  assert names == ["Alpha", "Diffuse Color", "Diffuse Direct", "Diffuse Indirect", "Emission", "Environment",
+                   "Glossy Color", "Glossy Direct", "Glossy Indirect", "Subsurface Color", "Subsurface Direct",
+                   "Subsurface Indirect", "Transmission Color", "Transmission Direct", "Transmission Indirect",
+                   "Volume Direct", "Volume Indirect"]
+  assert len(a.feature_prediction_tuples) == 17 and all(fp.load_data for fp in a.feature_predictions)
+  assert [f.name for f in a.auxiliary_features] == ["Normal"]
+  assert a.feature_predictions[0].number_of_channels == 1
+  assert a.feature_flags is not None and a.feature_flags.embedding_dimension == 8
+  assert a.number_of_input_channels == 16 and a.number_of_output_channels == 25
+  kinds = [e[0] for e in a.input_layouts[0]]
+  assert kinds == ["source"] * 3 + ["variance"] + ["source"] * 3 + ["variance"] + ["embedding"] * 8
+  assert a.input_layouts[3][0][1].name == "Diffuse Indirect" and a.input_layouts[3][4][1].name == "Normal"
+
+
+def test_combined_tuples_and_synthetic_members():
+  j, n, h, w = cases.case("combined_onehot")
+  a = Architecture(j)
+  assert len(a.feature_prediction_tuples) == 8 and len(a.feature_predictions) == 24
+  assert a.feature_flags is None and a.feature_flag_mode == FeatureFlagMode.ONE_HOT_ENCODING
+  vol = a.feature_prediction_tuples[-1]
+  assert vol.name == "Volume" and [fp.load_data for fp in vol.feature_predictions] == [False, True, True]
+  assert vol.feature_predictions[0].name == "Volume Color"
+  assert vol.feature_predictions[0].feature_prediction_type == FeaturePredictionType.COLOR
+  assert a.number_of_input_channels == 4 * 4 + 8 and a.number_of_output_channels == 3 * 9
+  assert float(vol.feature_predictions[0].synthetic_source(1, 2, 2)[0, 0, 0, 0]) == 1.0
+  assert float(vol.feature_predictions[1].feature_standardization.use_log1p) == 1.0
+
+
+def test_baseline_configs_match_survey_work_counts():
+  a = Architecture(synthetic.baseline_architecture_json("unet32"))
+  assert a.number_of_input_channels == 32
+  assert int(a.mac_per_pixel()) == 566182                  # SURVEY Appendix B.1 / BASELINE.md section 3
+  assert a.spec.parameter_count() == 1691218
+  t = Architecture(synthetic.baseline_architecture_json("tiramisu32"))
+  assert int(t.mac_per_pixel()) == 4157694
+  assert t.spec.scale_channels == [1216, 1184, 640]        # Appendix B.2
+  assert Architecture(synthetic.baseline_architecture_json("rgb9")).number_of_input_channels == 9
+  assert int(Architecture(synthetic.example_architecture_json()).mac_per_pixel()) == 556966
+
+
+@pytest.mark.parametrize("name", cases.GOLDEN_CASES + ("rgb9",))
+def test_layout_and_variables_agree_with_oracle(name):
+  j, arch, weights, features = cases.build(name)
+  oracle = reference_model.Architecture(j, weights=weights)
+  assert [t.name for t in oracle.feature_prediction_tuples] == [t.name for t in arch.feature_prediction_tuples]
+  assert [f.name for f in oracle.feature_predictions] == [f.name for f in arch.feature_predictions]
+  assert oracle.number_of_output_channels == arch.number_of_output_channels
+  for f in oracle.feature_predictions + oracle.auxiliary_features:
+    f.initialize_sources(features, np.float64)
+    f.standardize()
+  for tup, layout in zip(oracle.feature_prediction_tuples, arch.input_layouts):
+    x = oracle._network_input(tup, features)
+    assert x.shape[3] == len(layout) == arch.number_of_input_channels
+    # spot-check the channel order: every 'source' channel equals the oracle's standardised source
+    for ch, entry in enumerate(layout):
+      if entry[0] == "source":
+        fp = next(f for f in oracle.feature_predictions + oracle.auxiliary_features if f.name == entry[1].name)
+        src = fp.source[0]
+        np.testing.assert_array_equal(x[..., ch], src[..., entry[2] if src.shape[3] == 3 else 0])
+  oracle2 = reference_model.Architecture(j, weights=weights)
+  oracle2.predict(features)
+  assert [(n, tuple(oracle2.store.values[n].shape)) for n in oracle2.store.created] == arch.spec.variable_shapes()
+
+
+def test_render_passes_and_naming_contract():
+  assert RenderPasses.number_of_channels("Alpha") == 1 and RenderPasses.number_of_channels("Depth") == 1
+  assert RenderPasses.number_of_channels("Normal") == 3 and RenderPasses.number_of_channels("") == 3
+  assert RenderPasses.is_combined_feature_render_pass("Glossy") and not RenderPasses.is_combined_feature_render_pass("Volume")
+  assert RenderPasses.direct_or_indirect_to_color_render_pass("Diffuse Direct") == "Diffuse Color"
+  assert RenderPasses.direct_or_indirect_to_color_render_pass("Diffuse Indirect") == "Diffuse Indirect"   # reference typo kept
+  assert RenderPasses.combined_to_color_render_pass("Emission") == "Emission"
+  assert not RenderPasses.is_rgb_color_render_pass("Screen Space Normal") and RenderPasses.is_rgb_color_render_pass("Shadow")
+  usage = RenderPassesUsage(use_volume_indirect=True, use_alpha=True, use_glossy_color=True)
+  assert usage.render_passes() == ["Alpha", "Glossy Color", "Volume Indirect"]
+  assert Naming.source_feature_name("Normal", index=0) == "source_image/0/Normal"
+  assert Naming.source_feature_name("Normal", samples_per_pixel=16, index=1, masked=True) == "source_image/16/1/Normal Masked"
+  assert Naming.target_feature_name("Alpha") == "target_image/Alpha"
+  assert Naming.feature_prediction_name("Diffuse Color") == "prediction/Diffuse Color"
+  assert Naming.feature_flags_name("Diffuse") == "feature_flag/Diffuse"
+  assert Naming.mean_name("Diffuse", masked=True, scale_index=2) == "combined_diffuse_mean_masked/4"
+  assert Naming.difference_name("Volume Direct") == "volume_direct_difference"
