@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Headline benchmark: megapixels/sec denoised, U-Net KPCN 32-channel render-pass stack at 1080p (BASELINE.json
+configs[1]) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo's CUDA path
+  python bench.py --impl reference [...]                              # restated reference on the host CPU cores
+
+One "step" = one full 1920x1080 frame through Architecture.predict: all 17 feature-prediction tuple passes of
+the SINGLE-mode JSON (shared weights, Architecture.py:561-571), each pass = SourceEncoder concat -> U-Net ->
+1x1 post-process -> kernel-prediction apply at 3 scales -> multi-scale composition -> inverse standardisation.
+`value` = frame megapixels / step time with the sources resident in HBM; `e2e` = the same call fed from pinned
+HOST buffers with the 17 full-resolution predictions copied back to the host inside the timed region.
+N > 1: one process per GPU (torchrun), every rank denoises its own frame (frames are independent: no
+data-path collective), barrier + max-over-ranks timing, weak scaling.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from deepdenoiser_b200 import synthetic  # noqa: E402
+from deepdenoiser_b200.Architecture import Architecture  # noqa: E402
+
+HEIGHT, WIDTH = 1080, 1920
+METRIC = "megapixels/sec denoised (U-Net KPCN 32-ch 1080p)"
+
+
+def peaks():
+  path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(path):
+    p = json.load(open(path))
+    return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+            "source": "MEASURED_PEAKS.json (sustained bf16 dense)"}
+  return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+  """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+  QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+           "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index):
+    super().__init__(daemon=True)
+    self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+  def run(self):
+    while not self.stop_flag.is_set():
+      try:
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(",")]
+        if len(parts) >= 6:
+          self.samples.append(parts)
+      except Exception:  # noqa: BLE001
+        pass
+      self.stop_flag.wait(0.2)
+
+  def summary(self):
+    if not self.samples:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    sm = sorted(float(s[0]) for s in self.samples)
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+    return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+            "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def cpu_reference(arch_json, weights, threads, tiles, tile=128, overlap=14):
+  """The reference's CPU inference path restated (oracle/reference_model.py on torch-CPU float32, oneDNN): the
+  frame is cut into 128x128 tiles with overlap 14 (Prediction.py:259-310 => 19 x 11 = 209 tiles at 1080p), each
+  tile is a batch-1 run of all 17 tuple passes.  Times `tiles` tiles and scales to the 209 of a frame."""
+  from oracle import reference_model, torch_ops
+  torch.set_num_threads(threads)
+  host = Architecture(arch_json)
+  model = reference_model.Architecture(arch_json, ops=torch_ops, dtype=torch.float32, weights=weights)
+  feats = synthetic.synthetic_features(host, 1, tile, tile, seed=1234)
+  with torch.no_grad():
+    model.predict(feats)                       # warm-up (oneDNN primitive caches)
+    t0 = time.perf_counter()
+    for _ in range(tiles):
+      model.predict(feats)
+    dt = (time.perf_counter() - t0) / tiles
+  delta = tile - 2 * overlap
+  count = lambda n: int(np.ceil((n - 2 * overlap - 2 * delta) / delta)) + 2  # noqa: E731
+  tiles_per_frame = count(HEIGHT) * count(WIDTH)
+  return HEIGHT * WIDTH / 1e6 / (tiles_per_frame * dt), dt, tiles_per_frame
+
+
+def run_reference(args, arch_json, weights, config):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  threads = os.cpu_count() or 1
+  values = []
+  for _ in range(args.warmup):
+    cpu_reference(arch_json, weights, threads, 1)
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    v, dt, tpf = cpu_reference(arch_json, weights, threads, args.ref_tiles)
+    values.append(v)
+  wall = time.perf_counter() - t0
+  value = float(np.median(values))
+  sample = ("%d tiles of 128x128 (overlap 14) x 17 tuple passes per step, scaled to the %d tiles of a 1080p frame; "
+            "restated reference (oracle/reference_model.py on torch-CPU float32 / oneDNN), TensorFlow 1.x is not "
+            "installable here" % (args.ref_tiles, tpf))
+  line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": args.gpus,
+          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * HEIGHT * WIDTH / 1e6 / value,
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": config,
+          "cpu_baseline": {"value": value, "unit": "MP/s", "cores": threads, "kind": "port", "sample": sample},
+          "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+          "gpu_launches": 0, "wall_s": wall}
+  print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- CUDA arm
+def conv_roofline(arch, feats_dev, steps):
+  """Device time of the dominant kernel (conv_tc_kernel: every 3x3 / 1x1 / transposed convolution of the pass) measured
+  with CUDA events around each launch on the launching stream, and the algorithmic FLOPs of those launches."""
+  net = arch.network
+  records = []
+  orig_conv, orig_t2 = net._conv, arch.ctx.conv2d_transpose2x2
+
+  def timed(flops, fn):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    records.append((e0, e1, flops))
+
+  def conv(var, x, y, relu=False, residual=None, y_relu=None):
+    px = x.t.shape[0] * x.t.shape[1] * x.t.shape[2]
+    timed(2.0 * px * var.ksize * var.ksize * var.cin * var.cout,
+          lambda: orig_conv(var, x, y, relu=relu, residual=residual, y_relu=y_relu))
+
+  def t2(xd, wp, bias, yd, relu=False):
+    timed(2.0 * xd.n * xd.h * xd.w * 4 * xd.c * yd.c, lambda: orig_t2(xd, wp, bias, yd, relu=relu))
+
+  net._conv, arch.ctx.conv2d_transpose2x2 = conv, t2
+  try:
+    for _ in range(steps):
+      arch.predict(feats_dev)
+    torch.cuda.synchronize()
+  finally:
+    net._conv, arch.ctx.conv2d_transpose2x2 = orig_conv, orig_t2
+  ms = sum(e0.elapsed_time(e1) for e0, e1, _ in records)
+  flops = sum(f for _, _, f in records)
+  return flops / steps, ms / steps, len(records) // steps
+
+
+def run_cuda(args, arch_json, weights, config):
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback (use --impl reference for "
+                     "the CPU baseline)")
+  torch.cuda.set_device(local)
+  dist = None
+  if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+  def barrier():
+    if dist is not None:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  jj = dict(arch_json)
+  jj["b200"] = {"dtype": "float16"}
+  arch = Architecture(jj, weights=weights, device=local)
+  feats = synthetic.synthetic_features(arch, 1, HEIGHT, WIDTH, seed=1234 + rank)
+  pinned = {k: torch.from_numpy(v).pin_memory() for k, v in feats.items()}
+  feats_dev = {k: v.cuda(non_blocking=True) for k, v in pinned.items()}
+  h2d = sum(v.numel() * 4 for v in pinned.values())
+  out = arch.predict(feats_dev)                  # allocates every buffer
+  out_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out[0].items()}
+  d2h = sum(v.numel() * 4 for v in out_host.values())
+  torch.cuda.synchronize()
+
+  def timed_loop(fn, steps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+      fn()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if dist is not None:
+      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+  def step_resident():
+    arch.predict(feats_dev)
+
+  def step_e2e():
+    res = arch.predict(pinned)[0]
+    for k, v in res.items():
+      out_host[k].copy_(v, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+
+  for _ in range(max(args.warmup, 3)):
+    step_resident()
+  sampler = ClockSampler(local)
+  sampler.start()
+  l0 = arch.ctx.launch_count()
+  total_ms = timed_loop(step_resident, args.steps)
+  launches = arch.ctx.launch_count() - l0
+  sampler.stop_flag.set()
+  sampler.join(timeout=2)
+  for _ in range(2):
+    step_e2e()
+  e2e_ms = timed_loop(step_e2e, args.steps)
+
+  ms_per_step = total_ms / args.steps
+  mp = HEIGHT * WIDTH / 1e6
+  value = world * mp / (ms_per_step / 1e3)
+  e2e_value = world * mp / (e2e_ms / args.steps / 1e3)
+  line = None
+  if rank == 0:
+    pk = peaks()
+    flops, conv_ms, conv_launches = conv_roofline(arch, feats_dev, 2)
+    achieved = flops / (conv_ms / 1e3) / 1e12
+    tuples = len(arch.feature_prediction_tuples)
+    cfg = dict(config)
+    cfg.update({"tuple_passes_per_frame": tuples, "mp_per_s_per_tuple_pass": value / world * tuples,
+                "l2": "per-step working set (activations of 17 x 1080p passes, >10 GB) is far larger than the 126 MB L2",
+                "frame_flops": flops, "conv_share_of_step": conv_ms / ms_per_step})
+    line = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic", "config": cfg,
+            "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)", "achieved": achieved,
+                         "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                         "launches_per_step": conv_launches, "ms_per_step_in_kernel": conv_ms, "peak_source": pk["source"]},
+            "clocks": sampler.summary()}
+    if world == 1 and not args.no_cpu_baseline:
+      threads = os.cpu_count() or 1
+      v, dt, tpf = cpu_reference(arch_json, weights, threads, args.ref_tiles)
+      line["cpu_baseline"] = {"value": v, "unit": "MP/s", "cores": threads, "kind": "port",
+                              "sample": "%d tiles of 128x128 x 17 passes (%.2f s/tile), scaled to %d tiles/frame; restated "
+                                        "reference on torch-CPU float32 (TensorFlow 1.x not installable)" %
+                                        (args.ref_tiles, dt, tpf)}
+    print(json.dumps(line))
+  if dist is not None:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=10)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+  ap.add_argument("--ref-tiles", type=int, default=4, help="tiles timed per CPU-baseline sample")
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  args = ap.parse_args()
+  arch_json = synthetic.baseline_architecture_json("unet32")
+  weights = synthetic.randomize_biases(Architecture(arch_json).weights)
+  config = {"workload": "configs[1]: U-Net [64,96,128]x4 KPCN K=5, 32-ch render-pass stack, 1920x1080 frame, batch 1, "
+                        "SINGLE tuples (17 passes/frame), 3 scales", "height": HEIGHT, "width": WIDTH,
+            "input_channels": 32, "kernel_size": 5}
+  if args.impl == "reference":
+    run_reference(args, arch_json, weights, config)
+  else:
+    run_cuda(args, arch_json, weights, config)
+
+
+if __name__ == "__main__":
+  main()

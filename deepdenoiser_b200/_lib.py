@@ -108,7 +108,9 @@ def desc(t, c=None, coff=0):
   if c is None:
     c = cs - coff
   assert 0 <= coff and coff + c <= cs
-  return dd_tensor(t.data_ptr(), _dtype_code(t), n, h, w, c, cs, coff)
+  d = dd_tensor(t.data_ptr(), _dtype_code(t), n, h, w, c, cs, coff)
+  d._keep = t   # the descriptor keeps its storage alive (kernels run asynchronously)
+  return d
 
 
 class Context:

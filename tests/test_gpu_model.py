@@ -1,0 +1,121 @@
+"""End-to-end parity of Architecture.predict on the GPU (through the C ABI) against the oracle and the
+committed golden vectors.
+
+Tolerances (per-pixel L1, i.e. |out - oracle| per element, relative to max(1, |oracle|_max) of the pass):
+  float32 mode : <= 1e-4   - the north-star bound; the CUDA path accumulates in fp32 like the reference
+  float16 mode : <= 5e-2 max, <= 5e-3 mean - fp16 storage of ~22 stacked conv layers (fp32 accumulate, fp32
+                 logits / softmax / filter apply); see DESIGN.md "precision"
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from deepdenoiser_b200 import synthetic
+from deepdenoiser_b200.Architecture import Architecture, ModeKeys
+from oracle import np_ops, reference_model
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def run_case(name, dtype):
+  j, host_arch, weights, features = cases.build(name)
+  j = dict(j)
+  j["b200"] = {"dtype": dtype}
+  arch = Architecture(j, weights=weights)
+  out = arch.predict({k: torch.from_numpy(v) for k, v in features.items()}, ModeKeys.PREDICT)
+  torch.cuda.synchronize()
+  oracle = reference_model.Architecture(j, ops=np_ops, dtype=np.float64, weights=weights).predict_numpy(features)
+  return arch, out, oracle
+
+
+def errors(out, oracle):
+  worst_max, worst_mean = 0.0, 0.0
+  assert len(out) == len(oracle)
+  for s in range(len(oracle)):
+    assert set(out[s]) == set(oracle[s])
+    for k, want in oracle[s].items():
+      got = out[s][k].float().cpu().numpy().astype(np.float64)
+      assert got.shape == want.shape, (k, got.shape, want.shape)
+      assert np.isfinite(got).all(), k
+      scale = max(1.0, float(np.abs(want).max()))
+      worst_max = max(worst_max, float(np.abs(got - want).max()) / scale)
+      worst_mean = max(worst_mean, float(np.abs(got - want).mean()) / scale)
+  return worst_max, worst_mean
+
+
+@pytest.mark.parametrize("name", cases.GOLDEN_CASES + ("rgb9",))
+def test_predict_float32_matches_oracle_1e4(name):
+  arch, out, oracle = run_case(name, "float32")
+  mx, mean = errors(out, oracle)
+  print(name, "fp32 max %.2e mean %.2e" % (mx, mean))
+  assert mx <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["example", "combined_onehot", "tiramisu", "variants", "rgb9"])
+def test_predict_float16_tensor_core_path(name):
+  arch, out, oracle = run_case(name, "float16")
+  mx, mean = errors(out, oracle)
+  print(name, "fp16 max %.2e mean %.2e" % (mx, mean))
+  assert mx <= 5e-2 and mean <= 5e-3
+
+
+@pytest.mark.parametrize("name", cases.GOLDEN_CASES)
+def test_predict_float32_matches_committed_golden(name):
+  arch, out, _ = run_case(name, "float32")
+  z = np.load(os.path.join(GOLDEN, name + ".npz"))
+  checked = 0
+  for key in z.files:
+    if "|" not in key:
+      continue
+    s, k = key.split("|", 1)
+    want = z[key].astype(np.float64)
+    got = out[int(s)][k].float().cpu().numpy()
+    assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), key
+    checked += 1
+  assert checked > 0
+
+
+def test_tuple_chunking_does_not_change_results():
+  j, host_arch, weights, features = cases.build("example")
+  outs = []
+  for chunk in (1 << 30, 16 * 16 * 3):            # all 17 tuples at once vs 3 tuples per chunk
+    jj = dict(j)
+    jj["b200"] = {"dtype": "float32", "max_chunk_pixels": chunk}
+    arch = Architecture(jj, weights=weights)
+    outs.append(arch.predict({k: torch.from_numpy(v) for k, v in features.items()}))
+  for s in range(3):
+    for k in outs[0][s]:
+      assert torch.equal(outs[0][s][k], outs[1][s][k]), (s, k)
+
+
+def test_identity_network_reproduces_source():
+  """Known answer through the whole path: zero weights => equal logits => box-filtered standardised source at every
+  scale; composition of box filters of pooled images; checked against the oracle at tight tolerance."""
+  j, host_arch, weights, features = cases.build("example")
+  zero = {k: np.zeros_like(v) for k, v in weights.items()}
+  jj = dict(j)
+  jj["b200"] = {"dtype": "float16"}               # with zero weights the fp16 path is exact too
+  arch = Architecture(jj, weights=zero)
+  out = arch.predict({k: torch.from_numpy(v) for k, v in features.items()})
+  oracle = reference_model.Architecture(j, ops=np_ops, dtype=np.float64, weights=zero).predict_numpy(features)
+  mx, _ = errors(out, oracle)
+  assert mx <= 2e-5
+
+
+def test_larger_image_and_batch_float16():
+  """Tile shapes of the real workloads (width > 128 => several strips, rows % 4 != 0, batch > 1)."""
+  j = synthetic.baseline_architecture_json("unet32")
+  host = Architecture(j)
+  weights = synthetic.randomize_biases(host.weights)
+  features = synthetic.synthetic_features(host, 2, 36, 264, seed=5)
+  jj = dict(j)
+  jj["b200"] = {"dtype": "float16"}
+  out = Architecture(jj, weights=weights).predict({k: torch.from_numpy(v) for k, v in features.items()})
+  oracle = reference_model.Architecture(j, ops=np_ops, dtype=np.float64, weights=weights).predict_numpy(features)
+  mx, mean = errors(out, oracle)
+  print("unet32 36x264 fp16 max %.2e mean %.2e" % (mx, mean))
+  assert mx <= 5e-2 and mean <= 5e-3

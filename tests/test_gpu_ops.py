@@ -1,0 +1,298 @@
+"""GPU parity of every libdd_b200 entry point against the oracle operators (oracle/np_ops.py), called through
+the C ABI (ctypes) exactly like the product does.  fp32 paths: <= 2e-5 relative to the output scale (fp32
+reassociation); fp16 tensor-core convolution: compared with the oracle run on the SAME fp16-rounded operands,
+tolerance 2e-3 * output scale (one fp16 rounding of the result + fp32 accumulation order)."""
+import numpy as np
+import pytest
+import torch
+
+from deepdenoiser_b200 import _lib
+from oracle import np_ops
+
+pytestmark = pytest.mark.gpu
+RNG = np.random.default_rng(11)
+
+
+def dev(x, dtype=torch.float32):
+  return torch.from_numpy(np.ascontiguousarray(x)).to("cuda", dtype)
+
+
+def close(got, want, tol, what=""):
+  got = got.detach().float().cpu().numpy().astype(np.float64)
+  scale = max(1.0, float(np.abs(want).max()))
+  err = float(np.abs(got - want).max())
+  assert err <= tol * scale, "%s: max err %.3e > %.1e * %.3g" % (what, err, tol, scale)
+
+
+def pad_bias(b):
+  out = torch.zeros((b.shape[0] + 15) // 16 * 16)
+  out[:b.shape[0]] = torch.from_numpy(b)
+  return out.cuda()
+
+
+# ------------------------------------------------------------------------------------------------ convolution
+@pytest.mark.parametrize("ks,cin,cout,h,w", [(3, 12, 10, 17, 23), (1, 7, 5, 9, 31), (3, 32, 64, 8, 130)])
+def test_conv2d_exact_fp32(ctx, ks, cin, cout, h, w):
+  x = RNG.standard_normal((2, h, w, cin)).astype(np.float32)
+  k = (RNG.standard_normal((ks, ks, cin, cout)) * 0.2).astype(np.float32)
+  b = RNG.standard_normal(cout).astype(np.float32)
+  res = RNG.standard_normal((2, h, w, cout)).astype(np.float32)
+  wp = ctx.pack_conv_weights(torch.from_numpy(k), torch.float32)
+  y = torch.empty(2, h, w, cout, device="cuda")
+  yr = torch.empty(2, h, w, cout, device="cuda")
+  ctx.conv2d(_lib.desc(dev(x)), wp, dev(b), ks, _lib.desc(y), relu=False, residual=_lib.desc(dev(res)),
+             y_relu=_lib.desc(yr))
+  want = np_ops.conv2d_same(x.astype(np.float64), k, b) + res
+  close(y, want, 2e-5, "conv")
+  close(yr, np.maximum(want, 0), 2e-5, "relu copy")
+
+
+CONV_TC_CASES = [
+    # ks, cin, cout, n, h, w, cstride_in, coff_in
+    (3, 64, 64, 2, 21, 150, 64, 0),
+    (3, 32, 64, 1, 16, 300, 32, 0),
+    (3, 16, 64, 1, 16, 128, 16, 0),
+    (3, 9, 64, 1, 12, 64, 16, 0),            # cfg1: 9 source channels in a 16-wide buffer
+    (3, 96, 96, 1, 10, 130, 96, 0),
+    (3, 192, 96, 1, 10, 130, 200, 8),        # concat buffer window
+    (3, 128, 128, 1, 9, 140, 128, 0),
+    (3, 24, 24, 1, 12, 40, 24, 0),           # compose residual convs
+    (1, 64, 25, 2, 9, 150, 64, 0),           # post-process K=5
+    (1, 25, 25, 1, 9, 150, 32, 0),
+    (1, 128, 75, 1, 7, 40, 128, 0),          # COMBINED post-process
+    (1, 320, 200, 1, 6, 129, 320, 0),        # wide 1x1 (Tiramisu transition, split over chunks)
+]
+
+
+@pytest.mark.parametrize("ks,cin,cout,n,h,w,cs,coff", CONV_TC_CASES)
+def test_conv2d_tensor_core_fp16(ctx, ks, cin, cout, n, h, w, cs, coff):
+  xfull = (RNG.standard_normal((n, h, w, cs)) * 0.5).astype(np.float16)
+  k = (RNG.standard_normal((ks, ks, cin, cout)) / np.sqrt(ks * ks * cin)).astype(np.float32)
+  b = (RNG.standard_normal(cout) * 0.1).astype(np.float32)
+  wp = ctx.pack_conv_weights(torch.from_numpy(k), torch.float16)
+  c8 = (cout + 7) // 8 * 8
+  xd = dev(xfull, torch.float16)
+  for out_dtype in (torch.float16, torch.float32):
+    y = torch.full((n, h, w, c8 + 8), float("nan"), dtype=out_dtype, device="cuda")
+    ctx.conv2d(_lib.desc(xd, cin, coff), wp, pad_bias(b), ks, _lib.desc(y, cout, 8 if c8 + 8 >= cout + 8 else 0),
+               relu=True)
+    x64 = xfull[..., coff:coff + cin].astype(np.float64)
+    k64 = k.astype(np.float16).astype(np.float64)
+    want = np_ops.conv2d_same(x64, k64, b.astype(np.float64), relu=True)
+    close(y[..., 8:8 + cout], want, 2e-3 if out_dtype == torch.float16 else 2e-4, "tc conv %s" % out_dtype)
+    assert torch.isnan(y[..., :8].float()).all(), "wrote outside the channel window"
+
+
+def test_conv2d_tensor_core_residual_and_relu_copy(ctx):
+  n, h, w, c = 1, 11, 70, 24
+  x = (RNG.standard_normal((n, h, w, c)) * 0.5).astype(np.float16)
+  res = (RNG.standard_normal((n, h, w, c)) * 0.5).astype(np.float16)
+  k = (RNG.standard_normal((3, 3, c, c)) / np.sqrt(9 * c)).astype(np.float32)
+  b = (RNG.standard_normal(c) * 0.1).astype(np.float32)
+  wp = ctx.pack_conv_weights(torch.from_numpy(k), torch.float16)
+  y = torch.empty(n, h, w, c, dtype=torch.float16, device="cuda")
+  yr = torch.empty(n, h, w, c, dtype=torch.float16, device="cuda")
+  ctx.conv2d(_lib.desc(dev(x, torch.float16)), wp, pad_bias(b), 3, _lib.desc(y), relu=False,
+             residual=_lib.desc(dev(res, torch.float16)), y_relu=_lib.desc(yr))
+  want = np_ops.conv2d_same(x.astype(np.float64), k.astype(np.float16).astype(np.float64), b.astype(np.float64))
+  want = want + res.astype(np.float64)
+  close(y, want, 2e-3, "residual")
+  close(yr, np.maximum(want, 0), 2e-3, "relu copy")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("cin,cout", [(128, 96), (96, 64), (24, 16)])
+def test_conv2d_transpose_2x2(ctx, dtype, cin, cout):
+  n, h, w = 2, 6, 70
+  x = (RNG.standard_normal((n, h, w, cin)) * 0.5).astype(np.float16)
+  k = (RNG.standard_normal((2, 2, cout, cin)) / np.sqrt(cin)).astype(np.float32)
+  b = (RNG.standard_normal(cout) * 0.1).astype(np.float32)
+  wp = ctx.pack_conv_weights(torch.from_numpy(k), dtype, transposed=True)
+  y = torch.full((n, 2 * h, 2 * w, 2 * cout), float("nan"), dtype=dtype, device="cuda")
+  ctx.conv2d_transpose2x2(_lib.desc(dev(x, dtype)), wp, pad_bias(b), _lib.desc(y, cout, cout), relu=True)
+  k64 = k.astype(np.float16).astype(np.float64) if dtype == torch.float16 else k.astype(np.float64)
+  want = np_ops.conv2d_transpose_same_s2(x.astype(np.float64), k64, b.astype(np.float64), relu=True)
+  close(y[..., cout:], want, 2e-3 if dtype == torch.float16 else 2e-5, "convT2x2")
+  assert torch.isnan(y[..., :cout].float()).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_conv2d_transpose_3x3_tf_same(ctx, dtype):
+  n, h, w, cin, cout = 1, 7, 66, 40, 32
+  x = (RNG.standard_normal((n, h, w, cin)) * 0.5).astype(np.float16)
+  k = (RNG.standard_normal((3, 3, cout, cin)) / np.sqrt(4 * cin)).astype(np.float32)
+  b = (RNG.standard_normal(cout) * 0.1).astype(np.float32)
+  phases = []
+  for py in range(2):
+    for px in range(2):
+      wz = np.zeros((3, 3, cin, cout), dtype=np.float32)
+      for dy in (0, -1):
+        for dx in (0, -1):
+          r, s = py - 2 * dy, px - 2 * dx
+          if r <= 2 and s <= 2:
+            wz[dy + 1, dx + 1] = k[r, s].T
+      phases.append(ctx.pack_conv_weights(torch.from_numpy(wz), dtype))
+  y = torch.full((n, 2 * h, 2 * w, cout), float("nan"), dtype=dtype, device="cuda")
+  ya = torch.full((n, 2 * h, 2 * w, cout), float("nan"), dtype=dtype, device="cuda")
+  ctx.conv2d_transpose3x3(_lib.desc(dev(x, dtype)), phases, pad_bias(b), _lib.desc(y), _lib.desc(ya), relu=True)
+  k64 = k.astype(np.float16).astype(np.float64) if dtype == torch.float16 else k.astype(np.float64)
+  want = np_ops.conv2d_transpose_same_s2(x.astype(np.float64), k64, b.astype(np.float64), relu=True)
+  close(y, want, 2e-3 if dtype == torch.float16 else 2e-5, "convT3x3")
+  close(ya, want, 2e-3 if dtype == torch.float16 else 2e-5, "convT3x3 relu copy")
+
+
+# ------------------------------------------------------------------------------------------------ pooling
+@pytest.mark.parametrize("k", [2, 3])
+@pytest.mark.parametrize("dtype,c,h,w", [(torch.float16, 64, 12, 18), (torch.float16, 24, 7, 9), (torch.float32, 5, 9, 6)])
+def test_maxpool_tf_same(ctx, k, dtype, c, h, w):
+  x = RNG.standard_normal((2, h, w, c)).astype(np.float16)
+  y = torch.empty(2, (h + 1) // 2, (w + 1) // 2, c, dtype=dtype, device="cuda")
+  ctx.maxpool_s2(_lib.desc(dev(x, dtype)), k, _lib.desc(y))
+  close(y, np_ops.max_pool_same_s2(x.astype(np.float64), k), 0.0, "maxpool")      # exact: a max of inputs
+
+
+@pytest.mark.parametrize("f,h,w", [(2, 12, 20), (4, 12, 20), (2, 7, 9)])
+def test_avgpool_tf_same(ctx, f, h, w):
+  x = RNG.standard_normal((3, h, w, 3)).astype(np.float32)
+  y = torch.empty(3, -(-h // f), -(-w // f), 3, device="cuda")
+  ctx.avgpool(_lib.desc(dev(x)), f, _lib.desc(y))
+  close(y, np_ops.avg_pool_same(x.astype(np.float64), f), 2e-6, "avgpool")
+
+
+# ------------------------------------------------------------------------------------------------ source encoder
+@pytest.mark.parametrize("c", [1, 3])
+@pytest.mark.parametrize("mode,rel,before,comp,log1p,mean,var",
+                         [("uniform", True, False, True, True, 0.0, 1.0),
+                          ("neighbor", False, False, False, True, 0.25, 2.0),
+                          ("uniform", True, True, True, False, 0.0, 1.0),
+                          ("neighbor", True, True, False, True, -0.5, 0.5)])
+def test_standardize_variance(ctx, c, mode, rel, before, comp, log1p, mean, var):
+  x = (RNG.standard_normal((2, 9, 13, c)) * 3).astype(np.float32)
+  x[0, :3, :4] = 0.0
+  prm = _lib.dd_standardize_params(int(log1p), mean, var, 1, 0 if mode == "uniform" else 1, int(rel), int(before),
+                                   int(comp), 1e-4)
+  s = torch.empty(2, 9, 13, 3, device="cuda")
+  vc = 1 if comp else c
+  v = torch.empty(2, 9, 13, vc, device="cuda")
+  ctx.standardize_variance(_lib.desc(dev(x)), prm, _lib.desc(s), _lib.desc(v))
+  x64 = x.astype(np.float64)
+  std = np_ops.signed_log1p(x64) if log1p else x64
+  std = (std - mean) / np.sqrt(var)
+  want_v = np_ops.variance_feature(x64 if before else std, mode, rel, comp)
+  close(s, np.repeat(std, 3, axis=3) if c == 1 else std, 2e-6, "standardize")
+  # E[x^2]-E[x]^2 cancels catastrophically in fp32; relative variance divides by >= 1e-4
+  tol = 3e-2 if rel else 2e-5
+  close(v, want_v, tol, "variance")
+
+
+def test_assemble_input_gathers_channels(ctx):
+  n, h, w, tuples, c = 2, 5, 7, 3, 16
+  a = RNG.standard_normal((n, h, w, 3)).astype(np.float32)
+  b = RNG.standard_normal((n, h, w, 1)).astype(np.float32)
+  emb = RNG.standard_normal((tuples, 4)).astype(np.float32)
+  ad, bd, ed = dev(a), dev(b), dev(emb)
+  table = np.zeros((tuples, c), dtype=np.dtype([("ptr", "<u8"), ("cstride", "<i4"), ("cidx", "<i4"),
+                                                ("constant", "<f4"), ("pad", "<i4")]))
+  want = np.zeros((tuples * n, h, w, c))
+  for t in range(tuples):
+    for ch in range(3):
+      table[t, ch] = (ad.data_ptr(), 3, (ch + t) % 3, 0, 0)
+      want[t * n:(t + 1) * n, ..., ch] = a[..., (ch + t) % 3]
+    table[t, 3] = (bd.data_ptr(), 1, 0, 0, 0)
+    want[t * n:(t + 1) * n, ..., 3] = b[..., 0]
+    for j in range(4):
+      table[t, 4 + j] = (ed.data_ptr() + (t * 4 + j) * 4, 0, 0, 0, 0)
+      want[t * n:(t + 1) * n, ..., 4 + j] = emb[t, j]
+    table[t, 8] = (0, 0, 0, 1.5, 0)
+    want[t * n:(t + 1) * n, ..., 8] = 1.5
+  td = torch.from_numpy(table.view(np.uint8).reshape(-1)).cuda()
+  for dtype, tol in ((torch.float32, 0.0), (torch.float16, 1e-3)):
+    out = torch.empty(tuples * n, h, w, c, dtype=dtype, device="cuda")
+    ctx.assemble_input(td, tuples, n, _lib.desc(out))
+    close(out, want, tol, "assemble %s" % dtype)
+
+
+# ------------------------------------------------------------------------------------------------ kernel prediction
+@pytest.mark.parametrize("k,features,ipt,h,w,ldtype", [(5, 1, 1, 19, 37, torch.float32), (5, 3, 2, 16, 40, torch.float16),
+                                                       (21, 1, 2, 33, 45, torch.float32), (21, 1, 1, 12, 10, torch.float16),
+                                                       (3, 3, 1, 8, 8, torch.float32), (7, 2, 1, 40, 33, torch.float32)])
+def test_kernel_predict(ctx, k, features, ipt, h, w, ldtype):
+  tuples = 2
+  b = tuples * ipt
+  k2 = k * k
+  cpad = (features * k2 + 7) // 8 * 8
+  logits = np.zeros((b, h, w, cpad), dtype=np.float32)
+  logits[..., :features * k2] = RNG.standard_normal((b, h, w, features * k2)) * 2
+  logits = logits.astype(np.float16).astype(np.float32) if ldtype == torch.float16 else logits
+  src = (RNG.standard_normal((features * b, h, w, 3)) * 2).astype(np.float32)
+  out = torch.empty(features * b, h, w, 3, device="cuda")
+  ctx.kernel_predict(_lib.desc(dev(src)), _lib.desc(dev(logits, ldtype), features * k2, 0), k, features, ipt,
+                     _lib.desc(out))
+  want = np.zeros((features * b, h, w, 3))
+  for bi in range(b):
+    t, n = divmod(bi, ipt)
+    for f in range(features):
+      o = (t * features + f) * ipt + n
+      want[o] = np_ops.kernel_prediction(src[o:o + 1].astype(np.float64),
+                                         logits[bi:bi + 1, ..., f * k2:(f + 1) * k2].astype(np.float64), k)[0]
+  close(out, want, 5e-6, "kernel prediction")
+
+
+def test_kernel_predict_known_answers(ctx):
+  k, h, w = 5, 12, 13
+  src = RNG.standard_normal((1, h, w, 3)).astype(np.float32)
+  # equal logits -> symmetric-border box filter; one-hot -> shift by (i-p, j-p)
+  out = torch.empty(1, h, w, 3, device="cuda")
+  ctx.kernel_predict(_lib.desc(dev(src)), _lib.desc(dev(np.zeros((1, h, w, 32), np.float32)), 25, 0), k, 1, 1, _lib.desc(out))
+  xp = np.pad(src.astype(np.float64), ((0, 0), (2, 2), (2, 2), (0, 0)), mode="symmetric")
+  close(out, sum(xp[:, i:i + h, j:j + w] for i in range(5) for j in range(5)) / 25, 1e-6, "box")
+  logits = np.full((1, h, w, 32), -1e4, np.float32)
+  logits[..., 1 * 5 + 4] = 0
+  ctx.kernel_predict(_lib.desc(dev(src)), _lib.desc(dev(logits), 25, 0), k, 1, 1, _lib.desc(out))
+  close(out, xp[:, 1:1 + h, 4:4 + w], 1e-7, "shift")
+
+
+# ------------------------------------------------------------------------------------------------ multi-scale
+def test_compose_head_tail_and_invert(ctx):
+  n, h, w = 2, 10, 14
+  small = RNG.standard_normal((n, h // 2, w // 2, 3)).astype(np.float32)
+  large = RNG.standard_normal((n, h, w, 3)).astype(np.float32)
+  hw_ = (RNG.standard_normal((6, 24)) * 0.4).astype(np.float32)
+  hb = (RNG.standard_normal(24) * 0.1).astype(np.float32)
+  y = torch.empty(n, h, w, 24, device="cuda")
+  ctx.compose_head(_lib.desc(dev(small)), _lib.desc(dev(large)), torch.from_numpy(hw_), torch.from_numpy(hb), 24, _lib.desc(y))
+  up = np_ops.resize_nearest_x2(small.astype(np.float64))
+  x6 = np.concatenate([up, large.astype(np.float64)], axis=3)
+  want_head = np.maximum(x6 @ hw_.astype(np.float64) + hb, 0)
+  close(y, want_head, 2e-6, "compose head")
+  t = RNG.standard_normal((n, h, w, 24)).astype(np.float32)
+  tw = (RNG.standard_normal(24) * 0.3).astype(np.float32)
+  tb = np.array([0.1], np.float32)
+  out = torch.empty(n, h, w, 3, device="cuda")
+  for inv in (None, _lib.dd_invert_params(1, 0.25, 2.0)):
+    ctx.compose_tail(_lib.desc(dev(t)), torch.from_numpy(tw), torch.from_numpy(tb), 24, _lib.desc(dev(small)),
+                     _lib.desc(dev(large)), inv, _lib.desc(out))
+    wgt = np_ops.sigmoid(np.maximum(t.astype(np.float64) @ tw.astype(np.float64) + 0.1, 0))[..., None]
+    assert wgt.min() >= 0.5
+    low = np_ops.resize_nearest_x2(np_ops.avg_pool_same(large.astype(np.float64), 2))
+    want = large - wgt * low + wgt * up
+    if inv is not None:
+      want = np_ops.signed_expm1(want * np.sqrt(2.0) + 0.25)
+    close(out, want, 5e-6, "compose tail")
+  x = (RNG.standard_normal((n, h, w, 3)) * 2).astype(np.float32)
+  xd = dev(x)
+  ctx.invert_standardization(_lib.desc(xd), _lib.dd_invert_params(1, 0.0, 1.0), _lib.desc(xd))   # in place
+  close(xd, np_ops.signed_expm1(x.astype(np.float64)), 2e-6, "invert")
+
+
+def test_bad_arguments_are_reported_not_crashed(ctx):
+  x = torch.zeros(1, 4, 4, 3, device="cuda")
+  with pytest.raises(_lib.DDError, match="kernel size"):
+    ctx.kernel_predict(_lib.desc(x), _lib.desc(torch.zeros(1, 4, 4, 16, device="cuda")), 4, 1, 1, _lib.desc(x))
+  with pytest.raises(_lib.DDError):
+    ctx.maxpool_s2(_lib.desc(x), 5, _lib.desc(x))
+  with pytest.raises(_lib.DDError, match="unknown option"):
+    ctx.set_option("nope", 1)
+  n0 = ctx.launch_count()
+  ctx.avgpool(_lib.desc(x), 2, _lib.desc(torch.zeros(1, 2, 2, 3, device="cuda")))
+  assert ctx.launch_count() == n0 + 1
