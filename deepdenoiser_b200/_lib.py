@@ -53,6 +53,7 @@ SIGNATURES = {
     "dd_ctx_sm_count": (_i, [_vp]),
     "dd_ctx_set_option": (_i, [_vp, ctypes.c_char_p, _i]),
     "dd_ctx_launch_count": (ctypes.c_int64, [_vp]),
+    "dd_ctx_set_trace_buffer": (_i, [_vp, _vp]),
     "dd_conv2d_packed_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "dd_conv2d_pack_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "dd_conv2d_fwd": (_i, [_vp, _T, _vp, _vp, _i, _u32, _T, _T, _T, _vp]),
@@ -150,6 +151,9 @@ class Context:
 
   def set_option(self, name, value):
     self._check(self.lib.dd_ctx_set_option(self.handle, name.encode(), int(value)))
+
+  def set_trace_buffer(self, t):
+    self._check(self.lib.dd_ctx_set_trace_buffer(self.handle, t.data_ptr() if t is not None else None))
 
   # -- conv
   def pack_conv_weights(self, w, dtype, transposed=False):

@@ -3,7 +3,7 @@
 
 #include <vector>
 
-#include "conv_tc.cuh"
+#include "conv_rows.cuh"
 #include "dd_internal.h"
 
 namespace dd {
@@ -87,146 +87,202 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int encode_map(dd_ctx* ctx, CUtensorMap* map, void* base, int rank, const cuuint64_t* dims,
+static int encode_map(dd_ctx* ctx, CUtensorMap* map, CUtensorMapDataType dt, void* base, int rank, const cuuint64_t* dims,
                       const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapL2promotion promo) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
-      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), base, dims, strides, box, estr,
-      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      map, dt, static_cast<cuuint32_t>(rank), base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu box %u %u %u)",
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu %llu strides %llu %llu box %u %u %u)",
               static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
-              (unsigned long long)dims[2], box[0], box[1], box[2]);
+              (unsigned long long)dims[2], (unsigned long long)dims[3], (unsigned long long)strides[0],
+              (unsigned long long)strides[1], box[0], box[1], box[2]);
     return DD_ERR_CUDA;
   }
   return DD_OK;
 }
 
+// Packed fp16 weight tensor of the row-pipeline kernel: [chunk][shift s][tap r][cpad_total][64 ch], zero padded.
+//   3x3: s, r in 0..2 (tap = r*3 + s);  1x1: one tile per chunk;  transposed 2x2: 1x1 with rows (sub-pixel, cpad)
+static int packed_cpad(int cout) { return round_up(cout, 32); }
+
 struct TcLaunch {
   const dd_tensor* x;
-  const void* w_packed;     // [taps][rows_total][cin64] fp16
-  int rows_total;           // rows in the packed weight matrix
-  int row0;                 // first row used by this launch
-  int n_umma;               // rows used
-  int ngroups, group_c, cout_store;
-  int ksize;
+  const void* w_packed;
+  int ksize;                // 3 or 1
+  int rows_total;           // cpad rows per (chunk, s, r) in the packed tensor
+  int row0;                 // first row (output channel) used by this launch
+  int cpad;                 // rows used == accumulator block width
+  int ngroups, group_c;     // column groups inside the block (sub-pixels of conv2d_transpose 2x2)
+  int cout;                 // channels stored per group
   const float* bias;
+  int bias_count;
   uint32_t flags;
   const dd_tensor* residual;
-  const dd_tensor* y;
+  const dd_tensor* y;       // for ngroups > 1 / ups == 2: the full-resolution output
   const dd_tensor* y_relu;
-  int ups, sp0;
-  uint32_t tap_mask;        // 0 = all taps
+  int ups, sp0;             // ups == 2: group g -> sub-pixel sp0 + g -> (ay, ax) = (sp >> 1, sp & 1)
+  int s_mask, rm_lo, rm_hi; // tap subset (3x3 only); s_mask == 0 -> all
 };
 
-static int launch_conv_tc(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream) {
+// view of `t` seen through a stride-`ups` sub-pixel lattice starting at (ay, ax)
+static int encode_out_map(dd_ctx* ctx, CUtensorMap* map, const dd_tensor* t, int c_first, int channels, int in_h, int in_w,
+                          int ups, int ay, int ax) {
+  const size_t es = elem_size(t->dtype);
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(channels), static_cast<cuuint64_t>(in_w), static_cast<cuuint64_t>(in_h),
+                        static_cast<cuuint64_t>(t->n)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(ups) * t->cstride * es,
+                           static_cast<cuuint64_t>(ups) * t->w * t->cstride * es,
+                           static_cast<cuuint64_t>(t->h) * t->w * t->cstride * es};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(128 / es), 32, 1, 1};
+  uint8_t* base = reinterpret_cast<uint8_t*>(t->ptr) +
+                  ((static_cast<size_t>(ay) * t->w + ax) * t->cstride + t->coff + c_first) * es;
+  return encode_map(ctx, map, t->dtype == DD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base,
+                    4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+}
+
+static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream) {
   const dd_tensor* x = L.x;
   const dd_tensor* y = L.y;
   DD_CHECK_ARG(ctx->encode_tiled, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   DD_CHECK_ARG(x->dtype == DD_F16, "tensor-core conv needs fp16 input");
   DD_CHECK_ARG(x->coff % 8 == 0 && x->cstride % 8 == 0, "conv input view must be 16-byte aligned (coff %d cstride %d)",
                x->coff, x->cstride);
-  DD_CHECK_ARG(L.n_umma % 16 == 0 && L.n_umma >= 16 && L.n_umma <= 256, "UMMA N %d unsupported", L.n_umma);
+  DD_CHECK_ARG(L.cpad % 32 == 0 && L.cpad >= 32 && L.cpad <= 256, "accumulator block width %d unsupported", L.cpad);
   const int align_out = (y->dtype == DD_F16) ? 8 : 4;
   DD_CHECK_ARG(y->coff % align_out == 0 && y->cstride % align_out == 0, "conv output view misaligned");
-  DD_CHECK_ARG(y->coff + L.cout_store <= y->cstride, "conv output buffer too narrow for padded store (%d+%d>%d)",
-               y->coff, L.cout_store, y->cstride);
 
-  ConvTcParams p;
+  ConvRowsParams p;
   memset(&p, 0, sizeof(p));
   p.N = x->n; p.H = x->h; p.W = x->w;
-  p.Cin = round_up(x->c, 16);
-  p.n_umma = L.n_umma;
-  p.acc_stride = round_up(L.n_umma, 32);
-  p.taps = L.ksize * L.ksize;
-  p.tap_mask = L.tap_mask ? L.tap_mask : (p.taps == 9 ? 0x1FFu : 1u);
-  p.n_chunks = (p.Cin + kConvCH - 1) / kConvCH;
-  p.shift_mode = (p.taps == 9) ? ctx->conv_shift_mode : 0;
-
-  // rows per tile: as many as TMEM (2 sets) and shared memory allow
-  const size_t smem_cap = ctx->max_smem_optin - 1024 /*align*/ - 512 /*barriers*/;
-  const uint32_t b_stage = static_cast<uint32_t>(L.n_umma) * 128u;
-  int R = 0, a_stages = 2, b_stages = 0;
-  uint32_t a_stage = 0;
-  const int cand[3] = {4, 2, 1};
-  for (int ci = 0; ci < 3; ++ci) {
-    int r = cand[ci];
-    if (ctx->conv_rows > 0) r = ctx->conv_rows;
-    if (2 * r * p.acc_stride > 512) { if (ctx->conv_rows > 0) break; continue; }
-    const int box_w = (p.taps == 9 && p.shift_mode != 2) ? kConvTileW + 2 : kConvTileW;
-    const int rows = (p.taps == 9) ? r + 2 : r;
-    const uint32_t as = static_cast<uint32_t>(round_up(rows * box_w * 128, 1024));
-    const size_t left = (smem_cap > 2ull * as) ? smem_cap - 2ull * as : 0;
-    int bs = static_cast<int>(left / b_stage);
-    if (bs > 8) bs = 8;
-    if (bs >= 2) { R = r; a_stage = as; b_stages = bs; break; }
-    if (ctx->conv_rows > 0) break;
+  p.strips = (p.W + kRowsTileW - 1) / kRowsTileW;
+  p.total_rows = static_cast<long long>(p.N) * p.strips * p.H;
+  const int cin16 = round_up(x->c, 16);
+  p.n_chunks = (cin16 + 63) / 64;
+  p.ksteps_last = (cin16 - 64 * (p.n_chunks - 1)) / 16;
+  const bool k3 = (L.ksize == 3);
+  p.halo = k3 ? 1 : 0;
+  if (k3) {
+    const int mask = L.s_mask ? L.s_mask : 7;
+    for (int s = 0; s < 3; ++s)
+      if (mask & (1 << s)) p.s_list[p.n_s++] = s;
+    p.rm_lo = L.rm_lo; p.rm_hi = L.rm_hi;
+    p.tiles_per_chunk = 3;
+    p.b_r0 = L.rm_lo;
+  } else {
+    p.n_s = 1; p.s_list[0] = 0;
+    p.rm_lo = p.rm_hi = 1;
+    p.tiles_per_chunk = 1;
+    p.b_r0 = 0;
   }
-  DD_CHECK_ARG(R > 0, "no tile configuration fits (n_umma %d taps %d)", L.n_umma, p.taps);
-  if (ctx->conv_b_stages > 0 && ctx->conv_b_stages < b_stages) b_stages = ctx->conv_b_stages;
-  p.R = R;
-  p.a_box_w = (p.taps == 9 && p.shift_mode != 2) ? kConvTileW + 2 : kConvTileW;
-  const int a_rows = (p.taps == 9) ? R + 2 : R;
-  p.a_stages = a_stages; p.b_stages = b_stages;
-  p.a_stage_bytes = a_stage; p.b_stage_bytes = b_stage;
-  p.a_tx_bytes = static_cast<uint32_t>(a_rows * p.a_box_w * 128);
-  p.b_tx_bytes = b_stage;
-  uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(2 * R * p.acc_stride)) cols <<= 1;
-  p.tmem_cols = cols;
-  p.strips = (p.W + kConvTileW - 1) / kConvTileW;
-  p.bands = (p.H + R - 1) / R;
-  p.num_tiles = p.strips * p.bands * p.N;
+  const int n_r = p.rm_hi - p.rm_lo + 1;
+  p.cpad = L.cpad;
+  p.b_row0 = L.row0;
+  p.ring = 512 / p.cpad; if (p.ring > kRowsMaxRing) p.ring = kRowsMaxRing;
+  p.max_stack = 256 / p.cpad;
+  DD_CHECK_ARG(p.ring >= n_r + 1 || n_r == 1, "accumulator ring too small (cpad %d)", p.cpad);
 
-  p.ngroups = L.ngroups; p.group_c = L.group_c; p.cout_store = L.cout_store;
-  p.ups = L.ups; p.sp0 = L.sp0;
-  p.OH = y->h; p.OW = y->w;
-  p.bias = L.bias;
+  // shared memory plan
+  const uint32_t a_box_w = k3 ? kRowsTileW + 2 : kRowsTileW;
+  p.a_tx_bytes = a_box_w * 128u;
+  p.a_slot_bytes = static_cast<uint32_t>(round_up(static_cast<int>(p.a_tx_bytes), 1024));
+  p.b_tile_bytes = static_cast<uint32_t>(n_r * p.cpad) * 128u;
+  p.b_tx_bytes = p.b_tile_bytes;
+  const size_t fixed = 32768 /*staging*/ + 1024 /*bias*/ + 2048 /*barriers + MMA plan*/;
+  const size_t avail = ctx->max_smem_optin - 1024 /*alignment slack*/ - fixed;
+  const size_t w_total = static_cast<size_t>(p.n_chunks) * p.n_s * p.b_tile_bytes;
+  size_t b_bytes;
+  if (!ctx->conv_force_stream && w_total + 4ull * p.a_slot_bytes <= avail) {
+    p.w_resident = 1; p.b_stages = 1; p.G = 1;
+    b_bytes = w_total;
+    p.a_slots = static_cast<int>((avail - w_total) / p.a_slot_bytes);
+    if (p.a_slots > 8) p.a_slots = 8;
+  } else {
+    p.w_resident = 0;
+    p.b_stages = 2;
+    b_bytes = 2ull * p.b_tile_bytes;
+    DD_CHECK_ARG(b_bytes + 2ull * p.a_slot_bytes <= avail, "weight tile too large for shared memory (cpad %d)", p.cpad);
+    p.a_slots = static_cast<int>((avail - b_bytes) / p.a_slot_bytes);
+    if (p.a_slots > 12) p.a_slots = 12;
+    int g = p.ring - (n_r - 1) - 0;          // live blocks of a group: G + (n_r - 1)
+    if (n_r == 1) g = p.ring - 1;
+    if (g > p.a_slots / 2) g = p.a_slots / 2;
+    if (g < 1) g = 1;
+    if (g > 8) g = 8;
+    if (ctx->conv_rows > 0 && ctx->conv_rows < g) g = ctx->conv_rows;
+    p.G = g;
+    if (b_bytes + static_cast<size_t>(p.a_slots) * p.a_slot_bytes + p.b_tile_bytes <= avail) {
+      p.b_stages = 3; b_bytes += p.b_tile_bytes;
+    }
+  }
+  DD_CHECK_ARG(p.a_slots >= p.G && p.a_slots >= 2, "no shared-memory configuration fits (cpad %d chunks %d)", p.cpad, p.n_chunks);
+  p.a_off = 0;
+  p.b_off = static_cast<uint32_t>(p.a_slots) * p.a_slot_bytes;
+  p.stage_off = p.b_off + static_cast<uint32_t>(round_up(static_cast<int>(b_bytes), 1024));
+  p.bias_off = p.stage_off + 32768;
+  p.bar_off = p.bias_off + 1024;
+  const size_t smem = 1024 + p.bar_off + 2048;
+
+  // epilogue
+  p.ngroups = L.ngroups; p.group_c = L.group_c; p.cout_store = L.cout; p.ups = L.ups;
   p.relu = (L.flags & DD_CONV_RELU) ? 1 : 0;
   p.out_f32 = (y->dtype == DD_F32);
-  p.out = y->ptr; p.out_cstride = y->cstride; p.out_coff = y->coff;
-  if (L.y_relu) {
-    DD_CHECK_ARG(L.y_relu->dtype == DD_F16 && L.y_relu->coff % 8 == 0 && L.y_relu->cstride % 8 == 0,
-                 "relu-copy output must be aligned fp16");
-    p.out_relu = reinterpret_cast<__half*>(L.y_relu->ptr);
-    p.out_relu_cstride = L.y_relu->cstride; p.out_relu_coff = L.y_relu->coff;
-  }
+  p.bias = L.bias; p.bias_count = L.bias_count;
+  p.trace = ctx->conv_trace;
   if (L.residual) {
-    DD_CHECK_ARG(L.residual->dtype == DD_F16 && L.residual->coff % 8 == 0 && L.residual->cstride % 8 == 0,
-                 "residual must be aligned fp16");
+    DD_CHECK_ARG(L.ups == 1 && L.ngroups == 1, "residual needs a plain convolution");
+    DD_CHECK_ARG(L.residual->dtype == DD_F16 && L.residual->coff % 8 == 0 && L.residual->cstride % 8 == 0 &&
+                     L.cout % 8 == 0, "residual must be aligned fp16 with a multiple of 8 channels");
     p.residual = reinterpret_cast<const __half*>(L.residual->ptr);
     p.res_cstride = L.residual->cstride; p.res_coff = L.residual->coff;
   }
 
-  // tensor maps
-  CUtensorMap tmA, tmB;
+  ConvRowsMaps maps;
+  memset(&maps, 0, sizeof(maps));
   {
-    cuuint64_t dims[4] = {static_cast<cuuint64_t>(x->c), static_cast<cuuint64_t>(x->w),
-                          static_cast<cuuint64_t>(x->h), static_cast<cuuint64_t>(x->n)};
-    cuuint64_t strides[3] = {static_cast<cuuint64_t>(x->cstride) * 2,
-                             static_cast<cuuint64_t>(x->w) * x->cstride * 2,
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(x->c), static_cast<cuuint64_t>(x->w), static_cast<cuuint64_t>(x->h),
+                          static_cast<cuuint64_t>(x->n)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(x->cstride) * 2, static_cast<cuuint64_t>(x->w) * x->cstride * 2,
                              static_cast<cuuint64_t>(x->h) * x->w * x->cstride * 2};
-    cuuint32_t box[4] = {static_cast<cuuint32_t>(kConvCH), static_cast<cuuint32_t>(p.a_box_w),
-                         static_cast<cuuint32_t>(a_rows), 1};
+    cuuint32_t box[4] = {64, a_box_w, 1, 1};
     void* base = reinterpret_cast<__half*>(x->ptr) + x->coff;
-    int rc = encode_map(ctx, &tmA, base, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    int rc = encode_map(ctx, &maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, 4, dims, strides, box,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc) return rc;
   }
   {
-    const int cin64 = round_up(x->c, 64);
-    cuuint64_t dims[3] = {static_cast<cuuint64_t>(cin64), static_cast<cuuint64_t>(L.rows_total - L.row0),
-                          static_cast<cuuint64_t>(p.taps)};
-    cuuint64_t strides[2] = {static_cast<cuuint64_t>(cin64) * 2, static_cast<cuuint64_t>(L.rows_total) * cin64 * 2};
-    cuuint32_t box[3] = {static_cast<cuuint32_t>(kConvCH), static_cast<cuuint32_t>(L.n_umma), 1};
-    void* base = reinterpret_cast<__half*>(const_cast<void*>(L.w_packed)) + static_cast<size_t>(L.row0) * cin64;
-    int rc = encode_map(ctx, &tmB, base, 3, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    const int r_total = k3 ? 3 : 1;
+    cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(L.rows_total), static_cast<cuuint64_t>(r_total),
+                          static_cast<cuuint64_t>(p.n_chunks * p.tiles_per_chunk)};
+    cuuint64_t strides[3] = {128, static_cast<cuuint64_t>(L.rows_total) * 128,
+                             static_cast<cuuint64_t>(L.rows_total) * 128 * r_total};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.cpad), static_cast<cuuint32_t>(n_r), 1};
+    int rc = encode_map(ctx, &maps.b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, const_cast<void*>(L.w_packed), 4, dims, strides, box,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+  }
+  for (int g = 0; g < L.ngroups; ++g) {
+    const int sp = L.sp0 + g;
+    int rc = encode_out_map(ctx, &maps.out[g], y, 0, L.cout, x->h, x->w, L.ups, L.ups == 2 ? (sp >> 1) : 0,
+                            L.ups == 2 ? (sp & 1) : 0);
+    if (rc) return rc;
+  }
+  if (L.y_relu) {
+    DD_CHECK_ARG(L.y_relu->dtype == DD_F16 && L.y_relu->coff % 8 == 0 && L.y_relu->cstride % 8 == 0 && L.ngroups == 1,
+                 "relu-copy output must be aligned fp16");
+    p.has_relu_copy = 1;
+    int rc = encode_out_map(ctx, &maps.out_relu, L.y_relu, 0, L.cout, x->h, x->w, L.ups, L.ups == 2 ? (L.sp0 >> 1) : 0,
+                            L.ups == 2 ? (L.sp0 & 1) : 0);
     if (rc) return rc;
   }
 
-  const size_t smem = 1024 + static_cast<size_t>(a_stages) * a_stage + static_cast<size_t>(b_stages) * b_stage + 512;
-  DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-  conv_tc_kernel<<<grid, kConvThreads, smem, stream>>>(tmA, tmB, p);
+  int grid = ctx->sm_count;
+  if (p.total_rows < grid) grid = static_cast<int>(p.total_rows);
+  p.rows_per_cta = static_cast<int>((p.total_rows + grid - 1) / grid);
+  grid = static_cast<int>((p.total_rows + p.rows_per_cta - 1) / p.rows_per_cta);
+  DD_CUDA(cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  conv_rows_kernel<<<grid, kRowsThreads, smem, stream>>>(maps, p);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }
@@ -296,23 +352,29 @@ int dd_ctx_destroy(dd_ctx* ctx) {
 int dd_ctx_sm_count(const dd_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 int64_t dd_ctx_launch_count(const dd_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
+int dd_ctx_set_trace_buffer(dd_ctx* ctx, void* device_buffer) {
+  DD_CHECK_ARG(ctx, "NULL ctx");
+  ctx->conv_trace = reinterpret_cast<unsigned long long*>(device_buffer);
+  return DD_OK;
+}
+
 int dd_ctx_set_option(dd_ctx* ctx, const char* name, int value) {
   DD_CHECK_ARG(ctx && name, "NULL argument");
-  if (!strcmp(name, "conv_shift_mode")) { DD_CHECK_ARG(value >= 0 && value <= 2, "bad shift mode"); ctx->conv_shift_mode = value; return DD_OK; }
-  if (!strcmp(name, "conv_rows")) { ctx->conv_rows = value; return DD_OK; }
-  if (!strcmp(name, "conv_b_stages")) { ctx->conv_b_stages = value; return DD_OK; }
+  if (!strcmp(name, "conv_rows")) { ctx->conv_rows = value; return DD_OK; }               // cap on G (rows per weight pass)
+  if (!strcmp(name, "conv_force_stream")) { ctx->conv_force_stream = value; return DD_OK; } // never keep weights resident
   set_error("unknown option '%s'", name);
   return DD_ERR_INVALID;
 }
 
 size_t dd_conv2d_packed_bytes(int ksize, int cin, int cout, int dtype, int transposed) {
-  const int taps = transposed ? 1 : ksize * ksize;
-  const int groups = transposed ? ksize * ksize : 1;
+  const int k2 = ksize * ksize;
   if (dtype == DD_F16) {
-    const int rows = transposed ? groups * round_up(cout, 16) : round_up(cout, 16);
-    return static_cast<size_t>(taps) * rows * round_up(cin, 64) * 2;
+    const int chunks = (round_up(cin, 16) + 63) / 64;
+    const int rows = transposed ? k2 * packed_cpad(cout) : packed_cpad(cout);
+    const int tiles = transposed ? 1 : k2;
+    return static_cast<size_t>(chunks) * tiles * rows * 64 * 2;
   }
-  return static_cast<size_t>(taps) * groups * cout * cin * 4;
+  return static_cast<size_t>(k2) * cout * cin * 4;
 }
 
 int dd_conv2d_pack_weights(dd_ctx* ctx, const float* w, int ksize, int cin, int cout, int dtype, int transposed,
@@ -320,25 +382,30 @@ int dd_conv2d_pack_weights(dd_ctx* ctx, const float* w, int ksize, int cin, int 
   DD_CHECK_ARG(ctx && w && packed_dev, "NULL argument");
   DD_CHECK_ARG(ksize >= 1 && ksize <= 3 && cin > 0 && cout > 0, "bad conv shape");
   DD_CHECK_ARG(!transposed || ksize == 2, "only 2x2 transposed convolutions are packed here");
+  DD_CHECK_ARG(transposed || ksize != 2, "2x2 kernels exist only as transposed convolutions");
   const size_t bytes = dd_conv2d_packed_bytes(ksize, cin, cout, dtype, transposed);
   const int k2 = ksize * ksize;
   std::vector<uint8_t> host(bytes, 0);
   if (dtype == DD_F16) {
-    const int cin64 = round_up(cin, 64);
-    const int c16 = round_up(cout, 16);
+    const int cpad = packed_cpad(cout);
     __half* dst = reinterpret_cast<__half*>(host.data());
     if (!transposed) {
-      // TF [kh,kw,cin,cout] -> [tap][cout16][cin64]
-      for (int t = 0; t < k2; ++t)
-        for (int o = 0; o < cout; ++o)
+      // TF [kh,kw,cin,cout] -> [chunk][s][r][cpad][64]   (tap (r,s): r = row offset, s = column offset)
+      for (int r = 0; r < ksize; ++r)
+        for (int s = 0; s < ksize; ++s)
           for (int c = 0; c < cin; ++c)
-            dst[(static_cast<size_t>(t) * c16 + o) * cin64 + c] = __float2half_rn(w[(static_cast<size_t>(t) * cin + c) * cout + o]);
+            for (int o = 0; o < cout; ++o) {
+              const size_t tile = static_cast<size_t>(c / 64) * ksize + s;
+              dst[((tile * ksize + r) * cpad + o) * 64 + (c % 64)] =
+                  __float2half_rn(w[(static_cast<size_t>(r * ksize + s) * cin + c) * cout + o]);
+            }
     } else {
-      // TF transpose layout [kh,kw,cout,cin] -> one 1x1 GEMM with rows (sub-pixel, cout16)
+      // TF transpose layout [kh,kw,cout,cin] -> [chunk][sub-pixel][cpad][64]: one 1x1 GEMM, rows (sub-pixel, cout)
       for (int sp = 0; sp < k2; ++sp)
         for (int o = 0; o < cout; ++o)
           for (int c = 0; c < cin; ++c)
-            dst[(static_cast<size_t>(sp) * c16 + o) * cin64 + c] = __float2half_rn(w[(static_cast<size_t>(sp) * cout + o) * cin + c]);
+            dst[((static_cast<size_t>(c / 64) * k2 + sp) * cpad + o) * 64 + (c % 64)] =
+                __float2half_rn(w[(static_cast<size_t>(sp) * cout + o) * cin + c]);
     }
   } else {
     float* dst = reinterpret_cast<float*>(host.data());
@@ -371,15 +438,27 @@ int dd_conv2d_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const f
     return launch_conv_simt(ctx, x, reinterpret_cast<const float*>(w_packed), bias, ksize, y->c, flags, residual, y,
                             y_relu, 1, 0, 0, s);
   }
-  const int c16 = round_up(y->c, 16);
-  DD_CHECK_ARG(c16 <= 256, "cout %d > 256: split the layer", y->c);
-  TcLaunch L;
-  memset(&L, 0, sizeof(L));
-  L.x = x; L.w_packed = w_packed; L.rows_total = c16; L.row0 = 0; L.n_umma = c16;
-  L.ngroups = 1; L.group_c = c16; L.cout_store = round_up(y->c, 8);
-  L.ksize = ksize; L.bias = bias; L.flags = flags; L.residual = residual; L.y = y; L.y_relu = y_relu;
-  L.ups = 1; L.sp0 = 0;
-  return launch_conv_tc(ctx, L, s);
+  // output channels are processed in slices of at most 256 (one UMMA N); each slice is its own launch
+  const int cpad_total = packed_cpad(y->c);
+  for (int row0 = 0; row0 < cpad_total; row0 += 256) {
+    const int cpad = (cpad_total - row0 < 256) ? (cpad_total - row0) : 256;
+    const int cout = (y->c - row0 < cpad) ? (y->c - row0) : cpad;
+    dd_tensor ys = *y, yr, rs;
+    ys.coff += row0; ys.c = cout;
+    if (y_relu) { yr = *y_relu; yr.coff += row0; yr.c = cout; }
+    if (residual) { rs = *residual; rs.coff += row0; rs.c = cout; }
+    TcLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.x = x; L.w_packed = w_packed; L.ksize = ksize; L.rows_total = cpad_total; L.row0 = row0; L.cpad = cpad;
+    L.ngroups = 1; L.group_c = cpad; L.cout = cout;
+    L.bias = bias ? bias + row0 : nullptr;
+    L.bias_count = round_up(y->c, 16) - row0 < 256 ? round_up(y->c, 16) - row0 : 256;
+    L.flags = flags; L.residual = residual ? &rs : nullptr; L.y = &ys; L.y_relu = y_relu ? &yr : nullptr;
+    L.ups = 1; L.sp0 = 0; L.s_mask = 0; L.rm_lo = 0; L.rm_hi = 2;
+    int rc = launch_conv_rows(ctx, L, s);
+    if (rc) return rc;
+  }
+  return DD_OK;
 }
 
 int dd_conv2d_transpose2x2_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const float* bias,
@@ -398,25 +477,24 @@ int dd_conv2d_transpose2x2_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_pa
     }
     return DD_OK;
   }
-  const int c16 = round_up(cout, 16);
-  DD_CHECK_ARG(c16 == round_up(cout, 8), "transpose2x2 tensor path needs cout %% 16 in {0, 9..15}");
+  const int cpad1 = packed_cpad(cout);
+  DD_CHECK_ARG(cpad1 <= 256, "cout %d > 256", cout);
   // sub-pixels per launch: as many column groups as fit in one UMMA (N <= 256)
   int per = 4;
-  while (per * c16 > 256) per >>= 1;
-  DD_CHECK_ARG(per >= 1, "cout too large for transpose2x2");
+  while (per * cpad1 > 256) per >>= 1;
   for (int sp0 = 0; sp0 < 4; sp0 += per) {
     TcLaunch L;
     memset(&L, 0, sizeof(L));
-    L.x = x; L.w_packed = w_packed; L.rows_total = 4 * c16; L.row0 = sp0 * c16; L.n_umma = per * c16;
-    L.ngroups = per; L.group_c = c16; L.cout_store = round_up(cout, 8);
-    L.ksize = 1; L.bias = bias; L.flags = flags; L.residual = nullptr; L.y = y; L.y_relu = nullptr;
+    L.x = x; L.w_packed = w_packed; L.ksize = 1; L.rows_total = 4 * cpad1; L.row0 = sp0 * cpad1; L.cpad = per * cpad1;
+    L.ngroups = per; L.group_c = cpad1; L.cout = cout;
+    L.bias = bias; L.bias_count = round_up(cout, 16);
+    L.flags = flags; L.residual = nullptr; L.y = y; L.y_relu = nullptr;
     L.ups = 2; L.sp0 = sp0;
-    int rc = launch_conv_tc(ctx, L, s);
+    int rc = launch_conv_rows(ctx, L, s);
     if (rc) return rc;
   }
   return DD_OK;
 }
-
 
 int dd_conv2d_transpose3x3_fwd(dd_ctx* ctx, const dd_tensor* x, const void* const* w_phase, const float* bias,
                                uint32_t flags, const dd_tensor* y, const dd_tensor* y_relu, void* stream) {
@@ -437,21 +515,20 @@ int dd_conv2d_transpose3x3_fwd(dd_ctx* ctx, const dd_tensor* x, const void* cons
       if (rc) return rc;
       continue;
     }
-    // taps of the phase kernel sit at slab offsets (dy+1, dx+1), dy,dx in {0,-1}; W index py-2dy must be <= 2
-    uint32_t mask = 0;
-    for (int dy = 0; dy >= -1; --dy)
-      for (int dx = 0; dx >= -1; --dx)
-        if (py - 2 * dy <= 2 && px - 2 * dx <= 2) mask |= 1u << ((dy + 1) * 3 + (dx + 1));
-    const int c16 = round_up(cout, 16);
-    DD_CHECK_ARG(c16 <= 256, "cout %d > 256", cout);
+    // taps of the phase kernel sit at (r, s) = (dy+1, dx+1), dy,dx in {0,-1}; W index py-2dy (px-2dx) must be <= 2:
+    // phase 0 uses offsets {0,-1}, phase 1 only offset 0
+    const int cpad = packed_cpad(cout);
+    DD_CHECK_ARG(cpad <= 256, "cout %d > 256", cout);
     TcLaunch L;
     memset(&L, 0, sizeof(L));
-    L.x = x; L.w_packed = w_phase[ph]; L.rows_total = c16; L.row0 = 0; L.n_umma = c16;
-    L.ngroups = 1; L.group_c = c16; L.cout_store = round_up(cout, 8);
-    L.ksize = 3; L.bias = bias; L.flags = flags; L.residual = nullptr; L.y = y; L.y_relu = y_relu;
-    L.ups = 2; L.sp0 = ph; L.tap_mask = mask;
-    DD_CHECK_ARG(ctx->conv_shift_mode == 0, "tap subsets need conv_shift_mode 0");
-    int rc = launch_conv_tc(ctx, L, s);
+    L.x = x; L.w_packed = w_phase[ph]; L.ksize = 3; L.rows_total = cpad; L.row0 = 0; L.cpad = cpad;
+    L.ngroups = 1; L.group_c = cpad; L.cout = cout;
+    L.bias = bias; L.bias_count = round_up(cout, 16);
+    L.flags = flags; L.residual = nullptr; L.y = y; L.y_relu = y_relu;
+    L.ups = 2; L.sp0 = ph;
+    L.s_mask = (px == 0) ? 3 : 2;                 // s = dx + 1: {0,1} or {1}
+    L.rm_lo = (py == 0) ? 0 : 1; L.rm_hi = 1;     // r = dy + 1
+    int rc = launch_conv_rows(ctx, L, s);
     if (rc) return rc;
   }
   return DD_OK;

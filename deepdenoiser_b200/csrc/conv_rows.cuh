@@ -1,0 +1,486 @@
+// tcgen05 implicit-GEMM convolution, "row pipeline" formulation (stride 1, TF 'SAME' zero padding, 3x3 / 1x1, NHWC fp16
+// in, fp32 accumulate in TMEM, fused bias / ReLU / ReLU-copy / residual / channel-window (zero-copy concat) /
+// pixel-shuffle (conv2d_transpose) epilogue written with TMA stores).
+//
+// Replaces tf.layers.conv2d / conv2d_transpose call sites of the reference:
+//   UNet.py:29-31,56-58  Tiramisu.py:35-37,50-52,62-64,77-79  Architecture.py:238-243
+//   MultiScalePrediction.py:64-66,73-75,88-90
+//
+// Mapping onto the hardware
+//   unit of work   one INPUT row t of a 128-pixel column strip.  It is fetched ONCE (TMA box 64ch x 130px, OOB -> 0
+//                  gives SAME padding) and feeds all three vertical taps: out row j = t + 1 - r receives tap r.
+//   UMMA           M = 128 pixels, K = 16, N = n_r * cpad: the weights of the vertical taps r that share this A view
+//                  are STACKED along N, so one instruction updates the accumulators of up to three output rows.
+//                  (A [128x16] is read from shared memory once per instruction; with N = 64 the operand traffic
+//                  would be 192 B/clk - above the 128 B/clk of shared memory - stacked it is <= 107 B/clk.)
+//   horizontal tap view of the same row slot shifted by s pixels = +s*128 B in the 128B-swizzled slot
+//   accumulators   TMEM ring of `ring` blocks of cpad fp32 columns; output row number q (running) lives in block
+//                  ring-1-(q % ring), so the blocks of rows j, j-1, j-2 are adjacent in increasing column order
+//                  (= stacking order r = 0,1,2); a wrap of the ring splits the instruction in two.
+//   weights        [chunk][shift s][tap r][cpad][64ch] fp16; resident in shared memory for the whole kernel when
+//                  they fit, otherwise streamed per (chunk, s) and amortised over a group of G input rows.
+//   epilogue       4 warps: tcgen05.ld -> +bias (+residual) -> ReLU -> fp16/fp32 -> 128B-swizzled staging row in
+//                  shared memory -> one TMA store per 32 pixels x 64 channels (full-line writes; the tensor map
+//                  clips channels / pixels outside the view, sub-pixel views implement the pixel shuffle).
+//   warps          0: A producer  1: B producer  2: MMA issuer  3: TMEM allocator  4-11: epilogue (two sets of
+//                  four warps, one TMEM lane quarter each, alternating output rows)
+//   grid           persistent: the N*strips*H output rows are split into gridDim contiguous ranges (+-1 row).
+#pragma once
+#include "dd_ptx.cuh"
+
+namespace dd {
+
+constexpr int kRowsThreads = 384;
+constexpr int kRowsTileW = 128;
+constexpr int kRowsMaxRing = 8;
+
+struct ConvRowsMaps {
+  CUtensorMap a;        // input  [C, W, H, N] fp16, box [64, a_box_w, 1, 1]
+  CUtensorMap b;        // weights [64, cpad, n_r, tiles] fp16, box [64, cpad, n_r, 1]
+  CUtensorMap out[4];   // primary output view per column group (sub-pixel), box [64 | 32, 32, 1, 1]
+  CUtensorMap out_relu; // optional fp16 relu(primary) view
+};
+
+struct ConvRowsParams {
+  int N, H, W, strips;
+  long long total_rows;   // N * strips * H output rows
+  int rows_per_cta;
+  int n_chunks, ksteps_last;
+  int n_s;                // horizontal shifts iterated
+  int s_list[3];
+  int halo;               // 1: 3x3 (a_box_w = 130, x origin -1), 0: 1x1
+  int rm_lo, rm_hi;       // vertical taps present (r = t - j + 1); 1x1 uses rm_lo = rm_hi = 1
+  int cpad;               // UMMA N per stacked tap == accumulator block width in columns
+  int ring;               // accumulator blocks in TMEM (blk_stride = cpad)
+  int max_stack;          // taps stacked in one instruction: floor(256 / cpad)
+  int tiles_per_chunk;    // weight tiles per 64-channel chunk in the packed tensor (3 for 3x3, 1 for 1x1)
+  int b_r0, b_row0;       // B-map coordinates of tap rm_lo / of the first output-channel row of this launch
+  int G;                  // input rows per weight pass
+  int w_resident;
+  int a_slots, b_stages;
+  uint32_t a_slot_bytes, a_tx_bytes, b_tile_bytes, b_tx_bytes;
+  uint32_t a_off, b_off, stage_off, bias_off, bar_off;   // shared memory carve-up (from the 1024B-aligned base)
+  // epilogue
+  int ngroups, group_c, cout_store, ups;
+  int relu, out_f32, has_relu_copy;
+  int bias_count;
+  const float* bias;
+  const __half* residual;
+  int res_cstride, res_coff;
+  unsigned long long* trace;
+};
+
+// ---------------------------------------------------------------- extra PTX (bulk tensor store, x32 TMEM load)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+struct RowsSegment {
+  int n, x0, y0, y1;
+};
+
+// Walks the contiguous output-row range of this CTA as (image, strip, row-range) segments.
+struct RowsWalker {
+  long long lin, lin_end;
+  int H, strips;
+  __device__ RowsWalker(const ConvRowsParams& p) {
+    lin = static_cast<long long>(blockIdx.x) * p.rows_per_cta;
+    lin_end = lin + p.rows_per_cta;
+    if (lin_end > p.total_rows) lin_end = p.total_rows;
+    H = p.H; strips = p.strips;
+  }
+  __device__ bool next(RowsSegment& s) {
+    if (lin >= lin_end) return false;
+    const long long col = lin / H;          // (n * strips + strip)
+    s.y0 = static_cast<int>(lin - col * H);
+    s.n = static_cast<int>(col / strips);
+    s.x0 = static_cast<int>(col % strips) * kRowsTileW;
+    long long left = lin_end - lin;
+    s.y1 = (s.y0 + left > H) ? H : static_cast<int>(s.y0 + left);
+    lin += s.y1 - s.y0;
+    return true;
+  }
+};
+
+__global__ void __launch_bounds__(kRowsThreads, 1)
+conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* a_smem = smem + p.a_off;
+  uint8_t* b_smem = smem + p.b_off;
+  uint8_t* st_smem = smem + p.stage_off;
+  float* bias_smem = reinterpret_cast<float*>(smem + p.bias_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+  uint64_t* a_full = bars;                       // [a_slots]
+  uint64_t* a_empty = a_full + p.a_slots;        // [a_slots]
+  uint64_t* b_full = a_empty + p.a_slots;        // [b_stages] (resident: [1])
+  uint64_t* b_empty = b_full + p.b_stages;       // [b_stages]
+  uint64_t* acc_full = b_empty + p.b_stages;     // [ring]
+  uint64_t* acc_empty = acc_full + kRowsMaxRing; // [ring]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kRowsMaxRing);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a);
+    tma_prefetch_desc(&maps.b);
+    tma_prefetch_desc(&maps.out[0]);
+    for (int i = 0; i < p.a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < kRowsMaxRing; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 3) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (warp >= 4) {
+    for (int i = threadIdx.x - 128; i < 256; i += 256) bias_smem[i] = (p.bias && i < p.bias_count) ? p.bias[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int t_lo_off = p.rm_lo - 1;   // first input row of a segment = y0 + t_lo_off
+  const int t_hi_off = p.rm_hi - 2;   // last input row           = y1 + t_hi_off
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ A producer: one input row x one 64ch chunk per item
+    if (elect_one()) {
+      RowsWalker walk(p);
+      RowsSegment sg;
+      int slot = 0; uint32_t phase = 0;
+      while (walk.next(sg)) {
+        const int t_first = sg.y0 + t_lo_off, t_last = sg.y1 + t_hi_off;
+        for (int tg = t_first; tg <= t_last; tg += p.G) {
+          const int gcur = (t_last + 1 - tg < p.G) ? (t_last + 1 - tg) : p.G;
+          for (int c = 0; c < p.n_chunks; ++c) {
+            for (int g = 0; g < gcur; ++g) {
+              mbar_wait(&a_empty[slot], phase ^ 1);
+              mbar_arrive_expect_tx(&a_full[slot], p.a_tx_bytes);
+              tma_load_4d(a_smem + static_cast<size_t>(slot) * p.a_slot_bytes, &maps.a, &a_full[slot], c * 64,
+                          sg.x0 - p.halo, tg + g, sg.n);
+              if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ B producer
+    if (elect_one()) {
+      if (p.w_resident) {
+        const int tiles = p.n_chunks * p.n_s;
+        mbar_arrive_expect_tx(&b_full[0], p.b_tx_bytes * static_cast<uint32_t>(tiles));
+        for (int i = 0; i < tiles; ++i)
+          tma_load_4d(b_smem + static_cast<size_t>(i) * p.b_tile_bytes, &maps.b, &b_full[0], 0, p.b_row0, p.b_r0,
+                      (i / p.n_s) * p.tiles_per_chunk + p.s_list[i % p.n_s]);
+      } else {
+        RowsWalker walk(p);
+        RowsSegment sg;
+        int stage = 0; uint32_t phase = 0;
+        while (walk.next(sg)) {
+          const int t_first = sg.y0 + t_lo_off, t_last = sg.y1 + t_hi_off;
+          for (int tg = t_first; tg <= t_last; tg += p.G) {
+            for (int c = 0; c < p.n_chunks; ++c) {
+              for (int si = 0; si < p.n_s; ++si) {
+                mbar_wait(&b_empty[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&b_full[stage], p.b_tx_bytes);
+                tma_load_4d(b_smem + static_cast<size_t>(stage) * p.b_tile_bytes, &maps.b, &b_full[stage], 0, p.b_row0,
+                            p.b_r0, c * p.tiles_per_chunk + p.s_list[si]);
+                if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint64_t desc_tmpl = make_desc_sw128(0, 0);
+      const uint32_t d_lo = static_cast<uint32_t>(desc_tmpl), d_hi = static_cast<uint32_t>(desc_tmpl >> 32);
+      const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
+      // per-group instruction plan (private scratch of this thread in shared memory): for every input row g of the
+      // group, the UMMA "pieces" its stacked taps break into (ring wrap / N <= 256 / first touch of an output row).
+      // piece = {TMEM column, instruction descriptor, B byte offset >> 4, accumulate}
+      uint4* plan = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [8 rows][1 hdr + 3 + 4 pieces]
+      RowsWalker walk(p);
+      RowsSegment sg;
+      int a_slot = 0; uint32_t a_phase = 0;
+      int b_stage = 0; uint32_t b_phase = 0;
+      uint32_t q_seg = 0;                  // running index of the first output row of the segment
+      int it = 0;
+      if (p.w_resident) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
+      while (walk.next(sg)) {
+        const int t_first = sg.y0 + t_lo_off, t_last = sg.y1 + t_hi_off;
+        // accumulator block / use count of the output row fed by tap r = 0 of input row t (index q_seg + t + 1 - y0);
+        // tap r lands r blocks further.  Maintained incrementally (one division per segment).
+        uint32_t q_top = q_seg + static_cast<uint32_t>(t_first + 1 - sg.y0);
+        int blk_top = p.ring - 1 - static_cast<int>(q_top % static_cast<uint32_t>(p.ring));
+        uint32_t use_top = q_top / static_cast<uint32_t>(p.ring);
+        for (int tg = t_first; tg <= t_last; tg += p.G, ++it) {
+          const int gcur = (t_last + 1 - tg < p.G) ? (t_last + 1 - tg) : p.G;
+          if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 8 + 0] = clock64();
+          // ---- plan the group
+          for (int g = 0; g < gcur; ++g) {
+            const int t = tg + g;
+            int r_lo = t + 2 - sg.y1; if (r_lo < p.rm_lo) r_lo = p.rm_lo;     // taps landing on rows of the segment
+            int r_hi = t + 1 - sg.y0; if (r_hi > p.rm_hi) r_hi = p.rm_hi;
+            int blk = blk_top + r_lo; if (blk >= p.ring) blk -= p.ring;      // block of the row served by tap r_lo
+            // use count of that row: rows in a block past the wrap belong to the previous use
+            const uint32_t use = (blk_top + r_lo >= p.ring) ? use_top - 1u : use_top;
+            const bool ft = (r_lo == p.rm_lo);   // this input row initialises the accumulator of that output row
+            uint4* row_plan = plan + g * 8;
+            int n_norm = 0, n_first = 0;
+            int r = r_lo, bk = blk;
+            while (r <= r_hi) {
+              int cnt = r_hi - r + 1;
+              if (bk + cnt > p.ring) cnt = p.ring - bk;
+              if (cnt > p.max_stack) cnt = p.max_stack;
+              row_plan[1 + n_norm++] = make_uint4(static_cast<uint32_t>(bk * p.cpad), make_idesc_f16(kRowsTileW, cnt * p.cpad),
+                                                  static_cast<uint32_t>((r - p.rm_lo) * p.cpad) * 8u, 1u);
+              r += cnt; bk += cnt; if (bk >= p.ring) bk -= p.ring;
+            }
+            if (ft) {
+              row_plan[4 + n_first++] = make_uint4(static_cast<uint32_t>(blk * p.cpad), make_idesc_f16(kRowsTileW, p.cpad),
+                                                   static_cast<uint32_t>((r_lo - p.rm_lo) * p.cpad) * 8u, 0u);
+              r = r_lo + 1; bk = blk + 1; if (bk >= p.ring) bk -= p.ring;
+              while (r <= r_hi) {
+                int cnt = r_hi - r + 1;
+                if (bk + cnt > p.ring) cnt = p.ring - bk;
+                if (cnt > p.max_stack) cnt = p.max_stack;
+                row_plan[4 + n_first++] = make_uint4(static_cast<uint32_t>(bk * p.cpad), make_idesc_f16(kRowsTileW, cnt * p.cpad),
+                                                     static_cast<uint32_t>((r - p.rm_lo) * p.cpad) * 8u, 1u);
+                r += cnt; bk += cnt; if (bk >= p.ring) bk -= p.ring;
+              }
+            }
+            row_plan[0] = make_uint4(static_cast<uint32_t>(n_norm), static_cast<uint32_t>(n_first),
+                                     static_cast<uint32_t>(blk), (use & 1u) ^ 1u);
+            // next input row: its r = 0 output row is one further
+            if (--blk_top < 0) { blk_top = p.ring - 1; ++use_top; }
+          }
+          if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 8 + 1] = clock64();
+          const int a_slot0 = a_slot; const uint32_t a_phase0 = a_phase;
+          for (int c = 0; c < p.n_chunks; ++c) {
+            const int ksteps = (c == p.n_chunks - 1) ? p.ksteps_last : 4;
+            for (int si = 0; si < p.n_s; ++si) {
+              uint32_t b_tile;
+              if (p.w_resident) {
+                b_tile = b_base + static_cast<uint32_t>(c * p.n_s + si) * p.b_tile_bytes;
+              } else {
+                mbar_wait(&b_full[b_stage], b_phase);
+                tc_fence_after();
+                b_tile = b_base + static_cast<uint32_t>(b_stage) * p.b_tile_bytes;
+              }
+              const uint32_t b_lo0 = d_lo + (b_tile >> 4);
+              const uint32_t s_off = static_cast<uint32_t>(p.s_list[si]) * 128u;
+              int lin_slot = a_slot0 + c * gcur;      // slots of this chunk's rows: a_slot0 + c * gcur + g (mod a_slots)
+              uint32_t ph = a_phase0;
+              while (lin_slot >= p.a_slots) { lin_slot -= p.a_slots; ph ^= 1; }
+              for (int g = 0; g < gcur; ++g) {
+                const uint4* row_plan = plan + g * 8;
+                const uint4 hdr = row_plan[0];
+                const bool first_pass = (c == 0 && si == 0 && hdr.y != 0);
+                // pieces of this row into registers (on the first pass the k = 0 step uses the first-touch list)
+                uint4 pn[3], pf[4];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) pn[i] = row_plan[1 + i];
+                if (first_pass) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) pf[i] = row_plan[4 + i];
+                }
+                if (si == 0) {
+                  mbar_wait(&a_full[lin_slot], ph);
+                  tc_fence_after();
+                  if (p.trace && blockIdx.x == 0 && it < 64 && c == 0 && g == 0) p.trace[it * 8 + 2] = clock64();
+                }
+                if (first_pass) {
+                  // the block of the new output row is (re)initialised now: its previous user must have been drained
+                  mbar_wait(&acc_empty[hdr.z], hdr.w);
+                  tc_fence_after();
+                }
+                const uint32_t a_lo = d_lo + ((a_base + static_cast<uint32_t>(lin_slot) * p.a_slot_bytes + s_off) >> 4);
+                int k0 = 0;
+                if (first_pass) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    if (i < static_cast<int>(hdr.y))
+                      umma_f16(tmem_base + pf[i].x, desc_from(a_lo, d_hi), desc_from(b_lo0 + pf[i].z, d_hi), pf[i].y, pf[i].w);
+                  k0 = 1;
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                  if (i < static_cast<int>(hdr.x)) {
+                    const uint32_t b_lo = b_lo0 + pn[i].z;
+                    const uint32_t d_col = tmem_base + pn[i].x;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      if (k >= k0 && k < ksteps)
+                        umma_f16(d_col, desc_from(a_lo + 2u * k, d_hi), desc_from(b_lo + 2u * k, d_hi), pn[i].y, 1u);
+                  }
+                }
+                if (si == p.n_s - 1) umma_commit(&a_empty[lin_slot]);
+                if (++lin_slot == p.a_slots) { lin_slot = 0; ph ^= 1; }
+              }
+              if (!p.w_resident) {
+                umma_commit(&b_empty[b_stage]);
+                if (++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
+              }
+            }
+          }
+          // advance the A ring past this group
+          {
+            a_slot = a_slot0 + p.n_chunks * gcur; a_phase = a_phase0;
+            while (a_slot >= p.a_slots) { a_slot -= p.a_slots; a_phase ^= 1; }
+          }
+          // output rows completed by this group: j = t + 1 - rm_hi for t in the group, clipped to the segment
+          for (int g = 0; g < gcur; ++g) {
+            const int j = tg + g + 1 - p.rm_hi;
+            if (j < sg.y0 || j >= sg.y1) continue;
+            const uint32_t q = q_seg + static_cast<uint32_t>(j - sg.y0);
+            umma_commit(&acc_full[p.ring - 1 - static_cast<int>(q % static_cast<uint32_t>(p.ring))]);
+          }
+          if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 8 + 3] = clock64();
+        }
+        q_seg += static_cast<uint32_t>(sg.y1 - sg.y0);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: 2 sets of 4 warps, rows alternate
+    const int wq = warp & 3;                       // TMEM lane quarter
+    const int eset = (warp - 4) >> 2;              // rows with (q & 1) == eset
+    uint8_t* stage = st_smem + static_cast<size_t>(warp - 4) * 4096;   // one 4 KB staging row set per warp
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
+    RowsWalker walk(p);
+    RowsSegment sg;
+    uint32_t q = 0;
+    int it = 0;
+    const uint32_t ring = static_cast<uint32_t>(p.ring);
+    while (walk.next(sg)) {
+      for (int j = sg.y0; j < sg.y1; ++j, ++q, ++it) {
+        if ((q & 1u) != static_cast<uint32_t>(eset)) continue;
+        const int blk = p.ring - 1 - static_cast<int>(q % ring);
+        const uint32_t use = q / ring;
+        const bool tr = p.trace && blockIdx.x == 0 && it < 64 && wq == 0 && lane == 0;
+        if (tr) p.trace[it * 8 + 4] = clock64();
+        mbar_wait(&acc_full[blk], use & 1u);
+        tc_fence_after();
+        if (tr) p.trace[it * 8 + 5] = clock64();
+        const int x_in = sg.x0 + wq * 32 + lane;              // input-grid pixel of this thread (TMEM lane)
+        const int x_warp = sg.x0 + wq * 32;
+        const uint32_t t_blk = t_lane + static_cast<uint32_t>(blk * p.cpad);
+        uint8_t* row = stage + lane * 128;
+        // the single staging set may be rewritten once the previous store of this warp has finished reading it
+        auto begin_rows = [&]() {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        };
+        auto end_rows = [&](const CUtensorMap* m, int c0) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(m, stage, c0, x_warp, j, sg.n);
+            tma_store_commit();
+          }
+        };
+        const int n_pass = p.has_relu_copy ? 2 : 1;    // pass 1 re-reads TMEM and writes the fp16 relu(primary) copy
+        for (int g = 0; g < p.ngroups; ++g) {
+          for (int pass = 0; pass < n_pass; ++pass) {
+            const bool f32_rows = p.out_f32 && pass == 0;
+            const bool do_relu = p.relu || pass == 1;
+            const CUtensorMap* omap = (pass == 0) ? &maps.out[g] : &maps.out_relu;
+            for (int cb = 0; cb < p.cout_store; cb += 32) {
+              uint32_t v[32];
+              __syncwarp();
+              tmem_ld_32x32(t_blk + static_cast<uint32_t>(g * p.group_c + cb), v);
+              uint4 rv[4];
+              const bool has_res = (p.residual != nullptr) && (x_in < p.W);
+              if (has_res) {
+                const size_t opix = (static_cast<size_t>(sg.n) * p.H + j) * p.W + x_in;
+                const __half* rp = p.residual + opix * p.res_cstride + p.res_coff + cb;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  rv[i] = (cb + i * 8 < p.cout_store) ? __ldg(reinterpret_cast<const uint4*>(rp + i * 8))
+                                                      : make_uint4(0, 0, 0, 0);
+              }
+              tmem_ld_wait();
+              float* f = reinterpret_cast<float*>(v);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] += bias_smem[cb + i];
+              if (has_res) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const __half2* rh = reinterpret_cast<const __half2*>(&rv[i]);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 r2 = __half22float2(rh[e]);
+                    f[i * 8 + 2 * e] += r2.x; f[i * 8 + 2 * e + 1] += r2.y;
+                  }
+                }
+              }
+              if (do_relu) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+              }
+              if (f32_rows) {
+                // 32 fp32 channels fill one 128-byte staging row
+                begin_rows();
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  *reinterpret_cast<float4*>(row + ((i ^ (lane & 7)) << 4)) =
+                      make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                end_rows(omap, cb);
+              } else {
+                // 32 fp16 channels fill half a staging row; flush every 64 channels
+                const int sub = (cb >> 5) & 1;
+                if (sub == 0) begin_rows();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  uint4 pk; __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) ph[e] = __floats2half2_rn(f[i * 8 + 2 * e], f[i * 8 + 2 * e + 1]);
+                  *reinterpret_cast<uint4*>(row + (((sub * 4 + i) ^ (lane & 7)) << 4)) = pk;
+                }
+                if (sub == 1 || cb + 32 >= p.cout_store) end_rows(omap, cb & ~63);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (tr) p.trace[it * 8 + 6] = clock64();
+        if (lane == 0) mbar_arrive(&acc_empty[blk]);
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace dd

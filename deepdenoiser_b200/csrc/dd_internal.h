@@ -16,9 +16,9 @@ struct dd_ctx {
   int sm_count = 0;
   size_t max_smem_optin = 0;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime
-  int conv_shift_mode = 0;       // see conv_tc.cuh (validated on hardware; 2 is the all-aligned fallback)
-  int conv_rows = 0;             // 0 = auto
-  int conv_b_stages = 0;         // 0 = auto
+  int conv_rows = 0;             // cap on input rows per weight pass (0 = auto), see conv_rows.cuh
+  int conv_force_stream = 0;     // debug: stream weights even when they would fit in shared memory
+  unsigned long long* conv_trace = nullptr;  // debug: device buffer [64][8] of clock64 stamps (CTA 0)
   std::atomic<int64_t> launches{0};
 };
 

@@ -56,6 +56,9 @@ int dd_ctx_destroy(dd_ctx* ctx);
 int dd_ctx_sm_count(const dd_ctx* ctx);
 /* Tuning / experiment knobs ("conv_shift_mode", "conv_rows", ...). Returns DD_ERR_INVALID if unknown. */
 int dd_ctx_set_option(dd_ctx* ctx, const char* name, int value);
+/* Debug: device buffer of 64*8 uint64 that CTA 0 of every subsequent tensor-core conv launch fills with clock64()
+ * stamps of its pipeline roles (NULL disables).  Used by tools/probe_conv.py to see where tile time goes. */
+int dd_ctx_set_trace_buffer(dd_ctx* ctx, void* device_buffer);
 /* Number of kernels this library has launched through `ctx` (bench.py's gpu_launches). */
 int64_t dd_ctx_launch_count(const dd_ctx* ctx);
 

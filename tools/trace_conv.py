@@ -1,0 +1,40 @@
+"""Per-tile pipeline timeline of the tcgen05 conv kernel (CTA 0): where do the cycles of a tile go?"""
+import sys, os
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from deepdenoiser_b200 import _lib
+ctx = _lib.Context(0)
+dev = ctx.device
+
+def run(n, h, w, cin, cout, ks, iters=3):
+  x = (torch.randn(n, h, w, cin, device=dev) * 0.5).half()
+  wt = torch.randn(ks, ks, cin, cout) * 0.05
+  wp = ctx.pack_conv_weights(wt, torch.float16)
+  bias = torch.zeros((cout + 15) // 16 * 16, device=dev)
+  y = torch.empty(n, h, w, (cout + 7) // 8 * 8, dtype=torch.float16, device=dev)
+  xd, yd = _lib.desc(x), _lib.desc(y, cout, 0)
+  trace = torch.zeros(64 * 8 + 64, dtype=torch.int64, device=dev)
+  for _ in range(iters):
+    ctx.conv2d(xd, wp, bias, ks, yd, relu=True)
+  ctx.set_trace_buffer(trace)
+  ctx.conv2d(xd, wp, bias, ks, yd, relu=True)
+  torch.cuda.synchronize()
+  ctx.set_trace_buffer(None)
+  full = trace.cpu()
+  t = full[:512].view(64, 8)
+  mm = [int(v) for v in full[512:572] if int(v) != 0]
+  print('  per-MMA issue deltas (group 6):', [mm[i + 1] - mm[i] for i in range(len(mm) - 1)])
+  base = int(t[0, 0])
+  print("conv %dx%dx%d %d->%d k%d: rows = tile iteration; cycles relative to start" % (n, h, w, cin, cout, ks))
+  print("  it | grp:enter        -   a_full   issued | epi:enter  t_full    done | mma_busy epi_busy  period  (mma: per group of G rows; epi: per row)")
+  prev = None
+  for i in range(12):
+    r = [int(v) - base for v in t[i]]
+    period = (r[3] - prev) if prev is not None else 0
+    prev = r[3]
+    print("  %2d | %9d %8d %8d %8d | %9d %8d %8d | %8d %8d %8d" % (i, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[3] - r[2], r[6] - r[5], period))
+
+run(1, 1080, 1920, 64, 64, 3)
+run(1, 1080, 1920, 128, 64, 3)
+run(1, 540, 960, 96, 96, 3)
+run(1, 1080, 1920, 64, 25, 1)
