@@ -22,8 +22,8 @@
 //   epilogue       4 warps: tcgen05.ld -> +bias (+residual) -> ReLU -> fp16/fp32 -> 128B-swizzled staging row in
 //                  shared memory -> one TMA store per 32 pixels x 64 channels (full-line writes; the tensor map
 //                  clips channels / pixels outside the view, sub-pixel views implement the pixel shuffle).
-//   warps          0: A producer  1: B producer  2: MMA issuer  3: TMEM allocator  4-11: epilogue (two sets of
-//                  four warps, one TMEM lane quarter each, alternating output rows)
+//   warps          0-7: epilogue (two sets of four warps, one TMEM lane quarter each, alternating output rows)
+//                  8: A producer  9: B producer  10: TMEM allocator  11: MMA issuer
 //   grid           persistent: the N*strips*H output rows are split into gridDim contiguous ranges (+-1 row).
 #pragma once
 #include "dd_ptx.cuh"
@@ -138,7 +138,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&maps.a);
     tma_prefetch_desc(&maps.b);
     tma_prefetch_desc(&maps.out[0]);
@@ -147,12 +147,12 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
     for (int i = 0; i < kRowsMaxRing; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_mbar_init();
   }
-  if (warp == 3) {
+  if (warp == 10) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  if (warp >= 4) {
-    for (int i = threadIdx.x - 128; i < 256; i += 256) bias_smem[i] = (p.bias && i < p.bias_count) ? p.bias[i] : 0.f;
+  if (warp < 8) {
+    for (int i = threadIdx.x; i < 256; i += 256) bias_smem[i] = (p.bias && i < p.bias_count) ? p.bias[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -162,7 +162,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
   const int t_lo_off = p.rm_lo - 1;   // first input row of a segment = y0 + t_lo_off
   const int t_hi_off = p.rm_hi - 2;   // last input row           = y1 + t_hi_off
 
-  if (warp == 0) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ A producer: one input row x one 64ch chunk per item
     if (elect_one()) {
       RowsWalker walk(p);
@@ -184,7 +184,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------------ B producer
     if (elect_one()) {
       if (p.w_resident) {
@@ -213,8 +213,9 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
         }
       }
     }
-  } else if (warp == 2) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 11) {
+    // ------------------------------------------------------------------ MMA issuer (highest warp id: the scheduler
+    // prefers it over the epilogue warp sharing its sub-partition)
     if (elect_one()) {
       const uint64_t desc_tmpl = make_desc_sw128(0, 0);
       const uint32_t d_lo = static_cast<uint32_t>(desc_tmpl), d_hi = static_cast<uint32_t>(desc_tmpl >> 32);
@@ -364,11 +365,11 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
         q_seg += static_cast<uint32_t>(sg.y1 - sg.y0);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ------------------------------------------------------------------ epilogue: 2 sets of 4 warps, rows alternate
     const int wq = warp & 3;                       // TMEM lane quarter
-    const int eset = (warp - 4) >> 2;              // rows with (q & 1) == eset
-    uint8_t* stage = st_smem + static_cast<size_t>(warp - 4) * 4096;   // one 4 KB staging row set per warp
+    const int eset = warp >> 2;                    // rows with (q & 1) == eset
+    uint8_t* stage = st_smem + static_cast<size_t>(warp) * 4096;   // one 4 KB staging row set per warp
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
     RowsWalker walk(p);
     RowsSegment sg;
@@ -477,7 +478,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 3) {
+  if (warp == 10) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

@@ -13,7 +13,7 @@ def run(n, h, w, cin, cout, ks, iters=3):
   bias = torch.zeros((cout + 15) // 16 * 16, device=dev)
   y = torch.empty(n, h, w, (cout + 7) // 8 * 8, dtype=torch.float16, device=dev)
   xd, yd = _lib.desc(x), _lib.desc(y, cout, 0)
-  trace = torch.zeros(64 * 8 + 64, dtype=torch.int64, device=dev)
+  trace = torch.zeros(64 * 8 + 128, dtype=torch.int64, device=dev)
   for _ in range(iters):
     ctx.conv2d(xd, wp, bias, ks, yd, relu=True)
   ctx.set_trace_buffer(trace)
@@ -22,8 +22,8 @@ def run(n, h, w, cin, cout, ks, iters=3):
   ctx.set_trace_buffer(None)
   full = trace.cpu()
   t = full[:512].view(64, 8)
-  mm = [int(v) for v in full[512:572] if int(v) != 0]
-  print('  per-MMA issue deltas (group 6):', [mm[i + 1] - mm[i] for i in range(len(mm) - 1)])
+  mm = [(int(full[576 + i]), int(full[512 + i])) for i in range(60) if int(full[512 + i]) != 0]
+  print('  group 6 stamps (tag:+cycles since previous):', ' '.join('%d:+%d' % (mm[i][0], mm[i][1] - mm[i - 1][1]) for i in range(1, len(mm))))
   base = int(t[0, 0])
   print("conv %dx%dx%d %d->%d k%d: rows = tile iteration; cycles relative to start" % (n, h, w, cin, cout, ks))
   print("  it | grp:enter        -   a_full   issued | epi:enter  t_full    done | mma_busy epi_busy  period  (mma: per group of G rows; epi: per row)")
