@@ -132,20 +132,22 @@ def conv_roofline(arch, feats_dev, steps):
   records = []
   orig_conv, orig_t2 = net._conv, arch.ctx.conv2d_transpose2x2
 
-  def timed(flops, fn):
+  def timed(flops, fn, label=""):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     fn()
     e1.record()
-    records.append((e0, e1, flops))
+    records.append((e0, e1, flops, label))
 
   def conv(var, x, y, relu=False, residual=None, y_relu=None):
     px = x.t.shape[0] * x.t.shape[1] * x.t.shape[2]
     timed(2.0 * px * var.ksize * var.ksize * var.cin * var.cout,
-          lambda: orig_conv(var, x, y, relu=relu, residual=residual, y_relu=y_relu))
+          lambda: orig_conv(var, x, y, relu=relu, residual=residual, y_relu=y_relu),
+          "%dx%d %d->%d @%dx%dx%d" % (var.ksize, var.ksize, var.cin, var.cout, x.t.shape[0], x.t.shape[1], x.t.shape[2]))
 
   def t2(xd, wp, bias, yd, relu=False):
-    timed(2.0 * xd.n * xd.h * xd.w * 4 * xd.c * yd.c, lambda: orig_t2(xd, wp, bias, yd, relu=relu))
+    timed(2.0 * xd.n * xd.h * xd.w * 4 * xd.c * yd.c, lambda: orig_t2(xd, wp, bias, yd, relu=relu),
+          "T2x2 %d->%d @%dx%dx%d" % (xd.c, yd.c, xd.n, xd.h, xd.w))
 
   net._conv, arch.ctx.conv2d_transpose2x2 = conv, t2
   try:
@@ -154,8 +156,15 @@ def conv_roofline(arch, feats_dev, steps):
     torch.cuda.synchronize()
   finally:
     net._conv, arch.ctx.conv2d_transpose2x2 = orig_conv, orig_t2
-  ms = sum(e0.elapsed_time(e1) for e0, e1, _ in records)
-  flops = sum(f for _, _, f in records)
+  ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in records)
+  flops = sum(f for _, _, f, _ in records)
+  if os.environ.get("DD_BENCH_LAYERS"):
+    agg = {}
+    for e0, e1, f, label in records:
+      a = agg.setdefault(label, [0, 0.0, 0.0])
+      a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += f
+    for label, (n, t, f) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+      print("  %-34s n=%3d  %8.3f ms/step  %7.1f TFLOP/s" % (label, n // steps, t / steps, f / t / 1e9), file=sys.stderr)
   return flops / steps, ms / steps, len(records) // steps
 
 

@@ -189,7 +189,7 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
   p.a_slot_bytes = static_cast<uint32_t>(round_up(static_cast<int>(p.a_tx_bytes), 1024));
   p.b_tile_bytes = static_cast<uint32_t>(n_r * p.cpad) * 128u;
   p.b_tx_bytes = p.b_tile_bytes;
-  const size_t fixed = 32768 /*staging*/ + 1024 /*bias*/ + 2048 /*barriers + MMA plan*/;
+  const size_t fixed = 32768 /*staging*/ + 1024 /*bias*/ + 3072 /*barriers + MMA plans*/;
   const size_t avail = ctx->max_smem_optin - 1024 /*alignment slack*/ - fixed;
   const size_t w_total = static_cast<size_t>(p.n_chunks) * p.n_s * p.b_tile_bytes;
   size_t b_bytes;
@@ -222,7 +222,7 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
   p.stage_off = p.b_off + static_cast<uint32_t>(round_up(static_cast<int>(b_bytes), 1024));
   p.bias_off = p.stage_off + 32768;
   p.bar_off = p.bias_off + 1024;
-  const size_t smem = 1024 + p.bar_off + 2048;
+  const size_t smem = 1024 + p.bar_off + 3072;
 
   // epilogue
   p.ngroups = L.ngroups; p.group_c = L.group_c; p.cout_store = L.cout; p.ups = L.ups;

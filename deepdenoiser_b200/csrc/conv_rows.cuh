@@ -217,13 +217,73 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
     // ------------------------------------------------------------------ MMA issuer (highest warp id: the scheduler
     // prefers it over the epilogue warp sharing its sub-partition)
     if (elect_one()) {
+      // Single issuing thread: scalar integer code on the critical path of the tensor pipe (one UMMA of N = 192
+      // lasts 96 cycles), so the row loop avoids divisions, parameter loads and recomputation: the UMMA "pieces"
+      // a row breaks into (ring wrap / N <= 256 / first touch of an output row) are tabulated once per block index.
+      //   piece = {TMEM column, instruction descriptor, B offset >> 4, accumulate};  row plan = hdr + 3 normal + 4 first-touch
       const uint64_t desc_tmpl = make_desc_sw128(0, 0);
       const uint32_t d_lo = static_cast<uint32_t>(desc_tmpl), d_hi = static_cast<uint32_t>(desc_tmpl >> 32);
       const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
-      // per-group instruction plan (private scratch of this thread in shared memory): for every input row g of the
-      // group, the UMMA "pieces" its stacked taps break into (ring wrap / N <= 256 / first touch of an output row).
-      // piece = {TMEM column, instruction descriptor, B byte offset >> 4, accumulate}
-      uint4* plan = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [8 rows][1 hdr + 3 + 4 pieces]
+      uint4* plan = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [8 rows of a group][8]
+      uint4* table = plan + 64;                                                         // [ring blocks][8], full tap range
+      const int ring = p.ring, rm_lo = p.rm_lo, rm_hi = p.rm_hi, n_s = p.n_s, n_chunks = p.n_chunks, a_slots = p.a_slots;
+      const uint32_t a_slot_bytes = p.a_slot_bytes, b_tile_bytes = p.b_tile_bytes;
+      const uint32_t s_off0 = static_cast<uint32_t>(p.s_list[0]) * 8u, s_off1 = static_cast<uint32_t>(p.s_list[1]) * 8u,
+                     s_off2 = static_cast<uint32_t>(p.s_list[2]) * 8u;                   // shifts in descriptor units
+
+      auto build_plan = [&](uint4* row_plan, int blk, uint32_t use, int r_lo, int r_hi) {
+        const bool ft = (r_lo == rm_lo);   // this input row initialises the accumulator of the row served by tap r_lo
+        int n_norm = 0, n_first = 0;
+        int r = r_lo, bk = blk;
+        while (r <= r_hi) {
+          int cnt = r_hi - r + 1;
+          if (bk + cnt > ring) cnt = ring - bk;
+          if (cnt > p.max_stack) cnt = p.max_stack;
+          row_plan[1 + n_norm++] = make_uint4(static_cast<uint32_t>(bk * p.cpad), make_idesc_f16(kRowsTileW, cnt * p.cpad),
+                                              static_cast<uint32_t>((r - rm_lo) * p.cpad) * 8u, 1u);
+          r += cnt; bk += cnt; if (bk >= ring) bk -= ring;
+        }
+        if (ft) {
+          row_plan[4 + n_first++] = make_uint4(static_cast<uint32_t>(blk * p.cpad), make_idesc_f16(kRowsTileW, p.cpad),
+                                               static_cast<uint32_t>((r_lo - rm_lo) * p.cpad) * 8u, 0u);
+          r = r_lo + 1; bk = blk + 1; if (bk >= ring) bk -= ring;
+          while (r <= r_hi) {
+            int cnt = r_hi - r + 1;
+            if (bk + cnt > ring) cnt = ring - bk;
+            if (cnt > p.max_stack) cnt = p.max_stack;
+            row_plan[4 + n_first++] = make_uint4(static_cast<uint32_t>(bk * p.cpad), make_idesc_f16(kRowsTileW, cnt * p.cpad),
+                                                 static_cast<uint32_t>((r - rm_lo) * p.cpad) * 8u, 1u);
+            r += cnt; bk += cnt; if (bk >= ring) bk -= ring;
+          }
+        }
+        row_plan[0] = make_uint4(static_cast<uint32_t>(n_norm), static_cast<uint32_t>(n_first), static_cast<uint32_t>(blk),
+                                 (use & 1u) ^ 1u);
+      };
+      // issues the UMMAs of one (input row, chunk, shift): k-steps x pieces, operands already resident
+      auto issue = [&](const uint4& hdr, const uint4 (&pn)[3], const uint4 (&pf)[4], bool first_pass, uint32_t a_lo,
+                       uint32_t b_lo0, int ksteps) {
+        int k0 = 0;
+        if (first_pass) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < static_cast<int>(hdr.y))
+              umma_f16(tmem_base + pf[i].x, desc_from(a_lo, d_hi), desc_from(b_lo0 + pf[i].z, d_hi), pf[i].y, pf[i].w);
+          k0 = 1;
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if (i < static_cast<int>(hdr.x)) {
+            const uint32_t b_lo = b_lo0 + pn[i].z;
+            const uint32_t d_col = tmem_base + pn[i].x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k >= k0 && k < ksteps)
+                umma_f16(d_col, desc_from(a_lo + 2u * k, d_hi), desc_from(b_lo + 2u * k, d_hi), pn[i].y, 1u);
+          }
+        }
+      };
+
+      for (int bk = 0; bk < ring; ++bk) build_plan(table + bk * 8, bk, 0u, rm_lo, rm_hi);
       RowsWalker walk(p);
       RowsSegment sg;
       int a_slot = 0; uint32_t a_phase = 0;
@@ -235,132 +295,136 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
         const int t_first = sg.y0 + t_lo_off, t_last = sg.y1 + t_hi_off;
         // accumulator block / use count of the output row fed by tap r = 0 of input row t (index q_seg + t + 1 - y0);
         // tap r lands r blocks further.  Maintained incrementally (one division per segment).
-        uint32_t q_top = q_seg + static_cast<uint32_t>(t_first + 1 - sg.y0);
-        int blk_top = p.ring - 1 - static_cast<int>(q_top % static_cast<uint32_t>(p.ring));
-        uint32_t use_top = q_top / static_cast<uint32_t>(p.ring);
-        for (int tg = t_first; tg <= t_last; tg += p.G, ++it) {
-          const int gcur = (t_last + 1 - tg < p.G) ? (t_last + 1 - tg) : p.G;
-          if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 8 + 0] = clock64();
-          // ---- plan the group
-          for (int g = 0; g < gcur; ++g) {
-            const int t = tg + g;
-            int r_lo = t + 2 - sg.y1; if (r_lo < p.rm_lo) r_lo = p.rm_lo;     // taps landing on rows of the segment
-            int r_hi = t + 1 - sg.y0; if (r_hi > p.rm_hi) r_hi = p.rm_hi;
-            int blk = blk_top + r_lo; if (blk >= p.ring) blk -= p.ring;      // block of the row served by tap r_lo
-            // use count of that row: rows in a block past the wrap belong to the previous use
-            const uint32_t use = (blk_top + r_lo >= p.ring) ? use_top - 1u : use_top;
-            const bool ft = (r_lo == p.rm_lo);   // this input row initialises the accumulator of that output row
-            uint4* row_plan = plan + g * 8;
-            int n_norm = 0, n_first = 0;
-            int r = r_lo, bk = blk;
-            while (r <= r_hi) {
-              int cnt = r_hi - r + 1;
-              if (bk + cnt > p.ring) cnt = p.ring - bk;
-              if (cnt > p.max_stack) cnt = p.max_stack;
-              row_plan[1 + n_norm++] = make_uint4(static_cast<uint32_t>(bk * p.cpad), make_idesc_f16(kRowsTileW, cnt * p.cpad),
-                                                  static_cast<uint32_t>((r - p.rm_lo) * p.cpad) * 8u, 1u);
-              r += cnt; bk += cnt; if (bk >= p.ring) bk -= p.ring;
+        const uint32_t q_top0 = q_seg + static_cast<uint32_t>(t_first + 1 - sg.y0);
+        int blk_top = ring - 1 - static_cast<int>(q_top0 % static_cast<uint32_t>(ring));
+        uint32_t use_top = q_top0 / static_cast<uint32_t>(ring);
+        if (p.G == 1) {
+          // ---------------- one input row at a time (weights resident, or a single-row weight pass)
+          for (int t = t_first; t <= t_last; ++t, ++it) {
+            const bool tr = p.trace && blockIdx.x == 0 && it < 64;
+            if (tr) p.trace[it * 8 + 0] = clock64();
+            int r_lo = t + 2 - sg.y1; if (r_lo < rm_lo) r_lo = rm_lo;     // taps landing on rows of the segment
+            int r_hi = t + 1 - sg.y0; if (r_hi > rm_hi) r_hi = rm_hi;
+            int blk = blk_top + r_lo; uint32_t use = use_top;
+            if (blk >= ring) { blk -= ring; use -= 1u; }                  // block / use of the row served by tap r_lo
+            const uint4* row_plan;
+            if (r_lo == rm_lo && r_hi == rm_hi) {
+              row_plan = table + blk * 8;
+            } else {
+              build_plan(plan, blk, use, r_lo, r_hi);
+              row_plan = plan;
             }
-            if (ft) {
-              row_plan[4 + n_first++] = make_uint4(static_cast<uint32_t>(blk * p.cpad), make_idesc_f16(kRowsTileW, p.cpad),
-                                                   static_cast<uint32_t>((r_lo - p.rm_lo) * p.cpad) * 8u, 0u);
-              r = r_lo + 1; bk = blk + 1; if (bk >= p.ring) bk -= p.ring;
-              while (r <= r_hi) {
-                int cnt = r_hi - r + 1;
-                if (bk + cnt > p.ring) cnt = p.ring - bk;
-                if (cnt > p.max_stack) cnt = p.max_stack;
-                row_plan[4 + n_first++] = make_uint4(static_cast<uint32_t>(bk * p.cpad), make_idesc_f16(kRowsTileW, cnt * p.cpad),
-                                                     static_cast<uint32_t>((r - p.rm_lo) * p.cpad) * 8u, 1u);
-                r += cnt; bk += cnt; if (bk >= p.ring) bk -= p.ring;
+            const uint4 hdr = row_plan[0];
+            uint4 pn[3], pf[4];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) pn[i] = row_plan[1 + i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pf[i] = row_plan[4 + i];
+            const bool initialises = (r_lo == rm_lo);
+            for (int c = 0; c < n_chunks; ++c) {
+              const int ksteps = (c == n_chunks - 1) ? p.ksteps_last : 4;
+              mbar_wait(&a_full[a_slot], a_phase);
+              if (c == 0 && initialises) mbar_wait(&acc_empty[blk], (use & 1u) ^ 1u);   // previous user drained
+              tc_fence_after();
+              if (tr && c == 0) p.trace[it * 8 + 2] = clock64();
+              const uint32_t a_lo0 = d_lo + ((a_base + static_cast<uint32_t>(a_slot) * a_slot_bytes) >> 4);
+              for (int si = 0; si < n_s; ++si) {
+                uint32_t b_tile;
+                if (p.w_resident) {
+                  b_tile = b_base + static_cast<uint32_t>(c * n_s + si) * b_tile_bytes;
+                } else {
+                  mbar_wait(&b_full[b_stage], b_phase);
+                  tc_fence_after();
+                  b_tile = b_base + static_cast<uint32_t>(b_stage) * b_tile_bytes;
+                }
+                const uint32_t s_off = (si == 0) ? s_off0 : ((si == 1) ? s_off1 : s_off2);
+                issue(hdr, pn, pf, initialises && c == 0 && si == 0, a_lo0 + s_off, d_lo + (b_tile >> 4), ksteps);
+                if (!p.w_resident) {
+                  umma_commit(&b_empty[b_stage]);
+                  if (++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
+                }
+              }
+              umma_commit(&a_empty[a_slot]);
+              if (++a_slot == a_slots) { a_slot = 0; a_phase ^= 1; }
+            }
+            // output row completed by this input row: the one served by tap rm_hi, if it belongs to the segment
+            {
+              const int j = t + 1 - rm_hi;
+              if (j >= sg.y0 && j < sg.y1) {
+                int blk_done = blk_top + rm_hi; if (blk_done >= ring) blk_done -= ring;
+                umma_commit(&acc_full[blk_done]);
               }
             }
-            row_plan[0] = make_uint4(static_cast<uint32_t>(n_norm), static_cast<uint32_t>(n_first),
-                                     static_cast<uint32_t>(blk), (use & 1u) ^ 1u);
-            // next input row: its r = 0 output row is one further
-            if (--blk_top < 0) { blk_top = p.ring - 1; ++use_top; }
+            if (--blk_top < 0) { blk_top = ring - 1; ++use_top; }
+            if (tr) p.trace[it * 8 + 3] = clock64();
           }
-          if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 8 + 1] = clock64();
-          const int a_slot0 = a_slot; const uint32_t a_phase0 = a_phase;
-          for (int c = 0; c < p.n_chunks; ++c) {
-            const int ksteps = (c == p.n_chunks - 1) ? p.ksteps_last : 4;
-            for (int si = 0; si < p.n_s; ++si) {
-              uint32_t b_tile;
-              if (p.w_resident) {
-                b_tile = b_base + static_cast<uint32_t>(c * p.n_s + si) * p.b_tile_bytes;
-              } else {
+        } else {
+          // ---------------- groups of G input rows per weight pass (streamed weights)
+          for (int tg = t_first; tg <= t_last; tg += p.G, ++it) {
+            const int gcur = (t_last + 1 - tg < p.G) ? (t_last + 1 - tg) : p.G;
+            const bool tr = p.trace && blockIdx.x == 0 && it < 64;
+            if (tr) p.trace[it * 8 + 0] = clock64();
+            {
+              int bt = blk_top; uint32_t ut = use_top;
+              for (int g = 0; g < gcur; ++g) {
+                const int t = tg + g;
+                int r_lo = t + 2 - sg.y1; if (r_lo < rm_lo) r_lo = rm_lo;
+                int r_hi = t + 1 - sg.y0; if (r_hi > rm_hi) r_hi = rm_hi;
+                int blk = bt + r_lo; uint32_t use = ut;
+                if (blk >= ring) { blk -= ring; use -= 1u; }
+                build_plan(plan + g * 8, blk, use, r_lo, r_hi);
+                if (--bt < 0) { bt = ring - 1; ++ut; }
+              }
+            }
+            const int a_slot0 = a_slot; const uint32_t a_phase0 = a_phase;
+            for (int c = 0; c < n_chunks; ++c) {
+              const int ksteps = (c == n_chunks - 1) ? p.ksteps_last : 4;
+              for (int si = 0; si < n_s; ++si) {
                 mbar_wait(&b_full[b_stage], b_phase);
                 tc_fence_after();
-                b_tile = b_base + static_cast<uint32_t>(b_stage) * p.b_tile_bytes;
-              }
-              const uint32_t b_lo0 = d_lo + (b_tile >> 4);
-              const uint32_t s_off = static_cast<uint32_t>(p.s_list[si]) * 128u;
-              int lin_slot = a_slot0 + c * gcur;      // slots of this chunk's rows: a_slot0 + c * gcur + g (mod a_slots)
-              uint32_t ph = a_phase0;
-              while (lin_slot >= p.a_slots) { lin_slot -= p.a_slots; ph ^= 1; }
-              for (int g = 0; g < gcur; ++g) {
-                const uint4* row_plan = plan + g * 8;
-                const uint4 hdr = row_plan[0];
-                const bool first_pass = (c == 0 && si == 0 && hdr.y != 0);
-                // pieces of this row into registers (on the first pass the k = 0 step uses the first-touch list)
-                uint4 pn[3], pf[4];
+                const uint32_t b_lo0 = d_lo + ((b_base + static_cast<uint32_t>(b_stage) * b_tile_bytes) >> 4);
+                const uint32_t s_off = (si == 0) ? s_off0 : ((si == 1) ? s_off1 : s_off2);
+                int lin_slot = a_slot0 + c * gcur;      // slots of this chunk's rows: a_slot0 + c * gcur + g (mod a_slots)
+                uint32_t ph = a_phase0;
+                while (lin_slot >= a_slots) { lin_slot -= a_slots; ph ^= 1; }
+                for (int g = 0; g < gcur; ++g) {
+                  const uint4* row_plan = plan + g * 8;
+                  const uint4 hdr = row_plan[0];
+                  const bool first_pass = (c == 0 && si == 0 && hdr.y != 0);
+                  uint4 pn[3], pf[4];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) pn[i] = row_plan[1 + i];
-                if (first_pass) {
+                  for (int i = 0; i < 3; ++i) pn[i] = row_plan[1 + i];
 #pragma unroll
                   for (int i = 0; i < 4; ++i) pf[i] = row_plan[4 + i];
-                }
-                if (si == 0) {
-                  mbar_wait(&a_full[lin_slot], ph);
-                  tc_fence_after();
-                  if (p.trace && blockIdx.x == 0 && it < 64 && c == 0 && g == 0) p.trace[it * 8 + 2] = clock64();
-                }
-                if (first_pass) {
-                  // the block of the new output row is (re)initialised now: its previous user must have been drained
-                  mbar_wait(&acc_empty[hdr.z], hdr.w);
-                  tc_fence_after();
-                }
-                const uint32_t a_lo = d_lo + ((a_base + static_cast<uint32_t>(lin_slot) * p.a_slot_bytes + s_off) >> 4);
-                int k0 = 0;
-                if (first_pass) {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i)
-                    if (i < static_cast<int>(hdr.y))
-                      umma_f16(tmem_base + pf[i].x, desc_from(a_lo, d_hi), desc_from(b_lo0 + pf[i].z, d_hi), pf[i].y, pf[i].w);
-                  k0 = 1;
-                }
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                  if (i < static_cast<int>(hdr.x)) {
-                    const uint32_t b_lo = b_lo0 + pn[i].z;
-                    const uint32_t d_col = tmem_base + pn[i].x;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                      if (k >= k0 && k < ksteps)
-                        umma_f16(d_col, desc_from(a_lo + 2u * k, d_hi), desc_from(b_lo + 2u * k, d_hi), pn[i].y, 1u);
+                  if (si == 0) {
+                    mbar_wait(&a_full[lin_slot], ph);
+                    if (first_pass) mbar_wait(&acc_empty[hdr.z], hdr.w);    // previous user of the new row's block drained
+                    tc_fence_after();
+                    if (tr && c == 0 && g == 0) p.trace[it * 8 + 2] = clock64();
                   }
+                  const uint32_t a_lo = d_lo + ((a_base + static_cast<uint32_t>(lin_slot) * a_slot_bytes) >> 4) + s_off;
+                  issue(hdr, pn, pf, first_pass, a_lo, b_lo0, ksteps);
+                  if (si == n_s - 1) umma_commit(&a_empty[lin_slot]);
+                  if (++lin_slot == a_slots) { lin_slot = 0; ph ^= 1; }
                 }
-                if (si == p.n_s - 1) umma_commit(&a_empty[lin_slot]);
-                if (++lin_slot == p.a_slots) { lin_slot = 0; ph ^= 1; }
-              }
-              if (!p.w_resident) {
                 umma_commit(&b_empty[b_stage]);
                 if (++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
               }
             }
+            // advance the A ring past this group
+            a_slot = a_slot0 + n_chunks * gcur; a_phase = a_phase0;
+            while (a_slot >= a_slots) { a_slot -= a_slots; a_phase ^= 1; }
+            // output rows completed by this group: tap rm_hi of each input row, if that row belongs to the segment
+            for (int g = 0; g < gcur; ++g) {
+              const int j = tg + g + 1 - rm_hi;
+              if (j >= sg.y0 && j < sg.y1) {
+                int blk_done = blk_top + rm_hi; if (blk_done >= ring) blk_done -= ring;
+                umma_commit(&acc_full[blk_done]);
+              }
+              if (--blk_top < 0) { blk_top = ring - 1; ++use_top; }
+            }
+            if (tr) p.trace[it * 8 + 3] = clock64();
           }
-          // advance the A ring past this group
-          {
-            a_slot = a_slot0 + p.n_chunks * gcur; a_phase = a_phase0;
-            while (a_slot >= p.a_slots) { a_slot -= p.a_slots; a_phase ^= 1; }
-          }
-          // output rows completed by this group: j = t + 1 - rm_hi for t in the group, clipped to the segment
-          for (int g = 0; g < gcur; ++g) {
-            const int j = tg + g + 1 - p.rm_hi;
-            if (j < sg.y0 || j >= sg.y1) continue;
-            const uint32_t q = q_seg + static_cast<uint32_t>(j - sg.y0);
-            umma_commit(&acc_full[p.ring - 1 - static_cast<int>(q % static_cast<uint32_t>(p.ring))]);
-          }
-          if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 8 + 3] = clock64();
         }
         q_seg += static_cast<uint32_t>(sg.y1 - sg.y0);
       }

@@ -10,14 +10,14 @@ if [[ $what == all || $what == tests ]]; then
   timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -5 gpurun_out/smoke.log
 fi
 if [[ $what == all || $what == bench ]]; then
-  timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
-  tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
+  DD_BENCH_LAYERS=1 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+  tail -40 gpurun_out/bench.err; cat gpurun_out/bench.json
 fi
 if [[ $what == all || $what == ncu ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 400 --csv \
       --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
   tail -2 gpurun_out/ncu_launch.log
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 30 -c 3 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_rows -s 2 -c 3 \
       -o gpurun_out/prof_conv -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
   tail -2 gpurun_out/ncu_full.log
   ls -la gpurun_out
