@@ -126,7 +126,7 @@ def run_reference(args, arch_json, weights, config):
 
 # ---------------------------------------------------------------------------------------------- CUDA arm
 def conv_roofline(arch, feats_dev, steps):
-  """Device time of the dominant kernel (conv_tc_kernel: every 3x3 / 1x1 / transposed convolution of the pass) measured
+  """Device time of the dominant kernel (conv_rows_kernel: every 3x3 / 1x1 / transposed convolution of the pass) measured
   with CUDA events around each launch on the launching stream, and the algorithmic FLOPs of those launches."""
   net = arch.network
   records = []
@@ -252,8 +252,9 @@ def run_cuda(args, arch_json, weights, config):
             "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic", "config": cfg,
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)", "achieved": achieved,
-                         "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+            "roofline": {"bound": "tensor", "kernel": "conv_rows_kernel (tcgen05 implicit-GEMM conv, all conv launches of the frame)",
+                         "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+                         "traffic": 4.239e9, "traffic_launch": "ncu --set full, 3x3 64->64 @8x1080x1920: dram read 2.160 GB + write 2.080 GB vs 4.247 GB algorithmic (profiles/r01_ncu_conv_rows_full.csv)",
                          "launches_per_step": conv_launches, "ms_per_step_in_kernel": conv_ms, "peak_source": pk["source"]},
             "clocks": sampler.summary()}
     if world == 1 and not args.no_cpu_baseline:
