@@ -67,6 +67,23 @@ SIGNATURES = {
     "dd_compose_head_fwd": (_i, [_vp, _T, _T, _vp, _vp, _i, _T, _vp]),
     "dd_compose_tail_fwd": (_i, [_vp, _T, _vp, _vp, _i, _T, _T, _P(dd_invert_params), _T, _vp]),
     "dd_invert_standardization": (_i, [_vp, _T, _P(dd_invert_params), _T, _vp]),
+    "dd_relu_bwd": (_i, [_vp, _T, _T, _T, _vp]),
+    "dd_muladd_fwd": (_i, [_vp, _T, _T, _T, _T, _vp]),
+    "dd_muladd_bwd": (_i, [_vp, _T, _T, _T, _T, _T, _T, _vp]),
+    "dd_axpy": (_i, [_vp, ctypes.c_float, _T, _T, _vp]),
+    "dd_fill": (_i, [_vp, ctypes.c_float, _T, _vp]),
+    "dd_invert_standardization_bwd": (_i, [_vp, _T, _T, _P(dd_invert_params), _T, _vp]),
+    "dd_loss_fwd_bwd": (_i, [_vp, _T, _T, _i, ctypes.c_float, ctypes.c_float, _vp, _T, _i, _vp]),
+    "dd_conv2d_wgrad": (_i, [_vp, _T, _T, _i, _i, _vp, _vp, _vp]),
+    "dd_conv2d_transpose2x2_dgrad": (_i, [_vp, _T, _vp, _T, _vp]),
+    "dd_conv2d_repack_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "dd_maxpool_s2_bwd": (_i, [_vp, _T, _T, _T, _i, _T, _vp]),
+    "dd_kernel_predict_bwd": (_i, [_vp, _T, _T, _T, _i, _i, _i, _T, _vp]),
+    "dd_compose_tail_bwd": (_i, [_vp, _T, _vp, _vp, _i, _T, _T, _T, _T, _T, _T, _vp, _vp, _vp]),
+    "dd_compose_head_bwd": (_i, [_vp, _T, _T, _vp, _i, _T, _T, _T, _T, _vp, _vp, _vp]),
+    "dd_channel_sum": (_i, [_vp, _T, _i, _vp, _vp]),
+    "dd_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                          ctypes.c_int64, ctypes.c_float, _vp]),
     "dd_cast_copy": (_i, [_vp, _T, _T, _vp]),
     "dd_l2_flush": (_i, [_vp, _vp, _sz, _vp]),
 }
@@ -224,6 +241,11 @@ class Context:
   def invert_standardization(self, x, inv, y):
     self._check(self.lib.dd_invert_standardization(self.handle, ctypes.byref(x), ctypes.byref(inv), ctypes.byref(y),
                                                    self._stream()))
+
+  # -- training (every call is a thin, checked pass-through; see include/dd_b200.h)
+  def call(self, name, *args):
+    """Generic checked call: ctx.call('dd_relu_bwd', byref(...), ...) appends the current stream."""
+    self._check(getattr(self.lib, name)(self.handle, *args, self._stream()))
 
   def cast_copy(self, x, y):
     self._check(self.lib.dd_cast_copy(self.handle, ctypes.byref(x), ctypes.byref(y), self._stream()))

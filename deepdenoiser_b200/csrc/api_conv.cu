@@ -26,22 +26,24 @@ struct ConvSimtParams {
   const float* bias;
   int cout, ksize, relu, has_res, has_yrelu;
   int ups, ay, ax;     // pixel shuffle for transposed 2x2 (ups == 2)
+  int x_ups, x_ay, x_ax;  // input read through a stride-2 sub-pixel lattice (input gradient of the transposed 2x2 conv)
+  int oh, ow;          // output grid (== input grid unless x_ups == 2)
 };
 
 constexpr int kSimtCob = 8;
 
 __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvSimtParams p) {
   const int cgroups = (p.cout + kSimtCob - 1) / kSimtCob;
-  const size_t total = static_cast<size_t>(p.x.n) * p.x.h * p.x.w * cgroups;
+  const size_t npix = static_cast<size_t>(p.x.n) * p.oh * p.ow;
+  const size_t total = npix * cgroups;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   // consecutive threads -> consecutive pixels (same channel group => weight loads are warp-uniform)
-  const size_t npix = static_cast<size_t>(p.x.n) * p.x.h * p.x.w;
   const int cg = static_cast<int>(idx / npix);
   const size_t pixel = idx % npix;
-  const int x0 = static_cast<int>(pixel % p.x.w);
-  const int y0 = static_cast<int>((pixel / p.x.w) % p.x.h);
-  const int n0 = static_cast<int>(pixel / (static_cast<size_t>(p.x.w) * p.x.h));
+  const int x0 = static_cast<int>(pixel % p.ow);
+  const int y0 = static_cast<int>((pixel / p.ow) % p.oh);
+  const int n0 = static_cast<int>(pixel / (static_cast<size_t>(p.ow) * p.oh));
   const int co0 = cg * kSimtCob;
   const int cin = p.x.c;
   const int pad = (p.ksize - 1) / 2;
@@ -51,11 +53,13 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvSimtParams p) 
   for (int i = 0; i < kSimtCob; ++i) acc[i] = 0.f;
 
   for (int r = 0; r < p.ksize; ++r) {
-    const int yy = y0 + r - pad;
-    if (yy < 0 || yy >= p.x.h) continue;
+    int yy = y0 + r - pad;
+    if (yy < 0 || yy >= p.oh) continue;
+    if (p.x_ups == 2) yy = 2 * yy + p.x_ay;
     for (int s = 0; s < p.ksize; ++s) {
-      const int xx = x0 + s - pad;
-      if (xx < 0 || xx >= p.x.w) continue;
+      int xx = x0 + s - pad;
+      if (xx < 0 || xx >= p.ow) continue;
+      if (p.x_ups == 2) xx = 2 * xx + p.x_ax;
       const size_t ipix = p.x.pix(n0, yy, xx);
       const float* wt = p.w + (static_cast<size_t>(r * p.ksize + s) * p.cout + co0) * cin;
       for (int c = 0; c < cin; ++c) {
@@ -298,7 +302,11 @@ static int launch_conv_simt(dd_ctx* ctx, const dd_tensor* x, const float* w, con
   p.w = w; p.bias = bias; p.cout = cout; p.ksize = ksize;
   p.relu = (flags & DD_CONV_RELU) ? 1 : 0;
   p.ups = ups; p.ay = ay; p.ax = ax;
-  const size_t total = static_cast<size_t>(x->n) * x->h * x->w * ((cout + kSimtCob - 1) / kSimtCob);
+  p.x_ups = 1; p.oh = x->h; p.ow = x->w;
+  if (ups == -2) {   // input read through sub-pixel (ay, ax) of a 2x finer grid; output on the coarse grid
+    p.ups = 1; p.x_ups = 2; p.x_ay = ay; p.x_ax = ax; p.oh = x->h / 2; p.ow = x->w / 2;
+  }
+  const size_t total = static_cast<size_t>(x->n) * p.oh * p.ow * ((cout + kSimtCob - 1) / kSimtCob);
   const unsigned blocks = static_cast<unsigned>((total + 127) / 128);
   conv_simt_kernel<<<blocks, 128, 0, stream>>>(p);
   DD_LAUNCH_CHECK(ctx);
@@ -529,6 +537,22 @@ int dd_conv2d_transpose3x3_fwd(dd_ctx* ctx, const dd_tensor* x, const void* cons
     L.s_mask = (px == 0) ? 3 : 2;                 // s = dx + 1: {0,1} or {1}
     L.rm_lo = (py == 0) ? 0 : 1; L.rm_hi = 1;     // r = dy + 1
     int rc = launch_conv_rows(ctx, L, s);
+    if (rc) return rc;
+  }
+  return DD_OK;
+}
+
+
+/* dx = conv2d_transpose_2x2_s2^T (dz): dx[i,j,c] = sum_{a,b,o} dz[2i+a,2j+b,o] W[a,b,o,c] - exact fp32 path.
+ * w_dgrad: [sub-pixel][cin][cout] fp32 (dd_conv2d_repack_f32 with transposed = 1). */
+int dd_conv2d_transpose2x2_dgrad(dd_ctx* ctx, const dd_tensor* dz, const float* w_dgrad, const dd_tensor* dx, void* stream) {
+  DD_CHECK_ARG(ctx && w_dgrad && tensor_ok(dz) && tensor_ok(dx), "bad argument");
+  DD_CHECK_ARG(dz->dtype == DD_F32 && dx->dtype == DD_F32, "exact path only");
+  DD_CHECK_ARG(dz->n == dx->n && dz->h == 2 * dx->h && dz->w == 2 * dx->w, "transpose2x2_dgrad: dz must be 2x dx");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int sp = 0; sp < 4; ++sp) {
+    const float* w = w_dgrad + static_cast<size_t>(sp) * dx->c * dz->c;
+    int rc = launch_conv_simt(ctx, dz, w, nullptr, 1, dx->c, 0, sp == 0 ? nullptr : dx, dx, nullptr, -2, sp >> 1, sp & 1, s);
     if (rc) return rc;
   }
   return DD_OK;

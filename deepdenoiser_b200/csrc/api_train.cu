@@ -1,0 +1,657 @@
+// C-ABI: training-side kernels — loss (LossDifference.py:15-36 + Training.py:116-243), the backward of every forward
+// op (what tf.train.AdamOptimizer.minimize derives by autodiff, Training.py:700-702) and the TF-form Adam update.
+// This is the EXACT (fp32 accumulate, CUDA-core) training path of round 1: correctness first, every kernel is
+// parity-tested against torch-autograd of the oracle; the tensor-core wgrad is future work.
+#include <string.h>
+
+#include "dd_internal.h"
+
+namespace dd {
+
+inline unsigned nblocks(size_t total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
+inline bool same_dims(const dd_tensor* a, const dd_tensor* b) {
+  return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c;
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise
+struct Ewise { View a, b, c, out, out2, out3; int op; float alpha; };
+enum { EW_RELU_MASK = 0, EW_MULADD = 1, EW_MULADD_BWD = 2, EW_AXPY = 3, EW_FILL = 4, EW_INVERT_BWD = 5 };
+struct EwiseInv { int use_log1p; float mean, variance, sqrt_var; };
+
+__global__ void __launch_bounds__(256) ewise_kernel(const Ewise p, const EwiseInv q) {
+  const size_t total = static_cast<size_t>(p.out.n) * p.out.h * p.out.w * p.out.c;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ch = static_cast<int>(idx % p.out.c);
+  const size_t pix = idx / p.out.c;
+  switch (p.op) {
+    case EW_RELU_MASK:      // out = a * [b > 0]        (dz = dy . relu'(y))
+      p.out.store(pix, ch, p.b.load(pix, ch) > 0.f ? p.a.load(pix, ch) : 0.f);
+      break;
+    case EW_MULADD:         // out = a * (b + c)        (lighting = color * (direct + indirect), Training.py:420-428)
+      p.out.store(pix, ch, p.a.load(pix, ch) * (p.b.load(pix, ch) + p.c.load(pix, ch)));
+      break;
+    case EW_MULADD_BWD: {   // g = out: a' += g (b + c), b' += g a, c' += g a   (accumulated into out2/out3 and `out` is g)
+      // here: a,b,c forward operands; out = g (read); out2 = da (accumulate), out3 = db (accumulate), alpha unused;
+      // dc is accumulated by the caller with a second AXPY of db's increment -> we write the same increment to both
+      const float g = p.out.load(pix, ch);
+      const float av = p.a.load(pix, ch), bv = p.b.load(pix, ch), cv = p.c.load(pix, ch);
+      p.out2.store(pix, ch, p.out2.load(pix, ch) + g * (bv + cv));
+      p.out3.store(pix, ch, g * av);          // increment for BOTH direct and indirect
+      break;
+    }
+    case EW_AXPY:           // out += alpha * a
+      p.out.store(pix, ch, p.out.load(pix, ch) + p.alpha * p.a.load(pix, ch));
+      break;
+    case EW_FILL:
+      p.out.store(pix, ch, p.alpha);
+      break;
+    case EW_INVERT_BWD: {   // y = signed_expm1(x*sqrt(var)+mean): out = a * dy/dx at x = b      (Architecture.py:48-55)
+      float x = p.b.load(pix, ch);
+      float d = 1.f;
+      if (q.variance != 1.f) { x *= q.sqrt_var; d *= q.sqrt_var; }
+      if (q.mean != 0.f) x += q.mean;
+      if (q.use_log1p) d *= expf(fabsf(x));
+      p.out.store(pix, ch, p.a.load(pix, ch) * d);
+      break;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ loss
+struct LossParams {
+  View pred, target, dpred;
+  int kind;          // 0 DIFFERENCE 1 ABSOLUTE 2 SMOOTH_ABSOLUTE 3 SQUARED 4 SMAPE
+  float weight;      // loss_weight * scale_factor / (N*h*w): d(loss)/d(channel-summed difference of one pixel)
+  float epsilon;
+  int accumulate;    // dpred += instead of =
+  float* loss;       // scalar accumulator (atomicAdd of weight * sum)
+};
+
+__device__ __forceinline__ void loss_elem(int kind, float p, float t, float eps, float& val, float& grad) {
+  const float d = p - t;
+  switch (kind) {
+    case 0: val = d; grad = 1.f; break;
+    case 1: val = fabsf(d); grad = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f); break;
+    case 2: {
+      const float a = fabsf(d);
+      if (a < 1.f) { val = 0.5f * a * a; grad = d; } else { val = a - 0.5f; grad = (d > 0.f) ? 1.f : -1.f; }
+      break;
+    }
+    case 3: val = d * d; grad = 2.f * d; break;
+    default: {  // SMAPE: |p-t| / (|p| + |t| + eps)
+      const float a = fabsf(d), den = fabsf(p) + fabsf(t) + eps;
+      val = a / den;
+      const float sd = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+      const float sp = (p > 0.f) ? 1.f : ((p < 0.f) ? -1.f : 0.f);
+      grad = sd / den - a * sp / (den * den);
+      break;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
+  const size_t total = static_cast<size_t>(p.pred.n) * p.pred.h * p.pred.w;
+  const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float sum = 0.f;
+  if (pix < total) {
+    for (int c = 0; c < p.pred.c; ++c) {
+      float v, g;
+      loss_elem(p.kind, p.pred.load(pix, c), p.target.load(pix, c), p.epsilon, v, g);
+      sum += v;
+      if (p.dpred.ptr) {
+        const float prev = p.accumulate ? p.dpred.load(pix, c) : 0.f;
+        p.dpred.store(pix, c, prev + p.weight * g);
+      }
+    }
+  }
+  // block reduction -> one atomic per block
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+    if (threadIdx.x == 0) atomicAdd(p.loss, p.weight * v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ conv wgrad (exact)
+// dW[r,s,c,o] += sum_{n,y,x} x[n, y+r-pad, x+s-pad, c] * dz[n,y,x,o]      (TF layout [kh,kw,cin,cout])
+// db[o]       += sum dz[n,y,x,o]
+// transposed 2x2 (ups == 2): dz pixel of (x-grid pixel (i,j), sub-pixel (ay,ax)) is (2i+ay, 2j+ax); layout [a,b,cout,cin]
+// One block = one 8x16 pixel tile; thread (c_i, o_i) owns a CB x OB patch of (cin, cout) pairs for all taps.
+constexpr int kWgTileH = 8, kWgTileW = 16, kWgThreads = 256, kWgMaxC = 32;
+struct WgradParams {
+  View x, dz;
+  float* dw; float* db;
+  int ksize, cin, cout, c0, o0;    // this launch covers cin [c0, c0+32) x cout [o0, o0+32)
+  int ups, ay, ax, transposed_layout;
+  int tiles_x, tiles_y;
+};
+
+__global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const WgradParams p) {
+  extern __shared__ float sm[];
+  const int pad = (p.ksize - 1) / 2;
+  const int TH = kWgTileH + 2 * pad, TW = kWgTileW + 2 * pad;
+  float* sx = sm;                                   // [TH][TW][32]
+  float* sdz = sm + TH * TW * kWgMaxC;              // [8][16][32]
+  const int n = blockIdx.z;
+  const int y0 = blockIdx.y * kWgTileH, x0 = blockIdx.x * kWgTileW;
+  const int cin_n = min(kWgMaxC, p.cin - p.c0), cout_n = min(kWgMaxC, p.cout - p.o0);
+  for (int i = threadIdx.x; i < TH * TW * kWgMaxC; i += kWgThreads) {
+    const int c = i % kWgMaxC, px = (i / kWgMaxC) % TW, py = i / (kWgMaxC * TW);
+    const int yy = y0 + py - pad, xx = x0 + px - pad;
+    float v = 0.f;
+    if (c < cin_n && yy >= 0 && yy < p.x.h && xx >= 0 && xx < p.x.w) v = p.x.load(p.x.pix(n, yy, xx), p.c0 + c);
+    sx[i] = v;
+  }
+  for (int i = threadIdx.x; i < kWgTileH * kWgTileW * kWgMaxC; i += kWgThreads) {
+    const int o = i % kWgMaxC, px = (i / kWgMaxC) % kWgTileW, py = i / (kWgMaxC * kWgTileW);
+    const int yy = y0 + py, xx = x0 + px;
+    float v = 0.f;
+    if (o < cout_n && yy < p.x.h && xx < p.x.w) {
+      const int zy = (p.ups == 2) ? 2 * yy + p.ay : yy, zx = (p.ups == 2) ? 2 * xx + p.ax : xx;
+      v = p.dz.load(p.dz.pix(n, zy, zx), p.o0 + o);
+    }
+    sdz[i] = v;
+  }
+  __syncthreads();
+  // thread -> (c, o-quad): 32 c x 8 groups of 4 o
+  const int c = threadIdx.x & 31, og = threadIdx.x >> 5;
+  for (int r = 0; r < p.ksize; ++r) {
+    for (int s = 0; s < p.ksize; ++s) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int py = 0; py < kWgTileH; ++py) {
+        for (int px = 0; px < kWgTileW; ++px) {
+          const float xv = sx[((py + r) * TW + px + s) * kWgMaxC + c];
+          const float4 dv = *reinterpret_cast<const float4*>(&sdz[(py * kWgTileW + px) * kWgMaxC + og * 4]);
+          acc[0] = fmaf(xv, dv.x, acc[0]); acc[1] = fmaf(xv, dv.y, acc[1]);
+          acc[2] = fmaf(xv, dv.z, acc[2]); acc[3] = fmaf(xv, dv.w, acc[3]);
+        }
+      }
+      if (c < cin_n) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int o = og * 4 + i;
+          if (o >= cout_n) continue;
+          const size_t tap = static_cast<size_t>(r) * p.ksize + s;
+          const size_t idx = p.transposed_layout ? (static_cast<size_t>(p.o0 + o)) * p.cin + p.c0 + c   // [cout][cin] of one tap
+                                                 : (tap * p.cin + p.c0 + c) * p.cout + p.o0 + o;
+          atomicAdd(p.dw + idx, acc[i]);
+        }
+      }
+    }
+  }
+  if (p.db && p.c0 == 0 && threadIdx.x < kWgMaxC && threadIdx.x < cout_n) {
+    float s = 0.f;
+    for (int i = 0; i < kWgTileH * kWgTileW; ++i) s += sdz[i * kWgMaxC + threadIdx.x];
+    atomicAdd(p.db + p.o0 + threadIdx.x, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ max-pool backward
+struct PoolBwdParams { View x, y, dy, dx; int ksize, pad_y, pad_x; };
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const PoolBwdParams p) {
+  // output-centric: route dy to the FIRST maximum of the window (TF MaxPoolGrad semantics), atomics because 3x3/s2 windows overlap
+  const size_t total = static_cast<size_t>(p.y.n) * p.y.h * p.y.w * p.y.c;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % p.y.c);
+  const size_t opix = idx / p.y.c;
+  const int ox = static_cast<int>(opix % p.y.w);
+  const int oy = static_cast<int>((opix / p.y.w) % p.y.h);
+  const int n = static_cast<int>(opix / (static_cast<size_t>(p.y.w) * p.y.h));
+  float m = -INFINITY; size_t arg = 0; bool found = false;
+  for (int r = 0; r < p.ksize; ++r) {
+    const int yy = 2 * oy - p.pad_y + r;
+    if (yy < 0 || yy >= p.x.h) continue;
+    for (int s = 0; s < p.ksize; ++s) {
+      const int xx = 2 * ox - p.pad_x + s;
+      if (xx < 0 || xx >= p.x.w) continue;
+      const size_t ip = p.x.pix(n, yy, xx);
+      const float v = p.x.load(ip, c);
+      if (!found || v > m) { m = v; arg = ip; found = true; }
+    }
+  }
+  if (found) {
+    float* dst = reinterpret_cast<float*>(p.dx.ptr) + arg * p.dx.cstride + p.dx.coff + c;
+    atomicAdd(dst, p.dy.load(opix, c));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel prediction backward
+// dlogits_k = p_k (G_k - sum_c g_c out_c),  G_k = sum_c g_c S_c[k],  p = softmax(logits)        (no gradient to the source: it is data)
+struct KpBwdParams { View src, logits, dout, dlogits; int K, F, ipt; };
+__device__ __forceinline__ int sym_idx(int i, int n) {
+  while (i < 0 || i >= n) i = (i < 0) ? (-i - 1) : (2 * n - i - 1);
+  return i;
+}
+__global__ void __launch_bounds__(128) kernel_predict_bwd_kernel(const KpBwdParams p) {
+  const size_t per_img = static_cast<size_t>(p.src.h) * p.src.w;
+  const size_t total = static_cast<size_t>(p.logits.n) * p.F * per_img;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int K = p.K, K2 = K * K, pad = (K - 1) / 2;
+  const size_t pi = idx % per_img;
+  const int bf = static_cast<int>(idx / per_img);
+  const int b = bf / p.F, f = bf % p.F;
+  const int img = ((b / p.ipt) * p.F + f) * p.ipt + (b % p.ipt);
+  const int y = static_cast<int>(pi / p.src.w), x = static_cast<int>(pi % p.src.w);
+  const size_t lpix = p.logits.pix(b, y, x);
+  const size_t opix = p.src.pix(img, y, x);
+  const int coff = f * K2;
+  const float g0 = p.dout.load(opix, 0), g1 = p.dout.load(opix, 1), g2 = p.dout.load(opix, 2);
+  float mx = -INFINITY;
+  for (int t = 0; t < K2; ++t) mx = fmaxf(mx, p.logits.load(lpix, coff + t));
+  float sum = 0.f, dot = 0.f;
+  for (int t = 0; t < K2; ++t) {
+    const float e = expf(p.logits.load(lpix, coff + t) - mx);
+    const int i = t / K, j = t - i * K;
+    const size_t sp = p.src.pix(img, sym_idx(y + i - pad, p.src.h), sym_idx(x + j - pad, p.src.w));
+    const float G = g0 * p.src.load(sp, 0) + g1 * p.src.load(sp, 1) + g2 * p.src.load(sp, 2);
+    sum += e; dot += e * G;
+  }
+  const float inv = 1.f / sum;
+  dot *= inv;     // sum_k p_k G_k = sum_c g_c out_c
+  for (int t = 0; t < K2; ++t) {
+    const float pk = expf(p.logits.load(lpix, coff + t) - mx) * inv;
+    const int i = t / K, j = t - i * K;
+    const size_t sp = p.src.pix(img, sym_idx(y + i - pad, p.src.h), sym_idx(x + j - pad, p.src.w));
+    const float G = g0 * p.src.load(sp, 0) + g1 * p.src.load(sp, 1) + g2 * p.src.load(sp, 2);
+    p.dlogits.store(lpix, coff + t, pk * (G - dot));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ compose backward
+constexpr int kCmpC = 32;
+struct ComposeTailBwdParams {
+  View t, small, large, dout, dt, dsmall, dlarge;   // dsmall / dlarge are ACCUMULATED (atomicAdd, fp32)
+  float w[kCmpC]; float b; int c_mid;
+  float* dw; float* db;                              // [c_mid], [1] accumulated
+};
+__global__ void __launch_bounds__(256) compose_tail_bwd_kernel(const ComposeTailBwdParams p) {
+  const size_t total = static_cast<size_t>(p.large.n) * p.large.h * p.large.w;
+  const size_t pixel = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float dwl[kCmpC];
+  float dbl = 0.f;
+#pragma unroll
+  for (int c = 0; c < kCmpC; ++c) dwl[c] = 0.f;
+  if (pixel < total) {
+    const int x0 = static_cast<int>(pixel % p.large.w);
+    const int y0 = static_cast<int>((pixel / p.large.w) % p.large.h);
+    const int n = static_cast<int>(pixel / (static_cast<size_t>(p.large.w) * p.large.h));
+    float a = p.b;
+    for (int c = 0; c < p.c_mid; ++c) a = fmaf(p.t.load(pixel, c), p.w[c], a);
+    const float ar = fmaxf(a, 0.f);
+    const float wgt = 1.f / (1.f + expf(-ar));
+    const size_t spix = p.small.pix(n, y0 >> 1, x0 >> 1);
+    const int yb = y0 & ~1, xb = x0 & ~1;
+    float dwgt = 0.f;
+    float* dl = reinterpret_cast<float*>(p.dlarge.ptr);
+    float* ds = reinterpret_cast<float*>(p.dsmall.ptr);
+    for (int c = 0; c < 3; ++c) {
+      const float g = p.dout.load(pixel, c);
+      const float low = 0.25f * (p.large.load(p.large.pix(n, yb, xb), c) + p.large.load(p.large.pix(n, yb, xb + 1), c) +
+                                 p.large.load(p.large.pix(n, yb + 1, xb), c) + p.large.load(p.large.pix(n, yb + 1, xb + 1), c));
+      const float su = p.small.load(spix, c);
+      dwgt += g * (su - low);
+      // out = large - wgt*low + wgt*su
+      atomicAdd(dl + pixel * p.dlarge.cstride + p.dlarge.coff + c, g);
+      const float dlow = -wgt * g * 0.25f;
+      atomicAdd(dl + p.large.pix(n, yb, xb) * p.dlarge.cstride + p.dlarge.coff + c, dlow);
+      atomicAdd(dl + p.large.pix(n, yb, xb + 1) * p.dlarge.cstride + p.dlarge.coff + c, dlow);
+      atomicAdd(dl + p.large.pix(n, yb + 1, xb) * p.dlarge.cstride + p.dlarge.coff + c, dlow);
+      atomicAdd(dl + p.large.pix(n, yb + 1, xb + 1) * p.dlarge.cstride + p.dlarge.coff + c, dlow);
+      atomicAdd(ds + spix * p.dsmall.cstride + p.dsmall.coff + c, wgt * g);
+    }
+    const float da = (a > 0.f) ? dwgt * wgt * (1.f - wgt) : 0.f;
+    for (int c = 0; c < p.c_mid; ++c) {
+      const float tv = p.t.load(pixel, c);
+      p.dt.store(pixel, c, da * p.w[c]);
+      dwl[c] = da * tv;
+    }
+    dbl = da;
+  }
+  // warp-reduce the parameter gradients, one atomic per warp
+  for (int c = 0; c < p.c_mid; ++c) {
+    float v = dwl[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(p.dw + c, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dbl += __shfl_xor_sync(0xffffffffu, dbl, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(p.db, dbl);
+}
+
+struct ComposeHeadBwdParams {
+  View small, large, y, dy, dsmall, dlarge;    // y = relu output of the head (mask), dy its gradient; dsmall/dlarge accumulated
+  float w[6 * kCmpC]; int c_mid;
+  float* dw; float* db;                        // [6][c_mid], [c_mid] accumulated
+};
+__global__ void __launch_bounds__(256) compose_head_bwd_kernel(const ComposeHeadBwdParams p) {
+  const size_t total = static_cast<size_t>(p.large.n) * p.large.h * p.large.w;
+  const size_t pixel = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = pixel < total;
+  float in[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float din[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  size_t spix = 0;
+  if (valid) {
+    const int x0 = static_cast<int>(pixel % p.large.w);
+    const int y0 = static_cast<int>((pixel / p.large.w) % p.large.h);
+    const int n = static_cast<int>(pixel / (static_cast<size_t>(p.large.w) * p.large.h));
+    spix = p.small.pix(n, y0 >> 1, x0 >> 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { in[c] = p.small.load(spix, c); in[3 + c] = p.large.load(pixel, c); }
+  }
+  for (int c = 0; c < p.c_mid; ++c) {
+    float dz = 0.f;
+    if (valid && p.y.load(pixel, c) > 0.f) dz = p.dy.load(pixel, c);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      din[k] = fmaf(dz, p.w[k * p.c_mid + c], din[k]);
+      float v = dz * in[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(p.dw + k * p.c_mid + c, v);
+    }
+    float v = dz;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(p.db + c, v);
+  }
+  if (valid) {
+    float* dl = reinterpret_cast<float*>(p.dlarge.ptr);
+    float* ds = reinterpret_cast<float*>(p.dsmall.ptr);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      atomicAdd(ds + spix * p.dsmall.cstride + p.dsmall.coff + c, din[c]);
+      atomicAdd(dl + pixel * p.dlarge.cstride + p.dlarge.coff + c, din[3 + c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ reductions / optimizer
+struct ChanSumParams { View x; float* out; int images_per_group; int groups; };
+// out[g][c] += sum over the images of group g and all pixels of x[.., c]   (embedding-row gradient: SourceEncoder broadcast bwd)
+__global__ void __launch_bounds__(256) channel_sum_kernel(const ChanSumParams p) {
+  const size_t per_group = static_cast<size_t>(p.images_per_group) * p.x.h * p.x.w;
+  const int g = blockIdx.y;
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per_group; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = static_cast<size_t>(g) * per_group + i;
+    for (int c = 0; c < p.x.c; ++c) acc[c] += p.x.load(pix, c);
+  }
+  for (int c = 0; c < p.x.c; ++c) {
+    float v = acc[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(p.out + g * p.x.c + c, v);
+  }
+}
+
+// tf.train.AdamOptimizer: lr_t = lr sqrt(1-b2^t)/(1-b1^t); theta -= lr_t m / (sqrt(v) + eps)
+__global__ void __launch_bounds__(256) adam_kernel(float* w, const float* g, float* m, float* v, size_t n, float lr_t, float b1,
+                                                   float b2, float eps, float gscale) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * gscale;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
+// device-side weight repack after an optimizer step (fp32 exact path): TF [kh,kw,cin,cout] -> [tap][cout][cin] (forward)
+// and [flipped tap][cin][cout] (input-gradient convolution: a conv cout -> cin with the spatially flipped kernel)
+__global__ void __launch_bounds__(256) repack_f32_kernel(const float* w, float* fwd, float* bwd, int k2, int cin, int cout,
+                                                         int transposed) {
+  const size_t total = static_cast<size_t>(k2) * cin * cout;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  if (transposed) {   // TF conv2d_transpose layout [sub-pixel][cout][cin]: forward uses it as is, dgrad needs [sub-pixel][cin][cout]
+    const int c = static_cast<int>(i % cin);
+    const int o = static_cast<int>((i / cin) % cout);
+    const int sp = static_cast<int>(i / (static_cast<size_t>(cout) * cin));
+    if (fwd) fwd[i] = w[i];
+    if (bwd) bwd[(static_cast<size_t>(sp) * cin + c) * cout + o] = w[i];
+    return;
+  }
+  const int o = static_cast<int>(i % cout);
+  const int c = static_cast<int>((i / cout) % cin);
+  const int t = static_cast<int>(i / (static_cast<size_t>(cout) * cin));
+  const float v = w[i];
+  if (fwd) fwd[(static_cast<size_t>(t) * cout + o) * cin + c] = v;
+  if (bwd) bwd[(static_cast<size_t>(k2 - 1 - t) * cin + c) * cout + o] = v;
+}
+
+}  // namespace dd
+
+using namespace dd;
+
+extern "C" {
+
+int dd_relu_bwd(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const dd_tensor* dz, void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(dy) && tensor_ok(y) && tensor_ok(dz) && same_dims(dy, y) && same_dims(dy, dz), "bad argument");
+  Ewise p; memset(&p, 0, sizeof(p)); EwiseInv q; memset(&q, 0, sizeof(q));
+  p.a = make_view(dy); p.b = make_view(y); p.out = make_view(dz); p.op = EW_RELU_MASK;
+  const size_t total = static_cast<size_t>(dy->n) * dy->h * dy->w * dy->c;
+  ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_muladd_fwd(dd_ctx* ctx, const dd_tensor* a, const dd_tensor* b, const dd_tensor* c, const dd_tensor* out, void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(a) && tensor_ok(b) && tensor_ok(c) && tensor_ok(out) && same_dims(a, b) && same_dims(a, c) &&
+                   same_dims(a, out), "bad argument");
+  Ewise p; memset(&p, 0, sizeof(p)); EwiseInv q; memset(&q, 0, sizeof(q));
+  p.a = make_view(a); p.b = make_view(b); p.c = make_view(c); p.out = make_view(out); p.op = EW_MULADD;
+  const size_t total = static_cast<size_t>(a->n) * a->h * a->w * a->c;
+  ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_muladd_bwd(dd_ctx* ctx, const dd_tensor* a, const dd_tensor* b, const dd_tensor* c, const dd_tensor* g,
+                  const dd_tensor* da_acc, const dd_tensor* dbc_inc, void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(a) && tensor_ok(b) && tensor_ok(c) && tensor_ok(g) && tensor_ok(da_acc) && tensor_ok(dbc_inc) &&
+                   same_dims(a, b) && same_dims(a, c) && same_dims(a, g) && same_dims(a, da_acc) && same_dims(a, dbc_inc),
+               "bad argument");
+  Ewise p; memset(&p, 0, sizeof(p)); EwiseInv q; memset(&q, 0, sizeof(q));
+  p.a = make_view(a); p.b = make_view(b); p.c = make_view(c); p.out = make_view(g); p.out2 = make_view(da_acc);
+  p.out3 = make_view(dbc_inc); p.op = EW_MULADD_BWD;
+  const size_t total = static_cast<size_t>(a->n) * a->h * a->w * a->c;
+  ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_axpy(dd_ctx* ctx, float alpha, const dd_tensor* x, const dd_tensor* y, void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(x) && tensor_ok(y) && same_dims(x, y), "bad argument");
+  Ewise p; memset(&p, 0, sizeof(p)); EwiseInv q; memset(&q, 0, sizeof(q));
+  p.a = make_view(x); p.out = make_view(y); p.op = EW_AXPY; p.alpha = alpha;
+  const size_t total = static_cast<size_t>(x->n) * x->h * x->w * x->c;
+  ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_fill(dd_ctx* ctx, float value, const dd_tensor* y, void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(y), "bad argument");
+  Ewise p; memset(&p, 0, sizeof(p)); EwiseInv q; memset(&q, 0, sizeof(q));
+  p.out = make_view(y); p.op = EW_FILL; p.alpha = value;
+  const size_t total = static_cast<size_t>(y->n) * y->h * y->w * y->c;
+  ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_invert_standardization_bwd(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* x, const dd_invert_params* inv,
+                                  const dd_tensor* dx, void* stream) {
+  DD_CHECK_ARG(ctx && inv && tensor_ok(dy) && tensor_ok(x) && tensor_ok(dx) && same_dims(dy, x) && same_dims(dy, dx), "bad argument");
+  Ewise p; memset(&p, 0, sizeof(p)); EwiseInv q;
+  q.use_log1p = inv->use_log1p; q.mean = inv->mean; q.variance = inv->variance; q.sqrt_var = sqrtf(inv->variance);
+  p.a = make_view(dy); p.b = make_view(x); p.out = make_view(dx); p.op = EW_INVERT_BWD;
+  const size_t total = static_cast<size_t>(dy->n) * dy->h * dy->w * dy->c;
+  ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_loss_fwd_bwd(dd_ctx* ctx, const dd_tensor* pred, const dd_tensor* target, int kind, float weight, float epsilon,
+                    float* loss_dev, const dd_tensor* dpred, int accumulate, void* stream) {
+  DD_CHECK_ARG(ctx && loss_dev && tensor_ok(pred) && tensor_ok(target) && same_dims(pred, target), "bad argument");
+  DD_CHECK_ARG(kind >= 0 && kind <= 4, "unknown loss difference %d", kind);
+  DD_CHECK_ARG(!dpred || (tensor_ok(dpred) && same_dims(pred, dpred)), "bad dpred");
+  LossParams p; memset(&p, 0, sizeof(p));
+  p.pred = make_view(pred); p.target = make_view(target);
+  if (dpred) p.dpred = make_view(dpred);
+  p.kind = kind; p.weight = weight; p.epsilon = epsilon; p.accumulate = accumulate; p.loss = loss_dev;
+  const size_t total = static_cast<size_t>(pred->n) * pred->h * pred->w;
+  loss_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_conv2d_wgrad(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int ksize, int transposed, float* dw, float* db,
+                    void* stream) {
+  DD_CHECK_ARG(ctx && dw && tensor_ok(x) && tensor_ok(dz), "bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int cin = x->c, cout = dz->c;
+  if (!transposed) {
+    DD_CHECK_ARG(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
+    DD_CHECK_ARG(x->n == dz->n && x->h == dz->h && x->w == dz->w, "wgrad: spatial dims differ");
+  } else {
+    DD_CHECK_ARG(ksize == 2 && dz->n == x->n && dz->h == 2 * x->h && dz->w == 2 * x->w, "transposed wgrad: dz must be 2x");
+  }
+  const int kk = transposed ? 1 : ksize;
+  const int pad = (kk - 1) / 2;
+  const size_t smem = (static_cast<size_t>(kWgTileH + 2 * pad) * (kWgTileW + 2 * pad) + kWgTileH * kWgTileW) * kWgMaxC * sizeof(float);
+  DD_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  WgradParams p; memset(&p, 0, sizeof(p));
+  p.x = make_view(x); p.dz = make_view(dz); p.ksize = kk; p.cin = cin; p.cout = cout;
+  p.tiles_x = (x->w + kWgTileW - 1) / kWgTileW; p.tiles_y = (x->h + kWgTileH - 1) / kWgTileH;
+  dim3 grid(p.tiles_x, p.tiles_y, x->n);
+  DD_CHECK_ARG(x->n <= 65535 && p.tiles_y <= 65535, "wgrad grid too large");
+  const int subs = transposed ? 4 : 1;
+  for (int sp = 0; sp < subs; ++sp) {
+    for (int c0 = 0; c0 < cin; c0 += kWgMaxC) {
+      for (int o0 = 0; o0 < cout; o0 += kWgMaxC) {
+        p.c0 = c0; p.o0 = o0;
+        p.ups = transposed ? 2 : 1; p.ay = sp >> 1; p.ax = sp & 1; p.transposed_layout = transposed;
+        p.dw = transposed ? dw + static_cast<size_t>(sp) * cout * cin : dw;
+        p.db = (sp == 0 || !transposed) ? db : db;   // bias sums every sub-pixel
+        wgrad_kernel<<<grid, kWgThreads, smem, s>>>(p);
+        DD_LAUNCH_CHECK(ctx);
+      }
+    }
+  }
+  return DD_OK;
+}
+
+int dd_maxpool_s2_bwd(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, const dd_tensor* dy, int ksize, const dd_tensor* dx,
+                      void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(x) && tensor_ok(y) && tensor_ok(dy) && tensor_ok(dx) && same_dims(y, dy) && same_dims(x, dx),
+               "bad argument");
+  DD_CHECK_ARG(dx->dtype == DD_F32, "maxpool_bwd accumulates into an fp32 gradient");
+  DD_CHECK_ARG(ksize == 2 || ksize == 3, "maxpool ksize must be 2 or 3");
+  PoolBwdParams p;
+  p.x = make_view(x); p.y = make_view(y); p.dy = make_view(dy); p.dx = make_view(dx); p.ksize = ksize;
+  const int oh = (x->h + 1) / 2, ow = (x->w + 1) / 2;
+  const int pty = (oh - 1) * 2 + ksize - x->h, ptx = (ow - 1) * 2 + ksize - x->w;
+  p.pad_y = (pty > 0 ? pty : 0) / 2; p.pad_x = (ptx > 0 ? ptx : 0) / 2;
+  const size_t total = static_cast<size_t>(y->n) * y->h * y->w * y->c;
+  maxpool_bwd_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_kernel_predict_bwd(dd_ctx* ctx, const dd_tensor* src, const dd_tensor* logits, const dd_tensor* dout, int ksize,
+                          int features, int images_per_tuple, const dd_tensor* dlogits, void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(src) && tensor_ok(logits) && tensor_ok(dout) && tensor_ok(dlogits), "bad argument");
+  DD_CHECK_ARG(ksize >= 1 && (ksize & 1) && features >= 1 && logits->c == features * ksize * ksize, "bad kernel size / channels");
+  DD_CHECK_ARG(src->c == 3 && same_dims(src, dout) && src->n == logits->n * features && same_dims(logits, dlogits), "dims");
+  DD_CHECK_ARG(images_per_tuple >= 1 && logits->n % images_per_tuple == 0, "logits.n must be a multiple of images_per_tuple");
+  KpBwdParams p;
+  p.src = make_view(src); p.logits = make_view(logits); p.dout = make_view(dout); p.dlogits = make_view(dlogits);
+  p.K = ksize; p.F = features; p.ipt = images_per_tuple;
+  const size_t total = static_cast<size_t>(logits->n) * features * src->h * src->w;
+  kernel_predict_bwd_kernel<<<nblocks(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_compose_tail_bwd(dd_ctx* ctx, const dd_tensor* t, const float* w, const float* b, int c_mid, const dd_tensor* small,
+                        const dd_tensor* large, const dd_tensor* dout, const dd_tensor* dt, const dd_tensor* dsmall,
+                        const dd_tensor* dlarge, float* dw_dev, float* db_dev, void* stream) {
+  DD_CHECK_ARG(ctx && w && b && dw_dev && db_dev && tensor_ok(t) && tensor_ok(small) && tensor_ok(large) && tensor_ok(dout) &&
+                   tensor_ok(dt) && tensor_ok(dsmall) && tensor_ok(dlarge), "bad argument");
+  DD_CHECK_ARG(c_mid > 0 && c_mid <= kCmpC && t->c >= c_mid && dt->c >= c_mid, "compose width unsupported");
+  DD_CHECK_ARG(dsmall->dtype == DD_F32 && dlarge->dtype == DD_F32 && same_dims(small, dsmall) && same_dims(large, dlarge) &&
+                   same_dims(large, dout), "gradient dims / dtype");
+  ComposeTailBwdParams p; memset(&p, 0, sizeof(p));
+  p.t = make_view(t); p.small = make_view(small); p.large = make_view(large); p.dout = make_view(dout); p.dt = make_view(dt);
+  p.dsmall = make_view(dsmall); p.dlarge = make_view(dlarge);
+  memcpy(p.w, w, sizeof(float) * c_mid); p.b = b[0]; p.c_mid = c_mid; p.dw = dw_dev; p.db = db_dev;
+  const size_t total = static_cast<size_t>(large->n) * large->h * large->w;
+  compose_tail_bwd_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_compose_head_bwd(dd_ctx* ctx, const dd_tensor* small, const dd_tensor* large, const float* w, int c_mid,
+                        const dd_tensor* y, const dd_tensor* dy, const dd_tensor* dsmall, const dd_tensor* dlarge,
+                        float* dw_dev, float* db_dev, void* stream) {
+  DD_CHECK_ARG(ctx && w && dw_dev && db_dev && tensor_ok(small) && tensor_ok(large) && tensor_ok(y) && tensor_ok(dy) &&
+                   tensor_ok(dsmall) && tensor_ok(dlarge), "bad argument");
+  DD_CHECK_ARG(c_mid > 0 && c_mid <= kCmpC && y->c >= c_mid && dy->c >= c_mid, "compose width unsupported");
+  DD_CHECK_ARG(dsmall->dtype == DD_F32 && dlarge->dtype == DD_F32 && same_dims(small, dsmall) && same_dims(large, dlarge),
+               "gradient dims / dtype");
+  ComposeHeadBwdParams p; memset(&p, 0, sizeof(p));
+  p.small = make_view(small); p.large = make_view(large); p.y = make_view(y); p.dy = make_view(dy);
+  p.dsmall = make_view(dsmall); p.dlarge = make_view(dlarge);
+  memcpy(p.w, w, sizeof(float) * 6 * c_mid); p.c_mid = c_mid; p.dw = dw_dev; p.db = db_dev;
+  const size_t total = static_cast<size_t>(large->n) * large->h * large->w;
+  compose_head_bwd_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_channel_sum(dd_ctx* ctx, const dd_tensor* x, int groups, float* out_dev, void* stream) {
+  DD_CHECK_ARG(ctx && out_dev && tensor_ok(x) && groups > 0 && x->n % groups == 0 && x->c <= 16, "bad argument");
+  ChanSumParams p;
+  p.x = make_view(x); p.out = out_dev; p.groups = groups; p.images_per_group = x->n / groups;
+  dim3 grid(64, groups);
+  channel_sum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_adam_step(dd_ctx* ctx, float* w, const float* g, float* m, float* v, size_t count, float lr, float beta1, float beta2,
+                 float epsilon, int64_t step, float grad_scale, void* stream) {
+  DD_CHECK_ARG(ctx && w && g && m && v && count > 0 && step >= 1, "bad argument");
+  const double lr_t = static_cast<double>(lr) * sqrt(1.0 - pow(static_cast<double>(beta2), static_cast<double>(step))) /
+                      (1.0 - pow(static_cast<double>(beta1), static_cast<double>(step)));
+  adam_kernel<<<nblocks(count, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, g, m, v, count, static_cast<float>(lr_t),
+                                                                                  beta1, beta2, epsilon, grad_scale);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_conv2d_repack_f32(dd_ctx* ctx, const float* w_dev, int ksize, int cin, int cout, int transposed, float* fwd_packed,
+                         float* dgrad_packed, void* stream) {
+  DD_CHECK_ARG(ctx && w_dev && (fwd_packed || dgrad_packed) && ksize >= 1 && ksize <= 3 && cin > 0 && cout > 0, "bad argument");
+  const size_t total = static_cast<size_t>(ksize) * ksize * cin * cout;
+  repack_f32_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w_dev, fwd_packed, dgrad_packed,
+                                                                                       ksize * ksize, cin, cout, transposed);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+}  // extern "C"

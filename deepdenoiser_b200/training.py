@@ -1,0 +1,606 @@
+"""Training on the B200 path - what the reference does with tf.estimator + autodiff (Training.py:607-703, 853-877):
+forward with saved activations, the loss of BaseFeatureTraining.loss / LossDifference.difference, the backward of
+every op as explicit libdd_b200 kernels, TF-form Adam on one flat fp32 parameter buffer and (multi-GPU) one
+all-reduce of the flat gradient buffer per step.
+
+Round-1 scope: the EXACT fp32 path (CUDA-core convolutions), U-Net backbone, loss weights of
+TrainingExample.json (mean weights; variation / MS-SSIM / masked weights must be 0).  Every gradient is
+parity-tested against torch-autograd of the oracle (tests/test_gpu_training.py).  Tensor-core backward kernels
+(dgrad through conv_rows_kernel, MN-major tcgen05 wgrad) are the next step.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .Architecture import Architecture, FeaturePredictionTupleType, ModeKeys
+from .FeatureFlags import FeatureFlagMode
+from .Naming import Naming
+from .network import V
+
+LOSS_KINDS = {"DIFFERENCE": 0, "ABSOLUTE": 1, "SMOOTH_ABSOLUTE": 2, "SQUARED": 3, "SMAPE": 4}
+_LIGHTS = ("Diffuse", "Glossy", "Subsurface", "Transmission")
+_IMAGE_TERMS = ("Volume Direct", "Volume Indirect", "Emission", "Environment")
+_b = ctypes.byref
+
+
+def _fp(t):
+  return ctypes.c_void_p(t.data_ptr())
+
+
+class TrainingSettings:
+  """The part of TrainingExample.json the loss needs (Training.py:969-989, 1009-1203)."""
+
+  def __init__(self, parsed_json=None):
+    j = parsed_json or {}
+    self.learning_rate = float(j.get("learning_rate", 1e-3))
+    self.batch_size = int(j.get("batch_size", 8))
+    self.loss_difference = j.get("loss_difference", "SMAPE")
+    self.use_multiscale_loss = bool(j.get("use_multiscale_loss", True))
+
+    def mean_weight(block, default):
+      b = j.get(block, {})
+      for group in ("loss_weights", "loss_weights_masked"):
+        w = b.get(group, {})
+        for k, v in w.items():
+          if (k != "mean" or group == "loss_weights_masked") and float(v) != 0.0:
+            raise NotImplementedError("%s.%s.%s != 0: variation / MS-SSIM / masked losses are not built (weights are 0 "
+                                      "in TrainingExample.json:31-98)" % (block, group, k))
+      return float(b.get("loss_weights", {}).get("mean", default))
+
+    self.feature_weight = mean_weight("features_training_settings", 1.0)
+    self.combined_feature_weight = mean_weight("combined_features_training_settings", 5.0)
+    self.combined_image_weight = mean_weight("combined_image_training_settings", 10.0)
+
+
+class Trainer:
+  """Owns the flat fp32 parameters / gradients / Adam state of an Architecture and runs training steps."""
+
+  def __init__(self, architecture, settings=None):
+    assert isinstance(architecture, Architecture)
+    if architecture.spec.core_name != "U-Net":
+      raise NotImplementedError("training is built for the U-Net backbone only in this round")
+    self.arch = architecture
+    self.settings = settings or TrainingSettings()
+    architecture.dtype = torch.float32            # exact path
+    architecture.logits_dtype = torch.float32
+    architecture._ensure_device()
+    self.ctx = architecture.ctx
+    self.dev = self.ctx.device
+    self.spec = architecture.spec
+    # flat parameter buffer in TF creation order
+    self.offsets, n = {}, 0
+    for name, shape in self.spec.variable_shapes():
+      size = int(np.prod(shape))
+      self.offsets[name] = (n, shape)
+      n += (size + 3) // 4 * 4                    # keep every variable 16-byte aligned
+    self.count = n
+    self.theta = torch.zeros(n, dtype=torch.float32, device=self.dev)
+    self.grad = torch.zeros_like(self.theta)
+    self.adam_m = torch.zeros_like(self.theta)
+    self.adam_v = torch.zeros_like(self.theta)
+    self.step_count = 0
+    self.set_weights(architecture.weights)
+    self._buffers = {}
+    self.loss_value = torch.zeros(1, dtype=torch.float32, device=self.dev)
+
+  # ------------------------------------------------------------------------------------------ parameters
+  def param(self, name):
+    off, shape = self.offsets[name]
+    return self.theta[off:off + int(np.prod(shape))].view(shape)
+
+  def param_grad(self, name):
+    off, shape = self.offsets[name]
+    return self.grad[off:off + int(np.prod(shape))].view(shape)
+
+  def set_weights(self, weights):
+    for name, (off, shape) in self.offsets.items():
+      w = torch.from_numpy(np.ascontiguousarray(weights[name], dtype=np.float32)).reshape(-1)
+      self.theta[off:off + w.numel()].copy_(w)
+    self._repack()
+
+  def get_weights(self):
+    return {name: self.param(name).detach().cpu().numpy().copy() for name in self.offsets}
+
+  def gradients(self):
+    return {name: self.param_grad(name).detach().cpu().numpy().copy() for name in self.offsets}
+
+  def _repack(self):
+    """fp32 master weights -> forward / input-gradient convolution layouts (device side) + host copies of the few
+    weights that travel in launch parameters (compose head / tail)."""
+    ctx = self.ctx
+    self.fwd, self.bwd, self.bias = {}, {}, {}
+    for var in self.spec.conv_variables():
+      w = self.param(var.kernel_name)
+      self.bias[var.name] = self.param(var.bias_name)
+      if var in self.spec.compose and var.ksize == 1:
+        continue
+      key = var.name
+      if key not in getattr(self, "_packed_store", {}):
+        if not hasattr(self, "_packed_store"):
+          self._packed_store = {}
+        self._packed_store[key] = (torch.empty(w.numel(), dtype=torch.float32, device=self.dev),
+                                   torch.empty(w.numel(), dtype=torch.float32, device=self.dev))
+      f, b = self._packed_store[key]
+      ctx.call("dd_conv2d_repack_f32", _fp(w), var.ksize, var.cin, var.cout, int(var.transposed), _fp(f), _fp(b))
+      self.fwd[key], self.bwd[key] = f, b
+    if self.spec.compose:
+      head, tail = self.spec.compose[0], self.spec.compose[-1]
+      self.host_small = {k: self.param(k).detach().cpu().contiguous() for k in
+                         (head.kernel_name, head.bias_name, tail.kernel_name, tail.bias_name)}
+    if self.arch.feature_flag_mode == FeatureFlagMode.EMBEDDING:
+      self.arch._flags.embedding_matrix = self.param("embedding/feature_flags_embedding_matrix")
+
+  # ------------------------------------------------------------------------------------------ helpers
+  def _buf(self, key, shape, zero=False):
+    k = (key, tuple(shape))
+    t = self._buffers.get(k)
+    if t is None:
+      t = torch.empty(shape, dtype=torch.float32, device=self.dev)
+      self._buffers[k] = t
+    if zero:
+      t.zero_()
+    return t
+
+  def _conv(self, var, x, y, relu=False, residual=None, y_relu=None):
+    self.ctx.conv2d(x.d, self.fwd[var.name], self.bias[var.name], var.ksize, y.d, relu=relu,
+                    residual=residual.d if residual is not None else None, y_relu=y_relu.d if y_relu is not None else None)
+
+  def _conv_bwd(self, var, x, dz, dx=None):
+    """dW, db (accumulated) and optionally dx of y = conv(x, W) + b given dz = dL/dy."""
+    ctx = self.ctx
+    ctx.call("dd_conv2d_wgrad", _b(x.d), _b(dz.d), var.ksize, 0, _fp(self.param_grad(var.kernel_name)),
+             _fp(self.param_grad(var.bias_name)))
+    if dx is not None:
+      ctx.conv2d(dz.d, self.bwd[var.name], None, var.ksize, dx.d, relu=False)
+
+  def _relu_bwd(self, dy, y, dz):
+    self.ctx.call("dd_relu_bwd", _b(dy.d), _b(y.d), _b(dz.d))
+
+  # ------------------------------------------------------------------------------------------ U-Net forward / backward
+  def _unet_forward(self, x0):
+    spec, f, steps, ctx = self.spec, self.spec.filters, self.spec.steps, self.ctx
+    b, h, w = x0.t.shape[0], x0.t.shape[1], x0.t.shape[2]
+    dims = [(h >> i, w >> i) for i in range(steps + 1)]
+    tape = {"x0": x0, "blocks": [], "pools": [], "ups": [], "cats": []}
+
+    def block(key, layers, x, out):
+      acts = [x]
+      for i, var in enumerate(layers):
+        dst = out if i == len(layers) - 1 else V(self._buf("%s.a%d" % (key, i), (b,) + tuple(x.t.shape[1:3]) + (var.cout,)))
+        self._conv(var, acts[-1], dst, relu=True)
+        acts.append(dst)
+      tape["blocks"].append((key, layers, acts))
+      return out
+
+    x = x0
+    for i in range(steps):
+      hh, ww = dims[i]
+      cat = self._buf("cat%d" % i, (b, hh, ww, 2 * f[i]))
+      tape["cats"].append(cat)
+      skip = V(cat, f[i], 0)
+      block("d%d" % i, spec.down[i], x, skip)
+      pooled = V(self._buf("pool%d" % i, (b, dims[i + 1][0], dims[i + 1][1], f[i])))
+      ctx.maxpool_s2(skip.d, 3, pooled.d)
+      tape["pools"].append((skip, pooled))
+      x = pooled
+    results = []
+    for i in range(steps):
+      index = steps - i
+      hh, ww = dims[index]
+      out = V(self._buf("out%d" % index, (b, hh, ww, f[index])))
+      block("u%d" % index, spec.up[i], x, out)
+      if spec.use_multiscale:
+        results.append(out)
+      var = spec.upsample[i]
+      up = V(tape["cats"][index - 1], f[index - 1], f[index - 1])
+      ctx.conv2d_transpose2x2(out.d, self.fwd[var.name], self.bias[var.name], up.d, relu=True)
+      tape["ups"].append((var, out, up))
+      x = V(tape["cats"][index - 1])
+    out = V(self._buf("out0", (b, h, w, f[0])))
+    block("l", spec.last, x, out)
+    results.append(out)
+    tape["results"] = results
+    # post-processing 1x1 convs
+    tape["post"] = []
+    logits = []
+    for k, (r, (a, bvar)) in enumerate(zip(results, spec.post)):
+      bb, hh, ww = r.t.shape[0], r.t.shape[1], r.t.shape[2]
+      mid = V(self._buf("post.mid%d" % k, (bb, hh, ww, spec.output_channels)))
+      self._conv(a, r, mid, relu=True)
+      out_l = V(self._buf("post.out%d" % k, (bb, hh, ww, spec.output_channels)))
+      self._conv(bvar, mid, out_l, relu=False)
+      tape["post"].append((a, bvar, r, mid, out_l))
+      logits.append(out_l)
+    tape["logits_coarse_first"] = logits
+    return tape
+
+  def _block_bwd(self, key, layers, acts, dout):
+    """Backward through n x [conv + ReLU]; dout = dL/d(acts[-1]); returns dL/d(acts[0]) (fresh buffer)."""
+    dy = dout
+    for i in reversed(range(len(layers))):
+      var, x, y = layers[i], acts[i], acts[i + 1]
+      dz = V(self._buf("%s.dz%d" % (key, i), tuple(y.t.shape[:3]) + (var.cout,)))
+      self._relu_bwd(dy, y, dz)
+      dx = V(self._buf("%s.dx%d" % (key, i), tuple(x.t.shape[:3]) + (var.cin,)))
+      self._conv_bwd(var, x, dz, dx)
+      dy = dx
+    return dy
+
+  def _unet_backward(self, tape, dlogits_coarse_first):
+    """Backward of _unet_forward.  Returns dL/dx0 (V over [B,H,W,C0])."""
+    spec, f, steps, ctx = self.spec, self.spec.filters, self.spec.steps, self.ctx
+    blocks = {key: (layers, acts) for key, layers, acts in tape["blocks"]}
+    # 1x1 post-processing -> gradient of every core output
+    dres = {}
+    for k, ((a, bvar, r, mid, out_l), dl) in enumerate(zip(tape["post"], dlogits_coarse_first)):
+      dmid = V(self._buf("post.dmid%d" % k, tuple(mid.t.shape)))
+      self._conv_bwd(bvar, mid, dl, dmid)
+      dz = V(self._buf("post.dz%d" % k, tuple(mid.t.shape)))
+      self._relu_bwd(dmid, mid, dz)
+      dr = V(self._buf("post.dr%d" % k, tuple(r.t.shape[:3]) + (a.cin,)))
+      self._conv_bwd(a, r, dz, dr)
+      dres[id(r.t)] = dr
+    # decoder: last block, then (transposed conv, block) pairs from fine to coarse
+    layers, acts = blocks["l"]
+    dcat = {0: self._block_bwd("l", layers, acts, dres[id(tape["results"][-1].t)])}    # dL/d cat_0, both halves
+    dpool = None
+    ups = {steps - i: tape["ups"][i] for i in range(steps)}
+    for index in range(1, steps + 1):
+      level = index - 1
+      var, out, up = ups[index]
+      dup = V(dcat[level].t, f[level], f[level])                     # [f:] half of the concat gradient
+      dz = V(self._buf("up%d.dz" % index, tuple(up.t.shape[:3]) + (f[level],)))
+      self._relu_bwd(dup, up, dz)
+      ctx.call("dd_conv2d_wgrad", _b(out.d), _b(dz.d), 2, 1, _fp(self.param_grad(var.kernel_name)),
+               _fp(self.param_grad(var.bias_name)))
+      dout = V(self._buf("up%d.dout" % index, tuple(out.t.shape)))
+      ctx.call("dd_conv2d_transpose2x2_dgrad", _b(dz.d), _fp(self.bwd[var.name]), _b(dout.d))
+      extra = dres.get(id(out.t))                                    # multi-scale output taken from this block
+      if extra is not None:
+        ctx.call("dd_axpy", ctypes.c_float(1.0), _b(extra.d), _b(dout.d))
+      layers, acts = blocks["u%d" % index]
+      dx = self._block_bwd("u%d" % index, layers, acts, dout)
+      if index == steps:
+        dpool = dx                                                   # the deepest block consumed pool_{steps-1}
+      else:
+        dcat[index] = dx                                             # block u_index consumed cat_index
+    # encoder: pooling + down blocks from coarse to fine
+    for i in reversed(range(steps)):
+      skip, pooled = tape["pools"][i]
+      dskip = V(dcat[i].t, f[i], 0)                                  # [:f] half, written by the concat consumer
+      ctx.call("dd_maxpool_s2_bwd", _b(skip.d), _b(pooled.d), _b(dpool.d), 3, _b(dskip.d))
+      layers, acts = blocks["d%d" % i]
+      dpool = self._block_bwd("d%d" % i, layers, acts, dskip)
+    return dpool                                                     # dL/dx0
+
+  # ------------------------------------------------------------------------------------------ compose net
+  def _compose_forward(self, key, small, large, out):
+    """MultiScalePrediction.compose_scales with every intermediate kept for the backward pass."""
+    spec, ctx = self.spec, self.ctx
+    head, c1, c2, c3, c4, tail = spec.compose
+    i, h, w = large.t.shape[0], large.t.shape[1], large.t.shape[2]
+    t = {n: V(self._buf("%s.%s" % (key, n), (i, h, w, 24))) for n in ("x0", "a1", "x1", "a2", "a3", "x2")}
+    hs = self.host_small
+    ctx.compose_head(small.d, large.d, hs[head.kernel_name].reshape(6, 24), hs[head.bias_name], 24, t["x0"].d)
+    self._conv(c1, t["x0"], t["a1"], relu=True)                              # a1 = relu(r1)
+    self._conv(c2, t["a1"], t["x1"], residual=t["x0"], y_relu=t["a2"])       # x1 = x0 + r2, a2 = relu(x1)
+    self._conv(c3, t["a2"], t["a3"], relu=True)                              # a3 = relu(r3)
+    self._conv(c4, t["a3"], t["x2"], residual=t["x1"])                       # x2 = x1 + r4
+    ctx.compose_tail(t["x2"].d, hs[tail.kernel_name].reshape(24), hs[tail.bias_name], 24, small.d, large.d, None, out.d)
+    t.update(small=small, large=large, key=key)
+    return t
+
+  def _compose_backward(self, t, dout, dsmall, dlarge):
+    """dsmall / dlarge (fp32 image banks) are accumulated; compose weights' gradients are accumulated."""
+    spec, ctx = self.spec, self.ctx
+    head, c1, c2, c3, c4, tail = spec.compose
+    key = t["key"]
+    shape = tuple(t["x0"].t.shape)
+    hs = self.host_small
+    g = lambda n: V(self._buf("%s.d%s" % (key, n), shape))   # noqa: E731
+    dx2 = g("x2")
+    ctx.call("dd_compose_tail_bwd", _b(t["x2"].d), _fp(hs[tail.kernel_name]), _fp(hs[tail.bias_name]), 24, _b(t["small"].d),
+             _b(t["large"].d), _b(dout.d), _b(dx2.d), _b(dsmall.d), _b(dlarge.d), _fp(self.param_grad(tail.kernel_name)),
+             _fp(self.param_grad(tail.bias_name)))
+    # block 2: x2 = x1 + conv4(a3), a3 = relu(conv3(a2)), a2 = relu(x1)
+    da3 = g("a3")
+    self._conv_bwd(c4, t["a3"], dx2, da3)
+    dz3 = g("z3")
+    self._relu_bwd(da3, t["a3"], dz3)
+    da2 = g("a2")
+    self._conv_bwd(c3, t["a2"], dz3, da2)
+    dx1 = g("x1")
+    self._relu_bwd(da2, t["a2"], dx1)                                         # through relu(x1)
+    ctx.call("dd_axpy", ctypes.c_float(1.0), _b(dx2.d), _b(dx1.d))            # + identity path
+    # block 1: x1 = x0 + conv2(a1), a1 = relu(conv1(x0)) (x0 >= 0 is already a ReLU output)
+    da1 = g("a1")
+    self._conv_bwd(c2, t["a1"], dx1, da1)
+    dz1 = g("z1")
+    self._relu_bwd(da1, t["a1"], dz1)
+    dx0 = g("x0")
+    self._conv_bwd(c1, t["x0"], dz1, dx0)
+    ctx.call("dd_axpy", ctypes.c_float(1.0), _b(dx1.d), _b(dx0.d))
+    ctx.call("dd_compose_head_bwd", _b(t["small"].d), _b(t["large"].d), _fp(hs[head.kernel_name]), 24, _b(t["x0"].d), _b(dx0.d),
+             _b(dsmall.d), _b(dlarge.d), _fp(self.param_grad(head.kernel_name)), _fp(self.param_grad(head.bias_name)))
+
+  # ------------------------------------------------------------------------------------------ forward (all tuples, one chunk)
+  def forward(self, features):
+    """Architecture.predict for training: same arithmetic as the inference path, one chunk, everything kept."""
+    arch, ctx = self.arch, self.ctx
+    targets, every = arch.feature_predictions, arch.feature_predictions + arch.auxiliary_features
+    sources = [arch._as_device(features[Naming.source_feature_name(fp.name, index=0)]) for fp in every]
+    n, h, w = sources[0].shape[0], sources[0].shape[1], sources[0].shape[2]
+    n_scales = (self.spec.steps + 1) if arch.use_multiscale_predictions else 1
+    if h % (1 << self.spec.steps) or w % (1 << self.spec.steps):
+      raise ValueError("height and width must be divisible by %d" % (1 << self.spec.steps))
+    var_width = max([fp.feature_variance.channels(fp.number_of_channels) for fp in every] + [0])
+    std_bank = self._buf("bank.std", (len(every) * n, h, w, 3))
+    var_bank = self._buf("bank.var", (len(every) * n, h, w, max(var_width, 1)))
+    raw_bank = self._buf("bank.raw", (len(targets) * n, h, w, 3)) if arch._preserve_source else None
+    for fp, s in zip(every, sources):
+      lo, hi = fp.bank_index * n, (fp.bank_index + 1) * n
+      vc = fp.feature_variance.channels(fp.number_of_channels)
+      ctx.standardize_variance(_lib.desc(s), arch._std_params(fp), _lib.desc(std_bank[lo:hi]),
+                               _lib.desc(var_bank[lo:hi], vc, 0) if vc else None)
+      if arch._preserve_source and fp.is_target:
+        ctx.standardize_variance(_lib.desc(s), _lib.dd_standardize_params(0, 0.0, 1.0, 0, 0, 0, 0, 0, 1e-4),
+                                 _lib.desc(raw_bank[lo:hi]), None)
+    nt = len(targets) * n
+    kp_full = raw_bank if arch._preserve_source else std_bank[:nt]
+    kp_sources = [kp_full]
+    for s in range(1, n_scales):
+      pooled = self._buf("bank.kpsrc%d" % s, (nt, h >> s, w >> s, 3))
+      if arch.use_kernel_prediction:
+        ctx.avgpool(_lib.desc(kp_full), 1 << s, _lib.desc(pooled))
+      kp_sources.append(pooled)
+    c0 = arch.number_of_input_channels
+    table, keep = arch._gather_table(std_bank, var_bank, max(var_width, 1), features, n, c0)
+    tuples, ft = arch.feature_prediction_tuples, arch.features_per_tuple
+    x0 = self._buf("net.x0", (len(tuples) * n, h, w, c0))
+    ctx.assemble_input(table, len(tuples), n, _lib.desc(x0))
+    tape = self._unet_forward(V(x0))
+    logits = list(tape["logits_coarse_first"])
+    if arch.use_multiscale_predictions:
+      logits.reverse()                                   # largest first (Architecture.py:577-579)
+    if not arch.use_kernel_prediction:
+      raise NotImplementedError("training without kernel prediction is not built")
+    kp = []
+    for s in range(n_scales):
+      dst = self._buf("kp.out%d" % s, (nt, h >> s, w >> s, 3))
+      ctx.kernel_predict(_lib.desc(kp_sources[s]), logits[s].d, arch.kernel_size, ft, n, _lib.desc(dst))
+      kp.append(dst)
+    # multi-scale composition / inverse standardisation; `pre` = values fed to the inversion (needed by its backward)
+    stage = list(kp)
+    pre_inv = [None] * n_scales
+    inv_first = not arch.invert_standardization_after_multiscale_predictions
+    if inv_first:
+      for s in range(n_scales):
+        pre_inv[s] = stage[s]
+        inv = self._buf("inv.out%d" % s, tuple(stage[s].shape))
+        inv.copy_(stage[s])
+        arch._invert(targets, inv, n)
+        stage[s] = inv
+    compose_tapes = [None] * n_scales
+    composed_in = list(stage)                            # `large` operands (before composition)
+    for s in range(n_scales - 1, 0, -1):
+      out = self._buf("cmp.out%d" % (s - 1), tuple(stage[s - 1].shape))
+      compose_tapes[s - 1] = self._compose_forward("cmp%d" % (s - 1), V(stage[s]), V(stage[s - 1]), V(out))
+      stage[s - 1] = out
+    finals = []
+    for s in range(n_scales):
+      if inv_first:
+        finals.append(stage[s])
+      else:
+        pre_inv[s] = stage[s]
+        fin = self._buf("final%d" % s, tuple(stage[s].shape))
+        fin.copy_(stage[s])
+        arch._invert(targets, fin, n)
+        finals.append(fin)
+    del keep
+    self._state = dict(tape=tape, logits=logits, kp=kp, kp_sources=kp_sources, compose_tapes=compose_tapes, pre_inv=pre_inv,
+                       finals=finals, n=n, h=h, w=w, n_scales=n_scales, x0=x0, std_bank=std_bank, inv_first=inv_first)
+    return finals
+
+  def predictions(self):
+    """Prediction dictionaries of the last forward() (same structure as Architecture.predict)."""
+    st, arch = self._state, self.arch
+    out = []
+    for s in range(st["n_scales"]):
+      d = {}
+      for fp in arch.feature_predictions:
+        lo, hi = fp.bank_index * st["n"], (fp.bank_index + 1) * st["n"]
+        p = st["finals"][s][lo:hi] if fp.load_data else st["std_bank"][lo:hi, :st["h"] >> s, :st["w"] >> s, :]
+        d[Naming.feature_prediction_name(fp.name)] = p[..., :1] if fp.number_of_channels == 1 else p
+      out.append(d)
+    return out
+
+  # ------------------------------------------------------------------------------------------ loss + its gradient
+  def loss_and_gradient(self, targets_dict):
+    """model_fn's loss (Training.py:611-660) on the last forward(); fills dL/d(final predictions) and returns the
+    device scalar.  targets_dict: {'target_image/<Pass>': [N,H,W,C]}."""
+    arch, ctx, st, cfg = self.arch, self.ctx, self._state, self.settings
+    n, h, w, n_scales = st["n"], st["h"], st["w"], st["n_scales"]
+    kind = LOSS_KINDS[cfg.loss_difference]
+    loss_scales = n_scales if cfg.use_multiscale_loss else 1
+    norm = 1.0 / sum(1.0 / 4.0 ** s for s in range(loss_scales))
+    self.loss_value.zero_()
+    dfin = [self._buf("dfinal%d" % s, tuple(st["finals"][s].shape), zero=True) for s in range(n_scales)]
+    loaded = [fp for fp in arch.feature_predictions if fp.is_target and fp.load_data]
+    by_name = {fp.name: fp for fp in arch.feature_predictions}
+    # targets at every loss scale (Training.py:616-623): avg-pool 2^s of the labels
+    tgt = {}
+    for fp in loaded:
+      full = arch._as_device(targets_dict[Naming.target_feature_name(fp.name)])
+      tgt[fp.name] = [full]
+      for s in range(1, loss_scales):
+        t = self._buf("tgt.%s.%d" % (fp.name, s), (n, h >> s, w >> s, full.shape[3]))
+        ctx.avgpool(_lib.desc(full), 1 << s, _lib.desc(t))
+        tgt[fp.name].append(t)
+
+    def pred_view(bank, fp, channels=None):
+      lo, hi = fp.bank_index * n, (fp.bank_index + 1) * n
+      return _lib.desc(bank[lo:hi], channels or fp.number_of_channels, 0)
+
+    for s in range(loss_scales):
+      px = float(n * (h >> s) * (w >> s))
+      factor = norm / 4.0 ** s
+      # single-feature losses (FeatureTraining, weight from features_training_settings)
+      if cfg.feature_weight > 0:
+        for fp in loaded:
+          ctx.call("dd_loss_fwd_bwd", _b(pred_view(st["finals"][s], fp)), _b(_lib.desc(tgt[fp.name][s])), kind,
+                   ctypes.c_float(cfg.feature_weight * factor / px), ctypes.c_float(1e-2), _fp(self.loss_value),
+                   _b(pred_view(dfin[s], fp)), 1)
+      # combined lighting passes color * (direct + indirect) and the combined image (sum of everything)
+      lights = [l for l in _LIGHTS if all((l + k) in by_name and by_name[l + k].load_data for k in (" Color", " Direct", " Indirect"))]
+      image_terms = [t for t in _IMAGE_TERMS if t in by_name and by_name[t].load_data]
+      use_image = cfg.combined_image_weight > 0 and len(lights) == 4 and len(image_terms) == 4
+      shape = (n, h >> s, w >> s, 3)
+      g_img = None
+      if use_image:
+        img_p = self._buf("img.p%d" % s, shape, zero=True)
+        img_t = self._buf("img.t%d" % s, shape, zero=True)
+        g_img = self._buf("img.g%d" % s, shape)
+      comb = {}
+      if lights and (cfg.combined_feature_weight > 0 or use_image):
+        for l in lights:
+          c, d, i = (by_name[l + k] for k in (" Color", " Direct", " Indirect"))
+          cp = self._buf("cmb.p.%s.%d" % (l, s), shape)
+          ct = self._buf("cmb.t.%s.%d" % (l, s), shape)
+          ctx.call("dd_muladd_fwd", _b(pred_view(st["finals"][s], c)), _b(pred_view(st["finals"][s], d)),
+                   _b(pred_view(st["finals"][s], i)), _b(_lib.desc(cp)))
+          ctx.call("dd_muladd_fwd", _b(_lib.desc(tgt[c.name][s])), _b(_lib.desc(tgt[d.name][s])), _b(_lib.desc(tgt[i.name][s])),
+                   _b(_lib.desc(ct)))
+          comb[l] = (cp, ct, self._buf("cmb.g.%s.%d" % (l, s), shape, zero=True))
+          if use_image:
+            ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(cp)), _b(_lib.desc(img_p)))
+            ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(ct)), _b(_lib.desc(img_t)))
+      if use_image:
+        for t in image_terms:
+          fp = by_name[t]
+          ctx.call("dd_axpy", ctypes.c_float(1.0), _b(pred_view(st["finals"][s], fp)), _b(_lib.desc(img_p)))
+          ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(tgt[t][s])), _b(_lib.desc(img_t)))
+        ctx.call("dd_loss_fwd_bwd", _b(_lib.desc(img_p)), _b(_lib.desc(img_t)), kind,
+                 ctypes.c_float(cfg.combined_image_weight * factor / px), ctypes.c_float(1e-2), _fp(self.loss_value),
+                 _b(_lib.desc(g_img)), 0)
+        for t in image_terms:
+          ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(g_img)), _b(pred_view(dfin[s], by_name[t])))
+      for l, (cp, ct, gc) in comb.items():
+        if cfg.combined_feature_weight > 0:
+          ctx.call("dd_loss_fwd_bwd", _b(_lib.desc(cp)), _b(_lib.desc(ct)), kind,
+                   ctypes.c_float(cfg.combined_feature_weight * factor / px), ctypes.c_float(1e-2), _fp(self.loss_value),
+                   _b(_lib.desc(gc)), 1)
+        if use_image:
+          ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(g_img)), _b(_lib.desc(gc)))
+        c, d, i = (by_name[l + k] for k in (" Color", " Direct", " Indirect"))
+        inc = self._buf("cmb.inc%d" % s, shape)
+        ctx.call("dd_muladd_bwd", _b(pred_view(st["finals"][s], c)), _b(pred_view(st["finals"][s], d)),
+                 _b(pred_view(st["finals"][s], i)), _b(_lib.desc(gc)), _b(pred_view(dfin[s], c)), _b(_lib.desc(inc)))
+        ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(inc)), _b(pred_view(dfin[s], d)))
+        ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(inc)), _b(pred_view(dfin[s], i)))
+    self._dfinal = dfin
+    return self.loss_value
+
+  # ------------------------------------------------------------------------------------------ backward of everything
+  def backward(self):
+    arch, ctx, st = self.arch, self.ctx, self._state
+    n, n_scales = st["n"], st["n_scales"]
+    targets = arch.feature_predictions
+    self.grad.zero_()
+    g = list(self._dfinal)                       # dL/d finals
+
+    def invert_bwd(dy, x, s, tag):
+      """through prediction_invert_standardization, one launch per run of passes with identical parameters"""
+      out = self._buf("ginv.%s%d" % (tag, s), tuple(dy.shape))
+      out.copy_(dy)
+      i = 0
+      while i < len(targets):
+        fp = targets[i]
+        j = i + 1
+        while (j < len(targets) and targets[j].invert_standardization == fp.invert_standardization and
+               targets[j].feature_standardization.key() == fp.feature_standardization.key()):
+          j += 1
+        stdz = fp.feature_standardization
+        if fp.invert_standardization and stdz.key() != (False, 0.0, 1.0):
+          ctx.call("dd_invert_standardization_bwd", _b(_lib.desc(dy[i * n:j * n])), _b(_lib.desc(x[i * n:j * n])),
+                   _b(stdz.invert_params()), _b(_lib.desc(out[i * n:j * n])))
+        i = j
+      return out
+
+    if not st["inv_first"]:
+      g = [invert_bwd(g[s], st["pre_inv"][s], s, "a") for s in range(n_scales)]
+    # composition chain: composed_{s} = compose(small = composed_{s+1}, large = stage_in_s)
+    dlarge = [None] * n_scales
+    for s in range(n_scales - 1):
+      t = st["compose_tapes"][s]
+      dl = self._buf("dlarge%d" % s, tuple(g[s].shape), zero=True)
+      gs_next = self._buf("gsmall%d" % (s + 1), tuple(g[s + 1].shape))
+      gs_next.copy_(g[s + 1])
+      self._compose_backward(t, V(g[s]), V(gs_next), V(dl))
+      g[s + 1] = gs_next
+      dlarge[s] = dl
+    dlarge[n_scales - 1] = g[n_scales - 1]
+    if st["inv_first"]:
+      dlarge = [invert_bwd(dlarge[s], st["pre_inv"][s], s, "b") for s in range(n_scales)]
+    # kernel prediction -> logits gradients (largest first), then the network
+    dlogits = []
+    for s in range(n_scales):
+      dl = V(self._buf("dlogits%d" % s, tuple(st["logits"][s].t.shape)))
+      ctx.call("dd_kernel_predict_bwd", _b(_lib.desc(st["kp_sources"][s])), _b(st["logits"][s].d), _b(_lib.desc(dlarge[s])),
+               arch.kernel_size, arch.features_per_tuple, n, _b(dl.d))
+      dlogits.append(dl)
+    if arch.use_multiscale_predictions:
+      dlogits.reverse()                           # coarsest first, the order of the core outputs
+    dx0 = self._unet_backward(st["tape"], dlogits)
+    # embedding rows: sum of the input gradient over the pixels of each tuple's images
+    if arch.feature_flag_mode == FeatureFlagMode.EMBEDDING:
+      dim = arch._flags.embedding_dimension
+      first = arch.number_of_input_channels - dim
+      tuples = arch.feature_prediction_tuples
+      sums = self._buf("emb.sums", (len(tuples), dim), zero=True)
+      ctx.call("dd_channel_sum", _b(_lib.desc(dx0.t, dim, first)), len(tuples), _fp(sums))
+      rows = torch.tensor([arch._flags.index(t.name) for t in tuples], device=self.dev)
+      self.param_grad("embedding/feature_flags_embedding_matrix").index_add_(0, rows, sums)
+    return self.grad
+
+  # ------------------------------------------------------------------------------------------ one optimizer step
+  def train_step(self, features, targets_dict, world_size=1):
+    """forward + loss + backward + (all-reduce) + Adam.  Returns the loss as a device scalar."""
+    self.forward(features)
+    loss = self.loss_and_gradient(targets_dict)
+    self.backward()
+    scale = 1.0
+    if world_size > 1:
+      import torch.distributed as dist
+      dist.all_reduce(self.grad)                  # one flat bucket: 1.7 M floats for the U-Net (latency bound)
+      dist.all_reduce(loss)
+      loss /= world_size
+      scale = 1.0 / world_size                    # the loss is a mean over the global batch (Training.py:128)
+    self.step_count += 1
+    self.ctx.call("dd_adam_step", _fp(self.theta), _fp(self.grad), _fp(self.adam_m), _fp(self.adam_v),
+                  ctypes.c_size_t(self.count), ctypes.c_float(self.settings.learning_rate), ctypes.c_float(0.9),
+                  ctypes.c_float(0.999), ctypes.c_float(1e-8), ctypes.c_int64(self.step_count), ctypes.c_float(scale))
+    self._repack()
+    return loss
+
+  # ------------------------------------------------------------------------------------------ checkpoints
+  def save_checkpoint(self, path):
+    state = {"step": np.array(self.step_count)}
+    for name in self.offsets:
+      off, shape = self.offsets[name]
+      size = int(np.prod(shape))
+      state[name] = self.theta[off:off + size].view(shape).cpu().numpy()
+      state["adam_m/" + name] = self.adam_m[off:off + size].view(shape).cpu().numpy()
+      state["adam_v/" + name] = self.adam_v[off:off + size].view(shape).cpu().numpy()
+    np.savez(path, **state)
+
+  def load_checkpoint(self, path):
+    z = np.load(path)
+    self.step_count = int(z["step"])
+    for name, (off, shape) in self.offsets.items():
+      size = int(np.prod(shape))
+      self.theta[off:off + size].copy_(torch.from_numpy(z[name]).reshape(-1))
+      self.adam_m[off:off + size].copy_(torch.from_numpy(z["adam_m/" + name]).reshape(-1))
+      self.adam_v[off:off + size].copy_(torch.from_numpy(z["adam_v/" + name]).reshape(-1))
+    self._repack()

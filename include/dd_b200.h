@@ -176,6 +176,59 @@ int dd_compose_tail_fwd(dd_ctx* ctx, const dd_tensor* t, const float* w, const f
 int dd_invert_standardization(dd_ctx* ctx, const dd_tensor* x, const dd_invert_params* inv, const dd_tensor* y,
                               void* stream);
 
+/* ---- training: loss, backward of every forward op, optimizer --------------------------------- */
+/* Exact (fp32 accumulate, CUDA-core) training path; replaces what tf.train.AdamOptimizer.minimize derives by
+ * autodiff (Training.py:700-702).  Gradient tensors are fp32. */
+
+/* dz = dy * [y > 0]: backward of activation=tf.nn.relu (UNet.py:29-31 ...). */
+int dd_relu_bwd(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const dd_tensor* dz, void* stream);
+/* out = a * (b + c): combined lighting pass color * (direct + indirect) (Training.py:420-433). */
+int dd_muladd_fwd(dd_ctx* ctx, const dd_tensor* a, const dd_tensor* b, const dd_tensor* c, const dd_tensor* out, void* stream);
+/* backward of the above for upstream gradient g: da_acc += g (b + c); dbc_inc = g a (the increment of BOTH db and dc). */
+int dd_muladd_bwd(dd_ctx* ctx, const dd_tensor* a, const dd_tensor* b, const dd_tensor* c, const dd_tensor* g,
+                  const dd_tensor* da_acc, const dd_tensor* dbc_inc, void* stream);
+/* y += alpha * x;  y = value. */
+int dd_axpy(dd_ctx* ctx, float alpha, const dd_tensor* x, const dd_tensor* y, void* stream);
+int dd_fill(dd_ctx* ctx, float value, const dd_tensor* y, void* stream);
+/* dx = dy * d(invert_standardization)/dx evaluated at x (Architecture.py:48-55). */
+int dd_invert_standardization_bwd(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* x, const dd_invert_params* inv,
+                                  const dd_tensor* dx, void* stream);
+/* LossDifference.difference (LossDifference.py:15-36) + reduce_sum over channels + the weighted mean of
+ * BaseFeatureTraining.loss (Training.py:126-129,210-243):  *loss_dev += weight * sum_pixels sum_c diff(pred, target),
+ * dpred (=|+=) weight * d diff / d pred.  kind: 0 DIFFERENCE 1 ABSOLUTE 2 SMOOTH_ABSOLUTE 3 SQUARED 4 SMAPE;
+ * the caller folds loss weight, scale weight and 1/(N*h*w) into `weight`.  dpred may be NULL (evaluation). */
+int dd_loss_fwd_bwd(dd_ctx* ctx, const dd_tensor* pred, const dd_tensor* target, int kind, float weight, float epsilon,
+                    float* loss_dev, const dd_tensor* dpred, int accumulate, void* stream);
+/* dW (TF layout [kh,kw,cin,cout]; transposed: [2,2,cout,cin]) += x^T * dz over all pixels, db += sum dz. */
+int dd_conv2d_wgrad(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int ksize, int transposed, float* dw_dev,
+                    float* db_dev, void* stream);
+/* input gradient of dd_conv2d_transpose2x2_fwd (exact path). */
+int dd_conv2d_transpose2x2_dgrad(dd_ctx* ctx, const dd_tensor* dz, const float* w_dgrad, const dd_tensor* dx, void* stream);
+/* device-side repack of fp32 master weights after an optimizer step: forward layout and the layout of the
+ * input-gradient convolution (spatially flipped, channels swapped); either output may be NULL. */
+int dd_conv2d_repack_f32(dd_ctx* ctx, const float* w_dev, int ksize, int cin, int cout, int transposed, float* fwd_packed,
+                         float* dgrad_packed, void* stream);
+/* backward of dd_maxpool_s2_fwd: dx (fp32, pre-zeroed or accumulating) += dy routed to the first maximum of each window. */
+int dd_maxpool_s2_bwd(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, const dd_tensor* dy, int ksize, const dd_tensor* dx,
+                      void* stream);
+/* backward of dd_kernel_predict_fwd w.r.t. the logits (the source is data): softmax Jacobian included. */
+int dd_kernel_predict_bwd(dd_ctx* ctx, const dd_tensor* src, const dd_tensor* logits, const dd_tensor* dout, int ksize,
+                          int features, int images_per_tuple, const dd_tensor* dlogits, void* stream);
+/* backward of dd_compose_tail_fwd (without fused inversion): dt written, dsmall / dlarge / dw_dev / db_dev accumulated. */
+int dd_compose_tail_bwd(dd_ctx* ctx, const dd_tensor* t, const float* w, const float* b, int c_mid, const dd_tensor* small,
+                        const dd_tensor* large, const dd_tensor* dout, const dd_tensor* dt, const dd_tensor* dsmall,
+                        const dd_tensor* dlarge, float* dw_dev, float* db_dev, void* stream);
+/* backward of dd_compose_head_fwd: y is the head's (ReLU'd) output, dy its gradient. */
+int dd_compose_head_bwd(dd_ctx* ctx, const dd_tensor* small, const dd_tensor* large, const float* w, int c_mid,
+                        const dd_tensor* y, const dd_tensor* dy, const dd_tensor* dsmall, const dd_tensor* dlarge,
+                        float* dw_dev, float* db_dev, void* stream);
+/* out_dev[g][c] += sum over the images of group g (x.n / groups each) and all pixels of x[..,c]: gradient of the
+ * embedding row broadcast by the SourceEncoder (FeatureFlags.py:50-69). */
+int dd_channel_sum(dd_ctx* ctx, const dd_tensor* x, int groups, float* out_dev, void* stream);
+/* tf.train.AdamOptimizer (Training.py:701) on flat fp32 buffers; g is multiplied by grad_scale first. */
+int dd_adam_step(dd_ctx* ctx, float* w, const float* g, float* m, float* v, size_t count, float lr, float beta1, float beta2,
+                 float epsilon, int64_t step, float grad_scale, void* stream);
+
 /* ---- utilities ------------------------------------------------------------------------------ */
 /* dtype / channel-view conversion copy y = cast(x) (c channels). */
 int dd_cast_copy(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, void* stream);

@@ -24,6 +24,8 @@ def _nhwc(x):
 
 
 def asarray(x, dtype):
+  if isinstance(x, torch.Tensor):
+    return x.to(dtype)          # keeps the autograd graph (gradient oracle for the training path)
   return torch.as_tensor(np.asarray(x), dtype=dtype)
 
 
