@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""python Training.py <training.json> [--validate] [--threads N] [--train_epochs E] [--validation_interval V]
+[--data_format channels_first|channels_last] [--synthetic_tiles N --synthetic_tile_size S --steps_per_epoch K]
+
+Same command line as the reference's TensorFlow/Training.py:33-61 (extra flags are additions).  The Estimator loop
+(Training.py:1252-1284) becomes a plain loop: forward + loss + explicit backward kernels + TF-form Adam
+(deepdenoiser_b200/training.py), one all-reduce of the flat gradient buffer per step when launched with
+`python -m torch.distributed.run --nproc-per-node N Training.py ...` (tiles are sharded over the ranks).
+Checkpoints (.npz: weights under their TF variable names + Adam moments + step) are written to the JSON's
+model_directory every 500 steps (Training.py:1214-1218) and the latest one is resumed; scalars go to
+<model_directory>/training_log.jsonl.  Data: the reference reads TFRecords made by TFRecordsCreator.py; until the
+TensorFlow-free reader lands this script trains on seeded synthetic render-pass tiles (--synthetic_tiles).
+"""
+import argparse
+import glob
+import json
+import multiprocessing
+import os
+import sys
+import time
+
+import torch
+
+from deepdenoiser_b200 import synthetic
+from deepdenoiser_b200.Architecture import Architecture
+from deepdenoiser_b200.training import Trainer, TrainingSettings
+
+parser = argparse.ArgumentParser(description="Training for the DeepDenoiser (B200-native path).")
+parser.add_argument("json_filename", help="The json specifying all the relevant details.")
+parser.add_argument("--validate", action="store_true", help="Perform a validation step.")
+parser.add_argument("--threads", default=multiprocessing.cpu_count() + 1, help="Number of threads to use")
+parser.add_argument("--train_epochs", type=int, default=10000, help="Number of epochs to train.")
+parser.add_argument("--validation_interval", type=int, default=1, help="Number of epochs after which a validation is made.")
+parser.add_argument("--data_format", type=str, default="channels_first", choices=["channels_first", "channels_last"],
+                    help="Accepted for compatibility; the device layout is always NHWC.")
+parser.add_argument("--synthetic_tiles", type=int, default=None, help="Global batch of synthetic tiles per step.")
+parser.add_argument("--synthetic_tile_size", type=int, default=64)
+parser.add_argument("--steps_per_epoch", type=int, default=10)
+parser.add_argument("--checkpoint_steps", type=int, default=500)
+
+
+def synthetic_batch(architecture, tiles, size, seed):
+  noisy = synthetic.synthetic_features(architecture, tiles, size, size, seed=seed)
+  clean = synthetic.synthetic_features(architecture, tiles, size, size, seed=seed + 7919)
+  features = {k: torch.from_numpy(v) for k, v in noisy.items()}
+  targets = {"target_image/" + fp.name: torch.from_numpy(clean["source_image/0/" + fp.name])
+             for fp in architecture.feature_predictions if fp.load_data}
+  return features, targets
+
+
+def main(parsed_arguments):
+  with open(parsed_arguments.json_filename, "r") as f:
+    training_json = json.load(f)
+  base = os.path.dirname(os.path.abspath(parsed_arguments.json_filename))
+  with open(os.path.join(base, training_json["architecture"]), "r") as f:      # relative to the training json (:953-961)
+    architecture_json = json.load(f)
+  architecture_json.setdefault("b200", {})["dtype"] = "float32"               # exact training path (round 1)
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+  architecture = Architecture(architecture_json, source_data_format="channels_last",
+                              data_format=parsed_arguments.data_format, device=local)
+  settings = TrainingSettings(training_json)
+  trainer = Trainer(architecture, settings)
+  model_dir = os.path.join(base, architecture.model_directory)
+  os.makedirs(model_dir, exist_ok=True)
+  checkpoints = sorted(glob.glob(os.path.join(model_dir, "ckpt-*.npz")), key=lambda p: int(p.split("-")[-1][:-4]))
+  if checkpoints:
+    trainer.load_checkpoint(checkpoints[-1])
+    if rank == 0:
+      print("resumed from", checkpoints[-1], "at step", trainer.step_count)
+  global_tiles = parsed_arguments.synthetic_tiles or settings.batch_size
+  if global_tiles % world:
+    raise ValueError("the global batch (%d tiles) must be divisible by the number of ranks (%d)" % (global_tiles, world))
+  per_rank = global_tiles // world
+  log = open(os.path.join(model_dir, "training_log.jsonl"), "a") if rank == 0 else None
+  size = parsed_arguments.synthetic_tile_size
+  for epoch in range(parsed_arguments.train_epochs):
+    for _ in range(parsed_arguments.steps_per_epoch):
+      step = trainer.step_count
+      features, targets = synthetic_batch(architecture, per_rank, size, seed=1000003 * step + rank)
+      t0 = time.perf_counter()
+      loss = float(trainer.train_step(features, targets, world_size=world).item())
+      dt = time.perf_counter() - t0
+      if rank == 0:
+        rec = {"step": trainer.step_count, "epoch": epoch, "loss": loss, "learning_rate": settings.learning_rate,
+               "batch_size": global_tiles, "tile": size, "ranks": world, "seconds": dt,
+               "megapixels_per_second": global_tiles * size * size / 1e6 / dt}
+        log.write(json.dumps(rec) + "\n")
+        log.flush()
+        print(json.dumps(rec))
+      if rank == 0 and trainer.step_count % parsed_arguments.checkpoint_steps == 0:
+        trainer.save_checkpoint(os.path.join(model_dir, "ckpt-%d.npz" % trainer.step_count))
+    if parsed_arguments.validate and (epoch + 1) % parsed_arguments.validation_interval == 0:
+      features, targets = synthetic_batch(architecture, per_rank, size, seed=424243 + rank)
+      trainer.forward(features)
+      val = float(trainer.loss_and_gradient(targets).item())
+      if rank == 0:
+        print(json.dumps({"validation_loss": val, "epoch": epoch, "step": trainer.step_count}))
+  if rank == 0:
+    trainer.save_checkpoint(os.path.join(model_dir, "ckpt-%d.npz" % trainer.step_count))
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+  return 0
+
+
+if __name__ == "__main__":
+  args, unparsed = parser.parse_known_args()
+  sys.exit(main(args))
