@@ -9,7 +9,8 @@ One "step" = one full 1920x1080 frame through Architecture.predict: all 17 featu
 the SINGLE-mode JSON (shared weights, Architecture.py:561-571), each pass = SourceEncoder concat -> U-Net ->
 1x1 post-process -> kernel-prediction apply at 3 scales -> multi-scale composition -> inverse standardisation.
 `value` = frame megapixels / step time with the sources resident in HBM; `e2e` = the same call fed from pinned
-HOST buffers with the 17 full-resolution predictions copied back to the host inside the timed region.
+HOST buffers with the 17 full-resolution predictions copied back to the host inside the timed region (uploads and
+downloads of neighbouring frames overlap the kernels: deepdenoiser_b200/pipeline.py).
 N > 1: one process per GPU (torchrun), every rank denoises its own frame (frames are independent: no
 data-path collective), barrier + max-over-ranks timing, weak scaling.
 Prints ONE JSON line on rank 0.
@@ -214,11 +215,15 @@ def run_cuda(args, arch_json, weights, config):
   def step_resident():
     arch.predict(feats_dev)
 
-  def step_e2e():
-    res = arch.predict(pinned)[0]
-    for k, v in res.items():
-      out_host[k].copy_(v, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+  # end-to-end arm: the same public call fed from PINNED HOST buffers, results copied back to pinned host buffers, with
+  # the upload of frame i+1 / download of frame i-1 overlapped with the kernels of frame i (deepdenoiser_b200/pipeline.py)
+  from deepdenoiser_b200.pipeline import FramePipeline
+  pipeline = FramePipeline(arch)
+  checks = []
+
+  def run_e2e(steps):
+    pipeline.run([pinned] * steps, on_result=lambda i, out: checks.append(float(out[first_key][0, 0, 0, 0])))
+    torch.cuda.current_stream().wait_stream(pipeline.s_out)
 
   for _ in range(max(args.warmup, 3)):
     step_resident()
@@ -229,9 +234,9 @@ def run_cuda(args, arch_json, weights, config):
   launches = arch.ctx.launch_count() - l0
   sampler.stop_flag.set()
   sampler.join(timeout=2)
-  for _ in range(2):
-    step_e2e()
-  e2e_ms = timed_loop(step_e2e, args.steps)
+  first_key = next(iter(out[0]))
+  run_e2e(2)
+  e2e_ms = timed_loop(lambda: run_e2e(args.steps), 1)
 
   ms_per_step = total_ms / args.steps
   mp = HEIGHT * WIDTH / 1e6

@@ -193,7 +193,8 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
   p.a_slot_bytes = static_cast<uint32_t>(round_up(static_cast<int>(p.a_tx_bytes), 1024));
   p.b_tile_bytes = static_cast<uint32_t>(n_r * p.cpad) * 128u;
   p.b_tx_bytes = p.b_tile_bytes;
-  const size_t fixed = 32768 /*staging*/ + 1024 /*bias*/ + 3072 /*barriers + MMA plans*/;
+  const size_t stage_bytes = static_cast<size_t>(kRowsEpiWarps) * 4096;   // one 4 KB staging row set per epilogue warp
+  const size_t fixed = stage_bytes + 1024 /*bias*/ + 3072 /*barriers + MMA plans*/;
   const size_t avail = ctx->max_smem_optin - 1024 /*alignment slack*/ - fixed;
   const size_t w_total = static_cast<size_t>(p.n_chunks) * p.n_s * p.b_tile_bytes;
   size_t b_bytes;
@@ -224,7 +225,7 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
   p.a_off = 0;
   p.b_off = static_cast<uint32_t>(p.a_slots) * p.a_slot_bytes;
   p.stage_off = p.b_off + static_cast<uint32_t>(round_up(static_cast<int>(b_bytes), 1024));
-  p.bias_off = p.stage_off + 32768;
+  p.bias_off = p.stage_off + static_cast<uint32_t>(stage_bytes);
   p.bar_off = p.bias_off + 1024;
   const size_t smem = 1024 + p.bar_off + 3072;
 

@@ -22,7 +22,7 @@
 //   epilogue       4 warps: tcgen05.ld -> +bias (+residual) -> ReLU -> fp16/fp32 -> 128B-swizzled staging row in
 //                  shared memory -> one TMA store per 32 pixels x 64 channels (full-line writes; the tensor map
 //                  clips channels / pixels outside the view, sub-pixel views implement the pixel shuffle).
-//   warps          0-7: epilogue (two sets of four warps, one TMEM lane quarter each, alternating output rows)
+//   warps          0-7: epilogue (two sets of four warps, one TMEM lane quarter each, output rows round-robin)
 //                  8: A producer  9: B producer  10: TMEM allocator  11: MMA issuer
 //   grid           persistent: the N*strips*H output rows are split into gridDim contiguous ranges (+-1 row).
 #pragma once
@@ -30,7 +30,12 @@
 
 namespace dd {
 
-constexpr int kRowsThreads = 384;
+constexpr int kRowsEpiSets = 2;          // epilogue warp sets (4 warps each), output rows round-robin over the sets
+                                         // (3 sets measured slower: the issuing thread, not the epilogue, bounds small layers)
+constexpr int kRowsEpiWarps = 4 * kRowsEpiSets;
+constexpr int kRowsWarpA = kRowsEpiWarps, kRowsWarpB = kRowsEpiWarps + 1, kRowsWarpTmem = kRowsEpiWarps + 2,
+              kRowsWarpMma = kRowsEpiWarps + 3;   // highest warp id: preferred by the scheduler
+constexpr int kRowsThreads = 32 * (kRowsEpiWarps + 4);
 constexpr int kRowsTileW = 128;
 constexpr int kRowsMaxRing = 8;
 
@@ -138,7 +143,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == kRowsWarpA && lane == 0) {
     tma_prefetch_desc(&maps.a);
     tma_prefetch_desc(&maps.b);
     tma_prefetch_desc(&maps.out[0]);
@@ -147,7 +152,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
     for (int i = 0; i < kRowsMaxRing; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_mbar_init();
   }
-  if (warp == 10) {
+  if (warp == kRowsWarpTmem) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -162,7 +167,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
   const int t_lo_off = p.rm_lo - 1;   // first input row of a segment = y0 + t_lo_off
   const int t_hi_off = p.rm_hi - 2;   // last input row           = y1 + t_hi_off
 
-  if (warp == 8) {
+  if (warp == kRowsWarpA) {
     // ------------------------------------------------------------------ A producer: one input row x one 64ch chunk per item
     if (elect_one()) {
       RowsWalker walk(p);
@@ -184,7 +189,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kRowsWarpB) {
     // ------------------------------------------------------------------ B producer
     if (elect_one()) {
       if (p.w_resident) {
@@ -213,7 +218,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
         }
       }
     }
-  } else if (warp == 11) {
+  } else if (warp == kRowsWarpMma) {
     // ------------------------------------------------------------------ MMA issuer (highest warp id: the scheduler
     // prefers it over the epilogue warp sharing its sub-partition)
     if (elect_one()) {
@@ -300,6 +305,10 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
         uint32_t use_top = q_top0 / static_cast<uint32_t>(ring);
         if (p.G == 1) {
           // ---------------- one input row at a time (weights resident, or a single-row weight pass)
+          // The barrier probes of row t+1 (its first A slot, the accumulator block it initialises) are issued right
+          // after the waits of row t: their ~100-200 cycle latency then overlaps the UMMAs of row t instead of idling
+          // the tensor pipe between rows; a failed probe falls back to the blocking wait.
+          bool probed = false, probe_a = false, probe_e = false;
           for (int t = t_first; t <= t_last; ++t, ++it) {
             const bool tr = p.trace && blockIdx.x == 0 && it < 64;
             if (tr) p.trace[it * 8 + 0] = clock64();
@@ -323,10 +332,26 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
             const bool initialises = (r_lo == rm_lo);
             for (int c = 0; c < n_chunks; ++c) {
               const int ksteps = (c == n_chunks - 1) ? p.ksteps_last : 4;
-              mbar_wait(&a_full[a_slot], a_phase);
-              if (c == 0 && initialises) mbar_wait(&acc_empty[blk], (use & 1u) ^ 1u);   // previous user drained
+              if (!(c == 0 && probed && probe_a)) mbar_wait(&a_full[a_slot], a_phase);
+              if (c == 0 && initialises && !(probed && probe_e))
+                mbar_wait(&acc_empty[blk], (use & 1u) ^ 1u);                              // previous user drained
               tc_fence_after();
               if (tr && c == 0) p.trace[it * 8 + 2] = clock64();
+              if (c == 0) {
+                probed = false;
+                if (t < t_last) {
+                  int nslot = a_slot + n_chunks; uint32_t nphase = a_phase;
+                  while (nslot >= a_slots) { nslot -= a_slots; nphase ^= 1; }
+                  int nr_lo = t + 3 - sg.y1; if (nr_lo < rm_lo) nr_lo = rm_lo;
+                  int nbt = blk_top - 1; uint32_t nut = use_top;
+                  if (nbt < 0) { nbt = ring - 1; ++nut; }
+                  int nblk = nbt + nr_lo;
+                  if (nblk >= ring) { nblk -= ring; nut -= 1u; }
+                  probe_a = mbar_try_wait(&a_full[nslot], nphase);
+                  probe_e = (nr_lo != rm_lo) || mbar_try_wait(&acc_empty[nblk], (nut & 1u) ^ 1u);
+                  probed = true;
+                }
+              }
               const uint32_t a_lo0 = d_lo + ((a_base + static_cast<uint32_t>(a_slot) * a_slot_bytes) >> 4);
               for (int si = 0; si < n_s; ++si) {
                 uint32_t b_tile;
@@ -429,10 +454,13 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
         q_seg += static_cast<uint32_t>(sg.y1 - sg.y0);
       }
     }
-  } else if (warp < 8) {
-    // ------------------------------------------------------------------ epilogue: 2 sets of 4 warps, rows alternate
+  } else if (warp < kRowsEpiWarps) {
+    // ------------------------------------------------------------------ epilogue: sets of 4 warps, rows round-robin
     const int wq = warp & 3;                       // TMEM lane quarter
-    const int eset = warp >> 2;                    // rows with (q & 1) == eset
+    const int eset = warp >> 2;                    // rows with q % n_sets == eset
+    // A set may only wait for use u of an accumulator barrier after use u-1 completed (parity waits cannot tell
+    // phases two apart): its previous row q - n_sets must be at least as late as row q - ring, i.e. n_sets <= ring.
+    const uint32_t n_sets = (p.ring < kRowsEpiSets) ? static_cast<uint32_t>(p.ring) : static_cast<uint32_t>(kRowsEpiSets);
     uint8_t* stage = st_smem + static_cast<size_t>(warp) * 4096;   // one 4 KB staging row set per warp
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
     RowsWalker walk(p);
@@ -442,7 +470,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
     const uint32_t ring = static_cast<uint32_t>(p.ring);
     while (walk.next(sg)) {
       for (int j = sg.y0; j < sg.y1; ++j, ++q, ++it) {
-        if ((q & 1u) != static_cast<uint32_t>(eset)) continue;
+        if (q % n_sets != static_cast<uint32_t>(eset)) continue;
         const int blk = p.ring - 1 - static_cast<int>(q % ring);
         const uint32_t use = q / ring;
         const bool tr = p.trace && blockIdx.x == 0 && it < 64 && wq == 0 && lane == 0;
@@ -542,7 +570,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 10) {
+  if (warp == kRowsWarpTmem) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
