@@ -200,74 +200,6 @@ __global__ void __launch_bounds__(256) assemble_kernel(const AssembleParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Kernel-prediction apply.  LANES threads cooperate on one pixel (LANES = 32 for large K so that the
-// K*K logits of a pixel are read as one coalesced run; 4 for small K).  The symmetric-padded source
-// tile lives in shared memory as float4 (rgb + pad) so a tap is one LDS.128.
-constexpr int kKpTileH = 8, kKpTileW = 32, kKpThreads = 256;
-struct KpParams {
-  View src, logits, out;
-  int K, F, ipt;     // kernel size, features per logits tensor, images per tuple
-  int tiles_x, tiles_y;
-};
-
-template <int LANES>
-__global__ void __launch_bounds__(kKpThreads) kernel_predict_kernel(const KpParams p) {
-  extern __shared__ float4 s_src[];
-  const int K = p.K, K2 = K * K, pad = (K - 1) / 2;
-  const int TW = kKpTileW + 2 * pad, TH = kKpTileH + 2 * pad;
-  // logits image b = tuple * ipt + n, feature f  ->  src/out image (tuple * F + f) * ipt + n
-  const int b = blockIdx.z / p.F, f = blockIdx.z % p.F;
-  const int img = ((b / p.ipt) * p.F + f) * p.ipt + (b % p.ipt);
-  const int ty0 = blockIdx.y * kKpTileH, tx0 = blockIdx.x * kKpTileW;
-  const int h = p.src.h, w = p.src.w;
-  for (int i = threadIdx.x; i < TW * TH; i += kKpThreads) {
-    const int ly = i / TW, lx = i % TW;
-    const int yy = sym_index(ty0 + ly - pad, h), xx = sym_index(tx0 + lx - pad, w);
-    const size_t sp = p.src.pix(img, yy, xx);
-    s_src[i] = make_float4(p.src.load(sp, 0), p.src.load(sp, 1), p.src.load(sp, 2), 0.f);
-  }
-  __syncthreads();
-  constexpr int PIX_PER_PASS = kKpThreads / LANES;
-  const int sub = threadIdx.x % LANES;
-  const int grp = threadIdx.x / LANES;
-  const int coff = f * K2;
-  for (int pp = grp; pp < kKpTileH * kKpTileW; pp += PIX_PER_PASS) {
-    const int ly = pp / kKpTileW, lx = pp % kKpTileW;
-    const int y = ty0 + ly, x = tx0 + lx;
-    const bool valid = (y < h) && (x < w);   // uniform across the LANES of a pixel
-    const size_t lpix = valid ? p.logits.pix(b, y, x) : 0;
-    // pass 1: max
-    float mx = -INFINITY;
-    if (valid) for (int t = sub; t < K2; t += LANES) mx = fmaxf(mx, p.logits.load(lpix, coff + t));
-#pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    // pass 2: exp, sum, weighted source
-    float sum = 0.f, r = 0.f, g = 0.f, bl = 0.f;
-    if (valid) {
-      for (int t = sub; t < K2; t += LANES) {
-        const float e = __expf(p.logits.load(lpix, coff + t) - mx);
-        const int i = t / K, j = t - i * K;
-        const float4 sv = s_src[(ly + i) * TW + lx + j];
-        sum += e;
-        r = fmaf(e, sv.x, r); g = fmaf(e, sv.y, g); bl = fmaf(e, sv.z, bl);
-      }
-    }
-#pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) {
-      sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      r += __shfl_xor_sync(0xffffffffu, r, o);
-      g += __shfl_xor_sync(0xffffffffu, g, o);
-      bl += __shfl_xor_sync(0xffffffffu, bl, o);
-    }
-    if (valid && sub == 0) {
-      const float inv = 1.f / sum;
-      const size_t op = p.out.pix(img, y, x);
-      p.out.store(op, 0, r * inv); p.out.store(op, 1, g * inv); p.out.store(op, 2, bl * inv);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 constexpr int kComposeMaxC = 32;
 struct ComposeHeadParams {
   View small, large, y;
@@ -441,30 +373,6 @@ int dd_assemble_input(dd_ctx* ctx, const dd_gather_entry* table_dev, int tuples,
   p.table = table_dev; p.out = make_view(out); p.tuples = tuples; p.n = n;
   const size_t total = static_cast<size_t>(out->n) * out->h * out->w;
   assemble_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  DD_LAUNCH_CHECK(ctx);
-  return DD_OK;
-}
-
-int dd_kernel_predict_fwd(dd_ctx* ctx, const dd_tensor* src, const dd_tensor* logits, int ksize, int features,
-                          int images_per_tuple, const dd_tensor* out, void* stream) {
-  DD_CHECK_ARG(ctx && tensor_ok(src) && tensor_ok(logits) && tensor_ok(out), "bad argument");
-  DD_CHECK_ARG(ksize >= 1 && (ksize & 1) && ksize <= 31, "kernel size must be odd and <= 31");
-  DD_CHECK_ARG(features >= 1 && logits->c == features * ksize * ksize, "logits must have features*K*K channels");
-  DD_CHECK_ARG(src->c == 3 && out->c == 3 && src->dtype == DD_F32 && out->dtype == DD_F32, "src/out must be fp32 rgb");
-  DD_CHECK_ARG(src->n == logits->n * features && out->n == src->n, "src/out batch must be logits.n * features");
-  DD_CHECK_ARG(src->h == logits->h && src->w == logits->w && same_spatial(src, out), "spatial dims differ");
-  KpParams p;
-  p.src = make_view(src); p.logits = make_view(logits); p.out = make_view(out);
-  DD_CHECK_ARG(images_per_tuple >= 1 && logits->n % images_per_tuple == 0, "logits.n must be a multiple of images_per_tuple");
-  p.K = ksize; p.F = features; p.ipt = images_per_tuple;
-  p.tiles_x = (src->w + kKpTileW - 1) / kKpTileW; p.tiles_y = (src->h + kKpTileH - 1) / kKpTileH;
-  const int pad = (ksize - 1) / 2;
-  const size_t smem = static_cast<size_t>(kKpTileW + 2 * pad) * (kKpTileH + 2 * pad) * sizeof(float4);
-  dim3 grid(p.tiles_x, p.tiles_y, src->n);
-  DD_CHECK_ARG(src->n <= 65535 && p.tiles_y <= 65535, "kernel_predict grid too large");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (ksize * ksize >= 64) kernel_predict_kernel<32><<<grid, kKpThreads, smem, s>>>(p);
-  else kernel_predict_kernel<4><<<grid, kKpThreads, smem, s>>>(p);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }
