@@ -347,8 +347,8 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
                   if (nbt < 0) { nbt = ring - 1; ++nut; }
                   int nblk = nbt + nr_lo;
                   if (nblk >= ring) { nblk -= ring; nut -= 1u; }
-                  probe_a = mbar_try_wait(&a_full[nslot], nphase);
-                  probe_e = (nr_lo != rm_lo) || mbar_try_wait(&acc_empty[nblk], (nut & 1u) ^ 1u);
+                  probe_a = mbar_test_wait(&a_full[nslot], nphase);
+                  probe_e = (nr_lo != rm_lo) || mbar_test_wait(&acc_empty[nblk], (nut & 1u) ^ 1u);
                   probed = true;
                 }
               }
@@ -475,11 +475,22 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
         const uint32_t use = q / ring;
         const bool tr = p.trace && blockIdx.x == 0 && it < 64 && wq == 0 && lane == 0;
         if (tr) p.trace[it * 8 + 4] = clock64();
+        const int x_in = sg.x0 + wq * 32 + lane;              // input-grid pixel of this thread (TMEM lane)
+        const int x_warp = sg.x0 + wq * 32;
+        // residual of a narrow layer (<= 32 channels): fetched before the accumulator wait so that its HBM latency
+        // overlaps the MMAs of this row, and kept for the relu-copy pass
+        const bool res_once = (p.residual != nullptr) && p.cout_store <= 32;
+        uint4 rv0[4];
+        if (res_once && x_in < p.W) {
+          const size_t opix = (static_cast<size_t>(sg.n) * p.H + j) * p.W + x_in;
+          const __half* rp = p.residual + opix * p.res_cstride + p.res_coff;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            rv0[i] = (i * 8 < p.cout_store) ? __ldg(reinterpret_cast<const uint4*>(rp + i * 8)) : make_uint4(0, 0, 0, 0);
+        }
         mbar_wait(&acc_full[blk], use & 1u);
         tc_fence_after();
         if (tr) p.trace[it * 8 + 5] = clock64();
-        const int x_in = sg.x0 + wq * 32 + lane;              // input-grid pixel of this thread (TMEM lane)
-        const int x_warp = sg.x0 + wq * 32;
         const uint32_t t_blk = t_lane + static_cast<uint32_t>(blk * p.cpad);
         uint8_t* row = stage + lane * 128;
         // the single staging set may be rewritten once the previous store of this warp has finished reading it
@@ -507,7 +518,10 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
               tmem_ld_32x32(t_blk + static_cast<uint32_t>(g * p.group_c + cb), v);
               uint4 rv[4];
               const bool has_res = (p.residual != nullptr) && (x_in < p.W);
-              if (has_res) {
+              if (has_res && res_once) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rv[i] = rv0[i];
+              } else if (has_res) {
                 const size_t opix = (static_cast<size_t>(sg.n) * p.H + j) * p.W + x_in;
                 const __half* rp = p.residual + opix * p.res_cstride + p.res_coff + cb;
 #pragma unroll

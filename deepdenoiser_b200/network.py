@@ -257,6 +257,7 @@ class DeviceNetwork:
     assert dtype in (torch.float16, torch.float32)
     self.ctx, self.spec, self.dtype = ctx, spec, dtype
     self.logits_dtype = logits_dtype if dtype == torch.float16 else torch.float32
+    self.fused_compose = True   # tests flip this to compare against the layer-by-layer path
     self.align = 8 if dtype == torch.float16 else 1
     if dtype == torch.float16:
       for f in spec.filters:
@@ -284,6 +285,14 @@ class DeviceNetwork:
       bias = torch.zeros(_round_up(var.cout, 16), dtype=torch.float32)
       bias[:var.cout] = torch.from_numpy(b)
       self.bias[var.name] = bias.to(dev)
+    self.compose_packed = None
+    if self.spec.compose and self.dtype == torch.float16:
+      head, c1, c2, c3, c4, tail = self.spec.compose
+      blob = _lib.pack_compose_weights(self.host[head.name][0], self.host[head.name][1],
+                                       [self.host[c.name][0] for c in (c1, c2, c3, c4)],
+                                       [self.host[c.name][1] for c in (c1, c2, c3, c4)],
+                                       self.host[tail.name][0], self.host[tail.name][1])
+      self.compose_packed = torch.from_numpy(blob).to(dev)
 
   # conv2d_transpose 3x3 stride 2 'same' (Tiramisu.py:62-64) = 4 output phases, each a stride-1
   # convolution of the input with a subset of the taps: out[2y+py, 2x+px] = sum_{dy,dx in {0,-1}}
@@ -471,6 +480,10 @@ class DeviceNetwork:
     """MultiScalePrediction.compose_scales (MultiScalePrediction.py:36-93) on fp32 image banks
     small [I,h/2,w/2,3], large [I,h,w,3] -> out [I,h,w,3]; `inv` fuses the inverse standardisation."""
     spec, ctx = self.spec, self.ctx
+    if self.compose_packed is not None and self.fused_compose:
+      # tensor-core mode: the whole weight net + blend is one launch, intermediates never leave shared memory
+      ctx.compose_scales(small.d, large.d, self.compose_packed, inv, out.d)
+      return
     i, h, w = large.t.shape[0], large.t.shape[1], large.t.shape[2]
     head, c1, c2, c3, c4, tail = spec.compose
     ta = V(self._buf("compose.a", (i, h, w, 24)))

@@ -285,6 +285,40 @@ def test_compose_head_tail_and_invert(ctx):
   close(xd, np_ops.signed_expm1(x.astype(np.float64)), 2e-6, "invert")
 
 
+@pytest.mark.parametrize("n,h,w,inv", [(1, 16, 32, False), (2, 20, 44, True), (1, 50, 70, False), (3, 6, 10, True)])
+def test_compose_scales_fused(ctx, n, h, w, inv):
+  """dd_compose_scales_fwd (one launch, fp16 activations in shared memory) against the float64 restatement of
+  MultiScalePrediction.compose_scales with the SAME weights; tiles, halos and image borders all occur."""
+  small = RNG.standard_normal((n, h // 2, w // 2, 3)).astype(np.float32)
+  large = (small.repeat(2, axis=1).repeat(2, axis=2) + 0.3 * RNG.standard_normal((n, h, w, 3))).astype(np.float32)
+  head_w = (RNG.standard_normal((1, 1, 6, 24)) * 0.4).astype(np.float32)
+  head_b = (RNG.standard_normal(24) * 0.1).astype(np.float32)
+  conv_w = [(RNG.standard_normal((3, 3, 24, 24)) * 0.08).astype(np.float32) for _ in range(4)]
+  conv_b = [(RNG.standard_normal(24) * 0.1).astype(np.float32) for _ in range(4)]
+  tail_w = (RNG.standard_normal((1, 1, 24, 1)) * 0.3).astype(np.float32)
+  tail_b = np.array([0.05], np.float32)
+  blob = torch.from_numpy(_lib.pack_compose_weights(head_w, head_b, conv_w, conv_b, tail_w, tail_b)).cuda()
+  out = torch.full((n, h, w, 3), float("nan"), device="cuda")
+  ip = _lib.dd_invert_params(1, 0.25, 2.0) if inv else None
+  ctx.compose_scales(_lib.desc(dev(small)), _lib.desc(dev(large)), blob, ip, _lib.desc(out))
+  f64 = lambda a: np.asarray(a, dtype=np.float64)
+  up = np_ops.resize_nearest_x2(f64(small))
+  x = np_ops.conv2d_same(np.concatenate([up, f64(large)], axis=3), f64(head_w), f64(head_b), relu=True)
+  for blk in range(2):
+    r = x
+    for i in range(2):
+      r = np_ops.conv2d_same(np.maximum(r, 0), f64(conv_w[2 * blk + i]), f64(conv_b[2 * blk + i]), relu=False)
+    x = x + r
+  wgt = np_ops.sigmoid(np_ops.conv2d_same(x, f64(tail_w), f64(tail_b), relu=True))
+  low = np_ops.resize_nearest_x2(np_ops.avg_pool_same(f64(large), 2))
+  want = f64(large) - wgt * low + wgt * up
+  if inv:
+    want = np_ops.signed_expm1(want * np.sqrt(2.0) + 0.25)
+  # fp16 activations between the layers: the blend weight carries ~1e-3 relative error
+  close(out, want, 1e-2, "fused compose")
+  assert np.abs(out.cpu().numpy() - want).mean() < 1e-3
+
+
 def test_bad_arguments_are_reported_not_crashed(ctx):
   x = torch.zeros(1, 4, 4, 3, device="cuda")
   with pytest.raises(_lib.DDError, match="kernel size"):
