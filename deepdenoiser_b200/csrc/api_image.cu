@@ -123,30 +123,49 @@ __device__ __forceinline__ float standardize_value(float v, const dd_standardize
   return v;
 }
 
+// One 32 x 8 pixel tile per block.  The (standardised, unless compute_before_standardization) values of the tile and
+// its one-pixel symmetric halo are computed ONCE into shared memory (log1p is the expensive part), then every thread
+// forms the 3x3 / plus-shaped local mean and second moment of its pixel from shared memory.
+constexpr int kStdTileW = 32, kStdTileH = 8, kStdHaloW = kStdTileW + 2, kStdHaloH = kStdTileH + 2;
 __global__ void __launch_bounds__(256) standardize_variance_kernel(const StdParams p) {
-  const size_t total = static_cast<size_t>(p.src.n) * p.src.h * p.src.w;
-  const size_t pixel = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (pixel >= total) return;
-  const int x0 = static_cast<int>(pixel % p.src.w);
-  const int y0 = static_cast<int>((pixel / p.src.w) % p.src.h);
-  const int n = static_cast<int>(pixel / (static_cast<size_t>(p.src.w) * p.src.h));
-  const int C = p.src.c;
+  __shared__ float s_val[3][kStdHaloH * kStdHaloW];
+  const int n = blockIdx.z;
+  const int ty0 = blockIdx.y * kStdTileH, tx0 = blockIdx.x * kStdTileW;
+  const int h = p.src.h, w = p.src.w, C = p.src.c;
+  if (p.has_v) {
+    for (int i = threadIdx.x; i < kStdHaloH * kStdHaloW; i += 256) {
+      const int ly = i / kStdHaloW, lx = i - ly * kStdHaloW;
+      const int yy = sym_index(ty0 + ly - 1, h), xx = sym_index(tx0 + lx - 1, w);
+      const size_t sp = p.src.pix(n, yy, xx);
+      for (int c = 0; c < C; ++c) {
+        float v = p.src.load(sp, c);
+        if (!p.q.compute_before_standardization) v = standardize_value(v, p.q, p.inv_sqrt_var);
+        s_val[c][i] = v;
+      }
+    }
+    __syncthreads();
+  }
+  const int ly = threadIdx.x >> 5, lx = threadIdx.x & 31;
+  const int y0 = ty0 + ly, x0 = tx0 + lx;
+  if (y0 >= h || x0 >= w) return;
+  const size_t pixel = p.src.pix(n, y0, x0);
   float var_sum = 0.f;
   for (int c = 0; c < C; ++c) {
-    const float centre = standardize_value(p.src.load(pixel, c), p.q, p.inv_sqrt_var);
     if (p.has_s) {
+      const float centre = (p.has_v && !p.q.compute_before_standardization)
+                               ? s_val[c][(ly + 1) * kStdHaloW + lx + 1]
+                               : standardize_value(p.src.load(pixel, c), p.q, p.inv_sqrt_var);
       if (C == 1) { p.sout.store(pixel, 0, centre); p.sout.store(pixel, 1, centre); p.sout.store(pixel, 2, centre); }
       else p.sout.store(pixel, c, centre);
     }
     if (p.has_v) {
       float m = 0.f, m2 = 0.f;
-      for (int r = -1; r <= 1; ++r) {
-        const int yy = sym_index(y0 + r, p.src.h);
-        for (int s = -1; s <= 1; ++s) {
-          if (p.q.variance_mode == 1 && r != 0 && s != 0) continue;  // 'neighbor': plus-shaped stencil
-          const int xx = sym_index(x0 + s, p.src.w);
-          float v = p.src.load(p.src.pix(n, yy, xx), c);
-          if (!p.q.compute_before_standardization) v = standardize_value(v, p.q, p.inv_sqrt_var);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          if (p.q.variance_mode == 1 && r != 1 && s != 1) continue;  // 'neighbor': plus-shaped stencil
+          const float v = s_val[c][(ly + r) * kStdHaloW + lx + s];
           m += v;
           m2 += v * v;
         }
@@ -359,8 +378,9 @@ int dd_standardize_variance(dd_ctx* ctx, const dd_tensor* src, const dd_standard
     DD_CHECK_ARG(tensor_ok(var_out) && same_spatial(src, var_out) && var_out->c == vc, "var_out has wrong dims");
     p.vout = make_view(var_out); p.has_v = 1;
   }
-  const size_t total = static_cast<size_t>(src->n) * src->h * src->w;
-  standardize_variance_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_CHECK_ARG(src->n <= 65535 && (src->h + kStdTileH - 1) / kStdTileH <= 65535, "standardize: grid too large");
+  dim3 grid((src->w + kStdTileW - 1) / kStdTileW, (src->h + kStdTileH - 1) / kStdTileH, src->n);
+  standardize_variance_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }
