@@ -70,6 +70,7 @@ SIGNATURES = {
     "dd_compose_scales_fwd": (_i, [_vp, _T, _T, _vp, _P(dd_invert_params), _T, _vp]),
     "dd_invert_standardization": (_i, [_vp, _T, _P(dd_invert_params), _T, _vp]),
     "dd_relu_bwd": (_i, [_vp, _T, _T, _T, _vp]),
+    "dd_relu_bwd_acc": (_i, [_vp, _T, _T, _T, _vp]),
     "dd_muladd_fwd": (_i, [_vp, _T, _T, _T, _T, _vp]),
     "dd_muladd_bwd": (_i, [_vp, _T, _T, _T, _T, _T, _T, _vp]),
     "dd_axpy": (_i, [_vp, ctypes.c_float, _T, _T, _vp]),
@@ -78,6 +79,7 @@ SIGNATURES = {
     "dd_loss_fwd_bwd": (_i, [_vp, _T, _T, _i, ctypes.c_float, ctypes.c_float, _vp, _T, _i, _vp]),
     "dd_conv2d_wgrad": (_i, [_vp, _T, _T, _i, _i, _vp, _vp, _vp]),
     "dd_conv2d_transpose2x2_dgrad": (_i, [_vp, _T, _vp, _T, _vp]),
+    "dd_conv2d_transpose3x3_dgrad": (_i, [_vp, _T, _vp, _T, _vp]),
     "dd_conv2d_repack_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "dd_maxpool_s2_bwd": (_i, [_vp, _T, _T, _T, _i, _T, _vp]),
     "dd_kernel_predict_bwd": (_i, [_vp, _T, _T, _T, _i, _i, _i, _T, _vp]),

@@ -9,8 +9,7 @@
 // intermediate lives in shared memory: a CTA owns a 32x16 output tile, computes the 40x24 halo region of x0 and shrinks
 // by one pixel per 3x3 layer (t1 38x22, x1 36x20, t3 34x18, x2 32x16).  The 3x3 layers are implicit GEMMs on the warp-level
 // tensor-core path (mma.sync m16n8k16, fp16 operands, fp32 accumulate): M = 16 consecutive pixels of the layer's output
-// region, N = 24 output channels (3 n-tiles), K = 9 taps x 32 (24 channels + 8 read from the next pixel, multiplied by
-// zero weight rows).  A fragments come from ldmatrix over the [pixel][24 ch] fp16 activation buffers (48-byte pixel
+// region, N = 24 output channels (3 n-tiles), K = 9 taps x 24 (one k16 + one k8 step per tap).  A fragments come from ldmatrix over the [pixel][24 ch] fp16 activation buffers (48-byte pixel
 // pitch: conflict-free), B fragments from the XOR-swizzled [tap][n][32] weights resident in shared memory.  ReLU on a
 // layer INPUT is applied to the A fragments in registers, so x1 is stored once (raw) and serves both as the input of
 // the third convolution and as the residual of the fourth.  Pixels outside the image are forced to zero after every
@@ -57,6 +56,15 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_1688(float (&d)[4], const uint32_t (&a)[2], uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(b0));
 }
 __device__ __forceinline__ uint32_t relu_h2(uint32_t v) {
   __half2 h = *reinterpret_cast<__half2*>(&v);
@@ -115,7 +123,7 @@ __device__ __forceinline__ void cf_conv_layer(const uint8_t* in, uint8_t* out, c
       int pl = (grp * 2 + mt) * 16 + ld_row;
       if (pl > NPIX - 1) pl = NPIX - 1;
       const int y = pl / WO, x = pl - y * WO;
-      a_addr[mt] = in_u32 + static_cast<uint32_t>((y * WI + x) * kCfPixBytes) + ld_k;
+      a_addr[mt] = in_u32 + static_cast<uint32_t>((y * WI + x) * kCfPixBytes);
     }
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
@@ -123,18 +131,23 @@ __device__ __forceinline__ void cf_conv_layer(const uint8_t* in, uint8_t* out, c
       uint32_t b[3][4];
 #pragma unroll
       for (int nt = 0; nt < 3; ++nt) ldmatrix_x4(b[nt], w_u32 + tap * (kCfC * 64) + b_off[nt]);
+      // K = 24 exactly: channels 0..15 as one k16 step, channels 16..23 as one k8 step (the legacy tensor path is the
+      // bound of this kernel, so no multiply-by-zero padding)
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint32_t a_tap = a_addr[mt] + static_cast<uint32_t>((dy * WI + dx) * kCfPixBytes);
+        uint32_t a[4], a8[2];
+        ldmatrix_x4(a, a_tap + ld_k);
+        ldmatrix_x2(a8, a_tap + 32);
+        if (RELU_IN) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          uint32_t a[4];
-          ldmatrix_x4(a, a_addr[mt] + static_cast<uint32_t>((dy * WI + dx) * kCfPixBytes + ks * 32));
-          if (RELU_IN) {
+          for (int i = 0; i < 4; ++i) a[i] = relu_h2(a[i]);
+          a8[0] = relu_h2(a8[0]); a8[1] = relu_h2(a8[1]);
+        }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = relu_h2(a[i]);
-          }
-#pragma unroll
-          for (int nt = 0; nt < 3; ++nt) mma_16816(acc[mt][nt], a, b[nt][2 * ks], b[nt][2 * ks + 1]);
+        for (int nt = 0; nt < 3; ++nt) {
+          mma_16816(acc[mt][nt], a, b[nt][0], b[nt][1]);
+          mma_1688(acc[mt][nt], a8, b[nt][2]);
         }
       }
     }

@@ -55,11 +55,11 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const ConvSimtParams p) 
   for (int r = 0; r < p.ksize; ++r) {
     int yy = y0 + r - pad;
     if (yy < 0 || yy >= p.oh) continue;
-    if (p.x_ups == 2) yy = 2 * yy + p.x_ay;
+    if (p.x_ups == 2) { yy = 2 * yy + p.x_ay; if (yy >= p.x.h) continue; }   // tap 2 of a 3x3 stride-2 lattice leaves the image
     for (int s = 0; s < p.ksize; ++s) {
       int xx = x0 + s - pad;
       if (xx < 0 || xx >= p.ow) continue;
-      if (p.x_ups == 2) xx = 2 * xx + p.x_ax;
+      if (p.x_ups == 2) { xx = 2 * xx + p.x_ax; if (xx >= p.x.w) continue; }
       const size_t ipix = p.x.pix(n0, yy, xx);
       const float* wt = p.w + (static_cast<size_t>(r * p.ksize + s) * p.cout + co0) * cin;
       for (int c = 0; c < cin; ++c) {
@@ -554,6 +554,22 @@ int dd_conv2d_transpose2x2_dgrad(dd_ctx* ctx, const dd_tensor* dz, const float* 
   for (int sp = 0; sp < 4; ++sp) {
     const float* w = w_dgrad + static_cast<size_t>(sp) * dx->c * dz->c;
     int rc = launch_conv_simt(ctx, dz, w, nullptr, 1, dx->c, 0, sp == 0 ? nullptr : dx, dx, nullptr, -2, sp >> 1, sp & 1, s);
+    if (rc) return rc;
+  }
+  return DD_OK;
+}
+
+/* dx = conv2d_transpose_3x3_s2^T (dz) (Tiramisu.py:62-64): dx[i,j,c] = sum_{r,s,o} dz[2i+r,2j+s,o] W[r,s,o,c], taps that
+ * leave the image contribute nothing (TF 'SAME': the transposed conv keeps rows/cols [0, 2n) of the 2n+1 it produces).
+ * w_dgrad: [tap][cin][cout] fp32 (dd_conv2d_repack_f32 with transposed = 1, ksize = 3). */
+int dd_conv2d_transpose3x3_dgrad(dd_ctx* ctx, const dd_tensor* dz, const float* w_dgrad, const dd_tensor* dx, void* stream) {
+  DD_CHECK_ARG(ctx && w_dgrad && tensor_ok(dz) && tensor_ok(dx), "bad argument");
+  DD_CHECK_ARG(dz->dtype == DD_F32 && dx->dtype == DD_F32, "exact path only");
+  DD_CHECK_ARG(dz->n == dx->n && dz->h == 2 * dx->h && dz->w == 2 * dx->w, "transpose3x3_dgrad: dz must be 2x dx");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int tap = 0; tap < 9; ++tap) {
+    const float* w = w_dgrad + static_cast<size_t>(tap) * dx->c * dz->c;
+    int rc = launch_conv_simt(ctx, dz, w, nullptr, 1, dx->c, 0, tap == 0 ? nullptr : dx, dx, nullptr, -2, tap / 3, tap % 3, s);
     if (rc) return rc;
   }
   return DD_OK;

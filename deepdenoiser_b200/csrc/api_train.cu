@@ -15,7 +15,7 @@ inline bool same_dims(const dd_tensor* a, const dd_tensor* b) {
 
 // ------------------------------------------------------------------------------------------------ elementwise
 struct Ewise { View a, b, c, out, out2, out3; int op; float alpha; };
-enum { EW_RELU_MASK = 0, EW_MULADD = 1, EW_MULADD_BWD = 2, EW_AXPY = 3, EW_FILL = 4, EW_INVERT_BWD = 5 };
+enum { EW_RELU_MASK = 0, EW_MULADD = 1, EW_MULADD_BWD = 2, EW_AXPY = 3, EW_FILL = 4, EW_INVERT_BWD = 5, EW_RELU_MASK_ACC = 6 };
 struct EwiseInv { int use_log1p; float mean, variance, sqrt_var; };
 
 __global__ void __launch_bounds__(256) ewise_kernel(const Ewise p, const EwiseInv q) {
@@ -27,6 +27,9 @@ __global__ void __launch_bounds__(256) ewise_kernel(const Ewise p, const EwiseIn
   switch (p.op) {
     case EW_RELU_MASK:      // out = a * [b > 0]        (dz = dy . relu'(y))
       p.out.store(pix, ch, p.b.load(pix, ch) > 0.f ? p.a.load(pix, ch) : 0.f);
+      break;
+    case EW_RELU_MASK_ACC:  // out += a * [b > 0]       (dense-block concat: several consumers add into one gradient)
+      if (p.b.load(pix, ch) > 0.f) p.out.store(pix, ch, p.out.load(pix, ch) + p.a.load(pix, ch));
       break;
     case EW_MULADD:         // out = a * (b + c)        (lighting = color * (direct + indirect), Training.py:420-428)
       p.out.store(pix, ch, p.a.load(pix, ch) * (p.b.load(pix, ch) + p.c.load(pix, ch)));
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(const WgradParams p) 
     float v = 0.f;
     if (o < cout_n && yy < p.x.h && xx < p.x.w) {
       const int zy = (p.ups == 2) ? 2 * yy + p.ay : yy, zx = (p.ups == 2) ? 2 * xx + p.ax : xx;
-      v = p.dz.load(p.dz.pix(n, zy, zx), p.o0 + o);
+      if (zy < p.dz.h && zx < p.dz.w) v = p.dz.load(p.dz.pix(n, zy, zx), p.o0 + o);   // 3x3 stride-2 taps may leave the image
     }
     sdz[i] = v;
   }
@@ -447,6 +450,16 @@ int dd_relu_bwd(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const dd_t
   return DD_OK;
 }
 
+int dd_relu_bwd_acc(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const dd_tensor* dz_acc, void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(dy) && tensor_ok(y) && tensor_ok(dz_acc) && same_dims(dy, y) && same_dims(dy, dz_acc), "bad argument");
+  Ewise p; memset(&p, 0, sizeof(p)); EwiseInv q; memset(&q, 0, sizeof(q));
+  p.a = make_view(dy); p.b = make_view(y); p.out = make_view(dz_acc); p.op = EW_RELU_MASK_ACC;
+  const size_t total = static_cast<size_t>(dy->n) * dy->h * dy->w * dy->c;
+  ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
 int dd_muladd_fwd(dd_ctx* ctx, const dd_tensor* a, const dd_tensor* b, const dd_tensor* c, const dd_tensor* out, void* stream) {
   DD_CHECK_ARG(ctx && tensor_ok(a) && tensor_ok(b) && tensor_ok(c) && tensor_ok(out) && same_dims(a, b) && same_dims(a, c) &&
                    same_dims(a, out), "bad argument");
@@ -528,7 +541,8 @@ int dd_conv2d_wgrad(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int ks
     DD_CHECK_ARG(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
     DD_CHECK_ARG(x->n == dz->n && x->h == dz->h && x->w == dz->w, "wgrad: spatial dims differ");
   } else {
-    DD_CHECK_ARG(ksize == 2 && dz->n == x->n && dz->h == 2 * x->h && dz->w == 2 * x->w, "transposed wgrad: dz must be 2x");
+    DD_CHECK_ARG((ksize == 2 || ksize == 3) && dz->n == x->n && dz->h == 2 * x->h && dz->w == 2 * x->w,
+                 "transposed wgrad: ksize 2 or 3, dz must be 2x");
   }
   const int kk = transposed ? 1 : ksize;
   const int pad = (kk - 1) / 2;
@@ -539,14 +553,17 @@ int dd_conv2d_wgrad(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int ks
   p.tiles_x = (x->w + kWgTileW - 1) / kWgTileW; p.tiles_y = (x->h + kWgTileH - 1) / kWgTileH;
   dim3 grid(p.tiles_x, p.tiles_y, x->n);
   DD_CHECK_ARG(x->n <= 65535 && p.tiles_y <= 65535, "wgrad grid too large");
-  const int subs = transposed ? 4 : 1;
+  // transposed: one launch per tap (a, b) of the k x k stride-2 kernel: dW[a,b,o,c] = sum x[i,j,c] dz[2i+a,2j+b,o]
+  const int subs = transposed ? ksize * ksize : 1;
   for (int sp = 0; sp < subs; ++sp) {
+    const int tap_a = transposed ? sp / ksize : 0, tap_b = transposed ? sp % ksize : 0;
     for (int c0 = 0; c0 < cin; c0 += kWgMaxC) {
       for (int o0 = 0; o0 < cout; o0 += kWgMaxC) {
         p.c0 = c0; p.o0 = o0;
-        p.ups = transposed ? 2 : 1; p.ay = sp >> 1; p.ax = sp & 1; p.transposed_layout = transposed;
+        p.ups = transposed ? 2 : 1; p.ay = tap_a; p.ax = tap_b; p.transposed_layout = transposed;
         p.dw = transposed ? dw + static_cast<size_t>(sp) * cout * cin : dw;
-        p.db = (sp == 0 || !transposed) ? db : db;   // bias sums every sub-pixel
+        // bias gradient = sum over ALL dz pixels: taps (a, b) in {0,1}^2 visit every pixel exactly once
+        p.db = (!transposed || (tap_a < 2 && tap_b < 2)) ? db : nullptr;
         wgrad_kernel<<<grid, kWgThreads, smem, s>>>(p);
         DD_LAUNCH_CHECK(ctx);
       }

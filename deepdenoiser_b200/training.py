@@ -3,7 +3,7 @@ forward with saved activations, the loss of BaseFeatureTraining.loss / LossDiffe
 every op as explicit libdd_b200 kernels, TF-form Adam on one flat fp32 parameter buffer and (multi-GPU) one
 all-reduce of the flat gradient buffer per step.
 
-Round-1 scope: the EXACT fp32 path (CUDA-core convolutions), U-Net backbone, loss weights of
+Round-1 scope: the EXACT fp32 path (CUDA-core convolutions), U-Net and Tiramisu backbones, loss weights of
 TrainingExample.json (mean weights; variation / MS-SSIM / masked weights must be 0).  Every gradient is
 parity-tested against torch-autograd of the oracle (tests/test_gpu_training.py).  Tensor-core backward kernels
 (dgrad through conv_rows_kernel, MN-major tcgen05 wgrad) are the next step.
@@ -59,8 +59,6 @@ class Trainer:
 
   def __init__(self, architecture, settings=None):
     assert isinstance(architecture, Architecture)
-    if architecture.spec.core_name != "U-Net":
-      raise NotImplementedError("training is built for the U-Net backbone only in this round")
     self.arch = architecture
     self.settings = settings or TrainingSettings()
     architecture.dtype = torch.float32            # exact path
@@ -123,6 +121,23 @@ class Trainer:
         self._packed_store[key] = (torch.empty(w.numel(), dtype=torch.float32, device=self.dev),
                                    torch.empty(w.numel(), dtype=torch.float32, device=self.dev))
       f, b = self._packed_store[key]
+      if var.transposed and var.ksize == 3:
+        # forward = 4 output phases, each an ordinary 3x3 'same' kernel holding a subset of the taps (network.py
+        # _pack_transpose3x3); SIMT layout [tap][cout][cin] == TF conv2d_transpose [kh,kw,cout,cin] per tap
+        ctx.call("dd_conv2d_repack_f32", _fp(w), 3, var.cin, var.cout, 1, None, _fp(b))
+        k = w.view(3, 3, var.cout, var.cin)
+        phases = []
+        for py in range(2):
+          for px in range(2):
+            ph = torch.zeros_like(k)
+            for dy in (0, -1):
+              for dx in (0, -1):
+                r, c = py - 2 * dy, px - 2 * dx
+                if r <= 2 and c <= 2:
+                  ph[dy + 1, dx + 1] = k[r, c]
+            phases.append(ph.contiguous())
+        self.fwd[key], self.bwd[key] = phases, b
+        continue
       ctx.call("dd_conv2d_repack_f32", _fp(w), var.ksize, var.cin, var.cout, int(var.transposed), _fp(f), _fp(b))
       self.fwd[key], self.bwd[key] = f, b
     if self.spec.compose:
@@ -202,10 +217,15 @@ class Trainer:
     block("l", spec.last, x, out)
     results.append(out)
     tape["results"] = results
-    # post-processing 1x1 convs
+    self._post_forward(tape)
+    return tape
+
+  def _post_forward(self, tape):
+    """AdjustNumberOfChannels (Architecture.py:230-244): conv1x1 + ReLU, conv1x1 on every core output (coarsest first)."""
+    spec = self.spec
     tape["post"] = []
     logits = []
-    for k, (r, (a, bvar)) in enumerate(zip(results, spec.post)):
+    for k, (r, (a, bvar)) in enumerate(zip(tape["results"], spec.post)):
       bb, hh, ww = r.t.shape[0], r.t.shape[1], r.t.shape[2]
       mid = V(self._buf("post.mid%d" % k, (bb, hh, ww, spec.output_channels)))
       self._conv(a, r, mid, relu=True)
@@ -214,7 +234,19 @@ class Trainer:
       tape["post"].append((a, bvar, r, mid, out_l))
       logits.append(out_l)
     tape["logits_coarse_first"] = logits
-    return tape
+
+  def _post_backward(self, tape, dlogits_coarse_first):
+    """Returns {id(core output buffer): gradient V} and accumulates the 1x1 weights' gradients."""
+    dres = {}
+    for k, ((a, bvar, r, mid, out_l), dl) in enumerate(zip(tape["post"], dlogits_coarse_first)):
+      dmid = V(self._buf("post.dmid%d" % k, tuple(mid.t.shape)))
+      self._conv_bwd(bvar, mid, dl, dmid)
+      dz = V(self._buf("post.dz%d" % k, tuple(mid.t.shape)))
+      self._relu_bwd(dmid, mid, dz)
+      dr = V(self._buf("post.dr%d" % k, tuple(r.t.shape[:3]) + (a.cin,)))
+      self._conv_bwd(a, r, dz, dr)
+      dres[id(r.t)] = dr
+    return dres
 
   def _block_bwd(self, key, layers, acts, dout):
     """Backward through n x [conv + ReLU]; dout = dL/d(acts[-1]); returns dL/d(acts[0]) (fresh buffer)."""
@@ -233,15 +265,7 @@ class Trainer:
     spec, f, steps, ctx = self.spec, self.spec.filters, self.spec.steps, self.ctx
     blocks = {key: (layers, acts) for key, layers, acts in tape["blocks"]}
     # 1x1 post-processing -> gradient of every core output
-    dres = {}
-    for k, ((a, bvar, r, mid, out_l), dl) in enumerate(zip(tape["post"], dlogits_coarse_first)):
-      dmid = V(self._buf("post.dmid%d" % k, tuple(mid.t.shape)))
-      self._conv_bwd(bvar, mid, dl, dmid)
-      dz = V(self._buf("post.dz%d" % k, tuple(mid.t.shape)))
-      self._relu_bwd(dmid, mid, dz)
-      dr = V(self._buf("post.dr%d" % k, tuple(r.t.shape[:3]) + (a.cin,)))
-      self._conv_bwd(a, r, dz, dr)
-      dres[id(r.t)] = dr
+    dres = self._post_backward(tape, dlogits_coarse_first)
     # decoder: last block, then (transposed conv, block) pairs from fine to coarse
     layers, acts = blocks["l"]
     dcat = {0: self._block_bwd("l", layers, acts, dres[id(tape["results"][-1].t)])}    # dL/d cat_0, both halves
@@ -274,6 +298,116 @@ class Trainer:
       layers, acts = blocks["d%d" % i]
       dpool = self._block_bwd("d%d" % i, layers, acts, dskip)
     return dpool                                                     # dL/dx0
+
+  # ------------------------------------------------------------------------------------------ Tiramisu forward / backward
+  # Same buffer plan as the inference path (network.py::_forward_tiramisu): per level one raw and one ReLU'd buffer whose
+  # channel windows ARE the concatenations (Tiramisu.py:40,104).  The backward keeps one gradient buffer per level with the
+  # same channel layout; a consumer that read relu(x) adds  dact * [raw > 0]  into it (dd_relu_bwd_acc), so by the time a
+  # layer's output window is used as dz every later reader has contributed.
+  def _tiramisu_forward(self, x0):
+    spec, f, steps, ctx = self.spec, self.spec.filters, self.spec.steps, self.ctx
+    b, h, w = x0.t.shape[0], x0.t.shape[1], x0.t.shape[2]
+    dims = [(h >> i, w >> i) for i in range(steps + 1)]
+    n = spec.convs_per_block
+    totals = {steps: spec.skip_channels[steps - 1] + n * f[steps]}
+    for level in range(steps):
+      totals[level] = spec.skip_channels[level] + f[level] + n * f[level]
+    raws = {l: self._buf("tira.raw%d" % l, (b,) + dims[l] + (totals[l],)) for l in totals}
+    acts = {l: self._buf("tira.act%d" % l, (b,) + dims[l] + (totals[l],)) for l in totals}
+    tape = {"x0": x0, "raws": raws, "acts": acts, "dims": dims, "totals": totals, "trans": [], "blocks": []}
+
+    def dense(layers, level, c):
+      for var in layers:
+        self._conv(var, V(acts[level], c, 0), V(raws[level], var.cout, c), relu=False, y_relu=V(acts[level], var.cout, c))
+        c += var.cout
+      return c
+
+    self._conv(spec.pre, x0, V(raws[0], f[0], 0), relu=True, y_relu=V(acts[0], f[0], 0))
+    c = f[0]
+    for i in range(steps):
+      c0 = c
+      c = dense(spec.down[i], i, c)
+      tape["blocks"].append(("down", i, i, spec.down[i], c0))
+      z = self._buf("tira.z%d" % i, (b,) + dims[i] + (c,))
+      za = self._buf("tira.za%d" % i, (b,) + dims[i] + (c,))
+      self._conv(spec.transition[i], V(acts[i], c, 0), V(z), relu=False, y_relu=V(za))
+      ctx.maxpool_s2(V(z).d, 2, V(raws[i + 1], c, 0).d)
+      ctx.maxpool_s2(V(za).d, 2, V(acts[i + 1], c, 0).d)
+      tape["trans"].append((i, c, z))
+    results, ups = [], []
+    for i in range(steps):
+      index = steps - i
+      c0 = c
+      c = dense(spec.up[i], index, c)
+      tape["blocks"].append(("up", i, index, spec.up[i], c0))
+      if spec.use_multiscale:
+        results.append(V(raws[index], c, 0))
+      var, level = spec.upsample[i], index - 1
+      cs = spec.skip_channels[level]
+      ctx.conv2d_transpose3x3(V(raws[index], c, 0).d, self.fwd[var.name], self.bias[var.name], V(raws[level], var.cout, cs).d,
+                              V(acts[level], var.cout, cs).d, relu=True)
+      ups.append((var, index, c, level, cs))
+      c = cs + var.cout
+    c0 = c
+    c = dense(spec.last, 0, c)
+    tape["blocks"].append(("last", 0, 0, spec.last, c0))
+    results.append(V(raws[0], c, 0))
+    tape["results"], tape["ups"] = results, ups
+    self._post_forward(tape)
+    return tape
+
+  def _tiramisu_backward(self, tape, dlogits_coarse_first):
+    spec, f, steps, ctx = self.spec, self.spec.filters, self.spec.steps, self.ctx
+    raws, acts, dims, totals = tape["raws"], tape["acts"], tape["dims"], tape["totals"]
+    b = tape["x0"].t.shape[0]
+    G = {l: self._buf("tira.g%d" % l, (b,) + dims[l] + (totals[l],), zero=True) for l in totals}
+    dres = self._post_backward(tape, dlogits_coarse_first)
+    for r in tape["results"]:
+      level = [l for l in raws if raws[l] is r.t][0]
+      ctx.call("dd_axpy", ctypes.c_float(1.0), _b(dres[id(r.t)].d), _b(V(G[level], r.c, 0).d))
+
+    def dense_bwd(layers, level, c0):
+      c = c0 + sum(v.cout for v in layers)
+      for var in reversed(layers):
+        c -= var.cout
+        dz = V(G[level], var.cout, c)                               # complete: every later reader already added
+        dact = V(self._buf("tira.dact%d" % level, (b,) + dims[level] + (totals[level],)), c, 0)
+        self._conv_bwd(var, V(acts[level], c, 0), dz, dact)
+        ctx.call("dd_relu_bwd_acc", _b(dact.d), _b(V(raws[level], c, 0).d), _b(V(G[level], c, 0).d))
+
+    blocks = {(kind, i): (level, layers, c0) for kind, i, level, layers, c0 in tape["blocks"]}
+    level, layers, c0 = blocks[("last", 0)]
+    dense_bwd(layers, level, c0)
+    for i in reversed(range(steps)):
+      var, index, c, level, cs = tape["ups"][i]
+      # y = relu(conv2d_transpose(raw_index[0:c])) written to raw_level[cs:cs+f]
+      dz = V(self._buf("tira.updz%d" % level, (b,) + dims[level] + (var.cout,)))
+      self._relu_bwd(V(G[level], var.cout, cs), V(raws[level], var.cout, cs), dz)
+      x = V(raws[index], c, 0)
+      ctx.call("dd_conv2d_wgrad", _b(x.d), _b(dz.d), 3, 1, _fp(self.param_grad(var.kernel_name)),
+               _fp(self.param_grad(var.bias_name)))
+      dx = V(self._buf("tira.updx%d" % index, (b,) + dims[index] + (c,)))
+      ctx.call("dd_conv2d_transpose3x3_dgrad", _b(dz.d), _fp(self.bwd[var.name]), _b(dx.d))
+      ctx.call("dd_axpy", ctypes.c_float(1.0), _b(dx.d), _b(V(G[index], c, 0).d))
+      lvl, layers, c0 = blocks[("up", i)]
+      dense_bwd(layers, lvl, c0)
+    for i in reversed(range(steps)):
+      _, c, z = tape["trans"][i]
+      # raw_{i+1}[0:c] = maxpool2(z), z = conv1x1(act_i[0:c])
+      dzp = V(self._buf("tira.dzp%d" % i, (b,) + dims[i] + (c,), zero=True))   # dd_maxpool_s2_bwd accumulates
+      ctx.call("dd_maxpool_s2_bwd", _b(V(z).d), _b(V(raws[i + 1], c, 0).d), _b(V(G[i + 1], c, 0).d), 2, _b(dzp.d))
+      var = spec.transition[i]
+      dact = V(self._buf("tira.dact%d" % i, (b,) + dims[i] + (totals[i],)), c, 0)
+      self._conv_bwd(var, V(acts[i], c, 0), dzp, dact)
+      ctx.call("dd_relu_bwd_acc", _b(dact.d), _b(V(raws[i], c, 0).d), _b(V(G[i], c, 0).d))
+      lvl, layers, c0 = blocks[("down", i)]
+      dense_bwd(layers, lvl, c0)
+    # pre-processing conv: raw_0[0:f0] = relu(conv(x0))
+    dz = V(self._buf("tira.predz", (b,) + dims[0] + (f[0],)))
+    self._relu_bwd(V(G[0], f[0], 0), V(raws[0], f[0], 0), dz)
+    dx0 = V(self._buf("tira.dx0", tuple(tape["x0"].t.shape)))
+    self._conv_bwd(spec.pre, tape["x0"], dz, dx0)
+    return dx0
 
   # ------------------------------------------------------------------------------------------ compose net
   def _compose_forward(self, key, small, large, out):
@@ -360,7 +494,7 @@ class Trainer:
     tuples, ft = arch.feature_prediction_tuples, arch.features_per_tuple
     x0 = self._buf("net.x0", (len(tuples) * n, h, w, c0))
     ctx.assemble_input(table, len(tuples), n, _lib.desc(x0))
-    tape = self._unet_forward(V(x0))
+    tape = self._unet_forward(V(x0)) if self.spec.core_name == "U-Net" else self._tiramisu_forward(V(x0))
     logits = list(tape["logits_coarse_first"])
     if arch.use_multiscale_predictions:
       logits.reverse()                                   # largest first (Architecture.py:577-579)
@@ -552,7 +686,10 @@ class Trainer:
       dlogits.append(dl)
     if arch.use_multiscale_predictions:
       dlogits.reverse()                           # coarsest first, the order of the core outputs
-    dx0 = self._unet_backward(st["tape"], dlogits)
+    if self.spec.core_name == "U-Net":
+      dx0 = self._unet_backward(st["tape"], dlogits)
+    else:
+      dx0 = self._tiramisu_backward(st["tape"], dlogits)
     # embedding rows: sum of the input gradient over the pixels of each tuple's images
     if arch.feature_flag_mode == FeatureFlagMode.EMBEDDING:
       dim = arch._flags.embedding_dimension

@@ -193,6 +193,9 @@ int dd_invert_standardization(dd_ctx* ctx, const dd_tensor* x, const dd_invert_p
 
 /* dz = dy * [y > 0]: backward of activation=tf.nn.relu (UNet.py:29-31 ...). */
 int dd_relu_bwd(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const dd_tensor* dz, void* stream);
+/* dz_acc += dy * [y > 0]: the same through a concatenation (Tiramisu.py:40: every later layer of a dense block and the
+ * transition read the same tensor, so their input gradients add up). */
+int dd_relu_bwd_acc(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const dd_tensor* dz_acc, void* stream);
 /* out = a * (b + c): combined lighting pass color * (direct + indirect) (Training.py:420-433). */
 int dd_muladd_fwd(dd_ctx* ctx, const dd_tensor* a, const dd_tensor* b, const dd_tensor* c, const dd_tensor* out, void* stream);
 /* backward of the above for upstream gradient g: da_acc += g (b + c); dbc_inc = g a (the increment of BOTH db and dc). */
@@ -215,6 +218,9 @@ int dd_conv2d_wgrad(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int ks
                     float* db_dev, void* stream);
 /* input gradient of dd_conv2d_transpose2x2_fwd (exact path). */
 int dd_conv2d_transpose2x2_dgrad(dd_ctx* ctx, const dd_tensor* dz, const float* w_dgrad, const dd_tensor* dx, void* stream);
+/* Input gradient of the 3x3 stride-2 'SAME' transposed convolution (Tiramisu.py:62-64): dx[i,j,c] = sum dz[2i+r,2j+s,o] W[r,s,o,c].
+ * w_dgrad: [tap][cin][cout] fp32 (dd_conv2d_repack_f32 with ksize = 3, transposed = 1). */
+int dd_conv2d_transpose3x3_dgrad(dd_ctx* ctx, const dd_tensor* dz, const float* w_dgrad, const dd_tensor* dx, void* stream);
 /* device-side repack of fp32 master weights after an optimizer step: forward layout and the layout of the
  * input-gradient convolution (spatially flipped, channels swapped); either output may be NULL. */
 int dd_conv2d_repack_f32(dd_ctx* ctx, const float* w_dev, int ksize, int cin, int cout, int transposed, float* fwd_packed,
