@@ -78,6 +78,10 @@ SIGNATURES = {
     "dd_invert_standardization_bwd": (_i, [_vp, _T, _T, _P(dd_invert_params), _T, _vp]),
     "dd_loss_fwd_bwd": (_i, [_vp, _T, _T, _i, ctypes.c_float, ctypes.c_float, _vp, _T, _i, _vp]),
     "dd_conv2d_wgrad": (_i, [_vp, _T, _T, _i, _i, _vp, _vp, _vp]),
+    "dd_conv2d_wgrad_tc": (_i, [_vp, _T, _T, _i, _i, _vp, ctypes.c_float, _vp]),
+    "dd_conv2d_pack_weights_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "dd_space_to_depth2_mask": (_i, [_vp, _T, _T, _T, _vp]),
+    "dd_relu_bwd_bias": (_i, [_vp, _T, _T, _T, _vp, ctypes.c_float, _vp]),
     "dd_conv2d_transpose2x2_dgrad": (_i, [_vp, _T, _vp, _T, _vp]),
     "dd_conv2d_transpose3x3_dgrad": (_i, [_vp, _T, _vp, _T, _vp]),
     "dd_conv2d_repack_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),

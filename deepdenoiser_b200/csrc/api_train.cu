@@ -537,6 +537,12 @@ int dd_conv2d_wgrad(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int ks
   DD_CHECK_ARG(ctx && dw && tensor_ok(x) && tensor_ok(dz), "bad argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int cin = x->c, cout = dz->c;
+  if (x->dtype == DD_F16 && dz->dtype == DD_F16) {
+    // mixed-precision path: tcgen05 wgrad (api_wgrad.cu); the bias gradient comes from dd_relu_bwd_bias
+    DD_CHECK_ARG(!transposed && !db, "tensor-core wgrad: stride-1 convolutions only, bias gradient via dd_relu_bwd_bias");
+    DD_CHECK_ARG(x->n == dz->n && x->h == dz->h && x->w == dz->w, "wgrad: spatial dims differ");
+    return launch_wgrad_rows(ctx, x, dz, ksize, 0, dw, 1.f, s);
+  }
   if (!transposed) {
     DD_CHECK_ARG(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
     DD_CHECK_ARG(x->n == dz->n && x->h == dz->h && x->w == dz->w, "wgrad: spatial dims differ");

@@ -18,6 +18,7 @@ struct dd_ctx {
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime
   int conv_rows = 0;             // cap on input rows per weight pass (0 = auto), see conv_rows.cuh
   int conv_force_stream = 0;     // debug: stream weights even when they would fit in shared memory
+  int wgrad_variant = 0;         // debug: descriptor variant of wgrad_rows_kernel
   unsigned long long* conv_trace = nullptr;  // debug: device buffer [64][8] of clock64 stamps (CTA 0)
   std::atomic<int64_t> launches{0};
 };
@@ -25,6 +26,9 @@ struct dd_ctx {
 namespace dd {
 
 void set_error(const char* fmt, ...);
+// api_wgrad.cu: tensor-core weight gradient (fp16 operands), dw fp32 accumulated; layout 0 [tap][cin][cout], 1 [tap][cout][cin]
+int launch_wgrad_rows(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int ksize, int layout, float* dw, float scale,
+                      cudaStream_t stream);
 
 #define DD_CHECK_ARG(cond, ...)                 \
   do {                                          \

@@ -216,6 +216,24 @@ int dd_loss_fwd_bwd(dd_ctx* ctx, const dd_tensor* pred, const dd_tensor* target,
 /* dW (TF layout [kh,kw,cin,cout]; transposed: [2,2,cout,cin]) += x^T * dz over all pixels, db += sum dz. */
 int dd_conv2d_wgrad(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int ksize, int transposed, float* dw_dev,
                     float* db_dev, void* stream);
+/* ---- mixed-precision (tensor-core) training: fp16 activations / activation gradients, fp32 master weights ---------- */
+/* Tensor-core weight gradient (tcgen05, pixel axis = GEMM K, both operands MN-major): x, dz fp16 views of equal spatial
+ * size, ksize 1 or 3 (stride 1, 'SAME'); dw_dev fp32 += scale * sum x (x) dz, layout 0 = TF [kh,kw,cin,cout],
+ * 1 = [tap][cout][cin] (TF conv2d_transpose kernels).  Replaces Conv2DBackpropFilter of TF autodiff (Training.py:700-702). */
+int dd_conv2d_wgrad_tc(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int ksize, int layout, float* dw_dev, float scale,
+                       void* stream);
+/* Device-side (re)pack of fp32 master weights into the fp16 layout of dd_conv2d_fwd after every optimizer step.
+ * mode 0: forward, w_dev TF [k,k,cin,cout];  mode 1: the input-gradient convolution of that layer (flipped taps, swapped
+ * channels; run it with dd_conv2d_fwd on dz);  mode 2: dd_conv2d_transpose2x2_fwd, w_dev TF [2,2,cout,cin].
+ * packed_dev: dd_conv2d_packed_bytes() bytes (mode 1: of the swapped shape), zeroed once by the caller. */
+int dd_conv2d_pack_weights_dev(dd_ctx* ctx, const float* w_dev, int ksize, int cin, int cout, int mode, void* packed_dev,
+                               void* stream);
+/* out[n,i,j,sp*C+c] = dy[n,2i+ay,2j+ax,c] * [y[same] > 0] (y may be NULL), sp = 2*ay+ax: turns the backward of the
+ * stride-2 2x2 transposed convolution (UNet.py:56-58) into 1x1 GEMMs on the coarse grid. */
+int dd_space_to_depth2_mask(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const dd_tensor* out, void* stream);
+/* dz = dy * [y > 0] (y and dz may be NULL) and db_dev[c] += scale * sum_pixels dz[..,c] (db_dev may be NULL) in one pass. */
+int dd_relu_bwd_bias(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const dd_tensor* dz, float* db_dev, float scale,
+                     void* stream);
 /* input gradient of dd_conv2d_transpose2x2_fwd (exact path). */
 int dd_conv2d_transpose2x2_dgrad(dd_ctx* ctx, const dd_tensor* dz, const float* w_dgrad, const dd_tensor* dx, void* stream);
 /* Input gradient of the 3x3 stride-2 'SAME' transposed convolution (Tiramisu.py:62-64): dx[i,j,c] = sum dz[2i+r,2j+s,o] W[r,s,o,c].

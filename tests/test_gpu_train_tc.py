@@ -1,0 +1,151 @@
+"""GPU parity of the mixed-precision (tensor-core) training kernels against torch fp32 references evaluated on the SAME
+fp16-rounded operands: tcgen05 weight gradient (dd_conv2d_wgrad_tc), device-side weight packing for the forward and the
+input-gradient convolution (dd_conv2d_pack_weights_dev), space-to-depth + ReLU mask and the fused ReLU-backward /
+bias-gradient pass.  Tolerance: 2e-3 of the result scale (fp32 accumulation order; inputs are identical fp16 values)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from deepdenoiser_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+_b = ctypes.byref
+
+
+def _fp(t):
+  return ctypes.c_void_p(t.data_ptr())
+
+
+def rel_err(got, want):
+  return float((got.double() - want.double()).abs().max()) / max(1e-6, float(want.double().abs().max()))
+
+
+WGRAD_CASES = [
+    # ks, cin, cout, n, h, w
+    (3, 64, 64, 1, 9, 128),
+    (3, 64, 64, 2, 21, 150),
+    (3, 32, 64, 1, 16, 300),
+    (3, 96, 96, 1, 10, 130),
+    (3, 192, 96, 1, 10, 64),
+    (3, 128, 128, 2, 9, 140),
+    (3, 24, 24, 1, 12, 40),
+    (3, 64, 64, 3, 40, 256),     # more rows than CTAs x minimum: several segments per CTA
+    (1, 64, 25, 2, 9, 150),
+    (1, 25, 25, 1, 7, 33),
+    (1, 384, 128, 1, 8, 64),
+]
+
+
+@pytest.mark.parametrize("ks,cin,cout,n,h,w", WGRAD_CASES)
+def test_wgrad_tc(ctx, ks, cin, cout, n, h, w):
+  g = torch.Generator(device="cuda").manual_seed(ks * 1000 + cin + cout + h)
+  cs_in, cs_out = (cin + 7) // 8 * 8, (cout + 7) // 8 * 8
+  x = torch.zeros(n, h, w, cs_in, device="cuda", dtype=torch.float16)
+  dz = torch.zeros(n, h, w, cs_out, device="cuda", dtype=torch.float16)
+  x[..., :cin] = torch.randn(n, h, w, cin, device="cuda", generator=g).half()
+  dz[..., :cout] = torch.randn(n, h, w, cout, device="cuda", generator=g).half()
+  # padding channels hold garbage on purpose: the kernel must ignore them
+  x[..., cin:] = 7.0
+  dz[..., cout:] = -3.0
+  dw = torch.full((ks, ks, cin, cout), 0.5, device="cuda")
+  ctx.call("dd_conv2d_wgrad_tc", _b(_lib.desc(x, cin, 0)), _b(_lib.desc(dz, cout, 0)), ks, 0, _fp(dw), ctypes.c_float(0.25))
+  xf = x[..., :cin].float().permute(0, 3, 1, 2).requires_grad_(False)
+  wt = torch.zeros(cout, cin, ks, ks, device="cuda", requires_grad=True)
+  y = F.conv2d(xf, wt, padding=ks // 2)
+  y.backward(dz[..., :cout].float().permute(0, 3, 1, 2))
+  want = 0.5 + 0.25 * wt.grad.permute(2, 3, 1, 0)            # [kh,kw,cin,cout]
+  err = rel_err(dw, want)
+  assert err <= 2e-3, "wgrad %s: relative error %.3e" % ((ks, cin, cout, n, h, w), err)
+
+
+def test_wgrad_tc_transposed_layout(ctx):
+  n, h, w, cin, cout = 1, 6, 70, 64, 48
+  g = torch.Generator(device="cuda").manual_seed(5)
+  x = torch.randn(n, h, w, cin, device="cuda", generator=g).half()
+  dz = torch.randn(n, h, w, cout, device="cuda", generator=g).half()
+  dw = torch.zeros(cout, cin, device="cuda")
+  ctx.call("dd_conv2d_wgrad_tc", _b(_lib.desc(x)), _b(_lib.desc(dz)), 1, 1, _fp(dw), ctypes.c_float(1.0))
+  want = torch.einsum("nhwc,nhwo->oc", x.float(), dz.float())
+  assert rel_err(dw, want) <= 2e-3
+
+
+@pytest.mark.parametrize("ks,cin,cout", [(3, 64, 64), (3, 32, 96), (1, 64, 25), (3, 192, 96)])
+def test_pack_weights_dev_forward_matches_host(ctx, ks, cin, cout):
+  wt = torch.randn(ks, ks, cin, cout) * 0.1
+  host = ctx.pack_conv_weights(wt, torch.float16)
+  devp = torch.zeros_like(host)
+  ctx.call("dd_conv2d_pack_weights_dev", _fp(wt.cuda()), ks, cin, cout, 0, _fp(devp))
+  assert torch.equal(host, devp)
+
+
+def test_pack_weights_dev_transposed_matches_host(ctx):
+  cin, cout = 96, 64
+  wt = torch.randn(2, 2, cout, cin) * 0.1
+  host = ctx.pack_conv_weights(wt, torch.float16, transposed=True)
+  devp = torch.zeros_like(host)
+  ctx.call("dd_conv2d_pack_weights_dev", _fp(wt.cuda()), 2, cin, cout, 2, _fp(devp))
+  assert torch.equal(host, devp)
+
+
+@pytest.mark.parametrize("ks,cin,cout", [(3, 64, 64), (3, 32, 64), (1, 64, 25), (3, 96, 128)])
+def test_dgrad_through_forward_kernel(ctx, ks, cin, cout):
+  """dx = conv(dz, flipped / channel-swapped W) on the tcgen05 forward kernel == autograd input gradient."""
+  n, h, w = 1, 12, 140
+  g = torch.Generator(device="cuda").manual_seed(cin * 7 + cout)
+  wt = (torch.randn(ks, ks, cin, cout, device="cuda", generator=g) * 0.1)
+  cs_out = (cout + 7) // 8 * 8
+  dz = torch.zeros(n, h, w, cs_out, device="cuda", dtype=torch.float16)
+  dz[..., :cout] = torch.randn(n, h, w, cout, device="cuda", generator=g).half()
+  nbytes = ctx.lib.dd_conv2d_packed_bytes(ks, cout, cin, _lib.DD_F16, 0)
+  packed = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+  ctx.call("dd_conv2d_pack_weights_dev", _fp(wt), ks, cin, cout, 1, _fp(packed))
+  cs_in = (cin + 7) // 8 * 8
+  dx = torch.zeros(n, h, w, cs_in, device="cuda", dtype=torch.float16)
+  ctx.conv2d(_lib.desc(dz, cout, 0), packed, None, ks, _lib.desc(dx, cin, 0))
+  xin = torch.zeros(n, cin, h, w, device="cuda", requires_grad=True)
+  w16 = wt.half().float().permute(3, 2, 0, 1)
+  y = F.conv2d(xin, w16, padding=ks // 2)
+  y.backward(dz[..., :cout].float().permute(0, 3, 1, 2))
+  want = xin.grad.permute(0, 2, 3, 1)
+  assert rel_err(dx[..., :cin].float(), want) <= 3e-3
+
+
+def test_space_to_depth_mask(ctx):
+  n, h, w, c = 2, 6, 10, 16
+  dy = torch.randn(n, 2 * h, 2 * w, c, device="cuda").half()
+  y = torch.randn(n, 2 * h, 2 * w, c, device="cuda").half()
+  out = torch.empty(n, h, w, 4 * c, device="cuda", dtype=torch.float16)
+  ctx.call("dd_space_to_depth2_mask", _b(_lib.desc(dy)), _b(_lib.desc(y)), _b(_lib.desc(out)))
+  m = dy * (y > 0)
+  want = torch.cat([m[:, ay::2, ax::2, :] for ay in (0, 1) for ax in (0, 1)], dim=3)
+  assert torch.equal(out, want)
+  ctx.call("dd_space_to_depth2_mask", _b(_lib.desc(dy)), None, _b(_lib.desc(out)))
+  want = torch.cat([dy[:, ay::2, ax::2, :] for ay in (0, 1) for ax in (0, 1)], dim=3)
+  assert torch.equal(out, want)
+
+
+@pytest.mark.parametrize("c,cstride,dtype", [(64, 64, torch.float16), (96, 200, torch.float16), (25, 32, torch.float16),
+                                             (24, 24, torch.float32)])
+def test_relu_bwd_bias(ctx, c, cstride, dtype):
+  n, h, w = 2, 13, 37
+  dy = torch.randn(n, h, w, cstride, device="cuda").to(dtype)
+  y = torch.randn(n, h, w, cstride, device="cuda").to(dtype)
+  dz = torch.full((n, h, w, cstride), 9.0, device="cuda", dtype=dtype)
+  db = torch.full((c,), 1.0, device="cuda")
+  coff = 8 if cstride >= c + 8 else 0
+  ctx.call("dd_relu_bwd_bias", _b(_lib.desc(dy, c, coff)), _b(_lib.desc(y, c, coff)), _b(_lib.desc(dz, c, coff)), _fp(db),
+           ctypes.c_float(0.5))
+  want = (dy * (y > 0))[..., coff:coff + c]
+  assert torch.equal(dz[..., coff:coff + c], want)
+  untouched = torch.ones(cstride, dtype=torch.bool)
+  untouched[coff:coff + c] = False
+  assert bool((dz[..., untouched] == 9.0).all())
+  want_db = 1.0 + 0.5 * want.float().sum(dim=(0, 1, 2))
+  assert rel_err(db, want_db) <= 1e-3
+  # bias gradient only (no mask, no store)
+  db2 = torch.zeros(c, device="cuda")
+  ctx.call("dd_relu_bwd_bias", _b(_lib.desc(dy, c, coff)), None, None, _fp(db2), ctypes.c_float(1.0))
+  assert rel_err(db2, dy[..., coff:coff + c].float().sum(dim=(0, 1, 2))) <= 1e-3
