@@ -3,10 +3,15 @@ forward with saved activations, the loss of BaseFeatureTraining.loss / LossDiffe
 every op as explicit libdd_b200 kernels, TF-form Adam on one flat fp32 parameter buffer and (multi-GPU) one
 all-reduce of the flat gradient buffer per step.
 
-Round-1 scope: the EXACT fp32 path (CUDA-core convolutions), U-Net and Tiramisu backbones, loss weights of
-TrainingExample.json (mean weights; variation / MS-SSIM / masked weights must be 0).  Every gradient is
-parity-tested against torch-autograd of the oracle (tests/test_gpu_training.py).  Tensor-core backward kernels
-(dgrad through conv_rows_kernel, MN-major tcgen05 wgrad) are the next step.
+Two arithmetic modes:
+  * precision="float32": the EXACT path (CUDA-core convolutions), U-Net and Tiramisu backbones; every gradient is
+    parity-tested against torch-autograd of the oracle to 1e-6 (tests/test_gpu_training.py).
+  * precision="float16": the TENSOR-CORE path (U-Net): fp16 activations and activation gradients, fp32 master weights /
+    gradients / Adam state, fp32 image-level arithmetic (kernel-prediction apply, composition blend, loss).  Forward and
+    input gradients run on conv_rows_kernel (the input gradient of a 3x3 conv is the conv of dz with flipped, channel-
+    swapped weights), weight gradients on wgrad_rows_kernel (tcgen05, MN-major), the 2x2 transposed conv's backward as
+    1x1 GEMMs on a space-to-depth view.  A static loss scale keeps the fp16 gradients in range; Adam divides it out.
+Loss weights of TrainingExample.json (mean weights; variation / MS-SSIM / masked weights must be 0).
 """
 import ctypes
 
@@ -57,11 +62,15 @@ class TrainingSettings:
 class Trainer:
   """Owns the flat fp32 parameters / gradients / Adam state of an Architecture and runs training steps."""
 
-  def __init__(self, architecture, settings=None):
+  def __init__(self, architecture, settings=None, precision="float32", loss_scale=None):
     assert isinstance(architecture, Architecture)
+    assert precision in ("float32", "float16"), precision
     self.arch = architecture
     self.settings = settings or TrainingSettings()
-    architecture.dtype = torch.float32            # exact path
+    self.mixed = (precision == "float16")
+    self.act_dtype = torch.float16 if self.mixed else torch.float32
+    self.loss_scale = loss_scale                  # None: chosen per batch (N*H*W/8) in mixed mode, 1 in exact mode
+    architecture.dtype = torch.float32            # the Architecture's own (inference) network is not used for training
     architecture.logits_dtype = torch.float32
     architecture._ensure_device()
     self.ctx = architecture.ctx
@@ -74,7 +83,13 @@ class Trainer:
       self.offsets[name] = (n, shape)
       n += (size + 3) // 4 * 4                    # keep every variable 16-byte aligned
     self.count = n
-    self.theta = torch.zeros(n, dtype=torch.float32, device=self.dev)
+    if self.mixed:
+      if self.spec.core_name != "U-Net":
+        raise NotImplementedError("tensor-core training covers the U-Net backbone; Tiramisu trains on the exact path")
+      if any(f % 8 for f in self.spec.filters):
+        raise _lib.DDError("float16 training needs filter counts that are multiples of 8")
+    # + slack: the tensor-core conv reads biases in groups of 16 floats
+    self.theta = torch.zeros(n + 64, dtype=torch.float32, device=self.dev)
     self.grad = torch.zeros_like(self.theta)
     self.adam_m = torch.zeros_like(self.theta)
     self.adam_v = torch.zeros_like(self.theta)
@@ -102,12 +117,16 @@ class Trainer:
     return {name: self.param(name).detach().cpu().numpy().copy() for name in self.offsets}
 
   def gradients(self):
-    return {name: self.param_grad(name).detach().cpu().numpy().copy() for name in self.offsets}
+    """Gradients of the last backward() with the loss scale divided out."""
+    inv = 1.0 / getattr(self, "_scale_used", 1.0)
+    return {name: (self.param_grad(name).detach() * inv).cpu().numpy().copy() for name in self.offsets}
 
   def _repack(self):
     """fp32 master weights -> forward / input-gradient convolution layouts (device side) + host copies of the few
     weights that travel in launch parameters (compose head / tail)."""
     ctx = self.ctx
+    if self.mixed:
+      return self._repack_mixed()
     self.fwd, self.bwd, self.bias = {}, {}, {}
     for var in self.spec.conv_variables():
       w = self.param(var.kernel_name)
@@ -147,31 +166,89 @@ class Trainer:
     if self.arch.feature_flag_mode == FeatureFlagMode.EMBEDDING:
       self.arch._flags.embedding_matrix = self.param("embedding/feature_flags_embedding_matrix")
 
+  def _repack_mixed(self):
+    """fp32 master weights -> fp16 layouts of conv_rows_kernel, on the device (dd_conv2d_pack_weights_dev): forward, the
+    input-gradient convolution (flipped taps, swapped channels) and, for the 2x2 transposed convs, the 1x1 GEMM of their
+    backward on the space-to-depth view (TF [2,2,cout,cin] read as a [4*cout, cin] 1x1 kernel)."""
+    ctx, lib = self.ctx, self.ctx.lib
+    if not hasattr(self, "_packed_store"):
+      self._packed_store = {}
+    self.fwd, self.bwd, self.bias = {}, {}, {}
+    for var in self.spec.conv_variables():
+      w = self.param(var.kernel_name)
+      self.bias[var.name] = self.param(var.bias_name)
+      if var in self.spec.compose and var.ksize == 1:
+        continue
+      store = self._packed_store.get(var.name)
+      if store is None:
+        if var.transposed:
+          assert var.ksize == 2
+          nf = lib.dd_conv2d_packed_bytes(2, var.cin, var.cout, _lib.DD_F16, 1)
+          nb = lib.dd_conv2d_packed_bytes(1, 4 * var.cout, var.cin, _lib.DD_F16, 0)
+        else:
+          nf = lib.dd_conv2d_packed_bytes(var.ksize, var.cin, var.cout, _lib.DD_F16, 0)
+          nb = lib.dd_conv2d_packed_bytes(var.ksize, var.cout, var.cin, _lib.DD_F16, 0)
+        store = (torch.zeros(nf, dtype=torch.uint8, device=self.dev), torch.zeros(nb, dtype=torch.uint8, device=self.dev))
+        self._packed_store[var.name] = store
+      f, b = store
+      if var.transposed:
+        ctx.call("dd_conv2d_pack_weights_dev", _fp(w), 2, var.cin, var.cout, 2, _fp(f))
+        ctx.call("dd_conv2d_pack_weights_dev", _fp(w), 1, 4 * var.cout, var.cin, 0, _fp(b))
+      else:
+        ctx.call("dd_conv2d_pack_weights_dev", _fp(w), var.ksize, var.cin, var.cout, 0, _fp(f))
+        ctx.call("dd_conv2d_pack_weights_dev", _fp(w), var.ksize, var.cin, var.cout, 1, _fp(b))
+      self.fwd[var.name], self.bwd[var.name] = f, b
+    if self.spec.compose:
+      head, tail = self.spec.compose[0], self.spec.compose[-1]
+      self.host_small = {k: self.param(k).detach().cpu().contiguous() for k in
+                         (head.kernel_name, head.bias_name, tail.kernel_name, tail.bias_name)}
+    if self.arch.feature_flag_mode == FeatureFlagMode.EMBEDDING:
+      self.arch._flags.embedding_matrix = self.param("embedding/feature_flags_embedding_matrix")
+
   # ------------------------------------------------------------------------------------------ helpers
-  def _buf(self, key, shape, zero=False):
-    k = (key, tuple(shape))
+  def _buf(self, key, shape, zero=False, dtype=torch.float32):
+    k = (key, tuple(shape), dtype)
     t = self._buffers.get(k)
     if t is None:
-      t = torch.empty(shape, dtype=torch.float32, device=self.dev)
+      t = torch.empty(shape, dtype=dtype, device=self.dev)
       self._buffers[k] = t
     if zero:
       t.zero_()
     return t
 
+  def _act(self, key, nhw, c, zero=False):
+    """Network activation / activation-gradient tensor [n,h,w,c] in the arithmetic mode's storage type; the channel
+    stride is padded to 16 bytes in fp16 mode (TMA)."""
+    cs = (c + 7) // 8 * 8 if self.mixed else c
+    return V(self._buf(key, tuple(nhw) + (cs,), zero=zero, dtype=self.act_dtype), c)
+
   def _conv(self, var, x, y, relu=False, residual=None, y_relu=None):
     self.ctx.conv2d(x.d, self.fwd[var.name], self.bias[var.name], var.ksize, y.d, relu=relu,
                     residual=residual.d if residual is not None else None, y_relu=y_relu.d if y_relu is not None else None)
 
-  def _conv_bwd(self, var, x, dz, dx=None):
-    """dW, db (accumulated) and optionally dx of y = conv(x, W) + b given dz = dL/dy."""
+  def _conv_bwd(self, var, x, dz, dx=None, bias_done=False):
+    """dW, db (accumulated) and optionally dx of y = conv(x, W) + b given dz = dL/dy.  bias_done: db was already
+    accumulated by the _relu_bwd that produced dz (tensor-core mode fuses the two passes)."""
     ctx = self.ctx
-    ctx.call("dd_conv2d_wgrad", _b(x.d), _b(dz.d), var.ksize, 0, _fp(self.param_grad(var.kernel_name)),
-             _fp(self.param_grad(var.bias_name)))
+    if self.mixed:
+      ctx.call("dd_conv2d_wgrad_tc", _b(x.d), _b(dz.d), var.ksize, 0, _fp(self.param_grad(var.kernel_name)), ctypes.c_float(1.0))
+      if not bias_done:
+        ctx.call("dd_relu_bwd_bias", _b(dz.d), None, None, _fp(self.param_grad(var.bias_name)), ctypes.c_float(1.0))
+    else:
+      ctx.call("dd_conv2d_wgrad", _b(x.d), _b(dz.d), var.ksize, 0, _fp(self.param_grad(var.kernel_name)),
+               _fp(self.param_grad(var.bias_name)))
     if dx is not None:
       ctx.conv2d(dz.d, self.bwd[var.name], None, var.ksize, dx.d, relu=False)
 
-  def _relu_bwd(self, dy, y, dz):
+  def _relu_bwd(self, dy, y, dz, bias_of=None):
+    """dz = dy * [y > 0]; tensor-core mode also accumulates the bias gradient of layer `bias_of` in the same pass
+    (returns True when it did)."""
+    if self.mixed:
+      db = _fp(self.param_grad(bias_of.bias_name)) if bias_of is not None else None
+      self.ctx.call("dd_relu_bwd_bias", _b(dy.d), _b(y.d), _b(dz.d), db, ctypes.c_float(1.0))
+      return bias_of is not None
     self.ctx.call("dd_relu_bwd", _b(dy.d), _b(y.d), _b(dz.d))
+    return False
 
   # ------------------------------------------------------------------------------------------ U-Net forward / backward
   def _unet_forward(self, x0):
@@ -183,7 +260,7 @@ class Trainer:
     def block(key, layers, x, out):
       acts = [x]
       for i, var in enumerate(layers):
-        dst = out if i == len(layers) - 1 else V(self._buf("%s.a%d" % (key, i), (b,) + tuple(x.t.shape[1:3]) + (var.cout,)))
+        dst = out if i == len(layers) - 1 else self._act("%s.a%d" % (key, i), (b,) + tuple(x.t.shape[1:3]), var.cout)
         self._conv(var, acts[-1], dst, relu=True)
         acts.append(dst)
       tape["blocks"].append((key, layers, acts))
@@ -192,11 +269,11 @@ class Trainer:
     x = x0
     for i in range(steps):
       hh, ww = dims[i]
-      cat = self._buf("cat%d" % i, (b, hh, ww, 2 * f[i]))
+      cat = self._act("cat%d" % i, (b, hh, ww), 2 * f[i]).t
       tape["cats"].append(cat)
       skip = V(cat, f[i], 0)
       block("d%d" % i, spec.down[i], x, skip)
-      pooled = V(self._buf("pool%d" % i, (b, dims[i + 1][0], dims[i + 1][1], f[i])))
+      pooled = self._act("pool%d" % i, (b, dims[i + 1][0], dims[i + 1][1]), f[i])
       ctx.maxpool_s2(skip.d, 3, pooled.d)
       tape["pools"].append((skip, pooled))
       x = pooled
@@ -204,7 +281,7 @@ class Trainer:
     for i in range(steps):
       index = steps - i
       hh, ww = dims[index]
-      out = V(self._buf("out%d" % index, (b, hh, ww, f[index])))
+      out = self._act("out%d" % index, (b, hh, ww), f[index])
       block("u%d" % index, spec.up[i], x, out)
       if spec.use_multiscale:
         results.append(out)
@@ -213,7 +290,7 @@ class Trainer:
       ctx.conv2d_transpose2x2(out.d, self.fwd[var.name], self.bias[var.name], up.d, relu=True)
       tape["ups"].append((var, out, up))
       x = V(tape["cats"][index - 1])
-    out = V(self._buf("out0", (b, h, w, f[0])))
+    out = self._act("out0", (b, h, w), f[0])
     block("l", spec.last, x, out)
     results.append(out)
     tape["results"] = results
@@ -227,9 +304,10 @@ class Trainer:
     logits = []
     for k, (r, (a, bvar)) in enumerate(zip(tape["results"], spec.post)):
       bb, hh, ww = r.t.shape[0], r.t.shape[1], r.t.shape[2]
-      mid = V(self._buf("post.mid%d" % k, (bb, hh, ww, spec.output_channels)))
+      mid = self._act("post.mid%d" % k, (bb, hh, ww), spec.output_channels)
       self._conv(a, r, mid, relu=True)
-      out_l = V(self._buf("post.out%d" % k, (bb, hh, ww, spec.output_channels)))
+      o8 = (spec.output_channels + 7) // 8 * 8 if self.mixed else spec.output_channels
+      out_l = V(self._buf("post.out%d" % k, (bb, hh, ww, o8)), spec.output_channels)     # logits stay fp32
       self._conv(bvar, mid, out_l, relu=False)
       tape["post"].append((a, bvar, r, mid, out_l))
       logits.append(out_l)
@@ -239,12 +317,13 @@ class Trainer:
     """Returns {id(core output buffer): gradient V} and accumulates the 1x1 weights' gradients."""
     dres = {}
     for k, ((a, bvar, r, mid, out_l), dl) in enumerate(zip(tape["post"], dlogits_coarse_first)):
-      dmid = V(self._buf("post.dmid%d" % k, tuple(mid.t.shape)))
+      nhw = tuple(mid.t.shape[:3])
+      dmid = self._act("post.dmid%d" % k, nhw, mid.c)
       self._conv_bwd(bvar, mid, dl, dmid)
-      dz = V(self._buf("post.dz%d" % k, tuple(mid.t.shape)))
-      self._relu_bwd(dmid, mid, dz)
-      dr = V(self._buf("post.dr%d" % k, tuple(r.t.shape[:3]) + (a.cin,)))
-      self._conv_bwd(a, r, dz, dr)
+      dz = self._act("post.dz%d" % k, nhw, mid.c)
+      done = self._relu_bwd(dmid, mid, dz, bias_of=a)
+      dr = self._act("post.dr%d" % k, nhw, a.cin)
+      self._conv_bwd(a, r, dz, dr, bias_done=done)
       dres[id(r.t)] = dr
     return dres
 
@@ -253,10 +332,10 @@ class Trainer:
     dy = dout
     for i in reversed(range(len(layers))):
       var, x, y = layers[i], acts[i], acts[i + 1]
-      dz = V(self._buf("%s.dz%d" % (key, i), tuple(y.t.shape[:3]) + (var.cout,)))
-      self._relu_bwd(dy, y, dz)
-      dx = V(self._buf("%s.dx%d" % (key, i), tuple(x.t.shape[:3]) + (var.cin,)))
-      self._conv_bwd(var, x, dz, dx)
+      dz = self._act("%s.dz%d" % (key, i), tuple(y.t.shape[:3]), var.cout)
+      done = self._relu_bwd(dy, y, dz, bias_of=var)
+      dx = self._act("%s.dx%d" % (key, i), tuple(x.t.shape[:3]), var.cin)
+      self._conv_bwd(var, x, dz, dx, bias_done=done)
       dy = dx
     return dy
 
@@ -275,12 +354,22 @@ class Trainer:
       level = index - 1
       var, out, up = ups[index]
       dup = V(dcat[level].t, f[level], f[level])                     # [f:] half of the concat gradient
-      dz = V(self._buf("up%d.dz" % index, tuple(up.t.shape[:3]) + (f[level],)))
-      self._relu_bwd(dup, up, dz)
-      ctx.call("dd_conv2d_wgrad", _b(out.d), _b(dz.d), 2, 1, _fp(self.param_grad(var.kernel_name)),
-               _fp(self.param_grad(var.bias_name)))
-      dout = V(self._buf("up%d.dout" % index, tuple(out.t.shape)))
-      ctx.call("dd_conv2d_transpose2x2_dgrad", _b(dz.d), _fp(self.bwd[var.name]), _b(dout.d))
+      dout = self._act("up%d.dout" % index, tuple(out.t.shape[:3]), out.c)
+      if self.mixed:
+        # ReLU mask + space-to-depth: the stride-2 2x2 transposed conv's backward becomes 1x1 GEMMs on the coarse grid
+        s2d = self._act("up%d.s2d" % index, tuple(out.t.shape[:3]), 4 * f[level])
+        ctx.call("dd_space_to_depth2_mask", _b(dup.d), _b(up.d), _b(s2d.d))
+        db4 = self._buf("up%d.db4" % index, (4, f[level]), zero=True)
+        ctx.call("dd_relu_bwd_bias", _b(s2d.d), None, None, _fp(db4), ctypes.c_float(1.0))
+        self.param_grad(var.bias_name).add_(db4.sum(dim=0))
+        ctx.call("dd_conv2d_wgrad_tc", _b(out.d), _b(s2d.d), 1, 1, _fp(self.param_grad(var.kernel_name)), ctypes.c_float(1.0))
+        ctx.conv2d(s2d.d, self.bwd[var.name], None, 1, dout.d, relu=False)
+      else:
+        dz = V(self._buf("up%d.dz" % index, tuple(up.t.shape[:3]) + (f[level],)))
+        self._relu_bwd(dup, up, dz)
+        ctx.call("dd_conv2d_wgrad", _b(out.d), _b(dz.d), 2, 1, _fp(self.param_grad(var.kernel_name)),
+                 _fp(self.param_grad(var.bias_name)))
+        ctx.call("dd_conv2d_transpose2x2_dgrad", _b(dz.d), _fp(self.bwd[var.name]), _b(dout.d))
       extra = dres.get(id(out.t))                                    # multi-scale output taken from this block
       if extra is not None:
         ctx.call("dd_axpy", ctypes.c_float(1.0), _b(extra.d), _b(dout.d))
@@ -294,7 +383,13 @@ class Trainer:
     for i in reversed(range(steps)):
       skip, pooled = tape["pools"][i]
       dskip = V(dcat[i].t, f[i], 0)                                  # [:f] half, written by the concat consumer
-      ctx.call("dd_maxpool_s2_bwd", _b(skip.d), _b(pooled.d), _b(dpool.d), 3, _b(dskip.d))
+      if self.mixed:
+        # dd_maxpool_s2_bwd scatters with fp32 atomics: route through an fp32 scratch tensor, then add
+        scratch = self._buf("pool%d.scatter" % i, tuple(skip.t.shape[:3]) + (f[i],), zero=True)
+        ctx.call("dd_maxpool_s2_bwd", _b(skip.d), _b(pooled.d), _b(dpool.d), 3, _b(_lib.desc(scratch)))
+        ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(scratch)), _b(dskip.d))
+      else:
+        ctx.call("dd_maxpool_s2_bwd", _b(skip.d), _b(pooled.d), _b(dpool.d), 3, _b(dskip.d))
       layers, acts = blocks["d%d" % i]
       dpool = self._block_bwd("d%d" % i, layers, acts, dskip)
     return dpool                                                     # dL/dx0
@@ -415,7 +510,7 @@ class Trainer:
     spec, ctx = self.spec, self.ctx
     head, c1, c2, c3, c4, tail = spec.compose
     i, h, w = large.t.shape[0], large.t.shape[1], large.t.shape[2]
-    t = {n: V(self._buf("%s.%s" % (key, n), (i, h, w, 24))) for n in ("x0", "a1", "x1", "a2", "a3", "x2")}
+    t = {n: self._act("%s.%s" % (key, n), (i, h, w), 24) for n in ("x0", "a1", "x1", "a2", "a3", "x2")}
     hs = self.host_small
     ctx.compose_head(small.d, large.d, hs[head.kernel_name].reshape(6, 24), hs[head.bias_name], 24, t["x0"].d)
     self._conv(c1, t["x0"], t["a1"], relu=True)                              # a1 = relu(r1)
@@ -433,7 +528,7 @@ class Trainer:
     key = t["key"]
     shape = tuple(t["x0"].t.shape)
     hs = self.host_small
-    g = lambda n: V(self._buf("%s.d%s" % (key, n), shape))   # noqa: E731
+    g = lambda n: self._act("%s.d%s" % (key, n), shape[:3], 24)   # noqa: E731
     dx2 = g("x2")
     ctx.call("dd_compose_tail_bwd", _b(t["x2"].d), _fp(hs[tail.kernel_name]), _fp(hs[tail.bias_name]), 24, _b(t["small"].d),
              _b(t["large"].d), _b(dout.d), _b(dx2.d), _b(dsmall.d), _b(dlarge.d), _fp(self.param_grad(tail.kernel_name)),
@@ -442,9 +537,9 @@ class Trainer:
     da3 = g("a3")
     self._conv_bwd(c4, t["a3"], dx2, da3)
     dz3 = g("z3")
-    self._relu_bwd(da3, t["a3"], dz3)
+    done = self._relu_bwd(da3, t["a3"], dz3, bias_of=c3)
     da2 = g("a2")
-    self._conv_bwd(c3, t["a2"], dz3, da2)
+    self._conv_bwd(c3, t["a2"], dz3, da2, bias_done=done)
     dx1 = g("x1")
     self._relu_bwd(da2, t["a2"], dx1)                                         # through relu(x1)
     ctx.call("dd_axpy", ctypes.c_float(1.0), _b(dx2.d), _b(dx1.d))            # + identity path
@@ -452,9 +547,9 @@ class Trainer:
     da1 = g("a1")
     self._conv_bwd(c2, t["a1"], dx1, da1)
     dz1 = g("z1")
-    self._relu_bwd(da1, t["a1"], dz1)
+    done = self._relu_bwd(da1, t["a1"], dz1, bias_of=c1)
     dx0 = g("x0")
-    self._conv_bwd(c1, t["x0"], dz1, dx0)
+    self._conv_bwd(c1, t["x0"], dz1, dx0, bias_done=done)
     ctx.call("dd_axpy", ctypes.c_float(1.0), _b(dx1.d), _b(dx0.d))
     ctx.call("dd_compose_head_bwd", _b(t["small"].d), _b(t["large"].d), _fp(hs[head.kernel_name]), 24, _b(t["x0"].d), _b(dx0.d),
              _b(dsmall.d), _b(dlarge.d), _fp(self.param_grad(head.kernel_name)), _fp(self.param_grad(head.bias_name)))
@@ -492,9 +587,10 @@ class Trainer:
     c0 = arch.number_of_input_channels
     table, keep = arch._gather_table(std_bank, var_bank, max(var_width, 1), features, n, c0)
     tuples, ft = arch.feature_prediction_tuples, arch.features_per_tuple
-    x0 = self._buf("net.x0", (len(tuples) * n, h, w, c0))
-    ctx.assemble_input(table, len(tuples), n, _lib.desc(x0))
-    tape = self._unet_forward(V(x0)) if self.spec.core_name == "U-Net" else self._tiramisu_forward(V(x0))
+    x0v = self._act("net.x0", (len(tuples) * n, h, w), c0)
+    x0 = x0v.t
+    ctx.assemble_input(table, len(tuples), n, x0v.d)
+    tape = self._unet_forward(x0v) if self.spec.core_name == "U-Net" else self._tiramisu_forward(x0v)
     logits = list(tape["logits_coarse_first"])
     if arch.use_multiscale_predictions:
       logits.reverse()                                   # largest first (Architecture.py:577-579)
@@ -557,6 +653,9 @@ class Trainer:
     arch, ctx, st, cfg = self.arch, self.ctx, self._state, self.settings
     n, h, w, n_scales = st["n"], st["h"], st["w"], st["n_scales"]
     kind = LOSS_KINDS[cfg.loss_difference]
+    # static loss scale of the fp16 path: the per-pixel gradient of a mean over N*H*W pixels would underflow fp16
+    S = float(self.loss_scale) if self.loss_scale is not None else (n * h * w / 8.0 if self.mixed else 1.0)
+    self._scale_used = S
     loss_scales = n_scales if cfg.use_multiscale_loss else 1
     norm = 1.0 / sum(1.0 / 4.0 ** s for s in range(loss_scales))
     self.loss_value.zero_()
@@ -584,7 +683,7 @@ class Trainer:
       if cfg.feature_weight > 0:
         for fp in loaded:
           ctx.call("dd_loss_fwd_bwd", _b(pred_view(st["finals"][s], fp)), _b(_lib.desc(tgt[fp.name][s])), kind,
-                   ctypes.c_float(cfg.feature_weight * factor / px), ctypes.c_float(1e-2), _fp(self.loss_value),
+                   ctypes.c_float(S * cfg.feature_weight * factor / px), ctypes.c_float(1e-2), _fp(self.loss_value),
                    _b(pred_view(dfin[s], fp)), 1)
       # combined lighting passes color * (direct + indirect) and the combined image (sum of everything)
       lights = [l for l in _LIGHTS if all((l + k) in by_name and by_name[l + k].load_data for k in (" Color", " Direct", " Indirect"))]
@@ -616,14 +715,14 @@ class Trainer:
           ctx.call("dd_axpy", ctypes.c_float(1.0), _b(pred_view(st["finals"][s], fp)), _b(_lib.desc(img_p)))
           ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(tgt[t][s])), _b(_lib.desc(img_t)))
         ctx.call("dd_loss_fwd_bwd", _b(_lib.desc(img_p)), _b(_lib.desc(img_t)), kind,
-                 ctypes.c_float(cfg.combined_image_weight * factor / px), ctypes.c_float(1e-2), _fp(self.loss_value),
+                 ctypes.c_float(S * cfg.combined_image_weight * factor / px), ctypes.c_float(1e-2), _fp(self.loss_value),
                  _b(_lib.desc(g_img)), 0)
         for t in image_terms:
           ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(g_img)), _b(pred_view(dfin[s], by_name[t])))
       for l, (cp, ct, gc) in comb.items():
         if cfg.combined_feature_weight > 0:
           ctx.call("dd_loss_fwd_bwd", _b(_lib.desc(cp)), _b(_lib.desc(ct)), kind,
-                   ctypes.c_float(cfg.combined_feature_weight * factor / px), ctypes.c_float(1e-2), _fp(self.loss_value),
+                   ctypes.c_float(S * cfg.combined_feature_weight * factor / px), ctypes.c_float(1e-2), _fp(self.loss_value),
                    _b(_lib.desc(gc)), 1)
         if use_image:
           ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(g_img)), _b(_lib.desc(gc)))
@@ -634,6 +733,8 @@ class Trainer:
         ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(inc)), _b(pred_view(dfin[s], d)))
         ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(inc)), _b(pred_view(dfin[s], i)))
     self._dfinal = dfin
+    if S != 1.0:
+      self.loss_value.div_(S)
     return self.loss_value
 
   # ------------------------------------------------------------------------------------------ backward of everything
@@ -680,7 +781,7 @@ class Trainer:
     # kernel prediction -> logits gradients (largest first), then the network
     dlogits = []
     for s in range(n_scales):
-      dl = V(self._buf("dlogits%d" % s, tuple(st["logits"][s].t.shape)))
+      dl = self._act("dlogits%d" % s, tuple(st["logits"][s].t.shape[:3]), st["logits"][s].c)
       ctx.call("dd_kernel_predict_bwd", _b(_lib.desc(st["kp_sources"][s])), _b(st["logits"][s].d), _b(_lib.desc(dlarge[s])),
                arch.kernel_size, arch.features_per_tuple, n, _b(dl.d))
       dlogits.append(dl)
@@ -714,6 +815,7 @@ class Trainer:
       dist.all_reduce(loss)
       loss /= world_size
       scale = 1.0 / world_size                    # the loss is a mean over the global batch (Training.py:128)
+    scale /= self._scale_used
     self.step_count += 1
     self.ctx.call("dd_adam_step", _fp(self.theta), _fp(self.grad), _fp(self.adam_m), _fp(self.adam_v),
                   ctypes.c_size_t(self.count), ctypes.c_float(self.settings.learning_rate), ctypes.c_float(0.9),
