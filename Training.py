@@ -37,6 +37,9 @@ parser.add_argument("--synthetic_tiles", type=int, default=None, help="Global ba
 parser.add_argument("--synthetic_tile_size", type=int, default=64)
 parser.add_argument("--steps_per_epoch", type=int, default=10)
 parser.add_argument("--checkpoint_steps", type=int, default=500)
+parser.add_argument("--precision", default=None, choices=["float32", "float16"],
+                    help="float16: tensor-core path (U-Net; fp16 activations, fp32 master weights); float32: exact path. "
+                         "Default: float16 for U-Net, float32 for Tiramisu.")
 
 
 def synthetic_batch(architecture, tiles, size, seed):
@@ -54,7 +57,7 @@ def main(parsed_arguments):
   base = os.path.dirname(os.path.abspath(parsed_arguments.json_filename))
   with open(os.path.join(base, training_json["architecture"]), "r") as f:      # relative to the training json (:953-961)
     architecture_json = json.load(f)
-  architecture_json.setdefault("b200", {})["dtype"] = "float32"               # exact training path (round 1)
+  architecture_json.setdefault("b200", {})["dtype"] = "float32"               # the Trainer owns the training arithmetic mode
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
   local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -64,7 +67,8 @@ def main(parsed_arguments):
   architecture = Architecture(architecture_json, source_data_format="channels_last",
                               data_format=parsed_arguments.data_format, device=local)
   settings = TrainingSettings(training_json)
-  trainer = Trainer(architecture, settings)
+  precision = parsed_arguments.precision or ("float16" if architecture.spec.core_name == "U-Net" else "float32")
+  trainer = Trainer(architecture, settings, precision=precision)
   model_dir = os.path.join(base, architecture.model_directory)
   os.makedirs(model_dir, exist_ok=True)
   checkpoints = sorted(glob.glob(os.path.join(model_dir, "ckpt-*.npz")), key=lambda p: int(p.split("-")[-1][:-4]))
@@ -87,7 +91,7 @@ def main(parsed_arguments):
       dt = time.perf_counter() - t0
       if rank == 0:
         rec = {"step": trainer.step_count, "epoch": epoch, "loss": loss, "learning_rate": settings.learning_rate,
-               "batch_size": global_tiles, "tile": size, "ranks": world, "seconds": dt,
+               "batch_size": global_tiles, "tile": size, "ranks": world, "seconds": dt, "precision": precision,
                "megapixels_per_second": global_tiles * size * size / 1e6 / dt}
         log.write(json.dumps(rec) + "\n")
         log.flush()

@@ -448,10 +448,14 @@ int dd_conv2d_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const f
     return launch_conv_simt(ctx, x, reinterpret_cast<const float*>(w_packed), bias, ksize, y->c, flags, residual, y,
                             y_relu, 1, 0, 0, s);
   }
-  // output channels are processed in slices of at most 256 (one UMMA N); each slice is its own launch
+  // output channels are processed in slices: at most 256 (one UMMA N) for 1x1, at most 128 for 3x3 (the TMEM ring must hold
+  // the three output rows an input row feeds plus one being drained: 4 blocks of <= 128 columns); each slice is a launch
   const int cpad_total = packed_cpad(y->c);
-  for (int row0 = 0; row0 < cpad_total; row0 += 256) {
-    const int cpad = (cpad_total - row0 < 256) ? (cpad_total - row0) : 256;
+  const int max_slice = (ksize == 3) ? 128 : 256;
+  const int n_slices = (cpad_total + max_slice - 1) / max_slice;
+  const int slice = round_up((cpad_total + n_slices - 1) / n_slices, 32);
+  for (int row0 = 0; row0 < cpad_total; row0 += slice) {
+    const int cpad = (cpad_total - row0 < slice) ? (cpad_total - row0) : slice;
     const int cout = (y->c - row0 < cpad) ? (y->c - row0) : cpad;
     dd_tensor ys = *y, yr, rs;
     ys.coff += row0; ys.c = cout;

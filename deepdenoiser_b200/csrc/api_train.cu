@@ -277,13 +277,14 @@ struct ComposeTailBwdParams {
   float* dw; float* db;                              // [c_mid], [1] accumulated
 };
 __global__ void __launch_bounds__(256) compose_tail_bwd_kernel(const ComposeTailBwdParams p) {
+  // grid-stride over pixels: the parameter gradients are accumulated per thread and flushed once per warp at the end
   const size_t total = static_cast<size_t>(p.large.n) * p.large.h * p.large.w;
-  const size_t pixel = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   float dwl[kCmpC];
   float dbl = 0.f;
 #pragma unroll
   for (int c = 0; c < kCmpC; ++c) dwl[c] = 0.f;
-  if (pixel < total) {
+  for (size_t pixel = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; pixel < total;
+       pixel += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int x0 = static_cast<int>(pixel % p.large.w);
     const int y0 = static_cast<int>((pixel / p.large.w) % p.large.h);
     const int n = static_cast<int>(pixel / (static_cast<size_t>(p.large.w) * p.large.h));
@@ -312,23 +313,32 @@ __global__ void __launch_bounds__(256) compose_tail_bwd_kernel(const ComposeTail
       atomicAdd(ds + spix * p.dsmall.cstride + p.dsmall.coff + c, wgt * g);
     }
     const float da = (a > 0.f) ? dwgt * wgt * (1.f - wgt) : 0.f;
-    for (int c = 0; c < p.c_mid; ++c) {
-      const float tv = p.t.load(pixel, c);
-      p.dt.store(pixel, c, da * p.w[c]);
-      dwl[c] = da * tv;
+#pragma unroll
+    for (int c = 0; c < kCmpC; ++c) {
+      if (c < p.c_mid) {
+        const float tv = p.t.load(pixel, c);
+        p.dt.store(pixel, c, da * p.w[c]);
+        dwl[c] = fmaf(da, tv, dwl[c]);
+      }
     }
-    dbl = da;
+    dbl += da;
   }
-  // warp-reduce the parameter gradients, one atomic per warp
-  for (int c = 0; c < p.c_mid; ++c) {
+  __shared__ float s_acc[kCmpC + 1];
+  for (int i = threadIdx.x; i <= kCmpC; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < kCmpC; ++c) {
     float v = dwl[c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(p.dw + c, v);
+    if ((threadIdx.x & 31) == 0 && c < p.c_mid) atomicAdd(&s_acc[c], v);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dbl += __shfl_xor_sync(0xffffffffu, dbl, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(p.db, dbl);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[kCmpC], dbl);
+  __syncthreads();
+  if (threadIdx.x < p.c_mid) atomicAdd(p.dw + threadIdx.x, s_acc[threadIdx.x]);
+  if (threadIdx.x == 0) atomicAdd(p.db, s_acc[kCmpC]);
 }
 
 struct ComposeHeadBwdParams {
@@ -337,44 +347,61 @@ struct ComposeHeadBwdParams {
   float* dw; float* db;                        // [6][c_mid], [c_mid] accumulated
 };
 __global__ void __launch_bounds__(256) compose_head_bwd_kernel(const ComposeHeadBwdParams p) {
+  // grid-stride over 256-pixel groups; dW [6][c_mid] and db [c_mid] are reduced per warp into shared memory and flushed with
+  // one global atomic per entry and block (every warp hitting the same 7 * c_mid global addresses serialised the old version)
+  __shared__ float s_acc[7 * kCmpC];
+  for (int i = threadIdx.x; i < 7 * kCmpC; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
   const size_t total = static_cast<size_t>(p.large.n) * p.large.h * p.large.w;
-  const size_t pixel = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const bool valid = pixel < total;
-  float in[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float din[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  size_t spix = 0;
-  if (valid) {
-    const int x0 = static_cast<int>(pixel % p.large.w);
-    const int y0 = static_cast<int>((pixel / p.large.w) % p.large.h);
-    const int n = static_cast<int>(pixel / (static_cast<size_t>(p.large.w) * p.large.h));
-    spix = p.small.pix(n, y0 >> 1, x0 >> 1);
+  for (size_t base = static_cast<size_t>(blockIdx.x) * blockDim.x; base < total; base += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pixel = base + threadIdx.x;
+    const bool valid = pixel < total;
+    float in[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float din[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    size_t spix = 0;
+    if (valid) {
+      const int x0 = static_cast<int>(pixel % p.large.w);
+      const int y0 = static_cast<int>((pixel / p.large.w) % p.large.h);
+      const int n = static_cast<int>(pixel / (static_cast<size_t>(p.large.w) * p.large.h));
+      spix = p.small.pix(n, y0 >> 1, x0 >> 1);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { in[c] = p.small.load(spix, c); in[3 + c] = p.large.load(pixel, c); }
-  }
-  for (int c = 0; c < p.c_mid; ++c) {
-    float dz = 0.f;
-    if (valid && p.y.load(pixel, c) > 0.f) dz = p.dy.load(pixel, c);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      din[k] = fmaf(dz, p.w[k * p.c_mid + c], din[k]);
-      float v = dz * in[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((threadIdx.x & 31) == 0) atomicAdd(p.dw + k * p.c_mid + c, v);
+      for (int c = 0; c < 3; ++c) { in[c] = p.small.load(spix, c); in[3 + c] = p.large.load(pixel, c); }
     }
-    float v = dz;
+    for (int c = 0; c < p.c_mid; ++c) {
+      float dz = 0.f;
+      if (valid && p.y.load(pixel, c) > 0.f) dz = p.dy.load(pixel, c);
+      float v[7];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(p.db + c, v);
-  }
-  if (valid) {
-    float* dl = reinterpret_cast<float*>(p.dlarge.ptr);
-    float* ds = reinterpret_cast<float*>(p.dsmall.ptr);
+      for (int k = 0; k < 6; ++k) {
+        din[k] = fmaf(dz, p.w[k * p.c_mid + c], din[k]);
+        v[k] = dz * in[k];
+      }
+      v[6] = dz;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      atomicAdd(ds + spix * p.dsmall.cstride + p.dsmall.coff + c, din[c]);
-      atomicAdd(dl + pixel * p.dlarge.cstride + p.dlarge.coff + c, din[3 + c]);
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+      }
+      if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) atomicAdd(&s_acc[k * kCmpC + c], v[k]);
+      }
     }
+    if (valid) {
+      float* dl = reinterpret_cast<float*>(p.dlarge.ptr);
+      float* ds = reinterpret_cast<float*>(p.dsmall.ptr);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        atomicAdd(ds + spix * p.dsmall.cstride + p.dsmall.coff + c, din[c]);
+        atomicAdd(dl + pixel * p.dlarge.cstride + p.dlarge.coff + c, din[3 + c]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 7 * p.c_mid; i += blockDim.x) {
+    const int k = i / p.c_mid, c = i % p.c_mid;
+    if (k < 6) atomicAdd(p.dw + k * p.c_mid + c, s_acc[k * kCmpC + c]);
+    else atomicAdd(p.db + c, s_acc[6 * kCmpC + c]);
   }
 }
 
@@ -623,7 +650,9 @@ int dd_compose_tail_bwd(dd_ctx* ctx, const dd_tensor* t, const float* w, const f
   p.dsmall = make_view(dsmall); p.dlarge = make_view(dlarge);
   memcpy(p.w, w, sizeof(float) * c_mid); p.b = b[0]; p.c_mid = c_mid; p.dw = dw_dev; p.db = db_dev;
   const size_t total = static_cast<size_t>(large->n) * large->h * large->w;
-  compose_tail_bwd_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  unsigned blocks = nblocks(total, 256);
+  if (blocks > static_cast<unsigned>(ctx->sm_count) * 8) blocks = static_cast<unsigned>(ctx->sm_count) * 8;
+  compose_tail_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }
@@ -641,7 +670,9 @@ int dd_compose_head_bwd(dd_ctx* ctx, const dd_tensor* small, const dd_tensor* la
   p.dsmall = make_view(dsmall); p.dlarge = make_view(dlarge);
   memcpy(p.w, w, sizeof(float) * 6 * c_mid); p.c_mid = c_mid; p.dw = dw_dev; p.db = db_dev;
   const size_t total = static_cast<size_t>(large->n) * large->h * large->w;
-  compose_head_bwd_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  unsigned blocks = nblocks(total, 256);
+  if (blocks > static_cast<unsigned>(ctx->sm_count) * 8) blocks = static_cast<unsigned>(ctx->sm_count) * 8;
+  compose_head_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }

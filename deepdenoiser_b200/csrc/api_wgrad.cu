@@ -455,6 +455,36 @@ __global__ void __launch_bounds__(256) relu_bias_generic_kernel(const ReluBiasPa
   }
 }
 
+
+// fast path: fp16 tensors, 8 channels (16 bytes) per thread
+__global__ void __launch_bounds__(256) s2d_mask_vec_kernel(const S2dParams p) {
+  const int C = p.dy.c, G = C >> 3;
+  const size_t total = static_cast<size_t>(p.out.n) * p.out.h * p.out.w * 4 * G;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g4 = static_cast<int>(idx % (4 * G));
+  const size_t opix = idx / (4 * G);
+  const int sp = g4 / G, g = g4 % G;
+  const int j = static_cast<int>(opix % p.out.w), i = static_cast<int>((opix / p.out.w) % p.out.h);
+  const int n = static_cast<int>(opix / (static_cast<size_t>(p.out.w) * p.out.h));
+  const size_t ipix = p.dy.pix(n, 2 * i + (sp >> 1), 2 * j + (sp & 1));
+  uint4 d = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.dy.ptr) + ipix * p.dy.cstride + p.dy.coff + g * 8);
+  if (p.has_y) {
+    const uint4 yv = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.y.ptr) + ipix * p.y.cstride + p.y.coff + g * 8);
+    const __half2* yh = reinterpret_cast<const __half2*>(&yv);
+    __half2* dh = reinterpret_cast<__half2*>(&d);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 yf = __half22float2(yh[e]);
+      float2 df = __half22float2(dh[e]);
+      if (!(yf.x > 0.f)) df.x = 0.f;
+      if (!(yf.y > 0.f)) df.y = 0.f;
+      dh[e] = __floats2half2_rn(df.x, df.y);
+    }
+  }
+  *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out.ptr) + opix * p.out.cstride + p.out.coff + sp * C + g * 8) = d;
+}
+
 }  // namespace dd
 
 using namespace dd;
@@ -492,7 +522,11 @@ int dd_space_to_depth2_mask(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y
   p.dy = make_view(dy); p.out = make_view(out); p.has_y = y ? 1 : 0;
   p.y = y ? make_view(y) : p.dy;
   const size_t total = static_cast<size_t>(out->n) * out->h * out->w * out->c;
-  s2d_mask_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  auto aligned = [](const dd_tensor* t) { return t->dtype == DD_F16 && t->c % 8 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0; };
+  if (aligned(dy) && aligned(out) && (!y || aligned(y)))
+    s2d_mask_vec_kernel<<<static_cast<unsigned>((total / 8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else
+    s2d_mask_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }

@@ -815,13 +815,17 @@ class Trainer:
       dist.all_reduce(loss)
       loss /= world_size
       scale = 1.0 / world_size                    # the loss is a mean over the global batch (Training.py:128)
-    scale /= self._scale_used
+    self.apply_gradients(scale)
+    return loss
+
+  def apply_gradients(self, scale=1.0):
+    """TF-form Adam on the flat buffers (the loss scale of the fp16 path is divided out here) + weight repack."""
+    scale /= getattr(self, "_scale_used", 1.0)
     self.step_count += 1
     self.ctx.call("dd_adam_step", _fp(self.theta), _fp(self.grad), _fp(self.adam_m), _fp(self.adam_v),
                   ctypes.c_size_t(self.count), ctypes.c_float(self.settings.learning_rate), ctypes.c_float(0.9),
                   ctypes.c_float(0.999), ctypes.c_float(1e-8), ctypes.c_int64(self.step_count), ctypes.c_float(scale))
     self._repack()
-    return loss
 
   # ------------------------------------------------------------------------------------------ checkpoints
   def save_checkpoint(self, path):

@@ -56,6 +56,7 @@ CONV_TC_CASES = [
     (3, 96, 96, 1, 10, 130, 96, 0),
     (3, 192, 96, 1, 10, 130, 200, 8),        # concat buffer window
     (3, 128, 128, 1, 9, 140, 128, 0),
+    (3, 96, 192, 1, 9, 140, 96, 0),          # wide output: two 96-column slices (input gradient of the 192->96 layer)
     (3, 24, 24, 1, 12, 40, 24, 0),           # compose residual convs
     (1, 64, 25, 2, 9, 150, 64, 0),           # post-process K=5
     (1, 25, 25, 1, 9, 150, 32, 0),

@@ -90,7 +90,7 @@ def test_pack_weights_dev_transposed_matches_host(ctx):
   assert torch.equal(host, devp)
 
 
-@pytest.mark.parametrize("ks,cin,cout", [(3, 64, 64), (3, 32, 64), (1, 64, 25), (3, 96, 128)])
+@pytest.mark.parametrize("ks,cin,cout", [(3, 64, 64), (3, 32, 64), (1, 64, 25), (3, 96, 128), (3, 192, 96)])
 def test_dgrad_through_forward_kernel(ctx, ks, cin, cout):
   """dx = conv(dz, flipped / channel-swapped W) on the tcgen05 forward kernel == autograd input gradient."""
   n, h, w = 1, 12, 140
