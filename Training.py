@@ -8,8 +8,11 @@ Same command line as the reference's TensorFlow/Training.py:33-61 (extra flags a
 `python -m torch.distributed.run --nproc-per-node N Training.py ...` (tiles are sharded over the ranks).
 Checkpoints (.npz: weights under their TF variable names + Adam moments + step) are written to the JSON's
 model_directory every 500 steps (Training.py:1214-1218) and the latest one is resumed; scalars go to
-<model_directory>/training_log.jsonl.  Data: the reference reads TFRecords made by TFRecordsCreator.py; until the
-TensorFlow-free reader lands this script trains on seeded synthetic render-pass tiles (--synthetic_tiles).
+<model_directory>/training_log.jsonl.
+Data: like the reference, `<base_tfrecords_directory>/training/*.tfrecords.gz` + `training.json` written by
+TFRecordsCreator.py (read without TensorFlow by deepdenoiser_b200/tfrecords.py; data augmentation on the GPU,
+deepdenoiser_b200/augmentation.py).  When that directory does not exist, or with --synthetic_tiles, the script trains on
+seeded synthetic render-pass tiles; --write_synthetic_tfrecords N first writes N such tiles in the reference's format.
 """
 import argparse
 import glob
@@ -21,7 +24,9 @@ import time
 
 import torch
 
-from deepdenoiser_b200 import synthetic
+import numpy as np
+
+from deepdenoiser_b200 import augmentation, synthetic, tfrecords
 from deepdenoiser_b200.Architecture import Architecture
 from deepdenoiser_b200.training import Trainer, TrainingSettings
 
@@ -37,6 +42,8 @@ parser.add_argument("--synthetic_tiles", type=int, default=None, help="Global ba
 parser.add_argument("--synthetic_tile_size", type=int, default=64)
 parser.add_argument("--steps_per_epoch", type=int, default=10)
 parser.add_argument("--checkpoint_steps", type=int, default=500)
+parser.add_argument("--write_synthetic_tfrecords", type=int, default=0,
+                    help="Write this many synthetic tiles as <base_tfrecords_directory>/training (reference format) and use them.")
 parser.add_argument("--precision", default=None, choices=["float32", "float16"],
                     help="float16: tensor-core path (U-Net; fp16 activations, fp32 master weights); float32: exact path. "
                          "Default: float16 for U-Net, float32 for Tiramisu.")
@@ -49,6 +56,40 @@ def synthetic_batch(architecture, tiles, size, seed):
   targets = {"target_image/" + fp.name: torch.from_numpy(clean["source_image/0/" + fp.name])
              for fp in architecture.feature_predictions if fp.load_data}
   return features, targets
+
+
+def write_synthetic_dataset(architecture, directory, tiles, size, seed=4242):
+  """Synthetic stand-in for TFRecordsCreator.py: `tiles` examples, one source per example, 16 samples per pixel."""
+  noisy = synthetic.synthetic_features(architecture, tiles, size, size, seed=seed)
+  clean = synthetic.synthetic_features(architecture, tiles, size, size, seed=seed + 7919)
+  every = list(architecture.feature_predictions) + list(architecture.auxiliary_features)
+
+  def examples():
+    for e in range(tiles):
+      feats = {}
+      for fp in every:
+        if not fp.load_data:
+          continue
+        feats["source_image/16/0/" + fp.name] = noisy["source_image/0/" + fp.name][e]
+        if fp.is_target:
+          feats["target_image/" + fp.name] = clean["source_image/0/" + fp.name][e]
+      yield feats
+
+  settings = {"tiles_height_width": size, "number_of_sources_per_example": 1, "source_samples_per_pixel_list": [16]}
+  return tfrecords.write_tile_dataset(directory, "training", examples(), settings)
+
+
+def tfrecord_batches(architecture, training_json, base, per_rank, rank, world, trainer, epoch_seed):
+  """input_fn_tfrecords (Training.py:728-850): records -> (sources, targets) examples -> device augmentation -> batches."""
+  directory = os.path.join(base, training_json["base_tfrecords_directory"])
+  dataset = tfrecords.TileDataset(os.path.join(directory, "training"), os.path.join(directory, "training.json"), architecture,
+                                  number_of_source_index_tuples=int(training_json.get("number_of_source_index_tuples", 1)))
+  usage = augmentation.DataAugmentationUsage.from_json(training_json)
+  augment = augmentation.DeviceAugmenter(trainer.ctx, usage)
+  rng = np.random.default_rng(epoch_seed * 7919 + rank)
+  for sources, targets in dataset.batches(per_rank, shuffle_seed=epoch_seed, rank=rank, world=world):
+    draws = augmentation.draw(usage, per_rank, rng)
+    yield augment(sources, targets, draws)
 
 
 def main(parsed_arguments):
@@ -82,10 +123,27 @@ def main(parsed_arguments):
   per_rank = global_tiles // world
   log = open(os.path.join(model_dir, "training_log.jsonl"), "a") if rank == 0 else None
   size = parsed_arguments.synthetic_tile_size
+  records_dir = os.path.join(base, training_json.get("base_tfrecords_directory", ""), "training")
+  if parsed_arguments.write_synthetic_tfrecords and rank == 0:
+    write_synthetic_dataset(architecture, os.path.dirname(records_dir), parsed_arguments.write_synthetic_tfrecords, size)
+  if world > 1:
+    dist.barrier()
+  use_records = parsed_arguments.synthetic_tiles is None and os.path.isdir(records_dir)
+  if rank == 0:
+    print("data:", ("TFRecords under " + records_dir) if use_records else "seeded synthetic tiles")
+
+  def epoch_batches(epoch):
+    if use_records:
+      for features, targets in tfrecord_batches(architecture, training_json, base, per_rank, rank, world, trainer, epoch + 1):
+        yield features, targets
+    else:
+      for _ in range(parsed_arguments.steps_per_epoch):
+        yield synthetic_batch(architecture, per_rank, size, seed=1000003 * trainer.step_count + rank)
+
   for epoch in range(parsed_arguments.train_epochs):
-    for _ in range(parsed_arguments.steps_per_epoch):
-      step = trainer.step_count
-      features, targets = synthetic_batch(architecture, per_rank, size, seed=1000003 * step + rank)
+    for features, targets in epoch_batches(epoch):
+      if use_records:
+        size = next(iter(features.values())).shape[1]
       t0 = time.perf_counter()
       loss = float(trainer.train_step(features, targets, world_size=world).item())
       dt = time.perf_counter() - t0

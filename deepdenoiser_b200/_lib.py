@@ -92,6 +92,8 @@ SIGNATURES = {
     "dd_channel_sum": (_i, [_vp, _T, _i, _vp, _vp]),
     "dd_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                           ctypes.c_int64, ctypes.c_float, _vp]),
+    "dd_crc32c": (ctypes.c_uint32, [ctypes.c_char_p, _sz]),
+    "dd_augment_tiles": (_i, [_vp, _T, _i, _vp, _vp, _vp, _vp, _T, _vp]),
     "dd_cast_copy": (_i, [_vp, _T, _T, _vp]),
     "dd_l2_flush": (_i, [_vp, _vp, _sz, _vp]),
 }

@@ -264,6 +264,23 @@ int dd_channel_sum(dd_ctx* ctx, const dd_tensor* x, int groups, float* out_dev, 
 int dd_adam_step(dd_ctx* ctx, float* w, const float* g, float* m, float* v, size_t count, float lr, float beta1, float beta2,
                  float epsilon, int64_t step, float grad_scale, void* stream);
 
+/* ---- training input pipeline ----------------------------------------------------------------- */
+/* CRC-32C (Castagnoli) of a host buffer: the checksum of the TFRecord framing written by TFRecordsCreator.py:221-230
+ * (tf.python_io.TFRecordWriter); host code, needs no device. */
+uint32_t dd_crc32c(const void* data, size_t size);
+/* On-device data augmentation of one batch of square tiles (DataAugmentation.py:10-200, driver Training.py:794-821):
+ * per example e: flip_left_right if flip[e] (:10-28), rot90 counter-clockwise rot[e] times (:47-61), channel permutation
+ * perm[e] in 0..5 for 3-channel colour passes (:106-125; table :117-123), screen-space-normal sign fix-ups
+ * (kind == DD_AUG_SCREEN_SPACE_NORMAL, :31-45,63-104) and the 3x3 rotation out = in . R[e] for world-space normals
+ * (kind == DD_AUG_NORMAL, matrix [e][9] row major or NULL, :184-200).  x, y: [E,S,S,C] fp32, y != x; flip / rot / perm:
+ * device int32 [E] (NULL = identity). */
+#define DD_AUG_PLAIN 0
+#define DD_AUG_COLOR 1
+#define DD_AUG_SCREEN_SPACE_NORMAL 2
+#define DD_AUG_NORMAL 3
+int dd_augment_tiles(dd_ctx* ctx, const dd_tensor* x, int kind, const int32_t* flip_dev, const int32_t* rot_dev,
+                     const int32_t* perm_dev, const float* rotation_dev, const dd_tensor* y, void* stream);
+
 /* ---- utilities ------------------------------------------------------------------------------ */
 /* dtype / channel-view conversion copy y = cast(x) (c channels). */
 int dd_cast_copy(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, void* stream);

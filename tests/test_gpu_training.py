@@ -197,3 +197,32 @@ def test_tensor_core_training_reduces_the_loss_like_the_exact_path():
   print("fp16 ", ["%.4f" % l for l in lm])
   assert lm[-1] < lm[0] - 0.4
   assert all(abs(a - b) <= 2e-2 * max(1.0, abs(a)) for a, b in zip(le, lm))     # same trajectory within fp16 noise
+
+
+def test_training_cli_reads_tfrecords_and_augments_on_device(tmp_path):
+  """Training.py end to end on the reference's data format: synthetic tiles written as GZIP TFRecords + training.json,
+  read back without TensorFlow, augmented on the GPU, tensor-core training steps, checkpoint + resume."""
+  import json, os, subprocess, sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  j = small_example(filters=(16, 24), n_convs=1, k=3)
+  j["model_directory"] = "model"
+  training = json.load(open(os.path.join(root, "configs", "TrainingExample.json")))
+  training["architecture"] = "arch.json"
+  training["base_tfrecords_directory"] = "records"
+  training["batch_size"] = 4
+  training["number_of_source_index_tuples"] = 2
+  json.dump(j, open(tmp_path / "arch.json", "w"))
+  json.dump(training, open(tmp_path / "train.json", "w"))
+  cmd = [sys.executable, os.path.join(root, "Training.py"), str(tmp_path / "train.json"), "--train_epochs", "2",
+         "--synthetic_tile_size", "32", "--write_synthetic_tfrecords", "6"]
+  out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+  assert out.returncode == 0, out.stderr[-2000:]
+  assert "TFRecords under" in out.stdout
+  assert sorted(os.listdir(tmp_path / "records" / "training")) == ["training_0.tfrecords.gz"]
+  steps = [json.loads(l) for l in out.stdout.splitlines() if l.startswith('{"step"')]
+  # 6 records x 2 index tuples = 12 examples = 3 batches of 4 per epoch, 2 epochs
+  assert [s["step"] for s in steps] == [1, 2, 3, 4, 5, 6] and steps[0]["precision"] == "float16" and steps[0]["tile"] == 32
+  assert all(np.isfinite(s["loss"]) for s in steps)
+  assert os.path.exists(tmp_path / "model" / "ckpt-6.npz")
+  out2 = subprocess.run(cmd[:4] + ["1"] + cmd[5:7], capture_output=True, text=True, timeout=600)
+  assert out2.returncode == 0 and "resumed from" in out2.stdout, out2.stderr[-2000:]
