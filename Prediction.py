@@ -62,7 +62,7 @@ def main(parsed_arguments):
   if rank == 0:
     loaded = {fp.name for fp in architecture.feature_predictions if fp.load_data}
     predictions = {k: v for k, v in predictions.items() if k[len("prediction/"):] in loaded}
-    image, _ = prediction.combine_passes(predictions)
+    image, _ = prediction.combine_passes(predictions, getattr(architecture, "ctx", None))
     for path in prediction.save_predictions(parsed_arguments.input, predictions, image):
       print(path)
   if world > 1:

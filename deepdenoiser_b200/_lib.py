@@ -94,6 +94,8 @@ SIGNATURES = {
                           ctypes.c_int64, ctypes.c_float, _vp]),
     "dd_crc32c": (ctypes.c_uint32, [ctypes.c_char_p, _sz]),
     "dd_augment_tiles": (_i, [_vp, _T, _i, _vp, _vp, _vp, _vp, _T, _vp]),
+    "dd_tiles_gather": (_i, [_vp, _T, _vp, _T, _vp]),
+    "dd_tiles_scatter": (_i, [_vp, _T, _vp, _T, _vp]),
     "dd_cast_copy": (_i, [_vp, _T, _T, _vp]),
     "dd_l2_flush": (_i, [_vp, _vp, _sz, _vp]),
 }

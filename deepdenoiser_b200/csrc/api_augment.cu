@@ -62,6 +62,36 @@ __global__ void __launch_bounds__(256) augment_kernel(const AugParams p) {
   dst[0] = v0; dst[1] = v1; dst[2] = v2;
 }
 
+
+// ------------------------------------------------------------------------------------------------ inference tiling
+// Prediction.py:282-310 cuts the frame into overlapping tiles on the host and :384-441 pastes the kept part of every
+// predicted tile back with numpy slicing; here both directions are one launch over a device table of
+// {y, x, crop_y0, crop_y1, crop_x0, crop_x1} per tile.
+struct TileParams { View image, tiles; const int32_t* table; int size; };
+
+__global__ void __launch_bounds__(256) tiles_gather_kernel(const TileParams p) {
+  const size_t total = static_cast<size_t>(p.tiles.n) * p.size * p.size;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int px = static_cast<int>(idx % p.size), py = static_cast<int>((idx / p.size) % p.size);
+  const int t = static_cast<int>(idx / (static_cast<size_t>(p.size) * p.size));
+  const int32_t* e = p.table + t * 6;
+  const size_t ipix = p.image.pix(0, e[0] + py, e[1] + px);
+  for (int c = 0; c < p.tiles.c; ++c) p.tiles.store(idx, c, p.image.load(ipix, c));
+}
+
+__global__ void __launch_bounds__(256) tiles_scatter_kernel(const TileParams p) {
+  const size_t total = static_cast<size_t>(p.tiles.n) * p.size * p.size;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int px = static_cast<int>(idx % p.size), py = static_cast<int>((idx / p.size) % p.size);
+  const int t = static_cast<int>(idx / (static_cast<size_t>(p.size) * p.size));
+  const int32_t* e = p.table + t * 6;
+  if (py < e[2] || py >= e[3] || px < e[4] || px >= e[5]) return;       // outside the part of the tile that is kept
+  const size_t ipix = p.image.pix(0, e[0] + py, e[1] + px);
+  for (int c = 0; c < p.tiles.c; ++c) p.image.store(ipix, c, p.tiles.load(idx, c));
+}
+
 }  // namespace dd
 
 using namespace dd;
@@ -81,6 +111,34 @@ extern "C" int dd_augment_tiles(dd_ctx* ctx, const dd_tensor* x, int kind, const
   p.kind = kind; p.flip = flip_dev; p.rot = rot_dev; p.perm = perm_dev; p.rotation = rotation_dev;
   const size_t total = static_cast<size_t>(p.E) * p.S * p.S;
   augment_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+static int tiles_common(dd_ctx* ctx, const dd_tensor* image, const int32_t* table_dev, const dd_tensor* tiles, TileParams* p) {
+  DD_CHECK_ARG(ctx && table_dev && tensor_ok(image) && tensor_ok(tiles), "bad argument");
+  DD_CHECK_ARG(image->n == 1 && tiles->h == tiles->w && tiles->c == image->c && tiles->h <= image->h && tiles->w <= image->w,
+               "tiles: image [1,H,W,C], tiles [T,S,S,C] with S <= H, W");
+  p->image = make_view(image); p->tiles = make_view(tiles); p->table = table_dev; p->size = tiles->h;
+  return DD_OK;
+}
+
+extern "C" int dd_tiles_gather(dd_ctx* ctx, const dd_tensor* image, const int32_t* table_dev, const dd_tensor* tiles, void* stream) {
+  TileParams p;
+  int rc = tiles_common(ctx, image, table_dev, tiles, &p);
+  if (rc) return rc;
+  const size_t total = static_cast<size_t>(tiles->n) * tiles->h * tiles->w;
+  tiles_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+extern "C" int dd_tiles_scatter(dd_ctx* ctx, const dd_tensor* tiles, const int32_t* table_dev, const dd_tensor* image, void* stream) {
+  TileParams p;
+  int rc = tiles_common(ctx, image, table_dev, tiles, &p);
+  if (rc) return rc;
+  const size_t total = static_cast<size_t>(tiles->n) * tiles->h * tiles->w;
+  tiles_scatter_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }

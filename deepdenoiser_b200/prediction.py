@@ -141,14 +141,37 @@ def tile_grid(height, width, tile_size=128, tile_overlap_size=14):
   return tiles, tile_size, tile_overlap_size
 
 
-def cut_tiles(image, tiles):
-  """[H,W,C] tensor -> [T,size,size,C] batch of tiles."""
+def tile_table(tiles):
+  """int32 [T][6] = {y, x, crop_y0, crop_y1, crop_x0, crop_x1}: the device table of dd_tiles_gather / dd_tiles_scatter."""
+  return torch.tensor([[t.y, t.x, t.crop[0], t.crop[1], t.crop[2], t.crop[3]] for t in tiles], dtype=torch.int32).reshape(-1, 6)
+
+
+def cut_tiles(image, tiles, ctx=None):
+  """[H,W,C] tensor -> [T,size,size,C] batch of tiles.  CUDA images are cut by one dd_tiles_gather launch."""
+  if ctx is not None and image.is_cuda:
+    import ctypes
+    from . import _lib
+    image = image.contiguous()
+    out = torch.empty((len(tiles), tiles[0].size, tiles[0].size, image.shape[2]), dtype=image.dtype, device=image.device)
+    table = tile_table(tiles).to(image.device)
+    ctx.call("dd_tiles_gather", ctypes.byref(_lib.desc(image.unsqueeze(0))), ctypes.c_void_p(table.data_ptr()),
+             ctypes.byref(_lib.desc(out)))
+    return out
   return torch.stack([image[t.y:t.y + t.size, t.x:t.x + t.size] for t in tiles], dim=0)
 
 
-def stitch_tiles(batch, tiles, height, width):
-  """[T,size,size,C] predictions -> [H,W,C] image, keeping each tile's crop (Prediction.py:384-441)."""
+def stitch_tiles(batch, tiles, height, width, ctx=None):
+  """[T,size,size,C] predictions -> [H,W,C] image, keeping each tile's crop (Prediction.py:384-441).  CUDA batches are
+  pasted by one dd_tiles_scatter launch."""
   out = torch.empty((height, width, batch.shape[3]), dtype=batch.dtype, device=batch.device)
+  if ctx is not None and batch.is_cuda:
+    import ctypes
+    from . import _lib
+    batch = batch.contiguous()
+    table = tile_table(tiles).to(batch.device)
+    ctx.call("dd_tiles_scatter", ctypes.byref(_lib.desc(batch)), ctypes.c_void_p(table.data_ptr()),
+             ctypes.byref(_lib.desc(out.unsqueeze(0))))
+    return out
   for i, t in enumerate(tiles):
     cy0, cy1, cx0, cx1 = t.crop
     dy0, dy1, dx0, dx1 = t.dest
@@ -164,13 +187,20 @@ def predict_image(architecture, features, height, width, tile_size=128, tile_ove
 
   full_frame=True skips the tiling (height and width must be divisible by 2^sampling steps): the reference tiles only
   to bound TensorFlow's memory; the results differ at tile borders where the tiles truncate the receptive field."""
-  predict_fn = predict_fn or (lambda f: architecture.predict(f)[0])
   dev = None
+  ctx = None
+  if predict_fn is None:
+    # product path: frame resident on the device, tiles cut / pasted by dd_tiles_gather / dd_tiles_scatter
+    architecture._ensure_device()
+    ctx = architecture.ctx
+    predict_fn = lambda f: architecture.predict(f)[0]   # noqa: E731
   tensors = {}
   for k, v in features.items():
     t = torch.as_tensor(v)
     if t.dim() == 2:
       t = t.unsqueeze(-1)
+    if ctx is not None:
+      t = t.to(ctx.device, torch.float32)      # the frame is uploaded ONCE; tiles are cut and pasted on the device
     tensors[k] = t
   if full_frame:
     out = predict_fn({k: v.unsqueeze(0) for k, v in tensors.items()})
@@ -181,7 +211,7 @@ def predict_image(architecture, features, height, width, tile_size=128, tile_ove
   for b0 in range(0, len(mine), tiles_per_batch):
     idx = mine[b0:b0 + tiles_per_batch]
     batch_tiles = [tiles[i] for i in idx]
-    batch = {k: cut_tiles(v, batch_tiles) for k, v in tensors.items()}
+    batch = {k: cut_tiles(v, batch_tiles, ctx) for k, v in tensors.items()}
     out = predict_fn(batch)
     for k, v in out.items():
       results.setdefault(k, []).append(v)
@@ -193,7 +223,7 @@ def predict_image(architecture, features, height, width, tile_size=128, tile_ove
       return None
   else:
     mine = list(range(len(tiles)))
-  return {k: stitch_tiles(v, tiles, height, width) for k, v in results.items()}
+  return {k: stitch_tiles(v, tiles, height, width, ctx if v.is_cuda else None) for k, v in results.items()}
 
 
 def _gather_tiles(results, mine, n_tiles, rank, world_size, dev):
@@ -213,11 +243,34 @@ def _gather_tiles(results, mine, n_tiles, rank, world_size, dev):
   return merged
 
 
-def combine_passes(predictions):
+def combine_passes(predictions, ctx=None):
   """Prediction.py:443-481: lighting = color * (direct + indirect); image = sum of the lighting passes + volume + env +
-  emission (alpha is ignored, as in the reference).  Missing passes contribute nothing."""
+  emission (alpha is ignored, as in the reference).  Missing passes contribute nothing.  With a Context and CUDA tensors the
+  arithmetic runs in libdd_b200 (dd_muladd_fwd / dd_axpy) so the stitched passes never leave the device before the .npy write."""
   def get(name):
     return predictions.get(Naming.feature_prediction_name(name))
+
+  on_device = ctx is not None and all(v.is_cuda for v in predictions.values())
+  if on_device:
+    import ctypes
+    from . import _lib
+    d = lambda t: ctypes.byref(_lib.desc(t.unsqueeze(0) if t.dim() == 3 else t))   # noqa: E731
+
+  def lighting(color, direct, indirect):
+    if not on_device:
+      return color * (direct + indirect)
+    color, direct, indirect = (t.float().contiguous() for t in (color, direct, indirect))
+    out = torch.empty_like(color)
+    ctx.call("dd_muladd_fwd", d(color), d(direct), d(indirect), d(out))
+    return out
+
+  def add(image, value):
+    if image is None:
+      return value.clone() if on_device else value
+    if not on_device:
+      return image + value
+    ctx.call("dd_axpy", ctypes.c_float(1.0), d(value.float().contiguous()), d(image))
+    return image
 
   image = None
   combined = {}
@@ -225,13 +278,13 @@ def combine_passes(predictions):
     color, direct, indirect = get(light + " Color"), get(light + " Direct"), get(light + " Indirect")
     if color is None or direct is None or indirect is None:
       continue
-    value = color * (direct + indirect)
+    value = lighting(color, direct, indirect)
     combined[light] = value
-    image = value if image is None else image + value
+    image = add(image, value)
   for name in (RenderPasses.VOLUME_DIRECT, RenderPasses.VOLUME_INDIRECT, RenderPasses.ENVIRONMENT, RenderPasses.EMISSION):
     value = get(name)
     if value is not None:
-      image = value if image is None else image + value
+      image = add(image, value)
   return image, combined
 
 

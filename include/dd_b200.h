@@ -281,6 +281,13 @@ uint32_t dd_crc32c(const void* data, size_t size);
 int dd_augment_tiles(dd_ctx* ctx, const dd_tensor* x, int kind, const int32_t* flip_dev, const int32_t* rot_dev,
                      const int32_t* perm_dev, const float* rotation_dev, const dd_tensor* y, void* stream);
 
+/* ---- inference tiling -------------------------------------------------------------------------- */
+/* Prediction.py:282-310 / :384-441 on the device: tiles[t] = image[y_t : y_t+S, x_t : x_t+S] and the inverse paste of the
+ * kept part [cy0,cy1) x [cx0,cx1) of every tile.  table_dev: int32 [T][6] = {y, x, cy0, cy1, cx0, cx1}; image [1,H,W,C],
+ * tiles [T,S,S,C]; the caller must make sure every table entry lies inside the image. */
+int dd_tiles_gather(dd_ctx* ctx, const dd_tensor* image, const int32_t* table_dev, const dd_tensor* tiles, void* stream);
+int dd_tiles_scatter(dd_ctx* ctx, const dd_tensor* tiles, const int32_t* table_dev, const dd_tensor* image, void* stream);
+
 /* ---- utilities ------------------------------------------------------------------------------ */
 /* dtype / channel-view conversion copy y = cast(x) (c channels). */
 int dd_cast_copy(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, void* stream);

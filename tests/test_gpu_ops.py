@@ -331,3 +331,21 @@ def test_bad_arguments_are_reported_not_crashed(ctx):
   n0 = ctx.launch_count()
   ctx.avgpool(_lib.desc(x), 2, _lib.desc(torch.zeros(1, 2, 2, 3, device="cuda")))
   assert ctx.launch_count() == n0 + 1
+
+
+# ------------------------------------------------------------------------------------------------ inference tiling
+def test_device_tiling_matches_host_slicing(ctx):
+  """dd_tiles_gather / dd_tiles_scatter == the reference's numpy slicing (Prediction.py:282-310, 384-441), bit exact."""
+  from deepdenoiser_b200 import prediction
+  h, w = 150, 333
+  tiles, size, overlap = prediction.tile_grid(h, w, 64, 7)
+  image = torch.from_numpy(RNG.standard_normal((h, w, 3)).astype(np.float32))
+  host_tiles = prediction.cut_tiles(image, tiles)
+  dev_tiles = prediction.cut_tiles(image.cuda(), tiles, ctx)
+  assert torch.equal(dev_tiles.cpu(), host_tiles)
+  pred = torch.from_numpy(RNG.standard_normal(tuple(host_tiles.shape)).astype(np.float32))
+  host_image = prediction.stitch_tiles(pred, tiles, h, w)
+  dev_image = prediction.stitch_tiles(pred.cuda(), tiles, h, w, ctx)
+  assert torch.equal(dev_image.cpu(), host_image)
+  # every pixel is covered exactly by the kept crops: stitching the cut tiles gives the image back
+  assert torch.equal(prediction.stitch_tiles(dev_tiles, tiles, h, w, ctx).cpu(), image)
