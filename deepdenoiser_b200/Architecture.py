@@ -391,7 +391,9 @@ class Architecture:
       x0 = net._buf("net.x0", (bc, h, w, c0p))
       ctx.assemble_input(table[t0 * c0p * entry_bytes:], t1 - t0, n, _lib.desc(x0))
       # 3. core architecture + 1x1 post-processing, all tuples of the chunk batched along N
-      logits = net.forward(V(x0, c0, 0))
+      core = net.forward_core(V(x0, c0, 0))                 # coarsest first
+      fuse = self.use_kernel_prediction and net.can_fuse_post_kp(self.kernel_size, ft)
+      logits = None if fuse else net.post_process(core)       # largest first
       # 4. split per feature + kernel prediction per scale (Architecture.py:581-591)
       lo, hi = t0 * ft * n, t1 * ft * n
       stage = []
@@ -399,7 +401,11 @@ class Architecture:
         last = (s == n_scales - 1)
         dst = finals[s][lo:hi] if last else net._buf("kp.out%d" % s, ((t1 - t0) * ft * n, h >> s, w >> s, 3),
                                                      torch.float32)
-        if self.use_kernel_prediction:
+        if fuse:
+          # 1x1 post-processing + kernel prediction in one kernel: the logits never reach HBM
+          k = (len(core) - 1 - s) if self.use_multiscale_predictions else 0
+          net.post_kernel_predict(k, core[k], _lib.desc(kp_sources[s][lo:hi]), self.kernel_size, ft, n, _lib.desc(dst))
+        elif self.use_kernel_prediction:
           ctx.kernel_predict(_lib.desc(kp_sources[s][lo:hi]), logits[s].d, self.kernel_size, ft, n, _lib.desc(dst))
         else:
           self._split_direct(logits[s], dst, t1 - t0, n)

@@ -96,6 +96,10 @@ SIGNATURES = {
     "dd_augment_tiles": (_i, [_vp, _T, _i, _vp, _vp, _vp, _vp, _T, _vp]),
     "dd_tiles_gather": (_i, [_vp, _T, _vp, _T, _vp]),
     "dd_tiles_scatter": (_i, [_vp, _T, _vp, _T, _vp]),
+    "dd_post_kp_supported": (_i, [_i, _i]),
+    "dd_post_kp_weights_bytes": (_sz, [_i, _i, _i]),
+    "dd_post_kp_pack_weights": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "dd_post_kp_fwd": (_i, [_vp, _T, _vp, _T, _i, _i, _i, _T, _vp]),
     "dd_cast_copy": (_i, [_vp, _T, _T, _vp]),
     "dd_l2_flush": (_i, [_vp, _vp, _sz, _vp]),
 }
@@ -256,6 +260,11 @@ class Context:
                                                ctypes.byref(inv) if inv is not None else None, ctypes.byref(out),
                                                self._stream()))
 
+  def post_kp(self, x, blob_dev, src, ksize, features, images_per_tuple, out):
+    """Fused 1x1 post-processing + kernel-prediction apply of one scale (dd_post_kp_fwd)."""
+    self._check(self.lib.dd_post_kp_fwd(self.handle, ctypes.byref(x), blob_dev.data_ptr(), ctypes.byref(src), ksize, features,
+                                        images_per_tuple, ctypes.byref(out), self._stream()))
+
   def invert_standardization(self, x, inv, y):
     self._check(self.lib.dd_invert_standardization(self.handle, ctypes.byref(x), ctypes.byref(inv), ctypes.byref(y),
                                                    self._stream()))
@@ -271,6 +280,23 @@ class Context:
   def l2_flush(self, scratch):
     self._check(self.lib.dd_l2_flush(self.handle, scratch.data_ptr(), scratch.numel() * scratch.element_size(),
                                      self._stream()))
+
+
+def pack_post_kp_weights(w1, b1, w2, b2, ksize, features):
+  """Host blob of dd_post_kp_fwd from the TF tensors of AdjustNumberOfChannels: w1 [1,1,cin,O], b1 [O], w2 [1,1,O,O], b2 [O]."""
+  import numpy as np
+  lib = load_library()
+  w1 = np.ascontiguousarray(np.asarray(w1, dtype=np.float32).reshape(-1, np.asarray(w1).shape[-1]))
+  w2 = np.ascontiguousarray(np.asarray(w2, dtype=np.float32).reshape(-1, np.asarray(w2).shape[-1]))
+  b1 = np.ascontiguousarray(b1, dtype=np.float32)
+  b2 = np.ascontiguousarray(b2, dtype=np.float32)
+  cin = w1.shape[0]
+  blob = np.zeros(lib.dd_post_kp_weights_bytes(cin, ksize, features), dtype=np.uint8)
+  rc = lib.dd_post_kp_pack_weights(w1.ctypes.data, b1.ctypes.data, w2.ctypes.data, b2.ctypes.data, cin, ksize, features,
+                                   blob.ctypes.data)
+  if rc != 0:
+    raise DDError("dd_post_kp_pack_weights failed: %s" % lib.dd_last_error().decode())
+  return blob
 
 
 def pack_compose_weights(head_w, head_b, conv_w, conv_b, tail_w, tail_b):

@@ -258,6 +258,7 @@ class DeviceNetwork:
     self.ctx, self.spec, self.dtype = ctx, spec, dtype
     self.logits_dtype = logits_dtype if dtype == torch.float16 else torch.float32
     self.fused_compose = True   # tests flip this to compare against the layer-by-layer path
+    self.fused_post_kp = True   # likewise: 1x1 post-processing + kernel-prediction apply in one kernel
     self.align = 8 if dtype == torch.float16 else 1
     if dtype == torch.float16:
       for f in spec.filters:
@@ -285,6 +286,7 @@ class DeviceNetwork:
       bias = torch.zeros(_round_up(var.cout, 16), dtype=torch.float32)
       bias[:var.cout] = torch.from_numpy(b)
       self.bias[var.name] = bias.to(dev)
+    self.post_kp_packed = {}    # (scale index in spec.post, K, features) -> device blob, built on first use
     self.compose_packed = None
     if self.spec.compose and self.dtype == torch.float16:
       head, c1, c2, c3, c4, tail = self.spec.compose
@@ -457,12 +459,37 @@ class DeviceNetwork:
     self.ctx.conv2d_transpose3x3(x.d, self.packed[var.name], self.bias[var.name], y.d, y_act.d, relu=True)
 
   # -- public ------------------------------------------------------------------------------------------
+  def forward_core(self, x0):
+    """Core architecture only: the multi-scale outputs, COARSEST first (the order of spec.post)."""
+    spec = self.spec
+    assert x0.c == spec.input_channels, (x0.c, spec.input_channels)
+    return self._forward_unet(x0) if spec.core_name == "U-Net" else self._forward_tiramisu(x0)
+
+  def can_fuse_post_kp(self, ksize, features):
+    return (self.fused_post_kp and self.dtype == torch.float16 and
+            bool(self.ctx.lib.dd_post_kp_supported(int(ksize), int(features))) and
+            self.spec.output_channels == features * ksize * ksize)
+
+  def post_kernel_predict(self, k, r, src, ksize, features, images_per_tuple, out):
+    """AdjustNumberOfChannels of core output `r` (index k of spec.post) + kernel prediction on `src`, fused."""
+    key = (k, ksize, features)
+    blob = self.post_kp_packed.get(key)
+    if blob is None:
+      a, bvar = self.spec.post[k]
+      blob = torch.from_numpy(_lib.pack_post_kp_weights(self.host[a.name][0], self.host[a.name][1], self.host[bvar.name][0],
+                                                        self.host[bvar.name][1], ksize, features)).to(self.ctx.device)
+      self.post_kp_packed[key] = blob
+    self.ctx.post_kp(r.d, blob, src, ksize, features, images_per_tuple, out)
+
   def forward(self, x0):
     """x0: V over [B,H,W,C0] (dtype of the network).  Returns the post-processed outputs (logits), LARGEST
     scale first (Architecture.py:577-579), as V over [B,h,w,O] tensors of `logits_dtype`."""
     spec = self.spec
-    assert x0.c == spec.input_channels, (x0.c, spec.input_channels)
-    results = self._forward_unet(x0) if spec.core_name == "U-Net" else self._forward_tiramisu(x0)
+    results = self.forward_core(x0)
+    return self.post_process(results)
+
+  def post_process(self, results):
+    spec = self.spec
     outs = []
     o = spec.output_channels
     for k, (r, (a, bvar)) in enumerate(zip(results, spec.post)):

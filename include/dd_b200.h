@@ -187,6 +187,19 @@ int dd_compose_scales_fwd(dd_ctx* ctx, const dd_tensor* small, const dd_tensor* 
 int dd_invert_standardization(dd_ctx* ctx, const dd_tensor* x, const dd_invert_params* inv, const dd_tensor* y,
                               void* stream);
 
+/* ---- fused output head ------------------------------------------------------------------------ */
+/* AdjustNumberOfChannels (Architecture.py:230-244: conv1x1 C->O + ReLU, conv1x1 O->O, O = features*K*K) + the per-feature
+ * split (Architecture.py:581-587) + KernelPrediction.kernel_prediction (KernelPrediction.py:11-63) of ONE scale in a single
+ * kernel: the logits never reach HBM.  x: fp16 core output [B,h,w,C]; src / out: fp32 [B*features,h,w,3] banks laid out as
+ * dd_kernel_predict_fwd expects.  Supported: K in {3,5}, features in {1,3} (dd_post_kp_supported); anything else runs the
+ * unfused dd_conv2d_fwd x2 + dd_kernel_predict_fwd path.  blob_dev: dd_post_kp_pack_weights() copied to the device. */
+int dd_post_kp_supported(int ksize, int features);
+size_t dd_post_kp_weights_bytes(int cin, int ksize, int features);
+int dd_post_kp_pack_weights(const float* w1, const float* b1, const float* w2, const float* b2, int cin, int ksize, int features,
+                            void* blob_host);
+int dd_post_kp_fwd(dd_ctx* ctx, const dd_tensor* x, const void* blob_dev, const dd_tensor* src, int ksize, int features,
+                   int images_per_tuple, const dd_tensor* out, void* stream);
+
 /* ---- training: loss, backward of every forward op, optimizer --------------------------------- */
 /* Exact (fp32 accumulate, CUDA-core) training path; replaces what tf.train.AdamOptimizer.minimize derives by
  * autodiff (Training.py:700-702).  Gradient tensors are fp32. */

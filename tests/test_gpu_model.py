@@ -119,3 +119,25 @@ def test_larger_image_and_batch_float16():
   mx, mean = errors(out, oracle)
   print("unet32 36x264 fp16 max %.2e mean %.2e" % (mx, mean))
   assert mx <= 5e-2 and mean <= 5e-3
+
+
+@pytest.mark.parametrize("name", ["example", "combined_onehot"])
+def test_fused_output_head_matches_layer_by_layer_path(name):
+  """The fused 1x1 + 1x1 + kernel-prediction kernel against the unfused launches on the same fp16 network: the only
+  difference is fp32 vs fp32 logits accumulated in another order (<= 2e-3 of the output scale)."""
+  j, host_arch, weights, features = cases.build(name)
+  jj = dict(j)
+  jj["b200"] = {"dtype": "float16"}
+  feats = {k: torch.from_numpy(v) for k, v in features.items()}
+  fused = Architecture(jj, weights=weights)
+  fused._ensure_device()
+  assert fused.network.can_fuse_post_kp(fused.kernel_size, fused.features_per_tuple)
+  a = fused.predict(feats)
+  plain = Architecture(jj, weights=weights)
+  plain._ensure_device()
+  plain.network.fused_post_kp = False
+  b = plain.predict(feats)
+  for s in range(len(a)):
+    for k in a[s]:
+      x, y = a[s][k].float().cpu().numpy(), b[s][k].float().cpu().numpy()
+      assert np.abs(x - y).max() <= 2e-3 * max(1.0, np.abs(y).max()), (s, k)

@@ -349,3 +349,38 @@ def test_device_tiling_matches_host_slicing(ctx):
   assert torch.equal(dev_image.cpu(), host_image)
   # every pixel is covered exactly by the kept crops: stitching the cut tiles gives the image back
   assert torch.equal(prediction.stitch_tiles(dev_tiles, tiles, h, w, ctx).cpu(), image)
+
+
+# ------------------------------------------------------------------------------------------------ fused output head
+@pytest.mark.parametrize("k,features,ipt,cin,cstride,coff,h,w", [
+    (5, 1, 1, 64, 64, 0, 21, 37), (5, 3, 2, 64, 64, 0, 9, 50), (3, 1, 2, 16, 16, 0, 16, 24), (3, 3, 1, 24, 40, 8, 10, 33),
+    (5, 1, 1, 96, 96, 0, 8, 16), (5, 1, 3, 128, 128, 0, 17, 19)])
+def test_post_kp_fused(ctx, k, features, ipt, cin, cstride, coff, h, w):
+  """dd_post_kp_fwd == conv1x1+ReLU -> conv1x1 -> softmax kernel prediction of the oracle on the same fp16-rounded
+  operands (x, weights; the hidden layer is rounded to fp16 like the unfused path stores it): 2e-3 of the output scale."""
+  tuples = 2
+  b = tuples * ipt
+  o = features * k * k
+  x = np.zeros((b, h, w, cstride), dtype=np.float32)
+  x[..., coff:coff + cin] = np.abs(RNG.standard_normal((b, h, w, cin)))          # core outputs are ReLU'd
+  x = x.astype(np.float16)
+  w1 = (RNG.standard_normal((1, 1, cin, o)) / np.sqrt(cin)).astype(np.float32)
+  b1 = (RNG.standard_normal(o) * 0.1).astype(np.float32)
+  w2 = (RNG.standard_normal((1, 1, o, o)) * 1.5 / np.sqrt(o)).astype(np.float32)
+  b2 = (RNG.standard_normal(o) * 0.1).astype(np.float32)
+  src = (RNG.standard_normal((features * b, h, w, 3)) * 2).astype(np.float32)
+  blob = torch.from_numpy(_lib.pack_post_kp_weights(w1, b1, w2, b2, k, features)).cuda()
+  out = torch.full((features * b, h, w, 3), 7.0, device="cuda")
+  ctx.post_kp(_lib.desc(torch.from_numpy(x).cuda(), cin, coff), blob, _lib.desc(dev(src)), k, features, ipt, _lib.desc(out))
+  xr = x[..., coff:coff + cin].astype(np.float64)
+  w1r, w2r = w1.astype(np.float16).astype(np.float64), w2.astype(np.float16).astype(np.float64)
+  hidden = np.maximum(np_ops.conv2d_same(xr, w1r, b1), 0).astype(np.float16).astype(np.float64)
+  logits = np_ops.conv2d_same(hidden, w2r, b2)
+  want = np.zeros((features * b, h, w, 3))
+  k2 = k * k
+  for bi in range(b):
+    t, n = divmod(bi, ipt)
+    for f in range(features):
+      oi = (t * features + f) * ipt + n
+      want[oi] = np_ops.kernel_prediction(src[oi:oi + 1].astype(np.float64), logits[bi:bi + 1, ..., f * k2:(f + 1) * k2], k)[0]
+  close(out, want, 2e-3, "fused post + kernel prediction")
