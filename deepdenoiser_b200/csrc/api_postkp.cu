@@ -13,6 +13,7 @@
 //               reduced with two shuffles; sources come from a symmetric-padded halo tile in shared memory
 //   grid        persistent: CTAs stride over the (image, tile) list, the weights are loaded once per CTA
 // This is memory bound (AI ~ 30 FLOP/B): mma.sync keeps the arithmetic far below the HBM time, tcgen05 would add nothing.
+#include <math.h>
 #include <string.h>
 
 #include "dd_internal.h"
@@ -28,7 +29,8 @@ struct PostKpParams {
   const float* b1; const float* b2;              // [O16] fp32 (zero padded)
   View src, out;                                  // fp32 rgb banks
   int B, h, w, ipt;
-  int tiles_x, tiles_y; long long total_tiles;
+  int tiles_x, tiles_y; int total_tiles;
+  int cp_shift;                                   // log2 of the power of two >= Cpad / 8 (activation-tile load mapping)
 };
 
 __device__ __forceinline__ void pk_ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
@@ -51,19 +53,36 @@ __device__ __forceinline__ int pk_sym(int i, int n) {
   return i;
 }
 
+__device__ __forceinline__ void pk_cp_async_16(uint32_t smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void pk_cp_async_4(uint32_t smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void pk_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void pk_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ float pk_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int K, int T>
 __global__ void __launch_bounds__(kPkThreads) post_kp_fused_kernel(const PostKpParams p) {
-  constexpr int K2 = K * K, O = T * K2, O16 = (O + 15) / 16 * 16, NT = O16 / 8, PAD = (K - 1) / 2;
+  // every feature owns KP = K*K rounded up to 16 logit columns (NTF n-tiles); padded columns carry a bias of -inf
+  constexpr int K2 = K * K, KP = (K2 + 15) / 16 * 16, O16 = T * KP, NT = O16 / 8, NTF = KP / 8, PAD = (K - 1) / 2;
   constexpr int TWs = kPkTileW + 2 * PAD, THs = kPkTileH + 2 * PAD;
+  constexpr int SRC_ELEMS = T * THs * TWs;
   extern __shared__ __align__(16) uint8_t pk_smem[];
-  const int xrow = p.Cpad * 2 + 16;                       // bytes per staged pixel
+  const int xrow = p.Cpad * 2 + 16;                       // bytes per staged pixel (odd multiple of 16: conflict-free ldmatrix)
   const int w1row = p.Cpad * 2 + 16, w2row = O16 * 2 + 16;
-  uint8_t* xs = pk_smem;                                  // [128][xrow]
-  uint8_t* w1s = xs + 128 * xrow;                         // [O16][w1row]
+  const int x_bytes = 128 * xrow;
+  uint8_t* xs = pk_smem;                                  // [2][128][xrow]
+  uint8_t* w1s = xs + 2 * x_bytes;                        // [O16][w1row]
   uint8_t* w2s = w1s + O16 * w1row;                       // [O16][w2row]
   float* b1s = reinterpret_cast<float*>(w2s + O16 * w2row);
   float* b2s = b1s + O16;
-  float4* s_src = reinterpret_cast<float4*>(b2s + O16);   // [T][THs][TWs]
+  float4* s_src = reinterpret_cast<float4*>(b2s + O16);   // [2][T][THs][TWs]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -78,40 +97,98 @@ __global__ void __launch_bounds__(kPkThreads) post_kp_fused_kernel(const PostKpP
     const int n = i / (O16 / 8), c = i % (O16 / 8);
     *reinterpret_cast<uint4*>(w2s + n * w2row + c * 16) = *reinterpret_cast<const uint4*>(p.w2t + static_cast<size_t>(n) * O16 + c * 8);
   }
-  for (int i = tid; i < O16; i += kPkThreads) { b1s[i] = p.b1[i]; b2s[i] = p.b2[i]; }
+  for (int i = tid; i < O16; i += kPkThreads) { b1s[i] = p.b1[i]; b2s[i] = p.b2[i] * 1.4426950408889634f; }   // logits in log2 units
 
-  const uint32_t xs_u = smem_u32(xs), w1_u = smem_u32(w1s), w2_u = smem_u32(w2s);
+  const uint32_t xs_u = smem_u32(xs), w1_u = smem_u32(w1s), w2_u = smem_u32(w2s), src_u = smem_u32(s_src);
   // ldmatrix lane addressing.  A (x4): matrices (rows 0-7,k 0-7), (rows 8-15,k 0-7), (rows 0-7,k 8-15), (rows 8-15,k 8-15)
   const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kof = (lane >> 4) * 16;
   // B (x4): matrices (n-tile j,k 0-7), (n-tile j,k 8-15), (n-tile j+1,k 0-7), (n-tile j+1,k 8-15); rows = n
   const int b_row = (lane & 7) + (lane >> 4) * 8, b_kof = ((lane >> 3) & 1) * 16;
   const int valid_chunks = p.C / 8;
+  // slot i = 2j + e of a feature (column 8j + 2*t4 + e of its KP) holds tap k = 4i + t4 (the host packs W2 / b2 that way):
+  // the four threads of a quad read CONSECUTIVE taps of the source tile; offsets are fixed for the whole kernel
+  int tap_off[NTF * 2];
+#pragma unroll
+  for (int i = 0; i < NTF * 2; ++i) {
+    const int k = 4 * i + t4;
+    tap_off[i] = (k < K2) ? (k / K) * TWs + (k % K) : 0;
+  }
+  // activation-tile load mapping: chunk = tid % CP, pixel = tid / CP (+ 256/CP per step), CP = power of two >= cchunks
+  const int cp_shift = p.cp_shift, cp_mask = (1 << cp_shift) - 1, px_step = kPkThreads >> cp_shift;
+  const int ld_c = tid & cp_mask, ld_px0 = tid >> cp_shift;
 
-  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    const int tx = static_cast<int>(tile % p.tiles_x);
-    const int ty = static_cast<int>((tile / p.tiles_x) % p.tiles_y);
-    const int b = static_cast<int>(tile / (static_cast<long long>(p.tiles_x) * p.tiles_y));
-    const int y0 = ty * kPkTileH, x0 = tx * kPkTileW;
-    __syncthreads();                                       // previous tile fully consumed (and weights visible)
-    // activation tile: 128 pixels x Cpad channels, zero outside the image / beyond C
-    for (int i = tid; i < 128 * cchunks; i += kPkThreads) {
-      const int px = i / cchunks, c = i % cchunks;
-      const int y = y0 + (px >> 4), x = x0 + (px & 15);
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (y < p.h && x < p.w && c < valid_chunks)
-        v = __ldg(reinterpret_cast<const uint4*>(p.x + ((static_cast<size_t>(b) * p.h + y) * p.w + x) * p.xcs + p.xoff + c * 8));
-      *reinterpret_cast<uint4*>(xs + px * xrow + c * 16) = v;
+  // Tile coordinates advance by gridDim.x tiles per step WITHOUT divisions: (db, dty, dtx) is gridDim.x decomposed once.
+  struct Coord { int b, ty, tx; };
+  const int tiles_per_image = p.tiles_x * p.tiles_y;
+  Coord delta;
+  delta.b = static_cast<int>(gridDim.x) / tiles_per_image;
+  { const int rem = static_cast<int>(gridDim.x) - delta.b * tiles_per_image; delta.ty = rem / p.tiles_x; delta.tx = rem - delta.ty * p.tiles_x; }
+  auto advance = [&](Coord& c) {
+    c.tx += delta.tx; if (c.tx >= p.tiles_x) { c.tx -= p.tiles_x; ++c.ty; }
+    c.ty += delta.ty; if (c.ty >= p.tiles_y) { c.ty -= p.tiles_y; ++c.b; }
+    c.b += delta.b;
+  };
+  auto first_image = [&](int b) {                      // bank image of feature 0 of logits image b; feature f: + f * ipt
+    if (p.ipt == 1) return b * T;
+    const int tup = b / p.ipt;
+    return tup * T * p.ipt + (b - tup * p.ipt);
+  };
+  // source halo tile: element i = tid + it * 256 -> (feature, ly, lx), fixed for the whole kernel
+  constexpr int SRC_ITERS = (SRC_ELEMS + kPkThreads - 1) / kPkThreads;
+  int src_f[SRC_ITERS], src_ly[SRC_ITERS], src_lx[SRC_ITERS];
+#pragma unroll
+  for (int it = 0; it < SRC_ITERS; ++it) {
+    const int i = tid + it * kPkThreads;
+    const int f = i / (THs * TWs), r = i - f * (THs * TWs);
+    src_f[it] = (i < SRC_ELEMS) ? f : -1; src_ly[it] = r / TWs - PAD; src_lx[it] = r % TWs - PAD;
+  }
+
+  auto issue_loads = [&](const Coord& c, int buf) {
+    const int y0 = c.ty * kPkTileH, x0 = c.tx * kPkTileW;
+    if (ld_c < cchunks) {
+      uint32_t dst = xs_u + static_cast<uint32_t>(buf * x_bytes + ld_c * 16 + ld_px0 * xrow);
+      const uint32_t dst_step = static_cast<uint32_t>(px_step * xrow);
+      const __half* tile_base = p.x + ((static_cast<size_t>(c.b) * p.h + y0) * p.w + x0) * p.xcs + p.xoff + ld_c * 8;
+      const bool chunk_ok = ld_c < valid_chunks;
+      const int w_xcs = p.w * p.xcs;
+      for (int px = ld_px0; px < 128; px += px_step) {
+        const int r = px >> 4, xx = px & 15;
+        if (chunk_ok && y0 + r < p.h && x0 + xx < p.w) {
+          pk_cp_async_16(dst, tile_base + r * w_xcs + xx * p.xcs);
+        } else {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");
+        }
+        dst += dst_step;
+      }
     }
     // source halo tiles (symmetric padding, KernelPrediction.py:30 via Conv2dUtilities.pad_equally)
-    for (int i = tid; i < T * THs * TWs; i += kPkThreads) {
-      const int f = i / (THs * TWs), r = i % (THs * TWs);
-      const int ly = r / TWs, lx = r % TWs;
-      const int img = ((b / p.ipt) * T + f) * p.ipt + (b % p.ipt);
-      const size_t sp = p.src.pix(img, pk_sym(y0 + ly - PAD, p.h), pk_sym(x0 + lx - PAD, p.w));
-      const float* s = reinterpret_cast<const float*>(p.src.ptr) + sp * p.src.cstride + p.src.coff;
-      s_src[i] = make_float4(s[0], s[1], s[2], 0.f);
+    const int img0 = first_image(c.b);
+#pragma unroll
+    for (int it = 0; it < SRC_ITERS; ++it) {
+      if (src_f[it] >= 0) {
+        const size_t sp = p.src.pix(img0 + src_f[it] * p.ipt, pk_sym(y0 + src_ly[it], p.h), pk_sym(x0 + src_lx[it], p.w));
+        const float* s = reinterpret_cast<const float*>(p.src.ptr) + sp * p.src.cstride + p.src.coff;
+        const uint32_t dst = src_u + static_cast<uint32_t>((buf * SRC_ELEMS + tid + it * kPkThreads) * 16);
+        pk_cp_async_4(dst, s); pk_cp_async_4(dst + 4, s + 1); pk_cp_async_4(dst + 8, s + 2);
+      }
     }
-    __syncthreads();
+    pk_cp_async_commit();
+  };
+
+  int tile = blockIdx.x;
+  int buf = 0;
+  Coord cur;
+  cur.b = tile / tiles_per_image;
+  { const int rem = tile - cur.b * tiles_per_image; cur.ty = rem / p.tiles_x; cur.tx = rem - cur.ty * p.tiles_x; }
+  if (tile < p.total_tiles) issue_loads(cur, 0);
+  for (; tile < p.total_tiles; tile += gridDim.x, buf ^= 1) {
+    const int b = cur.b;
+    const int y0 = cur.ty * kPkTileH, x0 = cur.tx * kPkTileW;
+    const int img0 = first_image(b);
+    advance(cur);                                          // cur = the NEXT tile of this CTA from here on
+    pk_cp_async_wait_all();
+    __syncthreads();                                       // this tile's data (and the weights) visible; the other buffer is free
+    if (tile + static_cast<int>(gridDim.x) < p.total_tiles) issue_loads(cur, buf ^ 1);   // in flight during the math below
 
     // ---------------------------------------------------------------- GEMM 1: hidden = relu(x W1 + b1)
     float acc[NT][4];
@@ -120,7 +197,7 @@ __global__ void __launch_bounds__(kPkThreads) post_kp_fused_kernel(const PostKpP
       const float bl = b1s[j * 8 + 2 * t4], bh = b1s[j * 8 + 2 * t4 + 1];
       acc[j][0] = bl; acc[j][1] = bh; acc[j][2] = bl; acc[j][3] = bh;
     }
-    const uint32_t a_base = xs_u + static_cast<uint32_t>((warp * 16 + a_row) * xrow + a_kof);
+    const uint32_t a_base = xs_u + static_cast<uint32_t>(buf * x_bytes + (warp * 16 + a_row) * xrow + a_kof);
     for (int ks = 0; ks < p.Cpad / 16; ++ks) {
       uint32_t a[4];
       pk_ldmatrix_x4(a, a_base + ks * 32);
@@ -132,12 +209,12 @@ __global__ void __launch_bounds__(kPkThreads) post_kp_fused_kernel(const PostKpP
         pk_mma(acc[j + 1], a, bf[2], bf[3]);
       }
     }
-    // ---------------------------------------------------------------- GEMM 2: logits = hidden W2 + b2
+    // ---------------------------------------------------------------- GEMM 2: logits = hidden W2 + b2 (then * log2 e)
     float lg[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      const float bl = b2s[j * 8 + 2 * t4], bh = b2s[j * 8 + 2 * t4 + 1];
-      lg[j][0] = bl; lg[j][1] = bh; lg[j][2] = bl; lg[j][3] = bh;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) lg[j][e] = 0.f;
     }
 #pragma unroll
     for (int kk = 0; kk < NT / 2; ++kk) {
@@ -154,9 +231,16 @@ __global__ void __launch_bounds__(kPkThreads) post_kp_fused_kernel(const PostKpP
         pk_mma(lg[j + 1], a, bf[2], bf[3]);
       }
     }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const float bl = b2s[j * 8 + 2 * t4], bh = b2s[j * 8 + 2 * t4 + 1];      // already scaled by log2 e
+      lg[j][0] = fmaf(lg[j][0], 1.4426950408889634f, bl); lg[j][1] = fmaf(lg[j][1], 1.4426950408889634f, bh);
+      lg[j][2] = fmaf(lg[j][2], 1.4426950408889634f, bl); lg[j][3] = fmaf(lg[j][3], 1.4426950408889634f, bh);
+    }
     // ---------------------------------------------------------------- softmax over K*K + filter apply, per feature
-    // this thread: pixels (row `warp`, column g) [regs 0,1] and (row `warp`, column g + 8) [regs 2,3]; logit columns
-    // j*8 + 2*t4 + {0,1} of every n-tile j
+    // this thread: pixels (row `warp`, column g) [regs 0,1] and (row `warp`, column g + 8) [regs 2,3]; branch free: the
+    // padded slots hold -inf (their bias), so they contribute exp2(-inf) = 0
+    const float4* src_cur = s_src + buf * SRC_ELEMS;
 #pragma unroll
     for (int f = 0; f < T; ++f) {
 #pragma unroll
@@ -164,30 +248,17 @@ __global__ void __launch_bounds__(kPkThreads) post_kp_fused_kernel(const PostKpP
         const int lx = g + half * 8;
         float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = j * 8 + 2 * t4 + e;
-            if (col >= f * K2 && col < (f + 1) * K2) mx = fmaxf(mx, lg[j][half * 2 + e]);
-          }
-        }
+        for (int i = 0; i < NTF * 2; ++i) mx = fmaxf(mx, lg[f * NTF + (i >> 1)][half * 2 + (i & 1)]);
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
         float sum = 0.f, r = 0.f, gg = 0.f, bb = 0.f;
-        const float4* tile_f = s_src + f * (THs * TWs) + warp * TWs + lx;
+        const float4* tile_f = src_cur + f * (THs * TWs) + warp * TWs + lx;
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = j * 8 + 2 * t4 + e;
-            if (col >= f * K2 && col < (f + 1) * K2) {
-              const int k = col - f * K2;
-              const float ev = __expf(lg[j][half * 2 + e] - mx);
-              const float4 sv = tile_f[(k / K) * TWs + (k % K)];
-              sum += ev;
-              r = fmaf(ev, sv.x, r); gg = fmaf(ev, sv.y, gg); bb = fmaf(ev, sv.z, bb);
-            }
-          }
+        for (int i = 0; i < NTF * 2; ++i) {
+          const float ev = pk_ex2(lg[f * NTF + (i >> 1)][half * 2 + (i & 1)] - mx);
+          const float4 sv = tile_f[tap_off[i]];
+          sum += ev;
+          r = fmaf(ev, sv.x, r); gg = fmaf(ev, sv.y, gg); bb = fmaf(ev, sv.z, bb);
         }
 #pragma unroll
         for (int o = 1; o <= 2; o <<= 1) {
@@ -198,25 +269,25 @@ __global__ void __launch_bounds__(kPkThreads) post_kp_fused_kernel(const PostKpP
         }
         const int y = y0 + warp, x = x0 + lx;
         if (t4 == half && y < p.h && x < p.w) {
-          const int img = ((b / p.ipt) * T + f) * p.ipt + (b % p.ipt);
           const float inv = 1.f / sum;
-          float* o = reinterpret_cast<float*>(p.out.ptr) + p.out.pix(img, y, x) * p.out.cstride + p.out.coff;
+          float* o = reinterpret_cast<float*>(p.out.ptr) + p.out.pix(img0 + f * p.ipt, y, x) * p.out.cstride + p.out.coff;
           o[0] = r * inv; o[1] = gg * inv; o[2] = bb * inv;
         }
       }
     }
   }
+  pk_cp_async_wait_all();
 }
 
 template <int K, int T>
 static int launch_post_kp(dd_ctx* ctx, const PostKpParams& p, cudaStream_t s) {
-  constexpr int K2 = K * K, O16 = (T * K2 + 15) / 16 * 16, PAD = (K - 1) / 2;
-  const size_t smem = 128ull * (p.Cpad * 2 + 16) + static_cast<size_t>(O16) * (p.Cpad * 2 + 16) +
+  constexpr int K2 = K * K, O16 = T * ((K2 + 15) / 16 * 16), PAD = (K - 1) / 2;
+  const size_t smem = 2 * 128ull * (p.Cpad * 2 + 16) + static_cast<size_t>(O16) * (p.Cpad * 2 + 16) +
                       static_cast<size_t>(O16) * (O16 * 2 + 16) + 2ull * O16 * sizeof(float) +
-                      static_cast<size_t>(T) * (kPkTileH + 2 * PAD) * (kPkTileW + 2 * PAD) * sizeof(float4);
+                      2 * static_cast<size_t>(T) * (kPkTileH + 2 * PAD) * (kPkTileW + 2 * PAD) * sizeof(float4);
   DD_CHECK_ARG(smem <= ctx->max_smem_optin, "post_kp: tile does not fit shared memory");
   DD_CUDA(cudaFuncSetAttribute(post_kp_fused_kernel<K, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  long long grid = static_cast<long long>(ctx->sm_count) * 4;
+  int grid = ctx->sm_count * 4;
   if (grid > p.total_tiles) grid = p.total_tiles;
   post_kp_fused_kernel<K, T><<<static_cast<unsigned>(grid), kPkThreads, smem, s>>>(p);
   DD_LAUNCH_CHECK(ctx);
@@ -233,8 +304,10 @@ int dd_post_kp_supported(int ksize, int features) {
   return (ksize == 3 || ksize == 5) && (features == 1 || features == 3);
 }
 
+static int post_kp_o16(int ksize, int features) { return features * round_up(ksize * ksize, 16); }
+
 size_t dd_post_kp_weights_bytes(int cin, int ksize, int features) {
-  const int o16 = round_up(features * ksize * ksize, 16), cpad = round_up(cin, 16);
+  const int o16 = post_kp_o16(ksize, features), cpad = round_up(cin, 16);
   return static_cast<size_t>(o16) * cpad * 2 + static_cast<size_t>(o16) * o16 * 2 + 2ull * o16 * 4;
 }
 
@@ -246,17 +319,25 @@ int dd_post_kp_pack_weights(const float* w1, const float* b1, const float* w2, c
     set_error("post_kp_pack_weights: bad argument");
     return DD_ERR_INVALID;
   }
-  const int o = features * ksize * ksize, o16 = round_up(o, 16), cpad = round_up(cin, 16);
+  const int k2 = ksize * ksize, kp = round_up(k2, 16), o = features * k2, o16 = features * kp, cpad = round_up(cin, 16);
   memset(blob_host, 0, dd_post_kp_weights_bytes(cin, ksize, features));
   __half* w1t = reinterpret_cast<__half*>(blob_host);
   __half* w2t = w1t + static_cast<size_t>(o16) * cpad;
   float* b1p = reinterpret_cast<float*>(w2t + static_cast<size_t>(o16) * o16);
   float* b2p = b1p + o16;
+  // hidden unit c -> row (c / K2) * KP + c % K2;  logit c = (feature f, tap k) -> column f * KP + 8j + 2*t4 + e with
+  // k = 4 * (2j + e) + t4 (the kernel's quad layout); padded logit columns get a bias of -inf (softmax weight 0)
+  auto hid = [&](int c) { return (c / k2) * kp + c % k2; };
+  auto col = [&](int c) {
+    const int f = c / k2, k = c % k2, slot = k / 4, t4 = k % 4;
+    return f * kp + 8 * (slot / 2) + 2 * t4 + (slot % 2);
+  };
   for (int c = 0; c < cin; ++c)
-    for (int n = 0; n < o; ++n) w1t[static_cast<size_t>(n) * cpad + c] = __float2half_rn(w1[static_cast<size_t>(c) * o + n]);
+    for (int n = 0; n < o; ++n) w1t[static_cast<size_t>(hid(n)) * cpad + c] = __float2half_rn(w1[static_cast<size_t>(c) * o + n]);
   for (int k = 0; k < o; ++k)
-    for (int n = 0; n < o; ++n) w2t[static_cast<size_t>(n) * o16 + k] = __float2half_rn(w2[static_cast<size_t>(k) * o + n]);
-  for (int n = 0; n < o; ++n) { b1p[n] = b1[n]; b2p[n] = b2[n]; }
+    for (int n = 0; n < o; ++n) w2t[static_cast<size_t>(col(n)) * o16 + hid(k)] = __float2half_rn(w2[static_cast<size_t>(k) * o + n]);
+  for (int n = 0; n < o16; ++n) b2p[n] = -INFINITY;
+  for (int n = 0; n < o; ++n) { b1p[hid(n)] = b1[n]; b2p[col(n)] = b2[n]; }
   return DD_OK;
 }
 
@@ -272,7 +353,7 @@ int dd_post_kp_fwd(dd_ctx* ctx, const dd_tensor* x, const void* blob_dev, const 
   PostKpParams p;
   memset(&p, 0, sizeof(p));
   p.x = reinterpret_cast<const __half*>(x->ptr); p.xcs = x->cstride; p.xoff = x->coff; p.C = x->c; p.Cpad = round_up(x->c, 16);
-  const int o16 = round_up(features * ksize * ksize, 16);
+  const int o16 = post_kp_o16(ksize, features);
   p.w1t = reinterpret_cast<const __half*>(blob_dev);
   p.w2t = p.w1t + static_cast<size_t>(o16) * p.Cpad;
   p.b1 = reinterpret_cast<const float*>(p.w2t + static_cast<size_t>(o16) * o16);
@@ -280,7 +361,10 @@ int dd_post_kp_fwd(dd_ctx* ctx, const dd_tensor* x, const void* blob_dev, const 
   p.src = make_view(src); p.out = make_view(out);
   p.B = x->n; p.h = x->h; p.w = x->w; p.ipt = images_per_tuple;
   p.tiles_x = (x->w + kPkTileW - 1) / kPkTileW; p.tiles_y = (x->h + kPkTileH - 1) / kPkTileH;
-  p.total_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * x->n;
+  DD_CHECK_ARG(static_cast<long long>(p.tiles_x) * p.tiles_y * x->n < (1ll << 30), "post_kp: too many tiles");
+  p.total_tiles = p.tiles_x * p.tiles_y * x->n;
+  while ((1 << p.cp_shift) < p.Cpad / 8) ++p.cp_shift;
+  DD_CHECK_ARG(p.cp_shift <= 7, "post_kp: at most 1024 input channels");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (ksize == 5 && features == 1) return launch_post_kp<5, 1>(ctx, p, s);
   if (ksize == 5 && features == 3) return launch_post_kp<5, 3>(ctx, p, s);
