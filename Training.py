@@ -45,8 +45,7 @@ parser.add_argument("--checkpoint_steps", type=int, default=500)
 parser.add_argument("--write_synthetic_tfrecords", type=int, default=0,
                     help="Write this many synthetic tiles as <base_tfrecords_directory>/training (reference format) and use them.")
 parser.add_argument("--precision", default=None, choices=["float32", "float16"],
-                    help="float16: tensor-core path (U-Net; fp16 activations, fp32 master weights); float32: exact path. "
-                         "Default: float16 for U-Net, float32 for Tiramisu.")
+                    help="float16 (default): tensor-core path (fp16 activations, fp32 master weights); float32: exact path.")
 
 
 def synthetic_batch(architecture, tiles, size, seed):
@@ -108,7 +107,7 @@ def main(parsed_arguments):
   architecture = Architecture(architecture_json, source_data_format="channels_last",
                               data_format=parsed_arguments.data_format, device=local)
   settings = TrainingSettings(training_json)
-  precision = parsed_arguments.precision or ("float16" if architecture.spec.core_name == "U-Net" else "float32")
+  precision = parsed_arguments.precision or "float16"
   trainer = Trainer(architecture, settings, precision=precision)
   model_dir = os.path.join(base, architecture.model_directory)
   os.makedirs(model_dir, exist_ok=True)

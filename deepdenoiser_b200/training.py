@@ -84,8 +84,6 @@ class Trainer:
       n += (size + 3) // 4 * 4                    # keep every variable 16-byte aligned
     self.count = n
     if self.mixed:
-      if self.spec.core_name != "U-Net":
-        raise NotImplementedError("tensor-core training covers the U-Net backbone; Tiramisu trains on the exact path")
       if any(f % 8 for f in self.spec.filters):
         raise _lib.DDError("float16 training needs filter counts that are multiples of 8")
     # + slack: the tensor-core conv reads biases in groups of 16 floats
@@ -179,6 +177,9 @@ class Trainer:
       self.bias[var.name] = self.param(var.bias_name)
       if var in self.spec.compose and var.ksize == 1:
         continue
+      if var.transposed and var.ksize == 3:
+        self._repack_transpose3x3(var, w)
+        continue
       store = self._packed_store.get(var.name)
       if store is None:
         if var.transposed:
@@ -204,6 +205,40 @@ class Trainer:
                          (head.kernel_name, head.bias_name, tail.kernel_name, tail.bias_name)}
     if self.arch.feature_flag_mode == FeatureFlagMode.EMBEDDING:
       self.arch._flags.embedding_matrix = self.param("embedding/feature_flags_embedding_matrix")
+
+  def _repack_transpose3x3(self, var, w):
+    """3x3 stride-2 'SAME' transposed conv (Tiramisu.py:62-64), tensor-core mode.  w: TF [3,3,cout,cin] master weights.
+    forward  = 4 output phases, each a 3x3 'same' conv holding a tap subset (network.py::_pack_transpose3x3);
+    backward = ONE 3x3 'same' conv on the space-to-depth view Z[i,j,sp*cout+o] = dz[2i+ay,2j+ax,o] (sp = 2ay+ax):
+               dx[i,j,c] = sum_{r,s,o} dz[2i+r,2j+s,o] W[r,s,o,c] = sum Z[i+r//2, j+s//2, (r%2,s%2), o] W[r,s,o,c], i.e. conv
+               taps (1+r//2, 1+s//2) with input-channel block sp = 2(r%2)+(s%2); the other taps / blocks are zero."""
+    ctx, lib = self.ctx, self.ctx.lib
+    cin, cout = var.cin, var.cout
+    k = w.view(3, 3, cout, cin)
+    store = self._packed_store.get(var.name)
+    if store is None:
+      nf = lib.dd_conv2d_packed_bytes(3, cin, cout, _lib.DD_F16, 0)
+      nb = lib.dd_conv2d_packed_bytes(3, 4 * cout, cin, _lib.DD_F16, 0)
+      store = ([torch.zeros(nf, dtype=torch.uint8, device=self.dev) for _ in range(4)],
+               torch.zeros(nb, dtype=torch.uint8, device=self.dev))
+      self._packed_store[var.name] = store
+    phases, bwd = store
+    for py in range(2):
+      for px in range(2):
+        ph = torch.zeros(3, 3, cin, cout, dtype=torch.float32, device=self.dev)
+        for dy in (0, -1):
+          for dx in (0, -1):
+            r, c = py - 2 * dy, px - 2 * dx
+            if r <= 2 and c <= 2:
+              ph[dy + 1, dx + 1] = k[r, c].t()
+        ctx.call("dd_conv2d_pack_weights_dev", _fp(ph), 3, cin, cout, 0, _fp(phases[py * 2 + px]))
+    wc = torch.zeros(3, 3, 4 * cout, cin, dtype=torch.float32, device=self.dev)
+    for r in range(3):
+      for c in range(3):
+        sp = 2 * (r % 2) + (c % 2)
+        wc[1 + r // 2, 1 + c // 2, sp * cout:(sp + 1) * cout] = k[r, c]
+    ctx.call("dd_conv2d_pack_weights_dev", _fp(wc), 3, 4 * cout, cin, 0, _fp(bwd))
+    self.fwd[var.name], self.bwd[var.name] = phases, bwd
 
   # ------------------------------------------------------------------------------------------ helpers
   def _buf(self, key, shape, zero=False, dtype=torch.float32):
@@ -407,8 +442,8 @@ class Trainer:
     totals = {steps: spec.skip_channels[steps - 1] + n * f[steps]}
     for level in range(steps):
       totals[level] = spec.skip_channels[level] + f[level] + n * f[level]
-    raws = {l: self._buf("tira.raw%d" % l, (b,) + dims[l] + (totals[l],)) for l in totals}
-    acts = {l: self._buf("tira.act%d" % l, (b,) + dims[l] + (totals[l],)) for l in totals}
+    raws = {l: self._buf("tira.raw%d" % l, (b,) + dims[l] + (totals[l],), dtype=self.act_dtype) for l in totals}
+    acts = {l: self._buf("tira.act%d" % l, (b,) + dims[l] + (totals[l],), dtype=self.act_dtype) for l in totals}
     tape = {"x0": x0, "raws": raws, "acts": acts, "dims": dims, "totals": totals, "trans": [], "blocks": []}
 
     def dense(layers, level, c):
@@ -423,8 +458,8 @@ class Trainer:
       c0 = c
       c = dense(spec.down[i], i, c)
       tape["blocks"].append(("down", i, i, spec.down[i], c0))
-      z = self._buf("tira.z%d" % i, (b,) + dims[i] + (c,))
-      za = self._buf("tira.za%d" % i, (b,) + dims[i] + (c,))
+      z = self._buf("tira.z%d" % i, (b,) + dims[i] + (c,), dtype=self.act_dtype)
+      za = self._buf("tira.za%d" % i, (b,) + dims[i] + (c,), dtype=self.act_dtype)
       self._conv(spec.transition[i], V(acts[i], c, 0), V(z), relu=False, y_relu=V(za))
       ctx.maxpool_s2(V(z).d, 2, V(raws[i + 1], c, 0).d)
       ctx.maxpool_s2(V(za).d, 2, V(acts[i + 1], c, 0).d)
@@ -455,7 +490,8 @@ class Trainer:
     spec, f, steps, ctx = self.spec, self.spec.filters, self.spec.steps, self.ctx
     raws, acts, dims, totals = tape["raws"], tape["acts"], tape["dims"], tape["totals"]
     b = tape["x0"].t.shape[0]
-    G = {l: self._buf("tira.g%d" % l, (b,) + dims[l] + (totals[l],), zero=True) for l in totals}
+    adt = self.act_dtype
+    G = {l: self._buf("tira.g%d" % l, (b,) + dims[l] + (totals[l],), zero=True, dtype=adt) for l in totals}
     dres = self._post_backward(tape, dlogits_coarse_first)
     for r in tape["results"]:
       level = [l for l in raws if raws[l] is r.t][0]
@@ -466,7 +502,7 @@ class Trainer:
       for var in reversed(layers):
         c -= var.cout
         dz = V(G[level], var.cout, c)                               # complete: every later reader already added
-        dact = V(self._buf("tira.dact%d" % level, (b,) + dims[level] + (totals[level],)), c, 0)
+        dact = V(self._buf("tira.dact%d" % level, (b,) + dims[level] + (totals[level],), dtype=adt), c, 0)
         self._conv_bwd(var, V(acts[level], c, 0), dz, dact)
         ctx.call("dd_relu_bwd_acc", _b(dact.d), _b(V(raws[level], c, 0).d), _b(V(G[level], c, 0).d))
 
@@ -476,32 +512,53 @@ class Trainer:
     for i in reversed(range(steps)):
       var, index, c, level, cs = tape["ups"][i]
       # y = relu(conv2d_transpose(raw_index[0:c])) written to raw_level[cs:cs+f]
-      dz = V(self._buf("tira.updz%d" % level, (b,) + dims[level] + (var.cout,)))
-      self._relu_bwd(V(G[level], var.cout, cs), V(raws[level], var.cout, cs), dz)
       x = V(raws[index], c, 0)
-      ctx.call("dd_conv2d_wgrad", _b(x.d), _b(dz.d), 3, 1, _fp(self.param_grad(var.kernel_name)),
-               _fp(self.param_grad(var.bias_name)))
-      dx = V(self._buf("tira.updx%d" % index, (b,) + dims[index] + (c,)))
-      ctx.call("dd_conv2d_transpose3x3_dgrad", _b(dz.d), _fp(self.bwd[var.name]), _b(dx.d))
+      dx = V(self._buf("tira.updx%d" % index, (b,) + dims[index] + (c,), dtype=adt))
+      if self.mixed:
+        # ReLU mask + space-to-depth of the fine gradient, then 3x3 'same' convs on the coarse grid (_repack_transpose3x3)
+        s2d = self._act("tira.s2d%d" % index, (b,) + dims[index], 4 * var.cout)
+        ctx.call("dd_space_to_depth2_mask", _b(V(G[level], var.cout, cs).d), _b(V(raws[level], var.cout, cs).d), _b(s2d.d))
+        db4 = self._buf("tira.db4_%d" % index, (4, var.cout), zero=True)
+        ctx.call("dd_relu_bwd_bias", _b(s2d.d), None, None, _fp(db4), ctypes.c_float(1.0))
+        self.param_grad(var.bias_name).add_(db4.sum(dim=0))
+        # dWc[tr,ts,(sp,o),c] = sum Z[i+tr-1, j+ts-1, (sp,o)] x[i,j,c]; W[r,s,o,c] sits at tr = 1+r//2, ts = 1+s//2, sp = 2(r%2)+(s%2)
+        dwc = self._buf("tira.dwc%d" % index, (3, 3, 4 * var.cout, c), zero=True)
+        ctx.call("dd_conv2d_wgrad_tc", _b(s2d.d), _b(x.d), 3, 0, _fp(dwc), ctypes.c_float(1.0))
+        dw = self.param_grad(var.kernel_name)                      # [3,3,cout,cin]
+        for r in range(3):
+          for cc in range(3):
+            sp = 2 * (r % 2) + (cc % 2)
+            dw[r, cc].add_(dwc[1 + r // 2, 1 + cc // 2, sp * var.cout:(sp + 1) * var.cout])
+        ctx.conv2d(s2d.d, self.bwd[var.name], None, 3, dx.d, relu=False)
+      else:
+        dz = V(self._buf("tira.updz%d" % level, (b,) + dims[level] + (var.cout,)))
+        self._relu_bwd(V(G[level], var.cout, cs), V(raws[level], var.cout, cs), dz)
+        ctx.call("dd_conv2d_wgrad", _b(x.d), _b(dz.d), 3, 1, _fp(self.param_grad(var.kernel_name)),
+                 _fp(self.param_grad(var.bias_name)))
+        ctx.call("dd_conv2d_transpose3x3_dgrad", _b(dz.d), _fp(self.bwd[var.name]), _b(dx.d))
       ctx.call("dd_axpy", ctypes.c_float(1.0), _b(dx.d), _b(V(G[index], c, 0).d))
       lvl, layers, c0 = blocks[("up", i)]
       dense_bwd(layers, lvl, c0)
     for i in reversed(range(steps)):
       _, c, z = tape["trans"][i]
       # raw_{i+1}[0:c] = maxpool2(z), z = conv1x1(act_i[0:c])
-      dzp = V(self._buf("tira.dzp%d" % i, (b,) + dims[i] + (c,), zero=True))   # dd_maxpool_s2_bwd accumulates
+      dzp = V(self._buf("tira.dzp%d" % i, (b,) + dims[i] + (c,), zero=True))   # dd_maxpool_s2_bwd accumulates (fp32 atomics)
       ctx.call("dd_maxpool_s2_bwd", _b(V(z).d), _b(V(raws[i + 1], c, 0).d), _b(V(G[i + 1], c, 0).d), 2, _b(dzp.d))
+      if self.mixed:
+        dzp16 = V(self._buf("tira.dzp16_%d" % i, (b,) + dims[i] + (c,), dtype=adt))
+        ctx.cast_copy(dzp.d, dzp16.d)
+        dzp = dzp16
       var = spec.transition[i]
-      dact = V(self._buf("tira.dact%d" % i, (b,) + dims[i] + (totals[i],)), c, 0)
+      dact = V(self._buf("tira.dact%d" % i, (b,) + dims[i] + (totals[i],), dtype=adt), c, 0)
       self._conv_bwd(var, V(acts[i], c, 0), dzp, dact)
       ctx.call("dd_relu_bwd_acc", _b(dact.d), _b(V(raws[i], c, 0).d), _b(V(G[i], c, 0).d))
       lvl, layers, c0 = blocks[("down", i)]
       dense_bwd(layers, lvl, c0)
     # pre-processing conv: raw_0[0:f0] = relu(conv(x0))
-    dz = V(self._buf("tira.predz", (b,) + dims[0] + (f[0],)))
-    self._relu_bwd(V(G[0], f[0], 0), V(raws[0], f[0], 0), dz)
-    dx0 = V(self._buf("tira.dx0", tuple(tape["x0"].t.shape)))
-    self._conv_bwd(spec.pre, tape["x0"], dz, dx0)
+    dz = self._act("tira.predz", (b,) + dims[0], f[0])
+    done = self._relu_bwd(V(G[0], f[0], 0), V(raws[0], f[0], 0), dz, bias_of=spec.pre)
+    dx0 = self._act("tira.dx0", tuple(tape["x0"].t.shape[:3]), tape["x0"].c)
+    self._conv_bwd(spec.pre, tape["x0"], dz, dx0, bias_done=done)
     return dx0
 
   # ------------------------------------------------------------------------------------------ compose net

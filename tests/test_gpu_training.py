@@ -226,3 +226,29 @@ def test_training_cli_reads_tfrecords_and_augments_on_device(tmp_path):
   assert os.path.exists(tmp_path / "model" / "ckpt-6.npz")
   out2 = subprocess.run(cmd[:4] + ["1"] + cmd[5:7], capture_output=True, text=True, timeout=600)
   assert out2.returncode == 0 and "resumed from" in out2.stdout, out2.stderr[-2000:]
+
+
+def test_tensor_core_training_tiramisu_backbone():
+  """Tiramisu on the tensor-core path: dense-block concat gradients in fp16 windows, 1x1 transition + 2x2 max-pool, and the
+  3x3 stride-2 transposed convolution whose backward runs as 3x3 convs / weight gradients on the space-to-depth view."""
+  j = small_example(filters=(8, 16, 16), n_convs=2, k=3)
+  j["architecture"]["core_architecture"]["name"] = "Tiramisu"
+  host, weights, features, targets = make_problem(j, n=2, h=16, w=24)
+  trainer = Trainer(Architecture(j, weights=weights), TrainingSettings({"loss_difference": "SQUARED"}), precision="float16")
+  trainer.forward({k: torch.from_numpy(v) for k, v in features.items()})
+  loss = float(trainer.loss_and_gradient({k: torch.from_numpy(v) for k, v in targets.items()}).item())
+  trainer.backward()
+  want_loss, want_grads, _ = oracle_loss_and_grads(j, weights, features, targets, kind="SQUARED")
+  assert abs(loss - want_loss) <= 1e-2 * max(1.0, abs(want_loss)), (loss, want_loss)
+  got = trainer.gradients()
+  a = np.concatenate([got[k].reshape(-1).astype(np.float64) for k in want_grads])
+  b = np.concatenate([want_grads[k].reshape(-1) for k in want_grads])
+  cosine = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+  worst = check_gradients(trainer, want_grads, rtol=0.2)
+  print("fp16 Tiramisu: loss %.5f (oracle %.5f), worst relative gradient error %.2e, cosine %.5f" % (loss, want_loss, worst, cosine))
+  assert cosine >= 0.995, cosine
+  # the transposed-convolution kernels in particular (the space-to-depth formulation)
+  for name, g in want_grads.items():
+    if "conv2d_transpose" in name and name.endswith("kernel"):
+      x, y = got[name].reshape(-1).astype(np.float64), g.reshape(-1)
+      assert float(x @ y / (np.linalg.norm(x) * np.linalg.norm(y))) >= 0.995, name
