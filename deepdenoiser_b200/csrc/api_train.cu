@@ -61,6 +61,50 @@ __global__ void __launch_bounds__(256) ewise_kernel(const Ewise p, const EwiseIn
   }
 }
 
+// 16-byte vectorised variant for aligned fp16 tensors (8 channels per thread): the activation-gradient traffic of the
+// tensor-core training path (ReLU masks through concatenations, gradient accumulation).
+__global__ void __launch_bounds__(256) ewise_vec_kernel(const Ewise p) {
+  const int G = p.out.c >> 3;
+  const size_t total = static_cast<size_t>(p.out.n) * p.out.h * p.out.w * G;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = static_cast<int>(idx % G);
+  const size_t pix = idx / G;
+  auto at = [&](const View& v) { return reinterpret_cast<__half*>(v.ptr) + pix * v.cstride + v.coff + g * 8; };
+  const uint4 av = *reinterpret_cast<const uint4*>(at(p.a));
+  const __half2* ah = reinterpret_cast<const __half2*>(&av);
+  uint4 ov;
+  __half2* oh = reinterpret_cast<__half2*>(&ov);
+  if (p.op == EW_AXPY) {
+    ov = *reinterpret_cast<const uint4*>(at(p.out));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 a = __half22float2(ah[i]), o = __half22float2(oh[i]);
+      oh[i] = __floats2half2_rn(fmaf(p.alpha, a.x, o.x), fmaf(p.alpha, a.y, o.y));
+    }
+  } else {
+    const uint4 bv = *reinterpret_cast<const uint4*>(at(p.b));
+    const __half2* bh = reinterpret_cast<const __half2*>(&bv);
+    if (p.op == EW_RELU_MASK_ACC) ov = *reinterpret_cast<const uint4*>(at(p.out));
+    else ov = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 a = __half22float2(ah[i]), b = __half22float2(bh[i]), o = __half22float2(oh[i]);
+      oh[i] = __floats2half2_rn(b.x > 0.f ? o.x + a.x : o.x, b.y > 0.f ? o.y + a.y : o.y);
+    }
+  }
+  *reinterpret_cast<uint4*>(at(p.out)) = ov;
+}
+
+inline bool vec_ok(const View& v) { return v.f16 && v.c % 8 == 0 && v.coff % 8 == 0 && v.cstride % 8 == 0; }
+// launches the vectorised kernel when every operand allows it; returns false otherwise
+inline bool try_ewise_vec(const Ewise& p, bool uses_b, cudaStream_t s) {
+  if (!(vec_ok(p.a) && vec_ok(p.out) && (!uses_b || vec_ok(p.b)))) return false;
+  const size_t total = static_cast<size_t>(p.out.n) * p.out.h * p.out.w * (p.out.c / 8);
+  ewise_vec_kernel<<<nblocks(total, 256), 256, 0, s>>>(p);
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------ loss
 struct LossParams {
   View pred, target, dpred;
@@ -472,7 +516,8 @@ int dd_relu_bwd(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const dd_t
   Ewise p; memset(&p, 0, sizeof(p)); EwiseInv q; memset(&q, 0, sizeof(q));
   p.a = make_view(dy); p.b = make_view(y); p.out = make_view(dz); p.op = EW_RELU_MASK;
   const size_t total = static_cast<size_t>(dy->n) * dy->h * dy->w * dy->c;
-  ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
+  if (!try_ewise_vec(p, true, static_cast<cudaStream_t>(stream)))
+    ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }
@@ -482,7 +527,8 @@ int dd_relu_bwd_acc(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const 
   Ewise p; memset(&p, 0, sizeof(p)); EwiseInv q; memset(&q, 0, sizeof(q));
   p.a = make_view(dy); p.b = make_view(y); p.out = make_view(dz_acc); p.op = EW_RELU_MASK_ACC;
   const size_t total = static_cast<size_t>(dy->n) * dy->h * dy->w * dy->c;
-  ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
+  if (!try_ewise_vec(p, true, static_cast<cudaStream_t>(stream)))
+    ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }
@@ -517,7 +563,8 @@ int dd_axpy(dd_ctx* ctx, float alpha, const dd_tensor* x, const dd_tensor* y, vo
   Ewise p; memset(&p, 0, sizeof(p)); EwiseInv q; memset(&q, 0, sizeof(q));
   p.a = make_view(x); p.out = make_view(y); p.op = EW_AXPY; p.alpha = alpha;
   const size_t total = static_cast<size_t>(x->n) * x->h * x->w * x->c;
-  ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
+  if (!try_ewise_vec(p, false, static_cast<cudaStream_t>(stream)))
+    ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }

@@ -149,3 +149,26 @@ def test_relu_bwd_bias(ctx, c, cstride, dtype):
   db2 = torch.zeros(c, device="cuda")
   ctx.call("dd_relu_bwd_bias", _b(_lib.desc(dy, c, coff)), None, None, _fp(db2), ctypes.c_float(1.0))
   assert rel_err(db2, dy[..., coff:coff + c].float().sum(dim=(0, 1, 2))) <= 1e-3
+
+
+def test_vectorised_elementwise_fp16_windows(ctx):
+  """dd_relu_bwd / dd_relu_bwd_acc / dd_axpy on aligned fp16 channel windows (16-byte vectorised path): bit exact against
+  torch in fp32 with one fp16 rounding, and channels outside the window stay untouched."""
+  n, h, w, cs, c, coff = 2, 9, 21, 48, 24, 16
+  dy = torch.randn(n, h, w, cs, device="cuda").half()
+  y = torch.randn(n, h, w, cs, device="cuda").half()
+  dz = torch.full((n, h, w, cs), 3.0, device="cuda", dtype=torch.float16)
+  win = slice(coff, coff + c)
+  ctx.call("dd_relu_bwd", _b(_lib.desc(dy, c, coff)), _b(_lib.desc(y, c, coff)), _b(_lib.desc(dz, c, coff)))
+  assert torch.equal(dz[..., win], (dy * (y > 0))[..., win])
+  assert bool((dz[..., :coff] == 3.0).all()) and bool((dz[..., coff + c:] == 3.0).all())
+  acc = torch.randn(n, h, w, cs, device="cuda").half()
+  want = acc.clone()
+  want[..., win] = (acc.float() + (dy * (y > 0)).float())[..., win].half()
+  ctx.call("dd_relu_bwd_acc", _b(_lib.desc(dy, c, coff)), _b(_lib.desc(y, c, coff)), _b(_lib.desc(acc, c, coff)))
+  assert torch.equal(acc, want)
+  yy = torch.randn(n, h, w, cs, device="cuda").half()
+  want = yy.clone()
+  want[..., win] = torch.addcmul(yy.float(), dy.float(), torch.tensor(0.5, device="cuda"))[..., win].half()
+  ctx.call("dd_axpy", ctypes.c_float(0.5), _b(_lib.desc(dy, c, coff)), _b(_lib.desc(yy, c, coff)))
+  assert torch.equal(yy, want)
