@@ -64,7 +64,7 @@ class ClockSampler(threading.Thread):
           self.samples.append(parts)
       except Exception:  # noqa: BLE001
         pass
-      self.stop_flag.wait(0.2)
+      self.stop_flag.wait(0.02)
 
   def summary(self):
     if not self.samples:
@@ -259,7 +259,7 @@ def run_cuda(args, arch_json, weights, config):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "conv_rows_kernel (tcgen05 implicit-GEMM conv, all conv launches of the frame)",
                          "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                         "traffic": 4.239e9, "traffic_launch": "ncu --set full, 3x3 64->64 @8x1080x1920: dram read 2.160 GB + write 2.080 GB vs 4.247 GB algorithmic (profiles/r01_ncu_conv_rows_full.csv)",
+                         "traffic": 4.239e9, "traffic_launch": "ncu --set full, one 3x3 64->64 @8x1080x1920 launch: dram read 2.161 GB + write 2.078 GB vs 4.247 GB algorithmic (profiles/r01_ncu_conv_rows_full.csv)",
                          "launches_per_step": conv_launches, "ms_per_step_in_kernel": conv_ms, "peak_source": pk["source"]},
             "clocks": sampler.summary()}
     if world == 1 and not args.no_cpu_baseline:

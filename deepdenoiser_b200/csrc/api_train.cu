@@ -166,6 +166,80 @@ __global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ variation / masked losses
+// BaseFeatureTraining.variation_mean (Training.py:139-186, 304-346): LossDifference.difference of the horizontal
+// (x[:, :, 1:] - x[:, :, :-1]) and vertical forward differences of prediction and target, mean over both sets.  One thread
+// per pixel; the gradient is GATHERED (each pixel takes part in up to four difference terms), so no atomics.
+struct VarLossParams { View pred, target, dpred; int kind; float weight, epsilon; float* loss; };
+__global__ void __launch_bounds__(256) variation_loss_kernel(const VarLossParams p) {
+  const int h = p.pred.h, w = p.pred.w;
+  const size_t total = static_cast<size_t>(p.pred.n) * h * w;
+  const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float sum = 0.f;
+  if (pix < total) {
+    const int x = static_cast<int>(pix % w), y = static_cast<int>((pix / w) % h);
+    for (int c = 0; c < p.pred.c; ++c) {
+      const float pc = p.pred.load(pix, c), tc = p.target.load(pix, c);
+      float g = 0.f, v, gr;
+      if (x + 1 < w) { loss_elem(p.kind, p.pred.load(pix + 1, c) - pc, p.target.load(pix + 1, c) - tc, p.epsilon, v, gr); sum += v; g -= gr; }
+      if (x > 0) { loss_elem(p.kind, pc - p.pred.load(pix - 1, c), tc - p.target.load(pix - 1, c), p.epsilon, v, gr); g += gr; }
+      if (y + 1 < h) { loss_elem(p.kind, p.pred.load(pix + w, c) - pc, p.target.load(pix + w, c) - tc, p.epsilon, v, gr); sum += v; g -= gr; }
+      if (y > 0) { loss_elem(p.kind, pc - p.pred.load(pix - w, c), tc - p.target.load(pix - w, c), p.epsilon, v, gr); g += gr; }
+      if (p.dpred.ptr) p.dpred.store(pix, c, p.dpred.load(pix, c) + p.weight * g);
+    }
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+    if (threadIdx.x == 0) atomicAdd(p.loss, p.weight * v);
+  }
+}
+
+// BaseFeatureTraining.masked_mean (Training.py:131-137): sum(difference * mask) / sum(mask) (0 when the mask is empty),
+// mask = Conv2dUtilities.non_zero_mask of the corresponding colour target (Conv2dUtilities.py:69-74: sign(sum_c |x|)).
+struct MaskedLossParams { View pred, target, mask, dpred; int kind; float weight, epsilon; float* loss; const float* mask_sum; };
+__global__ void __launch_bounds__(256) mask_sum_kernel(const View mask, float* out) {
+  const size_t total = static_cast<size_t>(mask.n) * mask.h * mask.w;
+  const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float m = 0.f;
+  if (pix < total) {
+    float a = 0.f;
+    for (int c = 0; c < mask.c; ++c) a += fabsf(mask.load(pix, c));
+    m = (a > 0.f) ? 1.f : 0.f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+  if ((threadIdx.x & 31) == 0 && m != 0.f) atomicAdd(out, m);
+}
+__global__ void __launch_bounds__(256) masked_loss_kernel(const MaskedLossParams p) {
+  const size_t total = static_cast<size_t>(p.pred.n) * p.pred.h * p.pred.w;
+  const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const float ms = *p.mask_sum;
+  const float wgt = (ms > 0.f) ? p.weight / ms : 0.f;
+  float sum = 0.f;
+  if (pix < total && wgt != 0.f) {
+    float a = 0.f;
+    for (int c = 0; c < p.mask.c; ++c) a += fabsf(p.mask.load(pix, c));
+    if (a > 0.f) {
+      for (int c = 0; c < p.pred.c; ++c) {
+        float v, g;
+        loss_elem(p.kind, p.pred.load(pix, c), p.target.load(pix, c), p.epsilon, v, g);
+        sum += v;
+        if (p.dpred.ptr) p.dpred.store(pix, c, p.dpred.load(pix, c) + wgt * g);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0 && sum != 0.f) atomicAdd(p.loss, wgt * sum);
+}
+
 // ------------------------------------------------------------------------------------------------ conv wgrad (exact)
 // dW[r,s,c,o] += sum_{n,y,x} x[n, y+r-pad, x+s-pad, c] * dz[n,y,x,o]      (TF layout [kh,kw,cin,cout])
 // db[o]       += sum dz[n,y,x,o]
@@ -602,6 +676,47 @@ int dd_loss_fwd_bwd(dd_ctx* ctx, const dd_tensor* pred, const dd_tensor* target,
   p.kind = kind; p.weight = weight; p.epsilon = epsilon; p.accumulate = accumulate; p.loss = loss_dev;
   const size_t total = static_cast<size_t>(pred->n) * pred->h * pred->w;
   loss_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_loss_variation_fwd_bwd(dd_ctx* ctx, const dd_tensor* pred, const dd_tensor* target, int kind, float weight, float epsilon,
+                              float* loss_dev, const dd_tensor* dpred_acc, void* stream) {
+  DD_CHECK_ARG(ctx && loss_dev && tensor_ok(pred) && tensor_ok(target) && same_dims(pred, target), "bad argument");
+  DD_CHECK_ARG(!dpred_acc || (tensor_ok(dpred_acc) && same_dims(pred, dpred_acc)), "bad gradient tensor");
+  DD_CHECK_ARG(kind >= 0 && kind <= 4, "unknown loss difference");
+  VarLossParams p; memset(&p, 0, sizeof(p));
+  p.pred = make_view(pred); p.target = make_view(target);
+  if (dpred_acc) p.dpred = make_view(dpred_acc);
+  p.kind = kind; p.weight = weight; p.epsilon = epsilon; p.loss = loss_dev;
+  const size_t total = static_cast<size_t>(pred->n) * pred->h * pred->w;
+  variation_loss_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_mask_sum(dd_ctx* ctx, const dd_tensor* mask_src, float* sum_dev, void* stream) {
+  DD_CHECK_ARG(ctx && sum_dev && tensor_ok(mask_src), "bad argument");
+  const size_t total = static_cast<size_t>(mask_src->n) * mask_src->h * mask_src->w;
+  mask_sum_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(make_view(mask_src), sum_dev);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_loss_masked_fwd_bwd(dd_ctx* ctx, const dd_tensor* pred, const dd_tensor* target, const dd_tensor* mask_src,
+                           const float* mask_sum_dev, int kind, float weight, float epsilon, float* loss_dev,
+                           const dd_tensor* dpred_acc, void* stream) {
+  DD_CHECK_ARG(ctx && loss_dev && mask_sum_dev && tensor_ok(pred) && tensor_ok(target) && tensor_ok(mask_src) &&
+                   same_dims(pred, target), "bad argument");
+  DD_CHECK_ARG(mask_src->n == pred->n && mask_src->h == pred->h && mask_src->w == pred->w, "mask dims differ");
+  DD_CHECK_ARG(!dpred_acc || (tensor_ok(dpred_acc) && same_dims(pred, dpred_acc)), "bad gradient tensor");
+  DD_CHECK_ARG(kind >= 0 && kind <= 4, "unknown loss difference");
+  MaskedLossParams p; memset(&p, 0, sizeof(p));
+  p.pred = make_view(pred); p.target = make_view(target); p.mask = make_view(mask_src);
+  if (dpred_acc) p.dpred = make_view(dpred_acc);
+  p.kind = kind; p.weight = weight; p.epsilon = epsilon; p.loss = loss_dev; p.mask_sum = mask_sum_dev;
+  const size_t total = static_cast<size_t>(pred->n) * pred->h * pred->w;
+  masked_loss_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }

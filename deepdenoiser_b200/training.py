@@ -23,6 +23,7 @@ from .Architecture import Architecture, FeaturePredictionTupleType, ModeKeys
 from .FeatureFlags import FeatureFlagMode
 from .Naming import Naming
 from .network import V
+from .RenderPasses import RenderPasses
 
 LOSS_KINDS = {"DIFFERENCE": 0, "ABSOLUTE": 1, "SMOOTH_ABSOLUTE": 2, "SQUARED": 3, "SMAPE": 4}
 _LIGHTS = ("Diffuse", "Glossy", "Subsurface", "Transmission")
@@ -44,19 +45,25 @@ class TrainingSettings:
     self.loss_difference = j.get("loss_difference", "SMAPE")
     self.use_multiscale_loss = bool(j.get("use_multiscale_loss", True))
 
-    def mean_weight(block, default):
+    def weights(block, default_mean):
+      """(mean, variation, masked mean) weights of one *_training_settings block (TrainingExample.json:31-98)."""
       b = j.get(block, {})
-      for group in ("loss_weights", "loss_weights_masked"):
-        w = b.get(group, {})
-        for k, v in w.items():
-          if (k != "mean" or group == "loss_weights_masked") and float(v) != 0.0:
-            raise NotImplementedError("%s.%s.%s != 0: variation / MS-SSIM / masked losses are not built (weights are 0 "
-                                      "in TrainingExample.json:31-98)" % (block, group, k))
-      return float(b.get("loss_weights", {}).get("mean", default))
+      lw, lm = b.get("loss_weights", {}), b.get("loss_weights_masked", {})
+      if float(lw.get("ms_ssim", 0.0)) != 0.0 or float(lm.get("ms_ssim", 0.0)) != 0.0:
+        raise NotImplementedError("%s: MS-SSIM loss terms (tf.image.ssim_multiscale, Training.py:188-204) are not built; "
+                                  "masked MS-SSIM raises in the reference too (:206-207)" % block)
+      if float(lm.get("variation", 0.0)) != 0.0:
+        raise NotImplementedError("%s: the reference's masked variation loss multiplies a [N, h(w-1)+(h-1)w] tensor with an "
+                                  "[N,h,w] mask (Training.py:146-149) and cannot run; not built" % block)
+      return float(lw.get("mean", default_mean)), float(lw.get("variation", 0.0)), float(lm.get("mean", 0.0))
 
-    self.feature_weight = mean_weight("features_training_settings", 1.0)
-    self.combined_feature_weight = mean_weight("combined_features_training_settings", 5.0)
-    self.combined_image_weight = mean_weight("combined_image_training_settings", 10.0)
+    self.feature_weight, self.feature_variation_weight, self.feature_masked_weight = weights("features_training_settings", 1.0)
+    (self.combined_feature_weight, self.combined_feature_variation_weight,
+     self.combined_feature_masked_weight) = weights("combined_features_training_settings", 5.0)
+    self.combined_image_weight, self.combined_image_variation_weight, masked = weights("combined_image_training_settings", 10.0)
+    if masked != 0.0:
+      raise NotImplementedError("combined_image_training_settings: the combined image has no mask in the reference "
+                                "(CombinedImageFeatureTraining.initialize, Training.py:475-495)")
 
 
 class Trainer:
@@ -733,6 +740,33 @@ class Trainer:
       lo, hi = fp.bank_index * n, (fp.bank_index + 1) * n
       return _lib.desc(bank[lo:hi], channels or fp.number_of_channels, 0)
 
+    def mask_pass(name):
+      """FeatureTraining.initialize (Training.py:374-392): the pass whose target defines the mask of feature `name`."""
+      if RenderPasses.is_color_render_pass(name) or name in (RenderPasses.ENVIRONMENT, RenderPasses.EMISSION,
+                                                               RenderPasses.VOLUME_DIRECT, RenderPasses.VOLUME_INDIRECT):
+        return name
+      if RenderPasses.is_direct_or_indirect_render_pass(name):
+        return RenderPasses.direct_or_indirect_to_color_render_pass(name)
+      return None
+
+    def extra_terms(pred_d, tgt_d, grad_d, s, variation_weight, masked_weight, mask_name, what):
+      """variation_mean / masked_mean of one feature at scale s (BaseFeatureTraining.loss, Training.py:226-240); the gradient is
+      accumulated into grad_d."""
+      hs, ws = h >> s, w >> s
+      factor_s = norm / 4.0 ** s
+      if variation_weight > 0:
+        count = float(n * (hs * (ws - 1) + (hs - 1) * ws))
+        ctx.call("dd_loss_variation_fwd_bwd", _b(pred_d), _b(tgt_d), kind, ctypes.c_float(S * variation_weight * factor_s / count),
+                 ctypes.c_float(1e-2), _fp(self.loss_value), _b(grad_d))
+      if masked_weight > 0:
+        if mask_name is None or mask_name not in tgt:
+          raise Exception("Masking is not supported for '%s': no corresponding colour target (Training.py:102-113, 380-392)" % what)
+        mask_d = _lib.desc(tgt[mask_name][s])
+        msum = self._buf("mask.sum.%s.%d" % (what, s), (1,), zero=True)
+        ctx.call("dd_mask_sum", _b(mask_d), _fp(msum))
+        ctx.call("dd_loss_masked_fwd_bwd", _b(pred_d), _b(tgt_d), _b(mask_d), _fp(msum), kind,
+                 ctypes.c_float(S * masked_weight * factor_s), ctypes.c_float(1e-2), _fp(self.loss_value), _b(grad_d))
+
     for s in range(loss_scales):
       px = float(n * (h >> s) * (w >> s))
       factor = norm / 4.0 ** s
@@ -742,10 +776,17 @@ class Trainer:
           ctx.call("dd_loss_fwd_bwd", _b(pred_view(st["finals"][s], fp)), _b(_lib.desc(tgt[fp.name][s])), kind,
                    ctypes.c_float(S * cfg.feature_weight * factor / px), ctypes.c_float(1e-2), _fp(self.loss_value),
                    _b(pred_view(dfin[s], fp)), 1)
+      if cfg.feature_variation_weight > 0 or cfg.feature_masked_weight > 0:
+        for fp in loaded:
+          extra_terms(pred_view(st["finals"][s], fp), _lib.desc(tgt[fp.name][s]), pred_view(dfin[s], fp), s,
+                      cfg.feature_variation_weight, cfg.feature_masked_weight, mask_pass(fp.name), fp.name)
       # combined lighting passes color * (direct + indirect) and the combined image (sum of everything)
       lights = [l for l in _LIGHTS if all((l + k) in by_name and by_name[l + k].load_data for k in (" Color", " Direct", " Indirect"))]
       image_terms = [t for t in _IMAGE_TERMS if t in by_name and by_name[t].load_data]
-      use_image = cfg.combined_image_weight > 0 and len(lights) == 4 and len(image_terms) == 4
+      use_image = ((cfg.combined_image_weight > 0 or cfg.combined_image_variation_weight > 0) and len(lights) == 4 and
+                   len(image_terms) == 4)
+      use_combined = (cfg.combined_feature_weight > 0 or cfg.combined_feature_variation_weight > 0 or
+                      cfg.combined_feature_masked_weight > 0)
       shape = (n, h >> s, w >> s, 3)
       g_img = None
       if use_image:
@@ -753,7 +794,7 @@ class Trainer:
         img_t = self._buf("img.t%d" % s, shape, zero=True)
         g_img = self._buf("img.g%d" % s, shape)
       comb = {}
-      if lights and (cfg.combined_feature_weight > 0 or use_image):
+      if lights and (use_combined or use_image):
         for l in lights:
           c, d, i = (by_name[l + k] for k in (" Color", " Direct", " Indirect"))
           cp = self._buf("cmb.p.%s.%d" % (l, s), shape)
@@ -774,6 +815,8 @@ class Trainer:
         ctx.call("dd_loss_fwd_bwd", _b(_lib.desc(img_p)), _b(_lib.desc(img_t)), kind,
                  ctypes.c_float(S * cfg.combined_image_weight * factor / px), ctypes.c_float(1e-2), _fp(self.loss_value),
                  _b(_lib.desc(g_img)), 0)
+        extra_terms(_lib.desc(img_p), _lib.desc(img_t), _lib.desc(g_img), s, cfg.combined_image_variation_weight, 0.0, None,
+                    "Combined")
         for t in image_terms:
           ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(g_img)), _b(pred_view(dfin[s], by_name[t])))
       for l, (cp, ct, gc) in comb.items():
@@ -781,6 +824,8 @@ class Trainer:
           ctx.call("dd_loss_fwd_bwd", _b(_lib.desc(cp)), _b(_lib.desc(ct)), kind,
                    ctypes.c_float(S * cfg.combined_feature_weight * factor / px), ctypes.c_float(1e-2), _fp(self.loss_value),
                    _b(_lib.desc(gc)), 1)
+        extra_terms(_lib.desc(cp), _lib.desc(ct), _lib.desc(gc), s, cfg.combined_feature_variation_weight,
+                    cfg.combined_feature_masked_weight, RenderPasses.combined_to_color_render_pass(l), l)
         if use_image:
           ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(g_img)), _b(_lib.desc(gc)))
         c, d, i = (by_name[l + k] for k in (" Color", " Direct", " Indirect"))

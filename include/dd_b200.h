@@ -226,6 +226,18 @@ int dd_invert_standardization_bwd(dd_ctx* ctx, const dd_tensor* dy, const dd_ten
  * the caller folds loss weight, scale weight and 1/(N*h*w) into `weight`.  dpred may be NULL (evaluation). */
 int dd_loss_fwd_bwd(dd_ctx* ctx, const dd_tensor* pred, const dd_tensor* target, int kind, float weight, float epsilon,
                     float* loss_dev, const dd_tensor* dpred, int accumulate, void* stream);
+/* BaseFeatureTraining.variation_mean (Training.py:139-186, 304-346): *loss_dev += weight * sum of LossDifference.difference
+ * over the horizontal and vertical forward differences of pred / target; dpred_acc += the gradient (may be NULL).  The caller
+ * folds loss weight, scale weight and 1 / (N * (h*(w-1) + (h-1)*w)) into `weight`. */
+int dd_loss_variation_fwd_bwd(dd_ctx* ctx, const dd_tensor* pred, const dd_tensor* target, int kind, float weight, float epsilon,
+                              float* loss_dev, const dd_tensor* dpred_acc, void* stream);
+/* *sum_dev += number of pixels with sum_c |mask_src| > 0 (Conv2dUtilities.non_zero_mask, Conv2dUtilities.py:69-74). */
+int dd_mask_sum(dd_ctx* ctx, const dd_tensor* mask_src, float* sum_dev, void* stream);
+/* BaseFeatureTraining.masked_mean (Training.py:131-137): *loss_dev += weight * sum(difference * mask) / *mask_sum_dev
+ * (nothing when the mask is empty), dpred_acc += its gradient. */
+int dd_loss_masked_fwd_bwd(dd_ctx* ctx, const dd_tensor* pred, const dd_tensor* target, const dd_tensor* mask_src,
+                           const float* mask_sum_dev, int kind, float weight, float epsilon, float* loss_dev,
+                           const dd_tensor* dpred_acc, void* stream);
 /* dW (TF layout [kh,kw,cin,cout]; transposed: [2,2,cout,cin]) += x^T * dz over all pixels, db += sum dz. */
 int dd_conv2d_wgrad(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int ksize, int transposed, float* dw_dev,
                     float* db_dev, void* stream);

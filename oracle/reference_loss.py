@@ -3,8 +3,9 @@ that torch.autograd provides the gradient oracle for the CUDA backward kernels.
 
 Follows Training.py: model_fn loss assembly :611-660, BaseFeatureTraining.loss :210-243 (scale weights (1/4^s) / sum),
 mean :126-129, FeatureTraining / CombinedFeatureTraining / CombinedImageFeatureTraining.initialize :374-495 and
-LossDifference.difference (LossDifference.py:15-36).  Masked / variation / MS-SSIM terms have weight 0 in
-TrainingExample.json:31-98 and are not restated.  PARITY UNPINNED (see oracle/np_ops.py).
+LossDifference.difference (LossDifference.py:15-36), variation_mean :139-186 + :304-346 and masked_mean :131-137 with the
+masks of FeatureTraining / CombinedFeatureTraining.initialize :374-392, :434-437.  MS-SSIM terms (weight 0 in
+TrainingExample.json:31-98) are not restated.  PARITY UNPINNED (see oracle/np_ops.py).
 """
 import torch
 
@@ -22,37 +23,79 @@ def multiscale_targets(labels, n_scales):
   return out
 
 
-def feature_loss(predicted, target, kind, weight, use_multiscale_loss=True):
-  """BaseFeatureTraining.loss with only mean_weight > 0 (Training.py:210-243)."""
+def variation_mean(predicted, target, kind):
+  """Training.py:139-186: mean over the concatenated horizontal / vertical variation differences."""
+  hor = torch_ops.loss_difference(predicted[:, :, 1:, :] - predicted[:, :, :-1, :], target[:, :, 1:, :] - target[:, :, :-1, :], kind)
+  ver = torch_ops.loss_difference(predicted[:, 1:, :, :] - predicted[:, :-1, :, :], target[:, 1:, :, :] - target[:, :-1, :, :], kind)
+  return torch.cat([hor.reshape(hor.shape[0], -1), ver.reshape(ver.shape[0], -1)], dim=1).mean()
+
+
+def non_zero_mask(x):
+  """Conv2dUtilities.non_zero_mask (Conv2dUtilities.py:69-74)."""
+  return torch.sign(x.abs().sum(dim=3))
+
+
+def masked_mean(predicted, target, mask_source, kind):
+  """Training.py:131-137."""
+  mask = non_zero_mask(mask_source)
+  total = mask.sum()
+  if float(total) <= 0:
+    return torch.zeros((), dtype=predicted.dtype)
+  return (torch_ops.loss_difference(predicted, target, kind) * mask / total).sum()
+
+
+def feature_loss(predicted, target, kind, weight, use_multiscale_loss=True, variation_weight=0.0, masked_weight=0.0,
+                 mask_source=None):
+  """BaseFeatureTraining.loss (Training.py:210-243) without the MS-SSIM terms."""
   scales = len(target) if use_multiscale_loss else 1
   norm = 1.0 / sum(1.0 / 4.0 ** s for s in range(scales))
   result = 0.0
   for s in range(scales):
-    mean = torch_ops.loss_difference(predicted[s], target[s], kind).mean()
-    result = result + weight * (norm / 4.0 ** s) * mean
+    factor = norm / 4.0 ** s
+    if weight > 0:
+      result = result + weight * factor * torch_ops.loss_difference(predicted[s], target[s], kind).mean()
+    if variation_weight > 0:
+      result = result + variation_weight * factor * variation_mean(predicted[s], target[s], kind)
+    if masked_weight > 0:
+      result = result + masked_weight * factor * masked_mean(predicted[s], target[s], mask_source[s], kind)
   return result
 
 
+def mask_pass(name):
+  """FeatureTraining.initialize (Training.py:380-388) incl. the reference's ' Inirect' typo (RenderPasses.py:88)."""
+  if name.endswith(" Color") or name in ("Environment", "Emission", "Volume Direct", "Volume Indirect"):
+    return name
+  if name.endswith(" Direct"):
+    return name.replace(" Direct", " Color")
+  if name.endswith(" Indirect"):
+    return name
+  return None
+
+
 def total_loss(predictions, labels, loaded_names, kind="SMAPE", feature_weight=1.0, combined_feature_weight=5.0,
-               combined_image_weight=10.0, use_multiscale_loss=True):
+               combined_image_weight=10.0, use_multiscale_loss=True, feature_variation_weight=0.0, feature_masked_weight=0.0,
+               combined_feature_variation_weight=0.0, combined_feature_masked_weight=0.0, combined_image_variation_weight=0.0):
   """predictions: list over scales of {'prediction/<Pass>': tensor}; labels: {'target_image/<Pass>': tensor}."""
   targets = multiscale_targets(labels, len(predictions))
   p = lambda name: [d["prediction/" + name] for d in predictions]     # noqa: E731
   t = lambda name: [d["target_image/" + name] for d in targets]       # noqa: E731
   loss = 0.0
-  if feature_weight > 0:
+  if feature_weight > 0 or feature_variation_weight > 0 or feature_masked_weight > 0:
     for name in loaded_names:
-      loss = loss + feature_loss(p(name), t(name), kind, feature_weight, use_multiscale_loss)
+      mask = t(mask_pass(name)) if (feature_masked_weight > 0 and mask_pass(name) is not None) else None
+      loss = loss + feature_loss(p(name), t(name), kind, feature_weight, use_multiscale_loss, feature_variation_weight,
+                                 feature_masked_weight if mask is not None else 0.0, mask)
   lights = [l for l in LIGHTS if all((l + k) in loaded_names for k in (" Color", " Direct", " Indirect"))]
   comb_p, comb_t = {}, {}
   for l in lights:
     comb_p[l] = [c * (d + i) for c, d, i in zip(p(l + " Color"), p(l + " Direct"), p(l + " Indirect"))]
     comb_t[l] = [c * (d + i) for c, d, i in zip(t(l + " Color"), t(l + " Direct"), t(l + " Indirect"))]
-    if combined_feature_weight > 0:
-      loss = loss + feature_loss(comb_p[l], comb_t[l], kind, combined_feature_weight, use_multiscale_loss)
+    if combined_feature_weight > 0 or combined_feature_variation_weight > 0 or combined_feature_masked_weight > 0:
+      loss = loss + feature_loss(comb_p[l], comb_t[l], kind, combined_feature_weight, use_multiscale_loss,
+                                 combined_feature_variation_weight, combined_feature_masked_weight, t(l + " Color"))
   terms = [x for x in IMAGE_TERMS if x in loaded_names]
-  if combined_image_weight > 0 and len(lights) == 4 and len(terms) == 4:
+  if (combined_image_weight > 0 or combined_image_variation_weight > 0) and len(lights) == 4 and len(terms) == 4:
     img_p = [sum(comb_p[l][s] for l in lights) + sum(p(x)[s] for x in terms) for s in range(len(predictions))]
     img_t = [sum(comb_t[l][s] for l in lights) + sum(t(x)[s] for x in terms) for s in range(len(predictions))]
-    loss = loss + feature_loss(img_p, img_t, kind, combined_image_weight, use_multiscale_loss)
+    loss = loss + feature_loss(img_p, img_t, kind, combined_image_weight, use_multiscale_loss, combined_image_variation_weight)
   return loss

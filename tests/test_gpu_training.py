@@ -252,3 +252,36 @@ def test_tensor_core_training_tiramisu_backbone():
     if "conv2d_transpose" in name and name.endswith("kernel"):
       x, y = got[name].reshape(-1).astype(np.float64), g.reshape(-1)
       assert float(x @ y / (np.linalg.norm(x) * np.linalg.norm(y))) >= 0.995, name
+
+
+def test_variation_and_masked_losses_match_autograd():
+  """variation_mean (all three feature groups) and masked_mean (features + combined lighting) with non-zero
+  weights, exact path, against torch-autograd of the restated reference loss."""
+  j = small_example(filters=(16, 16), n_convs=1, k=3)
+  host, weights, features, targets = make_problem(j, n=2, h=8, w=12)
+  tj = {"loss_difference": "SMAPE",
+        "features_training_settings": {"loss_weights": {"mean": 1.0, "variation": 0.7, "ms_ssim": 0.0},
+                                       "loss_weights_masked": {"mean": 0.4, "variation": 0.0, "ms_ssim": 0.0}},
+        "combined_features_training_settings": {"loss_weights": {"mean": 5.0, "variation": 1.5, "ms_ssim": 0.0},
+                                                "loss_weights_masked": {"mean": 2.0, "variation": 0.0, "ms_ssim": 0.0}},
+        "combined_image_training_settings": {"loss_weights": {"mean": 10.0, "variation": 3.0, "ms_ssim": 0.0}}}
+  trainer = Trainer(Architecture(j, weights=weights), TrainingSettings(tj))
+  trainer.forward({k: torch.from_numpy(v) for k, v in features.items()})
+  loss = float(trainer.loss_and_gradient({k: torch.from_numpy(v) for k, v in targets.items()}).item())
+  trainer.backward()
+  want_loss, want_grads, _ = oracle_loss_and_grads(
+      j, weights, features, targets, kind="SMAPE", feature_variation_weight=0.7, feature_masked_weight=0.4,
+      combined_feature_variation_weight=1.5, combined_feature_masked_weight=2.0, combined_image_variation_weight=3.0)
+  base_loss, _, _ = oracle_loss_and_grads(j, weights, features, targets, kind="SMAPE")
+  assert want_loss > base_loss + 1.0                      # the extra terms are really in play
+  assert abs(loss - want_loss) <= 1e-4 * max(1.0, abs(want_loss)), (loss, want_loss)
+  worst = check_gradients(trainer, want_grads)
+  print("variation + masked: loss %.5f (oracle %.5f, mean-only %.5f), worst relative gradient error %.2e" %
+        (loss, want_loss, base_loss, worst))
+
+
+def test_unbuilt_loss_terms_fail_loudly():
+  with pytest.raises(NotImplementedError):
+    TrainingSettings({"features_training_settings": {"loss_weights": {"mean": 1.0, "ms_ssim": 0.1}}})
+  with pytest.raises(NotImplementedError):
+    TrainingSettings({"features_training_settings": {"loss_weights_masked": {"variation": 0.1}}})
