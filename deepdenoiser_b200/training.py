@@ -35,6 +35,20 @@ def _fp(t):
   return ctypes.c_void_p(t.data_ptr())
 
 
+def data_parallel_reduce(grad, loss, world_size):
+  """The ONE exchange step of data-parallel training: every rank holds the gradient of the mean loss over ITS
+  tiles in one flat fp32 buffer; the buffers (and the scalar loss, for logging) are summed over the ranks in place and the
+  returned factor 1/world turns the sum into the gradient of the mean over the GLOBAL batch (Training.py:128 takes a mean).
+  Backend-agnostic (NCCL on the GPUs, gloo in the CPU tests)."""
+  if world_size <= 1:
+    return 1.0
+  import torch.distributed as dist
+  dist.all_reduce(grad)                       # one flat bucket: 1.7 M floats for the U-Net (latency bound)
+  dist.all_reduce(loss)
+  loss /= world_size
+  return 1.0 / world_size
+
+
 class TrainingSettings:
   """The part of TrainingExample.json the loss needs (Training.py:969-989, 1009-1203)."""
 
@@ -910,13 +924,7 @@ class Trainer:
     self.forward(features)
     loss = self.loss_and_gradient(targets_dict)
     self.backward()
-    scale = 1.0
-    if world_size > 1:
-      import torch.distributed as dist
-      dist.all_reduce(self.grad)                  # one flat bucket: 1.7 M floats for the U-Net (latency bound)
-      dist.all_reduce(loss)
-      loss /= world_size
-      scale = 1.0 / world_size                    # the loss is a mean over the global batch (Training.py:128)
+    scale = data_parallel_reduce(self.grad, loss, world_size)
     self.apply_gradients(scale)
     return loss
 

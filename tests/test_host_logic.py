@@ -131,3 +131,43 @@ def test_render_passes_and_naming_contract():
   assert Naming.feature_flags_name("Diffuse") == "feature_flag/Diffuse"
   assert Naming.mean_name("Diffuse", masked=True, scale_index=2) == "combined_diffuse_mean_masked/4"
   assert Naming.difference_name("Volume Direct") == "volume_direct_difference"
+
+
+# ------------------------------------------------------------------------------------------------ data-parallel exchange (gloo)
+def _dp_worker(rank, world, port, out_dir):
+  import os
+  import numpy as np
+  import torch
+  import torch.distributed as dist
+  from deepdenoiser_b200.training import data_parallel_reduce
+  os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  # a toy "mean over the tiles of this rank" loss: L_r = mean_i 0.5 * (theta . x_i)^2 over the rank's 3 tiles
+  rng = np.random.default_rng(7)
+  theta = torch.from_numpy(rng.standard_normal(5).astype(np.float32))
+  tiles = torch.from_numpy(rng.standard_normal((world * 3, 5)).astype(np.float32))
+  mine = tiles[rank * 3:(rank + 1) * 3]
+  proj = mine @ theta
+  loss = (0.5 * proj ** 2).mean().reshape(1).clone()
+  grad = ((proj[:, None] * mine).mean(dim=0)).clone()
+  scale = data_parallel_reduce(grad, loss, world)
+  np.savez(os.path.join(out_dir, "rank%d.npz" % rank), grad=(grad * scale).numpy(), loss=loss.numpy())
+  dist.destroy_process_group()
+
+
+def test_data_parallel_reduce_equals_the_global_batch_gradient(tmp_path):
+  import socket
+  import numpy as np
+  import torch
+  import torch.multiprocessing as mp
+  s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+  world = 2
+  mp.spawn(_dp_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+  rng = np.random.default_rng(7)
+  theta = rng.standard_normal(5).astype(np.float32)
+  tiles = rng.standard_normal((world * 3, 5)).astype(np.float32)
+  proj = tiles @ theta
+  want_loss, want_grad = float((0.5 * proj ** 2).mean()), (proj[:, None] * tiles).mean(axis=0)
+  for rank in range(world):
+    z = np.load(str(tmp_path / ("rank%d.npz" % rank)))
+    assert np.allclose(z["grad"], want_grad, atol=1e-6) and abs(float(z["loss"][0]) - want_loss) < 1e-6
