@@ -170,6 +170,10 @@ def conv_roofline(arch, feats_dev, steps):
 
 
 def run_cuda(args, arch_json, weights, config):
+  # the contract is ONE JSON line on stdout: libraries (NCCL prints its version there) write to stderr from here on
+  sys.stdout.flush()
+  json_fd = os.dup(1)
+  os.dup2(2, 1)
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
   local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -269,7 +273,8 @@ def run_cuda(args, arch_json, weights, config):
                               "sample": "%d tiles of 128x128 x 17 passes (%.2f s/tile), scaled to %d tiles/frame; restated "
                                         "reference on torch-CPU float32 (TensorFlow 1.x not installable)" %
                                         (args.ref_tiles, dt, tpf)}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
   if dist is not None:
     dist.barrier()
     dist.destroy_process_group()
