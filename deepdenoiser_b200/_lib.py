@@ -10,7 +10,7 @@ import os
 import torch
 
 DD_F32, DD_F16 = 0, 1
-DD_CONV_RELU, DD_CONV_RELU_COPY = 1, 2
+DD_CONV_RELU, DD_CONV_RELU_COPY, DD_CONV_RESIDUAL_MASK = 1, 2, 4
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdd_b200.so")
 
@@ -205,8 +205,9 @@ class Context:
                                                 packed.data_ptr(), self._stream()))
     return packed
 
-  def conv2d(self, x, w_packed, bias, ksize, y, relu=False, residual=None, y_relu=None):
-    flags = (DD_CONV_RELU if relu else 0) | (DD_CONV_RELU_COPY if y_relu is not None else 0)
+  def conv2d(self, x, w_packed, bias, ksize, y, relu=False, residual=None, y_relu=None, residual_is_mask=False):
+    flags = ((DD_CONV_RELU if relu else 0) | (DD_CONV_RELU_COPY if y_relu is not None else 0) |
+             (DD_CONV_RESIDUAL_MASK if residual_is_mask else 0))
     self._check(self.lib.dd_conv2d_fwd(
         self.handle, ctypes.byref(x), w_packed.data_ptr(), bias.data_ptr() if bias is not None else None, ksize,
         flags, ctypes.byref(residual) if residual is not None else None, ctypes.byref(y),

@@ -241,6 +241,7 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
                      L.cout % 8 == 0, "residual must be aligned fp16 with a multiple of 8 channels");
     p.residual = reinterpret_cast<const __half*>(L.residual->ptr);
     p.res_cstride = L.residual->cstride; p.res_coff = L.residual->coff;
+    p.res_is_mask = (L.flags & DD_CONV_RESIDUAL_MASK) ? 1 : 0;
   }
 
   ConvRowsMaps maps;
@@ -442,6 +443,7 @@ int dd_conv2d_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const f
   DD_CHECK_ARG(!residual || (tensor_ok(residual) && residual->c == y->c), "bad residual");
   DD_CHECK_ARG(!y_relu || (tensor_ok(y_relu) && y_relu->c == y->c), "bad y_relu");
   DD_CHECK_ARG(((flags & DD_CONV_RELU_COPY) != 0) == (y_relu != nullptr), "DD_CONV_RELU_COPY needs y_relu");
+  DD_CHECK_ARG(!(flags & DD_CONV_RESIDUAL_MASK) || (residual && x->dtype == DD_F16), "DD_CONV_RESIDUAL_MASK: fp16 path with a mask tensor");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (x->dtype == DD_F32) {
     DD_CHECK_ARG(y->dtype == DD_F32, "exact path writes fp32");

@@ -72,6 +72,7 @@ struct ConvRowsParams {
   const float* bias;
   const __half* residual;
   int res_cstride, res_coff;
+  int res_is_mask;        // the residual tensor is a ReLU mask source (DD_CONV_RESIDUAL_MASK) instead of an addend
   unsigned long long* trace;
 };
 
@@ -540,7 +541,12 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     const float2 r2 = __half22float2(rh[e]);
-                    f[i * 8 + 2 * e] += r2.x; f[i * 8 + 2 * e + 1] += r2.y;
+                    if (p.res_is_mask) {      // backward of a ReLU fused into the input-gradient conv: y = conv(x) * [mask > 0]
+                      if (!(r2.x > 0.f)) f[i * 8 + 2 * e] = 0.f;
+                      if (!(r2.y > 0.f)) f[i * 8 + 2 * e + 1] = 0.f;
+                    } else {
+                      f[i * 8 + 2 * e] += r2.x; f[i * 8 + 2 * e + 1] += r2.y;
+                    }
                   }
                 }
               }

@@ -385,6 +385,8 @@ class Trainer:
 
   def _block_bwd(self, key, layers, acts, dout):
     """Backward through n x [conv + ReLU]; dout = dL/d(acts[-1]); returns dL/d(acts[0]) (fresh buffer)."""
+    if self.mixed:
+      return self._block_bwd_fused(key, layers, acts, dout)
     dy = dout
     for i in reversed(range(len(layers))):
       var, x, y = layers[i], acts[i], acts[i + 1]
@@ -394,6 +396,26 @@ class Trainer:
       self._conv_bwd(var, x, dz, dx, bias_done=done)
       dy = dx
     return dy
+
+  def _block_bwd_fused(self, key, layers, acts, dout):
+    """Tensor-core mode: the input-gradient conv of layer i applies the ReLU mask of layer i-1 in its epilogue
+    (DD_CONV_RESIDUAL_MASK), so dz_{i-1} is produced directly and only a read-only pass remains for the bias gradient."""
+    ctx = self.ctx
+    last = len(layers) - 1
+    dz = self._act("%s.dz%d" % (key, last), tuple(acts[-1].t.shape[:3]), layers[last].cout)
+    self._relu_bwd(dout, acts[-1], dz, bias_of=layers[last])
+    for i in reversed(range(len(layers))):
+      var, x = layers[i], acts[i]
+      ctx.call("dd_conv2d_wgrad_tc", _b(x.d), _b(dz.d), var.ksize, 0, _fp(self.param_grad(var.kernel_name)), ctypes.c_float(1.0))
+      if i > 0:
+        dz_prev = self._act("%s.dz%d" % (key, i - 1), tuple(x.t.shape[:3]), var.cin)
+        ctx.conv2d(dz.d, self.bwd[var.name], None, var.ksize, dz_prev.d, residual=x.d, residual_is_mask=True)
+        ctx.call("dd_relu_bwd_bias", _b(dz_prev.d), None, None, _fp(self.param_grad(layers[i - 1].bias_name)), ctypes.c_float(1.0))
+        dz = dz_prev
+      else:
+        dx = self._act("%s.dx0" % key, tuple(x.t.shape[:3]), var.cin)
+        ctx.conv2d(dz.d, self.bwd[var.name], None, var.ksize, dx.d)
+        return dx
 
   def _unet_backward(self, tape, dlogits_coarse_first):
     """Backward of _unet_forward.  Returns dL/dx0 (V over [B,H,W,C0])."""

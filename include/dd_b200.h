@@ -78,6 +78,8 @@ int dd_conv2d_pack_weights(dd_ctx* ctx, const float* w_host, int ksize, int cin,
 /* flags for dd_conv2d_fwd */
 #define DD_CONV_RELU 1u        /* activation=tf.nn.relu on the output */
 #define DD_CONV_RELU_COPY 2u   /* additionally write relu(output) to y_relu (dense-block inputs) */
+#define DD_CONV_RESIDUAL_MASK 4u /* `residual` is a ReLU mask source: y = conv(x) * [residual > 0] (fp16 path; the input-gradient
+                                   conv of the tensor-core training path fuses the previous layer's ReLU backward this way) */
 
 /* y = conv2d(x, W) + b, stride 1, padding 'same', ksize 3 or 1; optional residual add and ReLU.
  * Replaces tf.layers.conv2d at UNet.py:29-31, Tiramisu.py:35-37,50-52,77-79, Architecture.py:238-243,

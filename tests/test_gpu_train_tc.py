@@ -172,3 +172,18 @@ def test_vectorised_elementwise_fp16_windows(ctx):
   want[..., win] = torch.addcmul(yy.float(), dy.float(), torch.tensor(0.5, device="cuda"))[..., win].half()
   ctx.call("dd_axpy", ctypes.c_float(0.5), _b(_lib.desc(dy, c, coff)), _b(_lib.desc(yy, c, coff)))
   assert torch.equal(yy, want)
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 64), (96, 24)])
+def test_conv_epilogue_relu_mask(ctx, cin, cout):
+  """DD_CONV_RESIDUAL_MASK: y = conv(x) * [mask > 0] - the ReLU backward of the previous layer fused into the input-gradient
+  convolution.  Must equal the unfused pair (conv, then dd_relu_bwd) bit for bit."""
+  n, h, w = 1, 11, 150
+  x = torch.randn(n, h, w, cin, device="cuda").half()
+  mask = torch.randn(n, h, w, cout, device="cuda").half()
+  wp = ctx.pack_conv_weights(torch.randn(3, 3, cin, cout) * 0.1, torch.float16)
+  plain = torch.empty(n, h, w, cout, device="cuda", dtype=torch.float16)
+  fused = torch.empty_like(plain)
+  ctx.conv2d(_lib.desc(x), wp, None, 3, _lib.desc(plain))
+  ctx.conv2d(_lib.desc(x), wp, None, 3, _lib.desc(fused), residual=_lib.desc(mask), residual_is_mask=True)
+  assert torch.equal(fused, plain * (mask > 0))
