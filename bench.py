@@ -166,7 +166,30 @@ def conv_roofline(arch, feats_dev, steps):
       a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += f
     for label, (n, t, f) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
       print("  %-34s n=%3d  %8.3f ms/step  %7.1f TFLOP/s" % (label, n // steps, t / steps, f / t / 1e9), file=sys.stderr)
-  return flops / steps, ms / steps, len(records) // steps
+  core = [(e0.elapsed_time(e1), f) for e0, e1, f, label in records if label.startswith("3x3")]
+  core_tflops = sum(f for _, f in core) / max(1e-9, sum(t for t, _ in core)) / 1e9
+  return flops / steps, ms / steps, len(records) // steps, core_tflops
+
+
+def l1_against_oracle(arch_json, weights, device):
+  """'L1 vs TF ref' of the metric: per-pixel |out - oracle| of the benchmarked fp16 path on a 32x64 crop of the same synthetic
+  render passes, against the float64 restatement of the reference (TensorFlow itself cannot run here), relative to
+  max(1, |oracle|max) of each output pass; mean and max over every pass of the full-resolution scale."""
+  from oracle import np_ops, reference_model
+  jj = dict(arch_json)
+  jj["b200"] = {"dtype": "float16"}
+  arch = Architecture(jj, weights=weights, device=device)
+  feats = synthetic.synthetic_features(arch, 1, 32, 64, seed=1234)
+  out = arch.predict({k: torch.from_numpy(v) for k, v in feats.items()})[0]
+  torch.cuda.synchronize()
+  want = reference_model.Architecture(arch_json, ops=np_ops, dtype=np.float64, weights=weights).predict_numpy(feats)[0]
+  means, worst = [], 0.0
+  for k, w in want.items():
+    scale = max(1.0, float(np.abs(w).max()))
+    err = np.abs(out[k].float().cpu().numpy().astype(np.float64) - w) / scale
+    means.append(float(err.mean()))
+    worst = max(worst, float(err.max()))
+  return {"mean": float(np.mean(means)), "max": worst, "passes": len(means), "crop": "1x32x64", "reference": "float64 oracle (oracle/reference_model.py)"}
 
 
 def run_cuda(args, arch_json, weights, config):
@@ -249,7 +272,7 @@ def run_cuda(args, arch_json, weights, config):
   line = None
   if rank == 0:
     pk = peaks()
-    flops, conv_ms, conv_launches = conv_roofline(arch, feats_dev, 2)
+    flops, conv_ms, conv_launches, core_tflops = conv_roofline(arch, feats_dev, 2)
     achieved = flops / (conv_ms / 1e3) / 1e12
     tuples = len(arch.feature_prediction_tuples)
     cfg = dict(config)
@@ -264,9 +287,13 @@ def run_cuda(args, arch_json, weights, config):
             "roofline": {"bound": "tensor", "kernel": "conv_rows_kernel (tcgen05 implicit-GEMM conv, all conv launches of the frame)",
                          "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                          "traffic": 4.239e9, "traffic_launch": "ncu --set full, one 3x3 64->64 @8x1080x1920 launch: dram read 2.161 GB + write 2.078 GB vs 4.247 GB algorithmic (profiles/r01_ncu_conv_rows_full.csv)",
-                         "launches_per_step": conv_launches, "ms_per_step_in_kernel": conv_ms, "peak_source": pk["source"]},
+                         "launches_per_step": conv_launches, "ms_per_step_in_kernel": conv_ms, "peak_source": pk["source"],
+                         "unet_3x3_stack": {"achieved": core_tflops, "frac": core_tflops / pk["tflops"],
+                                            "note": "the 3x3 layers of the U-Net backbone only (96 % of the frame's conv FLOPs); "
+                                                    "`achieved` above also counts the 2x2 transposed convs"}},
             "clocks": sampler.summary()}
     if world == 1 and not args.no_cpu_baseline:
+      line["l1_vs_oracle"] = l1_against_oracle(arch_json, weights, local)
       threads = os.cpu_count() or 1
       v, dt, tpf = cpu_reference(arch_json, weights, threads, args.ref_tiles)
       line["cpu_baseline"] = {"value": v, "unit": "MP/s", "cores": threads, "kind": "port",
@@ -288,12 +315,19 @@ def main():
   ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
   ap.add_argument("--ref-tiles", type=int, default=4, help="tiles timed per CPU-baseline sample")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--arch", default="unet32", choices=["unet32", "tiramisu32"],
+                  help="unet32 = the headline configuration (configs[1]); tiramisu32 = the Tiramisu + 21x21 kernel-prediction "
+                       "network of configs[2], inference only (an extra measurement, not the headline)")
   args = ap.parse_args()
-  arch_json = synthetic.baseline_architecture_json("unet32")
+  arch_json = synthetic.baseline_architecture_json(args.arch)
   weights = synthetic.randomize_biases(Architecture(arch_json).weights)
   config = {"workload": "configs[1]: U-Net [64,96,128]x4 KPCN K=5, 32-ch render-pass stack, 1920x1080 frame, batch 1, "
                         "SINGLE tuples (17 passes/frame), 3 scales", "height": HEIGHT, "width": WIDTH,
             "input_channels": 32, "kernel_size": 5}
+  if args.arch == "tiramisu32":
+    config = {"workload": "configs[2] network, inference: Tiramisu [64,96,128]x4 KPCN K=21, 32-ch render-pass stack, 1920x1080 "
+                          "frame, batch 1, SINGLE tuples (17 passes/frame), 3 scales", "height": HEIGHT, "width": WIDTH,
+              "input_channels": 32, "kernel_size": 21}
   if args.impl == "reference":
     run_reference(args, arch_json, weights, config)
   else:
