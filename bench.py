@@ -325,6 +325,8 @@ def main():
                         "SINGLE tuples (17 passes/frame), 3 scales", "height": HEIGHT, "width": WIDTH,
             "input_channels": 32, "kernel_size": 5}
   if args.arch == "tiramisu32":
+    global METRIC
+    METRIC = "megapixels/sec denoised (Tiramisu KPCN K=21 32-ch 1080p; extra measurement, not the headline)"
     config = {"workload": "configs[2] network, inference: Tiramisu [64,96,128]x4 KPCN K=21, 32-ch render-pass stack, 1920x1080 "
                           "frame, batch 1, SINGLE tuples (17 passes/frame), 3 scales", "height": HEIGHT, "width": WIDTH,
               "input_channels": 32, "kernel_size": 21}
