@@ -187,3 +187,37 @@ def test_conv_epilogue_relu_mask(ctx, cin, cout):
   ctx.conv2d(_lib.desc(x), wp, None, 3, _lib.desc(plain))
   ctx.conv2d(_lib.desc(x), wp, None, 3, _lib.desc(fused), residual=_lib.desc(mask), residual_is_mask=True)
   assert torch.equal(fused, plain * (mask > 0))
+
+
+@pytest.mark.parametrize("k,features,ipt,h,w,ldtype", [(5, 1, 1, 9, 14, torch.float32), (21, 1, 2, 12, 10, torch.float32),
+                                                        (3, 3, 1, 8, 11, torch.float32), (5, 3, 2, 7, 9, torch.float16)])
+def test_kernel_predict_bwd_matches_autograd(ctx, k, features, ipt, h, w, ldtype):
+  """dd_kernel_predict_bwd against torch autograd of softmax + symmetric-padded KxK gather (KernelPrediction.py:11-63)."""
+  tuples = 2
+  b, k2, pad = tuples * ipt, k * k, (k - 1) // 2
+  g = torch.Generator(device="cuda").manual_seed(k * 10 + features)
+  cs = (features * k2 + 7) // 8 * 8
+  logits = torch.zeros(b, h, w, cs, device="cuda")
+  logits[..., :features * k2] = torch.randn(b, h, w, features * k2, device="cuda", generator=g) * 2
+  logits = logits.to(ldtype)
+  src = torch.randn(features * b, h, w, 3, device="cuda", generator=g)
+  dout = torch.randn(features * b, h, w, 3, device="cuda", generator=g)
+  dl = torch.zeros(b, h, w, cs, device="cuda", dtype=ldtype)
+  ctx.call("dd_kernel_predict_bwd", _b(_lib.desc(src)), _b(_lib.desc(logits, features * k2, 0)), _b(_lib.desc(dout)), k, features,
+           ipt, _b(_lib.desc(dl, features * k2, 0)))
+  lg = logits.float()[..., :features * k2].clone().requires_grad_(True)
+  idx_y = torch.arange(-pad, h + pad, device="cuda")
+  idx_x = torch.arange(-pad, w + pad, device="cuda")
+  sym = lambda i, n: torch.where(i < 0, -i - 1, torch.where(i >= n, 2 * n - i - 1, i))   # noqa: E731
+  loss = 0.0
+  for bi in range(b):
+    t, n = divmod(bi, ipt)
+    for f in range(features):
+      o = (t * features + f) * ipt + n
+      padded = src[o][sym(idx_y, h)][:, sym(idx_x, w)]                       # [h+2p, w+2p, 3], symmetric padding
+      wts = torch.softmax(lg[bi, :, :, f * k2:(f + 1) * k2], dim=-1)
+      out = sum(wts[..., i * k + j, None] * padded[i:i + h, j:j + w] for i in range(k) for j in range(k))
+      loss = loss + (out * dout[o]).sum()
+  loss.backward()
+  tol = 2e-3 if ldtype == torch.float16 else 2e-5
+  assert rel_err(dl.float()[..., :features * k2], lg.grad) <= tol
