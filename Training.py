@@ -109,6 +109,11 @@ def main(parsed_arguments):
   settings = TrainingSettings(training_json)
   precision = parsed_arguments.precision or "float16"
   trainer = Trainer(architecture, settings, precision=precision)
+  comm = None
+  if world > 1:
+    # the gradient exchange runs through libdd_b200's own NCCL communicator; torch.distributed carries the unique id only
+    from deepdenoiser_b200 import _lib
+    comm = _lib.Communicator(trainer.ctx, rank, world)
   model_dir = os.path.join(base, architecture.model_directory)
   os.makedirs(model_dir, exist_ok=True)
   checkpoints = sorted(glob.glob(os.path.join(model_dir, "ckpt-*.npz")), key=lambda p: int(p.split("-")[-1][:-4]))
@@ -144,7 +149,7 @@ def main(parsed_arguments):
       if use_records:
         size = next(iter(features.values())).shape[1]
       t0 = time.perf_counter()
-      loss = float(trainer.train_step(features, targets, world_size=world).item())
+      loss = float(trainer.train_step(features, targets, world_size=world, comm=comm).item())
       dt = time.perf_counter() - t0
       if rank == 0:
         rec = {"step": trainer.step_count, "epoch": epoch, "loss": loss, "learning_rate": settings.learning_rate,
@@ -164,6 +169,7 @@ def main(parsed_arguments):
   if rank == 0:
     trainer.save_checkpoint(os.path.join(model_dir, "ckpt-%d.npz" % trainer.step_count))
   if world > 1:
+    comm.close()
     dist.barrier()
     dist.destroy_process_group()
   return 0

@@ -103,6 +103,10 @@ SIGNATURES = {
     "dd_post_kp_weights_bytes": (_sz, [_i, _i, _i]),
     "dd_post_kp_pack_weights": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "dd_post_kp_fwd": (_i, [_vp, _T, _vp, _T, _i, _i, _i, _T, _vp]),
+    "dd_comm_unique_id": (_i, [_vp]),
+    "dd_comm_init": (_i, [_vp, _vp, _i, _i, _P(_vp)]),
+    "dd_comm_allreduce_sum_f32": (_i, [_vp, _vp, _sz, _vp]),
+    "dd_comm_destroy": (_i, [_vp]),
     "dd_cast_copy": (_i, [_vp, _T, _T, _vp]),
     "dd_l2_flush": (_i, [_vp, _vp, _sz, _vp]),
 }
@@ -284,6 +288,33 @@ class Context:
   def l2_flush(self, scratch):
     self._check(self.lib.dd_l2_flush(self.handle, scratch.data_ptr(), scratch.numel() * scratch.element_size(),
                                      self._stream()))
+
+
+class Communicator:
+  """dd_comm over NCCL: the flat-gradient all-reduce of data-parallel training through the C ABI.  The unique id travels
+  over torch.distributed (any initialised backend) - plumbing only; the reduction itself is ncclAllReduce on the caller's
+  stream."""
+
+  def __init__(self, ctx, rank, world):
+    import torch.distributed as dist
+    self.ctx, self.rank, self.world = ctx, rank, world
+    ident = ctypes.create_string_buffer(128)
+    if rank == 0:
+      ctx._check(ctx.lib.dd_comm_unique_id(ident))
+    box = [bytes(ident.raw)]
+    dist.broadcast_object_list(box, src=0)
+    handle = ctypes.c_void_p()
+    ctx._check(ctx.lib.dd_comm_init(ctx.handle, box[0], rank, world, ctypes.byref(handle)))
+    self.handle = handle
+
+  def all_reduce_sum(self, tensor):
+    assert tensor.dtype == torch.float32 and tensor.is_cuda and tensor.is_contiguous()
+    self.ctx._check(self.ctx.lib.dd_comm_allreduce_sum_f32(self.handle, tensor.data_ptr(), tensor.numel(), Context._stream()))
+
+  def close(self):
+    if self.handle:
+      self.ctx.lib.dd_comm_destroy(self.handle)
+      self.handle = None
 
 
 def pack_post_kp_weights(w1, b1, w2, b2, ksize, features):

@@ -35,16 +35,20 @@ def _fp(t):
   return ctypes.c_void_p(t.data_ptr())
 
 
-def data_parallel_reduce(grad, loss, world_size):
+def data_parallel_reduce(grad, loss, world_size, comm=None):
   """The ONE exchange step of data-parallel training: every rank holds the gradient of the mean loss over ITS
   tiles in one flat fp32 buffer; the buffers (and the scalar loss, for logging) are summed over the ranks in place and the
   returned factor 1/world turns the sum into the gradient of the mean over the GLOBAL batch (Training.py:128 takes a mean).
   Backend-agnostic (NCCL on the GPUs, gloo in the CPU tests)."""
   if world_size <= 1:
     return 1.0
-  import torch.distributed as dist
-  dist.all_reduce(grad)                       # one flat bucket: 1.7 M floats for the U-Net (latency bound)
-  dist.all_reduce(loss)
+  if comm is not None:                         # libdd_b200's own NCCL communicator (dd_comm_allreduce_sum_f32)
+    comm.all_reduce_sum(grad)
+    comm.all_reduce_sum(loss)
+  else:
+    import torch.distributed as dist
+    dist.all_reduce(grad)                     # one flat bucket: 1.7 M floats for the U-Net (latency bound)
+    dist.all_reduce(loss)
   loss /= world_size
   return 1.0 / world_size
 
@@ -941,12 +945,12 @@ class Trainer:
     return self.grad
 
   # ------------------------------------------------------------------------------------------ one optimizer step
-  def train_step(self, features, targets_dict, world_size=1):
+  def train_step(self, features, targets_dict, world_size=1, comm=None):
     """forward + loss + backward + (all-reduce) + Adam.  Returns the loss as a device scalar."""
     self.forward(features)
     loss = self.loss_and_gradient(targets_dict)
     self.backward()
-    scale = data_parallel_reduce(self.grad, loss, world_size)
+    scale = data_parallel_reduce(self.grad, loss, world_size, comm)
     self.apply_gradients(scale)
     return loss
 

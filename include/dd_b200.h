@@ -315,6 +315,16 @@ int dd_augment_tiles(dd_ctx* ctx, const dd_tensor* x, int kind, const int32_t* f
 int dd_tiles_gather(dd_ctx* ctx, const dd_tensor* image, const int32_t* table_dev, const dd_tensor* tiles, void* stream);
 int dd_tiles_scatter(dd_ctx* ctx, const dd_tensor* tiles, const int32_t* table_dev, const dd_tensor* image, void* stream);
 
+/* ---- data-parallel exchange (NCCL over NVLink) --------------------------------------------------- */
+/* One process per GPU; rank 0 calls dd_comm_unique_id and hands the 128 bytes to every rank (any side channel), every rank
+ * calls dd_comm_init, then dd_comm_allreduce_sum_f32 sums the flat fp32 gradient buffer IN PLACE on `stream` (no host sync).
+ * NCCL is loaded at run time (libnccl.so.2); without it these calls return DD_ERR_UNSUPPORTED and nothing else is affected. */
+typedef struct dd_comm dd_comm;
+int dd_comm_unique_id(void* id128);
+int dd_comm_init(dd_ctx* ctx, const void* id128, int rank, int world, dd_comm** out);
+int dd_comm_allreduce_sum_f32(dd_comm* comm, float* buf_dev, size_t count, void* stream);
+int dd_comm_destroy(dd_comm* comm);
+
 /* ---- utilities ------------------------------------------------------------------------------ */
 /* dtype / channel-view conversion copy y = cast(x) (c channels). */
 int dd_cast_copy(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, void* stream);

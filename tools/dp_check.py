@@ -32,10 +32,14 @@ per = tiles // world
 shard = slice(rank * per, (rank + 1) * per)
 trainer = Trainer(Architecture(j, weights=weights, device=local), TrainingSettings())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-loss = trainer.train_step({k: v[shard] for k, v in feats.items()}, {k: v[shard] for k, v in targs.items()}, world_size=world)
+# the exchange goes through libdd_b200's own NCCL communicator (dd_comm_*); torch.distributed only carries the unique id
+from deepdenoiser_b200 import _lib  # noqa: E402
+comm = _lib.Communicator(trainer.ctx, rank, world)
+loss = trainer.train_step({k: v[shard] for k, v in feats.items()}, {k: v[shard] for k, v in targs.items()}, world_size=world,
+                          comm=comm)
 torch.cuda.synchronize()
 e0.record()
-dist.all_reduce(trainer.grad)
+comm.all_reduce_sum(trainer.grad)
 e1.record()
 torch.cuda.synchronize()
 if rank == 0:
@@ -44,6 +48,7 @@ if rank == 0:
   dw = float((single.theta - trainer.theta).abs().max())
   print(json.dumps({"ranks": world, "dp_loss": float(loss), "single_process_loss": float(full_loss),
                     "max_weight_difference_after_one_step": dw, "allreduce_ms_flat_grad": e0.elapsed_time(e1),
-                    "grad_elements": trainer.count, "ok": bool(dw < 2e-5 and abs(float(loss) - float(full_loss)) < 1e-4)}))
+                    "grad_elements": trainer.count, "exchange": "dd_comm_allreduce_sum_f32 (NCCL through the C ABI)", "ok": bool(dw < 2e-5 and abs(float(loss) - float(full_loss)) < 1e-4)}))
+comm.close()
 dist.barrier()
 dist.destroy_process_group()
