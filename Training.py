@@ -44,7 +44,7 @@ parser.add_argument("--steps_per_epoch", type=int, default=10)
 parser.add_argument("--checkpoint_steps", type=int, default=500)
 parser.add_argument("--write_synthetic_tfrecords", type=int, default=0,
                     help="Write this many synthetic tiles as <base_tfrecords_directory>/training (reference format) and use them.")
-parser.add_argument("--precision", default=None, choices=["float32", "float16"],
+parser.add_argument("--precision", default=None, choices=["float32", "float16", "bfloat16"],
                     help="float16 (default): tensor-core path (fp16 activations, fp32 master weights); float32: exact path.")
 
 

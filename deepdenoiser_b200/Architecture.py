@@ -15,7 +15,7 @@ graph.  Differences that are deliberate:
     are batched along N instead of being unrolled into T copies of the graph;
   * the device layout is always NHWC; `data_format` is accepted and stored for interface compatibility only
     (the reference transposes to NCHW for cuDNN, Conv2dUtilities.py:50-66 - pure HBM traffic here);
-  * an optional "b200" block in the JSON selects the arithmetic: {"dtype": "float16" | "float32", ...}.
+  * an optional "b200" block in the JSON selects the arithmetic: {"dtype": "float16" | "bfloat16" | "float32", ...}.
 There is no CPU fallback: predict() raises if the CUDA library or a B200 is missing.
 """
 import json
@@ -184,7 +184,7 @@ class Architecture:
                             core["number_of_convolutions_per_block"], self.number_of_input_channels,
                             self.number_of_output_channels, self.use_multiscale_predictions, embedding_shape)
     options = dict(parsed_json.get("b200", {}))
-    self.dtype = {"float16": torch.float16, "float32": torch.float32}[options.get("dtype", "float16")]
+    self.dtype = {"float16": torch.float16, "bfloat16": torch.bfloat16, "float32": torch.float32}[options.get("dtype", "float16")]
     self.logits_dtype = {"float16": torch.float16, "float32": torch.float32}[options.get("logits_dtype", "float32")]
     self.max_chunk_pixels = int(options.get("max_chunk_pixels", 16 * 1024 * 1024))
     self.weights = dict(weights) if weights is not None else self.spec.init_weights(seed)

@@ -9,7 +9,8 @@ import os
 
 import torch
 
-DD_F32, DD_F16 = 0, 1
+DD_F32, DD_F16, DD_BF16 = 0, 1, 2
+DD_PACK_BF16 = 16
 DD_CONV_RELU, DD_CONV_RELU_COPY, DD_CONV_RESIDUAL_MASK = 1, 2, 4
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdd_b200.so")
@@ -139,6 +140,8 @@ def _dtype_code(t):
     return DD_F32
   if t.dtype == torch.float16:
     return DD_F16
+  if t.dtype == torch.bfloat16:
+    return DD_BF16
   raise DDError("unsupported tensor dtype %s" % t.dtype)
 
 
@@ -202,7 +205,7 @@ class Context:
     w = w.detach().to(torch.float32).contiguous().cpu()
     ks = w.shape[0]
     cin, cout = (w.shape[3], w.shape[2]) if transposed else (w.shape[2], w.shape[3])
-    code = DD_F16 if dtype == torch.float16 else DD_F32
+    code = DD_F16 if dtype == torch.float16 else (DD_BF16 if dtype == torch.bfloat16 else DD_F32)
     nbytes = self.lib.dd_conv2d_packed_bytes(ks, cin, cout, code, int(transposed))
     packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
     self._check(self.lib.dd_conv2d_pack_weights(self.handle, w.data_ptr(), ks, cin, cout, code, int(transposed),

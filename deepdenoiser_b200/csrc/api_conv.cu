@@ -142,7 +142,8 @@ static int encode_out_map(dd_ctx* ctx, CUtensorMap* map, const dd_tensor* t, int
   cuuint32_t box[4] = {static_cast<cuuint32_t>(128 / es), 32, 1, 1};
   uint8_t* base = reinterpret_cast<uint8_t*>(t->ptr) +
                   ((static_cast<size_t>(ay) * t->w + ax) * t->cstride + t->coff + c_first) * es;
-  return encode_map(ctx, map, t->dtype == DD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base,
+  return encode_map(ctx, map, t->dtype == DD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 :
+                    (t->dtype == DD_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), base,
                     4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_NONE);
 }
 
@@ -150,11 +151,12 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
   const dd_tensor* x = L.x;
   const dd_tensor* y = L.y;
   DD_CHECK_ARG(ctx->encode_tiled, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
-  DD_CHECK_ARG(x->dtype == DD_F16, "tensor-core conv needs fp16 input");
+  DD_CHECK_ARG(is_half_type(x->dtype), "tensor-core conv needs fp16 / bf16 input");
+  DD_CHECK_ARG(y->dtype == DD_F32 || y->dtype == x->dtype, "tensor-core conv writes fp32 or the input's 16-bit type");
   DD_CHECK_ARG(x->coff % 8 == 0 && x->cstride % 8 == 0, "conv input view must be 16-byte aligned (coff %d cstride %d)",
                x->coff, x->cstride);
   DD_CHECK_ARG(L.cpad % 32 == 0 && L.cpad >= 32 && L.cpad <= 256, "accumulator block width %d unsupported", L.cpad);
-  const int align_out = (y->dtype == DD_F16) ? 8 : 4;
+  const int align_out = is_half_type(y->dtype) ? 8 : 4;
   DD_CHECK_ARG(y->coff % align_out == 0 && y->cstride % align_out == 0, "conv output view misaligned");
 
   ConvRowsParams p;
@@ -233,12 +235,13 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
   p.ngroups = L.ngroups; p.group_c = L.group_c; p.cout_store = L.cout; p.ups = L.ups;
   p.relu = (L.flags & DD_CONV_RELU) ? 1 : 0;
   p.out_f32 = (y->dtype == DD_F32);
+  p.bf16 = (x->dtype == DD_BF16);
   p.bias = L.bias; p.bias_count = L.bias_count;
   p.trace = ctx->conv_trace;
   if (L.residual) {
     DD_CHECK_ARG(L.ups == 1 && L.ngroups == 1, "residual needs a plain convolution");
-    DD_CHECK_ARG(L.residual->dtype == DD_F16 && L.residual->coff % 8 == 0 && L.residual->cstride % 8 == 0 &&
-                     L.cout % 8 == 0, "residual must be aligned fp16 with a multiple of 8 channels");
+    DD_CHECK_ARG(L.residual->dtype == x->dtype && L.residual->coff % 8 == 0 && L.residual->cstride % 8 == 0 &&
+                     L.cout % 8 == 0, "residual must be aligned, of the input's 16-bit type, with a multiple of 8 channels");
     p.residual = reinterpret_cast<const __half*>(L.residual->ptr);
     p.res_cstride = L.residual->cstride; p.res_coff = L.residual->coff;
     p.res_is_mask = (L.flags & DD_CONV_RESIDUAL_MASK) ? 1 : 0;
@@ -253,7 +256,7 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
                              static_cast<cuuint64_t>(x->h) * x->w * x->cstride * 2};
     cuuint32_t box[4] = {64, a_box_w, 1, 1};
     void* base = reinterpret_cast<__half*>(x->ptr) + x->coff;
-    int rc = encode_map(ctx, &maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, 4, dims, strides, box,
+    int rc = encode_map(ctx, &maps.a, x->dtype == DD_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, 4, dims, strides, box,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc) return rc;
   }
@@ -275,8 +278,8 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
     if (rc) return rc;
   }
   if (L.y_relu) {
-    DD_CHECK_ARG(L.y_relu->dtype == DD_F16 && L.y_relu->coff % 8 == 0 && L.y_relu->cstride % 8 == 0 && L.ngroups == 1,
-                 "relu-copy output must be aligned fp16");
+    DD_CHECK_ARG(L.y_relu->dtype == x->dtype && L.y_relu->coff % 8 == 0 && L.y_relu->cstride % 8 == 0 && L.ngroups == 1,
+                 "relu-copy output must be aligned and of the input's 16-bit type");
     p.has_relu_copy = 1;
     int rc = encode_out_map(ctx, &maps.out_relu, L.y_relu, 0, L.cout, x->h, x->w, L.ups, L.ups == 2 ? (L.sp0 >> 1) : 0,
                             L.ups == 2 ? (L.sp0 & 1) : 0);
@@ -379,7 +382,7 @@ int dd_ctx_set_option(dd_ctx* ctx, const char* name, int value) {
 
 size_t dd_conv2d_packed_bytes(int ksize, int cin, int cout, int dtype, int transposed) {
   const int k2 = ksize * ksize;
-  if (dtype == DD_F16) {
+  if (is_half_type(dtype)) {
     const int chunks = (round_up(cin, 16) + 63) / 64;
     const int rows = transposed ? k2 * packed_cpad(cout) : packed_cpad(cout);
     const int tiles = transposed ? 1 : k2;
@@ -397,9 +400,13 @@ int dd_conv2d_pack_weights(dd_ctx* ctx, const float* w, int ksize, int cin, int 
   const size_t bytes = dd_conv2d_packed_bytes(ksize, cin, cout, dtype, transposed);
   const int k2 = ksize * ksize;
   std::vector<uint8_t> host(bytes, 0);
-  if (dtype == DD_F16) {
+  if (is_half_type(dtype)) {
     const int cpad = packed_cpad(cout);
-    __half* dst = reinterpret_cast<__half*>(host.data());
+    uint16_t* dst = reinterpret_cast<uint16_t*>(host.data());
+    auto cvt = [dtype](float v) -> uint16_t {
+      if (dtype == DD_BF16) { const __nv_bfloat16 b = __float2bfloat16_rn(v); return *reinterpret_cast<const uint16_t*>(&b); }
+      const __half h = __float2half_rn(v); return *reinterpret_cast<const uint16_t*>(&h);
+    };
     if (!transposed) {
       // TF [kh,kw,cin,cout] -> [chunk][s][r][cpad][64]   (tap (r,s): r = row offset, s = column offset)
       for (int r = 0; r < ksize; ++r)
@@ -408,7 +415,7 @@ int dd_conv2d_pack_weights(dd_ctx* ctx, const float* w, int ksize, int cin, int 
             for (int o = 0; o < cout; ++o) {
               const size_t tile = static_cast<size_t>(c / 64) * ksize + s;
               dst[((tile * ksize + r) * cpad + o) * 64 + (c % 64)] =
-                  __float2half_rn(w[(static_cast<size_t>(r * ksize + s) * cin + c) * cout + o]);
+                  cvt(w[(static_cast<size_t>(r * ksize + s) * cin + c) * cout + o]);
             }
     } else {
       // TF transpose layout [kh,kw,cout,cin] -> [chunk][sub-pixel][cpad][64]: one 1x1 GEMM, rows (sub-pixel, cout)
@@ -416,7 +423,7 @@ int dd_conv2d_pack_weights(dd_ctx* ctx, const float* w, int ksize, int cin, int 
         for (int o = 0; o < cout; ++o)
           for (int c = 0; c < cin; ++c)
             dst[((static_cast<size_t>(c / 64) * k2 + sp) * cpad + o) * 64 + (c % 64)] =
-                __float2half_rn(w[(static_cast<size_t>(sp) * cout + o) * cin + c]);
+                cvt(w[(static_cast<size_t>(sp) * cout + o) * cin + c]);
     }
   } else {
     float* dst = reinterpret_cast<float*>(host.data());
@@ -443,7 +450,7 @@ int dd_conv2d_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const f
   DD_CHECK_ARG(!residual || (tensor_ok(residual) && residual->c == y->c), "bad residual");
   DD_CHECK_ARG(!y_relu || (tensor_ok(y_relu) && y_relu->c == y->c), "bad y_relu");
   DD_CHECK_ARG(((flags & DD_CONV_RELU_COPY) != 0) == (y_relu != nullptr), "DD_CONV_RELU_COPY needs y_relu");
-  DD_CHECK_ARG(!(flags & DD_CONV_RESIDUAL_MASK) || (residual && x->dtype == DD_F16), "DD_CONV_RESIDUAL_MASK: fp16 path with a mask tensor");
+  DD_CHECK_ARG(!(flags & DD_CONV_RESIDUAL_MASK) || (residual && is_half_type(x->dtype)), "DD_CONV_RESIDUAL_MASK: 16-bit path with a mask tensor");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (x->dtype == DD_F32) {
     DD_CHECK_ARG(y->dtype == DD_F32, "exact path writes fp32");

@@ -438,6 +438,7 @@ int dd_kernel_predict_fwd(dd_ctx* ctx, const dd_tensor* src, const dd_tensor* lo
   const int TWs = kKpTileW + 2 * pad, THs = kKpTileH + 2 * pad;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int k2 = ksize * ksize;
+  DD_CHECK_ARG(logits->dtype == DD_F32 || logits->dtype == DD_F16, "kernel_predict: logits must be fp32 or fp16");
   const bool half = logits->dtype == DD_F16;
   const size_t es = elem_size(logits->dtype);
   const bool tma_ok = ctx->encode_tiled && (reinterpret_cast<uintptr_t>(logits->ptr) % 16 == 0) &&

@@ -70,33 +70,29 @@ __global__ void __launch_bounds__(256) ewise_vec_kernel(const Ewise p) {
   if (idx >= total) return;
   const int g = static_cast<int>(idx % G);
   const size_t pix = idx / G;
-  auto at = [&](const View& v) { return reinterpret_cast<__half*>(v.ptr) + pix * v.cstride + v.coff + g * 8; };
-  const uint4 av = *reinterpret_cast<const uint4*>(at(p.a));
-  const __half2* ah = reinterpret_cast<const __half2*>(&av);
-  uint4 ov;
-  __half2* oh = reinterpret_cast<__half2*>(&ov);
+  auto at = [&](const View& v) { return reinterpret_cast<uint16_t*>(v.ptr) + pix * v.cstride + v.coff + g * 8; };
+  float a[8], o[8];
+  unpack8(*reinterpret_cast<const uint4*>(at(p.a)), p.a.bf16, a);
   if (p.op == EW_AXPY) {
-    ov = *reinterpret_cast<const uint4*>(at(p.out));
+    unpack8(*reinterpret_cast<const uint4*>(at(p.out)), p.out.bf16, o);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 a = __half22float2(ah[i]), o = __half22float2(oh[i]);
-      oh[i] = __floats2half2_rn(fmaf(p.alpha, a.x, o.x), fmaf(p.alpha, a.y, o.y));
-    }
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(p.alpha, a[i], o[i]);
   } else {
-    const uint4 bv = *reinterpret_cast<const uint4*>(at(p.b));
-    const __half2* bh = reinterpret_cast<const __half2*>(&bv);
-    if (p.op == EW_RELU_MASK_ACC) ov = *reinterpret_cast<const uint4*>(at(p.out));
-    else ov = make_uint4(0, 0, 0, 0);
+    float b[8];
+    unpack8(*reinterpret_cast<const uint4*>(at(p.b)), p.b.bf16, b);
+    if (p.op == EW_RELU_MASK_ACC) {
+      unpack8(*reinterpret_cast<const uint4*>(at(p.out)), p.out.bf16, o);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 a = __half22float2(ah[i]), b = __half22float2(bh[i]), o = __half22float2(oh[i]);
-      oh[i] = __floats2half2_rn(b.x > 0.f ? o.x + a.x : o.x, b.y > 0.f ? o.y + a.y : o.y);
+      for (int i = 0; i < 8; ++i) o[i] = 0.f;
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = (b[i] > 0.f) ? o[i] + a[i] : o[i];
   }
-  *reinterpret_cast<uint4*>(at(p.out)) = ov;
+  *reinterpret_cast<uint4*>(at(p.out)) = pack8(o, p.out.bf16);
 }
 
-inline bool vec_ok(const View& v) { return v.f16 && v.c % 8 == 0 && v.coff % 8 == 0 && v.cstride % 8 == 0; }
+inline bool vec_ok(const View& v) { return vec16_ok(v); }
 // launches the vectorised kernel when every operand allows it; returns false otherwise
 inline bool try_ewise_vec(const Ewise& p, bool uses_b, cudaStream_t s) {
   if (!(vec_ok(p.a) && vec_ok(p.out) && (!uses_b || vec_ok(p.b)))) return false;

@@ -49,6 +49,7 @@ struct WgrParams {
   int layout;                // 0: [tap][cin][cout]   1: [tap][cout][cin]
   float scale;
   int variant;               // debug: bit0 swaps the LBO / SBO fields of the descriptors
+  int bf16;                  // operands are bfloat16
 };
 
 struct WgrSegment { int n, x0, y0, y1; };
@@ -169,7 +170,7 @@ wgrad_rows_kernel(const __grid_constant__ WgrMaps maps, const WgrParams p) {
     if (elect_one() && has_work) {
       const bool swap = (p.variant & 1) != 0;
       const uint32_t n_cols = p.k3 ? 192u : 64u;
-      const uint32_t idesc = make_idesc_f16(128, static_cast<int>(n_cols)) | (1u << 15) | (1u << 16);   // A, B MN-major
+      const uint32_t idesc = make_idesc_f16(128, static_cast<int>(n_cols)) | (1u << 15) | (1u << 16) | (p.bf16 ? kIdescBf16 : 0u);   // A, B MN-major
       const uint32_t x_base = smem_u32(x_smem), dz_base = smem_u32(dz_smem);
       const uint64_t a_tmpl = swap ? make_desc_mn_sw128(0, 1024, p.dz_slot_bytes) : make_desc_mn_sw128(0, p.dz_slot_bytes, 1024);
       const uint64_t b_tmpl = swap ? make_desc_mn_sw128(0, 1024, 128) : make_desc_mn_sw128(0, 128, 1024);
@@ -276,7 +277,8 @@ static int encode_nhwc_f16(dd_ctx* ctx, CUtensorMap* map, const dd_tensor* t, ui
   cuuint32_t estr[4] = {1, 1, 1, 1};
   void* base = reinterpret_cast<__half*>(t->ptr) + t->coff;
   CUresult r = reinterpret_cast<WgEncodeTiledFn>(ctx->encode_tiled)(
-      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      map, t->dtype == DD_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE,
       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("wgrad: cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
@@ -289,7 +291,7 @@ static int encode_nhwc_f16(dd_ctx* ctx, CUtensorMap* map, const dd_tensor* t, ui
 int launch_wgrad_rows(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int ksize, int layout, float* dw, float scale,
                       cudaStream_t stream) {
   DD_CHECK_ARG(ctx->encode_tiled, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
-  DD_CHECK_ARG(x->dtype == DD_F16 && dz->dtype == DD_F16, "tensor-core wgrad needs fp16 operands");
+  DD_CHECK_ARG(is_half_type(x->dtype) && dz->dtype == x->dtype, "tensor-core wgrad needs two fp16 or two bf16 operands");
   DD_CHECK_ARG(x->coff % 8 == 0 && x->cstride % 8 == 0 && dz->coff % 8 == 0 && dz->cstride % 8 == 0,
                "wgrad operand views must be 16-byte aligned");
   DD_CHECK_ARG(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
@@ -319,7 +321,7 @@ int launch_wgrad_rows(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int 
   p.bar_off = p.dz_off + static_cast<uint32_t>(p.rz + 1) * p.dz_slot_bytes;
   const size_t smem = 1024 + p.bar_off + 512;
   DD_CHECK_ARG(smem <= ctx->max_smem_optin, "wgrad: shared memory plan does not fit");
-  p.dw = dw; p.layout = layout; p.scale = scale; p.variant = ctx->wgrad_variant;
+  p.dw = dw; p.layout = layout; p.scale = scale; p.variant = ctx->wgrad_variant; p.bf16 = (x->dtype == DD_BF16);
   WgrMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc = encode_nhwc_f16(ctx, &maps.x, x, box_w);
@@ -337,7 +339,11 @@ int launch_wgrad_rows(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int 
 // is the host-side twin).  mode 0: forward of TF [k,k,cin,cout];  mode 1: input-gradient convolution of the same layer
 // (taps flipped, channels swapped: a conv with cin' = cout, cout' = cin);  mode 2: transposed 2x2, TF [2,2,cout,cin] ->
 // [chunk][sub-pixel][cpad][64].  The destination's padding must have been zeroed once.
-struct PackParams { const float* w; __half* dst; int ksize, cin, cout, cpad, mode; };
+struct PackParams { const float* w; uint16_t* dst; int ksize, cin, cout, cpad, mode, bf16; };
+__device__ __forceinline__ uint16_t pack_cvt(float v, int bf16) {
+  if (bf16) return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  return __half_as_ushort(__float2half_rn(v));
+}
 __global__ void __launch_bounds__(256) pack_f16_kernel(const PackParams p) {
   const int k = p.ksize, k2 = k * k;
   const size_t total = static_cast<size_t>(k2) * p.cin * p.cout;
@@ -346,7 +352,7 @@ __global__ void __launch_bounds__(256) pack_f16_kernel(const PackParams p) {
   const float v = p.w[idx];
   if (p.mode == 2) {           // idx = (sp * cout + o) * cin + c
     const int c = static_cast<int>(idx % p.cin), o = static_cast<int>((idx / p.cin) % p.cout), sp = static_cast<int>(idx / (static_cast<size_t>(p.cin) * p.cout));
-    p.dst[((static_cast<size_t>(c / 64) * k2 + sp) * p.cpad + o) * 64 + (c % 64)] = __float2half_rn(v);
+    p.dst[((static_cast<size_t>(c / 64) * k2 + sp) * p.cpad + o) * 64 + (c % 64)] = pack_cvt(v, p.bf16);
     return;
   }
   // idx = ((r * k + s) * cin + c) * cout + o
@@ -354,10 +360,10 @@ __global__ void __launch_bounds__(256) pack_f16_kernel(const PackParams p) {
   const int tap = static_cast<int>(idx / (static_cast<size_t>(p.cin) * p.cout));
   const int r = tap / k, s = tap % k;
   if (p.mode == 0) {
-    p.dst[(((static_cast<size_t>(c / 64) * k + s) * k + r) * p.cpad + o) * 64 + (c % 64)] = __float2half_rn(v);
+    p.dst[(((static_cast<size_t>(c / 64) * k + s) * k + r) * p.cpad + o) * 64 + (c % 64)] = pack_cvt(v, p.bf16);
   } else {
     const int rr = k - 1 - r, ss = k - 1 - s;
-    p.dst[(((static_cast<size_t>(o / 64) * k + ss) * k + rr) * p.cpad + c) * 64 + (o % 64)] = __float2half_rn(v);
+    p.dst[(((static_cast<size_t>(o / 64) * k + ss) * k + rr) * p.cpad + c) * 64 + (o % 64)] = pack_cvt(v, p.bf16);
   }
 }
 
@@ -401,27 +407,21 @@ __global__ void __launch_bounds__(256) relu_bias_vec_kernel(const ReluBiasParams
   const int g = static_cast<int>(idx % G);
   for (; idx < total; idx += stride) {
     const size_t pix = idx / G;
-    uint4 d = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.dy.ptr) + pix * p.dy.cstride + p.dy.coff + g * 8);
-    __half2* dh = reinterpret_cast<__half2*>(&d);
+    float d[8];
+    unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.dy.ptr) + pix * p.dy.cstride + p.dy.coff + g * 8), p.dy.bf16, d);
     if (p.has_y) {
-      const uint4 yv = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.y.ptr) + pix * p.y.cstride + p.y.coff + g * 8);
-      const __half2* yh = reinterpret_cast<const __half2*>(&yv);
+      float yv[8];
+      unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.y.ptr) + pix * p.y.cstride + p.y.coff + g * 8), p.y.bf16, yv);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 yf = __half22float2(yh[i]);
-        float2 df = __half22float2(dh[i]);
-        if (!(yf.x > 0.f)) df.x = 0.f;
-        if (!(yf.y > 0.f)) df.y = 0.f;
-        dh[i] = __floats2half2_rn(df.x, df.y);
-      }
+      for (int i = 0; i < 8; ++i) if (!(yv[i] > 0.f)) d[i] = 0.f;
     }
-    if (p.has_dz)
-      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.dz.ptr) + pix * p.dz.cstride + p.dz.coff + g * 8) = d;
+    if (p.has_dz) {
+      const uint4 packed = pack8(d, p.dz.bf16);
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dz.ptr) + pix * p.dz.cstride + p.dz.coff + g * 8) = packed;
+      if (p.has_y) unpack8(packed, p.dz.bf16, d);      // the bias gradient sums what was stored (rounded values)
+    }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 df = __half22float2(dh[i]);
-      acc[2 * i] += df.x; acc[2 * i + 1] += df.y;
-    }
+    for (int i = 0; i < 8; ++i) acc[i] += d[i];
   }
   if (p.db) {
 #pragma unroll
@@ -468,21 +468,16 @@ __global__ void __launch_bounds__(256) s2d_mask_vec_kernel(const S2dParams p) {
   const int j = static_cast<int>(opix % p.out.w), i = static_cast<int>((opix / p.out.w) % p.out.h);
   const int n = static_cast<int>(opix / (static_cast<size_t>(p.out.w) * p.out.h));
   const size_t ipix = p.dy.pix(n, 2 * i + (sp >> 1), 2 * j + (sp & 1));
-  uint4 d = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.dy.ptr) + ipix * p.dy.cstride + p.dy.coff + g * 8);
+  uint4 d = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.dy.ptr) + ipix * p.dy.cstride + p.dy.coff + g * 8);
   if (p.has_y) {
-    const uint4 yv = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.y.ptr) + ipix * p.y.cstride + p.y.coff + g * 8);
-    const __half2* yh = reinterpret_cast<const __half2*>(&yv);
-    __half2* dh = reinterpret_cast<__half2*>(&d);
+    float dv[8], yv[8];
+    unpack8(d, p.dy.bf16, dv);
+    unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.y.ptr) + ipix * p.y.cstride + p.y.coff + g * 8), p.y.bf16, yv);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 yf = __half22float2(yh[e]);
-      float2 df = __half22float2(dh[e]);
-      if (!(yf.x > 0.f)) df.x = 0.f;
-      if (!(yf.y > 0.f)) df.y = 0.f;
-      dh[e] = __floats2half2_rn(df.x, df.y);
-    }
+    for (int i = 0; i < 8; ++i) if (!(yv[i] > 0.f)) dv[i] = 0.f;
+    d = pack8(dv, p.dy.bf16);
   }
-  *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out.ptr) + opix * p.out.cstride + p.out.coff + sp * C + g * 8) = d;
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out.ptr) + opix * p.out.cstride + p.out.coff + sp * C + g * 8) = d;
 }
 
 }  // namespace dd
@@ -502,10 +497,12 @@ int dd_conv2d_wgrad_tc(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int
 int dd_conv2d_pack_weights_dev(dd_ctx* ctx, const float* w_dev, int ksize, int cin, int cout, int mode, void* packed_dev,
                                void* stream) {
   DD_CHECK_ARG(ctx && w_dev && packed_dev && cin > 0 && cout > 0, "bad argument");
+  const int bf16 = (mode & DD_PACK_BF16) ? 1 : 0;
+  mode &= ~DD_PACK_BF16;
   DD_CHECK_ARG(mode >= 0 && mode <= 2, "mode must be 0 (forward), 1 (input gradient) or 2 (transposed 2x2)");
   DD_CHECK_ARG(mode == 2 ? ksize == 2 : (ksize == 1 || ksize == 3), "bad kernel size for this mode");
   PackParams p;
-  p.w = w_dev; p.dst = reinterpret_cast<__half*>(packed_dev); p.ksize = ksize; p.cin = cin; p.cout = cout; p.mode = mode;
+  p.w = w_dev; p.dst = reinterpret_cast<uint16_t*>(packed_dev); p.ksize = ksize; p.cin = cin; p.cout = cout; p.mode = mode; p.bf16 = bf16;
   p.cpad = round_up(mode == 1 ? cin : cout, 32);
   const size_t total = static_cast<size_t>(ksize) * ksize * cin * cout;
   pack_f16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
@@ -522,8 +519,8 @@ int dd_space_to_depth2_mask(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y
   p.dy = make_view(dy); p.out = make_view(out); p.has_y = y ? 1 : 0;
   p.y = y ? make_view(y) : p.dy;
   const size_t total = static_cast<size_t>(out->n) * out->h * out->w * out->c;
-  auto aligned = [](const dd_tensor* t) { return t->dtype == DD_F16 && t->c % 8 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0; };
-  if (aligned(dy) && aligned(out) && (!y || aligned(y)))
+  auto aligned = [](const dd_tensor* t) { return is_half_type(t->dtype) && t->c % 8 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0; };
+  if (aligned(dy) && aligned(out) && dy->dtype == out->dtype && (!y || aligned(y)))
     s2d_mask_vec_kernel<<<static_cast<unsigned>((total / 8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   else
     s2d_mask_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
@@ -540,7 +537,7 @@ int dd_relu_bwd_bias(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const
   ReluBiasParams p;
   p.dy = make_view(dy); p.y = y ? make_view(y) : p.dy; p.dz = dz ? make_view(dz) : p.dy;
   p.db = db_dev; p.has_y = y ? 1 : 0; p.has_dz = dz ? 1 : 0; p.scale = scale;
-  auto aligned = [](const dd_tensor* t) { return t->dtype == DD_F16 && t->c % 8 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0; };
+  auto aligned = [](const dd_tensor* t) { return is_half_type(t->dtype) && t->c % 8 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0; };
   const bool vec = aligned(dy) && (!y || aligned(y)) && (!dz || aligned(dz));
   const int per = vec ? dy->c / 8 : dy->c;                       // grid stride must be a multiple of this
   const size_t total = static_cast<size_t>(dy->n) * dy->h * dy->w * per;

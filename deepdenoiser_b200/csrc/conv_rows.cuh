@@ -68,6 +68,7 @@ struct ConvRowsParams {
   // epilogue
   int ngroups, group_c, cout_store, ups;
   int relu, out_f32, has_relu_copy;
+  int bf16;               // 16-bit tensors are bfloat16 (operands, 16-bit outputs, residual / mask)
   int bias_count;
   const float* bias;
   const __half* residual;
@@ -237,6 +238,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
       const uint32_t s_off0 = static_cast<uint32_t>(p.s_list[0]) * 8u, s_off1 = static_cast<uint32_t>(p.s_list[1]) * 8u,
                      s_off2 = static_cast<uint32_t>(p.s_list[2]) * 8u;                   // shifts in descriptor units
 
+      const uint32_t fmt = p.bf16 ? kIdescBf16 : 0u;
       auto build_plan = [&](uint4* row_plan, int blk, uint32_t use, int r_lo, int r_hi) {
         const bool ft = (r_lo == rm_lo);   // this input row initialises the accumulator of the row served by tap r_lo
         int n_norm = 0, n_first = 0;
@@ -245,19 +247,19 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
           int cnt = r_hi - r + 1;
           if (bk + cnt > ring) cnt = ring - bk;
           if (cnt > p.max_stack) cnt = p.max_stack;
-          row_plan[1 + n_norm++] = make_uint4(static_cast<uint32_t>(bk * p.cpad), make_idesc_f16(kRowsTileW, cnt * p.cpad),
+          row_plan[1 + n_norm++] = make_uint4(static_cast<uint32_t>(bk * p.cpad), make_idesc_f16(kRowsTileW, cnt * p.cpad) | fmt,
                                               static_cast<uint32_t>((r - rm_lo) * p.cpad) * 8u, 1u);
           r += cnt; bk += cnt; if (bk >= ring) bk -= ring;
         }
         if (ft) {
-          row_plan[4 + n_first++] = make_uint4(static_cast<uint32_t>(blk * p.cpad), make_idesc_f16(kRowsTileW, p.cpad),
+          row_plan[4 + n_first++] = make_uint4(static_cast<uint32_t>(blk * p.cpad), make_idesc_f16(kRowsTileW, p.cpad) | fmt,
                                                static_cast<uint32_t>((r_lo - rm_lo) * p.cpad) * 8u, 0u);
           r = r_lo + 1; bk = blk + 1; if (bk >= ring) bk -= ring;
           while (r <= r_hi) {
             int cnt = r_hi - r + 1;
             if (bk + cnt > ring) cnt = ring - bk;
             if (cnt > p.max_stack) cnt = p.max_stack;
-            row_plan[4 + n_first++] = make_uint4(static_cast<uint32_t>(bk * p.cpad), make_idesc_f16(kRowsTileW, cnt * p.cpad),
+            row_plan[4 + n_first++] = make_uint4(static_cast<uint32_t>(bk * p.cpad), make_idesc_f16(kRowsTileW, cnt * p.cpad) | fmt,
                                                  static_cast<uint32_t>((r - rm_lo) * p.cpad) * 8u, 1u);
             r += cnt; bk += cnt; if (bk >= ring) bk -= ring;
           }
@@ -538,9 +540,10 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const __half2* rh = reinterpret_cast<const __half2*>(&rv[i]);
+                  const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv[i]);
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    const float2 r2 = __half22float2(rh[e]);
+                    const float2 r2 = p.bf16 ? __bfloat1622float2(rb[e]) : __half22float2(rh[e]);
                     if (p.res_is_mask) {      // backward of a ReLU fused into the input-gradient conv: y = conv(x) * [mask > 0]
                       if (!(r2.x > 0.f)) f[i * 8 + 2 * e] = 0.f;
                       if (!(r2.y > 0.f)) f[i * 8 + 2 * e + 1] = 0.f;
@@ -569,8 +572,14 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   uint4 pk; __half2* ph = reinterpret_cast<__half2*>(&pk);
+                  __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
+                  if (p.bf16) {
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) ph[e] = __floats2half2_rn(f[i * 8 + 2 * e], f[i * 8 + 2 * e + 1]);
+                    for (int e = 0; e < 4; ++e) pb[e] = __floats2bfloat162_rn(f[i * 8 + 2 * e], f[i * 8 + 2 * e + 1]);
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) ph[e] = __floats2half2_rn(f[i * 8 + 2 * e], f[i * 8 + 2 * e + 1]);
+                  }
                   *reinterpret_cast<uint4*>(row + (((sub * 4 + i) ^ (lane & 7)) << 4)) = pk;
                 }
                 if (sub == 1 || cb + 32 >= p.cout_store) end_rows(omap, cb & ~63);

@@ -3,6 +3,7 @@
 // Everything here is device-only and header-only.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
 
@@ -184,6 +185,8 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t bas
 // Instruction descriptor for kind::f16, fp16 A/B (K-major both), fp32 accumulate.
 //   [4,6) D format (1 = f32)  [7,10) A format (0 = f16)  [10,13) B format (0 = f16)
 //   [15] A major (0 = K)      [16] B major (0 = K)        [17,23) N >> 3   [24,29) M >> 4
+// kind::f16 covers fp16 (A/B format 0) and bfloat16 (format 1) operands
+constexpr uint32_t kIdescBf16 = (1u << 7) | (1u << 10);
 __host__ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
   uint32_t d = 0;
   d |= 1u << 4;

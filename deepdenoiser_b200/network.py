@@ -254,16 +254,18 @@ class DeviceNetwork:
   """Weights of a NetworkSpec packed on one GPU + the forward executor."""
 
   def __init__(self, ctx, spec, weights, dtype=torch.float16, logits_dtype=torch.float32):
-    assert dtype in (torch.float16, torch.float32)
+    assert dtype in (torch.float16, torch.bfloat16, torch.float32)
     self.ctx, self.spec, self.dtype = ctx, spec, dtype
+    # bfloat16 storage runs the same tensor-core kernels (kind::f16 with bf16 operands); the fused compose / output-head
+    # kernels are fp16 mma.sync code, so bf16 uses the layer-by-layer launches there
     self.logits_dtype = logits_dtype if dtype == torch.float16 else torch.float32
     self.fused_compose = True   # tests flip this to compare against the layer-by-layer path
     self.fused_post_kp = True   # likewise: 1x1 post-processing + kernel-prediction apply in one kernel
-    self.align = 8 if dtype == torch.float16 else 1
-    if dtype == torch.float16:
+    self.align = 8 if dtype in (torch.float16, torch.bfloat16) else 1
+    if dtype in (torch.float16, torch.bfloat16):
       for f in spec.filters:
         if f % 8:
-          raise _lib.DDError("float16 path needs filter counts that are multiples of 8 (got %s)" % spec.filters)
+          raise _lib.DDError("the 16-bit paths need filter counts that are multiples of 8 (got %s)" % spec.filters)
     self._buffers = {}
     self.load_weights(weights)
 

@@ -6,7 +6,7 @@ all-reduce of the flat gradient buffer per step.
 Two arithmetic modes:
   * precision="float32": the EXACT path (CUDA-core convolutions), U-Net and Tiramisu backbones; every gradient is
     parity-tested against torch-autograd of the oracle to 1e-6 (tests/test_gpu_training.py).
-  * precision="float16": the TENSOR-CORE path (U-Net): fp16 activations and activation gradients, fp32 master weights /
+  * precision="float16" | "bfloat16": the TENSOR-CORE path: 16-bit activations and activation gradients, fp32 master weights /
     gradients / Adam state, fp32 image-level arithmetic (kernel-prediction apply, composition blend, loss).  Forward and
     input gradients run on conv_rows_kernel (the input gradient of a 3x3 conv is the conv of dz with flipped, channel-
     swapped weights), weight gradients on wgrad_rows_kernel (tcgen05, MN-major), the 2x2 transposed conv's backward as
@@ -89,11 +89,12 @@ class Trainer:
 
   def __init__(self, architecture, settings=None, precision="float32", loss_scale=None):
     assert isinstance(architecture, Architecture)
-    assert precision in ("float32", "float16"), precision
+    assert precision in ("float32", "float16", "bfloat16"), precision
     self.arch = architecture
     self.settings = settings or TrainingSettings()
-    self.mixed = (precision == "float16")
-    self.act_dtype = torch.float16 if self.mixed else torch.float32
+    self.mixed = precision in ("float16", "bfloat16")
+    self.act_dtype = {"float32": torch.float32, "float16": torch.float16, "bfloat16": torch.bfloat16}[precision]
+    self.pack_flag = _lib.DD_PACK_BF16 if precision == "bfloat16" else 0
     self.loss_scale = loss_scale                  # None: chosen per batch (N*H*W/8) in mixed mode, 1 in exact mode
     architecture.dtype = torch.float32            # the Architecture's own (inference) network is not used for training
     architecture.logits_dtype = torch.float32
@@ -110,7 +111,7 @@ class Trainer:
     self.count = n
     if self.mixed:
       if any(f % 8 for f in self.spec.filters):
-        raise _lib.DDError("float16 training needs filter counts that are multiples of 8")
+        raise _lib.DDError("16-bit training needs filter counts that are multiples of 8")
     # + slack: the tensor-core conv reads biases in groups of 16 floats
     self.theta = torch.zeros(n + 64, dtype=torch.float32, device=self.dev)
     self.grad = torch.zeros_like(self.theta)
@@ -218,11 +219,11 @@ class Trainer:
         self._packed_store[var.name] = store
       f, b = store
       if var.transposed:
-        ctx.call("dd_conv2d_pack_weights_dev", _fp(w), 2, var.cin, var.cout, 2, _fp(f))
-        ctx.call("dd_conv2d_pack_weights_dev", _fp(w), 1, 4 * var.cout, var.cin, 0, _fp(b))
+        ctx.call("dd_conv2d_pack_weights_dev", _fp(w), 2, var.cin, var.cout, 2 | self.pack_flag, _fp(f))
+        ctx.call("dd_conv2d_pack_weights_dev", _fp(w), 1, 4 * var.cout, var.cin, 0 | self.pack_flag, _fp(b))
       else:
-        ctx.call("dd_conv2d_pack_weights_dev", _fp(w), var.ksize, var.cin, var.cout, 0, _fp(f))
-        ctx.call("dd_conv2d_pack_weights_dev", _fp(w), var.ksize, var.cin, var.cout, 1, _fp(b))
+        ctx.call("dd_conv2d_pack_weights_dev", _fp(w), var.ksize, var.cin, var.cout, 0 | self.pack_flag, _fp(f))
+        ctx.call("dd_conv2d_pack_weights_dev", _fp(w), var.ksize, var.cin, var.cout, 1 | self.pack_flag, _fp(b))
       self.fwd[var.name], self.bwd[var.name] = f, b
     if self.spec.compose:
       head, tail = self.spec.compose[0], self.spec.compose[-1]
@@ -256,13 +257,13 @@ class Trainer:
             r, c = py - 2 * dy, px - 2 * dx
             if r <= 2 and c <= 2:
               ph[dy + 1, dx + 1] = k[r, c].t()
-        ctx.call("dd_conv2d_pack_weights_dev", _fp(ph), 3, cin, cout, 0, _fp(phases[py * 2 + px]))
+        ctx.call("dd_conv2d_pack_weights_dev", _fp(ph), 3, cin, cout, 0 | self.pack_flag, _fp(phases[py * 2 + px]))
     wc = torch.zeros(3, 3, 4 * cout, cin, dtype=torch.float32, device=self.dev)
     for r in range(3):
       for c in range(3):
         sp = 2 * (r % 2) + (c % 2)
         wc[1 + r // 2, 1 + c // 2, sp * cout:(sp + 1) * cout] = k[r, c]
-    ctx.call("dd_conv2d_pack_weights_dev", _fp(wc), 3, 4 * cout, cin, 0, _fp(bwd))
+    ctx.call("dd_conv2d_pack_weights_dev", _fp(wc), 3, 4 * cout, cin, 0 | self.pack_flag, _fp(bwd))
     self.fwd[var.name], self.bwd[var.name] = phases, bwd
 
   # ------------------------------------------------------------------------------------------ helpers
@@ -758,7 +759,7 @@ class Trainer:
     n, h, w, n_scales = st["n"], st["h"], st["w"], st["n_scales"]
     kind = LOSS_KINDS[cfg.loss_difference]
     # static loss scale of the fp16 path: the per-pixel gradient of a mean over N*H*W pixels would underflow fp16
-    S = float(self.loss_scale) if self.loss_scale is not None else (n * h * w / 8.0 if self.mixed else 1.0)
+    S = float(self.loss_scale) if self.loss_scale is not None else (n * h * w / 8.0 if self.act_dtype == torch.float16 else 1.0)
     self._scale_used = S
     loss_scales = n_scales if cfg.use_multiscale_loss else 1
     norm = 1.0 / sum(1.0 / 4.0 ** s for s in range(loss_scales))

@@ -36,7 +36,7 @@ typedef enum dd_status {
   DD_ERR_NO_DEVICE = -4
 } dd_status;
 
-typedef enum dd_dtype { DD_F32 = 0, DD_F16 = 1 } dd_dtype;
+typedef enum dd_dtype { DD_F32 = 0, DD_F16 = 1, DD_BF16 = 2 } dd_dtype;   /* 16-bit types: storage only, fp32 accumulation */
 
 typedef struct dd_tensor {
   void* ptr;
@@ -252,7 +252,9 @@ int dd_conv2d_wgrad_tc(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int
 /* Device-side (re)pack of fp32 master weights into the fp16 layout of dd_conv2d_fwd after every optimizer step.
  * mode 0: forward, w_dev TF [k,k,cin,cout];  mode 1: the input-gradient convolution of that layer (flipped taps, swapped
  * channels; run it with dd_conv2d_fwd on dz);  mode 2: dd_conv2d_transpose2x2_fwd, w_dev TF [2,2,cout,cin].
+ * mode | DD_PACK_BF16 writes bfloat16 instead of fp16.
  * packed_dev: dd_conv2d_packed_bytes() bytes (mode 1: of the swapped shape), zeroed once by the caller. */
+#define DD_PACK_BF16 16
 int dd_conv2d_pack_weights_dev(dd_ctx* ctx, const float* w_dev, int ksize, int cin, int cout, int mode, void* packed_dev,
                                void* stream);
 /* out[n,i,j,sp*C+c] = dy[n,2i+ay,2j+ax,c] * [y[same] > 0] (y may be NULL), sp = 2*ay+ax: turns the backward of the

@@ -221,3 +221,43 @@ def test_kernel_predict_bwd_matches_autograd(ctx, k, features, ipt, h, w, ldtype
   loss.backward()
   tol = 2e-3 if ldtype == torch.float16 else 2e-5
   assert rel_err(dl.float()[..., :features * k2], lg.grad) <= tol
+
+
+# ------------------------------------------------------------------------------------------------ bfloat16 storage
+def test_conv_and_wgrad_bfloat16(ctx):
+  """The tensor-core kernels with bf16 operands (kind::f16, A/B format 1): forward conv, input gradient with fused ReLU mask
+  and weight gradient against torch on the same bf16-rounded operands."""
+  n, h, w, cin, cout = 1, 12, 140, 64, 96
+  g = torch.Generator(device="cuda").manual_seed(3)
+  x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+  wt = torch.randn(3, 3, cin, cout, device="cuda", generator=g) * 0.1
+  bias = torch.randn(96, device="cuda", generator=g)
+  nbytes = ctx.lib.dd_conv2d_packed_bytes(3, cin, cout, _lib.DD_BF16, 0)
+  packed = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+  ctx.call("dd_conv2d_pack_weights_dev", _fp(wt), 3, cin, cout, 0 | _lib.DD_PACK_BF16, _fp(packed))
+  host_packed = ctx.pack_conv_weights(wt.cpu(), torch.bfloat16)
+  assert torch.equal(packed, host_packed)
+  y = torch.empty(n, h, w, cout, device="cuda", dtype=torch.bfloat16)
+  ctx.conv2d(_lib.desc(x), packed, bias, 3, _lib.desc(y), relu=True)
+  want = torch.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wt.bfloat16().float().permute(3, 2, 0, 1), bias[:cout], padding=1))
+  assert rel_err(y.float(), want.permute(0, 2, 3, 1)) <= 1e-2            # one bf16 rounding of the result (2^-8)
+  # fp32 output of the same kernel is exact up to accumulation order
+  y32 = torch.empty(n, h, w, cout, device="cuda")
+  ctx.conv2d(_lib.desc(x), packed, bias, 3, _lib.desc(y32), relu=True)
+  assert rel_err(y32, want.permute(0, 2, 3, 1)) <= 1e-5
+  # weight gradient
+  dz = torch.randn(n, h, w, cout, device="cuda", generator=g).bfloat16()
+  dw = torch.zeros(3, 3, cin, cout, device="cuda")
+  ctx.call("dd_conv2d_wgrad_tc", _b(_lib.desc(x)), _b(_lib.desc(dz)), 3, 0, _fp(dw), ctypes.c_float(1.0))
+  wz = torch.zeros(cout, cin, 3, 3, device="cuda", requires_grad=True)
+  F.conv2d(x.float().permute(0, 3, 1, 2), wz, padding=1).backward(dz.float().permute(0, 3, 1, 2))
+  assert rel_err(dw, wz.grad.permute(2, 3, 1, 0)) <= 2e-3
+  # input gradient with the fused ReLU mask
+  pb = torch.zeros(ctx.lib.dd_conv2d_packed_bytes(3, cout, cin, _lib.DD_BF16, 0), dtype=torch.uint8, device="cuda")
+  ctx.call("dd_conv2d_pack_weights_dev", _fp(wt), 3, cin, cout, 1 | _lib.DD_PACK_BF16, _fp(pb))
+  dx = torch.empty(n, h, w, cin, device="cuda", dtype=torch.bfloat16)
+  ctx.conv2d(_lib.desc(dz), pb, None, 3, _lib.desc(dx), residual=_lib.desc(x), residual_is_mask=True)
+  xin = torch.zeros(n, cin, h, w, device="cuda", requires_grad=True)
+  F.conv2d(xin, wt.bfloat16().float().permute(3, 2, 0, 1), padding=1).backward(dz.float().permute(0, 3, 1, 2))
+  want_dx = xin.grad.permute(0, 2, 3, 1) * (x.float() > 0)
+  assert rel_err(dx.float(), want_dx) <= 1e-2

@@ -286,3 +286,42 @@ def test_unbuilt_loss_terms_fail_loudly():
     TrainingSettings({"features_training_settings": {"loss_weights": {"mean": 1.0, "ms_ssim": 0.1}}})
   with pytest.raises(NotImplementedError):
     TrainingSettings({"features_training_settings": {"loss_weights_masked": {"variation": 0.1}}})
+
+
+def test_bfloat16_training_and_inference():
+  """bfloat16 storage (BASELINE.json names bf16 training): the same tensor-core kernels with bf16 operands, no loss scale
+  needed (fp32 exponent range).  8 mantissa bits: predictions within 5e-2 of the output scale, gradient direction cosine
+  >= 0.97 against the float64 oracle, and the loss goes down like on the exact path."""
+  j = small_example(filters=(16, 24, 32), n_convs=2, k=3)
+  host, weights, features, targets = make_problem(j, n=2, h=16, w=24)
+  f = {k: torch.from_numpy(v) for k, v in features.items()}
+  t = {k: torch.from_numpy(v) for k, v in targets.items()}
+  trainer = Trainer(Architecture(j, weights=weights), TrainingSettings({"loss_difference": "SQUARED"}), precision="bfloat16")
+  trainer.forward(f)
+  loss = float(trainer.loss_and_gradient(t).item())
+  trainer.backward()
+  want_loss, want_grads, want_preds = oracle_loss_and_grads(j, weights, features, targets, kind="SQUARED")
+  assert trainer._scale_used == 1.0
+  assert abs(loss - want_loss) <= 3e-2 * max(1.0, abs(want_loss)), (loss, want_loss)
+  got = trainer.gradients()
+  a = np.concatenate([got[k].reshape(-1).astype(np.float64) for k in want_grads])
+  b = np.concatenate([want_grads[k].reshape(-1) for k in want_grads])
+  cosine = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+  print("bf16: loss %.5f (oracle %.5f), gradient cosine %.5f" % (loss, want_loss, cosine))
+  assert cosine >= 0.97, cosine
+  # inference through Architecture.predict with bf16 storage
+  jj = dict(j)
+  jj["b200"] = {"dtype": "bfloat16"}
+  out = Architecture(jj, weights=weights).predict(f)
+  worst = 0.0
+  for s in range(len(want_preds)):
+    for k_, v in want_preds[s].items():
+      v = v.detach().numpy()
+      worst = max(worst, float(np.abs(out[s][k_].float().cpu().numpy() - v).max()) / max(1.0, float(np.abs(v).max())))
+  print("bf16 inference: max relative error %.2e" % worst)
+  assert worst <= 5e-2
+  # a few SMAPE steps reduce the loss
+  tr = Trainer(Architecture(j, weights=weights), TrainingSettings({"learning_rate": 1e-3}), precision="bfloat16")
+  losses = [float(tr.train_step(f, t).item()) for _ in range(10)]
+  print("bf16 losses", ["%.4f" % l for l in losses])
+  assert losses[-1] < losses[0] - 0.3

@@ -2,7 +2,7 @@
 """Training-step benchmark (BASELINE.json configs[4]: tiles of 256x256x32-ch, U-Net [64,96,128]x4 KPCN K=5, SMAPE loss of
 TrainingExample.json) on the tensor-core (fp16) or exact (fp32) path.
 
-  python tools/bench_training.py [--tiles T] [--size S] [--steps K] [--warmup W] [--precision float16|float32] [--arch unet32]
+  python tools/bench_training.py [--tiles T] [--size S] [--steps K] [--warmup W] [--precision float16|bfloat16|float32] [--arch unet32]
   python -m torch.distributed.run --nproc-per-node N tools/bench_training.py ...     # T tiles PER RANK (weak scaling)
 
 One step = forward (all tuple passes) + loss + backward + gradient all-reduce (N > 1) + Adam + weight repack, inputs resident
