@@ -44,7 +44,13 @@ __global__ void __launch_bounds__(256) maxpool_generic_kernel(const PoolParams p
   p.y.store(opix, c, m);
 }
 
-// fp16, 8 channels (16 bytes) per thread
+// 16-bit storage (fp16 or bf16), 8 channels (16 bytes) per thread
+template <typename T2>
+__device__ __forceinline__ T2 pool_ninf();
+template <> __device__ __forceinline__ __half2 pool_ninf<__half2>() { return __float2half2_rn(-INFINITY); }
+template <> __device__ __forceinline__ __nv_bfloat162 pool_ninf<__nv_bfloat162>() { return __float2bfloat162_rn(-INFINITY); }
+
+template <typename T2>
 __global__ void __launch_bounds__(256) maxpool_h8_kernel(const PoolParams p) {
   const int cv = p.y.c / 8;
   const size_t total = static_cast<size_t>(p.y.n) * p.y.h * p.y.w * cv;
@@ -55,9 +61,9 @@ __global__ void __launch_bounds__(256) maxpool_h8_kernel(const PoolParams p) {
   const int ox = static_cast<int>(opix % p.y.w);
   const int oy = static_cast<int>((opix / p.y.w) % p.y.h);
   const int n = static_cast<int>(opix / (static_cast<size_t>(p.y.w) * p.y.h));
-  const __half* xin = reinterpret_cast<const __half*>(p.x.ptr);
-  __half2 m[4];
-  const __half2 ninf = __float2half2_rn(-INFINITY);
+  const uint16_t* xin = reinterpret_cast<const uint16_t*>(p.x.ptr);
+  T2 m[4];
+  const T2 ninf = pool_ninf<T2>();
 #pragma unroll
   for (int i = 0; i < 4; ++i) m[i] = ninf;
   for (int r = 0; r < p.ksize; ++r) {
@@ -67,16 +73,16 @@ __global__ void __launch_bounds__(256) maxpool_h8_kernel(const PoolParams p) {
       const int xx = 2 * ox - p.pad_x + s;
       if (xx < 0 || xx >= p.x.w) continue;
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(xin + p.x.pix(n, yy, xx) * p.x.cstride + p.x.coff + c));
-      const __half2* h = reinterpret_cast<const __half2*>(&v);
+      const T2* h = reinterpret_cast<const T2*>(&v);
 #pragma unroll
       for (int i = 0; i < 4; ++i) m[i] = __hmax2(m[i], h[i]);
     }
   }
   uint4 o;
-  __half2* oh = reinterpret_cast<__half2*>(&o);
+  T2* oh = reinterpret_cast<T2*>(&o);
 #pragma unroll
   for (int i = 0; i < 4; ++i) oh[i] = m[i];
-  *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.y.ptr) + opix * p.y.cstride + p.y.coff + c) = o;
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.y.ptr) + opix * p.y.cstride + p.y.coff + c) = o;
 }
 
 // average pooling factor x factor, stride factor, TF 'SAME' (padded cells excluded from the divisor)
@@ -197,18 +203,16 @@ __global__ void __launch_bounds__(256) assemble_kernel(const AssembleParams p) {
   const int t = static_cast<int>(b / p.n);
   const size_t spix = (b % p.n) * img_pix + (opix % img_pix);  // pixel index inside the [n,h,w] source
   const dd_gather_entry* row = p.table + static_cast<size_t>(t) * p.out.c;
-  if (p.out.f16 && (p.out.c % 8 == 0) && (p.out.coff % 8 == 0) && (p.out.cstride % 8 == 0)) {
-    __half* o = reinterpret_cast<__half*>(p.out.ptr) + opix * p.out.cstride + p.out.coff;
+  if (vec16_ok(p.out)) {
+    uint16_t* o = reinterpret_cast<uint16_t*>(p.out.ptr) + opix * p.out.cstride + p.out.coff;
     for (int c0 = 0; c0 < p.out.c; c0 += 8) {
-      uint4 pk;
-      __half* ph = reinterpret_cast<__half*>(&pk);
+      float f[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const dd_gather_entry e = row[c0 + i];
-        const float v = e.ptr ? __ldg(e.ptr + spix * e.cstride + e.cidx) : e.constant;
-        ph[i] = __float2half_rn(v);
+        f[i] = e.ptr ? __ldg(e.ptr + spix * e.cstride + e.cidx) : e.constant;
       }
-      *reinterpret_cast<uint4*>(o + c0) = pk;
+      *reinterpret_cast<uint4*>(o + c0) = pack8(f, p.out.bf16);
     }
   } else {
     for (int c = 0; c < p.out.c; ++c) {
@@ -333,11 +337,12 @@ int dd_maxpool_s2_fwd(dd_ctx* ctx, const dd_tensor* x, int ksize, const dd_tenso
   const int pty = (oh - 1) * 2 + ksize - x->h, ptx = (ow - 1) * 2 + ksize - x->w;
   p.pad_y = (pty > 0 ? pty : 0) / 2; p.pad_x = (ptx > 0 ? ptx : 0) / 2;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bool vec = x->dtype == DD_F16 && y->dtype == DD_F16 && x->c % 8 == 0 && x->coff % 8 == 0 &&
+  const bool vec = is_half_type(x->dtype) && y->dtype == x->dtype && x->c % 8 == 0 && x->coff % 8 == 0 &&
                    x->cstride % 8 == 0 && y->coff % 8 == 0 && y->cstride % 8 == 0;
   if (vec) {
     const size_t total = static_cast<size_t>(y->n) * y->h * y->w * (y->c / 8);
-    maxpool_h8_kernel<<<blocks_for(total, 256), 256, 0, s>>>(p);
+    if (x->dtype == DD_BF16) maxpool_h8_kernel<__nv_bfloat162><<<blocks_for(total, 256), 256, 0, s>>>(p);
+    else maxpool_h8_kernel<__half2><<<blocks_for(total, 256), 256, 0, s>>>(p);
   } else {
     const size_t total = static_cast<size_t>(y->n) * y->h * y->w * y->c;
     maxpool_generic_kernel<<<blocks_for(total, 256), 256, 0, s>>>(p);

@@ -116,7 +116,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], int bf16) {
   return v;
 }
 // a view the 16-byte vectorised kernels can take: 16-bit storage, 8-channel granularity
-inline bool vec16_ok(const View& v) { return (v.f16 || v.bf16) && v.c % 8 == 0 && v.coff % 8 == 0 && v.cstride % 8 == 0; }
+__host__ __device__ inline bool vec16_ok(const View& v) { return (v.f16 || v.bf16) && v.c % 8 == 0 && v.coff % 8 == 0 && v.cstride % 8 == 0; }
 
 inline View make_view(const dd_tensor* t) {
   View v;

@@ -261,3 +261,15 @@ def test_conv_and_wgrad_bfloat16(ctx):
   F.conv2d(xin, wt.bfloat16().float().permute(3, 2, 0, 1), padding=1).backward(dz.float().permute(0, 3, 1, 2))
   want_dx = xin.grad.permute(0, 2, 3, 1) * (x.float() > 0)
   assert rel_err(dx.float(), want_dx) <= 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_maxpool_16bit_vector_path(ctx, dtype):
+  """3x3 stride-2 TF-'SAME' max pooling (tail padding) on 16-bit tensors, 16-byte vectorised kernel: bit exact."""
+  n, h, w, c = 2, 12, 20, 24
+  x = torch.randn(n, h, w, c, device="cuda").to(dtype)
+  y = torch.empty(n, h // 2, w // 2, c, device="cuda", dtype=dtype)
+  ctx.maxpool_s2(_lib.desc(x), 3, _lib.desc(y))
+  xp = F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1), value=float("-inf"))
+  want = F.max_pool2d(xp, 3, 2).permute(0, 2, 3, 1).to(dtype)
+  assert torch.equal(y, want)
