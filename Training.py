@@ -78,7 +78,7 @@ def write_synthetic_dataset(architecture, directory, tiles, size, seed=4242):
   return tfrecords.write_tile_dataset(directory, "training", examples(), settings)
 
 
-def tfrecord_batches(architecture, training_json, base, per_rank, rank, world, trainer, epoch_seed):
+def tfrecord_batches(architecture, training_json, base, per_rank, rank, world, trainer, epoch_seed, threads=0):
   """input_fn_tfrecords (Training.py:728-850): records -> (sources, targets) examples -> device augmentation -> batches."""
   directory = os.path.join(base, training_json["base_tfrecords_directory"])
   dataset = tfrecords.TileDataset(os.path.join(directory, "training"), os.path.join(directory, "training.json"), architecture,
@@ -86,7 +86,7 @@ def tfrecord_batches(architecture, training_json, base, per_rank, rank, world, t
   usage = augmentation.DataAugmentationUsage.from_json(training_json)
   augment = augmentation.DeviceAugmenter(trainer.ctx, usage)
   rng = np.random.default_rng(epoch_seed * 7919 + rank)
-  for sources, targets in dataset.batches(per_rank, shuffle_seed=epoch_seed, rank=rank, world=world):
+  for sources, targets in dataset.batches(per_rank, shuffle_seed=epoch_seed, rank=rank, world=world, threads=threads):
     draws = augmentation.draw(usage, per_rank, rng)
     yield augment(sources, targets, draws)
 
@@ -138,7 +138,8 @@ def main(parsed_arguments):
 
   def epoch_batches(epoch):
     if use_records:
-      for features, targets in tfrecord_batches(architecture, training_json, base, per_rank, rank, world, trainer, epoch + 1):
+      for features, targets in tfrecord_batches(architecture, training_json, base, per_rank, rank, world, trainer, epoch + 1,
+                                                threads=min(8, max(1, int(parsed_arguments.threads) // max(1, world)))):
         yield features, targets
     else:
       for _ in range(parsed_arguments.steps_per_epoch):

@@ -280,13 +280,41 @@ class TileDataset:
         out.append((sources, targets))
     return out
 
-  def examples(self, files=None):
-    for path in (files or self.files):
-      for payload in read_records(path, verify_crc=self.verify_crc):
-        for pair in self.examples_of_record(payload):
+  def _examples_of_file(self, path):
+    out = []
+    for payload in read_records(path, verify_crc=self.verify_crc):
+      out.extend(self.examples_of_record(payload))
+    return out
+
+  def examples(self, files=None, threads=0):
+    """All (sources, targets) pairs of `files`, in file order.  threads > 0: files are read, gunzipped, CRC-checked and parsed
+    by a pool of worker threads `threads` files ahead of the consumer (tf.data's num_parallel_reads / num_parallel_calls,
+    Training.py:830-834; zlib and the CRC run outside the GIL), so the GPU step is not throttled by the input pipeline."""
+    files = list(files or self.files)
+    if threads <= 0:
+      for path in files:
+        for payload in read_records(path, verify_crc=self.verify_crc):
+          for pair in self.examples_of_record(payload):
+            yield pair
+      return
+    import collections
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+      pending = collections.deque()
+      it = iter(files)
+      for path in it:
+        pending.append(pool.submit(self._examples_of_file, path))
+        if len(pending) >= threads:
+          break
+      while pending:
+        done = pending.popleft().result()
+        nxt = next(it, None)
+        if nxt is not None:
+          pending.append(pool.submit(self._examples_of_file, nxt))
+        for pair in done:
           yield pair
 
-  def batches(self, batch_size, epochs=1, shuffle_seed=None, rank=0, world=1, drop_remainder=True):
+  def batches(self, batch_size, epochs=1, shuffle_seed=None, rank=0, world=1, drop_remainder=True, threads=0):
     """dataset.shuffle(20 * batch).batch(batch) (Training.py:836-839), files shuffled per epoch (:825-826) and sharded
     round-robin over `world` ranks.  Yields (sources, targets) dictionaries of [B,S,S,C] float32 arrays."""
     rng = random.Random(shuffle_seed)
@@ -296,7 +324,7 @@ class TileDataset:
         rng.shuffle(files)
       files = files[rank::world] if len(files) >= world else files
       pool, limit = [], (20 * batch_size if shuffle_seed is not None else batch_size)
-      stream = self.examples(files)
+      stream = self.examples(files, threads=threads)
       exhausted = False
       while True:
         while not exhausted and len(pool) < limit:

@@ -107,6 +107,12 @@ def test_tile_dataset_matches_what_was_written(tmp_path):
   assert len(batches) == 5 and all(b[0]["source_image/0/" + name].shape == (4, size, size, passes[-1][1]) or True for b in batches)
   key = "source_image/0/" + passes[0][0]
   assert batches[0][0][key].shape == (4, size, size, passes[0][1])
+  # threaded prefetch yields exactly the same examples in the same order
+  threaded = list(ds.examples(threads=3))
+  assert len(threaded) == len(got)
+  for (s0, t0), (s1, t1) in zip(got, threaded):
+    assert s0.keys() == s1.keys() and all(np.array_equal(s0[k], s1[k]) for k in s0)
+    assert all(np.array_equal(t0[k], t1[k]) for k in t0)
   # sharding over ranks: disjoint files
   r0 = list(ds.batches(2, shuffle_seed=None, rank=0, world=2))
   r1 = list(ds.batches(2, shuffle_seed=None, rank=1, world=2))
