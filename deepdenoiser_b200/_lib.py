@@ -81,6 +81,10 @@ SIGNATURES = {
     "dd_loss_variation_fwd_bwd": (_i, [_vp, _T, _T, _i, ctypes.c_float, ctypes.c_float, _vp, _T, _vp]),
     "dd_mask_sum": (_i, [_vp, _T, _vp, _vp]),
     "dd_loss_masked_fwd_bwd": (_i, [_vp, _T, _T, _T, _vp, _i, ctypes.c_float, ctypes.c_float, _vp, _T, _vp]),
+    "dd_ssim_stats": (_i, [_vp, _T, _T, _T, _vp]),
+    "dd_ssim_reduce": (_i, [_vp, _T, _i, ctypes.c_float, _vp, _vp]),
+    "dd_ssim_bwd": (_i, [_vp, _T, _T, _T, _vp, ctypes.c_float, _T, _vp]),
+    "dd_avgpool2_adjoint": (_i, [_vp, _T, _T, _vp]),
     "dd_conv2d_wgrad": (_i, [_vp, _T, _T, _i, _i, _vp, _vp, _vp]),
     "dd_conv2d_wgrad_tc": (_i, [_vp, _T, _T, _i, _i, _vp, ctypes.c_float, _vp]),
     "dd_conv2d_pack_weights_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

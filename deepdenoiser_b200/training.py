@@ -64,21 +64,23 @@ class TrainingSettings:
     self.use_multiscale_loss = bool(j.get("use_multiscale_loss", True))
 
     def weights(block, default_mean):
-      """(mean, variation, masked mean) weights of one *_training_settings block (TrainingExample.json:31-98)."""
+      """(mean, variation, masked mean, ms_ssim) weights of one *_training_settings block (TrainingExample.json:31-98)."""
       b = j.get(block, {})
       lw, lm = b.get("loss_weights", {}), b.get("loss_weights_masked", {})
-      if float(lw.get("ms_ssim", 0.0)) != 0.0 or float(lm.get("ms_ssim", 0.0)) != 0.0:
-        raise NotImplementedError("%s: MS-SSIM loss terms (tf.image.ssim_multiscale, Training.py:188-204) are not built; "
-                                  "masked MS-SSIM raises in the reference too (:206-207)" % block)
+      if float(lm.get("ms_ssim", 0.0)) != 0.0:
+        raise NotImplementedError("%s: masked MS-SSIM raises 'Not implemented' in the reference too (Training.py:206-207)" % block)
       if float(lm.get("variation", 0.0)) != 0.0:
         raise NotImplementedError("%s: the reference's masked variation loss multiplies a [N, h(w-1)+(h-1)w] tensor with an "
                                   "[N,h,w] mask (Training.py:146-149) and cannot run; not built" % block)
-      return float(lw.get("mean", default_mean)), float(lw.get("variation", 0.0)), float(lm.get("mean", 0.0))
+      return (float(lw.get("mean", default_mean)), float(lw.get("variation", 0.0)), float(lm.get("mean", 0.0)),
+              float(lw.get("ms_ssim", 0.0)))
 
-    self.feature_weight, self.feature_variation_weight, self.feature_masked_weight = weights("features_training_settings", 1.0)
-    (self.combined_feature_weight, self.combined_feature_variation_weight,
-     self.combined_feature_masked_weight) = weights("combined_features_training_settings", 5.0)
-    self.combined_image_weight, self.combined_image_variation_weight, masked = weights("combined_image_training_settings", 10.0)
+    (self.feature_weight, self.feature_variation_weight, self.feature_masked_weight,
+     self.feature_ms_ssim_weight) = weights("features_training_settings", 1.0)
+    (self.combined_feature_weight, self.combined_feature_variation_weight, self.combined_feature_masked_weight,
+     self.combined_feature_ms_ssim_weight) = weights("combined_features_training_settings", 5.0)
+    (self.combined_image_weight, self.combined_image_variation_weight, masked,
+     self.combined_image_ms_ssim_weight) = weights("combined_image_training_settings", 10.0)
     if masked != 0.0:
       raise NotImplementedError("combined_image_training_settings: the combined image has no mask in the reference "
                                 "(CombinedImageFeatureTraining.initialize, Training.py:475-495)")
@@ -790,6 +792,50 @@ class Trainer:
         return RenderPasses.direct_or_indirect_to_color_render_pass(name)
       return None
 
+    def ms_ssim_term(pred_d, tgt_d, grad_d, weight, what):
+      """weight * (1 - mean(tf.image.ssim_multiscale(pred, target, 1, (0.0448, 0.2856, 0.3001)))) on the full-resolution
+      prediction (BaseFeatureTraining.ms_ssim / loss, Training.py:188-204, 229-230) and its gradient, accumulated into grad_d."""
+      powers = (0.0448, 0.2856, 0.3001)
+      c = pred_d.c
+      if c != 3:
+        raise NotImplementedError("MS-SSIM of '%s': %d-channel passes take the reference's channels_first detour "
+                                  "(Training.py:197-199); only RGB passes are built" % (what, c))
+      if (h % 4) or (w % 4) or (h >> 2) < 11 or (w >> 2) < 11:
+        raise ValueError("MS-SSIM needs tiles divisible by 4 with at least 44 pixels per side (11x11 filter at the third scale)")
+      xs, ys = [pred_d], [tgt_d]
+      for k in (1, 2):
+        xk = self._buf("msssim.x.%s.%d" % (what, k), (n, h >> k, w >> k, c))
+        yk = self._buf("msssim.y.%s.%d" % (what, k), (n, h >> k, w >> k, c))
+        ctx.avgpool(xs[-1], 2, _lib.desc(xk))
+        ctx.avgpool(ys[-1], 2, _lib.desc(yk))
+        xs.append(_lib.desc(xk)); ys.append(_lib.desc(yk))
+      stats, sums = [], []
+      for k in range(3):
+        hk, wk = (h >> k) - 10, (w >> k) - 10
+        st_k = _lib.desc(self._buf("msssim.stats.%s.%d" % (what, k), (n, hk, wk, 4 * c)))
+        sm_k = self._buf("msssim.sums.%s.%d" % (what, k), (n, c, 2), zero=True)
+        ctx.call("dd_ssim_stats", _b(xs[k]), _b(ys[k]), _b(st_k))
+        ctx.call("dd_ssim_reduce", _b(st_k), c, ctypes.c_float(1.0), _fp(sm_k))
+        stats.append(st_k); sums.append(sm_k / float(hk * wk))
+      # per (image, channel, level) algebra on [n, c, 3] device tensors
+      v = torch.stack([sums[0][..., 0], sums[1][..., 0], sums[2][..., 1]], dim=-1)
+      m = torch.relu(v)
+      pw = torch.tensor(powers, dtype=torch.float32, device=self.dev)
+      ms = torch.prod(torch.pow(m, pw), dim=-1)
+      self.loss_value += S * weight * (1.0 - ms.mean())
+      dms = -S * weight / float(n * c)
+      dv = torch.where(m > 0, dms * pw * ms.unsqueeze(-1) / m.clamp_min(1e-30), torch.zeros_like(m))     # [n, c, 3]
+      zero = torch.zeros_like(dv[..., 0])
+      coefs = [torch.stack([dv[..., 0], zero], dim=-1).contiguous(), torch.stack([dv[..., 1], zero], dim=-1).contiguous(),
+               torch.stack([zero, dv[..., 2]], dim=-1).contiguous()]
+      d2 = self._buf("msssim.d2.%s" % what, (n, h >> 2, w >> 2, c), zero=True)
+      d1 = self._buf("msssim.d1.%s" % what, (n, h >> 1, w >> 1, c), zero=True)
+      ctx.call("dd_ssim_bwd", _b(xs[2]), _b(ys[2]), _b(stats[2]), _fp(coefs[2]), ctypes.c_float(1.0), _b(_lib.desc(d2)))
+      ctx.call("dd_ssim_bwd", _b(xs[1]), _b(ys[1]), _b(stats[1]), _fp(coefs[1]), ctypes.c_float(1.0), _b(_lib.desc(d1)))
+      ctx.call("dd_avgpool2_adjoint", _b(_lib.desc(d2)), _b(_lib.desc(d1)))
+      ctx.call("dd_ssim_bwd", _b(xs[0]), _b(ys[0]), _b(stats[0]), _fp(coefs[0]), ctypes.c_float(1.0), _b(grad_d))
+      ctx.call("dd_avgpool2_adjoint", _b(_lib.desc(d1)), _b(grad_d))
+
     def extra_terms(pred_d, tgt_d, grad_d, s, variation_weight, masked_weight, mask_name, what):
       """variation_mean / masked_mean of one feature at scale s (BaseFeatureTraining.loss, Training.py:226-240); the gradient is
       accumulated into grad_d."""
@@ -821,13 +867,17 @@ class Trainer:
         for fp in loaded:
           extra_terms(pred_view(st["finals"][s], fp), _lib.desc(tgt[fp.name][s]), pred_view(dfin[s], fp), s,
                       cfg.feature_variation_weight, cfg.feature_masked_weight, mask_pass(fp.name), fp.name)
+      if cfg.feature_ms_ssim_weight > 0 and s == 0:
+        for fp in loaded:
+          ms_ssim_term(pred_view(st["finals"][0], fp), _lib.desc(tgt[fp.name][0]), pred_view(dfin[0], fp),
+                       cfg.feature_ms_ssim_weight, fp.name)
       # combined lighting passes color * (direct + indirect) and the combined image (sum of everything)
       lights = [l for l in _LIGHTS if all((l + k) in by_name and by_name[l + k].load_data for k in (" Color", " Direct", " Indirect"))]
       image_terms = [t for t in _IMAGE_TERMS if t in by_name and by_name[t].load_data]
-      use_image = ((cfg.combined_image_weight > 0 or cfg.combined_image_variation_weight > 0) and len(lights) == 4 and
-                   len(image_terms) == 4)
+      use_image = ((cfg.combined_image_weight > 0 or cfg.combined_image_variation_weight > 0 or
+                    cfg.combined_image_ms_ssim_weight > 0) and len(lights) == 4 and len(image_terms) == 4)
       use_combined = (cfg.combined_feature_weight > 0 or cfg.combined_feature_variation_weight > 0 or
-                      cfg.combined_feature_masked_weight > 0)
+                      cfg.combined_feature_masked_weight > 0 or cfg.combined_feature_ms_ssim_weight > 0)
       shape = (n, h >> s, w >> s, 3)
       g_img = None
       if use_image:
@@ -858,6 +908,8 @@ class Trainer:
                  _b(_lib.desc(g_img)), 0)
         extra_terms(_lib.desc(img_p), _lib.desc(img_t), _lib.desc(g_img), s, cfg.combined_image_variation_weight, 0.0, None,
                     "Combined")
+        if cfg.combined_image_ms_ssim_weight > 0 and s == 0:
+          ms_ssim_term(_lib.desc(img_p), _lib.desc(img_t), _lib.desc(g_img), cfg.combined_image_ms_ssim_weight, "Combined")
         for t in image_terms:
           ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(g_img)), _b(pred_view(dfin[s], by_name[t])))
       for l, (cp, ct, gc) in comb.items():
@@ -867,6 +919,8 @@ class Trainer:
                    _b(_lib.desc(gc)), 1)
         extra_terms(_lib.desc(cp), _lib.desc(ct), _lib.desc(gc), s, cfg.combined_feature_variation_weight,
                     cfg.combined_feature_masked_weight, RenderPasses.combined_to_color_render_pass(l), l)
+        if cfg.combined_feature_ms_ssim_weight > 0 and s == 0:
+          ms_ssim_term(_lib.desc(cp), _lib.desc(ct), _lib.desc(gc), cfg.combined_feature_ms_ssim_weight, l)
         if use_image:
           ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(g_img)), _b(_lib.desc(gc)))
         c, d, i = (by_name[l + k] for k in (" Color", " Direct", " Indirect"))

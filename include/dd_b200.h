@@ -240,6 +240,16 @@ int dd_mask_sum(dd_ctx* ctx, const dd_tensor* mask_src, float* sum_dev, void* st
 int dd_loss_masked_fwd_bwd(dd_ctx* ctx, const dd_tensor* pred, const dd_tensor* target, const dd_tensor* mask_src,
                            const float* mask_sum_dev, int kind, float weight, float epsilon, float* loss_dev,
                            const dd_tensor* dpred_acc, void* stream);
+/* Multi-scale SSIM loss term (BaseFeatureTraining.ms_ssim, Training.py:188-204; tf.image.ssim_multiscale [external]).
+ * dd_ssim_stats: stats[n, h-10, w-10, {mx, my, sxy, sxx+syy} x C] = the 11x11 Gaussian (sigma 1.5) VALID filter responses of
+ * one level;  dd_ssim_reduce: sums_dev[n][c][2] += {sum cs, sum l*cs} over the filtered pixels;  dd_ssim_bwd: given
+ * coef_dev[n][c][2] = {d objective / d mean(cs), d objective / d mean(l cs)} accumulates d objective / d x into dx_acc;
+ * dd_avgpool2_adjoint: dfine_acc[2i+a, 2j+b] += dcoarse[i, j] / 4 (adjoint of the 2x2 average pooling between levels). */
+int dd_ssim_stats(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, const dd_tensor* stats, void* stream);
+int dd_ssim_reduce(dd_ctx* ctx, const dd_tensor* stats, int channels, float max_val, float* sums_dev, void* stream);
+int dd_ssim_bwd(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, const dd_tensor* stats, const float* coef_dev, float max_val,
+                const dd_tensor* dx_acc, void* stream);
+int dd_avgpool2_adjoint(dd_ctx* ctx, const dd_tensor* dcoarse, const dd_tensor* dfine_acc, void* stream);
 /* dW (TF layout [kh,kw,cin,cout]; transposed: [2,2,cout,cin]) += x^T * dz over all pixels, db += sum dz. */
 int dd_conv2d_wgrad(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int ksize, int transposed, float* dw_dev,
                     float* db_dev, void* stream);

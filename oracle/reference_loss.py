@@ -4,8 +4,8 @@ that torch.autograd provides the gradient oracle for the CUDA backward kernels.
 Follows Training.py: model_fn loss assembly :611-660, BaseFeatureTraining.loss :210-243 (scale weights (1/4^s) / sum),
 mean :126-129, FeatureTraining / CombinedFeatureTraining / CombinedImageFeatureTraining.initialize :374-495 and
 LossDifference.difference (LossDifference.py:15-36), variation_mean :139-186 + :304-346 and masked_mean :131-137 with the
-masks of FeatureTraining / CombinedFeatureTraining.initialize :374-392, :434-437.  MS-SSIM terms (weight 0 in
-TrainingExample.json:31-98) are not restated.  PARITY UNPINNED (see oracle/np_ops.py).
+masks of FeatureTraining / CombinedFeatureTraining.initialize :374-392, :434-437, and ms_ssim :188-204 with
+tf.image.ssim_multiscale restated from TensorFlow's image_ops_impl.py [external].  PARITY UNPINNED (see oracle/np_ops.py).
 """
 import torch
 
@@ -44,8 +44,48 @@ def masked_mean(predicted, target, mask_source, kind):
   return (torch_ops.loss_difference(predicted, target, kind) * mask / total).sum()
 
 
+def _fspecial_gauss(size, sigma, dtype):
+  """tf.image's _fspecial_gauss [external]: softmax-normalised 2-D Gaussian."""
+  coords = torch.arange(size, dtype=dtype) - (size - 1) / 2.0
+  g = coords ** 2 * (-0.5 / sigma ** 2)
+  g = g.reshape(1, -1) + g.reshape(-1, 1)
+  return torch.softmax(g.reshape(-1), dim=0).reshape(size, size)
+
+
+def ssim_multiscale(img1, img2, max_val=1.0, power_factors=(0.0448, 0.2856, 0.3001), filter_size=11, filter_sigma=1.5,
+                    k1=0.01, k2=0.03):
+  """tf.image.ssim_multiscale [external] on NHWC tensors with even sizes at every level: returns [N]."""
+  import torch.nn.functional as F
+  x, y = img1.permute(0, 3, 1, 2), img2.permute(0, 3, 1, 2)
+  ch = x.shape[1]
+  kernel = _fspecial_gauss(filter_size, filter_sigma, x.dtype).reshape(1, 1, filter_size, filter_size).repeat(ch, 1, 1, 1)
+  reducer = lambda t: F.conv2d(t, kernel, groups=ch)      # noqa: E731  depthwise, VALID
+  c1, c2 = (k1 * max_val) ** 2, (k2 * max_val) ** 2
+  mcs = []
+  for k in range(len(power_factors)):
+    if k > 0:
+      assert x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0
+      x, y = F.avg_pool2d(x, 2), F.avg_pool2d(y, 2)
+    mean0, mean1 = reducer(x), reducer(y)
+    num0, den0 = mean0 * mean1 * 2.0, mean0 ** 2 + mean1 ** 2
+    luminance = (num0 + c1) / (den0 + c1)
+    num1, den1 = reducer(x * y) * 2.0, reducer(x ** 2 + y ** 2)
+    cs = (num1 - num0 + c2) / (den1 - den0 + c2)
+    ssim_per_channel = (luminance * cs).mean(dim=(2, 3))
+    mcs.append(torch.relu(cs.mean(dim=(2, 3))))
+  mcs.pop()
+  stacked = torch.stack(mcs + [torch.relu(ssim_per_channel)], dim=-1)            # [N, C, levels]
+  pw = torch.tensor(power_factors, dtype=x.dtype)
+  return torch.prod(stacked ** pw, dim=-1).mean(dim=-1)
+
+
+def ms_ssim_loss(predicted, target):
+  """BaseFeatureTraining.ms_ssim (Training.py:188-204): 1 - mean(ssim_multiscale(..., max_val = 1, three power factors))."""
+  return 1.0 - ssim_multiscale(predicted, target, 1.0).mean()
+
+
 def feature_loss(predicted, target, kind, weight, use_multiscale_loss=True, variation_weight=0.0, masked_weight=0.0,
-                 mask_source=None):
+                 mask_source=None, ms_ssim_weight=0.0):
   """BaseFeatureTraining.loss (Training.py:210-243) without the MS-SSIM terms."""
   scales = len(target) if use_multiscale_loss else 1
   norm = 1.0 / sum(1.0 / 4.0 ** s for s in range(scales))
@@ -58,6 +98,8 @@ def feature_loss(predicted, target, kind, weight, use_multiscale_loss=True, vari
       result = result + variation_weight * factor * variation_mean(predicted[s], target[s], kind)
     if masked_weight > 0:
       result = result + masked_weight * factor * masked_mean(predicted[s], target[s], mask_source[s], kind)
+  if ms_ssim_weight > 0:
+    result = result + ms_ssim_weight * ms_ssim_loss(predicted[0], target[0])
   return result
 
 
@@ -74,28 +116,33 @@ def mask_pass(name):
 
 def total_loss(predictions, labels, loaded_names, kind="SMAPE", feature_weight=1.0, combined_feature_weight=5.0,
                combined_image_weight=10.0, use_multiscale_loss=True, feature_variation_weight=0.0, feature_masked_weight=0.0,
-               combined_feature_variation_weight=0.0, combined_feature_masked_weight=0.0, combined_image_variation_weight=0.0):
+               combined_feature_variation_weight=0.0, combined_feature_masked_weight=0.0, combined_image_variation_weight=0.0,
+               feature_ms_ssim_weight=0.0, combined_feature_ms_ssim_weight=0.0, combined_image_ms_ssim_weight=0.0):
   """predictions: list over scales of {'prediction/<Pass>': tensor}; labels: {'target_image/<Pass>': tensor}."""
   targets = multiscale_targets(labels, len(predictions))
   p = lambda name: [d["prediction/" + name] for d in predictions]     # noqa: E731
   t = lambda name: [d["target_image/" + name] for d in targets]       # noqa: E731
   loss = 0.0
-  if feature_weight > 0 or feature_variation_weight > 0 or feature_masked_weight > 0:
+  if feature_weight > 0 or feature_variation_weight > 0 or feature_masked_weight > 0 or feature_ms_ssim_weight > 0:
     for name in loaded_names:
       mask = t(mask_pass(name)) if (feature_masked_weight > 0 and mask_pass(name) is not None) else None
       loss = loss + feature_loss(p(name), t(name), kind, feature_weight, use_multiscale_loss, feature_variation_weight,
-                                 feature_masked_weight if mask is not None else 0.0, mask)
+                                 feature_masked_weight if mask is not None else 0.0, mask, feature_ms_ssim_weight)
   lights = [l for l in LIGHTS if all((l + k) in loaded_names for k in (" Color", " Direct", " Indirect"))]
   comb_p, comb_t = {}, {}
   for l in lights:
     comb_p[l] = [c * (d + i) for c, d, i in zip(p(l + " Color"), p(l + " Direct"), p(l + " Indirect"))]
     comb_t[l] = [c * (d + i) for c, d, i in zip(t(l + " Color"), t(l + " Direct"), t(l + " Indirect"))]
-    if combined_feature_weight > 0 or combined_feature_variation_weight > 0 or combined_feature_masked_weight > 0:
+    if (combined_feature_weight > 0 or combined_feature_variation_weight > 0 or combined_feature_masked_weight > 0 or
+        combined_feature_ms_ssim_weight > 0):
       loss = loss + feature_loss(comb_p[l], comb_t[l], kind, combined_feature_weight, use_multiscale_loss,
-                                 combined_feature_variation_weight, combined_feature_masked_weight, t(l + " Color"))
+                                 combined_feature_variation_weight, combined_feature_masked_weight, t(l + " Color"),
+                                 combined_feature_ms_ssim_weight)
   terms = [x for x in IMAGE_TERMS if x in loaded_names]
-  if (combined_image_weight > 0 or combined_image_variation_weight > 0) and len(lights) == 4 and len(terms) == 4:
+  if ((combined_image_weight > 0 or combined_image_variation_weight > 0 or combined_image_ms_ssim_weight > 0) and
+      len(lights) == 4 and len(terms) == 4):
     img_p = [sum(comb_p[l][s] for l in lights) + sum(p(x)[s] for x in terms) for s in range(len(predictions))]
     img_t = [sum(comb_t[l][s] for l in lights) + sum(t(x)[s] for x in terms) for s in range(len(predictions))]
-    loss = loss + feature_loss(img_p, img_t, kind, combined_image_weight, use_multiscale_loss, combined_image_variation_weight)
+    loss = loss + feature_loss(img_p, img_t, kind, combined_image_weight, use_multiscale_loss, combined_image_variation_weight,
+                               ms_ssim_weight=combined_image_ms_ssim_weight)
   return loss

@@ -281,9 +281,32 @@ def test_variation_and_masked_losses_match_autograd():
         (loss, want_loss, base_loss, worst))
 
 
+def test_ms_ssim_loss_matches_autograd():
+  """BaseFeatureTraining.ms_ssim (Training.py:188-204) with non-zero weights in all three feature groups: loss and every
+  gradient against torch-autograd of the restated tf.image.ssim_multiscale."""
+  j = small_example(filters=(16, 16), n_convs=1, k=3)
+  del j["combined_features"]["Alpha"]                      # 1-channel pass: the reference's channels_first detour is not built
+  host, weights, features, targets = make_problem(j, n=1, h=48, w=52)
+  tj = {"loss_difference": "SMAPE",
+        "features_training_settings": {"loss_weights": {"mean": 1.0, "variation": 0.0, "ms_ssim": 0.5}},
+        "combined_features_training_settings": {"loss_weights": {"mean": 5.0, "variation": 0.0, "ms_ssim": 2.0}},
+        "combined_image_training_settings": {"loss_weights": {"mean": 10.0, "variation": 0.0, "ms_ssim": 3.0}}}
+  trainer = Trainer(Architecture(j, weights=weights), TrainingSettings(tj))
+  trainer.forward({k: torch.from_numpy(v) for k, v in features.items()})
+  loss = float(trainer.loss_and_gradient({k: torch.from_numpy(v) for k, v in targets.items()}).item())
+  trainer.backward()
+  want_loss, want_grads, _ = oracle_loss_and_grads(j, weights, features, targets, kind="SMAPE", feature_ms_ssim_weight=0.5,
+                                                   combined_feature_ms_ssim_weight=2.0, combined_image_ms_ssim_weight=3.0)
+  base_loss, _, _ = oracle_loss_and_grads(j, weights, features, targets, kind="SMAPE")
+  assert want_loss > base_loss + 0.5
+  assert abs(loss - want_loss) <= 1e-4 * max(1.0, abs(want_loss)), (loss, want_loss)
+  worst = check_gradients(trainer, want_grads)
+  print("ms-ssim: loss %.5f (oracle %.5f, mean-only %.5f), worst relative gradient error %.2e" % (loss, want_loss, base_loss, worst))
+
+
 def test_unbuilt_loss_terms_fail_loudly():
   with pytest.raises(NotImplementedError):
-    TrainingSettings({"features_training_settings": {"loss_weights": {"mean": 1.0, "ms_ssim": 0.1}}})
+    TrainingSettings({"features_training_settings": {"loss_weights_masked": {"ms_ssim": 0.1}}})
   with pytest.raises(NotImplementedError):
     TrainingSettings({"features_training_settings": {"loss_weights_masked": {"variation": 0.1}}})
 

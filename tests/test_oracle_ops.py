@@ -188,3 +188,24 @@ def test_loss_difference_backends_agree(kind):
   if kind == "SMAPE":
     assert np.all(a <= 3.0) and np.all(a >= 0)
     np.testing.assert_allclose(np_ops.loss_difference(p, p, kind), 0)
+
+
+def test_ms_ssim_oracle_known_answers():
+  """tf.image.ssim_multiscale restated (oracle/reference_loss.py): identical images score exactly 1, the Gaussian is
+  normalised with centre weight (1 / sum_i exp(-i^2 / 4.5))^2, the score is symmetric in its arguments, falls with noise, and a
+  constant offset only touches the luminance term of the LAST scale (cs is offset invariant)."""
+  import torch
+  from oracle import reference_loss as rl
+  g = rl._fspecial_gauss(11, 1.5, torch.float64)
+  c = torch.arange(11, dtype=torch.float64) - 5
+  assert abs(float(g.sum()) - 1.0) < 1e-12 and abs(float(g[5, 5]) - float(1.0 / torch.exp(-c ** 2 / 4.5).sum()) ** 2) < 1e-12
+  torch.manual_seed(0)
+  x = torch.rand(2, 48, 52, 3, dtype=torch.float64)
+  assert float((rl.ssim_multiscale(x, x) - 1).abs().max()) < 1e-12 and abs(float(rl.ms_ssim_loss(x, x))) < 1e-12
+  y1, y2 = x + 0.05 * torch.randn_like(x), x + 0.2 * torch.randn_like(x)
+  s1, s2 = rl.ssim_multiscale(x, y1), rl.ssim_multiscale(x, y2)
+  assert bool((s1 > s2).all()) and bool((s1 < 1).all())
+  assert float((rl.ssim_multiscale(x, y1) - rl.ssim_multiscale(y1, x)).abs().max()) < 1e-12
+  # offset: structure terms unchanged, so only the luminance factor of the last scale (power 0.3001) can lower the score
+  off = rl.ssim_multiscale(x, x + 0.3)
+  assert bool((off < 1).all()) and bool((off > 0.5).all())
