@@ -333,11 +333,14 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
 #pragma unroll
             for (int i = 0; i < 4; ++i) pf[i] = row_plan[4 + i];
             const bool initialises = (r_lo == rm_lo);
+            if (tr) p.trace[it * 8 + 1] = clock64();                                      // plan in registers
             for (int c = 0; c < n_chunks; ++c) {
               const int ksteps = (c == n_chunks - 1) ? p.ksteps_last : 4;
               if (!(c == 0 && probed && probe_a)) mbar_wait(&a_full[a_slot], a_phase);
               if (c == 0 && initialises && !(probed && probe_e))
                 mbar_wait(&acc_empty[blk], (use & 1u) ^ 1u);                              // previous user drained
+              if (tr && c == 0) p.trace[it * 8 + 7] = clock64() | (static_cast<unsigned long long>((probed && probe_a) ? 1 : 0) << 62) |
+                                                      (static_cast<unsigned long long>((probed && probe_e) ? 1 : 0) << 61);
               tc_fence_after();
               if (tr && c == 0) p.trace[it * 8 + 2] = clock64();
               if (c == 0) {

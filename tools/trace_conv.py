@@ -28,13 +28,16 @@ def run(n, h, w, cin, cout, ks, iters=3, f32_out=False, residual=False, relu_cop
   print('  group 6 stamps (tag:+cycles since previous):', ' '.join('%d:+%d' % (mm[i][0], mm[i][1] - mm[i - 1][1]) for i in range(1, len(mm))))
   base = int(t[0, 0])
   print("conv %dx%dx%d %d->%d k%d: rows = tile iteration; cycles relative to start" % (n, h, w, cin, cout, ks))
-  print("  it | grp:enter        -   a_full   issued | epi:enter  t_full    done | mma_busy epi_busy  period  (mma: per group of G rows; epi: per row)")
+  print("  it | grp:enter     plan   a_full   issued | epi:enter  t_full    done | mma_busy epi_busy  period | waits_done probe_a probe_e")
   prev = None
   for i in range(12):
+    raw7 = int(t[i, 7])
+    pa, pe = (raw7 >> 62) & 1, (raw7 >> 61) & 1
+    t7 = (raw7 & ((1 << 61) - 1)) - base
     r = [int(v) - base for v in t[i]]
     period = (r[3] - prev) if prev is not None else 0
     prev = r[3]
-    print("  %2d | %9d %8d %8d %8d | %9d %8d %8d | %8d %8d %8d" % (i, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[3] - r[2], r[6] - r[5], period))
+    print("  %2d | %9d %8d %8d %8d | %9d %8d %8d | %8d %8d %8d | %9d %d %d" % (i, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[3] - r[2], r[6] - r[5], period, t7, pa, pe))
 
 import sys as _s
 which = _s.argv[1] if len(_s.argv) > 1 else "big"
@@ -45,6 +48,3 @@ if which == "small":
   run(2, 1080, 1920, 64, 25, 1)
 else:
   run(1, 1080, 1920, 64, 64, 3)
-  run(1, 1080, 1920, 128, 64, 3)
-  run(1, 540, 960, 96, 96, 3)
-  run(1, 1080, 1920, 64, 25, 1)
