@@ -348,3 +348,29 @@ def test_bfloat16_training_and_inference():
   losses = [float(tr.train_step(f, t).item()) for _ in range(10)]
   print("bf16 losses", ["%.4f" % l for l in losses])
   assert losses[-1] < losses[0] - 0.3
+
+
+def test_exact_training_path_matches_committed_golden():
+  """The exact CUDA training path against the COMMITTED fixture tests/golden/training_example.npz (float64 oracle autograd;
+  loss weights of TrainingExample.json + variation / masked-mean terms): loss to 1e-5, every gradient to 2e-3 of its scale."""
+  import importlib.util, os
+  here = os.path.dirname(os.path.abspath(__file__))
+  spec = importlib.util.spec_from_file_location("make_training_golden", os.path.join(here, "golden", "make_training_golden.py"))
+  gen = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(gen)
+  j, arch, weights, features, targets = gen.problem()
+  tj = {"loss_difference": "SMAPE",
+        "features_training_settings": {"loss_weights": {"mean": 1.0, "variation": 0.25, "ms_ssim": 0.0}},
+        "combined_features_training_settings": {"loss_weights": {"mean": 5.0, "variation": 0.5, "ms_ssim": 0.0},
+                                                "loss_weights_masked": {"mean": 1.0, "variation": 0.0, "ms_ssim": 0.0}},
+        "combined_image_training_settings": {"loss_weights": {"mean": 10.0, "variation": 0.0, "ms_ssim": 0.0}}}
+  jj = dict(j)
+  jj["b200"] = {"dtype": "float32"}
+  trainer = Trainer(Architecture(jj, weights=weights), TrainingSettings(tj))
+  trainer.forward({k: torch.from_numpy(v) for k, v in features.items()})
+  loss = float(trainer.loss_and_gradient({k: torch.from_numpy(v) for k, v in targets.items()}).item())
+  trainer.backward()
+  z = np.load(os.path.join(here, "golden", "training_example.npz"))
+  assert abs(loss - float(z["loss"])) <= 1e-5 * max(1.0, abs(float(z["loss"]))), (loss, float(z["loss"]))
+  want = {k[len("grad|"):]: z[k].astype(np.float64) for k in z.files if k.startswith("grad|")}
+  check_gradients(trainer, want)

@@ -105,3 +105,21 @@ def test_non_loaded_passes_return_source_crop():
     np.testing.assert_allclose(d["prediction/Volume Color"], np.log1p(1.0))
     np.testing.assert_allclose(d["prediction/Alpha Direct"], np.log1p(0.5))
     assert d["prediction/Volume Color"].shape[1] == 16 >> s
+
+
+def test_training_golden_is_reproduced_by_the_oracle():
+  """tests/golden/training_example.npz (loss + every parameter gradient of the restated loss, incl. variation and masked-mean
+  terms) is what the float64 torch oracle computes today."""
+  import importlib.util
+  import os
+  here = os.path.dirname(os.path.abspath(__file__))
+  spec = importlib.util.spec_from_file_location("make_training_golden", os.path.join(here, "golden", "make_training_golden.py"))
+  gen = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(gen)
+  j, arch, weights, features, targets = gen.problem()
+  loss, grads = gen.oracle_loss_and_gradients(j, weights, features, targets)
+  z = np.load(os.path.join(here, "golden", "training_example.npz"))
+  assert abs(loss - float(z["loss"])) <= 1e-9 * max(1.0, abs(loss))
+  for k, g in grads.items():
+    want = z["grad|" + k].astype(np.float64)
+    assert np.abs(g - want).max() <= 1e-6 * max(1e-6, np.abs(want).max()) + 1e-12, k
