@@ -171,3 +171,26 @@ def test_data_parallel_reduce_equals_the_global_batch_gradient(tmp_path):
   for rank in range(world):
     z = np.load(str(tmp_path / ("rank%d.npz" % rank)))
     assert np.allclose(z["grad"], want_grad, atol=1e-6) and abs(float(z["loss"][0]) - want_loss) < 1e-6
+
+
+def test_training_settings_parse_the_reference_json():
+  """TrainingSettings reads the loss blocks of TrainingExample.json (:31-98) and refuses only what the reference itself
+  cannot run."""
+  import json
+  import os
+  import pytest
+  from deepdenoiser_b200.training import TrainingSettings
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  s = TrainingSettings(json.load(open(os.path.join(root, "configs", "TrainingExample.json"))))
+  assert (s.feature_weight, s.combined_feature_weight, s.combined_image_weight) == (1.0, 5.0, 10.0)
+  assert s.loss_difference == "SMAPE" and s.use_multiscale_loss and s.learning_rate == 1e-3 and s.batch_size == 8
+  assert s.feature_variation_weight == 0.0 and s.feature_ms_ssim_weight == 0.0 and s.combined_feature_masked_weight == 0.0
+  s = TrainingSettings({"features_training_settings": {"loss_weights": {"mean": 2.0, "variation": 0.5, "ms_ssim": 0.25},
+                                                       "loss_weights_masked": {"mean": 0.75}}})
+  assert (s.feature_weight, s.feature_variation_weight, s.feature_ms_ssim_weight, s.feature_masked_weight) == (2.0, 0.5, 0.25, 0.75)
+  with pytest.raises(NotImplementedError):
+    TrainingSettings({"features_training_settings": {"loss_weights_masked": {"ms_ssim": 0.1}}})
+  with pytest.raises(NotImplementedError):
+    TrainingSettings({"combined_features_training_settings": {"loss_weights_masked": {"variation": 0.1}}})
+  with pytest.raises(NotImplementedError):
+    TrainingSettings({"combined_image_training_settings": {"loss_weights_masked": {"mean": 0.1}}})
