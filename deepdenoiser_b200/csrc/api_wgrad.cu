@@ -528,12 +528,8 @@ int dd_space_to_depth2_mask(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y
   return DD_OK;
 }
 
-int dd_relu_bwd_bias(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const dd_tensor* dz, float* db_dev, float scale,
-                     void* stream) {
-  DD_CHECK_ARG(ctx && tensor_ok(dy) && (!y || tensor_ok(y)) && (!dz || tensor_ok(dz)), "bad argument");
-  DD_CHECK_ARG(dy->c <= 1024, "relu_bwd_bias: at most 1024 channels");
-  DD_CHECK_ARG(!y || (y->n == dy->n && y->h == dy->h && y->w == dy->w && y->c == dy->c), "relu_bwd_bias: y differs from dy");
-  DD_CHECK_ARG(!dz || (dz->n == dy->n && dz->h == dy->h && dz->w == dy->w && dz->c == dy->c), "relu_bwd_bias: dz differs from dy");
+static int relu_bwd_bias_launch(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const dd_tensor* dz, float* db_dev, float scale,
+                                cudaStream_t stream) {
   ReluBiasParams p;
   p.dy = make_view(dy); p.y = y ? make_view(y) : p.dy; p.dz = dz ? make_view(dz) : p.dy;
   p.db = db_dev; p.has_y = y ? 1 : 0; p.has_dz = dz ? 1 : 0; p.scale = scale;
@@ -545,10 +541,37 @@ int dd_relu_bwd_bias(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const
   const size_t cap = static_cast<size_t>(ctx->sm_count) * 8;
   if (blocks > cap) blocks = cap;
   blocks = (blocks + per - 1) / per * per;
-  if (vec) relu_bias_vec_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  else relu_bias_generic_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  if (vec) relu_bias_vec_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
+  else relu_bias_generic_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
+}
+
+int dd_relu_bwd_bias(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const dd_tensor* dz, float* db_dev, float scale,
+                     void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(dy) && (!y || tensor_ok(y)) && (!dz || tensor_ok(dz)), "bad argument");
+  DD_CHECK_ARG(dy->c <= 1024, "relu_bwd_bias: at most 1024 channels");
+  DD_CHECK_ARG(!y || (y->n == dy->n && y->h == dy->h && y->w == dy->w && y->c == dy->c), "relu_bwd_bias: y differs from dy");
+  DD_CHECK_ARG(!dz || (dz->n == dy->n && dz->h == dy->h && dz->w == dy->w && dz->c == dy->c), "relu_bwd_bias: dz differs from dy");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // channel counts like 25 or 441 (K*K logits) in 16-byte aligned 16-bit buffers: the first c & ~7 channels take the
+  // vectorised kernel, the remaining <= 7 the generic one
+  auto base_ok = [](const dd_tensor* t) { return is_half_type(t->dtype) && t->coff % 8 == 0 && t->cstride % 8 == 0; };
+  const int head = dy->c & ~7;
+  if (dy->c % 8 != 0 && head >= 8 && base_ok(dy) && (!y || base_ok(y)) && (!dz || base_ok(dz))) {
+    dd_tensor a = *dy, b, c;
+    if (y) b = *y;
+    if (dz) c = *dz;
+    a.c = head; if (y) b.c = head; if (dz) c.c = head;
+    int rc = relu_bwd_bias_launch(ctx, &a, y ? &b : nullptr, dz ? &c : nullptr, db_dev, scale, s);
+    if (rc) return rc;
+    const int tail = dy->c - head;
+    a.coff += head; a.c = tail;
+    if (y) { b.coff += head; b.c = tail; }
+    if (dz) { c.coff += head; c.c = tail; }
+    return relu_bwd_bias_launch(ctx, &a, y ? &b : nullptr, dz ? &c : nullptr, db_dev ? db_dev + head : nullptr, scale, s);
+  }
+  return relu_bwd_bias_launch(ctx, dy, y, dz, db_dev, scale, s);
 }
 
 }  // extern "C"
