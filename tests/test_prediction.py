@@ -170,3 +170,25 @@ def test_prediction_cli_matches_tiled_oracle(tmp_path):
       predict_fn=lambda f: {k: torch.from_numpy(v) for k, v in oracle.predict_numpy({kk: vv.numpy() for kk, vv in f.items()})[0].items()})
   err = np.abs(got - want["prediction/Diffuse Direct"].numpy()).max()
   assert err <= 1e-4, err
+
+
+def test_tile_grid_partitions_any_image_exactly():
+  """Property (ragged sizes): for any image at least 16 pixels wide the kept crops of the reference's tile grid
+  (Prediction.py:259-310, 396-427) cover every pixel exactly once and every tile lies inside the image."""
+  from hypothesis import given, settings, strategies as st
+
+  @settings(max_examples=120, deadline=None)
+  @given(h=st.integers(16, 400), w=st.integers(16, 400), tile=st.sampled_from([32, 64, 128]), overlap=st.integers(2, 14))
+  def check(h, w, tile, overlap):
+    if 2 * overlap >= tile // 2:
+      return
+    tiles, size, ov = prediction.tile_grid(h, w, tile, overlap)
+    cover = np.zeros((h, w), dtype=np.int32)
+    for t in tiles:
+      assert 0 <= t.y and t.y + size <= h and 0 <= t.x and t.x + size <= w
+      dy0, dy1, dx0, dx1 = t.dest
+      assert (dy1 - dy0, dx1 - dx0) == (t.crop[1] - t.crop[0], t.crop[3] - t.crop[2])
+      cover[dy0:dy1, dx0:dx1] += 1
+    assert cover.min() == 1 and cover.max() == 1
+
+  check()

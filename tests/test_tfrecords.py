@@ -117,3 +117,25 @@ def test_tile_dataset_matches_what_was_written(tmp_path):
   r0 = list(ds.batches(2, shuffle_seed=None, rank=0, world=2))
   r1 = list(ds.batches(2, shuffle_seed=None, rank=1, world=2))
   assert len(r0) + len(r1) == (5 * 4) // 2 - 0 or len(r0) + len(r1) >= 8
+
+
+def test_example_round_trip_property():
+  """Property: serialize_example / parse_example and the record framing round-trip arbitrary feature dictionaries."""
+  from hypothesis import given, settings, strategies as st
+  names = st.text(alphabet="abcdefghijklmnopqrstuvwxyz/ _0123456789", min_size=1, max_size=24)
+  values = st.one_of(st.binary(min_size=0, max_size=300),
+                     st.lists(st.floats(-1e6, 1e6, width=32), min_size=1, max_size=20).map(lambda v: np.array(v, np.float32)),
+                     st.lists(st.integers(-2 ** 62, 2 ** 62), min_size=1, max_size=20).map(lambda v: np.array(v, np.int64)))
+
+  @settings(max_examples=60, deadline=None)
+  @given(features=st.dictionaries(names, values, min_size=0, max_size=6))
+  def check(features):
+    back = tfrecords.parse_example(tfrecords.serialize_example(features))
+    assert set(back) == set(features)
+    for k, v in features.items():
+      if isinstance(v, bytes):
+        assert bytes(back[k][0]) == v
+      else:
+        assert np.array_equal(np.asarray(back[k]), v)
+
+  check()
