@@ -29,7 +29,7 @@ parser.add_argument("--data_format", type=str, default="channels_first", choices
                     help="Accepted for compatibility; the device layout is always NHWC.")
 parser.add_argument("--full_frame", action="store_true",
                     help="Denoise the whole frame at once instead of 128x128 tiles (no 1.65x overlap overhead).")
-parser.add_argument("--dtype", default=None, choices=["float16", "float32"], help="Override the JSON's b200.dtype.")
+parser.add_argument("--dtype", default=None, choices=["float16", "bfloat16", "float32"], help="Override the JSON's b200.dtype.")
 parser.add_argument("--weights", default=None, help=".npz with the variables (TF names); default: seeded initialisation.")
 
 
