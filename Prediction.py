@@ -30,7 +30,8 @@ parser.add_argument("--data_format", type=str, default="channels_first", choices
 parser.add_argument("--full_frame", action="store_true",
                     help="Denoise the whole frame at once instead of 128x128 tiles (no 1.65x overlap overhead).")
 parser.add_argument("--dtype", default=None, choices=["float16", "bfloat16", "float32"], help="Override the JSON's b200.dtype.")
-parser.add_argument("--weights", default=None, help=".npz with the variables (TF names); default: seeded initialisation.")
+parser.add_argument("--weights", default=None,
+                    help=".npz with the variables (TF names); default: the latest Training.py checkpoint in the JSON's model_directory.")
 
 
 def main(parsed_arguments):
@@ -50,9 +51,14 @@ def main(parsed_arguments):
     import torch.distributed as dist
     dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
   weights = None
-  if parsed_arguments.weights:
-    import numpy as np
-    weights = dict(np.load(parsed_arguments.weights))
+  checkpoint = parsed_arguments.weights or prediction.latest_checkpoint(
+      parsed_architecture_json.get("model_directory", ""), os.path.dirname(os.path.abspath(parsed_arguments.json_filename)))
+  if checkpoint:
+    weights = prediction.load_checkpoint_weights(checkpoint)
+    if rank == 0:
+      print("weights:", checkpoint)
+  elif rank == 0:
+    print("weights: seeded initialisation (no checkpoint in the model directory, no --weights)")
   architecture = Architecture(parsed_architecture_json, source_data_format="channels_last",
                               data_format=parsed_arguments.data_format, device=local, weights=weights)
   features, height, width = prediction.load_features(architecture, parsed_arguments.input)

@@ -18,6 +18,25 @@ from .Naming import Naming
 from .RenderPasses import RenderPasses
 
 
+# ------------------------------------------------------------------------------------------------ checkpoints
+def latest_checkpoint(model_directory, base_directory=None):
+  """The newest `ckpt-<step>.npz` written by Training.py in the architecture's model_directory (tf.estimator.Estimator restores
+  the latest checkpoint of model_dir for predict(), Prediction.py:327-331).  The directory is tried relative to the JSON's
+  directory first (where Training.py writes), then relative to the working directory (the reference's behaviour)."""
+  import glob
+  for root in ([base_directory] if base_directory else []) + [os.getcwd()]:
+    found = glob.glob(os.path.join(root, model_directory, "ckpt-*.npz"))
+    if found:
+      return max(found, key=lambda path: int(os.path.basename(path)[len("ckpt-"):-len(".npz")]))
+  return None
+
+
+def load_checkpoint_weights(path):
+  """{TF variable name: array} of a Training.py checkpoint (Adam moments and the step counter are dropped)."""
+  z = np.load(path)
+  return {k: z[k] for k in z.files if k != "step" and not k.startswith("adam_m/") and not k.startswith("adam_v/")}
+
+
 # ------------------------------------------------------------------------------------------------ EXR input
 def exr_files(directory):
   """OpenEXRDirectory._exr_files (OpenEXRDirectory.py:118-124)."""

@@ -192,3 +192,17 @@ def test_tile_grid_partitions_any_image_exactly():
     assert cover.min() == 1 and cover.max() == 1
 
   check()
+
+
+def test_latest_checkpoint_is_found_and_stripped_of_optimizer_state(tmp_path):
+  """Prediction restores the newest Training.py checkpoint of the model directory (the Estimator's behaviour)."""
+  model = tmp_path / "Models" / "Example"
+  model.mkdir(parents=True)
+  assert prediction.latest_checkpoint("Models/Example", str(tmp_path)) is None
+  for step in (5, 500, 20):
+    np.savez(str(model / ("ckpt-%d.npz" % step)), step=np.array(step), **{"a/kernel": np.full((2, 2), float(step), np.float32),
+             "adam_m/a/kernel": np.zeros((2, 2), np.float32), "adam_v/a/kernel": np.zeros((2, 2), np.float32)})
+  path = prediction.latest_checkpoint("Models/Example", str(tmp_path))
+  assert os.path.basename(path) == "ckpt-500.npz"
+  weights = prediction.load_checkpoint_weights(path)
+  assert list(weights) == ["a/kernel"] and float(weights["a/kernel"][0, 0]) == 500.0
