@@ -209,3 +209,36 @@ def test_ms_ssim_oracle_known_answers():
   # offset: structure terms unchanged, so only the luminance factor of the last scale (power 0.3001) can lower the score
   off = rl.ssim_multiscale(x, x + 0.3)
   assert bool((off < 1).all()) and bool((off > 0.5).all())
+
+
+def test_two_restatements_agree_on_random_shapes():
+  """Property: the numpy (im2col / loops) and the torch (F.conv2d / pooling) restatements of the TF operators agree to 1e-10
+  in float64 on random shapes, including odd sizes where TF 'SAME' pads only the tail."""
+  import torch
+  from hypothesis import given, settings, strategies as st
+  from oracle import torch_ops
+
+  @settings(max_examples=40, deadline=None)
+  @given(n=st.integers(1, 2), h=st.integers(2, 13), w=st.integers(2, 13), cin=st.integers(1, 5), cout=st.integers(1, 5),
+         ks=st.sampled_from([1, 3]), seed=st.integers(0, 10 ** 6))
+  def check(n, h, w, cin, cout, ks, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, h, w, cin))
+    k = rng.standard_normal((ks, ks, cin, cout))
+    b = rng.standard_normal(cout)
+    tx = torch.from_numpy(x)
+    close = lambda a, t: np.abs(a - t.numpy()).max() <= 1e-10   # noqa: E731
+    assert close(np_ops.conv2d_same(x, k, b, relu=True), torch_ops.conv2d_same(tx, torch.from_numpy(k), torch.from_numpy(b), relu=True))
+    for pk in (2, 3):
+      assert close(np_ops.max_pool_same_s2(x, pk), torch_ops.max_pool_same_s2(tx, pk))
+    assert close(np_ops.avg_pool_same(x, 2), torch_ops.avg_pool_same(tx, 2))
+    kt = rng.standard_normal((3, 3, cout, cin))
+    assert close(np_ops.conv2d_transpose_same_s2(x, kt, b), torch_ops.conv2d_transpose_same_s2(tx, torch.from_numpy(kt), torch.from_numpy(b)))
+    ksz = 3
+    logits = rng.standard_normal((n, h, w, ksz * ksz))
+    src = rng.standard_normal((n, h, w, 3))
+    if h >= 2 and w >= 2:
+      assert close(np_ops.kernel_prediction(src, logits, ksz), torch_ops.kernel_prediction(torch.from_numpy(src), torch.from_numpy(logits), ksz))
+    assert close(np_ops.variance_feature(src), torch_ops.variance_feature(torch.from_numpy(src)))
+
+  check()
