@@ -47,9 +47,14 @@ def main(parsed_arguments):
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
   local = int(os.environ.get("LOCAL_RANK", "0"))
+  if torch.cuda.is_available():
+    torch.cuda.set_device(local)        # every launch uses torch.cuda.current_stream() of THIS device
   if world > 1:
     import torch.distributed as dist
-    dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+    if torch.cuda.is_available():
+      dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+      dist.init_process_group("gloo")
   weights = None
   checkpoint = parsed_arguments.weights or prediction.latest_checkpoint(
       parsed_architecture_json.get("model_directory", ""), os.path.dirname(os.path.abspath(parsed_arguments.json_filename)))

@@ -44,6 +44,8 @@ parser.add_argument("--steps_per_epoch", type=int, default=10)
 parser.add_argument("--checkpoint_steps", type=int, default=500)
 parser.add_argument("--write_synthetic_tfrecords", type=int, default=0,
                     help="Write this many synthetic tiles as <base_tfrecords_directory>/training (reference format) and use them.")
+parser.add_argument("--micro_batch", type=int, default=None,
+                    help="Tiles per forward/backward pass on each rank (gradient accumulation); default: the whole per-rank batch.")
 parser.add_argument("--precision", default=None, choices=["float32", "float16", "bfloat16"],
                     help="float16 (default): tensor-core path (fp16 activations, fp32 master weights); float32: exact path.")
 
@@ -78,11 +80,63 @@ def write_synthetic_dataset(architecture, directory, tiles, size, seed=4242):
   return tfrecords.write_tile_dataset(directory, "training", examples(), settings)
 
 
+_DATASETS = {}
+
+
+def tile_dataset(architecture, training_json, base, mode, settings_name=None):
+  """One TileDataset per (mode, sidecar json), cached: its per-file record counts are computed once."""
+  directory = os.path.join(base, training_json["base_tfrecords_directory"])
+  key = (mode, settings_name)
+  if key not in _DATASETS:
+    _DATASETS[key] = tfrecords.TileDataset(
+        os.path.join(directory, mode), os.path.join(directory, (settings_name or mode) + ".json"), architecture,
+        number_of_source_index_tuples=int(training_json.get("number_of_source_index_tuples", 1)))
+  return _DATASETS[key]
+
+
+def validation_sets(architecture, training_json, base):
+  """evaluation_jsons + extract_evaluation_json_information (Training.py:916-941, 1236-1250): one evaluation per
+  `validation*.json` sidecar (statistics files excluded); with group_by_samples_per_pixel the records of `validation_<spp>.json`
+  live under `validation/<spp>`, otherwise directly under `validation`."""
+  directory = os.path.join(base, training_json["base_tfrecords_directory"])
+  out = []
+  for name in sorted(os.listdir(directory)):
+    stem, ext = os.path.splitext(name)
+    if not (stem.startswith("validation") and ext == ".json" and "statistics" not in stem and
+            os.path.isfile(os.path.join(directory, name))):
+      continue
+    with open(os.path.join(directory, name), "r", encoding="utf-8") as f:
+      spp = json.load(f)["source_samples_per_pixel_list"][0]
+    sub = os.path.join("validation", str(spp))
+    mode = sub if os.path.isdir(os.path.join(directory, sub)) else "validation"
+    if os.path.isdir(os.path.join(directory, mode)):
+      out.append((stem, tile_dataset(architecture, training_json, base, mode, stem)))
+  return out
+
+
+def validate(trainer, datasets, per_rank, rank, world, threads=0):
+  """estimator.evaluate (Training.py:866-877): the mean loss over the validation records, no augmentation, no shuffle, every
+  rank evaluates its share and the (sum, count) pair is all-reduced.  Returns {name: mean loss}."""
+  results = {}
+  for name, dataset in datasets:
+    total = torch.zeros(2, dtype=torch.float64, device=trainer.dev)
+    for sources, targets in dataset.batches(per_rank, shuffle_seed=None, rank=rank, world=world, drop_remainder=False,
+                                            threads=threads):
+      n = next(iter(targets.values())).shape[0]
+      trainer.forward({k: torch.from_numpy(v) for k, v in sources.items()})
+      loss = trainer.loss_and_gradient({k: torch.from_numpy(v) for k, v in targets.items()})
+      total[0] += loss.double().squeeze() * n
+      total[1] += n
+    if world > 1:
+      import torch.distributed as dist
+      dist.all_reduce(total)
+    results[name] = float((total[0] / total[1].clamp(min=1)).item())
+  return results
+
+
 def tfrecord_batches(architecture, training_json, base, per_rank, rank, world, trainer, epoch_seed, threads=0):
   """input_fn_tfrecords (Training.py:728-850): records -> (sources, targets) examples -> device augmentation -> batches."""
-  directory = os.path.join(base, training_json["base_tfrecords_directory"])
-  dataset = tfrecords.TileDataset(os.path.join(directory, "training"), os.path.join(directory, "training.json"), architecture,
-                                  number_of_source_index_tuples=int(training_json.get("number_of_source_index_tuples", 1)))
+  dataset = tile_dataset(architecture, training_json, base, "training")
   usage = augmentation.DataAugmentationUsage.from_json(training_json)
   augment = augmentation.DeviceAugmenter(trainer.ctx, usage)
   rng = np.random.default_rng(epoch_seed * 7919 + rank)
@@ -101,6 +155,7 @@ def main(parsed_arguments):
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
   local = int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local)          # every launch below uses torch.cuda.current_stream() of THIS device
   if world > 1:
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -150,23 +205,40 @@ def main(parsed_arguments):
       if use_records:
         size = next(iter(features.values())).shape[1]
       t0 = time.perf_counter()
-      loss = float(trainer.train_step(features, targets, world_size=world, comm=comm).item())
+      loss = float(trainer.train_step(features, targets, world_size=world, comm=comm,
+                                      micro_batch=parsed_arguments.micro_batch).item())
       dt = time.perf_counter() - t0
+      skipped, scale_factor = trainer.update_loss_scale()      # the .item() above synchronised anyway
       if rank == 0:
         rec = {"step": trainer.step_count, "epoch": epoch, "loss": loss, "learning_rate": settings.learning_rate,
                "batch_size": global_tiles, "tile": size, "ranks": world, "seconds": dt, "precision": precision,
                "megapixels_per_second": global_tiles * size * size / 1e6 / dt}
+        if precision == "float16":
+          rec.update({"skipped_steps": skipped, "loss_scale_factor": scale_factor})
         log.write(json.dumps(rec) + "\n")
         log.flush()
         print(json.dumps(rec))
       if rank == 0 and trainer.step_count % parsed_arguments.checkpoint_steps == 0:
         trainer.save_checkpoint(os.path.join(model_dir, "ckpt-%d.npz" % trainer.step_count))
     if parsed_arguments.validate and (epoch + 1) % parsed_arguments.validation_interval == 0:
-      features, targets = synthetic_batch(architecture, per_rank, size, seed=424243 + rank)
-      trainer.forward(features)
-      val = float(trainer.loss_and_gradient(targets).item())
-      if rank == 0:
-        print(json.dumps({"validation_loss": val, "epoch": epoch, "step": trainer.step_count}))
+      if use_records:
+        # the reference evaluates on <base_tfrecords_directory>/validation (Training.py:1236-1250, 1268-1282)
+        results = validate(trainer, validation_sets(architecture, training_json, base), per_rank, rank, world,
+                           threads=min(8, max(1, int(parsed_arguments.threads) // max(1, world))))
+        if rank == 0:
+          rec = {"validation_loss": results, "epoch": epoch, "step": trainer.step_count}
+          log.write(json.dumps(rec) + "\n")
+          log.flush()
+          print(json.dumps(rec))
+      else:
+        features, targets = synthetic_batch(architecture, per_rank, size, seed=424243 + rank)
+        trainer.forward(features)
+        val = trainer.loss_and_gradient(targets).clone()
+        if world > 1:
+          dist.all_reduce(val)
+          val /= world
+        if rank == 0:
+          print(json.dumps({"validation_loss": {"synthetic": float(val.item())}, "epoch": epoch, "step": trainer.step_count}))
   if rank == 0:
     trainer.save_checkpoint(os.path.join(model_dir, "ckpt-%d.npz" % trainer.step_count))
   if world > 1:

@@ -100,6 +100,8 @@ SIGNATURES = {
     "dd_channel_sum": (_i, [_vp, _T, _i, _vp, _vp]),
     "dd_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                           ctypes.c_int64, ctypes.c_float, _vp]),
+    "dd_adam_step_guarded": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                  ctypes.c_float, _vp, _vp]),
     "dd_crc32c": (ctypes.c_uint32, [ctypes.c_char_p, _sz]),
     "dd_augment_tiles": (_i, [_vp, _T, _i, _vp, _vp, _vp, _vp, _T, _vp]),
     "dd_tiles_gather": (_i, [_vp, _T, _vp, _T, _vp]),
@@ -185,9 +187,10 @@ class Context:
     if rc != 0:
       raise DDError("libdd_b200 error %d: %s" % (rc, self.lib.dd_last_error().decode()))
 
-  @staticmethod
-  def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+  def _stream(self=None):
+    """The caller's current stream ON THIS CONTEXT'S DEVICE (not on whatever device is current)."""
+    device = self.device if isinstance(self, Context) else None
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
   # -- context
   def sm_count(self):
@@ -316,7 +319,7 @@ class Communicator:
 
   def all_reduce_sum(self, tensor):
     assert tensor.dtype == torch.float32 and tensor.is_cuda and tensor.is_contiguous()
-    self.ctx._check(self.ctx.lib.dd_comm_allreduce_sum_f32(self.handle, tensor.data_ptr(), tensor.numel(), Context._stream()))
+    self.ctx._check(self.ctx.lib.dd_comm_allreduce_sum_f32(self.handle, tensor.data_ptr(), tensor.numel(), self.ctx._stream()))
 
   def close(self):
     if self.handle:

@@ -570,6 +570,39 @@ __global__ void __launch_bounds__(256) adam_kernel(float* w, const float* g, flo
   w[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
 
+// ---- overflow-guarded optimizer step (fp16 training): no host synchronisation anywhere
+// state (device, int32[4]): [0] steps skipped so far, [1] "this step saw a non-finite gradient", [2] steps applied,
+//                           [3] bit pattern of the lr_t (float) of the step being applied
+__global__ void __launch_bounds__(256) nonfinite_kernel(const float* g, size_t n, int* state) {
+  bool bad = false;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float v = g[i];
+    bad |= !(fabsf(v) <= 3.0e38f);        // inf and NaN both fail
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(state + 1, 1);
+}
+__global__ void adam_decide_kernel(int* state, float lr, float b1, float b2) {
+  if (state[1]) {
+    state[0] += 1;
+  } else {
+    const int t = ++state[2];
+    const double lr_t = static_cast<double>(lr) * sqrt(1.0 - pow(static_cast<double>(b2), static_cast<double>(t))) /
+                        (1.0 - pow(static_cast<double>(b1), static_cast<double>(t)));
+    state[3] = __float_as_int(static_cast<float>(lr_t));
+  }
+}
+__global__ void __launch_bounds__(256) adam_guarded_kernel(float* w, const float* g, float* m, float* v, size_t n, const int* state,
+                                                           float b1, float b2, float eps, float gscale) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n || state[1]) return;
+  const float lr_t = __int_as_float(state[3]);
+  const float gi = g[i] * gscale;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
 // device-side weight repack after an optimizer step (fp32 exact path): TF [kh,kw,cin,cout] -> [tap][cout][cin] (forward)
 // and [flipped tap][cin][cout] (input-gradient convolution: a conv cout -> cin with the spatially flipped kernel)
 __global__ void __launch_bounds__(256) repack_f32_kernel(const float* w, float* fwd, float* bwd, int k2, int cin, int cout,
@@ -873,6 +906,22 @@ int dd_adam_step(dd_ctx* ctx, float* w, const float* g, float* m, float* v, size
                       (1.0 - pow(static_cast<double>(beta1), static_cast<double>(step)));
   adam_kernel<<<nblocks(count, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, g, m, v, count, static_cast<float>(lr_t),
                                                                                   beta1, beta2, epsilon, grad_scale);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_adam_step_guarded(dd_ctx* ctx, float* w, const float* g, float* m, float* v, size_t count, float lr, float beta1,
+                         float beta2, float epsilon, float grad_scale, int32_t* state_dev, void* stream) {
+  DD_CHECK_ARG(ctx && w && g && m && v && count > 0 && state_dev, "bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DD_CUDA(cudaMemsetAsync(state_dev + 1, 0, sizeof(int32_t), s));
+  unsigned blocks = nblocks(count, 256);
+  if (blocks > 1184u) blocks = 1184u;
+  nonfinite_kernel<<<blocks, 256, 0, s>>>(g, count, state_dev);
+  DD_LAUNCH_CHECK(ctx);
+  adam_decide_kernel<<<1, 1, 0, s>>>(state_dev, lr, beta1, beta2);
+  DD_LAUNCH_CHECK(ctx);
+  adam_guarded_kernel<<<nblocks(count, 256), 256, 0, s>>>(w, g, m, v, count, state_dev, beta1, beta2, epsilon, grad_scale);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }

@@ -286,16 +286,18 @@ class TileDataset:
       out.extend(self.examples_of_record(payload))
     return out
 
-  def examples(self, files=None, threads=0):
+  def examples(self, files=None, threads=0, with_file=False):
     """All (sources, targets) pairs of `files`, in file order.  threads > 0: files are read, gunzipped, CRC-checked and parsed
     by a pool of worker threads `threads` files ahead of the consumer (tf.data's num_parallel_reads / num_parallel_calls,
     Training.py:830-834; zlib and the CRC run outside the GIL), so the GPU step is not throttled by the input pipeline."""
-    files = list(files or self.files)
+    files = list(self.files if files is None else files)
     if threads <= 0:
       for path in files:
+        index = 0
         for payload in read_records(path, verify_crc=self.verify_crc):
           for pair in self.examples_of_record(payload):
-            yield pair
+            yield (path, index, pair) if with_file else pair
+            index += 1
       return
     import collections
     from concurrent.futures import ThreadPoolExecutor
@@ -303,28 +305,78 @@ class TileDataset:
       pending = collections.deque()
       it = iter(files)
       for path in it:
-        pending.append(pool.submit(self._examples_of_file, path))
+        pending.append((path, pool.submit(self._examples_of_file, path)))
         if len(pending) >= threads:
           break
       while pending:
-        done = pending.popleft().result()
+        path, future = pending.popleft()
+        done = future.result()
         nxt = next(it, None)
         if nxt is not None:
-          pending.append(pool.submit(self._examples_of_file, nxt))
-        for pair in done:
-          yield pair
+          pending.append((nxt, pool.submit(self._examples_of_file, nxt)))
+        for index, pair in enumerate(done):
+          yield (path, index, pair) if with_file else pair
+
+  def record_counts(self, threads=0):
+    """Records per file (framing only: gunzip + length fields, no CRC / parse), cached; aligned with self.files."""
+    if getattr(self, "_record_counts", None) is None:
+      def count(path):
+        return sum(1 for _ in read_records(path, verify_crc=False))
+      if threads > 0:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+          counts = list(pool.map(count, self.files))
+      else:
+        counts = [count(path) for path in self.files]
+      self._record_counts = dict(zip(self.files, counts))
+    return [self._record_counts[f] for f in self.files]
+
+  def examples_per_record(self):
+    return len(self.source_samples_per_pixel_list) * len(self.index_tuples)
+
+  def rank_share(self, files, rank, world):
+    """Example-granular sharding: the examples of `files` (in that order) form one global sequence, rank r owns the
+    contiguous range [r*per, (r+1)*per) with per = total // world, so EVERY rank sees the same number of examples (the
+    remainder is dropped) and therefore runs the same number of steps - each step holds a blocking all-reduce, unequal
+    counts would deadlock the job at the end of the epoch.  Returns [(file, first example, one past last example)]."""
+    self.record_counts()
+    per_record = self.examples_per_record()
+    counts = [self._record_counts[f] * per_record for f in files]
+    total = sum(counts)
+    per = total // world
+    lo, hi = rank * per, (rank + 1) * per
+    out, start = [], 0
+    for f, c in zip(files, counts):
+      a, b = max(lo, start), min(hi, start + c)
+      if a < b:
+        out.append((f, a - start, b - start))
+      start += c
+    return out, per
 
   def batches(self, batch_size, epochs=1, shuffle_seed=None, rank=0, world=1, drop_remainder=True, threads=0):
-    """dataset.shuffle(20 * batch).batch(batch) (Training.py:836-839), files shuffled per epoch (:825-826) and sharded
-    round-robin over `world` ranks.  Yields (sources, targets) dictionaries of [B,S,S,C] float32 arrays."""
+    """dataset.shuffle(20 * batch).batch(batch) (Training.py:836-839), files shuffled per epoch (:825-826, with a seed every
+    rank shares) and sharded over `world` ranks at EXAMPLE granularity (rank_share): every rank yields the same number of
+    batches.  Yields (sources, targets) dictionaries of [B,S,S,C] float32 arrays."""
     rng = random.Random(shuffle_seed)
     for _ in range(epochs):
       files = list(self.files)
       if shuffle_seed is not None:
         rng.shuffle(files)
-      files = files[rank::world] if len(files) >= world else files
+      if world > 1:
+        share, _ = self.rank_share(files, rank, world)
+      else:
+        share = [(f, 0, None) for f in files]
+      bounds = {f: (a, b) for f, a, b in share}
+
+      def stream_of(share=share, bounds=bounds):
+        it = self.examples([f for f, _, _ in share], threads=threads, with_file=True)
+        for path, index, pair in it:
+          a, b = bounds[path]
+          if index >= a and (b is None or index < b):
+            yield pair
+
       pool, limit = [], (20 * batch_size if shuffle_seed is not None else batch_size)
-      stream = self.examples(files, threads=threads)
+      stream = stream_of()
       exhausted = False
       while True:
         while not exhausted and len(pool) < limit:

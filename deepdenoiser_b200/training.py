@@ -14,6 +14,7 @@ Two arithmetic modes:
 Loss weights of TrainingExample.json (mean weights; variation / MS-SSIM / masked weights must be 0).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -120,6 +121,12 @@ class Trainer:
     self.adam_m = torch.zeros_like(self.theta)
     self.adam_v = torch.zeros_like(self.theta)
     self.step_count = 0
+    # overflow guard of the fp16 path (dd_adam_step_guarded): [skipped, flag, applied, lr_t bits]; lives on the device so the
+    # step never synchronises with the host.  `loss_scale_factor` multiplies the per-batch default scale and is lowered by
+    # update_loss_scale() after skipped steps.
+    self.guard = torch.zeros(4, dtype=torch.int32, device=self.dev)
+    self.loss_scale_factor = 1.0
+    self._skipped_seen, self._clean_since = 0, 0
     self.set_weights(architecture.weights)
     self._buffers = {}
     self.loss_value = torch.zeros(1, dtype=torch.float32, device=self.dev)
@@ -762,6 +769,8 @@ class Trainer:
     kind = LOSS_KINDS[cfg.loss_difference]
     # static loss scale of the fp16 path: the per-pixel gradient of a mean over N*H*W pixels would underflow fp16
     S = float(self.loss_scale) if self.loss_scale is not None else (n * h * w / 8.0 if self.act_dtype == torch.float16 else 1.0)
+    if self.act_dtype == torch.float16:
+      S *= self.loss_scale_factor
     self._scale_used = S
     loss_scales = n_scales if cfg.use_multiscale_loss else 1
     norm = 1.0 / sum(1.0 / 4.0 ** s for s in range(loss_scales))
@@ -876,6 +885,15 @@ class Trainer:
       image_terms = [t for t in _IMAGE_TERMS if t in by_name and by_name[t].load_data]
       use_image = ((cfg.combined_image_weight > 0 or cfg.combined_image_variation_weight > 0 or
                     cfg.combined_image_ms_ssim_weight > 0) and len(lights) == 4 and len(image_terms) == 4)
+      wants_image = (cfg.combined_image_weight > 0 or cfg.combined_image_variation_weight > 0 or
+                     cfg.combined_image_ms_ssim_weight > 0)
+      if wants_image and not use_image and not getattr(self, "_warned_image", False):
+        # the reference would fail with a KeyError here (CombinedImageFeatureTraining.initialize, Training.py:475-495 reads all
+        # 16 passes); architectures that load fewer passes train without the combined-image term - said once, not silently
+        import warnings
+        warnings.warn("combined_image_training_settings has non-zero weights but the architecture does not load the 4 lighting "
+                      "triples + Emission / Environment / Volume passes: the combined-image loss term is omitted")
+        self._warned_image = True
       use_combined = (cfg.combined_feature_weight > 0 or cfg.combined_feature_variation_weight > 0 or
                       cfg.combined_feature_masked_weight > 0 or cfg.combined_feature_ms_ssim_weight > 0)
       shape = (n, h >> s, w >> s, 3)
@@ -935,11 +953,14 @@ class Trainer:
     return self.loss_value
 
   # ------------------------------------------------------------------------------------------ backward of everything
-  def backward(self):
+  def backward(self, accumulate=False):
+    """Fills self.grad with the gradient of the last loss_and_gradient(); `accumulate` adds to what is there (every
+    parameter-gradient kernel accumulates), which is how train_step runs micro-batches."""
     arch, ctx, st = self.arch, self.ctx, self._state
     n, n_scales = st["n"], st["n_scales"]
     targets = arch.feature_predictions
-    self.grad.zero_()
+    if not accumulate:
+      self.grad.zero_()
     g = list(self._dfinal)                       # dL/d finals
 
     def invert_bwd(dy, x, s, tag):
@@ -1000,38 +1021,110 @@ class Trainer:
     return self.grad
 
   # ------------------------------------------------------------------------------------------ one optimizer step
-  def train_step(self, features, targets_dict, world_size=1, comm=None):
-    """forward + loss + backward + (all-reduce) + Adam.  Returns the loss as a device scalar."""
-    self.forward(features)
-    loss = self.loss_and_gradient(targets_dict)
-    self.backward()
+  def train_step(self, features, targets_dict, world_size=1, comm=None, micro_batch=None):
+    """forward + loss + backward + (all-reduce) + Adam.  Returns the loss as a device scalar.
+
+    `micro_batch`: tiles per forward/backward pass.  The batch (dim 0 of every [N,H,W,C] entry) is cut into N/micro_batch
+    equal micro-batches whose gradients accumulate in the flat fp32 buffer before the ONE all-reduce and the ONE optimizer
+    step, so the result is the step of the whole batch (the loss is a mean, Training.py:128) with the activation memory of
+    a micro-batch: batch 128 x 256^2 x 32 ch (TrainingExample.json:15 scaled to BASELINE configs[4]) fits one GPU."""
+    n = next(iter(targets_dict.values())).shape[0]
+    if micro_batch is None or micro_batch >= n:
+      self.forward(features)
+      loss = self.loss_and_gradient(targets_dict)
+      self.backward()
+      parts = 1
+    else:
+      if n % micro_batch:
+        raise ValueError("batch of %d tiles is not a multiple of the micro-batch %d" % (n, micro_batch))
+      parts = n // micro_batch
+      total = torch.zeros(1, dtype=torch.float32, device=self.dev)
+
+      def cut(d, lo):
+        return {k: (v[lo:lo + micro_batch] if v.shape[0] == n else v) for k, v in d.items()}
+
+      for m in range(parts):
+        self.forward(cut(features, m * micro_batch))
+        total += self.loss_and_gradient(cut(targets_dict, m * micro_batch))
+        self.backward(accumulate=m > 0)
+      loss = total / parts
     scale = data_parallel_reduce(self.grad, loss, world_size, comm)
-    self.apply_gradients(scale)
+    self.apply_gradients(scale / parts)
     return loss
 
   def apply_gradients(self, scale=1.0):
-    """TF-form Adam on the flat buffers (the loss scale of the fp16 path is divided out here) + weight repack."""
+    """TF-form Adam on the flat buffers (the loss scale of the fp16 path is divided out here) + weight repack.  The fp16
+    path uses the guarded step: a gradient holding inf / NaN skips the update on the device (no host sync)."""
     scale /= getattr(self, "_scale_used", 1.0)
     self.step_count += 1
-    self.ctx.call("dd_adam_step", _fp(self.theta), _fp(self.grad), _fp(self.adam_m), _fp(self.adam_v),
-                  ctypes.c_size_t(self.count), ctypes.c_float(self.settings.learning_rate), ctypes.c_float(0.9),
-                  ctypes.c_float(0.999), ctypes.c_float(1e-8), ctypes.c_int64(self.step_count), ctypes.c_float(scale))
+    if self.act_dtype == torch.float16:
+      self.ctx.call("dd_adam_step_guarded", _fp(self.theta), _fp(self.grad), _fp(self.adam_m), _fp(self.adam_v),
+                    ctypes.c_size_t(self.count), ctypes.c_float(self.settings.learning_rate), ctypes.c_float(0.9),
+                    ctypes.c_float(0.999), ctypes.c_float(1e-8), ctypes.c_float(scale), _fp(self.guard))
+    else:
+      self.ctx.call("dd_adam_step", _fp(self.theta), _fp(self.grad), _fp(self.adam_m), _fp(self.adam_v),
+                    ctypes.c_size_t(self.count), ctypes.c_float(self.settings.learning_rate), ctypes.c_float(0.9),
+                    ctypes.c_float(0.999), ctypes.c_float(1e-8), ctypes.c_int64(self.step_count), ctypes.c_float(scale))
     self._repack()
 
+  def update_loss_scale(self, growth_interval=500):
+    """Dynamic part of the fp16 loss scale; call it wherever the host synchronises anyway (logging / checkpoints).  Reads
+    the number of optimizer steps the guard skipped: any new one halves the scale factor, `growth_interval` clean steps
+    double it again (never above the static default).  Returns (skipped steps in total, current factor)."""
+    if self.act_dtype != torch.float16:
+      return 0, 1.0
+    skipped = int(self.guard[0].item())
+    if skipped > self._skipped_seen:
+      self.loss_scale_factor *= 0.5 ** (skipped - self._skipped_seen)
+      self._skipped_seen, self._clean_since = skipped, self.step_count
+    elif self.step_count - self._clean_since >= growth_interval and self.loss_scale_factor < 1.0:
+      self.loss_scale_factor = min(1.0, self.loss_scale_factor * 2.0)
+      self._clean_since = self.step_count
+    return skipped, self.loss_scale_factor
+
+  def applied_steps(self):
+    """Optimizer steps actually applied (the guarded fp16 step may skip some)."""
+    return int(self.guard[2].item()) if self.act_dtype == torch.float16 else self.step_count
+
   # ------------------------------------------------------------------------------------------ checkpoints
-  def save_checkpoint(self, path):
-    state = {"step": np.array(self.step_count)}
+  def save_checkpoint(self, path, keep=5):
+    """ckpt-<step>.npz written atomically (temp file + os.replace, so an interrupted write never leaves a truncated
+    'latest' checkpoint); refuses non-finite weights; keeps the newest `keep` ckpt-*.npz of the directory."""
+    if not bool(torch.isfinite(self.theta[:self.count]).all().item()):
+      raise _lib.DDError("refusing to checkpoint non-finite weights (step %d)" % self.step_count)
+    state = {"step": np.array(self.applied_steps())}
     for name in self.offsets:
       off, shape = self.offsets[name]
       size = int(np.prod(shape))
       state[name] = self.theta[off:off + size].view(shape).cpu().numpy()
       state["adam_m/" + name] = self.adam_m[off:off + size].view(shape).cpu().numpy()
       state["adam_v/" + name] = self.adam_v[off:off + size].view(shape).cpu().numpy()
-    np.savez(path, **state)
+    path = str(path)
+    if not path.endswith(".npz"):
+      path += ".npz"
+    tmp = path + ".tmp.%d" % os.getpid()
+    with open(tmp, "wb") as f:
+      np.savez(f, **state)
+      f.flush()
+      os.fsync(f.fileno())
+    os.replace(tmp, path)
+    directory, base = os.path.split(path)
+    if keep and base.startswith("ckpt-"):
+      found = []
+      for name in os.listdir(directory or "."):
+        if name.startswith("ckpt-") and name.endswith(".npz"):
+          try:
+            found.append((int(name[5:-4]), name))
+          except ValueError:
+            pass
+      for _, name in sorted(found)[:-keep]:
+        os.remove(os.path.join(directory or ".", name))
 
   def load_checkpoint(self, path):
     z = np.load(path)
     self.step_count = int(z["step"])
+    self.guard.zero_()
+    self.guard[2] = self.step_count
     for name, (off, shape) in self.offsets.items():
       size = int(np.prod(shape))
       self.theta[off:off + size].copy_(torch.from_numpy(z[name]).reshape(-1))

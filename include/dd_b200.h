@@ -303,6 +303,13 @@ int dd_channel_sum(dd_ctx* ctx, const dd_tensor* x, int groups, float* out_dev, 
 int dd_adam_step(dd_ctx* ctx, float* w, const float* g, float* m, float* v, size_t count, float lr, float beta1, float beta2,
                  float epsilon, int64_t step, float grad_scale, void* stream);
 
+/* The same optimizer step guarded against fp16 overflow, without a host synchronisation: the step is skipped when the
+ * gradient holds an inf / NaN (so a non-finite value never reaches w, m or v).  state_dev: device int32[4], zero-initialised by
+ * the caller once: [0] steps skipped so far, [1] scratch flag, [2] steps applied (the `step` of the bias correction),
+ * [3] scratch.  The caller reads [0] whenever convenient (e.g. when it logs) to lower its loss scale. */
+int dd_adam_step_guarded(dd_ctx* ctx, float* w, const float* g, float* m, float* v, size_t count, float lr, float beta1,
+                         float beta2, float epsilon, float grad_scale, int32_t* state_dev, void* stream);
+
 /* ---- training input pipeline ----------------------------------------------------------------- */
 /* CRC-32C (Castagnoli) of a host buffer: the checksum of the TFRecord framing written by TFRecordsCreator.py:221-230
  * (tf.python_io.TFRecordWriter); host code, needs no device. */

@@ -142,6 +142,71 @@ def test_adam_step_is_tf_form_and_training_reduces_the_loss():
   assert torch.equal(other.theta, trainer.theta) and torch.equal(other.adam_v, trainer.adam_v)
 
 
+def test_micro_batches_accumulate_to_the_full_batch_step():
+  """train_step(micro_batch=m): gradients of the micro-batches accumulate in the flat buffer and ONE optimizer step follows,
+  so weights after the step equal the full-batch step (the loss is a mean over the batch, Training.py:128)."""
+  j = small_example(filters=(16, 24), n_convs=1, k=3)
+  host, weights, features, targets = make_problem(j, n=4, h=16, w=16)
+  f = {k: torch.from_numpy(v) for k, v in features.items()}
+  t = {k: torch.from_numpy(v) for k, v in targets.items()}
+  full = Trainer(Architecture(j, weights=weights), TrainingSettings({"learning_rate": 1e-3}))
+  loss_full = float(full.train_step(f, t).item())
+  grad_full = full.grad.clone()
+  for mb in (2, 1):
+    part = Trainer(Architecture(j, weights=weights), TrainingSettings({"learning_rate": 1e-3}))
+    loss_part = float(part.train_step(f, t, micro_batch=mb).item())
+    assert abs(loss_part - loss_full) <= 1e-5 * max(1.0, abs(loss_full)), (mb, loss_part, loss_full)
+    parts = 4 // mb
+    scale = float(grad_full.abs().max())
+    assert float((part.grad / parts - grad_full).abs().max()) <= 2e-5 * scale, mb
+    assert float((part.theta - full.theta).abs().max()) <= 2e-6, mb
+  with pytest.raises(ValueError):
+    full.train_step(f, t, micro_batch=3)
+
+
+def test_fp16_overflow_skips_the_step_on_the_device():
+  """dd_adam_step_guarded: a gradient holding inf / NaN must not reach the weights or the Adam moments; the skipped-step
+  counter and update_loss_scale() react, clean steps are applied with the TF-form bias correction of the APPLIED count."""
+  j = small_example(filters=(16, 24), n_convs=1, k=3)
+  host, weights, features, targets = make_problem(j, n=2, h=16, w=16)
+  f = {k: torch.from_numpy(v) for k, v in features.items()}
+  t = {k: torch.from_numpy(v) for k, v in targets.items()}
+  trainer = Trainer(Architecture(j, weights=weights), TrainingSettings({"learning_rate": 1e-3}), precision="float16")
+  trainer.forward(f)
+  trainer.loss_and_gradient(t)
+  trainer.backward()
+  good = trainer.grad.clone()
+  theta0 = trainer.theta.clone()
+  trainer.grad[17] = float("inf")
+  trainer.apply_gradients()
+  assert torch.equal(trainer.theta, theta0) and float(trainer.adam_m.abs().max()) == 0.0
+  assert trainer.guard.tolist()[0] == 1 and trainer.guard.tolist()[2] == 0
+  trainer.grad.copy_(good)
+  trainer.grad[5] = float("nan")
+  trainer.apply_gradients()
+  assert torch.equal(trainer.theta, theta0)
+  skipped, factor = trainer.update_loss_scale()
+  assert skipped == 2 and factor == 0.25
+  trainer.grad.copy_(good)
+  trainer.apply_gradients()
+  assert trainer.applied_steps() == 1 and not torch.equal(trainer.theta, theta0)
+  assert bool(torch.isfinite(trainer.theta).all())
+  # first applied step from zero moments == the unguarded TF-form step 1
+  ref = Trainer(Architecture(j, weights=weights), TrainingSettings({"learning_rate": 1e-3}), precision="bfloat16")
+  ref.grad.copy_(good)
+  ref._scale_used = trainer._scale_used
+  ref.apply_gradients()
+  assert float((ref.theta - trainer.theta).abs().max()) <= 1e-7
+  import os, tempfile
+  d = tempfile.mkdtemp()
+  for step in range(1, 8):
+    trainer.save_checkpoint(os.path.join(d, "ckpt-%d.npz" % step))
+  assert sorted(os.listdir(d)) == ["ckpt-%d.npz" % i for i in range(3, 8)]       # newest 5 kept, no temp files left
+  trainer.theta[3] = float("nan")
+  with pytest.raises(Exception):
+    trainer.save_checkpoint(os.path.join(d, "ckpt-9.npz"))
+
+
 # ------------------------------------------------------------------------------------------------ tensor-core (fp16) training
 # fp16 activations / activation gradients with fp32 accumulation, master weights and image-level arithmetic, compared with
 # the float64 oracle.  Tolerances: predictions 5e-2 max (same bound as the fp16 inference tests), loss 1e-2 relative.

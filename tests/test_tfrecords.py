@@ -113,10 +113,49 @@ def test_tile_dataset_matches_what_was_written(tmp_path):
   for (s0, t0), (s1, t1) in zip(got, threaded):
     assert s0.keys() == s1.keys() and all(np.array_equal(s0[k], s1[k]) for k in s0)
     assert all(np.array_equal(t0[k], t1[k]) for k in t0)
-  # sharding over ranks: disjoint files
-  r0 = list(ds.batches(2, shuffle_seed=None, rank=0, world=2))
-  r1 = list(ds.batches(2, shuffle_seed=None, rank=1, world=2))
-  assert len(r0) + len(r1) == (5 * 4) // 2 - 0 or len(r0) + len(r1) >= 8
+  # sharding over ranks is example-granular: 3 unequal files (2 + 2 + 1 records = 8 + 8 + 4 examples), every rank yields
+  # the SAME number of batches (each training step holds a blocking all-reduce) and the shares are disjoint
+  for world in (2, 3):
+    for seed in (None, 5):
+      per_rank = [list(ds.batches(2, shuffle_seed=seed, rank=r, world=world, threads=r)) for r in range(world)]
+      assert len({len(b) for b in per_rank}) == 1, [len(b) for b in per_rank]
+      assert len(per_rank[0]) == (20 // world) // 2
+      seen = set()
+      for batches_r in per_rank:
+        for sources, _ in batches_r:
+          for tile in sources[key]:
+            sig = tile.tobytes()
+            assert sig not in seen
+            seen.add(sig)
+      assert len(seen) == world * ((20 // world) // 2) * 2
+
+
+def test_more_ranks_than_files_share_examples_not_duplicates(tmp_path):
+  """len(files) < world used to hand every rank ALL files (the global batch repeated world times)."""
+  arch = Architecture(synthetic.example_architecture_json())
+  size = 8
+  rng = np.random.default_rng(11)
+  written = []
+  for e in range(8):
+    feats = {}
+    for fp in list(arch.feature_predictions) + list(arch.auxiliary_features):
+      if fp.load_data:
+        feats["source_image/16/0/" + fp.name] = rng.standard_normal((size, size, fp.number_of_channels)).astype(np.float32)
+        if fp.is_target:
+          feats["target_image/" + fp.name] = rng.standard_normal((size, size, fp.number_of_channels)).astype(np.float32)
+    written.append(feats)
+  settings = {"tiles_height_width": size, "number_of_sources_per_example": 1, "source_samples_per_pixel_list": [16]}
+  files = tfrecords.write_tile_dataset(str(tmp_path), "training", written, settings, examples_per_tfrecords=16)
+  assert len(files) == 1
+  ds = tfrecords.TileDataset(str(tmp_path / "training"), str(tmp_path / "training.json"), arch)
+  assert ds.record_counts() == [8]
+  key = "source_image/0/" + next(fp.name for fp in arch.feature_predictions if fp.load_data)
+  seen = []
+  for r in range(4):
+    b = list(ds.batches(2, shuffle_seed=3, rank=r, world=4))
+    assert len(b) == 1
+    seen += [t.tobytes() for t in b[0][0][key]]
+  assert len(set(seen)) == 8
 
 
 def test_example_round_trip_property():
