@@ -13,6 +13,9 @@ HOST buffers with the 17 full-resolution predictions copied back to the host ins
 downloads of neighbouring frames overlap the kernels: deepdenoiser_b200/pipeline.py).
 N > 1: one process per GPU (torchrun), every rank denoises its own frame (frames are independent: no
 data-path collective), barrier + max-over-ranks timing, weak scaling.
+The same line carries, under `train`, the data-parallel TRAINING step of BASELINE configs[4] (global batch 128 tiles of
+256x256x32-ch, bf16, STRONG scaling: 128/N tiles per rank in micro-batches, one NCCL all-reduce of the flat gradient per
+step through dd_comm_allreduce_sum_f32) and of configs[2] (Tiramisu K=21), so the driver's 1/2/4/8 sweep captures them.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -115,8 +118,11 @@ def run_reference(args, arch_json, weights, config):
   sample = ("%d tiles of 128x128 (overlap 14) x 17 tuple passes per step, scaled to the %d tiles of a 1080p frame; "
             "restated reference (oracle/reference_model.py on torch-CPU float32 / oneDNN), TensorFlow 1.x is not "
             "installable here" % (args.ref_tiles, tpf))
+  # a step of this arm is the bounded SAMPLE (ref_tiles of the frame's tpf tiles): ms_per_step is the time actually spent per step,
+  # `value` the throughput it implies for whole frames (sample pixels / sample time == frame pixels / (tpf * time per tile))
   line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": args.gpus,
-          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * HEIGHT * WIDTH / 1e6 / value,
+          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
+          "sample_fraction_of_frame": args.ref_tiles / float(tpf),
           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
           "config": config,
           "cpu_baseline": {"value": value, "unit": "MP/s", "cores": threads, "kind": "port", "sample": sample},
@@ -171,25 +177,174 @@ def conv_roofline(arch, feats_dev, steps):
   return flops / steps, ms / steps, len(records) // steps, core_tflops
 
 
-def l1_against_oracle(arch_json, weights, device):
-  """'L1 vs TF ref' of the metric: per-pixel |out - oracle| of the benchmarked fp16 path on a 32x64 crop of the same synthetic
-  render passes, against the float64 restatement of the reference (TensorFlow itself cannot run here), relative to
-  max(1, |oracle|max) of each output pass; mean and max over every pass of the full-resolution scale."""
-  from oracle import np_ops, reference_model
-  jj = dict(arch_json)
-  jj["b200"] = {"dtype": "float16"}
-  arch = Architecture(jj, weights=weights, device=device)
-  feats = synthetic.synthetic_features(arch, 1, 32, 64, seed=1234)
-  out = arch.predict({k: torch.from_numpy(v) for k, v in feats.items()})[0]
-  torch.cuda.synchronize()
-  want = reference_model.Architecture(arch_json, ops=np_ops, dtype=np.float64, weights=weights).predict_numpy(feats)[0]
-  means, worst = [], 0.0
+def oracle_full_frame(arch_json, weights, feats, threads):
+  """The restated reference (oracle/reference_model.py, torch-CPU float32 - the arithmetic type of the reference,
+  Training.py:518-524) on the FULL 1080p frame, all tuple passes: the 'TF ref' side of the metric's 'L1 vs TF ref'."""
+  from oracle import reference_model, torch_ops
+  torch.set_num_threads(threads)
+  t0 = time.perf_counter()
+  model = reference_model.Architecture(arch_json, ops=torch_ops, dtype=torch.float32, weights=weights)
+  with torch.no_grad():
+    want = model.predict(feats)[0]
+  return {k: v.numpy() if hasattr(v, "numpy") else np.asarray(v) for k, v in want.items()}, time.perf_counter() - t0
+
+
+def l1_of(out, want):
+  """per-pixel |out - oracle| relative to max(1, |oracle|max) of each output pass (full resolution scale):
+  mean and max per pass + the overall worst."""
+  per_pass, means, worst = {}, [], 0.0
   for k, w in want.items():
     scale = max(1.0, float(np.abs(w).max()))
-    err = np.abs(out[k].float().cpu().numpy().astype(np.float64) - w) / scale
+    err = np.abs(out[k].float().cpu().numpy() - w) / scale
+    per_pass[k[len("prediction/"):]] = [float(err.mean()), float(err.max())]
     means.append(float(err.mean()))
     worst = max(worst, float(err.max()))
-  return {"mean": float(np.mean(means)), "max": worst, "passes": len(means), "crop": "1x32x64", "reference": "float64 oracle (oracle/reference_model.py)"}
+  return {"mean": float(np.mean(means)), "max": worst, "passes": len(means), "per_pass_mean_max": per_pass}
+
+
+def hbm_rooflines(arch, pk):
+  """HBM-bound kernels of the kernel-prediction apply at 1080p (KernelPrediction.py:22-61), timed alone with CUDA events,
+  L2 flushed between repetitions (inputs of one launch are > 126 MB anyway):
+    post_kp_fused_kernel<5>   fused 1x1 post-process x2 + softmax + 5x5 apply of 8 x 1080p tuple passes; algorithmic bytes/px
+                              = 2*64 (fp16 backbone features) + 12 (source) + 12 (prediction) = 152
+    kernel_predict_tma_kernel K = 21 apply on materialised fp32 logits (the cfg3 / Tiramisu head): 441*4 + 12 + 12 B/px"""
+  from deepdenoiser_b200 import _lib
+  from deepdenoiser_b200.network import V
+  ctx, net, dev = arch.ctx, arch.network, arch.ctx.device
+  out = {}
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+  def timed(fn, reps=5):
+    ms = []
+    for _ in range(reps + 1):
+      ctx.l2_flush(flush)
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record(); fn(); e1.record()
+      torch.cuda.synchronize()
+      ms.append(e0.elapsed_time(e1))
+    return float(np.mean(ms[1:]))
+
+  n = 8
+  g = torch.Generator(device=dev).manual_seed(5)
+  src = torch.randn(n, HEIGHT, WIDTH, 3, device=dev, generator=g)
+  dst = torch.empty_like(src)
+  if net.can_fuse_post_kp(5, 1):
+    feat = torch.randn(n, HEIGHT, WIDTH, 64, device=dev, generator=g).half()
+    k = len(net.spec.post) - 1
+    fn = lambda: net.post_kernel_predict(k, V(feat), _lib.desc(src), 5, 1, n, _lib.desc(dst))  # noqa: E731
+    fn()
+    ms = timed(fn)
+    b = n * HEIGHT * WIDTH * 152.0
+    out["post_kp_fused_k5"] = {"bound": "hbm", "kernel": "post_kp_fused_kernel<5,1> (1x1 post-process x2 + softmax + 5x5 apply), 8 x 1080p",
+                               "bytes": b, "ms": ms, "achieved": b / ms / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                               "frac": b / ms / 1e6 / pk["hbm_gbs"]}
+    del feat
+  for ksize, nn in ((5, 8), (21, 2)):
+    k2 = ksize * ksize
+    cs = (k2 + 7) // 8 * 8
+    logits = torch.randn(nn, HEIGHT, WIDTH, cs, device=dev, generator=g)
+    fn = lambda: ctx.kernel_predict(_lib.desc(src[:nn]), _lib.desc(logits, k2, 0), ksize, 1, nn, _lib.desc(dst[:nn]))  # noqa: E731
+    fn()
+    ms = timed(fn)
+    b = nn * HEIGHT * WIDTH * (k2 * 4.0 + 24.0)
+    out["kernel_predict_k%d" % ksize] = {"bound": "hbm", "kernel": "kernel_predict_tma_kernel K=%d, fp32 logits, %d x 1080p" % (ksize, nn),
+                                         "bytes": b, "ms": ms, "achieved": b / ms / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                         "frac": b / ms / 1e6 / pk["hbm_gbs"]}
+    del logits
+  del flush
+  return out
+
+
+def measured_traffic():
+  """roofline.traffic comes from an ncu --set full capture of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum
+  of one launch); tools/ncu_summary.py writes it to profiles/ncu_traffic.json when a capture is taken.  None when absent."""
+  path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+  if os.path.exists(path):
+    try:
+      return json.load(open(path)).get("conv_rows_kernel")
+    except Exception:  # noqa: BLE001
+      return None
+  return None
+
+
+# ---------------------------------------------------------------------------------------------- training leg
+def training_leg(name, arch_name, global_batch, tile, micro_batch, precision, steps, warmup, rank, world, local, dist):
+  """Data-parallel training step (Training.py:700-702 is the step being replaced; TrainingExample.json:15 the batch knob):
+  STRONG scaling - the global batch is fixed, rank r trains global_batch/world tiles in micro-batches (gradient accumulation in
+  the flat fp32 buffer), then ONE ncclAllReduce of that buffer through the C ABI (dd_comm_allreduce_sum_f32) and the identical
+  Adam step on every rank.  Inputs resident in HBM; CUDA events, barrier on both sides, max over ranks."""
+  from deepdenoiser_b200 import _lib
+  from deepdenoiser_b200.training import Trainer, TrainingSettings
+  if global_batch % world:
+    return {"skipped": "global batch %d not divisible by %d ranks" % (global_batch, world)}
+  per_rank = global_batch // world
+  micro = min(micro_batch, per_rank)
+  j = synthetic.baseline_architecture_json(arch_name)
+  j["b200"] = {"dtype": "float32"}
+  arch = Architecture(j, device=local)
+  trainer = Trainer(arch, TrainingSettings({"learning_rate": 1e-4}), precision=precision)
+  comm = _lib.Communicator(trainer.ctx, rank, world) if world > 1 else None
+  distinct = min(per_rank, 8)                       # synthetic tiles are generated on the host: 8 distinct ones, repeated
+  noisy = synthetic.synthetic_features(arch, distinct, tile, tile, seed=77 + rank)
+  clean = synthetic.synthetic_features(arch, distinct, tile, tile, seed=7996 + rank)
+  rep = per_rank // distinct
+  feats = {k: torch.from_numpy(v).cuda().repeat(rep, 1, 1, 1) for k, v in noisy.items()}
+  targets = {"target_image/" + fp.name: torch.from_numpy(clean["source_image/0/" + fp.name]).cuda().repeat(rep, 1, 1, 1)
+             for fp in arch.feature_predictions if fp.load_data}
+
+  def barrier():
+    if dist is not None:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  losses = []
+  for _ in range(warmup):
+    losses.append(trainer.train_step(feats, targets, world_size=world, comm=comm, micro_batch=micro))
+  l0 = trainer.ctx.launch_count()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  e0.record()
+  for _ in range(steps):
+    losses.append(trainer.train_step(feats, targets, world_size=world, comm=comm, micro_batch=micro))
+  e1.record()
+  barrier()
+  launches = (trainer.ctx.launch_count() - l0) // steps
+  ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
+  # the exchange alone: the same all-reduce of the flat gradient buffer, timed back to back
+  ar = torch.zeros(1, device="cuda")
+  if comm is not None:
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scratch = trainer.grad.clone()
+    comm.all_reduce_sum(scratch)
+    barrier()
+    a0.record()
+    for _ in range(10):
+      comm.all_reduce_sum(scratch)
+    a1.record()
+    barrier()
+    ar = torch.tensor([a0.elapsed_time(a1) / 10], device="cuda")
+  if dist is not None:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dist.all_reduce(ar, op=dist.ReduceOp.MAX)
+  ms, ar = float(ms.item()), float(ar.item())
+  tuples = len(arch.feature_prediction_tuples)
+  mac = arch.spec.mac_per_pixel(arch.features_per_tuple)
+  flops = 3.0 * 2.0 * mac * global_batch * tile * tile * tuples
+  finite = all(bool(torch.isfinite(l).all()) for l in losses)
+  result = {"workload": name, "arch": arch_name, "global_batch": global_batch, "tile": tile, "input_channels": arch.number_of_input_channels,
+            "precision": precision, "scaling": "strong", "tiles_per_rank": per_rank, "micro_batch": micro,
+            "tuple_passes": tuples, "ms_per_step": ms, "tiles_per_s": global_batch / ms * 1e3,
+            "megapixels_per_s": global_batch * tile * tile / 1e6 / ms * 1e3, "tflops": flops / ms / 1e9,
+            "allreduce_ms": ar, "collective": ("ncclAllReduce via dd_comm_allreduce_sum_f32, one flat fp32 bucket of %d floats, %d ranks"
+                                               % (trainer.count, world)) if world > 1 else "none (1 rank)",
+            "gpu_launches_per_step": int(launches), "steps": steps, "warmup": warmup,
+            "loss_first_last": [float(losses[0].item()), float(losses[-1].item())], "loss_finite": finite,
+            "max_memory_gb": torch.cuda.max_memory_allocated() / 1e9}
+  if comm is not None:
+    comm.close()
+  del trainer, arch, feats, targets
+  torch.cuda.empty_cache()
+  return result
 
 
 def run_cuda(args, arch_json, weights, config):
@@ -273,33 +428,62 @@ def run_cuda(args, arch_json, weights, config):
   if rank == 0:
     pk = peaks()
     flops, conv_ms, conv_launches, core_tflops = conv_roofline(arch, feats_dev, 2)
+    traffic = measured_traffic()
     achieved = flops / (conv_ms / 1e3) / 1e12
     tuples = len(arch.feature_prediction_tuples)
-    cfg = dict(config)
-    cfg.update({"tuple_passes_per_frame": tuples, "mp_per_s_per_tuple_pass": value / world * tuples,
-                "l2": "per-step working set (activations of 17 x 1080p passes, >10 GB) is far larger than the 126 MB L2",
-                "frame_flops": flops, "conv_share_of_step": conv_ms / ms_per_step})
+    mac = arch.spec.mac_per_pixel(arch.features_per_tuple)
+    detail = {"tuple_passes_per_frame": tuples, "mp_per_s_per_tuple_pass": value / world * tuples,
+              "conv_flops_per_frame": flops, "all_flops_per_frame": 2.0 * mac * HEIGHT * WIDTH * tuples,
+              "all_flops_note": "backbone + 1x1 post-process + compose net (SURVEY Appendix B); conv_flops = conv_rows_kernel launches only",
+              "whole_step_tflops": 2.0 * mac * HEIGHT * WIDTH * tuples / ms_per_step / 1e9,
+              "conv_share_of_step": conv_ms / ms_per_step}
     line = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic", "config": cfg,
+            "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic", "config": dict(config), "detail": detail,
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "conv_rows_kernel (tcgen05 implicit-GEMM conv, all conv launches of the frame)",
                          "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                         "traffic": 4.239e9, "traffic_launch": "ncu --set full, one 3x3 64->64 @8x1080x1920 launch: dram read 2.161 GB + write 2.078 GB vs 4.247 GB algorithmic (profiles/r01_ncu_conv_rows_full.csv)",
+                         "traffic": (traffic or {}).get("bytes"), "traffic_launch": (traffic or {}).get("launch"),
                          "launches_per_step": conv_launches, "ms_per_step_in_kernel": conv_ms, "peak_source": pk["source"],
                          "unet_3x3_stack": {"achieved": core_tflops, "frac": core_tflops / pk["tflops"],
                                             "note": "the 3x3 layers of the U-Net backbone only (96 % of the frame's conv FLOPs); "
                                                     "`achieved` above also counts the 2x2 transposed convs"}},
             "clocks": sampler.summary()}
+    line["roofline_hbm"] = hbm_rooflines(arch, pk)
     if world == 1 and not args.no_cpu_baseline:
-      line["l1_vs_oracle"] = l1_against_oracle(arch_json, weights, local)
       threads = os.cpu_count() or 1
+      # 'L1 vs TF ref' on the benchmarked shape: the FULL 1080p frame, all 17 tuple passes, against the restated reference
+      want, oracle_s = oracle_full_frame(arch_json, weights, feats, threads)
+      l1 = l1_of(arch.predict(feats_dev)[0], want)
+      l1.update({"frame": "1x%dx%d (full frame, every output pass)" % (HEIGHT, WIDTH), "mode": "float16 storage, fp32 accumulate",
+                 "reference": "oracle/reference_model.py on torch-CPU float32 (%.0f s on %d threads)" % (oracle_s, threads)})
+      line["l1_vs_oracle"] = l1
+      del want
       v, dt, tpf = cpu_reference(arch_json, weights, threads, args.ref_tiles)
       line["cpu_baseline"] = {"value": v, "unit": "MP/s", "cores": threads, "kind": "port",
                               "sample": "%d tiles of 128x128 x 17 passes (%.2f s/tile), scaled to %d tiles/frame; restated "
                                         "reference on torch-CPU float32 (TensorFlow 1.x not installable)" %
                                         (args.ref_tiles, dt, tpf)}
+  # ---- training legs (every rank takes part; strong scaling of a fixed global batch)
+  train = None
+  if not args.no_train:
+    arch.network.release_buffers()
+    del pipeline, feats_dev, out
+    torch.cuda.empty_cache()
+    train = {}
+    for key, kw in (("cfg5", dict(name="configs[4]: Training.py batch=128 of 256x256x32-ch tiles, U-Net [64,96,128]x4 KPCN K=5, bf16, SMAPE loss",
+                                  arch_name="unet32", global_batch=128, tile=256, micro_batch=8, precision="bfloat16", steps=2, warmup=1)),
+                    ("cfg3", dict(name="configs[2]: Tiramisu [64,96,128]x4 + KernelPrediction 21x21, bf16 training on 256x256x32-ch tiles (global batch 16)",
+                                  arch_name="tiramisu32", global_batch=16, tile=256, micro_batch=1, precision="bfloat16", steps=1, warmup=1))):
+      try:
+        train[key] = training_leg(rank=rank, world=world, local=local, dist=dist, **kw)
+      except Exception as e:  # noqa: BLE001 - the headline line must still be printed
+        train[key] = {"error": "%s: %s" % (type(e).__name__, e)}
+        torch.cuda.empty_cache()
+  if rank == 0:
+    if train is not None:
+      line["train"] = train
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
   if dist is not None:
@@ -313,8 +497,9 @@ def main():
   ap.add_argument("--steps", type=int, default=10)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-  ap.add_argument("--ref-tiles", type=int, default=4, help="tiles timed per CPU-baseline sample")
-  ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--ref-tiles", type=int, default=16, help="tiles timed per CPU-baseline sample (BASELINE.md section 5: >= 16)")
+  ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (full-frame oracle L1 + cpu_baseline)")
+  ap.add_argument("--no-train", action="store_true", help="skip the training legs (`train` key)")
   ap.add_argument("--arch", default="unet32", choices=["unet32", "tiramisu32"],
                   help="unet32 = the headline configuration (configs[1]); tiramisu32 = the Tiramisu + 21x21 kernel-prediction "
                        "network of configs[2], inference only (an extra measurement, not the headline)")

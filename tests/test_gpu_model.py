@@ -55,12 +55,20 @@ def test_predict_float32_matches_oracle_1e4(name):
   assert mx <= 1e-4
 
 
+# fp16 storage / fp32 accumulate against the float64 oracle.  Bounds = 2x what was measured on B200 in round 2 (max, mean of
+# |out - oracle| / max(1, |oracle|max)): example 4.2e-5 / 4.0e-6, combined_onehot 2.2e-3 / 7.4e-5, tiramisu 3.7e-3 / 7.3e-5,
+# variants 2.4e-3 / 2.6e-5, rgb9 1.2e-5 / 7.9e-7.  (The small random-weight nets amplify a logit perturbation far more than
+# the benchmark network does: 3.1e-4 / 1.6e-6 on the full 1080p frame, tests/test_gpu_bench_shapes.py and bench.py.)
+FP16_BOUNDS = {"example": (1e-4, 1e-5), "combined_onehot": (5e-3, 1.5e-4), "tiramisu": (8e-3, 1.5e-4),
+               "variants": (5e-3, 6e-5), "rgb9": (3e-5, 2e-6)}
+
+
 @pytest.mark.parametrize("name", ["example", "combined_onehot", "tiramisu", "variants", "rgb9"])
 def test_predict_float16_tensor_core_path(name):
   arch, out, oracle = run_case(name, "float16")
   mx, mean = errors(out, oracle)
   print(name, "fp16 max %.2e mean %.2e" % (mx, mean))
-  assert mx <= 5e-2 and mean <= 5e-3
+  assert mx <= FP16_BOUNDS[name][0] and mean <= FP16_BOUNDS[name][1]
 
 
 @pytest.mark.parametrize("name", cases.GOLDEN_CASES)
@@ -118,7 +126,7 @@ def test_larger_image_and_batch_float16():
   oracle = reference_model.Architecture(j, ops=np_ops, dtype=np.float64, weights=weights).predict_numpy(features)
   mx, mean = errors(out, oracle)
   print("unet32 36x264 fp16 max %.2e mean %.2e" % (mx, mean))
-  assert mx <= 5e-2 and mean <= 5e-3
+  assert mx <= 3e-4 and mean <= 6e-6          # measured 1.24e-4 / 2.6e-6
 
 
 @pytest.mark.parametrize("name", ["example", "combined_onehot"])

@@ -209,14 +209,17 @@ def test_fp16_overflow_skips_the_step_on_the_device():
 
 # ------------------------------------------------------------------------------------------------ tensor-core (fp16) training
 # fp16 activations / activation gradients with fp32 accumulation, master weights and image-level arithmetic, compared with
-# the float64 oracle.  Tolerances: predictions 5e-2 max (same bound as the fp16 inference tests), loss 1e-2 relative.
+# the float64 oracle.  Tolerances (1.5x - 2x what round 2 measured on B200): predictions 7e-4 max (measured 3.1e-4), loss
+# 1e-4 relative (measured 2e-6).
 # Gradients: the individual backward kernels are pinned to 2e-3 in tests/test_gpu_train_tc.py; end to end the fp16 forward
 # perturbs ReLU masks / max-pool argmaxes / softmax weights, which moves single gradient entries by up to ~15 % of a tensor's
 # largest entry while the gradient as a whole stays aligned (measured: cosine 0.9996 on this net, independent of the loss
-# scale, i.e. no under/overflow) - so with the smooth SQUARED loss the test asks for <= 0.25 per tensor AND cosine >= 0.995.
+# scale, i.e. no under/overflow; worst tensor 0.155 COMBINED / 0.078 SINGLE / 0.109 Tiramisu) - so with the smooth SQUARED
+# loss the test asks for <= 0.24 per tensor (1.5x measured) AND cosine >= 0.999.
 # SMAPE is not smooth where the target is 0 (d/dp |p-t|/(|p|+|t|+0.01) at
 # t = 0 is 0.01 sign(p)/(|p|+0.01)^2: a 1e-3 perturbation of a near-zero prediction flips a gradient of magnitude ~100), and
-# the synthetic passes hold ~20 % exact zeros, so there the test asks for the DIRECTION: cosine similarity >= 0.98 overall.
+# the synthetic passes hold ~20 % exact zeros, so there the test asks for the DIRECTION: cosine similarity >= 0.999 overall
+# (measured 0.9998).
 @pytest.mark.parametrize("tuple_type,invert_after,kind", [("SINGLE", True, "SQUARED"), ("COMBINED", False, "SQUARED"),
                                                           ("SINGLE", True, "SMAPE")])
 def test_tensor_core_training_gradients_match_autograd(tuple_type, invert_after, kind):
@@ -233,20 +236,20 @@ def test_tensor_core_training_gradients_match_autograd(tuple_type, invert_after,
     for k_, v in want_preds[s].items():
       v = v.detach().numpy()
       worst_pred = max(worst_pred, float(np.abs(got_preds[s][k_].cpu().numpy() - v).max()) / max(1.0, float(np.abs(v).max())))
-  assert worst_pred <= 5e-2, worst_pred
-  assert abs(loss - want_loss) <= 1e-2 * max(1.0, abs(want_loss)), (loss, want_loss)
+  assert worst_pred <= 7e-4, worst_pred
+  assert abs(loss - want_loss) <= 1e-4 * max(1.0, abs(want_loss)), (loss, want_loss)
   got = trainer.gradients()
   a = np.concatenate([got[k].reshape(-1).astype(np.float64) for k in want_grads])
   b = np.concatenate([want_grads[k].reshape(-1) for k in want_grads])
   cosine = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
   if kind == "SQUARED":
-    worst = check_gradients(trainer, want_grads, rtol=0.25)
-    assert cosine >= 0.995, cosine
+    worst = check_gradients(trainer, want_grads, rtol=0.24)
+    assert cosine >= 0.999, cosine
   else:
     worst = max(float(np.abs(got[k] - g).max()) / max(1e-6, float(np.abs(g).max())) for k, g in want_grads.items())
   print("fp16 %s %s: loss %.5f (oracle %.5f), predictions %.2e, worst relative gradient error %.2e, cosine %.5f" %
         (tuple_type, kind, loss, want_loss, worst_pred, worst, cosine))
-  assert cosine >= 0.98, cosine
+  assert cosine >= 0.999, cosine
 
 
 def test_tensor_core_training_reduces_the_loss_like_the_exact_path():
@@ -309,9 +312,9 @@ def test_tensor_core_training_tiramisu_backbone():
   a = np.concatenate([got[k].reshape(-1).astype(np.float64) for k in want_grads])
   b = np.concatenate([want_grads[k].reshape(-1) for k in want_grads])
   cosine = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
-  worst = check_gradients(trainer, want_grads, rtol=0.25)
+  worst = check_gradients(trainer, want_grads, rtol=0.17)         # measured 0.109
   print("fp16 Tiramisu: loss %.5f (oracle %.5f), worst relative gradient error %.2e, cosine %.5f" % (loss, want_loss, worst, cosine))
-  assert cosine >= 0.995, cosine
+  assert cosine >= 0.999, cosine                                 # measured 0.99981
   # the transposed-convolution kernels in particular (the space-to-depth formulation)
   for name, g in want_grads.items():
     if "conv2d_transpose" in name and name.endswith("kernel"):
@@ -378,8 +381,8 @@ def test_unbuilt_loss_terms_fail_loudly():
 
 def test_bfloat16_training_and_inference():
   """bfloat16 storage (BASELINE.json names bf16 training): the same tensor-core kernels with bf16 operands, no loss scale
-  needed (fp32 exponent range).  8 mantissa bits: predictions within 5e-2 of the output scale, gradient direction cosine
-  >= 0.97 against the float64 oracle, and the loss goes down like on the exact path."""
+  needed (fp32 exponent range).  8 mantissa bits: predictions within 1e-2 of the output scale (measured 4.6e-3), gradient
+  direction cosine >= 0.99 against the float64 oracle (measured 0.9966), and the loss goes down like on the exact path."""
   j = small_example(filters=(16, 24, 32), n_convs=2, k=3)
   host, weights, features, targets = make_problem(j, n=2, h=16, w=24)
   f = {k: torch.from_numpy(v) for k, v in features.items()}
@@ -396,7 +399,7 @@ def test_bfloat16_training_and_inference():
   b = np.concatenate([want_grads[k].reshape(-1) for k in want_grads])
   cosine = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
   print("bf16: loss %.5f (oracle %.5f), gradient cosine %.5f" % (loss, want_loss, cosine))
-  assert cosine >= 0.97, cosine
+  assert cosine >= 0.99, cosine
   # inference through Architecture.predict with bf16 storage
   jj = dict(j)
   jj["b200"] = {"dtype": "bfloat16"}
@@ -407,7 +410,7 @@ def test_bfloat16_training_and_inference():
       v = v.detach().numpy()
       worst = max(worst, float(np.abs(out[s][k_].float().cpu().numpy() - v).max()) / max(1.0, float(np.abs(v).max())))
   print("bf16 inference: max relative error %.2e" % worst)
-  assert worst <= 5e-2
+  assert worst <= 1e-2
   # a few SMAPE steps reduce the loss
   tr = Trainer(Architecture(j, weights=weights), TrainingSettings({"learning_rate": 1e-3}), precision="bfloat16")
   losses = [float(tr.train_step(f, t).item()) for _ in range(10)]
