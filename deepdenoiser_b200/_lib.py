@@ -68,7 +68,9 @@ SIGNATURES = {
     "dd_compose_head_fwd": (_i, [_vp, _T, _T, _vp, _vp, _i, _T, _vp]),
     "dd_compose_tail_fwd": (_i, [_vp, _T, _vp, _vp, _i, _T, _T, _P(dd_invert_params), _T, _vp]),
     "dd_compose_weights_bytes": (_sz, []),
-    "dd_compose_scales_fwd": (_i, [_vp, _T, _T, _vp, _P(dd_invert_params), _T, _vp]),
+    "dd_compose_params_floats": (_sz, []),
+    "dd_compose_pack_weights": (_i, [_P(_vp), _i, _vp]),
+    "dd_compose_scales_fwd": (_i, [_vp, _T, _T, _vp, _vp, _i, _P(dd_invert_params), _T, _vp]),
     "dd_invert_standardization": (_i, [_vp, _T, _P(dd_invert_params), _T, _vp]),
     "dd_relu_bwd": (_i, [_vp, _T, _T, _T, _vp]),
     "dd_relu_bwd_acc": (_i, [_vp, _T, _T, _T, _vp]),
@@ -272,9 +274,11 @@ class Context:
                                              ctypes.byref(inv) if inv is not None else None, ctypes.byref(out),
                                              self._stream()))
 
-  def compose_scales(self, small, large, packed_dev, inv, out):
-    """Fused compose_scales; `packed_dev` is the device blob built by pack_compose_weights()."""
-    self._check(self.lib.dd_compose_scales_fwd(self.handle, ctypes.byref(small), ctypes.byref(large), packed_dev.data_ptr(),
+  def compose_scales(self, small, large, packed, inv, out):
+    """Fused compose_scales; `packed` = (device weight blob, host float parameters, dtype code) of pack_compose_weights()."""
+    blob_dev, params_host, code = packed
+    self._check(self.lib.dd_compose_scales_fwd(self.handle, ctypes.byref(small), ctypes.byref(large), blob_dev.data_ptr(),
+                                               params_host.ctypes.data, code,
                                                ctypes.byref(inv) if inv is not None else None, ctypes.byref(out),
                                                self._stream()))
 
@@ -344,27 +348,24 @@ def pack_post_kp_weights(w1, b1, w2, b2, ksize, features):
   return blob
 
 
-def pack_compose_weights(head_w, head_b, conv_w, conv_b, tail_w, tail_b):
-  """Builds the host blob dd_compose_scales_fwd expects (layout: include/dd_b200.h): head_w [1,1,6,24] / [6,24],
-  head_b [24], conv_w 4 x TF kernels [3,3,24,24] (kh, kw, cin, cout), conv_b 4 x [24], tail_w [1,1,24,1] / [24], tail_b [1]."""
+def pack_compose_weights(head_w, head_b, conv_w, conv_b, tail_w, tail_b, dtype=DD_F16):
+  """Host data of dd_compose_scales_fwd: (weight blob [uint8], float parameters [292 float32], dtype code).  head_w [1,1,6,24] /
+  [6,24], head_b [24], conv_w 4 x TF kernels [3,3,24,24] (kh, kw, cin, cout), conv_b 4 x [24], tail_w [1,1,24,1] / [24],
+  tail_b [1]."""
   import numpy as np
+  lib = load_library()
   c = 24
-  blob = np.zeros(load_library().dd_compose_weights_bytes(), dtype=np.uint8)
-  halves = blob[:4 * 9 * c * 64].view(np.float16).reshape(4, 9, c, 32)
-  n = np.arange(c)
-  for i, w in enumerate(conv_w):
-    w = np.asarray(w, dtype=np.float32).reshape(9, c, c)          # [tap][cin][cout]
-    dense = np.zeros((9, c, 32), dtype=np.float16)                # [tap][cout][cin padded]
-    dense[:, :, :c] = np.transpose(w, (0, 2, 1)).astype(np.float16)
-    for j in range(4):                                            # 16-byte chunk j of row n goes to chunk j ^ ((n>>1)&3)
-      dst = j ^ ((n >> 1) & 3)
-      for nn in range(c):
-        halves[i, :, nn, dst[nn] * 8:(dst[nn] + 1) * 8] = dense[:, nn, j * 8:(j + 1) * 8]
-  fl = blob[4 * 9 * c * 64:].view(np.float32)
+  blob = np.zeros(lib.dd_compose_weights_bytes(), dtype=np.uint8)
+  kernels = [np.ascontiguousarray(np.asarray(w, dtype=np.float32).reshape(3, 3, c, c)) for w in conv_w]
+  ptrs = (ctypes.c_void_p * 4)(*[k.ctypes.data for k in kernels])
+  rc = lib.dd_compose_pack_weights(ptrs, int(dtype), blob.ctypes.data)
+  if rc != 0:
+    raise DDError("dd_compose_pack_weights failed: %s" % lib.dd_last_error().decode())
+  fl = np.zeros(lib.dd_compose_params_floats(), dtype=np.float32)
   fl[0:144] = np.asarray(head_w, dtype=np.float32).reshape(6, c).reshape(-1)
   fl[144:168] = np.asarray(head_b, dtype=np.float32).reshape(c)
   for i, b in enumerate(conv_b):
     fl[168 + i * c:168 + (i + 1) * c] = np.asarray(b, dtype=np.float32).reshape(c)
   fl[264:288] = np.asarray(tail_w, dtype=np.float32).reshape(c)
   fl[288] = float(np.asarray(tail_b, dtype=np.float32).reshape(-1)[0])
-  return blob
+  return blob, fl, int(dtype)

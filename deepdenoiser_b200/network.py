@@ -256,8 +256,8 @@ class DeviceNetwork:
   def __init__(self, ctx, spec, weights, dtype=torch.float16, logits_dtype=torch.float32):
     assert dtype in (torch.float16, torch.bfloat16, torch.float32)
     self.ctx, self.spec, self.dtype = ctx, spec, dtype
-    # bfloat16 storage runs the same tensor-core kernels (kind::f16 with bf16 operands); the fused compose / output-head
-    # kernels are fp16 mma.sync code, so bf16 uses the layer-by-layer launches there
+    # bfloat16 storage runs the same tensor-core kernels (kind::f16 with bf16 operands), the fused compose kernel included;
+    # the fused output-head kernel is fp16 mma.sync code, so bf16 uses the layer-by-layer launches there
     self.logits_dtype = logits_dtype if dtype == torch.float16 else torch.float32
     self.fused_compose = True   # tests flip this to compare against the layer-by-layer path
     self.fused_post_kp = True   # likewise: 1x1 post-processing + kernel-prediction apply in one kernel
@@ -290,13 +290,13 @@ class DeviceNetwork:
       self.bias[var.name] = bias.to(dev)
     self.post_kp_packed = {}    # (scale index in spec.post, K, features) -> device blob, built on first use
     self.compose_packed = None
-    if self.spec.compose and self.dtype == torch.float16:
+    if self.spec.compose and self.dtype in (torch.float16, torch.bfloat16):
       head, c1, c2, c3, c4, tail = self.spec.compose
-      blob = _lib.pack_compose_weights(self.host[head.name][0], self.host[head.name][1],
-                                       [self.host[c.name][0] for c in (c1, c2, c3, c4)],
-                                       [self.host[c.name][1] for c in (c1, c2, c3, c4)],
-                                       self.host[tail.name][0], self.host[tail.name][1])
-      self.compose_packed = torch.from_numpy(blob).to(dev)
+      blob, floats, code = _lib.pack_compose_weights(
+          self.host[head.name][0], self.host[head.name][1], [self.host[c.name][0] for c in (c1, c2, c3, c4)],
+          [self.host[c.name][1] for c in (c1, c2, c3, c4)], self.host[tail.name][0], self.host[tail.name][1],
+          dtype=_lib.DD_F16 if self.dtype == torch.float16 else _lib.DD_BF16)
+      self.compose_packed = (torch.from_numpy(blob).to(dev), floats, code)
 
   # conv2d_transpose 3x3 stride 2 'same' (Tiramisu.py:62-64) = 4 output phases, each a stride-1
   # convolution of the input with a subset of the taps: out[2y+py, 2x+px] = sum_{dy,dx in {0,-1}}
@@ -510,7 +510,7 @@ class DeviceNetwork:
     small [I,h/2,w/2,3], large [I,h,w,3] -> out [I,h,w,3]; `inv` fuses the inverse standardisation."""
     spec, ctx = self.spec, self.ctx
     if self.compose_packed is not None and self.fused_compose:
-      # tensor-core mode: the whole weight net + blend is one launch, intermediates never leave shared memory
+      # tensor-core mode: the whole weight net + blend is one tcgen05 launch, intermediates never leave shared memory / TMEM
       ctx.compose_scales(small.d, large.d, self.compose_packed, inv, out.d)
       return
     i, h, w = large.t.shape[0], large.t.shape[1], large.t.shape[2]

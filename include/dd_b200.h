@@ -174,17 +174,19 @@ typedef struct dd_invert_params {
 int dd_compose_tail_fwd(dd_ctx* ctx, const dd_tensor* t, const float* w, const float* b, int c_mid,
                         const dd_tensor* small, const dd_tensor* large, const dd_invert_params* inv,
                         const dd_tensor* out, void* stream);
-/* MultiScalePrediction.compose_scales (MultiScalePrediction.py:36-93) in one launch (tensor-core mode): head 1x1,
- * two residual blocks of 3x3 24->24 convolutions, tail 1x1 + sigmoid and the blend
+/* MultiScalePrediction.compose_scales (MultiScalePrediction.py:36-93) in one launch: head 1x1, two residual blocks of 3x3
+ * 24->24 convolutions on tcgen05 (row-streaming, layer-pipelined; csrc/compose_rows.cuh), tail 1x1 + sigmoid and the blend
  * out = large - w*up2(down2(large)) + w*up2(small), optionally followed by the inverse standardisation.
- * Intermediates stay in shared memory (fp16 between layers, fp32 accumulate; head / tail / blend in fp32).
- * packed_dev: DEVICE blob of dd_compose_weights_bytes() bytes, 16-byte aligned:
- *   4 x [tap = kh*3+kw][cout = 24][cin = 32] fp16, rows of 64 bytes whose 16-byte chunk j is stored at j ^ ((cout>>1)&3),
- *   cin 24..31 zero (TF kernels [3,3,24,24] of the four convolutions in graph order), then fp32:
- *   head_w[6][24], head_b[24], conv_b[4][24], tail_w[24], tail_b[1], 3 floats of padding. */
+ * Intermediates stay in shared memory / TMEM (16-bit between layers, fp32 accumulate; head / tail / blend in fp32).
+ * packed_dev:  DEVICE blob of dd_compose_weights_bytes() bytes, 16-byte aligned, built by dd_compose_pack_weights (host) from
+ *              the TF kernels [3,3,24,24] of the four convolutions in graph order; dtype DD_F16 / DD_BF16 = operand type.
+ * params_host: HOST fp32 [dd_compose_params_floats()] = head_w[6][24], head_b[24], conv_b[4][24], tail_w[24], tail_b[1], pad
+ *              (copied into the launch parameters). */
 size_t dd_compose_weights_bytes(void);
+size_t dd_compose_params_floats(void);
+int dd_compose_pack_weights(const float* const* conv_w, int dtype, void* blob_host);
 int dd_compose_scales_fwd(dd_ctx* ctx, const dd_tensor* small, const dd_tensor* large, const void* packed_dev,
-                          const dd_invert_params* inv, const dd_tensor* out, void* stream);
+                          const float* params_host, int dtype, const dd_invert_params* inv, const dd_tensor* out, void* stream);
 /* FeatureStandardization.invert_standardization on an fp32 image (Architecture.py:48-55). */
 int dd_invert_standardization(dd_ctx* ctx, const dd_tensor* x, const dd_invert_params* inv, const dd_tensor* y,
                               void* stream);

@@ -12,10 +12,11 @@ from deepdenoiser_b200 import _lib  # noqa: E402
 ctx = _lib.Context(0)
 dev = ctx.device
 rng = np.random.default_rng(0)
-blob = torch.from_numpy(_lib.pack_compose_weights(
+_blob, _floats, _code = _lib.pack_compose_weights(
     rng.standard_normal((6, 24)).astype(np.float32) * 0.3, np.zeros(24, np.float32),
     [rng.standard_normal((3, 3, 24, 24)).astype(np.float32) * 0.08 for _ in range(4)], [np.zeros(24, np.float32)] * 4,
-    rng.standard_normal(24).astype(np.float32) * 0.3, np.zeros(1, np.float32))).to(dev)
+    rng.standard_normal(24).astype(np.float32) * 0.3, np.zeros(1, np.float32))
+blob = (torch.from_numpy(_blob).to(dev), _floats, _code)
 out = []
 for (n, h, w) in [(8, 1080, 1920), (8, 540, 960), (1, 1080, 1920)]:
   small = torch.randn(n, h // 2, w // 2, 3, device=dev)

@@ -29,6 +29,7 @@ __device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo_
 }
 
 struct Params {
+  int swap;          // descriptor field order under test (one per process: a wrong order may fault)
   const __half* a;   // [2 chunks][kRowsA][8]
   const __half* b;   // [2 chunks][kRowsB][8]
   float* out;        // [cases][128][96]
@@ -55,7 +56,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
   const uint32_t idesc = make_idesc_f16(128, 96);
   uint32_t phase = 0;
   int c = 0;
-  for (int swap = 0; swap < 2; ++swap) {
+  {
+    const int swap = p.swap;
     for (int kind = 0; kind < 4; ++kind, ++c) {
       // kind 0..2: A view shifted by `kind` rows, chunk stride = plane size; kind 3: second chunk -> zero region
       if (tid == 0) {
@@ -82,7 +84,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(Params p) {
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 128); }
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const int swap_arg = argc > 1 ? atoi(argv[1]) : 0;
   std::vector<__half> a(2 * kRowsA * 8), b(2 * kRowsB * 8);
   std::vector<float> af(a.size()), bf(b.size());
   srand(7);
@@ -93,15 +96,16 @@ int main() {
   cudaMalloc(&da, a.size() * 2); cudaMalloc(&db, b.size() * 2); cudaMalloc(&dout, 8 * 128 * 96 * 4);
   cudaMemcpy(da, a.data(), a.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(db, b.data(), b.size() * 2, cudaMemcpyHostToDevice);
-  p.a = da; p.b = db; p.out = dout;
-  cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
-  probe_kernel<<<1, 128, 32768>>>(p);
+  p.a = da; p.b = db; p.out = dout; p.swap = swap_arg;
+  // 200 KB: whatever the field order means, every address a descriptor can form stays inside the allocation
+  cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  probe_kernel<<<1, 128, 200 * 1024>>>(p);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
   std::vector<float> out(8 * 128 * 96);
   cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost);
   int c = 0;
-  for (int swap = 0; swap < 2; ++swap)
+  for (int swap = swap_arg; swap <= swap_arg; ++swap)
     for (int kind = 0; kind < 4; ++kind, ++c) {
       double worst = 0;
       for (int m = 0; m < 128; ++m)
