@@ -50,15 +50,20 @@ int dd_compose_scales_fwd(dd_ctx* ctx, const dd_tensor* small, const dd_tensor* 
   p.strips = (p.W + kCrValid - 1) / kCrValid;
   p.total_rows = static_cast<long long>(p.N) * p.strips * p.H;
   p.bf16 = (dtype == DD_BF16);
-  p.desc_swap = ctx->compose_desc_swap;
   if (inv) { p.has_inv = 1; p.inv = *inv; p.sqrt_var = sqrtf(inv->variance); }
   memcpy(p.fl, params_host, sizeof(float) * kCrFloats);
+  p.trace = ctx->conv_trace;
   long long grid = ctx->sm_count;
   if (p.total_rows < grid) grid = p.total_rows;
   p.rows_per_cta = static_cast<int>((p.total_rows + grid - 1) / grid);
   grid = (p.total_rows + p.rows_per_cta - 1) / p.rows_per_cta;
-  DD_CUDA(cudaFuncSetAttribute(compose_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCrSmem));
-  compose_rows_kernel<<<static_cast<unsigned>(grid), kCrThreads, kCrSmem, static_cast<cudaStream_t>(stream)>>>(p);
+  if (p.bf16) {
+    DD_CUDA(cudaFuncSetAttribute(compose_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCrSmem));
+    compose_rows_kernel<true><<<static_cast<unsigned>(grid), kCrThreads, kCrSmem, static_cast<cudaStream_t>(stream)>>>(p);
+  } else {
+    DD_CUDA(cudaFuncSetAttribute(compose_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCrSmem));
+    compose_rows_kernel<false><<<static_cast<unsigned>(grid), kCrThreads, kCrSmem, static_cast<cudaStream_t>(stream)>>>(p);
+  }
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }

@@ -7,8 +7,8 @@
 //   w = sigmoid(relu(conv1x1_{24->1}(x2)));      out = large - w * up2(down2(large)) + w * s_up    tail + blend (fp32)
 //
 // Mapping onto the hardware
-//   unit of work   one image ROW of a 128-pixel column strip, streamed top to bottom through all four 3x3 layers:
-//                  while layer 1 consumes x0 row t, layer 2 consumes its input row t-2, layer 3 row t-4, layer 4 row t-6.
+//   unit of work   one image ROW of a 128-pixel column strip, streamed top to bottom through all four 3x3 layers: every
+//                  layer free-runs on its own barriers, trailing its producer by the two rows a 3x3 window needs.
 //                  A strip yields 122 finished pixels per row (each 3x3 layer eats one pixel on both sides: 130 -> 122).
 //   UMMA           M = 128 pixels, K = 16, N = 96: like conv_rows.cuh the three vertical taps are STACKED along N, so the
 //                  input row t of a layer updates the accumulators of its output rows t+1, t, t-1 in one instruction
@@ -21,7 +21,7 @@
 //                  3 - g % 4.  A drained block is re-zeroed with tcgen05.st, so every UMMA accumulates (no first-touch split).
 //   warps          0-3 / 4-7 / 8-11 / 12-15: epilogue of layer 1 / 2 / 3 / 4 (one TMEM lane = one pixel per thread):
 //                  + bias, residual, ReLU, fp16 -> next layer's operand row in shared memory; layer 4 adds the tail + blend
-//                  16-19: head (x0 rows from the fp32 inputs)      20: TMEM allocator + the single UMMA-issuing thread
+//                  16-20: head (x0 rows from the fp32 inputs)      21-24: one UMMA-issuing thread per layer (21 also allocates TMEM)
 //   grid           persistent: the N * strips * H output rows are split into gridDim contiguous ranges; a range adds 4 halo
 //                  rows above and below (recomputed, not exchanged), clipped at the image border where SAME padding applies.
 #pragma once
@@ -40,9 +40,8 @@ constexpr int kCrWChunk = 96 * 16;            // one 8-channel chunk of a weight
 constexpr int kCrWTile = 3 * kCrWChunk;       // 4608 B per (layer, horizontal tap s)
 constexpr int kCrWBytes = 12 * kCrWTile;      // 55296 B
 constexpr int kCrX0Slots = 6, kCrMidSlots = 4, kCrResSlots = 6;
-constexpr int kCrSkew = 2;                    // rows by which each layer trails the previous one
-constexpr int kCrWarps = 21, kCrThreads = kCrWarps * 32;
-constexpr int kCrWarpHead = 16, kCrWarpMma = 20;
+constexpr int kCrWarps = 25, kCrThreads = kCrWarps * 32;
+constexpr int kCrWarpHead = 16, kCrWarpMma = 21;            // head: 5 warps = 130 pixels of a row slot (+ idle lanes); 4 issuing warps
 // shared memory carve-up (bytes from the 1024-aligned base)
 constexpr int kCrOffW = 0;
 constexpr int kCrOffX0 = kCrOffW + kCrWBytes + kCrWChunk;            // + finite pad behind the last weight tile
@@ -63,21 +62,17 @@ struct ComposeRowsParams {
   int N, H, W, strips;
   long long total_rows;
   int rows_per_cta;
-  int bf16, desc_swap;
+  int bf16;
   int has_inv;
   dd_invert_params inv;
   float sqrt_var;
+  unsigned long long* trace;       // debug: [9 roles][64 rows][8] clock64 stamps of CTA 0 (NULL = off)
   float fl[kCrFloats];
 };
 
-__device__ __forceinline__ uint64_t cr_desc(uint32_t saddr, uint32_t lbo_bytes, int swap) {
-  // K-major, no swizzle: LBO = byte distance between the two 16-byte K chunks of a K=16 step, SBO = distance between 8-row groups
-  const uint32_t lbo = lbo_bytes >> 4, sbo = 128u >> 4;
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>((swap ? sbo : lbo) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>((swap ? lbo : sbo) & 0x3FFF) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
+__device__ __forceinline__ uint64_t cr_desc_from(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
 __device__ __forceinline__ void tmem_zero_32x32(uint32_t taddr) {
@@ -119,6 +114,7 @@ struct CrWalker {
 
 __device__ __forceinline__ float cr_signed_expm1(float v) { return copysignf(expm1f(fabsf(v)), v) * (v != 0.f); }
 
+template <bool BF16>
 __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __grid_constant__ ComposeRowsParams p) {
   extern __shared__ __align__(1024) uint8_t cr_raw[];
   const uint32_t base_u32 = (smem_u32(cr_raw) + 1023u) & ~1023u;
@@ -142,7 +138,7 @@ __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __gri
   for (int i = threadIdx.x + kCrWBytes / 16; i < kCrOffBars / 16; i += kCrThreads)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kCrX0Slots; ++i) { mbar_init(&x0_full[i], 4); mbar_init(&x0_empty[i], 5); }
+    for (int i = 0; i < kCrX0Slots; ++i) { mbar_init(&x0_full[i], 5); mbar_init(&x0_empty[i], 5); }
     for (int i = 0; i < 3 * kCrMidSlots; ++i) { mbar_init(&mid_full[i], 4); mbar_init(&mid_empty[i], 1); }
     for (int i = 0; i < kCrResSlots; ++i) { mbar_init(&rx1_full[i], 4); mbar_init(&rx1_empty[i], 4); }
     for (int i = 0; i < 16; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
@@ -160,120 +156,144 @@ __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __gri
   const int W = p.W;
 
   if (warp >= kCrWarpHead && warp < kCrWarpMma) {
-    // ------------------------------------------------------------------ head: x0 rows
-    const int ht = threadIdx.x - kCrWarpHead * 32;
+    // ------------------------------------------------------------------ head: x0 rows (one slot pixel per thread; the
+    // six inputs of the NEXT row are in flight while this row is computed)
+    const int q = threadIdx.x - kCrWarpHead * 32;
     uint8_t* ring = smem + kCrOffX0;
     CrWalker walk(p);
     CrSeg sg;
-    uint32_t g = 0;
+    uint32_t slot = 0, phase = 0, gh = 0;
+    unsigned long long* tr = (p.trace && blockIdx.x == 0 && q == 0) ? p.trace + 4 * 64 * 8 : nullptr;
     while (walk.next(sg)) {
-      for (int t = sg.lo; t < sg.hi; ++t, ++g) {
-        const uint32_t slot = g % kCrX0Slots, use = g / kCrX0Slots;
-        mbar_wait(&x0_empty[slot], (use & 1u) ^ 1u);
-        uint8_t* row = ring + slot * kCrSlot;
-        for (int q = ht; q < kCrRowPx; q += 128) {
-          const int x = sg.xs + q;
-          uint4 o[3] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-          if (x >= 0 && x < W) {
-            const float* lp = p.large + ((static_cast<size_t>(sg.n) * p.H + t) * W + x) * p.large_cs + p.large_co;
-            const float* sp = p.small + ((static_cast<size_t>(sg.n) * (p.H >> 1) + (t >> 1)) * (W >> 1) + (x >> 1)) * p.small_cs + p.small_co;
-            float in[6];
-            in[0] = __ldg(sp); in[1] = __ldg(sp + 1); in[2] = __ldg(sp + 2);
-            in[3] = __ldg(lp); in[4] = __ldg(lp + 1); in[5] = __ldg(lp + 2);
-            float a[kCrC];
+      const int x = sg.xs + q;
+      const bool live = q < kCrRowPx && x >= 0 && x < W;
+      const float* lbase = p.large + (static_cast<size_t>(sg.n) * p.H * W + x) * p.large_cs + p.large_co;
+      const float* sbase = p.small + (static_cast<size_t>(sg.n) * (p.H >> 1) * (W >> 1) + (x >> 1)) * p.small_cs + p.small_co;
+      float nxt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      auto fetch = [&](int t) {
+        if (live) {
+          const float* lp = lbase + static_cast<size_t>(t) * W * p.large_cs;
+          const float* sp = sbase + static_cast<size_t>(t >> 1) * (W >> 1) * p.small_cs;
+          nxt[0] = __ldg(sp); nxt[1] = __ldg(sp + 1); nxt[2] = __ldg(sp + 2);
+          nxt[3] = __ldg(lp); nxt[4] = __ldg(lp + 1); nxt[5] = __ldg(lp + 2);
+        }
+      };
+      fetch(sg.lo);
+      for (int t = sg.lo; t < sg.hi; ++t, ++gh) {
+        const bool trace = tr && gh < 64;
+        if (trace) tr[gh * 8 + 0] = clock64();
+        float in[6];
 #pragma unroll
-            for (int c = 0; c < kCrC; ++c) {
-              float v = p.fl[144 + c];
+        for (int k = 0; k < 6; ++k) in[k] = nxt[k];
+        if (t + 1 < sg.hi) fetch(t + 1);
+        uint4 o[3] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (live) {
+          float a[kCrC];
 #pragma unroll
-              for (int k = 0; k < 6; ++k) v = fmaf(in[k], p.fl[k * kCrC + c], v);
-              a[c] = fmaxf(v, 0.f);
-            }
+          for (int c = 0; c < kCrC; ++c) {
+            float v = p.fl[144 + c];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              float f8[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f8[e] = a[j * 8 + e];
-              o[j] = pack8(f8, p.bf16);
-            }
+            for (int k = 0; k < 6; ++k) v = fmaf(in[k], p.fl[k * kCrC + c], v);
+            a[c] = fmaxf(v, 0.f);
           }
 #pragma unroll
-          for (int j = 0; j < 3; ++j) *reinterpret_cast<uint4*>(row + j * kCrPlane + q * 16) = o[j];
+          for (int j = 0; j < 3; ++j) {
+            float f8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f8[e] = a[j * 8 + e];
+            o[j] = pack8(f8, BF16);
+          }
+        }
+        if (trace) tr[gh * 8 + 1] = clock64();
+        mbar_wait_sleep(&x0_empty[slot], phase ^ 1u);
+        if (trace) tr[gh * 8 + 2] = clock64();
+        if (q < kCrRowPx) {
+          uint8_t* row = ring + slot * kCrSlot + q * 16;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) *reinterpret_cast<uint4*>(row + j * kCrPlane) = o[j];
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&x0_full[slot]);
+        if (trace) tr[gh * 8 + 3] = clock64();
+        if (++slot == kCrX0Slots) { slot = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == kCrWarpMma) {
-    // ------------------------------------------------------------------ UMMA issuer: four layers, skewed by kCrSkew rows
+  } else if (warp >= kCrWarpMma) {
+    // ------------------------------------------------------------------ UMMA issuers: warp kCrWarpMma + l drives layer l
+    // One thread issues the 6-12 UMMAs of a row, so everything per instruction is two integer adds: descriptors are
+    // (lo, hi) register pairs whose hi word (SBO = 128 B, version) never changes and whose lo word is a per-row base plus
+    // compile-time offsets; the one or two accumulator "pieces" of a row are worked out once per row.  The four layers
+    // are independent instruction streams (their own TMEM columns and operand rings) coupled by mbarriers only, so four
+    // threads issue them: a single thread's scalar work per row step was the bound of the first version.
     if (elect_one()) {
-      const uint32_t fmt = p.bf16 ? kIdescBf16 : 0u;
-      const uint32_t w_base = base_u32 + kCrOffW, zero_addr = base_u32 + kCrOffZero;
-      const uint32_t ring_base[4] = {base_u32 + kCrOffX0, base_u32 + kCrOffA1, base_u32 + kCrOffAx1, base_u32 + kCrOffA3};
-      // per-layer iterators over the same (segment, row) sequence
-      long long lin[4]; uint32_t g[4], g_lo[4], g_hi[4], untouched[4];
-      const long long lin0 = static_cast<long long>(blockIdx.x) * p.rows_per_cta;
-      long long lin_end = lin0 + p.rows_per_cta;
+      const int l = warp - kCrWarpMma;
+      const uint32_t idesc0 = make_idesc_f16(128, 0) | (BF16 ? kIdescBf16 : 0u);
+      constexpr uint32_t kHi = (128u >> 4) | (1u << 14);                      // SBO = 128 B, descriptor version 1, no swizzle
+      const uint32_t w_lo = (((base_u32 + kCrOffW) >> 4) | (static_cast<uint32_t>(kCrWChunk >> 4) << 16)) +
+                            static_cast<uint32_t>((l * 3 * kCrWTile) >> 4);
+      const uint32_t zero_q = (base_u32 + kCrOffZero) >> 4;                   // addresses in 16-byte units from here on
+      const uint32_t ring_q = (base_u32 + (l == 0 ? kCrOffX0 : (l == 1 ? kCrOffA1 : (l == 2 ? kCrOffAx1 : kCrOffA3)))) >> 4;
+      const uint32_t slots = (l == 0) ? kCrX0Slots : kCrMidSlots;
+      uint64_t* in_full0 = (l == 0) ? x0_full : mid_full + (l - 1) * kCrMidSlots;
+      uint64_t* in_empty0 = (l == 0) ? x0_empty : mid_empty + (l - 1) * kCrMidSlots;
+      uint64_t* accf = acc_full + l * 4;
+      uint64_t* acce = acc_empty + l * 4;
+      const uint32_t d_layer = tmem_base + static_cast<uint32_t>(l * 128);
+      long long lin = static_cast<long long>(blockIdx.x) * p.rows_per_cta;
+      long long lin_end = lin + p.rows_per_cta;
       if (lin_end > p.total_rows) lin_end = p.total_rows;
-      for (int l = 0; l < 4; ++l) { lin[l] = lin0; g[l] = 0; g_lo[l] = 0; g_hi[l] = 0; untouched[l] = 0; }
-      int done = 0;
-      for (uint32_t step = 0; done < 4; ++step) {
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          if (step < static_cast<uint32_t>(l * kCrSkew)) continue;
-          if (g[l] == g_hi[l]) {
-            // next segment of this layer (same arithmetic as CrWalker, only the row counts matter here)
-            if (lin[l] >= lin_end) { if (g[l] != 0xffffffffu) { g[l] = g_hi[l] = 0xffffffffu; ++done; } continue; }
-            const long long col = lin[l] / p.H;
-            const int y0 = static_cast<int>(lin[l] - col * p.H);
-            const long long left = lin_end - lin[l];
-            const int y1 = (y0 + left > p.H) ? p.H : static_cast<int>(y0 + left);
-            const int lo = y0 - 4 < 0 ? 0 : y0 - 4, hi = y1 + 4 > p.H ? p.H : y1 + 4;
-            lin[l] += y1 - y0;
-            g_lo[l] = g[l];
-            g_hi[l] = g[l] + static_cast<uint32_t>(hi - lo);
-          }
-          const uint32_t gg = g[l];
-          const uint32_t slots = (l == 0) ? kCrX0Slots : kCrMidSlots;
-          const uint32_t slot = gg % slots, use = gg / slots;
-          uint64_t* in_full = (l == 0) ? &x0_full[slot] : &mid_full[(l - 1) * kCrMidSlots + slot];
-          uint64_t* in_empty = (l == 0) ? &x0_empty[slot] : &mid_empty[(l - 1) * kCrMidSlots + slot];
-          mbar_wait(in_full, use & 1u);
-          // output rows this input row feeds: q = gg + 1 - r, clipped to the segment
-          const uint32_t q_hi = (gg + 1 < g_hi[l]) ? gg + 1 : g_hi[l] - 1;
-          const uint32_t q_lo = (gg > g_lo[l]) ? gg - 1 : g_lo[l];
-          while (untouched[l] <= q_hi) {
-            const uint32_t nu = untouched[l]++;
-            mbar_wait(&acc_empty[l * 4 + (3 - (nu & 3u))], (nu >> 2) & 1u);
+      uint32_t g = 0, untouched = 0, slot = 0, phase = 0;
+      unsigned long long* tr = (p.trace && blockIdx.x == 0) ? p.trace + (5 + l) * 64 * 8 : nullptr;
+      while (lin < lin_end) {
+        // next segment (same arithmetic as CrWalker; only the row count matters here)
+        const long long col = lin / p.H;
+        const int y0 = static_cast<int>(lin - col * p.H);
+        const long long left = lin_end - lin;
+        const int y1 = (y0 + left > p.H) ? p.H : static_cast<int>(y0 + left);
+        const int lo = y0 - 4 < 0 ? 0 : y0 - 4, hi = y1 + 4 > p.H ? p.H : y1 + 4;
+        lin += y1 - y0;
+        const uint32_t g_lo = g, g_hi = g + static_cast<uint32_t>(hi - lo);
+        for (; g < g_hi; ++g) {
+          const bool trace = tr && g < 64;
+          if (trace) tr[g * 8 + 0] = clock64();
+          mbar_wait_sleep(&in_full0[slot], phase);
+          if (trace) tr[g * 8 + 1] = clock64();
+          // output rows this input row feeds: q = g + 1 - r, clipped to the segment
+          const uint32_t q_hi = (g + 1 < g_hi) ? g + 1 : g_hi - 1;
+          const uint32_t q_lo = (g > g_lo) ? g - 1 : g_lo;
+          while (untouched <= q_hi) {
+            mbar_wait_sleep(&acce[3 - (untouched & 3u)], (untouched >> 2) & 1u);
+            ++untouched;
           }
           tc_fence_after();
-          const int r_lo = static_cast<int>(gg + 1 - q_hi), r_hi = static_cast<int>(gg + 1 - q_lo);
-          const int b0 = 3 - static_cast<int>((gg + 1) & 3u);
-          const uint32_t slot_addr = ring_base[l] + slot * kCrSlot;
-          const uint32_t d_layer = tmem_base + static_cast<uint32_t>(l * 128);
+          if (trace) tr[g * 8 + 2] = clock64();
+          // the taps r_lo..r_hi land in blocks (b0 + r) & 3: one instruction, or two when the ring wraps
+          const uint32_t r_lo = g + 1 - q_hi, r_hi = g + 1 - q_lo;
+          const uint32_t blk_a = (3u - ((g + 1) & 3u) + r_lo) & 3u;
+          uint32_t cnt_a = r_hi - r_lo + 1;
+          if (blk_a + cnt_a > 4u) cnt_a = 4u - blk_a;
+          const uint32_t cnt_b = r_hi - r_lo + 1 - cnt_a;                      // second piece starts at block 0
+          const uint32_t d_a = d_layer + blk_a * 32u, i_a = idesc0 + ((cnt_a * 4u) << 17), b_a = r_lo * 32u;
+          const uint32_t i_b = idesc0 + ((cnt_b * 4u) << 17), b_b = (r_lo + cnt_a) * 32u;
+          const uint32_t slot_q = ring_q + slot * (kCrSlot >> 4);
+          const uint32_t a_k0 = slot_q | (static_cast<uint32_t>(kCrPlane >> 4) << 16);
+          const uint32_t a_k1 = (slot_q + 2u * (kCrPlane >> 4)) | ((zero_q - slot_q - 2u * (kCrPlane >> 4)) << 16);
 #pragma unroll
           for (int s = 0; s < 3; ++s) {
-            const uint32_t w_tile = w_base + static_cast<uint32_t>((l * 3 + s) * kCrWTile);
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              const uint32_t a_addr = slot_addr + static_cast<uint32_t>(ks * 2 * kCrPlane + s * 16);
-              const uint32_t a_lbo = (ks == 0) ? static_cast<uint32_t>(kCrPlane) : zero_addr - (slot_addr + 2u * kCrPlane);
-              const uint64_t ad = cr_desc(a_addr, a_lbo, p.desc_swap);
-              int r = r_lo;
-              while (r <= r_hi) {
-                const int blk = (b0 + r) & 3;
-                int cnt = r_hi - r + 1;
-                if (blk + cnt > 4) cnt = 4 - blk;
-                const uint64_t bd = cr_desc(w_tile + static_cast<uint32_t>(ks * 2 * kCrWChunk + r * 32 * 16), kCrWChunk, p.desc_swap);
-                umma_f16(d_layer + static_cast<uint32_t>(blk * 32), ad, bd, make_idesc_f16(128, cnt * 32) | fmt, 1u);
-                r += cnt;
-              }
+              const uint32_t a_lo = (ks == 0 ? a_k0 : a_k1) + static_cast<uint32_t>(s);
+              const uint32_t b_lo = w_lo + static_cast<uint32_t>((s * kCrWTile + ks * 2 * kCrWChunk) >> 4);
+              umma_f16(d_a, cr_desc_from(a_lo, kHi), cr_desc_from(b_lo + b_a, kHi), i_a, 1u);
+              if (cnt_b) umma_f16(d_layer, cr_desc_from(a_lo, kHi), cr_desc_from(b_lo + b_b, kHi), i_b, 1u);
             }
           }
-          umma_commit(in_empty);
-          if (gg > g_lo[l]) umma_commit(&acc_full[l * 4 + (3 - ((gg - 1) & 3u))]);     // row gg-1 has all three taps
-          if (gg + 1 == g_hi[l]) umma_commit(&acc_full[l * 4 + (3 - (gg & 3u))]);     // last input row of the segment
-          g[l] = gg + 1;
+          umma_commit(&in_empty0[slot]);
+          if (g > g_lo) umma_commit(&accf[3 - ((g - 1) & 3u)]);      // row g-1 has all three taps
+          if (g + 1 == g_hi) umma_commit(&accf[3 - (g & 3u)]);      // last input row of the segment
+          if (trace) tr[g * 8 + 3] = clock64();
+          if (++slot == slots) { slot = 0; phase ^= 1u; }
         }
       }
     }
@@ -295,11 +315,14 @@ __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __gri
     CrWalker walk(p);
     CrSeg sg;
     uint32_t g = 0;
+    unsigned long long* tr = (p.trace && blockIdx.x == 0 && wq == 0 && lane == 0) ? p.trace + L * 64 * 8 : nullptr;
     while (walk.next(sg)) {
       const int x = sg.xs + m + 1;
       const bool inside = x >= 0 && x < W;
       for (int t = sg.lo; t < sg.hi; ++t, ++g) {
         const uint32_t blk = 3u - (g & 3u), use = g >> 2;
+        const bool trace = tr && g < 64;
+        if (trace) tr[g * 8 + 0] = clock64();
         // layer 4: fetch the blend operands before waiting for the accumulator
         const bool emit = (L == 3) && inside && t >= sg.y0 && t < sg.y1 && m >= 3 && m < 3 + kCrValid;
         float lg[3] = {0.f, 0.f, 0.f}, low[3] = {0.f, 0.f, 0.f}, sm[3] = {0.f, 0.f, 0.f};
@@ -316,8 +339,9 @@ __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __gri
             sm[c] = __ldg(sp + c);
           }
         }
-        mbar_wait(&acc_full[L * 4 + blk], use & 1u);
+        mbar_wait_sleep(&acc_full[L * 4 + blk], use & 1u);
         tc_fence_after();
+        if (trace) tr[g * 8 + 1] = clock64();
         uint32_t vr[32];
         tmem_ld_32x32(t_lane + blk * 32, vr);
         tmem_ld_wait();
@@ -326,6 +350,7 @@ __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __gri
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[L * 4 + blk]);
+        if (trace) tr[g * 8 + 2] = clock64();
         float v[kCrC];
 #pragma unroll
         for (int c = 0; c < kCrC; ++c) v[c] = __uint_as_float(vr[c]) + bias[c];
@@ -335,13 +360,13 @@ __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __gri
           const uint32_t rs = g % kCrResSlots, ru = g / kCrResSlots;     // kCrX0Slots == kCrResSlots
           uint64_t* rfull = (L == 1) ? &x0_full[rs] : &rx1_full[rs];
           uint64_t* rempty = (L == 1) ? &x0_empty[rs] : &rx1_empty[rs];
-          mbar_wait(rfull, ru & 1u);
+          mbar_wait_sleep(rfull, ru & 1u);
           const uint8_t* rrow = smem + (L == 1 ? kCrOffX0 : kCrOffRx1) + rs * kCrSlot + (m + 1) * 16;
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
             const uint4 rv = *reinterpret_cast<const uint4*>(rrow + j * kCrPlane);
             float f8[8];
-            unpack8(rv, p.bf16, f8);
+            unpack8(rv, BF16, f8);
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[j * 8 + e] += f8[e];
           }
@@ -352,12 +377,13 @@ __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __gri
         if (L < 3) {
           // operand row of the next layer: relu, zero outside the image (SAME padding of the next layer), 16-bit
           const uint32_t slot = g % kCrMidSlots, ou = g / kCrMidSlots;
-          mbar_wait(&out_empty[slot], (ou & 1u) ^ 1u);
+          mbar_wait_sleep(&out_empty[slot], (ou & 1u) ^ 1u);
+          if (trace) tr[g * 8 + 3] = clock64();
           uint8_t* orow = out_ring + slot * kCrSlot + (m + 1) * 16;
           uint8_t* rrow = nullptr;
           if (L == 1) {
             const uint32_t rs = g % kCrResSlots, ru = g / kCrResSlots;
-            mbar_wait(&rx1_empty[rs], (ru & 1u) ^ 1u);
+            mbar_wait_sleep(&rx1_empty[rs], (ru & 1u) ^ 1u);
             rrow = smem + kCrOffRx1 + rs * kCrSlot + (m + 1) * 16;
           }
 #pragma unroll
@@ -369,8 +395,8 @@ __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __gri
               r8[e] = raw;
               f8[e] = fmaxf(raw, 0.f);
             }
-            *reinterpret_cast<uint4*>(orow + j * kCrPlane) = pack8(f8, p.bf16);
-            if (L == 1) *reinterpret_cast<uint4*>(rrow + j * kCrPlane) = pack8(r8, p.bf16);
+            *reinterpret_cast<uint4*>(orow + j * kCrPlane) = pack8(f8, BF16);
+            if (L == 1) *reinterpret_cast<uint4*>(rrow + j * kCrPlane) = pack8(r8, BF16);
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -378,6 +404,7 @@ __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __gri
             mbar_arrive(&out_full[slot]);
             if (L == 1) mbar_arrive(&rx1_full[g % kCrResSlots]);
           }
+          if (trace) tr[g * 8 + 4] = clock64();
         } else if (emit) {
           // tail + blend (MultiScalePrediction.py:45-52,73-77)
           float s = p.fl[288];
