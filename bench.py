@@ -459,7 +459,26 @@ def run_cuda(args, arch_json, weights, config):
       l1.update({"frame": "1x%dx%d (full frame, every output pass)" % (HEIGHT, WIDTH), "mode": "float16 storage, fp32 accumulate",
                  "reference": "oracle/reference_model.py on torch-CPU float32 (%.0f s on %d threads)" % (oracle_s, threads)})
       line["l1_vs_oracle"] = l1
-      del want
+      # the high-accuracy TENSOR-CORE mode (float16x2: fp16 hi + lo pairs, three tcgen05 passes per layer): the mode that meets
+      # the reference's 1e-4 bound; same frame, same weights, timed the same way (fewer steps: it is not the headline)
+      arch.network.release_buffers()
+      torch.cuda.empty_cache()
+      jx = dict(arch_json)
+      jx["b200"] = {"dtype": "float16x2"}
+      arch_x2 = Architecture(jx, weights=weights, device=local)
+      out_x2 = arch_x2.predict(feats_dev)[0]
+      l1x = l1_of(out_x2, want)
+      for _ in range(2):
+        arch_x2.predict(feats_dev)
+      x2_steps = 3
+      x2_ms = timed_loop(lambda: arch_x2.predict(feats_dev), x2_steps) / x2_steps
+      l1x.pop("per_pass_mean_max")
+      line["high_accuracy_mode"] = {"dtype": "f16x2 (split fp16 pairs: x_hi.W_hi + x_lo.W_hi + x_hi.W_lo on tcgen05, fp32 accumulate)",
+                                    "ms_per_step": x2_ms, "value": mp / (x2_ms / 1e3), "unit": "MP/s", "steps": x2_steps,
+                                    "l1_vs_oracle": l1x, "meets_1e-4": bool(l1x["max"] <= 1e-4)}
+      arch_x2.network.release_buffers()
+      del arch_x2, out_x2, want
+      torch.cuda.empty_cache()
       v, dt, tpf = cpu_reference(arch_json, weights, threads, args.ref_tiles)
       line["cpu_baseline"] = {"value": v, "unit": "MP/s", "cores": threads, "kind": "port",
                               "sample": "%d tiles of 128x128 x 17 passes (%.2f s/tile), scaled to %d tiles/frame; restated "

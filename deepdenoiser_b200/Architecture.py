@@ -184,7 +184,10 @@ class Architecture:
                             core["number_of_convolutions_per_block"], self.number_of_input_channels,
                             self.number_of_output_channels, self.use_multiscale_predictions, embedding_shape)
     options = dict(parsed_json.get("b200", {}))
-    self.dtype = {"float16": torch.float16, "bfloat16": torch.bfloat16, "float32": torch.float32}[options.get("dtype", "float16")]
+    # "float16x2": split-fp16 tensor-core arithmetic (fp16 hi + lo pairs, 3 MMA passes): the mode that meets the 1e-4 parity
+    # bound of the fp32 reference on tensor cores
+    self.dtype = {"float16": torch.float16, "bfloat16": torch.bfloat16, "float32": torch.float32,
+                  "float16x2": "float16x2"}[options.get("dtype", "float16")]
     self.logits_dtype = {"float16": torch.float16, "float32": torch.float32}[options.get("logits_dtype", "float32")]
     self.max_chunk_pixels = int(options.get("max_chunk_pixels", 16 * 1024 * 1024))
     self.weights = dict(weights) if weights is not None else self.spec.init_weights(seed)
@@ -388,10 +391,15 @@ class Architecture:
     for t0 in range(0, len(tuples), per_chunk):
       t1 = min(len(tuples), t0 + per_chunk)
       bc = (t1 - t0) * n
-      x0 = net._buf("net.x0", (bc, h, w, c0p))
-      ctx.assemble_input(table[t0 * c0p * entry_bytes:], t1 - t0, n, _lib.desc(x0))
       # 3. core architecture + 1x1 post-processing, all tuples of the chunk batched along N
-      core = net.forward_core(V(x0, c0, 0))                 # coarsest first
+      if net.split:
+        x0 = net._buf("net.x0x2", (bc, h, w, 2 * c0p))
+        ctx.assemble_input_split(table[t0 * c0p * entry_bytes:], t1 - t0, n, _lib.desc(x0, c0p, 0), _lib.desc(x0, c0p, c0p))
+        core = net.forward_core(net._sv(x0, c0, 0))           # coarsest first
+      else:
+        x0 = net._buf("net.x0", (bc, h, w, c0p))
+        ctx.assemble_input(table[t0 * c0p * entry_bytes:], t1 - t0, n, _lib.desc(x0))
+        core = net.forward_core(V(x0, c0, 0))                 # coarsest first
       fuse = self.use_kernel_prediction and net.can_fuse_post_kp(self.kernel_size, ft)
       logits = None if fuse else net.post_process(core)       # largest first
       # 4. split per feature + kernel prediction per scale (Architecture.py:581-591)

@@ -10,6 +10,7 @@ import os
 import torch
 
 DD_F32, DD_F16, DD_BF16 = 0, 1, 2
+DD_F16X2 = 3   # weight-packing code of the split-fp16 mode
 DD_PACK_BF16 = 16
 DD_CONV_RELU, DD_CONV_RELU_COPY, DD_CONV_RESIDUAL_MASK = 1, 2, 4
 
@@ -59,6 +60,10 @@ SIGNATURES = {
     "dd_conv2d_pack_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "dd_conv2d_fwd": (_i, [_vp, _T, _vp, _vp, _i, _u32, _T, _T, _T, _vp]),
     "dd_conv2d_transpose2x2_fwd": (_i, [_vp, _T, _vp, _vp, _u32, _T, _vp]),
+    "dd_conv2d_fwd_split": (_i, [_vp, _T, _T, _vp, _vp, _i, _u32, _T, _T, _vp]),
+    "dd_conv2d_transpose2x2_fwd_split": (_i, [_vp, _T, _T, _vp, _vp, _u32, _T, _T, _vp]),
+    "dd_maxpool_s2_fwd_split": (_i, [_vp, _T, _T, _i, _T, _T, _vp]),
+    "dd_assemble_input_split": (_i, [_vp, _vp, _i, _i, _T, _T, _vp]),
     "dd_conv2d_transpose3x3_fwd": (_i, [_vp, _T, _P(_vp), _vp, _u32, _T, _T, _vp]),
     "dd_maxpool_s2_fwd": (_i, [_vp, _T, _i, _T, _vp]),
     "dd_avgpool_fwd": (_i, [_vp, _T, _i, _T, _vp]),
@@ -214,7 +219,7 @@ class Context:
     w = w.detach().to(torch.float32).contiguous().cpu()
     ks = w.shape[0]
     cin, cout = (w.shape[3], w.shape[2]) if transposed else (w.shape[2], w.shape[3])
-    code = DD_F16 if dtype == torch.float16 else (DD_BF16 if dtype == torch.bfloat16 else DD_F32)
+    code = DD_F16X2 if dtype == "float16x2" else (DD_F16 if dtype == torch.float16 else (DD_BF16 if dtype == torch.bfloat16 else DD_F32))
     nbytes = self.lib.dd_conv2d_packed_bytes(ks, cin, cout, code, int(transposed))
     packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
     self._check(self.lib.dd_conv2d_pack_weights(self.handle, w.data_ptr(), ks, cin, cout, code, int(transposed),
@@ -228,6 +233,25 @@ class Context:
         self.handle, ctypes.byref(x), w_packed.data_ptr(), bias.data_ptr() if bias is not None else None, ksize,
         flags, ctypes.byref(residual) if residual is not None else None, ctypes.byref(y),
         ctypes.byref(y_relu) if y_relu is not None else None, self._stream()))
+
+  def conv2d_split(self, x_hi, x_lo, w_packed, bias, ksize, y_hi, y_lo, relu=False):
+    """float16x2 mode (dd_conv2d_fwd_split): fp16 pairs in, an fp16 pair or one fp32 tensor (y_lo None) out."""
+    self._check(self.lib.dd_conv2d_fwd_split(
+        self.handle, ctypes.byref(x_hi), ctypes.byref(x_lo), w_packed.data_ptr(), bias.data_ptr() if bias is not None else None,
+        ksize, DD_CONV_RELU if relu else 0, ctypes.byref(y_hi), ctypes.byref(y_lo) if y_lo is not None else None, self._stream()))
+
+  def conv2d_transpose2x2_split(self, x_hi, x_lo, w_packed, bias, y_hi, y_lo, relu=False):
+    self._check(self.lib.dd_conv2d_transpose2x2_fwd_split(
+        self.handle, ctypes.byref(x_hi), ctypes.byref(x_lo), w_packed.data_ptr(), bias.data_ptr() if bias is not None else None,
+        DD_CONV_RELU if relu else 0, ctypes.byref(y_hi), ctypes.byref(y_lo), self._stream()))
+
+  def maxpool_s2_split(self, x_hi, x_lo, ksize, y_hi, y_lo):
+    self._check(self.lib.dd_maxpool_s2_fwd_split(self.handle, ctypes.byref(x_hi), ctypes.byref(x_lo), ksize, ctypes.byref(y_hi),
+                                                 ctypes.byref(y_lo), self._stream()))
+
+  def assemble_input_split(self, table_dev, tuples, n, out_hi, out_lo):
+    self._check(self.lib.dd_assemble_input_split(self.handle, table_dev.data_ptr(), tuples, n, ctypes.byref(out_hi),
+                                                 ctypes.byref(out_lo), self._stream()))
 
   def conv2d_transpose2x2(self, x, w_packed, bias, y, relu=False):
     self._check(self.lib.dd_conv2d_transpose2x2_fwd(

@@ -128,6 +128,8 @@ struct TcLaunch {
   const dd_tensor* y_relu;
   int ups, sp0;             // ups == 2: group g -> sub-pixel sp0 + g -> (ay, ax) = (sp >> 1, sp & 1)
   int s_mask, rm_lo, rm_hi; // tap subset (3x3 only); s_mask == 0 -> all
+  const dd_tensor* x_lo;    // split-fp16 mode: low halves of the input (same shape as x) / of the 16-bit output
+  const dd_tensor* y_lo;
 };
 
 // view of `t` seen through a stride-`ups` sub-pixel lattice starting at (ay, ax)
@@ -165,8 +167,21 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
   p.strips = (p.W + kRowsTileW - 1) / kRowsTileW;
   p.total_rows = static_cast<long long>(p.N) * p.strips * p.H;
   const int cin16 = round_up(x->c, 16);
-  p.n_chunks = (cin16 + 63) / 64;
-  p.ksteps_last = (cin16 - 64 * (p.n_chunks - 1)) / 16;
+  p.nb = (cin16 + 63) / 64;
+  p.ksteps_last = (cin16 - 64 * (p.nb - 1)) / 16;
+  p.split = L.x_lo ? 1 : 0;
+  p.n_chunks = p.split ? 3 * p.nb : p.nb;
+  const int w_chunks = p.split ? 2 * p.nb : p.nb;          // chunks of the packed weight tensor ([W_hi | W_lo] when split)
+  if (p.split) {
+    DD_CHECK_ARG(x->dtype == DD_F16 && L.x_lo->dtype == DD_F16 && L.x_lo->c == x->c && L.x_lo->n == x->n && L.x_lo->h == x->h &&
+                     L.x_lo->w == x->w && L.x_lo->coff % 8 == 0 && L.x_lo->cstride % 8 == 0, "split conv: bad low-half input view");
+    DD_CHECK_ARG(!L.residual && !L.y_relu, "split conv: no residual / relu copy");
+  }
+  if (L.y_lo) {
+    DD_CHECK_ARG(p.split && y->dtype == DD_F16 && L.y_lo->dtype == DD_F16 && L.y_lo->c == y->c && L.y_lo->coff % 8 == 0 &&
+                     L.y_lo->cstride % 8 == 0, "split conv: bad low-half output view");
+    p.split_out = 1;
+  }
   const bool k3 = (L.ksize == 3);
   p.halo = k3 ? 1 : 0;
   if (k3) {
@@ -198,7 +213,7 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
   const size_t stage_bytes = static_cast<size_t>(kRowsEpiWarps) * 4096;   // one 4 KB staging row set per epilogue warp
   const size_t fixed = stage_bytes + 1024 /*bias*/ + 3072 /*barriers + MMA plans*/;
   const size_t avail = ctx->max_smem_optin - 1024 /*alignment slack*/ - fixed;
-  const size_t w_total = static_cast<size_t>(p.n_chunks) * p.n_s * p.b_tile_bytes;
+  const size_t w_total = static_cast<size_t>(w_chunks) * p.n_s * p.b_tile_bytes;
   size_t b_bytes;
   if (!ctx->conv_force_stream && w_total + 4ull * p.a_slot_bytes <= avail) {
     p.w_resident = 1; p.b_stages = 1; p.G = 1;
@@ -259,11 +274,19 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
     int rc = encode_map(ctx, &maps.a, x->dtype == DD_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, 4, dims, strides, box,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc) return rc;
+    if (p.split) {
+      const dd_tensor* xl = L.x_lo;
+      cuuint64_t lstrides[3] = {static_cast<cuuint64_t>(xl->cstride) * 2, static_cast<cuuint64_t>(xl->w) * xl->cstride * 2,
+                                static_cast<cuuint64_t>(xl->h) * xl->w * xl->cstride * 2};
+      rc = encode_map(ctx, &maps.a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, reinterpret_cast<__half*>(xl->ptr) + xl->coff, 4, dims,
+                      lstrides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+      if (rc) return rc;
+    }
   }
   {
     const int r_total = k3 ? 3 : 1;
     cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(L.rows_total), static_cast<cuuint64_t>(r_total),
-                          static_cast<cuuint64_t>(p.n_chunks * p.tiles_per_chunk)};
+                          static_cast<cuuint64_t>(w_chunks * p.tiles_per_chunk)};
     cuuint64_t strides[3] = {128, static_cast<cuuint64_t>(L.rows_total) * 128,
                              static_cast<cuuint64_t>(L.rows_total) * 128 * r_total};
     cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.cpad), static_cast<cuuint32_t>(n_r), 1};
@@ -276,6 +299,11 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
     int rc = encode_out_map(ctx, &maps.out[g], y, 0, L.cout, x->h, x->w, L.ups, L.ups == 2 ? (sp >> 1) : 0,
                             L.ups == 2 ? (sp & 1) : 0);
     if (rc) return rc;
+    if (p.split_out) {
+      rc = encode_out_map(ctx, &maps.out_lo[g], L.y_lo, 0, L.cout, x->h, x->w, L.ups, L.ups == 2 ? (sp >> 1) : 0,
+                          L.ups == 2 ? (sp & 1) : 0);
+      if (rc) return rc;
+    }
   }
   if (L.y_relu) {
     DD_CHECK_ARG(L.y_relu->dtype == x->dtype && L.y_relu->coff % 8 == 0 && L.y_relu->cstride % 8 == 0 && L.ngroups == 1,
@@ -382,8 +410,8 @@ int dd_ctx_set_option(dd_ctx* ctx, const char* name, int value) {
 
 size_t dd_conv2d_packed_bytes(int ksize, int cin, int cout, int dtype, int transposed) {
   const int k2 = ksize * ksize;
-  if (is_half_type(dtype)) {
-    const int chunks = (round_up(cin, 16) + 63) / 64;
+  if (is_half_type(dtype) || dtype == DD_F16X2) {
+    const int chunks = (round_up(cin, 16) + 63) / 64 * (dtype == DD_F16X2 ? 2 : 1);
     const int rows = transposed ? k2 * packed_cpad(cout) : packed_cpad(cout);
     const int tiles = transposed ? 1 : k2;
     return static_cast<size_t>(chunks) * tiles * rows * 64 * 2;
@@ -400,30 +428,40 @@ int dd_conv2d_pack_weights(dd_ctx* ctx, const float* w, int ksize, int cin, int 
   const size_t bytes = dd_conv2d_packed_bytes(ksize, cin, cout, dtype, transposed);
   const int k2 = ksize * ksize;
   std::vector<uint8_t> host(bytes, 0);
-  if (is_half_type(dtype)) {
+  if (is_half_type(dtype) || dtype == DD_F16X2) {
     const int cpad = packed_cpad(cout);
     uint16_t* dst = reinterpret_cast<uint16_t*>(host.data());
     auto cvt = [dtype](float v) -> uint16_t {
       if (dtype == DD_BF16) { const __nv_bfloat16 b = __float2bfloat16_rn(v); return *reinterpret_cast<const uint16_t*>(&b); }
       const __half h = __float2half_rn(v); return *reinterpret_cast<const uint16_t*>(&h);
     };
+    // DD_F16X2: W = W_hi + W_lo, W_hi = fp16(W), W_lo = fp16(W - W_hi); the chunks of W_lo follow those of W_hi
+    const int nb = (round_up(cin, 16) + 63) / 64;
+    auto lo_of = [](float v) -> float { return v - __half2float(__float2half_rn(v)); };
     if (!transposed) {
       // TF [kh,kw,cin,cout] -> [chunk][s][r][cpad][64]   (tap (r,s): r = row offset, s = column offset)
       for (int r = 0; r < ksize; ++r)
         for (int s = 0; s < ksize; ++s)
           for (int c = 0; c < cin; ++c)
             for (int o = 0; o < cout; ++o) {
+              const float v = w[(static_cast<size_t>(r * ksize + s) * cin + c) * cout + o];
               const size_t tile = static_cast<size_t>(c / 64) * ksize + s;
-              dst[((tile * ksize + r) * cpad + o) * 64 + (c % 64)] =
-                  cvt(w[(static_cast<size_t>(r * ksize + s) * cin + c) * cout + o]);
+              dst[((tile * ksize + r) * cpad + o) * 64 + (c % 64)] = cvt(v);
+              if (dtype == DD_F16X2) {
+                const size_t tile_lo = static_cast<size_t>(nb + c / 64) * ksize + s;
+                dst[((tile_lo * ksize + r) * cpad + o) * 64 + (c % 64)] = cvt(lo_of(v));
+              }
             }
     } else {
       // TF transpose layout [kh,kw,cout,cin] -> [chunk][sub-pixel][cpad][64]: one 1x1 GEMM, rows (sub-pixel, cout)
       for (int sp = 0; sp < k2; ++sp)
         for (int o = 0; o < cout; ++o)
-          for (int c = 0; c < cin; ++c)
-            dst[((static_cast<size_t>(c / 64) * k2 + sp) * cpad + o) * 64 + (c % 64)] =
-                cvt(w[(static_cast<size_t>(sp) * cout + o) * cin + c]);
+          for (int c = 0; c < cin; ++c) {
+            const float v = w[(static_cast<size_t>(sp) * cout + o) * cin + c];
+            dst[((static_cast<size_t>(c / 64) * k2 + sp) * cpad + o) * 64 + (c % 64)] = cvt(v);
+            if (dtype == DD_F16X2)
+              dst[((static_cast<size_t>(nb + c / 64) * k2 + sp) * cpad + o) * 64 + (c % 64)] = cvt(lo_of(v));
+          }
     }
   } else {
     float* dst = reinterpret_cast<float*>(host.data());
@@ -441,8 +479,9 @@ int dd_conv2d_pack_weights(dd_ctx* ctx, const float* w, int ksize, int cin, int 
   return DD_OK;
 }
 
-int dd_conv2d_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const float* bias, int ksize, uint32_t flags,
-                  const dd_tensor* residual, const dd_tensor* y, const dd_tensor* y_relu, void* stream) {
+static int conv2d_fwd_impl(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* x_lo, const void* w_packed, const float* bias,
+                           int ksize, uint32_t flags, const dd_tensor* residual, const dd_tensor* y, const dd_tensor* y_lo,
+                           const dd_tensor* y_relu, void* stream) {
   DD_CHECK_ARG(ctx && w_packed, "NULL argument");
   DD_CHECK_ARG(tensor_ok(x) && tensor_ok(y), "bad tensor descriptor");
   DD_CHECK_ARG(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
@@ -466,8 +505,9 @@ int dd_conv2d_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const f
   for (int row0 = 0; row0 < cpad_total; row0 += slice) {
     const int cpad = (cpad_total - row0 < slice) ? (cpad_total - row0) : slice;
     const int cout = (y->c - row0 < cpad) ? (y->c - row0) : cpad;
-    dd_tensor ys = *y, yr, rs;
+    dd_tensor ys = *y, yr, rs, yl;
     ys.coff += row0; ys.c = cout;
+    if (y_lo) { yl = *y_lo; yl.coff += row0; yl.c = cout; }
     if (y_relu) { yr = *y_relu; yr.coff += row0; yr.c = cout; }
     if (residual) { rs = *residual; rs.coff += row0; rs.c = cout; }
     TcLaunch L;
@@ -478,14 +518,28 @@ int dd_conv2d_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const f
     L.bias_count = round_up(y->c, 16) - row0 < 256 ? round_up(y->c, 16) - row0 : 256;
     L.flags = flags; L.residual = residual ? &rs : nullptr; L.y = &ys; L.y_relu = y_relu ? &yr : nullptr;
     L.ups = 1; L.sp0 = 0; L.s_mask = 0; L.rm_lo = 0; L.rm_hi = 2;
+    L.x_lo = x_lo; L.y_lo = y_lo ? &yl : nullptr;
     int rc = launch_conv_rows(ctx, L, s);
     if (rc) return rc;
   }
   return DD_OK;
 }
 
-int dd_conv2d_transpose2x2_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const float* bias,
-                               uint32_t flags, const dd_tensor* y, void* stream) {
+int dd_conv2d_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const float* bias, int ksize, uint32_t flags,
+                  const dd_tensor* residual, const dd_tensor* y, const dd_tensor* y_relu, void* stream) {
+  return conv2d_fwd_impl(ctx, x, nullptr, w_packed, bias, ksize, flags, residual, y, nullptr, y_relu, stream);
+}
+
+int dd_conv2d_fwd_split(dd_ctx* ctx, const dd_tensor* x_hi, const dd_tensor* x_lo, const void* w_packed, const float* bias,
+                        int ksize, uint32_t flags, const dd_tensor* y_hi, const dd_tensor* y_lo, void* stream) {
+  DD_CHECK_ARG(tensor_ok(x_hi) && tensor_ok(x_lo) && x_hi->dtype == DD_F16, "split conv: fp16 (hi, lo) input pair expected");
+  DD_CHECK_ARG(tensor_ok(y_hi) && ((y_hi->dtype == DD_F32 && !y_lo) || (y_hi->dtype == DD_F16 && tensor_ok(y_lo))),
+               "split conv: output is an fp16 (hi, lo) pair or one fp32 tensor");
+  return conv2d_fwd_impl(ctx, x_hi, x_lo, w_packed, bias, ksize, flags, nullptr, y_hi, y_lo, nullptr, stream);
+}
+
+static int transpose2x2_impl(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* x_lo, const void* w_packed, const float* bias,
+                             uint32_t flags, const dd_tensor* y, const dd_tensor* y_lo, void* stream) {
   DD_CHECK_ARG(ctx && w_packed, "NULL argument");
   DD_CHECK_ARG(tensor_ok(x) && tensor_ok(y), "bad tensor descriptor");
   DD_CHECK_ARG(y->n == x->n && y->h == 2 * x->h && y->w == 2 * x->w, "transpose2x2: output must be 2x input");
@@ -513,10 +567,23 @@ int dd_conv2d_transpose2x2_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_pa
     L.bias = bias; L.bias_count = round_up(cout, 16);
     L.flags = flags; L.residual = nullptr; L.y = y; L.y_relu = nullptr;
     L.ups = 2; L.sp0 = sp0;
+    L.x_lo = x_lo; L.y_lo = y_lo;
     int rc = launch_conv_rows(ctx, L, s);
     if (rc) return rc;
   }
   return DD_OK;
+}
+
+int dd_conv2d_transpose2x2_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const float* bias,
+                               uint32_t flags, const dd_tensor* y, void* stream) {
+  return transpose2x2_impl(ctx, x, nullptr, w_packed, bias, flags, y, nullptr, stream);
+}
+
+int dd_conv2d_transpose2x2_fwd_split(dd_ctx* ctx, const dd_tensor* x_hi, const dd_tensor* x_lo, const void* w_packed,
+                                     const float* bias, uint32_t flags, const dd_tensor* y_hi, const dd_tensor* y_lo, void* stream) {
+  DD_CHECK_ARG(tensor_ok(x_hi) && tensor_ok(x_lo) && tensor_ok(y_hi) && tensor_ok(y_lo) && x_hi->dtype == DD_F16 &&
+                   y_hi->dtype == DD_F16, "split transposed conv: fp16 (hi, lo) pairs expected");
+  return transpose2x2_impl(ctx, x_hi, x_lo, w_packed, bias, flags, y_hi, y_lo, stream);
 }
 
 int dd_conv2d_transpose3x3_fwd(dd_ctx* ctx, const dd_tensor* x, const void* const* w_phase, const float* bias,

@@ -85,6 +85,43 @@ __global__ void __launch_bounds__(256) maxpool_h8_kernel(const PoolParams p) {
   *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.y.ptr) + opix * p.y.cstride + p.y.coff + c) = o;
 }
 
+// split-fp16 pairs (x = hi + lo, the "float16x2" mode): the maximum is taken on the fp32 sums and re-split exactly
+__global__ void __launch_bounds__(256) maxpool_split_kernel(const PoolParams p, const View xlo, const View ylo) {
+  const int cv = p.y.c / 8;
+  const size_t total = static_cast<size_t>(p.y.n) * p.y.h * p.y.w * cv;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % cv) * 8;
+  const size_t opix = idx / cv;
+  const int ox = static_cast<int>(opix % p.y.w);
+  const int oy = static_cast<int>((opix / p.y.w) % p.y.h);
+  const int n = static_cast<int>(opix / (static_cast<size_t>(p.y.w) * p.y.h));
+  const uint16_t* xh = reinterpret_cast<const uint16_t*>(p.x.ptr);
+  const uint16_t* xl = reinterpret_cast<const uint16_t*>(xlo.ptr);
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+  for (int r = 0; r < p.ksize; ++r) {
+    const int yy = 2 * oy - p.pad_y + r;
+    if (yy < 0 || yy >= p.x.h) continue;
+    for (int s = 0; s < p.ksize; ++s) {
+      const int xx = 2 * ox - p.pad_x + s;
+      if (xx < 0 || xx >= p.x.w) continue;
+      const size_t ip = p.x.pix(n, yy, xx);
+      float fh[8], fl[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(xh + ip * p.x.cstride + p.x.coff + c)), 0, fh);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(xl + ip * xlo.cstride + xlo.coff + c)), 0, fl);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], fh[i] + fl[i]);
+    }
+  }
+  float hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { hi[i] = __half2float(__float2half_rn(m[i])); lo[i] = m[i] - hi[i]; }
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.y.ptr) + opix * p.y.cstride + p.y.coff + c) = pack8(hi, 0);
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ylo.ptr) + opix * ylo.cstride + ylo.coff + c) = pack8(lo, 0);
+}
+
 // average pooling factor x factor, stride factor, TF 'SAME' (padded cells excluded from the divisor)
 struct AvgPoolParams {
   View x, y;
@@ -193,6 +230,8 @@ struct AssembleParams {
   const dd_gather_entry* table;
   View out;
   int tuples, n;
+  int split;       // float16x2 mode: out = fp16(v), out_lo = fp16(v - out)
+  View out_lo;
 };
 __global__ void __launch_bounds__(256) assemble_kernel(const AssembleParams p) {
   const size_t img_pix = static_cast<size_t>(p.out.h) * p.out.w;
@@ -213,6 +252,12 @@ __global__ void __launch_bounds__(256) assemble_kernel(const AssembleParams p) {
         f[i] = e.ptr ? __ldg(e.ptr + spix * e.cstride + e.cidx) : e.constant;
       }
       *reinterpret_cast<uint4*>(o + c0) = pack8(f, p.out.bf16);
+      if (p.split) {
+        float lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) lo[i] = f[i] - __half2float(__float2half_rn(f[i]));
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_lo.ptr) + opix * p.out_lo.cstride + p.out_lo.coff + c0) = pack8(lo, 0);
+      }
     }
   } else {
     for (int c = 0; c < p.out.c; ++c) {
@@ -351,6 +396,27 @@ int dd_maxpool_s2_fwd(dd_ctx* ctx, const dd_tensor* x, int ksize, const dd_tenso
   return DD_OK;
 }
 
+int dd_maxpool_s2_fwd_split(dd_ctx* ctx, const dd_tensor* x_hi, const dd_tensor* x_lo, int ksize, const dd_tensor* y_hi,
+                            const dd_tensor* y_lo, void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(x_hi) && tensor_ok(x_lo) && tensor_ok(y_hi) && tensor_ok(y_lo), "bad argument");
+  DD_CHECK_ARG(ksize == 2 || ksize == 3, "maxpool ksize must be 2 or 3");
+  const dd_tensor* all[4] = {x_hi, x_lo, y_hi, y_lo};
+  for (const dd_tensor* t : all)
+    DD_CHECK_ARG(t->dtype == DD_F16 && t->c == x_hi->c && t->c % 8 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0,
+                 "maxpool_split: fp16 views with multiples of 8 channels expected");
+  const int oh = (x_hi->h + 1) / 2, ow = (x_hi->w + 1) / 2;
+  DD_CHECK_ARG(y_hi->n == x_hi->n && y_hi->h == oh && y_hi->w == ow && y_lo->h == oh && y_lo->w == ow && x_lo->h == x_hi->h &&
+                   x_lo->w == x_hi->w, "maxpool_split: bad dims");
+  PoolParams p;
+  p.x = make_view(x_hi); p.y = make_view(y_hi); p.ksize = ksize;
+  const int pty = (oh - 1) * 2 + ksize - x_hi->h, ptx = (ow - 1) * 2 + ksize - x_hi->w;
+  p.pad_y = (pty > 0 ? pty : 0) / 2; p.pad_x = (ptx > 0 ? ptx : 0) / 2;
+  const size_t total = static_cast<size_t>(y_hi->n) * oh * ow * (y_hi->c / 8);
+  maxpool_split_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, make_view(x_lo), make_view(y_lo));
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
 int dd_avgpool_fwd(dd_ctx* ctx, const dd_tensor* x, int factor, const dd_tensor* y, void* stream) {
   DD_CHECK_ARG(ctx && tensor_ok(x) && tensor_ok(y), "bad argument");
   DD_CHECK_ARG(factor >= 1 && factor <= 16, "avgpool factor out of range");
@@ -395,8 +461,24 @@ int dd_assemble_input(dd_ctx* ctx, const dd_gather_entry* table_dev, int tuples,
   DD_CHECK_ARG(ctx && table_dev && tensor_ok(out), "bad argument");
   DD_CHECK_ARG(tuples > 0 && n > 0 && out->n == tuples * n, "assemble: out.n must be tuples*n");
   AssembleParams p;
+  memset(&p, 0, sizeof(p));
   p.table = table_dev; p.out = make_view(out); p.tuples = tuples; p.n = n;
   const size_t total = static_cast<size_t>(out->n) * out->h * out->w;
+  assemble_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_assemble_input_split(dd_ctx* ctx, const dd_gather_entry* table_dev, int tuples, int n, const dd_tensor* out_hi,
+                            const dd_tensor* out_lo, void* stream) {
+  DD_CHECK_ARG(ctx && table_dev && tensor_ok(out_hi) && tensor_ok(out_lo), "bad argument");
+  DD_CHECK_ARG(tuples > 0 && n > 0 && out_hi->n == tuples * n, "assemble: out.n must be tuples*n");
+  AssembleParams p;
+  memset(&p, 0, sizeof(p));
+  p.table = table_dev; p.out = make_view(out_hi); p.out_lo = make_view(out_lo); p.tuples = tuples; p.n = n; p.split = 1;
+  DD_CHECK_ARG(out_hi->dtype == DD_F16 && out_lo->dtype == DD_F16 && vec16_ok(p.out) && vec16_ok(p.out_lo) && out_lo->c == out_hi->c &&
+                   out_lo->h == out_hi->h && out_lo->w == out_hi->w, "assemble_split: fp16 views with multiples of 8 channels expected");
+  const size_t total = static_cast<size_t>(out_hi->n) * out_hi->h * out_hi->w;
   assemble_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;

@@ -44,6 +44,8 @@ struct ConvRowsMaps {
   CUtensorMap b;        // weights [64, cpad, n_r, tiles] fp16, box [64, cpad, n_r, 1]
   CUtensorMap out[4];   // primary output view per column group (sub-pixel), box [64 | 32, 32, 1, 1]
   CUtensorMap out_relu; // optional fp16 relu(primary) view
+  CUtensorMap a_lo;     // split mode: the low halves of the input (x = hi + lo)
+  CUtensorMap out_lo[4];// split mode: the low halves of the 16-bit output
 };
 
 struct ConvRowsParams {
@@ -69,6 +71,12 @@ struct ConvRowsParams {
   int ngroups, group_c, cout_store, ups;
   int relu, out_f32, has_relu_copy;
   int bf16;               // 16-bit tensors are bfloat16 (operands, 16-bit outputs, residual / mask)
+  // split-fp16 arithmetic (the high-accuracy tensor-core mode): x = x_hi + x_lo, W = W_hi + W_lo (each an fp16 pair with
+  // ~22 significant bits); x.W ~= x_hi.W_hi + x_lo.W_hi + x_hi.W_lo is three chunk passes over the same accumulators:
+  // A chunk c of the 3 * nb reads part c / nb in (hi, lo, hi) of the input, weight chunk (c / nb == 2 ? nb : 0) + c % nb.
+  int split;              // 0: plain; 1: split input + split weights
+  int nb;                 // 64-channel chunks of the input proper (n_chunks == nb, or 3 * nb when split)
+  int split_out;          // the 16-bit output is written as hi (primary maps) + lo (out_lo maps)
   int bias_count;
   const float* bias;
   const __half* residual;
@@ -183,8 +191,9 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
             for (int g = 0; g < gcur; ++g) {
               mbar_wait(&a_empty[slot], phase ^ 1);
               mbar_arrive_expect_tx(&a_full[slot], p.a_tx_bytes);
-              tma_load_4d(a_smem + static_cast<size_t>(slot) * p.a_slot_bytes, &maps.a, &a_full[slot], c * 64,
-                          sg.x0 - p.halo, tg + g, sg.n);
+              const int part = c / p.nb;
+              tma_load_4d(a_smem + static_cast<size_t>(slot) * p.a_slot_bytes, part == 1 ? &maps.a_lo : &maps.a, &a_full[slot],
+                          (c - part * p.nb) * 64, sg.x0 - p.halo, tg + g, sg.n);
               if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
             }
           }
@@ -195,7 +204,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
     // ------------------------------------------------------------------ B producer
     if (elect_one()) {
       if (p.w_resident) {
-        const int tiles = p.n_chunks * p.n_s;
+        const int tiles = (p.split ? 2 * p.nb : p.n_chunks) * p.n_s;
         mbar_arrive_expect_tx(&b_full[0], p.b_tx_bytes * static_cast<uint32_t>(tiles));
         for (int i = 0; i < tiles; ++i)
           tma_load_4d(b_smem + static_cast<size_t>(i) * p.b_tile_bytes, &maps.b, &b_full[0], 0, p.b_row0, p.b_r0,
@@ -211,8 +220,9 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
               for (int si = 0; si < p.n_s; ++si) {
                 mbar_wait(&b_empty[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&b_full[stage], p.b_tx_bytes);
+                const int bc = (c >= 2 * p.nb) ? c - p.nb : (c >= p.nb ? c - p.nb : c);   // weight chunk of A chunk c
                 tma_load_4d(b_smem + static_cast<size_t>(stage) * p.b_tile_bytes, &maps.b, &b_full[stage], 0, p.b_row0,
-                            p.b_r0, c * p.tiles_per_chunk + p.s_list[si]);
+                            p.b_r0, bc * p.tiles_per_chunk + p.s_list[si]);
                 if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
               }
             }
@@ -335,7 +345,9 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
             const bool initialises = (r_lo == rm_lo);
             if (tr) p.trace[it * 8 + 1] = clock64();                                      // plan in registers
             for (int c = 0; c < n_chunks; ++c) {
-              const int ksteps = (c == n_chunks - 1) ? p.ksteps_last : 4;
+              int cc = c; while (cc >= p.nb) cc -= p.nb;
+              const int ksteps = (cc == p.nb - 1) ? p.ksteps_last : 4;
+              const int bc = (c >= 2 * p.nb) ? c - p.nb : cc;                              // resident weight chunk of A chunk c
               if (!(c == 0 && probed && probe_a)) mbar_wait(&a_full[a_slot], a_phase);
               if (c == 0 && initialises && !(probed && probe_e))
                 mbar_wait(&acc_empty[blk], (use & 1u) ^ 1u);                              // previous user drained
@@ -362,7 +374,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
               for (int si = 0; si < n_s; ++si) {
                 uint32_t b_tile;
                 if (p.w_resident) {
-                  b_tile = b_base + static_cast<uint32_t>(c * n_s + si) * b_tile_bytes;
+                  b_tile = b_base + static_cast<uint32_t>(bc * n_s + si) * b_tile_bytes;
                 } else {
                   mbar_wait(&b_full[b_stage], b_phase);
                   tc_fence_after();
@@ -409,7 +421,8 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
             }
             const int a_slot0 = a_slot; const uint32_t a_phase0 = a_phase;
             for (int c = 0; c < n_chunks; ++c) {
-              const int ksteps = (c == n_chunks - 1) ? p.ksteps_last : 4;
+              int cc = c; while (cc >= p.nb) cc -= p.nb;
+              const int ksteps = (cc == p.nb - 1) ? p.ksteps_last : 4;
               for (int si = 0; si < n_s; ++si) {
                 mbar_wait(&b_full[b_stage], b_phase);
                 tc_fence_after();
@@ -512,12 +525,16 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
             tma_store_commit();
           }
         };
-        const int n_pass = p.has_relu_copy ? 2 : 1;    // pass 1 re-reads TMEM and writes the fp16 relu(primary) copy
+        // pass 0: primary output; then (optional) the fp16 relu(primary) copy; then (split mode) the low halves of the primary:
+        // every extra pass re-reads the accumulator from TMEM
+        const int n_pass = 1 + (p.has_relu_copy ? 1 : 0) + (p.split_out ? 1 : 0);
         for (int g = 0; g < p.ngroups; ++g) {
           for (int pass = 0; pass < n_pass; ++pass) {
+            const bool lo_pass = p.split_out && pass == n_pass - 1;
+            const bool relu_pass = p.has_relu_copy && pass == 1;
             const bool f32_rows = p.out_f32 && pass == 0;
-            const bool do_relu = p.relu || pass == 1;
-            const CUtensorMap* omap = (pass == 0) ? &maps.out[g] : &maps.out_relu;
+            const bool do_relu = p.relu || relu_pass;
+            const CUtensorMap* omap = lo_pass ? &maps.out_lo[g] : (relu_pass ? &maps.out_relu : &maps.out[g]);
             for (int cb = 0; cb < p.cout_store; cb += 32) {
               uint32_t v[32];
               __syncwarp();
@@ -581,7 +598,13 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
                     for (int e = 0; e < 4; ++e) pb[e] = __floats2bfloat162_rn(f[i * 8 + 2 * e], f[i * 8 + 2 * e + 1]);
                   } else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) ph[e] = __floats2half2_rn(f[i * 8 + 2 * e], f[i * 8 + 2 * e + 1]);
+                    for (int e = 0; e < 4; ++e) {
+                      ph[e] = __floats2half2_rn(f[i * 8 + 2 * e], f[i * 8 + 2 * e + 1]);
+                      if (lo_pass) {      // what the fp16 rounding of the primary pass dropped
+                        const float2 hi = __half22float2(ph[e]);
+                        ph[e] = __floats2half2_rn(f[i * 8 + 2 * e] - hi.x, f[i * 8 + 2 * e + 1] - hi.y);
+                      }
+                    }
                   }
                   *reinterpret_cast<uint4*>(row + (((sub * 4 + i) ^ (lane & 7)) << 4)) = pk;
                 }

@@ -238,13 +238,14 @@ class NetworkSpec:
 # ------------------------------------------------------------------------------------------------ device side
 class V:
   """Channel window [coff, coff+c) of a contiguous NHWC torch tensor (the Python face of dd_tensor)."""
-  __slots__ = ("t", "c", "coff", "d")
+  __slots__ = ("t", "c", "coff", "d", "lo")
 
   def __init__(self, t, c=None, coff=0):
     self.t = t
     self.coff = coff
     self.c = t.shape[3] - coff if c is None else c
     self.d = _lib.desc(t, self.c, coff)
+    self.lo = None        # float16x2 mode: the view of the low halves (same channels, second half of the buffer)
 
   def window(self, c, coff):
     return V(self.t, c, self.coff + coff)
@@ -254,11 +255,19 @@ class DeviceNetwork:
   """Weights of a NetworkSpec packed on one GPU + the forward executor."""
 
   def __init__(self, ctx, spec, weights, dtype=torch.float16, logits_dtype=torch.float32):
-    assert dtype in (torch.float16, torch.bfloat16, torch.float32)
+    assert dtype in (torch.float16, torch.bfloat16, torch.float32, "float16x2")
+    # "float16x2": the high-accuracy tensor-core mode - every activation / weight is an fp16 (hi, lo) pair, three MMA passes
+    # per layer (dd_conv2d_fwd_split); buffers hold [hi channels | lo channels]
+    self.split = (dtype == "float16x2")
+    self.pack_dtype = dtype
+    if self.split:
+      dtype = torch.float16
+      if spec.core_name != "U-Net":
+        raise _lib.DDError("the float16x2 mode is built for the U-Net core (the benchmarked network) only")
     self.ctx, self.spec, self.dtype = ctx, spec, dtype
     # bfloat16 storage runs the same tensor-core kernels (kind::f16 with bf16 operands), the fused compose kernel included;
     # the fused output-head kernel is fp16 mma.sync code, so bf16 uses the layer-by-layer launches there
-    self.logits_dtype = logits_dtype if dtype == torch.float16 else torch.float32
+    self.logits_dtype = logits_dtype if (dtype == torch.float16 and not self.split) else torch.float32
     self.fused_compose = True   # tests flip this to compare against the layer-by-layer path
     self.fused_post_kp = True   # likewise: 1x1 post-processing + kernel-prediction apply in one kernel
     self.align = 8 if dtype in (torch.float16, torch.bfloat16) else 1
@@ -284,7 +293,7 @@ class DeviceNetwork:
         # one packed 3x3 weight set per output phase is built lazily by _transpose3x3
         self.packed[var.name] = self._pack_transpose3x3(k)
       else:
-        self.packed[var.name] = ctx.pack_conv_weights(torch.from_numpy(k), self.dtype, transposed=var.transposed)
+        self.packed[var.name] = ctx.pack_conv_weights(torch.from_numpy(k), self.pack_dtype, transposed=var.transposed)
       bias = torch.zeros(_round_up(var.cout, 16), dtype=torch.float32)
       bias[:var.cout] = torch.from_numpy(b)
       self.bias[var.name] = bias.to(dev)
@@ -352,6 +361,68 @@ class DeviceNetwork:
       self._conv(var, cur, dst, relu=True)
       cur = dst
     return out
+
+  # -- U-Net on fp16 (hi, lo) pairs (float16x2 mode) -------------------------------------------------------------
+  def _sv(self, t, c=None, coff=0):
+    """Split view: channels [coff, coff+c) of the hi half and of the lo half of a [.., 2*Ct] buffer."""
+    ct = t.shape[3] // 2
+    v = V(t, ct - coff if c is None else c, coff)
+    v.lo = V(t, v.c, ct + coff)
+    return v
+
+  def _sbuf(self, key, shape):
+    return self._buf("x2." + key, tuple(shape[:3]) + (2 * shape[3],))
+
+  def _conv_split(self, var, x, y, relu=False):
+    assert x.c == var.cin and y.c == var.cout and x.lo is not None
+    self.ctx.conv2d_split(x.d, x.lo.d, self.packed[var.name], self.bias[var.name], var.ksize, y.d,
+                          y.lo.d if y.lo is not None else None, relu=relu)
+
+  def _block_split(self, key, layers, x, out):
+    b, h, w = x.t.shape[0], x.t.shape[1], x.t.shape[2]
+    cur = x
+    for i, var in enumerate(layers):
+      dst = out if i == len(layers) - 1 else self._sv(self._sbuf("%s.pp%d" % (key, i % 2), (b, h, w, _round_up(var.cout, 8))), var.cout)
+      self._conv_split(var, cur, dst, relu=True)
+      cur = dst
+    return out
+
+  def _forward_unet_split(self, x0):
+    spec, f, steps, ctx = self.spec, self.spec.filters, self.spec.steps, self.ctx
+    b, h, w = x0.t.shape[0], x0.t.shape[1], x0.t.shape[2]
+    dims = [(h, w)]
+    for i in range(steps):
+      hh, ww = dims[-1]
+      if hh % 2 or ww % 2:
+        raise _lib.DDError("height/width must be divisible by 2^%d (got %dx%d)" % (steps, h, w))
+      dims.append((hh // 2, ww // 2))
+    cats, x = [], x0
+    for i in range(steps):
+      hh, ww = dims[i]
+      cat = self._sbuf("unet.cat%d" % i, (b, hh, ww, 2 * f[i]))
+      cats.append(cat)
+      skip = self._sv(cat, f[i], 0)
+      self._block_split("unet.d%d" % i, spec.down[i], x, skip)
+      pooled = self._sv(self._sbuf("unet.pool%d" % i, (b, dims[i + 1][0], dims[i + 1][1], f[i])))
+      ctx.maxpool_s2_split(skip.d, skip.lo.d, 3, pooled.d, pooled.lo.d)
+      x = pooled
+    results = []
+    for i in range(steps):
+      index = steps - i
+      hh, ww = dims[index]
+      out = self._sv(self._sbuf("unet.out%d" % index, (b, hh, ww, f[index])))
+      self._block_split("unet.u%d" % index, spec.up[i], x, out)
+      if spec.use_multiscale:
+        results.append(out)
+      cat = cats[index - 1]
+      var = spec.upsample[i]
+      up = self._sv(cat, f[index - 1], f[index - 1])
+      ctx.conv2d_transpose2x2_split(out.d, out.lo.d, self.packed[var.name], self.bias[var.name], up.d, up.lo.d, relu=True)
+      x = self._sv(cat)
+    out = self._sv(self._sbuf("unet.out0", (b, h, w, f[0])))
+    self._block_split("unet.l", spec.last, x, out)
+    results.append(out)
+    return results
 
   # -- U-Net ---------------------------------------------------------------------------------------------
   def _forward_unet(self, x0):
@@ -465,10 +536,12 @@ class DeviceNetwork:
     """Core architecture only: the multi-scale outputs, COARSEST first (the order of spec.post)."""
     spec = self.spec
     assert x0.c == spec.input_channels, (x0.c, spec.input_channels)
+    if self.split:
+      return self._forward_unet_split(x0)
     return self._forward_unet(x0) if spec.core_name == "U-Net" else self._forward_tiramisu(x0)
 
   def can_fuse_post_kp(self, ksize, features):
-    return (self.fused_post_kp and self.dtype == torch.float16 and
+    return (self.fused_post_kp and self.dtype == torch.float16 and not self.split and
             bool(self.ctx.lib.dd_post_kp_supported(int(ksize), int(features))) and
             self.spec.output_channels == features * ksize * ksize)
 
@@ -496,10 +569,15 @@ class DeviceNetwork:
     o = spec.output_channels
     for k, (r, (a, bvar)) in enumerate(zip(results, spec.post)):
       b, h, w = r.t.shape[0], r.t.shape[1], r.t.shape[2]
-      mid = V(self._buf("post.mid%d" % k, (b, h, w, _round_up(o, self.align))), o)
-      self._conv(a, r, mid, relu=True)
       out = V(self._buf("post.out%d" % k, (b, h, w, _round_up(o, 8)), self.logits_dtype), o)
-      self._conv(bvar, mid, out, relu=False)
+      if self.split:
+        mid = self._sv(self._sbuf("post.mid%d" % k, (b, h, w, _round_up(o, 8))), o)
+        self._conv_split(a, r, mid, relu=True)
+        self._conv_split(bvar, mid, out, relu=False)        # fp32 logits: no low half
+      else:
+        mid = V(self._buf("post.mid%d" % k, (b, h, w, _round_up(o, self.align))), o)
+        self._conv(a, r, mid, relu=True)
+        self._conv(bvar, mid, out, relu=False)
       outs.append(out)
     if spec.use_multiscale:
       outs.reverse()

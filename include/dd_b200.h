@@ -37,6 +37,8 @@ typedef enum dd_status {
 } dd_status;
 
 typedef enum dd_dtype { DD_F32 = 0, DD_F16 = 1, DD_BF16 = 2 } dd_dtype;   /* 16-bit types: storage only, fp32 accumulation */
+/* weight-packing code of the split-fp16 ("float16x2") tensor-core mode: W = W_hi + W_lo, both fp16 (dd_conv2d_fwd_split) */
+#define DD_F16X2 3
 
 typedef struct dd_tensor {
   void* ptr;
@@ -96,6 +98,18 @@ int dd_conv2d_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const f
 int dd_conv2d_transpose2x2_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const float* bias,
                                uint32_t flags, const dd_tensor* y, void* stream);
 
+/* The high-accuracy tensor-core mode ("float16x2"): every activation x is an fp16 PAIR x = x_hi + x_lo (x_hi = fp16(x),
+ * x_lo = fp16(x - x_hi): ~22 significant bits), weights likewise (packed with dtype DD_F16X2), and
+ *   x.W ~= x_hi.W_hi + x_lo.W_hi + x_hi.W_lo
+ * runs as three chunk passes of the same tcgen05 kernel over one fp32 accumulator (the dropped x_lo.W_lo term is 2^-22
+ * relative).  The reference computes in fp32 (Training.py:518-524); this mode is what meets its 1e-4 parity bound on tensor
+ * cores, at 3x the MMA work.  y is an fp16 pair (y_hi, y_lo) or one fp32 tensor (y_lo NULL); same shapes / flags as above
+ * (no residual / relu copy). */
+int dd_conv2d_fwd_split(dd_ctx* ctx, const dd_tensor* x_hi, const dd_tensor* x_lo, const void* w_packed, const float* bias,
+                        int ksize, uint32_t flags, const dd_tensor* y_hi, const dd_tensor* y_lo, void* stream);
+int dd_conv2d_transpose2x2_fwd_split(dd_ctx* ctx, const dd_tensor* x_hi, const dd_tensor* x_lo, const void* w_packed,
+                                     const float* bias, uint32_t flags, const dd_tensor* y_hi, const dd_tensor* y_lo, void* stream);
+
 /* y = relu?(conv2d_transpose(x, W, k=3, stride=2, 'same') + b) (Tiramisu.py:62-64; SURVEY A.5: full 2n+1
  * output cropped at the tail).  Computed as 4 output phases, each a stride-1 conv of x with the taps that
  * land on that phase: w_phase[py*2+px] is an ordinary packed 3x3 kernel (dd_conv2d_pack_weights,
@@ -108,6 +122,9 @@ int dd_conv2d_transpose3x3_fwd(dd_ctx* ctx, const dd_tensor* x, const void* cons
 /* tf.layers.max_pooling2d(pool=ksize, strides=2, 'same'): ksize 3 (UNet.py:42-44, pad bottom/right only)
  * or 2 (Tiramisu.py:55-57).  y dims = ceil(x dims / 2). */
 int dd_maxpool_s2_fwd(dd_ctx* ctx, const dd_tensor* x, int ksize, const dd_tensor* y, void* stream);
+/* the same on fp16 (hi, lo) pairs of the float16x2 mode: max of hi + lo, re-split */
+int dd_maxpool_s2_fwd_split(dd_ctx* ctx, const dd_tensor* x_hi, const dd_tensor* x_lo, int ksize, const dd_tensor* y_hi,
+                            const dd_tensor* y_lo, void* stream);
 /* tf.layers.average_pooling2d(factor, factor, 'same') (MultiScalePrediction.py:11-13); fp32 images. */
 int dd_avgpool_fwd(dd_ctx* ctx, const dd_tensor* x, int factor, const dd_tensor* y, void* stream);
 
@@ -144,6 +161,9 @@ typedef struct dd_gather_entry {
 } dd_gather_entry;
 int dd_assemble_input(dd_ctx* ctx, const dd_gather_entry* table_dev, int tuples, int n, const dd_tensor* out,
                       void* stream);
+/* float16x2 mode: the same gather written as an fp16 (hi, lo) pair */
+int dd_assemble_input_split(dd_ctx* ctx, const dd_gather_entry* table_dev, int tuples, int n, const dd_tensor* out_hi,
+                            const dd_tensor* out_lo, void* stream);
 
 /* ---- kernel prediction ---------------------------------------------------------------------- */
 /* KernelPrediction.kernel_prediction (KernelPrediction.py:11-63) with use_softmax=True, mode='symmetric',

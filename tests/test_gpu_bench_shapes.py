@@ -131,9 +131,10 @@ def single_tuple_json():
   return j
 
 
-# Measured on B200 (round 2): fp16 storage max 2.6e-4 / mean 4e-6 of the output scale at 1080p - the asserted bounds are
-# 2x that.  float32 (exact path) is not run at this size: it is the SIMT kernel, pinned on the small cases.
-@pytest.mark.parametrize("dtype,tol_max,tol_mean", [("float16", 6e-4, 1e-5)])
+# Measured on B200 (round 2): fp16 storage max 2.3e-4 / mean 9e-7 of the output scale at 1080p - the asserted bounds are
+# ~2x that; float16x2 (the split-fp16 tensor-core mode) must meet the north-star 1e-4 outright.  float32 (exact path) is not
+# run at this size: it is the SIMT kernel, pinned on the small cases.
+@pytest.mark.parametrize("dtype,tol_max,tol_mean", [("float16", 6e-4, 1e-5), ("float16x2", 1e-4, 5e-6)])
 def test_predict_full_1080p_frame_single_tuple_vs_oracle(dtype, tol_max, tol_mean):
   j = single_tuple_json()
   host = Architecture(j)

@@ -2,9 +2,10 @@
 committed golden vectors.
 
 Tolerances (per-pixel L1, i.e. |out - oracle| per element, relative to max(1, |oracle|_max) of the pass):
-  float32 mode : <= 1e-4   - the north-star bound; the CUDA path accumulates in fp32 like the reference
-  float16 mode : <= 5e-2 max, <= 5e-3 mean - fp16 storage of ~22 stacked conv layers (fp32 accumulate, fp32
-                 logits / softmax / filter apply); see DESIGN.md "precision"
+  float32 mode   : <= 1e-4 - the north-star bound; the exact (SIMT) path accumulates in fp32 like the reference
+  float16x2 mode : <= 1e-4 - the same bound on TENSOR CORES (fp16 hi + lo pairs, three tcgen05 passes per layer)
+  float16 mode   : 2x the measured error of each case (FP16_BOUNDS) - fp16 storage of ~22 stacked conv layers (fp32
+                   accumulate, fp32 logits / softmax / filter apply); see DESIGN.md "precision"
 """
 import os
 
@@ -69,6 +70,16 @@ def test_predict_float16_tensor_core_path(name):
   mx, mean = errors(out, oracle)
   print(name, "fp16 max %.2e mean %.2e" % (mx, mean))
   assert mx <= FP16_BOUNDS[name][0] and mean <= FP16_BOUNDS[name][1]
+
+
+@pytest.mark.parametrize("name", ["example", "combined_onehot", "variants", "rgb9"])
+def test_predict_float16x2_tensor_core_path_meets_1e4(name):
+  """The high-accuracy TENSOR-CORE mode (fp16 hi + lo pairs, three tcgen05 passes per layer, fp32 accumulate) meets the
+  reference's 1e-4 bound on every U-Net case - the same bound the exact SIMT path is held to."""
+  arch, out, oracle = run_case(name, "float16x2")
+  mx, mean = errors(out, oracle)
+  print(name, "fp16x2 max %.2e mean %.2e" % (mx, mean))
+  assert mx <= 1e-4
 
 
 @pytest.mark.parametrize("name", cases.GOLDEN_CASES)

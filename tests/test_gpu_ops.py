@@ -84,6 +84,79 @@ def test_conv2d_tensor_core_fp16(ctx, ks, cin, cout, n, h, w, cs, coff):
     assert torch.isnan(y[..., :8].float()).all(), "wrote outside the channel window"
 
 
+def _split16(x):
+  """x (float32) -> fp16 pair (hi, lo) with x ~= hi + lo to ~22 bits."""
+  hi = x.astype(np.float16)
+  lo = (x - hi.astype(np.float32)).astype(np.float16)
+  return hi, lo
+
+
+SPLIT_CASES = [
+    # ks, cin, cout, n, h, w
+    (3, 64, 64, 2, 21, 150),
+    (3, 32, 64, 1, 16, 300),
+    (3, 96, 96, 1, 10, 130),       # 1.5 chunks per part
+    (3, 192, 96, 1, 10, 130),      # streamed weights
+    (3, 128, 128, 1, 9, 140),
+    (1, 64, 25, 2, 9, 150),        # post-process 1x1, fp32 output
+    (1, 25, 25, 1, 9, 150),
+]
+
+
+@pytest.mark.parametrize("ks,cin,cout,n,h,w", SPLIT_CASES)
+def test_conv2d_split_fp16x2(ctx, ks, cin, cout, n, h, w):
+  """dd_conv2d_fwd_split (float16x2 mode: x = hi + lo, W = W_hi + W_lo, three MMA passes) against the float64 convolution of
+  the ORIGINAL float32 operands: 2e-5 of the output scale - the floor is the fp32 accumulation of 3 * K products in TMEM
+  (measured 7e-6 at K = 864), the dropped lo.lo term and the fp16 rounding of the lo halves are ~2^-22 relative; plain fp16
+  operands give ~5e-4 here."""
+  x = (RNG.standard_normal((n, h, w, cin)) * 0.5).astype(np.float32)
+  k = (RNG.standard_normal((ks, ks, cin, cout)) / np.sqrt(ks * ks * cin)).astype(np.float32)
+  b = (RNG.standard_normal(cout) * 0.1).astype(np.float32)
+  wp = ctx.pack_conv_weights(torch.from_numpy(k), "float16x2")
+  ci8, co8 = (cin + 7) // 8 * 8, (cout + 7) // 8 * 8
+  xbuf = torch.zeros(n, h, w, 2 * ci8, dtype=torch.float16, device="cuda")
+  hi, lo = _split16(x)
+  xbuf[..., :cin] = dev(hi, torch.float16)
+  xbuf[..., ci8:ci8 + cin] = dev(lo, torch.float16)
+  want = np_ops.conv2d_same(x.astype(np.float64), k.astype(np.float64), b.astype(np.float64), relu=True)
+  # (a) fp16 pair out
+  ybuf = torch.full((n, h, w, 2 * co8), float("nan"), dtype=torch.float16, device="cuda")
+  ctx.conv2d_split(_lib.desc(xbuf, cin, 0), _lib.desc(xbuf, cin, ci8), wp, pad_bias(b), ks, _lib.desc(ybuf, cout, 0),
+                   _lib.desc(ybuf, cout, co8), relu=True)
+  got = ybuf[..., :cout].float() + ybuf[..., co8:co8 + cout].float()
+  close(got, want, 2e-5, "split conv, pair out")
+  # (b) fp32 out
+  y32 = torch.full((n, h, w, co8), float("nan"), device="cuda")
+  ctx.conv2d_split(_lib.desc(xbuf, cin, 0), _lib.desc(xbuf, cin, ci8), wp, pad_bias(b), ks, _lib.desc(y32, cout, 0), None, relu=True)
+  close(y32[..., :cout], want, 2e-5, "split conv, fp32 out")
+
+
+def test_split_transpose2x2_maxpool_assemble(ctx):
+  n, h, w, cin, cout = 2, 6, 70, 128, 96
+  x = (RNG.standard_normal((n, h, w, cin)) * 0.5).astype(np.float32)
+  k = (RNG.standard_normal((2, 2, cout, cin)) / np.sqrt(cin)).astype(np.float32)
+  b = (RNG.standard_normal(cout) * 0.1).astype(np.float32)
+  wp = ctx.pack_conv_weights(torch.from_numpy(k), "float16x2", transposed=True)
+  hi, lo = _split16(x)
+  xbuf = torch.cat([dev(hi, torch.float16), dev(lo, torch.float16)], dim=3).contiguous()
+  # written into the second half of a skip-concat pair buffer [hi(2c) | lo(2c)]
+  ybuf = torch.full((n, 2 * h, 2 * w, 4 * cout), float("nan"), dtype=torch.float16, device="cuda")
+  ctx.conv2d_transpose2x2_split(_lib.desc(xbuf, cin, 0), _lib.desc(xbuf, cin, cin), wp, pad_bias(b),
+                                _lib.desc(ybuf, cout, cout), _lib.desc(ybuf, cout, 3 * cout), relu=True)
+  want = np_ops.conv2d_transpose_same_s2(x.astype(np.float64), k.astype(np.float64), b.astype(np.float64), relu=True)
+  close(ybuf[..., cout:2 * cout].float() + ybuf[..., 3 * cout:].float(), want, 2e-5, "split convT2x2")
+  assert torch.isnan(ybuf[..., :cout].float()).all() and torch.isnan(ybuf[..., 2 * cout:3 * cout].float()).all()
+  # max-pool 3x3 s2 on pairs: exact max of hi + lo, re-split
+  c = 64
+  v = (RNG.standard_normal((n, 10, 14, c)) * 2).astype(np.float32)
+  vh, vl = _split16(v)
+  vbuf = torch.cat([dev(vh, torch.float16), dev(vl, torch.float16)], dim=3).contiguous()
+  pbuf = torch.empty(n, 5, 7, 2 * c, dtype=torch.float16, device="cuda")
+  ctx.maxpool_s2_split(_lib.desc(vbuf, c, 0), _lib.desc(vbuf, c, c), 3, _lib.desc(pbuf, c, 0), _lib.desc(pbuf, c, c))
+  pair = vh.astype(np.float32) + vl.astype(np.float32)
+  close(pbuf[..., :c].float() + pbuf[..., c:].float(), np_ops.max_pool_same_s2(pair.astype(np.float64), 3), 1e-6, "split maxpool")
+
+
 def test_conv2d_tensor_core_residual_and_relu_copy(ctx):
   n, h, w, c = 1, 11, 70, 24
   x = (RNG.standard_normal((n, h, w, c)) * 0.5).astype(np.float16)
