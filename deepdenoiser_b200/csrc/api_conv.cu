@@ -318,8 +318,13 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
   if (p.total_rows < grid) grid = static_cast<int>(p.total_rows);
   p.rows_per_cta = static_cast<int>((p.total_rows + grid - 1) / grid);
   grid = static_cast<int>((p.total_rows + p.rows_per_cta - 1) / p.rows_per_cta);
-  DD_CUDA(cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  conv_rows_kernel<<<grid, kRowsThreads, smem, stream>>>(maps, p);
+  if (p.split) {
+    DD_CUDA(cudaFuncSetAttribute(conv_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    conv_rows_kernel<true><<<grid, kRowsThreads, smem, stream>>>(maps, p);
+  } else {
+    DD_CUDA(cudaFuncSetAttribute(conv_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    conv_rows_kernel<false><<<grid, kRowsThreads, smem, stream>>>(maps, p);
+  }
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }

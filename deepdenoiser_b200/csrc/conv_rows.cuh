@@ -132,6 +132,8 @@ struct RowsWalker {
   }
 };
 
+// SPLIT: the float16x2 instantiation (three chunk passes, low-half output pass); the plain instantiation carries none of it
+template <bool SPLIT>
 __global__ void __launch_bounds__(kRowsThreads, 1)
 conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -191,9 +193,9 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
             for (int g = 0; g < gcur; ++g) {
               mbar_wait(&a_empty[slot], phase ^ 1);
               mbar_arrive_expect_tx(&a_full[slot], p.a_tx_bytes);
-              const int part = c / p.nb;
-              tma_load_4d(a_smem + static_cast<size_t>(slot) * p.a_slot_bytes, part == 1 ? &maps.a_lo : &maps.a, &a_full[slot],
-                          (c - part * p.nb) * 64, sg.x0 - p.halo, tg + g, sg.n);
+              const int part = SPLIT ? c / p.nb : 0;
+              tma_load_4d(a_smem + static_cast<size_t>(slot) * p.a_slot_bytes, (SPLIT && part == 1) ? &maps.a_lo : &maps.a,
+                          &a_full[slot], (c - part * p.nb) * 64, sg.x0 - p.halo, tg + g, sg.n);
               if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
             }
           }
@@ -204,7 +206,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
     // ------------------------------------------------------------------ B producer
     if (elect_one()) {
       if (p.w_resident) {
-        const int tiles = (p.split ? 2 * p.nb : p.n_chunks) * p.n_s;
+        const int tiles = (SPLIT ? 2 * p.nb : p.n_chunks) * p.n_s;
         mbar_arrive_expect_tx(&b_full[0], p.b_tx_bytes * static_cast<uint32_t>(tiles));
         for (int i = 0; i < tiles; ++i)
           tma_load_4d(b_smem + static_cast<size_t>(i) * p.b_tile_bytes, &maps.b, &b_full[0], 0, p.b_row0, p.b_r0,
@@ -220,7 +222,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
               for (int si = 0; si < p.n_s; ++si) {
                 mbar_wait(&b_empty[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&b_full[stage], p.b_tx_bytes);
-                const int bc = (c >= 2 * p.nb) ? c - p.nb : (c >= p.nb ? c - p.nb : c);   // weight chunk of A chunk c
+                const int bc = (SPLIT && c >= p.nb) ? c - p.nb : c;                        // weight chunk of A chunk c
                 tma_load_4d(b_smem + static_cast<size_t>(stage) * p.b_tile_bytes, &maps.b, &b_full[stage], 0, p.b_row0,
                             p.b_r0, bc * p.tiles_per_chunk + p.s_list[si]);
                 if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
@@ -345,9 +347,10 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
             const bool initialises = (r_lo == rm_lo);
             if (tr) p.trace[it * 8 + 1] = clock64();                                      // plan in registers
             for (int c = 0; c < n_chunks; ++c) {
-              int cc = c; while (cc >= p.nb) cc -= p.nb;
+              int cc = c;
+              if (SPLIT) { while (cc >= p.nb) cc -= p.nb; }
               const int ksteps = (cc == p.nb - 1) ? p.ksteps_last : 4;
-              const int bc = (c >= 2 * p.nb) ? c - p.nb : cc;                              // resident weight chunk of A chunk c
+              const int bc = (SPLIT && c >= 2 * p.nb) ? c - p.nb : cc;                     // resident weight chunk of A chunk c
               if (!(c == 0 && probed && probe_a)) mbar_wait(&a_full[a_slot], a_phase);
               if (c == 0 && initialises && !(probed && probe_e))
                 mbar_wait(&acc_empty[blk], (use & 1u) ^ 1u);                              // previous user drained
@@ -421,7 +424,8 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
             }
             const int a_slot0 = a_slot; const uint32_t a_phase0 = a_phase;
             for (int c = 0; c < n_chunks; ++c) {
-              int cc = c; while (cc >= p.nb) cc -= p.nb;
+              int cc = c;
+              if (SPLIT) { while (cc >= p.nb) cc -= p.nb; }
               const int ksteps = (cc == p.nb - 1) ? p.ksteps_last : 4;
               for (int si = 0; si < n_s; ++si) {
                 mbar_wait(&b_full[b_stage], b_phase);
@@ -527,10 +531,10 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
         };
         // pass 0: primary output; then (optional) the fp16 relu(primary) copy; then (split mode) the low halves of the primary:
         // every extra pass re-reads the accumulator from TMEM
-        const int n_pass = 1 + (p.has_relu_copy ? 1 : 0) + (p.split_out ? 1 : 0);
+        const int n_pass = 1 + (p.has_relu_copy ? 1 : 0) + ((SPLIT && p.split_out) ? 1 : 0);
         for (int g = 0; g < p.ngroups; ++g) {
           for (int pass = 0; pass < n_pass; ++pass) {
-            const bool lo_pass = p.split_out && pass == n_pass - 1;
+            const bool lo_pass = SPLIT && p.split_out && pass == n_pass - 1;
             const bool relu_pass = p.has_relu_copy && pass == 1;
             const bool f32_rows = p.out_f32 && pass == 0;
             const bool do_relu = p.relu || relu_pass;
@@ -600,7 +604,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                       ph[e] = __floats2half2_rn(f[i * 8 + 2 * e], f[i * 8 + 2 * e + 1]);
-                      if (lo_pass) {      // what the fp16 rounding of the primary pass dropped
+                      if (SPLIT && lo_pass) {      // what the fp16 rounding of the primary pass dropped
                         const float2 hi = __half22float2(ph[e]);
                         ph[e] = __floats2half2_rn(f[i * 8 + 2 * e] - hi.x, f[i * 8 + 2 * e + 1] - hi.y);
                       }
