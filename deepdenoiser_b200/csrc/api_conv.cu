@@ -222,19 +222,25 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
     if (p.a_slots > 8) p.a_slots = 8;
   } else {
     p.w_resident = 0;
-    p.b_stages = 2;
-    b_bytes = 2ull * p.b_tile_bytes;
+    // measured (tools/probe_conv_stream.py, round 2): L2 feeds the weight stream easily, what matters is that the epilogue
+    // overlaps the next rows - rows of a group complete together, so small groups + a deeper weight pipeline win when the
+    // TMEM ring is short (128-column blocks: 3 stages, 1 row per pass: 128->128 850 -> 942 TFLOP/s; 96-column blocks: 2 rows
+    // per pass: 96->96 814 -> 868)
+    p.b_stages = (ctx->conv_b_stages >= 2 && ctx->conv_b_stages <= 6) ? ctx->conv_b_stages : (p.cpad >= 128 ? 3 : 2);
+    b_bytes = static_cast<size_t>(p.b_stages) * p.b_tile_bytes;
+    if (!ctx->conv_b_stages && b_bytes + 2ull * p.a_slot_bytes > avail) { p.b_stages = 2; b_bytes = 2ull * p.b_tile_bytes; }
     DD_CHECK_ARG(b_bytes + 2ull * p.a_slot_bytes <= avail, "weight tile too large for shared memory (cpad %d)", p.cpad);
     p.a_slots = static_cast<int>((avail - b_bytes) / p.a_slot_bytes);
     if (p.a_slots > 12) p.a_slots = 12;
-    int g = p.ring - (n_r - 1) - 0;          // live blocks of a group: G + (n_r - 1)
+    int g = p.ring - n_r;                    // live blocks of a group: G + (n_r - 1), one more being drained
     if (n_r == 1) g = p.ring - 1;
     if (g > p.a_slots / 2) g = p.a_slots / 2;
     if (g < 1) g = 1;
     if (g > 8) g = 8;
     if (ctx->conv_rows > 0 && ctx->conv_rows < g) g = ctx->conv_rows;
     p.G = g;
-    if (b_bytes + static_cast<size_t>(p.a_slots) * p.a_slot_bytes + p.b_tile_bytes <= avail) {
+    if (!ctx->conv_b_stages && p.b_stages == 2 &&
+        b_bytes + static_cast<size_t>(p.a_slots) * p.a_slot_bytes + p.b_tile_bytes <= avail) {
       p.b_stages = 3; b_bytes += p.b_tile_bytes;
     }
   }
@@ -408,6 +414,7 @@ int dd_ctx_set_option(dd_ctx* ctx, const char* name, int value) {
   DD_CHECK_ARG(ctx && name, "NULL argument");
   if (!strcmp(name, "conv_rows")) { ctx->conv_rows = value; return DD_OK; }               // cap on G (rows per weight pass)
   if (!strcmp(name, "wgrad_variant")) { ctx->wgrad_variant = value; return DD_OK; }
+  if (!strcmp(name, "conv_b_stages")) { ctx->conv_b_stages = value; return DD_OK; }       // weight stages when streaming (0 = auto)
   if (!strcmp(name, "conv_force_stream")) { ctx->conv_force_stream = value; return DD_OK; } // never keep weights resident
   set_error("unknown option '%s'", name);
   return DD_ERR_INVALID;

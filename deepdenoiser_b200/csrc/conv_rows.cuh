@@ -418,18 +418,32 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
                 int r_hi = t + 1 - sg.y0; if (r_hi > rm_hi) r_hi = rm_hi;
                 int blk = bt + r_lo; uint32_t use = ut;
                 if (blk >= ring) { blk -= ring; use -= 1u; }
-                build_plan(plan + g * 8, blk, use, r_lo, r_hi);
+                if (r_lo == rm_lo && r_hi == rm_hi) {
+                  // interior row: the tabulated plan of this block index, with the wait parity of this use patched in
+                  // (building a plan costs ~500 cycles of this thread, 8 % of a 96-channel group)
+                  uint4* dst = plan + g * 8;
+                  const uint4* src = table + blk * 8;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) dst[i] = src[i];
+                  dst[0].w = (use & 1u) ^ 1u;
+                } else {
+                  build_plan(plan + g * 8, blk, use, r_lo, r_hi);
+                }
                 if (--bt < 0) { bt = ring - 1; ++ut; }
               }
             }
             const int a_slot0 = a_slot; const uint32_t a_phase0 = a_phase;
+            if (tr) p.trace[it * 8 + 1] = clock64();                                      // plans built
+            long long wait_b = 0, wait_a = 0;
             for (int c = 0; c < n_chunks; ++c) {
               int cc = c;
               if (SPLIT) { while (cc >= p.nb) cc -= p.nb; }
               const int ksteps = (cc == p.nb - 1) ? p.ksteps_last : 4;
               for (int si = 0; si < n_s; ++si) {
+                const long long tb0 = tr ? clock64() : 0;
                 mbar_wait(&b_full[b_stage], b_phase);
                 tc_fence_after();
+                if (tr) wait_b += clock64() - tb0;
                 const uint32_t b_lo0 = d_lo + ((b_base + static_cast<uint32_t>(b_stage) * b_tile_bytes) >> 4);
                 const uint32_t s_off = (si == 0) ? s_off0 : ((si == 1) ? s_off1 : s_off2);
                 int lin_slot = a_slot0 + c * gcur;      // slots of this chunk's rows: a_slot0 + c * gcur + g (mod a_slots)
@@ -445,9 +459,11 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
 #pragma unroll
                   for (int i = 0; i < 4; ++i) pf[i] = row_plan[4 + i];
                   if (si == 0) {
+                    const long long ta0 = tr ? clock64() : 0;
                     mbar_wait(&a_full[lin_slot], ph);
                     if (first_pass) mbar_wait(&acc_empty[hdr.z], hdr.w);    // previous user of the new row's block drained
                     tc_fence_after();
+                    if (tr) wait_a += clock64() - ta0;
                     if (tr && c == 0 && g == 0) p.trace[it * 8 + 2] = clock64();
                   }
                   const uint32_t a_lo = d_lo + ((a_base + static_cast<uint32_t>(lin_slot) * a_slot_bytes) >> 4) + s_off;
@@ -471,7 +487,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
               }
               if (--blk_top < 0) { blk_top = ring - 1; ++use_top; }
             }
-            if (tr) p.trace[it * 8 + 3] = clock64();
+            if (tr) { p.trace[it * 8 + 3] = clock64(); p.trace[512 + it] = wait_b; p.trace[576 + it] = wait_a; }
           }
         }
         q_seg += static_cast<uint32_t>(sg.y1 - sg.y0);
@@ -557,6 +573,13 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
                                                       : make_uint4(0, 0, 0, 0);
               }
               tmem_ld_wait();
+              // the accumulator block is free as soon as its last column chunk sits in registers: the issuing thread can
+              // start the next row on it while this row is still being converted and stored
+              if (g == p.ngroups - 1 && pass == n_pass - 1 && cb + 32 >= p.cout_store) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[blk]);
+              }
               float* f = reinterpret_cast<float*>(v);
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] += bias_smem[cb + i];
@@ -617,10 +640,8 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
             }
           }
         }
-        tc_fence_before();
         __syncwarp();
         if (tr) p.trace[it * 8 + 6] = clock64();
-        if (lane == 0) mbar_arrive(&acc_empty[blk]);
       }
     }
     if (lane == 0) tma_store_wait_all();

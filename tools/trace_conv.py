@@ -15,7 +15,7 @@ def run(n, h, w, cin, cout, ks, iters=3, f32_out=False, residual=False, relu_cop
   res = _lib.desc(torch.zeros(n, h, w, (cout + 7) // 8 * 8, dtype=torch.float16, device=dev), cout, 0) if residual else None
   yr = _lib.desc(torch.zeros(n, h, w, (cout + 7) // 8 * 8, dtype=torch.float16, device=dev), cout, 0) if relu_copy else None
   xd, yd = _lib.desc(x), _lib.desc(y, cout, 0)
-  trace = torch.zeros(64 * 8 + 128, dtype=torch.int64, device=dev)
+  trace = torch.zeros(64 * 8 + 256, dtype=torch.int64, device=dev)
   for _ in range(iters):
     ctx.conv2d(xd, wp, bias, ks, yd, relu=not residual, residual=res, y_relu=yr)
   ctx.set_trace_buffer(trace)
@@ -24,8 +24,8 @@ def run(n, h, w, cin, cout, ks, iters=3, f32_out=False, residual=False, relu_cop
   ctx.set_trace_buffer(None)
   full = trace.cpu()
   t = full[:512].view(64, 8)
-  mm = [(int(full[576 + i]), int(full[512 + i])) for i in range(60) if int(full[512 + i]) != 0]
-  print('  group 6 stamps (tag:+cycles since previous):', ' '.join('%d:+%d' % (mm[i][0], mm[i][1] - mm[i - 1][1]) for i in range(1, len(mm))))
+  print('  streamed path, cycles the issuing thread waited per group (weights | input rows + accumulators):',
+        ' '.join('%d|%d' % (int(full[512 + i]), int(full[576 + i])) for i in range(12)))
   base = int(t[0, 0])
   print("conv %dx%dx%d %d->%d k%d: rows = tile iteration; cycles relative to start" % (n, h, w, cin, cout, ks))
   print("  it | grp:enter     plan   a_full   issued | epi:enter  t_full    done | mma_busy epi_busy  period | waits_done probe_a probe_e")
@@ -48,3 +48,7 @@ if which == "small":
   run(2, 1080, 1920, 64, 25, 1)
 else:
   run(1, 1080, 1920, 64, 64, 3)
+if which == "mid":
+  run(8, 540, 960, 96, 96, 3)
+  run(8, 540, 960, 192, 96, 3)
+  run(8, 270, 480, 128, 128, 3)
