@@ -387,6 +387,8 @@ class Architecture:
     tuples = self.feature_prediction_tuples
     ft = self.features_per_tuple
     per_chunk = max(1, min(len(tuples), self.max_chunk_pixels // max(1, n * h * w)))
+    # balanced chunks (17 tuples at 1080p: 6 + 6 + 5 instead of 8 + 8 + 1): no launch is left with a single image
+    per_chunk = -(-len(tuples) // -(-len(tuples) // per_chunk))
     entry_bytes = self._ENTRY.itemsize
     for t0 in range(0, len(tuples), per_chunk):
       t1 = min(len(tuples), t0 + per_chunk)

@@ -48,7 +48,6 @@ struct WgrParams {
   float* dw;
   int layout;                // 0: [tap][cin][cout]   1: [tap][cout][cin]
   float scale;
-  int variant;               // debug: bit0 swaps the LBO / SBO fields of the descriptors
   int bf16;                  // operands are bfloat16
 };
 
@@ -168,12 +167,11 @@ wgrad_rows_kernel(const __grid_constant__ WgrMaps maps, const WgrParams p) {
   } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one() && has_work) {
-      const bool swap = (p.variant & 1) != 0;
       const uint32_t n_cols = p.k3 ? 192u : 64u;
       const uint32_t idesc = make_idesc_f16(128, static_cast<int>(n_cols)) | (1u << 15) | (1u << 16) | (p.bf16 ? kIdescBf16 : 0u);   // A, B MN-major
       const uint32_t x_base = smem_u32(x_smem), dz_base = smem_u32(dz_smem);
-      const uint64_t a_tmpl = swap ? make_desc_mn_sw128(0, 1024, p.dz_slot_bytes) : make_desc_mn_sw128(0, p.dz_slot_bytes, 1024);
-      const uint64_t b_tmpl = swap ? make_desc_mn_sw128(0, 1024, 128) : make_desc_mn_sw128(0, 128, 1024);
+      const uint64_t a_tmpl = make_desc_mn_sw128(0, p.dz_slot_bytes, 1024);
+      const uint64_t b_tmpl = make_desc_mn_sw128(0, 128, 1024);
       const uint32_t a_lo = static_cast<uint32_t>(a_tmpl), a_hi = static_cast<uint32_t>(a_tmpl >> 32);
       const uint32_t b_lo = static_cast<uint32_t>(b_tmpl), b_hi = static_cast<uint32_t>(b_tmpl >> 32);
       WgrWalker walk(p, part);
@@ -321,7 +319,7 @@ int launch_wgrad_rows(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* dz, int 
   p.bar_off = p.dz_off + static_cast<uint32_t>(p.rz + 1) * p.dz_slot_bytes;
   const size_t smem = 1024 + p.bar_off + 512;
   DD_CHECK_ARG(smem <= ctx->max_smem_optin, "wgrad: shared memory plan does not fit");
-  p.dw = dw; p.layout = layout; p.scale = scale; p.variant = ctx->wgrad_variant; p.bf16 = (x->dtype == DD_BF16);
+  p.dw = dw; p.layout = layout; p.scale = scale; p.bf16 = (x->dtype == DD_BF16);
   WgrMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc = encode_nhwc_f16(ctx, &maps.x, x, box_w);

@@ -20,7 +20,6 @@ struct dd_ctx {
   int conv_rows = 0;             // cap on input rows per weight pass (0 = auto), see conv_rows.cuh
   int conv_b_stages = 0;         // debug: weight stages of the streaming configuration (0 = auto)
   int conv_force_stream = 0;     // debug: stream weights even when they would fit in shared memory
-  int wgrad_variant = 0;         // debug: descriptor variant of wgrad_rows_kernel
   unsigned long long* conv_trace = nullptr;  // debug: device buffer [64][8] of clock64 stamps (CTA 0)
   std::atomic<int64_t> launches{0};
 };

@@ -1,5 +1,5 @@
-"""GPU probe for the tcgen05 weight-gradient kernel: correctness of the descriptor variants + TFLOP/s on the U-Net layer
-shapes.  Writes gpurun_out/probe_wgrad.json."""
+"""GPU probe for the tcgen05 weight-gradient kernel: a correctness spot check + TFLOP/s on the U-Net layer shapes.
+Writes gpurun_out/probe_wgrad.json."""
 import ctypes
 import json
 import os
@@ -17,7 +17,6 @@ out = []
 
 
 def check(variant, ks, cin, cout, n, h, w):
-  ctx.set_option("wgrad_variant", variant)
   x = torch.randn(n, h, w, cin, device="cuda").half()
   dz = torch.randn(n, h, w, cout, device="cuda").half()
   dw = torch.zeros(ks, ks, cin, cout, device="cuda")
@@ -59,12 +58,8 @@ def time_case(ks, cin, cout, n, h, w, iters=10):
 
 if __name__ == "__main__":
   os.makedirs("gpurun_out", exist_ok=True)
-  good = None
-  for variant in (0, 1):
-    check(variant, 3, 64, 64, 1, 9, 128)
-  for variant in (0, 1):
-    check(variant, 1, 64, 64, 1, 9, 128)
-  ctx.set_option("wgrad_variant", 0)
+  check(0, 3, 64, 64, 1, 9, 128)
+  check(0, 1, 64, 64, 1, 9, 128)
   check(0, 3, 128, 96, 2, 33, 200)
   for shape in [(3, 64, 64, 16, 256, 256), (3, 32, 64, 16, 256, 256), (3, 128, 64, 16, 256, 256), (3, 96, 96, 16, 128, 128),
                 (3, 192, 96, 16, 128, 128), (3, 128, 128, 16, 64, 64), (3, 64, 64, 8, 1080, 1920), (1, 64, 32, 16, 256, 256)]:
