@@ -74,7 +74,7 @@ SIGNATURES = {
     "dd_compose_tail_fwd": (_i, [_vp, _T, _vp, _vp, _i, _T, _T, _P(dd_invert_params), _T, _vp]),
     "dd_compose_weights_bytes": (_sz, []),
     "dd_compose_params_floats": (_sz, []),
-    "dd_compose_pack_weights": (_i, [_P(_vp), _i, _vp]),
+    "dd_compose_pack_weights": (_i, [_P(_vp), _P(_vp), _i, _vp]),
     "dd_compose_scales_fwd": (_i, [_vp, _T, _T, _vp, _vp, _i, _P(dd_invert_params), _T, _vp]),
     "dd_invert_standardization": (_i, [_vp, _T, _P(dd_invert_params), _T, _vp]),
     "dd_relu_bwd": (_i, [_vp, _T, _T, _T, _vp]),
@@ -381,8 +381,10 @@ def pack_compose_weights(head_w, head_b, conv_w, conv_b, tail_w, tail_b, dtype=D
   c = 24
   blob = np.zeros(lib.dd_compose_weights_bytes(), dtype=np.uint8)
   kernels = [np.ascontiguousarray(np.asarray(w, dtype=np.float32).reshape(3, 3, c, c)) for w in conv_w]
+  biases = [np.ascontiguousarray(np.asarray(b, dtype=np.float32).reshape(c)) for b in conv_b]
   ptrs = (ctypes.c_void_p * 4)(*[k.ctypes.data for k in kernels])
-  rc = lib.dd_compose_pack_weights(ptrs, int(dtype), blob.ctypes.data)
+  bptrs = (ctypes.c_void_p * 4)(*[b.ctypes.data for b in biases])
+  rc = lib.dd_compose_pack_weights(ptrs, bptrs, int(dtype), blob.ctypes.data)
   if rc != 0:
     raise DDError("dd_compose_pack_weights failed: %s" % lib.dd_last_error().decode())
   fl = np.zeros(lib.dd_compose_params_floats(), dtype=np.float32)

@@ -10,24 +10,39 @@ extern "C" {
 size_t dd_compose_weights_bytes(void) { return kCrWBytes; }
 size_t dd_compose_params_floats(void) { return kCrFloats; }
 
-/* Host-side packing of the four 3x3 24->24 kernels (TF layout [3,3,24,24] = [kh,kw,cin,cout]) into the operand layout of
- * compose_rows_kernel: [layer][kw = s][8-channel chunk j][row n = kh * 32 + cout][8 cin] 16-bit, zero padded. */
-int dd_compose_pack_weights(const float* const* conv_w, int dtype, void* blob_host) {
-  DD_CHECK_ARG(conv_w && blob_host && (dtype == DD_F16 || dtype == DD_BF16), "bad argument");
+/* Host-side packing of the four 3x3 24->24 layers (TF kernels [3,3,24,24] = [kh,kw,cin,cout], biases [24]) into the operand
+ * layout of compose_rows_kernel: per layer three tiles [kw = s][8-channel chunk j][row n = kh * 32 + cout][8 cin] 16-bit, zero
+ * padded; the centre tile (s = 1) has a 4th chunk whose K indices 24 / 25 hold the bias (hi / lo halves) in the rows of the
+ * centre tap (kh = 1); then the 24x24 identity of the residual connections and 96 rows of zeros. */
+int dd_compose_pack_weights(const float* const* conv_w, const float* const* conv_b, int dtype, void* blob_host) {
+  DD_CHECK_ARG(conv_w && conv_b && blob_host && (dtype == DD_F16 || dtype == DD_BF16), "bad argument");
   uint16_t* dst = reinterpret_cast<uint16_t*>(blob_host);
   memset(dst, 0, kCrWBytes);
-  for (int l = 0; l < 4; ++l)
-    for (int r = 0; r < 3; ++r)
-      for (int s = 0; s < 3; ++s)
+  auto cvt = [dtype](float v) -> uint16_t {
+    if (dtype == DD_BF16) { const __nv_bfloat16 b = __float2bfloat16_rn(v); return *reinterpret_cast<const uint16_t*>(&b); }
+    const __half h = __float2half_rn(v); return *reinterpret_cast<const uint16_t*>(&h);
+  };
+  auto back = [dtype](uint16_t bits) -> float {
+    if (dtype == DD_BF16) return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&bits));
+    return __half2float(*reinterpret_cast<const __half*>(&bits));
+  };
+  for (int l = 0; l < 4; ++l) {
+    for (int s = 0; s < 3; ++s) {
+      const size_t tile = (static_cast<size_t>(l) * kCrWLayer + s * kCrWTile + (s == 2 ? kCrWChunk : 0)) / 2;   // in 16-bit elements
+      for (int r = 0; r < 3; ++r)
         for (int c = 0; c < kCrC; ++c)
-          for (int o = 0; o < kCrC; ++o) {
-            const float v = conv_w[l][((r * 3 + s) * kCrC + c) * kCrC + o];
-            uint16_t bits;
-            if (dtype == DD_BF16) { const __nv_bfloat16 b = __float2bfloat16_rn(v); bits = *reinterpret_cast<const uint16_t*>(&b); }
-            else { const __half h = __float2half_rn(v); bits = *reinterpret_cast<const uint16_t*>(&h); }
-            const size_t tile = static_cast<size_t>(l * 3 + s) * (kCrWTile / 2);
-            dst[tile + (static_cast<size_t>(c / 8) * 96 + r * 32 + o) * 8 + (c % 8)] = bits;
-          }
+          for (int o = 0; o < kCrC; ++o)
+            dst[tile + (static_cast<size_t>(c / 8) * 96 + r * 32 + o) * 8 + (c % 8)] = cvt(conv_w[l][((r * 3 + s) * kCrC + c) * kCrC + o]);
+      if (s == 1)
+        for (int o = 0; o < kCrC; ++o) {
+          const uint16_t hi = cvt(conv_b[l][o]);
+          dst[tile + (static_cast<size_t>(3) * 96 + 32 + o) * 8 + 0] = hi;
+          dst[tile + (static_cast<size_t>(3) * 96 + 32 + o) * 8 + 1] = cvt(conv_b[l][o] - back(hi));
+        }
+    }
+  }
+  for (int o = 0; o < kCrC; ++o)
+    dst[kCrOffIdent / 2 + (static_cast<size_t>(o / 8) * 32 + o) * 8 + (o % 8)] = cvt(1.f);
   return DD_OK;
 }
 

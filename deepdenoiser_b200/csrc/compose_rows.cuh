@@ -37,19 +37,26 @@ constexpr int kCrSlotPx = 136;
 constexpr int kCrPlane = kCrSlotPx * 16;      // one 8-channel chunk of a row: 2176 B
 constexpr int kCrSlot = 3 * kCrPlane;         // 6528 B
 constexpr int kCrWChunk = 96 * 16;            // one 8-channel chunk of a weight tile: rows n = tap r * 32 + cout
-constexpr int kCrWTile = 3 * kCrWChunk;       // 4608 B per (layer, horizontal tap s)
-constexpr int kCrWBytes = 12 * kCrWTile;      // 55296 B
+constexpr int kCrWTile = 3 * kCrWChunk;       // 4608 B per (layer, horizontal tap s): input channels 0..23
+// the centre column's tile (s = 1) has a 4th chunk: K index 24 / 25 of tap r = 1 holds the layer's bias (hi / lo halves) - the
+// activations' 4th chunk is the constant (1, 1, 0, ...), so the tensor core adds the bias; the other tiles' 4th chunk is zeros
+constexpr int kCrWLayer = 3 * kCrWTile + kCrWChunk;   // 15360 B: tiles at 0 (s=0), kCrWTile (s=1, 4 chunks), 2*kCrWTile+kCrWChunk (s=2)
+constexpr int kCrOffIdent = 4 * kCrWLayer;            // identity [32 cout][24 cin]: the residual x + conv(..) as one more UMMA
+constexpr int kCrIdentChunk = 32 * 16;
+constexpr int kCrOffZeroB = kCrOffIdent + 3 * kCrIdentChunk;   // 96 rows of zeros: 4th chunk of every other weight tile
+constexpr int kCrWBytes = kCrOffZeroB + kCrWChunk;    // 64512 B
 constexpr int kCrX0Slots = 6, kCrMidSlots = 4, kCrResSlots = 6;
 constexpr int kCrWarps = 25, kCrThreads = kCrWarps * 32;
 constexpr int kCrWarpHead = 16, kCrWarpMma = 21;            // head: 5 warps = 130 pixels of a row slot (+ idle lanes); 4 issuing warps
 // shared memory carve-up (bytes from the 1024-aligned base)
 constexpr int kCrOffW = 0;
-constexpr int kCrOffX0 = kCrOffW + kCrWBytes + kCrWChunk;            // + finite pad behind the last weight tile
+constexpr int kCrOffX0 = kCrOffW + kCrWBytes;
 constexpr int kCrOffA1 = kCrOffX0 + kCrX0Slots * kCrSlot;
 constexpr int kCrOffAx1 = kCrOffA1 + kCrMidSlots * kCrSlot;
 constexpr int kCrOffA3 = kCrOffAx1 + kCrMidSlots * kCrSlot;
 constexpr int kCrOffRx1 = kCrOffA3 + kCrMidSlots * kCrSlot;
-constexpr int kCrOffZero = kCrOffRx1 + kCrResSlots * kCrSlot;        // the all-zero chunk (must be the highest operand address)
+constexpr int kCrOffZero = kCrOffRx1 + kCrResSlots * kCrSlot;        // the constant 4th activation chunk (1, 1, 0, ..) per pixel
+                                                                     // (must be the highest operand address: LBO is unsigned)
 constexpr int kCrOffBars = kCrOffZero + kCrPlane;
 constexpr int kCrNumBars = 2 * kCrX0Slots + 6 * kCrMidSlots + 2 * kCrResSlots + 32;
 constexpr int kCrSmem = 1024 + kCrOffBars + kCrNumBars * 8 + 16;
@@ -135,12 +142,14 @@ __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __gri
   // ---- one-time setup: weights + zeroed operand rings, barriers, TMEM
   for (int i = threadIdx.x; i < kCrWBytes / 16; i += kCrThreads)
     reinterpret_cast<uint4*>(smem + kCrOffW)[i] = __ldg(reinterpret_cast<const uint4*>(p.wblob) + i);
-  for (int i = threadIdx.x + kCrWBytes / 16; i < kCrOffBars / 16; i += kCrThreads)
+  for (int i = threadIdx.x + kCrWBytes / 16; i < kCrOffZero / 16; i += kCrThreads)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < kCrPlane / 16; i += kCrThreads)      // K index 24, 25 = 1.0 for every pixel (bias hi + lo)
+    reinterpret_cast<uint4*>(smem + kCrOffZero)[i] = make_uint4(BF16 ? 0x3F803F80u : 0x3C003C00u, 0, 0, 0);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kCrX0Slots; ++i) { mbar_init(&x0_full[i], 5); mbar_init(&x0_empty[i], 5); }
+    for (int i = 0; i < kCrX0Slots; ++i) { mbar_init(&x0_full[i], 5); mbar_init(&x0_empty[i], 2); }   // layer 1 + layer 2 (residual)
     for (int i = 0; i < 3 * kCrMidSlots; ++i) { mbar_init(&mid_full[i], 4); mbar_init(&mid_empty[i], 1); }
-    for (int i = 0; i < kCrResSlots; ++i) { mbar_init(&rx1_full[i], 4); mbar_init(&rx1_empty[i], 4); }
+    for (int i = 0; i < kCrResSlots; ++i) { mbar_init(&rx1_full[i], 4); mbar_init(&rx1_empty[i], 1); }  // layer 4 (residual)
     for (int i = 0; i < 16; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_mbar_init();
   }
@@ -230,9 +239,15 @@ __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __gri
       const int l = warp - kCrWarpMma;
       const uint32_t idesc0 = make_idesc_f16(128, 0) | (BF16 ? kIdescBf16 : 0u);
       constexpr uint32_t kHi = (128u >> 4) | (1u << 14);                      // SBO = 128 B, descriptor version 1, no swizzle
-      const uint32_t w_lo = (((base_u32 + kCrOffW) >> 4) | (static_cast<uint32_t>(kCrWChunk >> 4) << 16)) +
-                            static_cast<uint32_t>((l * 3 * kCrWTile) >> 4);
-      const uint32_t zero_q = (base_u32 + kCrOffZero) >> 4;                   // addresses in 16-byte units from here on
+      const uint32_t w_q = (base_u32 + kCrOffW + l * kCrWLayer) >> 4;           // addresses in 16-byte units from here on
+      const uint32_t zerob_q = (base_u32 + kCrOffW + kCrOffZeroB) >> 4, ident_q = (base_u32 + kCrOffW + kCrOffIdent) >> 4;
+      const uint32_t zero_q = (base_u32 + kCrOffZero) >> 4;                   // the constant (1, 1, 0, ..) activation chunk
+      // residual layers (2 and 4): x + conv(..) - the row of x (x0 / raw x1, already an operand row) times the identity
+      const bool has_res = (l == 1 || l == 3);
+      const uint32_t res_ring_q = (base_u32 + (l == 1 ? kCrOffX0 : kCrOffRx1)) >> 4;
+      uint64_t* res_full0 = (l == 1) ? x0_full : rx1_full;
+      uint64_t* res_empty0 = (l == 1) ? x0_empty : rx1_empty;
+      uint32_t rslot = 0, rphase = 0;
       const uint32_t ring_q = (base_u32 + (l == 0 ? kCrOffX0 : (l == 1 ? kCrOffA1 : (l == 2 ? kCrOffAx1 : kCrOffA3)))) >> 4;
       const uint32_t slots = (l == 0) ? kCrX0Slots : kCrMidSlots;
       uint64_t* in_full0 = (l == 0) ? x0_full : mid_full + (l - 1) * kCrMidSlots;
@@ -284,10 +299,27 @@ __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __gri
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
               const uint32_t a_lo = (ks == 0 ? a_k0 : a_k1) + static_cast<uint32_t>(s);
-              const uint32_t b_lo = w_lo + static_cast<uint32_t>((s * kCrWTile + ks * 2 * kCrWChunk) >> 4);
+              // weight tile of column s (s = 2 sits behind the 4-chunk centre tile); second K step: chunk 2 + (bias chunk of the
+              // centre tile | the zero rows for s = 0, 2)
+              const uint32_t tile_q = w_q + static_cast<uint32_t>((s * kCrWTile + (s == 2 ? kCrWChunk : 0) + ks * 2 * kCrWChunk) >> 4);
+              const uint32_t lbo = (ks == 0 || s == 1) ? static_cast<uint32_t>(kCrWChunk >> 4) : zerob_q - tile_q;
+              const uint32_t b_lo = tile_q | (lbo << 16);
               umma_f16(d_a, cr_desc_from(a_lo, kHi), cr_desc_from(b_lo + b_a, kHi), i_a, 1u);
               if (cnt_b) umma_f16(d_layer, cr_desc_from(a_lo, kHi), cr_desc_from(b_lo + b_b, kHi), i_b, 1u);
             }
+          }
+          if (has_res) {
+            // output row g (tap r = 1 of this input row) += identity . residual row g, centre column (s = 1)
+            mbar_wait_sleep(&res_full0[rslot], rphase);
+            tc_fence_after();
+            const uint32_t rq = res_ring_q + rslot * (kCrSlot >> 4) + 1u;
+            const uint32_t d_r = d_layer + ((3u - ((g + 1) & 3u) + 1u) & 3u) * 32u, i_r = idesc0 + (4u << 17);
+            umma_f16(d_r, cr_desc_from(rq | (static_cast<uint32_t>(kCrPlane >> 4) << 16), kHi),
+                     cr_desc_from(ident_q | (static_cast<uint32_t>(kCrIdentChunk >> 4) << 16), kHi), i_r, 1u);
+            const uint32_t rq2 = rq + 2u * (kCrPlane >> 4), iq2 = ident_q + 2u * (kCrIdentChunk >> 4);
+            umma_f16(d_r, cr_desc_from(rq2 | ((zero_q + 1u - rq2) << 16), kHi), cr_desc_from(iq2 | ((zerob_q - iq2) << 16), kHi), i_r, 1u);
+            umma_commit(&res_empty0[rslot]);
+            if (++rslot == kCrResSlots) { rslot = 0; rphase ^= 1u; }
           }
           umma_commit(&in_empty0[slot]);
           if (g > g_lo) umma_commit(&accf[3 - ((g - 1) & 3u)]);      // row g-1 has all three taps
@@ -311,10 +343,9 @@ __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __gri
     uint8_t* out_ring = smem + (L == 0 ? kCrOffA1 : (L == 1 ? kCrOffAx1 : kCrOffA3));
     uint64_t* out_full = mid_full + (L < 3 ? L : 0) * kCrMidSlots;
     uint64_t* out_empty = mid_empty + (L < 3 ? L : 0) * kCrMidSlots;
-    const float* bias = p.fl + 168 + L * kCrC;
     CrWalker walk(p);
     CrSeg sg;
-    uint32_t g = 0;
+    uint32_t g = 0, oslot = 0, ophase = 0, rslot = 0, rphase = 0;
     unsigned long long* tr = (p.trace && blockIdx.x == 0 && wq == 0 && lane == 0) ? p.trace + L * 64 * 8 : nullptr;
     while (walk.next(sg)) {
       const int x = sg.xs + m + 1;
@@ -342,6 +373,7 @@ __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __gri
         mbar_wait_sleep(&acc_full[L * 4 + blk], use & 1u);
         tc_fence_after();
         if (trace) tr[g * 8 + 1] = clock64();
+        // bias and (layers 2, 4) the residual were added by the tensor core: the accumulator IS the layer output
         uint32_t vr[32];
         tmem_ld_32x32(t_lane + blk * 32, vr);
         tmem_ld_wait();
@@ -351,65 +383,55 @@ __global__ void __launch_bounds__(kCrThreads, 1) compose_rows_kernel(const __gri
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[L * 4 + blk]);
         if (trace) tr[g * 8 + 2] = clock64();
-        float v[kCrC];
-#pragma unroll
-        for (int c = 0; c < kCrC; ++c) v[c] = __uint_as_float(vr[c]) + bias[c];
-
-        if (L == 1 || L == 3) {
-          // residual: x0 row g (layer 2) / x1 row g (layer 4), this thread's pixel
-          const uint32_t rs = g % kCrResSlots, ru = g / kCrResSlots;     // kCrX0Slots == kCrResSlots
-          uint64_t* rfull = (L == 1) ? &x0_full[rs] : &rx1_full[rs];
-          uint64_t* rempty = (L == 1) ? &x0_empty[rs] : &rx1_empty[rs];
-          mbar_wait_sleep(rfull, ru & 1u);
-          const uint8_t* rrow = smem + (L == 1 ? kCrOffX0 : kCrOffRx1) + rs * kCrSlot + (m + 1) * 16;
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(rrow + j * kCrPlane);
-            float f8[8];
-            unpack8(rv, BF16, f8);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[j * 8 + e] += f8[e];
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(rempty);
-        }
 
         if (L < 3) {
-          // operand row of the next layer: relu, zero outside the image (SAME padding of the next layer), 16-bit
-          const uint32_t slot = g % kCrMidSlots, ou = g / kCrMidSlots;
-          mbar_wait_sleep(&out_empty[slot], (ou & 1u) ^ 1u);
+          // operand row of the next layer: 16-bit, relu, zero outside the image (SAME padding of the next layer);
+          // layer 2 also publishes the raw row: the residual operand of layer 4
+          uint4 raw[3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            float f8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f8[e] = __uint_as_float(vr[j * 8 + e]);
+            raw[j] = inside ? pack8(f8, BF16) : make_uint4(0, 0, 0, 0);
+          }
+          mbar_wait_sleep(&out_empty[oslot], ophase ^ 1u);
           if (trace) tr[g * 8 + 3] = clock64();
-          uint8_t* orow = out_ring + slot * kCrSlot + (m + 1) * 16;
-          uint8_t* rrow = nullptr;
+          uint8_t* orow = out_ring + oslot * kCrSlot + (m + 1) * 16;
           if (L == 1) {
-            const uint32_t rs = g % kCrResSlots, ru = g / kCrResSlots;
-            mbar_wait_sleep(&rx1_empty[rs], (ru & 1u) ^ 1u);
-            rrow = smem + kCrOffRx1 + rs * kCrSlot + (m + 1) * 16;
+            mbar_wait_sleep(&rx1_empty[rslot], rphase ^ 1u);
+            uint8_t* rrow = smem + kCrOffRx1 + rslot * kCrSlot + (m + 1) * 16;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) *reinterpret_cast<uint4*>(rrow + j * kCrPlane) = raw[j];
           }
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
-            float f8[8], r8[8];
+            uint4 a = raw[j];
+            if (BF16) {
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&a);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float raw = inside ? v[j * 8 + e] : 0.f;
-              r8[e] = raw;
-              f8[e] = fmaxf(raw, 0.f);
+              for (int e = 0; e < 4; ++e) h[e] = __hmax2(h[e], __float2bfloat162_rn(0.f));
+            } else {
+              __half2* h = reinterpret_cast<__half2*>(&a);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __hmax2(h[e], __float2half2_rn(0.f));
             }
-            *reinterpret_cast<uint4*>(orow + j * kCrPlane) = pack8(f8, BF16);
-            if (L == 1) *reinterpret_cast<uint4*>(rrow + j * kCrPlane) = pack8(r8, BF16);
+            *reinterpret_cast<uint4*>(orow + j * kCrPlane) = a;
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            mbar_arrive(&out_full[slot]);
-            if (L == 1) mbar_arrive(&rx1_full[g % kCrResSlots]);
+            mbar_arrive(&out_full[oslot]);
+            if (L == 1) mbar_arrive(&rx1_full[rslot]);
           }
+          if (++oslot == kCrMidSlots) { oslot = 0; ophase ^= 1u; }
+          if (L == 1 && ++rslot == kCrResSlots) { rslot = 0; rphase ^= 1u; }
           if (trace) tr[g * 8 + 4] = clock64();
         } else if (emit) {
           // tail + blend (MultiScalePrediction.py:45-52,73-77)
           float s = p.fl[288];
 #pragma unroll
-          for (int c = 0; c < kCrC; ++c) s = fmaf(v[c], p.fl[264 + c], s);
+          for (int c = 0; c < kCrC; ++c) s = fmaf(__uint_as_float(vr[c]), p.fl[264 + c], s);
           const float a = fmaxf(s, 0.f);
           const float wgt = 1.f / (1.f + __expf(-a));
           float* op = p.out + ((static_cast<size_t>(sg.n) * p.H + t) * W + x) * p.out_cs + p.out_co;

@@ -199,12 +199,13 @@ int dd_compose_tail_fwd(dd_ctx* ctx, const dd_tensor* t, const float* w, const f
  * out = large - w*up2(down2(large)) + w*up2(small), optionally followed by the inverse standardisation.
  * Intermediates stay in shared memory / TMEM (16-bit between layers, fp32 accumulate; head / tail / blend in fp32).
  * packed_dev:  DEVICE blob of dd_compose_weights_bytes() bytes, 16-byte aligned, built by dd_compose_pack_weights (host) from
- *              the TF kernels [3,3,24,24] of the four convolutions in graph order; dtype DD_F16 / DD_BF16 = operand type.
+ *              the TF kernels [3,3,24,24] and biases [24] of the four convolutions in graph order (the biases and the residual
+ *              connections are folded into the tensor-core operands); dtype DD_F16 / DD_BF16 = operand type.
  * params_host: HOST fp32 [dd_compose_params_floats()] = head_w[6][24], head_b[24], conv_b[4][24], tail_w[24], tail_b[1], pad
  *              (copied into the launch parameters). */
 size_t dd_compose_weights_bytes(void);
 size_t dd_compose_params_floats(void);
-int dd_compose_pack_weights(const float* const* conv_w, int dtype, void* blob_host);
+int dd_compose_pack_weights(const float* const* conv_w, const float* const* conv_b, int dtype, void* blob_host);
 int dd_compose_scales_fwd(dd_ctx* ctx, const dd_tensor* small, const dd_tensor* large, const void* packed_dev,
                           const float* params_host, int dtype, const dd_invert_params* inv, const dd_tensor* out, void* stream);
 /* FeatureStandardization.invert_standardization on an fp32 image (Architecture.py:48-55). */
