@@ -203,6 +203,7 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
   p.ring = 512 / p.cpad; if (p.ring > kRowsMaxRing) p.ring = kRowsMaxRing;
   p.max_stack = 256 / p.cpad;
   DD_CHECK_ARG(p.ring >= n_r + 1 || n_r == 1, "accumulator ring too small (cpad %d)", p.cpad);
+  DD_CHECK_ARG(n_r <= 2 * p.max_stack, "taps of a row need more than two UMMA pieces (cpad %d)", p.cpad);
 
   // shared memory plan
   const uint32_t a_box_w = k3 ? kRowsTileW + 2 : kRowsTileW;
@@ -259,6 +260,7 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
   p.bf16 = (x->dtype == DD_BF16);
   p.bias = L.bias; p.bias_count = L.bias_count;
   p.trace = ctx->conv_trace;
+  p.dbg = ctx->conv_dbg;
   if (L.residual) {
     DD_CHECK_ARG(L.ups == 1 && L.ngroups == 1, "residual needs a plain convolution");
     DD_CHECK_ARG(L.residual->dtype == x->dtype && L.residual->coff % 8 == 0 && L.residual->cstride % 8 == 0 &&
@@ -319,6 +321,8 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
                             L.ups == 2 ? (L.sp0 & 1) : 0);
     if (rc) return rc;
   }
+
+  p.epi_plain = (!p.out_f32 && !p.residual && !p.has_relu_copy && !p.split_out) ? 1 : 0;
 
   int grid = ctx->sm_count;
   if (p.total_rows < grid) grid = static_cast<int>(p.total_rows);
@@ -414,6 +418,7 @@ int dd_ctx_set_option(dd_ctx* ctx, const char* name, int value) {
   DD_CHECK_ARG(ctx && name, "NULL argument");
   if (!strcmp(name, "conv_rows")) { ctx->conv_rows = value; return DD_OK; }               // cap on G (rows per weight pass)
   if (!strcmp(name, "conv_b_stages")) { ctx->conv_b_stages = value; return DD_OK; }       // weight stages when streaming (0 = auto)
+  if (!strcmp(name, "conv_dbg")) { ctx->conv_dbg = value; return DD_OK; }                 // ablation switches (wrong results)
   if (!strcmp(name, "conv_force_stream")) { ctx->conv_force_stream = value; return DD_OK; } // never keep weights resident
   set_error("unknown option '%s'", name);
   return DD_ERR_INVALID;

@@ -83,6 +83,11 @@ struct ConvRowsParams {
   int res_cstride, res_coff;
   int res_is_mask;        // the residual tensor is a ReLU mask source (DD_CONV_RESIDUAL_MASK) instead of an addend
   unsigned long long* trace;
+  // ablation switches of tools/ablate_conv.py (results are WRONG with any of them set): 1 epilogue skips convert / stage /
+  // store, 2 epilogue skips the TMEM load too, 4 no UMMAs are issued, 8 every A load fetches input row 0 of image 0 (L2 hits),
+  // 16 only the first k-step of every (chunk, shift) is issued
+  int dbg;
+  int epi_plain;          // one 16-bit output, optional ReLU, no residual / mask / relu copy / split output: the compact epilogue
 };
 
 // ---------------------------------------------------------------- extra PTX (bulk tensor store, x32 TMEM load)
@@ -162,6 +167,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
     for (int i = 0; i < p.a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < kRowsMaxRing; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    tmem_slot[1] = 0u;                   // barrier watcher's progress counter
     fence_mbar_init();
   }
   if (warp == kRowsWarpTmem) {
@@ -178,25 +184,41 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
 
   const int t_lo_off = p.rm_lo - 1;   // first input row of a segment = y0 + t_lo_off
   const int t_hi_off = p.rm_hi - 2;   // last input row           = y1 + t_hi_off
+  const uint32_t ready_addr = smem_u32(tmem_slot + 1);
 
   if (warp == kRowsWarpA) {
     // ------------------------------------------------------------------ A producer: one input row x one 64ch chunk per item
+    // (every parameter pinned in a register, see pin() in dd_ptx.cuh: this loop has to stay well ahead of the UMMA issuer)
     if (elect_one()) {
+      const uint32_t scr = smem_u32(tmem_slot + 2 + warp);
+      const int group_rows = pin(p.G, scr), n_chunks = pin(p.n_chunks, scr), nb = pin(p.nb, scr), a_slots = pin(p.a_slots, scr),
+                halo = pin(p.halo, scr), fixed_row = pin(p.dbg & 8, scr);
+      const uint32_t a_tx_bytes = pin(p.a_tx_bytes, scr), a_slot_bytes = pin(p.a_slot_bytes, scr);
+      const uint32_t a_dst0 = pin(smem_u32(a_smem), scr), bar_full = pin(smem_u32(a_full), scr), bar_empty = pin(smem_u32(a_empty), scr);
+      const int t_lo = pin(t_lo_off, scr), t_hi = pin(t_hi_off, scr);
+      unsigned long long* const trace = (blockIdx.x == 0) ? pin(p.trace, scr) : nullptr;
+      int item = 0;
       RowsWalker walk(p);
       RowsSegment sg;
       int slot = 0; uint32_t phase = 0;
       while (walk.next(sg)) {
-        const int t_first = sg.y0 + t_lo_off, t_last = sg.y1 + t_hi_off;
-        for (int tg = t_first; tg <= t_last; tg += p.G) {
-          const int gcur = (t_last + 1 - tg < p.G) ? (t_last + 1 - tg) : p.G;
-          for (int c = 0; c < p.n_chunks; ++c) {
+        const int t_first = sg.y0 + t_lo, t_last = sg.y1 + t_hi;
+        const int x0 = sg.x0 - halo, img = fixed_row ? 0 : sg.n;
+        for (int tg = t_first; tg <= t_last; tg += group_rows) {
+          const int gcur = (t_last + 1 - tg < group_rows) ? (t_last + 1 - tg) : group_rows;
+          for (int c = 0; c < n_chunks; ++c) {
+            const int part = SPLIT ? c / nb : 0;
+            const CUtensorMap* map = (SPLIT && part == 1) ? &maps.a_lo : &maps.a;
+            const int c0 = (c - part * nb) * 64;
             for (int g = 0; g < gcur; ++g) {
-              mbar_wait(&a_empty[slot], phase ^ 1);
-              mbar_arrive_expect_tx(&a_full[slot], p.a_tx_bytes);
-              const int part = SPLIT ? c / p.nb : 0;
-              tma_load_4d(a_smem + static_cast<size_t>(slot) * p.a_slot_bytes, (SPLIT && part == 1) ? &maps.a_lo : &maps.a,
-                          &a_full[slot], (c - part * p.nb) * 64, sg.x0 - p.halo, tg + g, sg.n);
-              if (++slot == p.a_slots) { slot = 0; phase ^= 1; }
+              mbar_wait_addr(bar_empty + 8u * slot, phase ^ 1);
+              if (trace && item < 64) trace[896 + item] = clock64();
+              mbar_arrive_expect_tx_addr(bar_full + 8u * slot, a_tx_bytes);
+              tma_load_4d_addr(a_dst0 + static_cast<uint32_t>(slot) * a_slot_bytes, map, bar_full + 8u * slot, c0, x0,
+                               fixed_row ? 0 : tg + g, img);
+              if (trace && item < 64) trace[960 + item] = clock64();
+              ++item;
+              if (++slot == a_slots) { slot = 0; phase ^= 1; }
             }
           }
         }
@@ -212,282 +234,398 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
           tma_load_4d(b_smem + static_cast<size_t>(i) * p.b_tile_bytes, &maps.b, &b_full[0], 0, p.b_row0, p.b_r0,
                       (i / p.n_s) * p.tiles_per_chunk + p.s_list[i % p.n_s]);
       } else {
+        const uint32_t scr = smem_u32(tmem_slot + 2 + warp);
+        const int group_rows = pin(p.G, scr), n_chunks = pin(p.n_chunks, scr), nb = pin(p.nb, scr), n_s = pin(p.n_s, scr),
+                  b_stages = pin(p.b_stages, scr), b_row0 = pin(p.b_row0, scr), b_r0 = pin(p.b_r0, scr),
+                  tiles_per_chunk = pin(p.tiles_per_chunk, scr), s0 = pin(p.s_list[0], scr), s1 = pin(p.s_list[1], scr),
+                  s2 = pin(p.s_list[2], scr);
+        const uint32_t b_tx_bytes = pin(p.b_tx_bytes, scr), b_tile_bytes = pin(p.b_tile_bytes, scr);
+        const uint32_t b_dst0 = pin(smem_u32(b_smem), scr), bar_full = pin(smem_u32(b_full), scr), bar_empty = pin(smem_u32(b_empty), scr);
+        const int t_lo = pin(t_lo_off, scr), t_hi = pin(t_hi_off, scr);
         RowsWalker walk(p);
         RowsSegment sg;
         int stage = 0; uint32_t phase = 0;
         while (walk.next(sg)) {
-          const int t_first = sg.y0 + t_lo_off, t_last = sg.y1 + t_hi_off;
-          for (int tg = t_first; tg <= t_last; tg += p.G) {
-            for (int c = 0; c < p.n_chunks; ++c) {
-              for (int si = 0; si < p.n_s; ++si) {
-                mbar_wait(&b_empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&b_full[stage], p.b_tx_bytes);
-                const int bc = (SPLIT && c >= p.nb) ? c - p.nb : c;                        // weight chunk of A chunk c
-                tma_load_4d(b_smem + static_cast<size_t>(stage) * p.b_tile_bytes, &maps.b, &b_full[stage], 0, p.b_row0,
-                            p.b_r0, bc * p.tiles_per_chunk + p.s_list[si]);
-                if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+          const int t_first = sg.y0 + t_lo, t_last = sg.y1 + t_hi;
+          for (int tg = t_first; tg <= t_last; tg += group_rows) {
+            for (int c = 0; c < n_chunks; ++c) {
+              const int bc = (SPLIT && c >= nb) ? c - nb : c;                          // weight chunk of A chunk c
+              for (int si = 0; si < n_s; ++si) {
+                mbar_wait_addr(bar_empty + 8u * stage, phase ^ 1);
+                mbar_arrive_expect_tx_addr(bar_full + 8u * stage, b_tx_bytes);
+                tma_load_4d_addr(b_dst0 + static_cast<uint32_t>(stage) * b_tile_bytes, &maps.b, bar_full + 8u * stage, 0, b_row0,
+                                 b_r0, bc * tiles_per_chunk + (si == 0 ? s0 : (si == 1 ? s1 : s2)));
+                if (++stage == b_stages) { stage = 0; phase ^= 1; }
               }
             }
           }
         }
       }
     }
-  } else if (warp == kRowsWarpMma) {
-    // ------------------------------------------------------------------ MMA issuer (highest warp id: the scheduler
-    // prefers it over the epilogue warp sharing its sub-partition)
+  } else if (warp == kRowsWarpTmem) {
+    // ------------------------------------------------------------------ barrier watcher
+    // Polling an mbarrier costs the polling thread ~200-250 cycles even when the phase has long completed (measured, round 2,
+    // tools/trace_conv.py: "wait a_full" 260 + "wait acc_empty" 210 cycles per row with no UMMA and no epilogue in flight), and
+    // the tensor pipe queues only one or two UMMAs behind the one in flight - every cycle the issuing thread spends in a wait is
+    // an idle cycle of the pipe.  So this otherwise idle thread does the polling: it walks the barrier waits of the issuing
+    // thread in exactly the issuing thread's order and publishes how many have completed in a shared-memory counter; the
+    // issuing thread compares a cached copy and re-reads the counter (one ~30-cycle shared-memory load) only when it runs dry.
     if (elect_one()) {
-      // Single issuing thread: scalar integer code on the critical path of the tensor pipe (one UMMA of N = 192
-      // lasts 96 cycles), so the row loop avoids divisions, parameter loads and recomputation: the UMMA "pieces"
-      // a row breaks into (ring wrap / N <= 256 / first touch of an output row) are tabulated once per block index.
-      //   piece = {TMEM column, instruction descriptor, B offset >> 4, accumulate};  row plan = hdr + 3 normal + 4 first-touch
-      const uint64_t desc_tmpl = make_desc_sw128(0, 0);
-      const uint32_t d_lo = static_cast<uint32_t>(desc_tmpl), d_hi = static_cast<uint32_t>(desc_tmpl >> 32);
-      const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
-      uint4* plan = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [8 rows of a group][8]
-      uint4* table = plan + 64;                                                         // [ring blocks][8], full tap range
-      const int ring = p.ring, rm_lo = p.rm_lo, rm_hi = p.rm_hi, n_s = p.n_s, n_chunks = p.n_chunks, a_slots = p.a_slots;
-      const uint32_t a_slot_bytes = p.a_slot_bytes, b_tile_bytes = p.b_tile_bytes;
-      const uint32_t s_off0 = static_cast<uint32_t>(p.s_list[0]) * 8u, s_off1 = static_cast<uint32_t>(p.s_list[1]) * 8u,
-                     s_off2 = static_cast<uint32_t>(p.s_list[2]) * 8u;                   // shifts in descriptor units
-
-      const uint32_t fmt = p.bf16 ? kIdescBf16 : 0u;
-      auto build_plan = [&](uint4* row_plan, int blk, uint32_t use, int r_lo, int r_hi) {
-        const bool ft = (r_lo == rm_lo);   // this input row initialises the accumulator of the row served by tap r_lo
-        int n_norm = 0, n_first = 0;
-        int r = r_lo, bk = blk;
-        while (r <= r_hi) {
-          int cnt = r_hi - r + 1;
-          if (bk + cnt > ring) cnt = ring - bk;
-          if (cnt > p.max_stack) cnt = p.max_stack;
-          row_plan[1 + n_norm++] = make_uint4(static_cast<uint32_t>(bk * p.cpad), make_idesc_f16(kRowsTileW, cnt * p.cpad) | fmt,
-                                              static_cast<uint32_t>((r - rm_lo) * p.cpad) * 8u, 1u);
-          r += cnt; bk += cnt; if (bk >= ring) bk -= ring;
-        }
-        if (ft) {
-          row_plan[4 + n_first++] = make_uint4(static_cast<uint32_t>(blk * p.cpad), make_idesc_f16(kRowsTileW, p.cpad) | fmt,
-                                               static_cast<uint32_t>((r_lo - rm_lo) * p.cpad) * 8u, 0u);
-          r = r_lo + 1; bk = blk + 1; if (bk >= ring) bk -= ring;
-          while (r <= r_hi) {
-            int cnt = r_hi - r + 1;
-            if (bk + cnt > ring) cnt = ring - bk;
-            if (cnt > p.max_stack) cnt = p.max_stack;
-            row_plan[4 + n_first++] = make_uint4(static_cast<uint32_t>(bk * p.cpad), make_idesc_f16(kRowsTileW, cnt * p.cpad) | fmt,
-                                                 static_cast<uint32_t>((r - rm_lo) * p.cpad) * 8u, 1u);
-            r += cnt; bk += cnt; if (bk >= ring) bk -= ring;
-          }
-        }
-        row_plan[0] = make_uint4(static_cast<uint32_t>(n_norm), static_cast<uint32_t>(n_first), static_cast<uint32_t>(blk),
-                                 (use & 1u) ^ 1u);
-      };
-      // issues the UMMAs of one (input row, chunk, shift): k-steps x pieces, operands already resident
-      auto issue = [&](const uint4& hdr, const uint4 (&pn)[3], const uint4 (&pf)[4], bool first_pass, uint32_t a_lo,
-                       uint32_t b_lo0, int ksteps) {
-        int k0 = 0;
-        if (first_pass) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < static_cast<int>(hdr.y))
-              umma_f16(tmem_base + pf[i].x, desc_from(a_lo, d_hi), desc_from(b_lo0 + pf[i].z, d_hi), pf[i].y, pf[i].w);
-          k0 = 1;
-        }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          if (i < static_cast<int>(hdr.x)) {
-            const uint32_t b_lo = b_lo0 + pn[i].z;
-            const uint32_t d_col = tmem_base + pn[i].x;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k >= k0 && k < ksteps)
-                umma_f16(d_col, desc_from(a_lo + 2u * k, d_hi), desc_from(b_lo + 2u * k, d_hi), pn[i].y, 1u);
-          }
-        }
-      };
-
-      for (int bk = 0; bk < ring; ++bk) build_plan(table + bk * 8, bk, 0u, rm_lo, rm_hi);
+      const uint32_t scr = smem_u32(tmem_slot + 2 + warp);
+      const int ring = pin(p.ring, scr), rm_lo = pin(p.rm_lo, scr), n_s = pin(p.n_s, scr), n_chunks = pin(p.n_chunks, scr),
+                a_slots = pin(p.a_slots, scr), b_stages = pin(p.b_stages, scr), group_rows = pin(p.G, scr);
+      const bool w_resident = pin(p.w_resident, scr) != 0;
+      const int t_lo = pin(t_lo_off, scr), t_hi = pin(t_hi_off, scr);
+      const uint32_t ready = pin(ready_addr, scr);
+      const uint32_t bar_a_full = pin(smem_u32(a_full), scr), bar_b_full = pin(smem_u32(b_full), scr),
+                     bar_acc_empty = pin(smem_u32(acc_empty), scr);
+      unsigned long long* const trace = (blockIdx.x == 0) ? pin(p.trace, scr) : nullptr;
+      int item = 0;
+      uint32_t count = 0;
+      auto publish = [&]() { st_release_shared(ready, ++count); };
       RowsWalker walk(p);
       RowsSegment sg;
       int a_slot = 0; uint32_t a_phase = 0;
       int b_stage = 0; uint32_t b_phase = 0;
-      uint32_t q_seg = 0;                  // running index of the first output row of the segment
-      int it = 0;
-      if (p.w_resident) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
+      uint32_t q_seg = 0;
+      if (w_resident) { mbar_wait_addr(bar_b_full, 0u); publish(); }
       while (walk.next(sg)) {
-        const int t_first = sg.y0 + t_lo_off, t_last = sg.y1 + t_hi_off;
-        // accumulator block / use count of the output row fed by tap r = 0 of input row t (index q_seg + t + 1 - y0);
-        // tap r lands r blocks further.  Maintained incrementally (one division per segment).
+        const int t_first = sg.y0 + t_lo, t_last = sg.y1 + t_hi;
         const uint32_t q_top0 = q_seg + static_cast<uint32_t>(t_first + 1 - sg.y0);
         int blk_top = ring - 1 - static_cast<int>(q_top0 % static_cast<uint32_t>(ring));
         uint32_t use_top = q_top0 / static_cast<uint32_t>(ring);
-        if (p.G == 1) {
-          // ---------------- one input row at a time (weights resident, or a single-row weight pass)
-          // The barrier probes of row t+1 (its first A slot, the accumulator block it initialises) are issued right
-          // after the waits of row t: their ~100-200 cycle latency then overlaps the UMMAs of row t instead of idling
-          // the tensor pipe between rows; a failed probe falls back to the blocking wait.
-          bool probed = false, probe_a = false, probe_e = false;
-          for (int t = t_first; t <= t_last; ++t, ++it) {
-            const bool tr = p.trace && blockIdx.x == 0 && it < 64;
-            if (tr) p.trace[it * 8 + 0] = clock64();
-            int r_lo = t + 2 - sg.y1; if (r_lo < rm_lo) r_lo = rm_lo;     // taps landing on rows of the segment
-            int r_hi = t + 1 - sg.y0; if (r_hi > rm_hi) r_hi = rm_hi;
-            int blk = blk_top + r_lo; uint32_t use = use_top;
-            if (blk >= ring) { blk -= ring; use -= 1u; }                  // block / use of the row served by tap r_lo
-            const uint4* row_plan;
-            if (r_lo == rm_lo && r_hi == rm_hi) {
-              row_plan = table + blk * 8;
-            } else {
-              build_plan(plan, blk, use, r_lo, r_hi);
-              row_plan = plan;
+        // block / wait parity of the output row an input row initialises (the first clauses of make_plan below)
+        auto init_block = [&](int t, int bt, uint32_t ut, int& blk, uint32_t& par) {
+          int r_lo = t + 2 - sg.y1; if (r_lo < rm_lo) r_lo = rm_lo;
+          blk = bt + r_lo; uint32_t use = ut;
+          if (blk >= ring) { blk -= ring; use -= 1u; }
+          par = (use & 1u) ^ 1u;
+          return r_lo == rm_lo;
+        };
+        if (group_rows == 1) {
+          for (int t = t_first; t <= t_last; ++t) {
+            int blk; uint32_t par;
+            const bool init = init_block(t, blk_top, use_top, blk, par);
+            for (int c = 0; c < n_chunks; ++c) {
+              mbar_wait_addr(bar_a_full + 8u * a_slot, a_phase); publish();
+              if (trace && item < 64) trace[768 + item] = clock64();
+              if (c == 0 && init) { mbar_wait_addr(bar_acc_empty + 8u * blk, par); publish(); }
+              if (trace && item < 64) trace[832 + item] = clock64();
+              ++item;
+              if (++a_slot == a_slots) { a_slot = 0; a_phase ^= 1; }
+              if (!w_resident) {
+                for (int si = 0; si < n_s; ++si) {
+                  mbar_wait_addr(bar_b_full + 8u * b_stage, b_phase); publish();
+                  if (++b_stage == b_stages) { b_stage = 0; b_phase ^= 1; }
+                }
+              }
             }
-            const uint4 hdr = row_plan[0];
-            uint4 pn[3], pf[4];
+            if (--blk_top < 0) { blk_top = ring - 1; ++use_top; }
+          }
+        } else {
+          for (int tg = t_first; tg <= t_last; tg += group_rows) {
+            const int gcur = (t_last + 1 - tg < group_rows) ? (t_last + 1 - tg) : group_rows;
+            const int a_slot0 = a_slot; const uint32_t a_phase0 = a_phase;
+            for (int c = 0; c < n_chunks; ++c) {
+              for (int si = 0; si < n_s; ++si) {
+                mbar_wait_addr(bar_b_full + 8u * b_stage, b_phase); publish();
+                if (++b_stage == b_stages) { b_stage = 0; b_phase ^= 1; }
+                if (si == 0) {
+                  int lin_slot = a_slot0 + c * gcur; uint32_t ph = a_phase0;
+                  while (lin_slot >= a_slots) { lin_slot -= a_slots; ph ^= 1; }
+                  int bt = blk_top; uint32_t ut = use_top;
+                  for (int g = 0; g < gcur; ++g) {
+                    mbar_wait_addr(bar_a_full + 8u * lin_slot, ph); publish();
+                    if (c == 0) {
+                      int blk; uint32_t par;
+                      if (init_block(tg + g, bt, ut, blk, par)) { mbar_wait_addr(bar_acc_empty + 8u * blk, par); publish(); }
+                      if (--bt < 0) { bt = ring - 1; ++ut; }
+                    }
+                    if (++lin_slot == a_slots) { lin_slot = 0; ph ^= 1; }
+                  }
+                }
+              }
+            }
+            a_slot = a_slot0 + n_chunks * gcur; a_phase = a_phase0;
+            while (a_slot >= a_slots) { a_slot -= a_slots; a_phase ^= 1; }
+            for (int g = 0; g < gcur; ++g) { if (--blk_top < 0) { blk_top = ring - 1; ++use_top; } }
+          }
+        }
+        q_seg += static_cast<uint32_t>(sg.y1 - sg.y0);
+      }
+    }
+  } else if (warp == kRowsWarpMma) {
+    // ------------------------------------------------------------------ MMA issuer (highest warp id: the scheduler
+    // prefers it over the epilogue warp sharing its sub-partition)
+    if (elect_one()) {
+      // ONE thread issues every UMMA of the CTA, and its scalar instruction stream is the critical path of the kernel: a
+      // lone thread retires a dependent instruction every ~4-10 cycles, the tensor pipe queues only one or two UMMAs, and an
+      // N = 192 UMMA lasts 96 cycles.  Measured (round 2, tools/ablate_conv.py): with the table-driven generic issue loop of
+      // round 1 a 64->64 row took ~3000 cycles whether 12, 3 or 0 of its UMMAs were issued (tensor work: 1152).  Hence:
+      //  * the row's UMMA list is reduced to what the ring geometry allows - the taps of a row cover consecutive accumulator
+      //    blocks that wrap around the ring at most once, and N <= 256 splits at most once, i.e. every (row, chunk, shift,
+      //    k-step) is piece A [+ piece B] - derived with a dozen branch-free integer instructions per row and issued as
+      //    predicated straight-line code: no plan tables, no shared-memory loads, no loops over pieces;
+      //  * no mbarrier polling here (see the barrier watcher above): `await` is a register compare, rarely a shared load;
+      //  * the plan of the next row is computed behind the first UMMAs of this row.
+      // every parameter the loops below touch is pinned in a register (see pin() in dd_ptx.cuh)
+      const uint32_t scr = smem_u32(tmem_slot + 2 + warp);
+      const uint64_t desc_tmpl = make_desc_sw128(0, 0);
+      const uint32_t d_lo = static_cast<uint32_t>(desc_tmpl), d_hi = static_cast<uint32_t>(desc_tmpl >> 32);
+      const uint32_t a_desc0 = pin(d_lo + (smem_u32(a_smem) >> 4), scr), b_desc0 = pin(d_lo + (smem_u32(b_smem) >> 4), scr);
+      const uint32_t a_slot_units = pin(p.a_slot_bytes >> 4, scr), b_tile_units = pin(p.b_tile_bytes >> 4, scr);
+      const int ring = pin(p.ring, scr), rm_lo = pin(p.rm_lo, scr), rm_hi = pin(p.rm_hi, scr), n_s = pin(p.n_s, scr), n_chunks = pin(p.n_chunks, scr),
+                a_slots = pin(p.a_slots, scr), max_stack = pin(p.max_stack, scr), b_stages = pin(p.b_stages, scr), nb = pin(p.nb, scr),
+                ksteps_last = pin(p.ksteps_last, scr), dbg = pin(p.dbg, scr), group_rows = pin(p.G, scr);
+      const bool w_resident = pin(p.w_resident, scr) != 0;
+      const uint32_t cpad = pin(static_cast<uint32_t>(p.cpad), scr);
+      const uint32_t idesc0 = pin(make_idesc_f16(kRowsTileW, 0) | (p.bf16 ? kIdescBf16 : 0u), scr);
+      const uint32_t istep = pin((cpad >> 3) << 17, scr);  // one more stacked tap in the N field of the instruction descriptor
+      const uint32_t bstep = pin(cpad * 8u, scr);          // one tap further in the weight tile (descriptor units of 16 B, 128 B rows)
+      const uint32_t s_off0 = pin(static_cast<uint32_t>(p.s_list[0]) * 8u, scr), s_off1 = pin(static_cast<uint32_t>(p.s_list[1]) * 8u, scr),
+                     s_off2 = pin(static_cast<uint32_t>(p.s_list[2]) * 8u, scr);              // shifts in descriptor units
+      const uint32_t bar_a_empty = pin(smem_u32(a_empty), scr), bar_b_empty = pin(smem_u32(b_empty), scr),
+                     bar_acc_full = pin(smem_u32(acc_full), scr), ready = pin(ready_addr, scr);
+      const int t_lo = pin(t_lo_off, scr), t_hi = pin(t_hi_off, scr);
+      unsigned long long* const trace = (blockIdx.x == 0) ? pin(p.trace, scr) : nullptr;
+      uint4* plan = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(bars) + 512);   // streamed path: [8 rows of a group][2]
+
+      uint32_t needed = 0, seen = 0;       // barrier waits consumed / known complete (watcher's counter)
+      auto await = [&]() {
+        ++needed;
+        while (static_cast<int32_t>(seen - needed) < 0) seen = ld_acquire_shared(ready);
+      };
+
+      struct RowPlan {
+        uint32_t dA, iA, bA;   // piece A: TMEM address, instruction descriptor, offset of its first tap in the weight tile
+        uint32_t dB, iB, bB;   // piece B (iB == 0: none): the taps behind the ring wrap / beyond N = 256
+        uint32_t iR;           // first touch: piece A minus its first tap (0: piece A is a single tap)
+        bool init;             // this input row is the first contribution to the output row served by its lowest tap
+      };
+      auto plan_taps = [&](int r_lo, int r_hi, int blk, RowPlan& pl) {      // taps r_lo..r_hi, tap r_lo on block blk
+        const int n = r_hi - r_lo + 1;
+        int cnt_a = ring - blk; if (cnt_a > n) cnt_a = n; if (cnt_a > max_stack) cnt_a = max_stack;
+        const int cnt_b = n - cnt_a;
+        int blk_b = blk + cnt_a; if (blk_b >= ring) blk_b -= ring;
+        pl.dA = tmem_base + static_cast<uint32_t>(blk) * cpad;
+        pl.iA = idesc0 + static_cast<uint32_t>(cnt_a) * istep;
+        pl.bA = static_cast<uint32_t>(r_lo - rm_lo) * bstep;
+        pl.dB = tmem_base + static_cast<uint32_t>(blk_b) * cpad;
+        pl.iB = cnt_b ? idesc0 + static_cast<uint32_t>(cnt_b) * istep : 0u;
+        pl.bB = pl.bA + static_cast<uint32_t>(cnt_a) * bstep;
+        pl.iR = cnt_a > 1 ? idesc0 + static_cast<uint32_t>(cnt_a - 1) * istep : 0u;
+        pl.init = (r_lo == rm_lo);
+      };
+      // Interior rows (all taps inside the segment) have one plan per accumulator block index: tabulated once, two 16-byte
+      // shared-memory loads per row; only the first / last input rows of a segment are computed on the spot.
+      uint4* table = plan + 16;                                                         // [ring][2]
+      for (int bk = 0; bk < ring; ++bk) {
+        RowPlan pl;
+        plan_taps(rm_lo, rm_hi, bk, pl);
+        table[2 * bk] = make_uint4(pl.dA, pl.iA, pl.bA, pl.dB);
+        table[2 * bk + 1] = make_uint4(pl.iB, pl.bB, pl.iR, 1u);
+      }
+      auto make_plan = [&](int t, const RowsSegment& sg, int bt, RowPlan& pl) {
+        int r_lo = t + 2 - sg.y1; if (r_lo < rm_lo) r_lo = rm_lo;     // taps landing on rows of the segment
+        int r_hi = t + 1 - sg.y0; if (r_hi > rm_hi) r_hi = rm_hi;
+        int blk = bt + r_lo;
+        if (blk >= ring) blk -= ring;                                 // block of the row served by tap r_lo
+        if (r_lo == rm_lo && r_hi == rm_hi) {
+          const uint4 q0 = table[2 * blk], q1 = table[2 * blk + 1];
+          pl.dA = q0.x; pl.iA = q0.y; pl.bA = q0.z; pl.dB = q0.w; pl.iB = q1.x; pl.bB = q1.y; pl.iR = q1.z; pl.init = true;
+        } else {
+          plan_taps(r_lo, r_hi, blk, pl);
+        }
+      };
+      // the UMMAs of one (input row, chunk, shift): k-steps x pieces, operands resident; predicated, branch free
+      auto issue_shift = [&](const RowPlan& pl, bool first, uint32_t a_lo, uint32_t b_lo, int ksteps) {
+        if (dbg & 20) { if (dbg & 4) return; ksteps = 1; }
+        const uint32_t b_a = b_lo + pl.bA, b_b = b_lo + pl.bB;
+        // first touch of an output row: its own block with accumulate = 0, then the rest of piece A
+        umma_f16(pl.dA, desc_from(a_lo, d_hi), desc_from(b_a, d_hi), first ? idesc0 + istep : pl.iA, first ? 0u : 1u);
+        if (first && pl.iR) umma_f16(pl.dA + cpad, desc_from(a_lo, d_hi), desc_from(b_a + bstep, d_hi), pl.iR, 1u);
+        if (pl.iB) umma_f16(pl.dB, desc_from(a_lo, d_hi), desc_from(b_b, d_hi), pl.iB, 1u);
+        if (ksteps == 4) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i) pn[i] = row_plan[1 + i];
+          for (int k = 1; k < 4; ++k) {
+            umma_f16(pl.dA, desc_from(a_lo + 2u * k, d_hi), desc_from(b_a + 2u * k, d_hi), pl.iA, 1u);
+            if (pl.iB) umma_f16(pl.dB, desc_from(a_lo + 2u * k, d_hi), desc_from(b_b + 2u * k, d_hi), pl.iB, 1u);
+          }
+        } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) pf[i] = row_plan[4 + i];
-            const bool initialises = (r_lo == rm_lo);
-            if (tr) p.trace[it * 8 + 1] = clock64();                                      // plan in registers
+          for (int k = 1; k < 3; ++k) {
+            if (k < ksteps) {
+              umma_f16(pl.dA, desc_from(a_lo + 2u * k, d_hi), desc_from(b_a + 2u * k, d_hi), pl.iA, 1u);
+              if (pl.iB) umma_f16(pl.dB, desc_from(a_lo + 2u * k, d_hi), desc_from(b_b + 2u * k, d_hi), pl.iB, 1u);
+            }
+          }
+        }
+      };
+
+      RowsWalker walk(p);
+      RowsSegment sg;
+      int a_slot = 0;
+      int b_stage = 0;
+      uint32_t q_seg = 0;                  // running index of the first output row of the segment
+      int it = 0;
+      if (w_resident) { await(); tc_fence_after(); }
+      while (walk.next(sg)) {
+        const int t_first = sg.y0 + t_lo, t_last = sg.y1 + t_hi;
+        // accumulator block of the output row fed by tap r = 0 of input row t (running index q_seg + t + 1 - y0); tap r lands
+        // r blocks further.  Maintained incrementally (one division per segment).
+        const uint32_t q_top0 = q_seg + static_cast<uint32_t>(t_first + 1 - sg.y0);
+        int blk_top = ring - 1 - static_cast<int>(q_top0 % static_cast<uint32_t>(ring));
+        if (group_rows == 1) {
+          // ---------------- one input row at a time (weights resident, or a single-row weight pass)
+          RowPlan pl;
+          make_plan(t_first, sg, blk_top, pl);
+          for (int t = t_first; t <= t_last; ++t, ++it) {
+            const bool tr = trace && it < 64;
+            if (tr) trace[it * 8 + 0] = clock64();
+            RowPlan nxt = pl;
+            if (tr && (dbg & 256) && it == 8) {
+              // in-situ latency probe of the issuing thread (tools/trace_conv.py probe): dependent integer chain, parameter
+              // (constant bank) loads, shared-memory loads, back-to-back clock reads
+              unsigned long long c0 = clock64();
+              uint32_t x;
+              asm volatile("mov.u32 %0, %1;" : "=r"(x) : "r"(it));
+#pragma unroll
+              for (int i = 0; i < 32; ++i) x = x * 3u + 1u;
+              asm volatile("mov.u32 %0, %1;" : "=r"(x) : "r"(x));
+              unsigned long long c1 = clock64();
+              const uint32_t* pm = reinterpret_cast<const uint32_t*>(&maps);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x = pm[(x & 255u)] + i;
+              asm volatile("mov.u32 %0, %1;" : "=r"(x) : "r"(x));
+              unsigned long long c2 = clock64();
+              const volatile uint32_t* ps = reinterpret_cast<const volatile uint32_t*>(plan);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x = ps[(x & 63u)] + i;
+              unsigned long long c3 = clock64();
+              unsigned long long c4 = clock64();
+              unsigned long long c5 = clock64();
+              trace[768] = c1 - c0; trace[769] = c2 - c1; trace[770] = c3 - c2; trace[771] = c4 - c3; trace[772] = c5 - c4;
+              trace[773] = x;
+            }
             for (int c = 0; c < n_chunks; ++c) {
               int cc = c;
-              if (SPLIT) { while (cc >= p.nb) cc -= p.nb; }
-              const int ksteps = (cc == p.nb - 1) ? p.ksteps_last : 4;
-              const int bc = (SPLIT && c >= 2 * p.nb) ? c - p.nb : cc;                     // resident weight chunk of A chunk c
-              if (!(c == 0 && probed && probe_a)) mbar_wait(&a_full[a_slot], a_phase);
-              if (c == 0 && initialises && !(probed && probe_e))
-                mbar_wait(&acc_empty[blk], (use & 1u) ^ 1u);                              // previous user drained
-              if (tr && c == 0) p.trace[it * 8 + 7] = clock64() | (static_cast<unsigned long long>((probed && probe_a) ? 1 : 0) << 62) |
-                                                      (static_cast<unsigned long long>((probed && probe_e) ? 1 : 0) << 61);
+              if (SPLIT) { while (cc >= nb) cc -= nb; }
+              const int ksteps = (cc == nb - 1) ? ksteps_last : 4;
+              const int bc = (SPLIT && c >= 2 * nb) ? c - nb : cc;                         // resident weight chunk of A chunk c
+              await();                                                                    // A slot landed
+              if (c == 0 && pl.init) await();                                             // previous user of the new row's block drained
+              if (tr && c == 0) trace[it * 8 + 1] = clock64();
               tc_fence_after();
-              if (tr && c == 0) p.trace[it * 8 + 2] = clock64();
-              if (c == 0) {
-                probed = false;
-                if (t < t_last) {
-                  int nslot = a_slot + n_chunks; uint32_t nphase = a_phase;
-                  while (nslot >= a_slots) { nslot -= a_slots; nphase ^= 1; }
-                  int nr_lo = t + 3 - sg.y1; if (nr_lo < rm_lo) nr_lo = rm_lo;
-                  int nbt = blk_top - 1; uint32_t nut = use_top;
-                  if (nbt < 0) { nbt = ring - 1; ++nut; }
-                  int nblk = nbt + nr_lo;
-                  if (nblk >= ring) { nblk -= ring; nut -= 1u; }
-                  probe_a = mbar_test_wait(&a_full[nslot], nphase);
-                  probe_e = (nr_lo != rm_lo) || mbar_test_wait(&acc_empty[nblk], (nut & 1u) ^ 1u);
-                  probed = true;
+              if (tr && c == 0) trace[it * 8 + 2] = clock64();
+              const uint32_t a_lo = a_desc0 + static_cast<uint32_t>(a_slot) * a_slot_units;
+              uint32_t b_res = b_desc0 + static_cast<uint32_t>(bc * n_s) * b_tile_units;
+#pragma unroll
+              for (int si = 0; si < 3; ++si) {
+                if (si < n_s) {
+                  uint32_t b_lo;
+                  if (w_resident) {
+                    b_lo = b_res; b_res += b_tile_units;
+                  } else {
+                    await();
+                    tc_fence_after();
+                    b_lo = b_desc0 + static_cast<uint32_t>(b_stage) * b_tile_units;
+                  }
+                  const uint32_t s_off = (si == 0) ? s_off0 : ((si == 1) ? s_off1 : s_off2);
+                  issue_shift(pl, si == 0 && c == 0 && pl.init, a_lo + s_off, b_lo, ksteps);
+                  if (!w_resident) {
+                    umma_commit_addr(bar_b_empty + 8u * b_stage);
+                    if (++b_stage == b_stages) b_stage = 0;
+                  }
+                  if (si == 0 && c == 0 && t < t_last) {      // the next row's plan, behind the UMMAs queued so far
+                    int nbt = blk_top - 1; if (nbt < 0) nbt = ring - 1;
+                    make_plan(t + 1, sg, nbt, nxt);
+                  }
                 }
               }
-              const uint32_t a_lo0 = d_lo + ((a_base + static_cast<uint32_t>(a_slot) * a_slot_bytes) >> 4);
-              for (int si = 0; si < n_s; ++si) {
-                uint32_t b_tile;
-                if (p.w_resident) {
-                  b_tile = b_base + static_cast<uint32_t>(bc * n_s + si) * b_tile_bytes;
-                } else {
-                  mbar_wait(&b_full[b_stage], b_phase);
-                  tc_fence_after();
-                  b_tile = b_base + static_cast<uint32_t>(b_stage) * b_tile_bytes;
-                }
-                const uint32_t s_off = (si == 0) ? s_off0 : ((si == 1) ? s_off1 : s_off2);
-                issue(hdr, pn, pf, initialises && c == 0 && si == 0, a_lo0 + s_off, d_lo + (b_tile >> 4), ksteps);
-                if (!p.w_resident) {
-                  umma_commit(&b_empty[b_stage]);
-                  if (++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
-                }
-              }
-              umma_commit(&a_empty[a_slot]);
-              if (++a_slot == a_slots) { a_slot = 0; a_phase ^= 1; }
+              if (tr && c == n_chunks - 1) trace[512 + it] = clock64();
+              umma_commit_addr(bar_a_empty + 8u * a_slot);
+              if (tr && c == n_chunks - 1) trace[576 + it] = clock64();
+              if (++a_slot == a_slots) a_slot = 0;
             }
             // output row completed by this input row: the one served by tap rm_hi, if it belongs to the segment
             {
               const int j = t + 1 - rm_hi;
               if (j >= sg.y0 && j < sg.y1) {
                 int blk_done = blk_top + rm_hi; if (blk_done >= ring) blk_done -= ring;
-                umma_commit(&acc_full[blk_done]);
+                umma_commit_addr(bar_acc_full + 8u * blk_done);
               }
             }
-            if (--blk_top < 0) { blk_top = ring - 1; ++use_top; }
-            if (tr) p.trace[it * 8 + 3] = clock64();
+            if (--blk_top < 0) blk_top = ring - 1;
+            pl = nxt;
+            if (tr) trace[it * 8 + 3] = clock64();
           }
         } else {
           // ---------------- groups of G input rows per weight pass (streamed weights)
-          for (int tg = t_first; tg <= t_last; tg += p.G, ++it) {
-            const int gcur = (t_last + 1 - tg < p.G) ? (t_last + 1 - tg) : p.G;
-            const bool tr = p.trace && blockIdx.x == 0 && it < 64;
-            if (tr) p.trace[it * 8 + 0] = clock64();
+          for (int tg = t_first; tg <= t_last; tg += group_rows, ++it) {
+            const int gcur = (t_last + 1 - tg < group_rows) ? (t_last + 1 - tg) : group_rows;
+            const bool tr = trace && it < 64;
+            if (tr) trace[it * 8 + 0] = clock64();
             {
-              int bt = blk_top; uint32_t ut = use_top;
+              int bt = blk_top;
               for (int g = 0; g < gcur; ++g) {
-                const int t = tg + g;
-                int r_lo = t + 2 - sg.y1; if (r_lo < rm_lo) r_lo = rm_lo;
-                int r_hi = t + 1 - sg.y0; if (r_hi > rm_hi) r_hi = rm_hi;
-                int blk = bt + r_lo; uint32_t use = ut;
-                if (blk >= ring) { blk -= ring; use -= 1u; }
-                if (r_lo == rm_lo && r_hi == rm_hi) {
-                  // interior row: the tabulated plan of this block index, with the wait parity of this use patched in
-                  // (building a plan costs ~500 cycles of this thread, 8 % of a 96-channel group)
-                  uint4* dst = plan + g * 8;
-                  const uint4* src = table + blk * 8;
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) dst[i] = src[i];
-                  dst[0].w = (use & 1u) ^ 1u;
-                } else {
-                  build_plan(plan + g * 8, blk, use, r_lo, r_hi);
-                }
-                if (--bt < 0) { bt = ring - 1; ++ut; }
+                RowPlan pl;
+                make_plan(tg + g, sg, bt, pl);
+                plan[2 * g] = make_uint4(pl.dA, pl.iA, pl.bA, pl.dB);
+                plan[2 * g + 1] = make_uint4(pl.iB, pl.bB, pl.iR, pl.init ? 1u : 0u);
+                if (--bt < 0) bt = ring - 1;
               }
             }
-            const int a_slot0 = a_slot; const uint32_t a_phase0 = a_phase;
-            if (tr) p.trace[it * 8 + 1] = clock64();                                      // plans built
+            const int a_slot0 = a_slot;
+            if (tr) trace[it * 8 + 1] = clock64();                                      // plans built
             long long wait_b = 0, wait_a = 0;
             for (int c = 0; c < n_chunks; ++c) {
               int cc = c;
-              if (SPLIT) { while (cc >= p.nb) cc -= p.nb; }
-              const int ksteps = (cc == p.nb - 1) ? p.ksteps_last : 4;
+              if (SPLIT) { while (cc >= nb) cc -= nb; }
+              const int ksteps = (cc == nb - 1) ? ksteps_last : 4;
               for (int si = 0; si < n_s; ++si) {
                 const long long tb0 = tr ? clock64() : 0;
-                mbar_wait(&b_full[b_stage], b_phase);
+                await();                                                                  // weight stage landed
                 tc_fence_after();
                 if (tr) wait_b += clock64() - tb0;
-                const uint32_t b_lo0 = d_lo + ((b_base + static_cast<uint32_t>(b_stage) * b_tile_bytes) >> 4);
+                const uint32_t b_lo = b_desc0 + static_cast<uint32_t>(b_stage) * b_tile_units;
                 const uint32_t s_off = (si == 0) ? s_off0 : ((si == 1) ? s_off1 : s_off2);
                 int lin_slot = a_slot0 + c * gcur;      // slots of this chunk's rows: a_slot0 + c * gcur + g (mod a_slots)
-                uint32_t ph = a_phase0;
-                while (lin_slot >= a_slots) { lin_slot -= a_slots; ph ^= 1; }
+                while (lin_slot >= a_slots) lin_slot -= a_slots;
                 for (int g = 0; g < gcur; ++g) {
-                  const uint4* row_plan = plan + g * 8;
-                  const uint4 hdr = row_plan[0];
-                  const bool first_pass = (c == 0 && si == 0 && hdr.y != 0);
-                  uint4 pn[3], pf[4];
-#pragma unroll
-                  for (int i = 0; i < 3; ++i) pn[i] = row_plan[1 + i];
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) pf[i] = row_plan[4 + i];
+                  const uint4 q0 = plan[2 * g], q1 = plan[2 * g + 1];
+                  RowPlan pl;
+                  pl.dA = q0.x; pl.iA = q0.y; pl.bA = q0.z; pl.dB = q0.w; pl.iB = q1.x; pl.bB = q1.y; pl.iR = q1.z;
+                  pl.init = q1.w != 0u;
+                  const bool first = (c == 0 && si == 0 && pl.init);
                   if (si == 0) {
                     const long long ta0 = tr ? clock64() : 0;
-                    mbar_wait(&a_full[lin_slot], ph);
-                    if (first_pass) mbar_wait(&acc_empty[hdr.z], hdr.w);    // previous user of the new row's block drained
+                    await();                                                              // A slot landed
+                    if (c == 0 && pl.init) await();                                       // the new row's block drained
                     tc_fence_after();
                     if (tr) wait_a += clock64() - ta0;
-                    if (tr && c == 0 && g == 0) p.trace[it * 8 + 2] = clock64();
+                    if (tr && c == 0 && g == 0) trace[it * 8 + 2] = clock64();
                   }
-                  const uint32_t a_lo = d_lo + ((a_base + static_cast<uint32_t>(lin_slot) * a_slot_bytes) >> 4) + s_off;
-                  issue(hdr, pn, pf, first_pass, a_lo, b_lo0, ksteps);
-                  if (si == n_s - 1) umma_commit(&a_empty[lin_slot]);
-                  if (++lin_slot == a_slots) { lin_slot = 0; ph ^= 1; }
+                  issue_shift(pl, first, a_desc0 + static_cast<uint32_t>(lin_slot) * a_slot_units + s_off, b_lo, ksteps);
+                  if (si == n_s - 1) umma_commit_addr(bar_a_empty + 8u * lin_slot);
+                  if (++lin_slot == a_slots) lin_slot = 0;
                 }
-                umma_commit(&b_empty[b_stage]);
-                if (++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
+                umma_commit_addr(bar_b_empty + 8u * b_stage);
+                if (++b_stage == b_stages) b_stage = 0;
               }
             }
             // advance the A ring past this group
-            a_slot = a_slot0 + n_chunks * gcur; a_phase = a_phase0;
-            while (a_slot >= a_slots) { a_slot -= a_slots; a_phase ^= 1; }
+            a_slot = a_slot0 + n_chunks * gcur;
+            while (a_slot >= a_slots) a_slot -= a_slots;
             // output rows completed by this group: tap rm_hi of each input row, if that row belongs to the segment
             for (int g = 0; g < gcur; ++g) {
               const int j = tg + g + 1 - rm_hi;
               if (j >= sg.y0 && j < sg.y1) {
                 int blk_done = blk_top + rm_hi; if (blk_done >= ring) blk_done -= ring;
-                umma_commit(&acc_full[blk_done]);
+                umma_commit_addr(bar_acc_full + 8u * blk_done);
               }
-              if (--blk_top < 0) { blk_top = ring - 1; ++use_top; }
+              if (--blk_top < 0) blk_top = ring - 1;
             }
-            if (tr) { p.trace[it * 8 + 3] = clock64(); p.trace[512 + it] = wait_b; p.trace[576 + it] = wait_a; }
+            if (tr) { trace[it * 8 + 3] = clock64(); trace[640 + it] = wait_b; trace[704 + it] = wait_a; }
           }
         }
         q_seg += static_cast<uint32_t>(sg.y1 - sg.y0);
@@ -545,6 +683,59 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
             tma_store_commit();
           }
         };
+        if (p.epi_plain) {
+          // The common layer: one 16-bit output, optional ReLU, nothing else.  Kept small on purpose - an epilogue warp shares
+          // the ~6 KB L0 instruction cache of its SM sub-partition with the UMMA-issuing thread, and the general path below
+          // (residual / mask / relu copy / fp32 / split outputs) spreads one row over ~5 KB of code.
+          const uint32_t lo2 = p.relu ? 0u : (p.bf16 ? 0xFF80FF80u : 0xFC00FC00u);       // max(x, -inf) = x: ReLU as a constant
+          for (int g = 0; g < p.ngroups; ++g) {
+#pragma unroll 1
+            for (int cb = 0; cb < p.cout_store; cb += 32) {
+              uint32_t v[32];
+              __syncwarp();
+              const bool last = (g == p.ngroups - 1 && cb + 32 >= p.cout_store);
+              if (!(p.dbg & 2)) { tmem_ld_32x32(t_blk + static_cast<uint32_t>(g * p.group_c + cb), v); tmem_ld_wait(); }
+              if (last) {   // the accumulator block is free as soon as its last column chunk sits in registers
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[blk]);
+              }
+              if (p.dbg & 3) continue;
+              const int sub = (cb >> 5) & 1;
+              if (sub == 0) begin_rows();
+              const float4* b4 = reinterpret_cast<const float4*>(bias_smem + cb);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 pk; uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+                const float4 ba = b4[2 * i], bb = b4[2 * i + 1];
+                const float f0 = __uint_as_float(v[8 * i]) + ba.x, f1 = __uint_as_float(v[8 * i + 1]) + ba.y,
+                            f2 = __uint_as_float(v[8 * i + 2]) + ba.z, f3 = __uint_as_float(v[8 * i + 3]) + ba.w,
+                            f4 = __uint_as_float(v[8 * i + 4]) + bb.x, f5 = __uint_as_float(v[8 * i + 5]) + bb.y,
+                            f6 = __uint_as_float(v[8 * i + 6]) + bb.z, f7 = __uint_as_float(v[8 * i + 7]) + bb.w;
+                if (p.bf16) {
+                  const __nv_bfloat162 l = *reinterpret_cast<const __nv_bfloat162*>(&lo2);
+                  __nv_bfloat162 h;
+                  h = __hmax2(__floats2bfloat162_rn(f0, f1), l); pw[0] = *reinterpret_cast<uint32_t*>(&h);
+                  h = __hmax2(__floats2bfloat162_rn(f2, f3), l); pw[1] = *reinterpret_cast<uint32_t*>(&h);
+                  h = __hmax2(__floats2bfloat162_rn(f4, f5), l); pw[2] = *reinterpret_cast<uint32_t*>(&h);
+                  h = __hmax2(__floats2bfloat162_rn(f6, f7), l); pw[3] = *reinterpret_cast<uint32_t*>(&h);
+                } else {
+                  const __half2 l = *reinterpret_cast<const __half2*>(&lo2);
+                  __half2 h;
+                  h = __hmax2(__floats2half2_rn(f0, f1), l); pw[0] = *reinterpret_cast<uint32_t*>(&h);
+                  h = __hmax2(__floats2half2_rn(f2, f3), l); pw[1] = *reinterpret_cast<uint32_t*>(&h);
+                  h = __hmax2(__floats2half2_rn(f4, f5), l); pw[2] = *reinterpret_cast<uint32_t*>(&h);
+                  h = __hmax2(__floats2half2_rn(f6, f7), l); pw[3] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(row + (((sub * 4 + i) ^ (lane & 7)) << 4)) = pk;
+              }
+              if (sub == 1 || cb + 32 >= p.cout_store) end_rows(&maps.out[g], cb & ~63);
+            }
+          }
+          __syncwarp();
+          if (tr) p.trace[it * 8 + 6] = clock64();
+          continue;
+        }
         // pass 0: primary output; then (optional) the fp16 relu(primary) copy; then (split mode) the low halves of the primary:
         // every extra pass re-reads the accumulator from TMEM
         const int n_pass = 1 + (p.has_relu_copy ? 1 : 0) + ((SPLIT && p.split_out) ? 1 : 0);
@@ -558,6 +749,15 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
             for (int cb = 0; cb < p.cout_store; cb += 32) {
               uint32_t v[32];
               __syncwarp();
+              if (p.dbg & 3) {
+                if (!(p.dbg & 2)) { tmem_ld_32x32(t_blk + static_cast<uint32_t>(g * p.group_c + cb), v); tmem_ld_wait(); }
+                if (g == p.ngroups - 1 && pass == n_pass - 1 && cb + 32 >= p.cout_store) {
+                  tc_fence_before();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(&acc_empty[blk]);
+                }
+                continue;
+              }
               tmem_ld_32x32(t_blk + static_cast<uint32_t>(g * p.group_c + cb), v);
               uint4 rv[4];
               const bool has_res = (p.residual != nullptr) && (x_in < p.W);

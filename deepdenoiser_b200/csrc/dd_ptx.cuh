@@ -79,6 +79,69 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Raw shared-window address forms for the single-thread UMMA issue loops (no generic -> shared conversion per call).
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 26)) asm volatile("trap;");
+  }
+}
+
+// Pins a kernel parameter (or anything derived from one) in a register.  ptxas otherwise re-reads parameters from the constant
+// bank wherever they are used, and a constant-bank load costs a lone thread 40-80 cycles (measured in situ, round 2,
+// tools/trace_conv.py probe: 8 dependent parameter loads = 620 cycles, 8 dependent shared-memory loads = 290) - ten of them
+// per row in the UMMA-issuing loop of conv_rows.cuh were a third of its critical path.
+// The value makes a round trip through a scratch word of shared memory (volatile store + load): a plain `mov` is seen through
+// by ptxas, which then rematerialises the parameter load again.  `scratch` must be private to the calling warp.
+__device__ __forceinline__ uint32_t pin(uint32_t v, uint32_t scratch) {
+  uint32_t r;
+  asm volatile("st.volatile.shared::cta.u32 [%1], %2;\n\tld.volatile.shared::cta.u32 %0, [%1];" : "=r"(r) : "r"(scratch), "r"(v) : "memory");
+  return r;
+}
+__device__ __forceinline__ int pin(int v, uint32_t scratch) { return static_cast<int>(pin(static_cast<uint32_t>(v), scratch)); }
+template <typename T>
+__device__ __forceinline__ T* pin(T* v, uint32_t scratch) {
+  const uint64_t u = reinterpret_cast<uint64_t>(v);
+  const uint64_t r = static_cast<uint64_t>(pin(static_cast<uint32_t>(u), scratch)) |
+                     (static_cast<uint64_t>(pin(static_cast<uint32_t>(u >> 32), scratch)) << 32);
+  return reinterpret_cast<T*>(r);
+}
+
+// Raw shared-window address forms of the producer-side operations
+__device__ __forceinline__ void mbar_arrive_expect_tx_addr(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_addr(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// CTA-scope release / acquire on a shared-memory word (the barrier watcher's progress counter in conv_rows.cuh).
+__device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // Wait used by compose_rows.cuh (25 warps, most of them waiting at any time): try_wait with a suspend-time hint.  Measured
 // alternatives (round 2, 8 x 1080p): plain try_wait loop 1.57 ms, this 1.57 ms, test_wait + nanosleep(96) 1.65 ms (the wake-up
 // latency costs more than the probes' issue slots).
@@ -160,6 +223,9 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
