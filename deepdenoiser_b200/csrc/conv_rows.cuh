@@ -434,29 +434,48 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
           const uint4 q0 = table[2 * blk], q1 = table[2 * blk + 1];
           pl.dA = q0.x; pl.iA = q0.y; pl.bA = q0.z; pl.dB = q0.w; pl.iB = q1.x; pl.bB = q1.y; pl.iR = q1.z; pl.init = true;
         } else {
+          // the volatile moves keep the compiler from computing this rare path speculatively on every row
+          asm volatile("mov.b32 %0, %0;\n\tmov.b32 %1, %1;\n\tmov.b32 %2, %2;" : "+r"(r_lo), "+r"(r_hi), "+r"(blk));
           plan_taps(r_lo, r_hi, blk, pl);
         }
       };
-      // the UMMAs of one (input row, chunk, shift): k-steps x pieces, operands resident; predicated, branch free
+      // the UMMAs of one (input row, chunk, shift): k-steps x pieces, operands resident.  Real branches around the optional
+      // pieces: a predicated-off tcgen05.mma still costs the thread its ~45-cycle issue slot (tools/umma_queue.cu: 45-56 cycles of
+      // the issuing thread per UMMA on an idle pipe; the pipe queues 6-8 UMMAs before the issue is throttled to its own rate).
       auto issue_shift = [&](const RowPlan& pl, bool first, uint32_t a_lo, uint32_t b_lo, int ksteps) {
         if (dbg & 20) { if (dbg & 4) return; ksteps = 1; }
         const uint32_t b_a = b_lo + pl.bA, b_b = b_lo + pl.bB;
-        // first touch of an output row: its own block with accumulate = 0, then the rest of piece A
-        umma_f16(pl.dA, desc_from(a_lo, d_hi), desc_from(b_a, d_hi), first ? idesc0 + istep : pl.iA, first ? 0u : 1u);
-        if (first && pl.iR) umma_f16(pl.dA + cpad, desc_from(a_lo, d_hi), desc_from(b_a + bstep, d_hi), pl.iR, 1u);
-        if (pl.iB) umma_f16(pl.dB, desc_from(a_lo, d_hi), desc_from(b_b, d_hi), pl.iB, 1u);
-        if (ksteps == 4) {
+        if (first) {
+          // first touch of an output row: its own block with accumulate = 0, then the rest of piece A
+          umma_f16(pl.dA, desc_from(a_lo, d_hi), desc_from(b_a, d_hi), idesc0 + istep, 0u);
+          if (pl.iR) umma_f16(pl.dA + cpad, desc_from(a_lo, d_hi), desc_from(b_a + bstep, d_hi), pl.iR, 1u);
+        } else {
+          umma_f16(pl.dA, desc_from(a_lo, d_hi), desc_from(b_a, d_hi), pl.iA, 1u);
+        }
+        if (pl.iB == 0u) {
+          if (ksteps == 4) {
 #pragma unroll
-          for (int k = 1; k < 4; ++k) {
-            umma_f16(pl.dA, desc_from(a_lo + 2u * k, d_hi), desc_from(b_a + 2u * k, d_hi), pl.iA, 1u);
-            if (pl.iB) umma_f16(pl.dB, desc_from(a_lo + 2u * k, d_hi), desc_from(b_b + 2u * k, d_hi), pl.iB, 1u);
+            for (int k = 1; k < 4; ++k) umma_f16(pl.dA, desc_from(a_lo + 2u * k, d_hi), desc_from(b_a + 2u * k, d_hi), pl.iA, 1u);
+          } else if (ksteps == 2) {
+            umma_f16(pl.dA, desc_from(a_lo + 2u, d_hi), desc_from(b_a + 2u, d_hi), pl.iA, 1u);
+          } else {
+            for (int k = 1; k < ksteps; ++k) umma_f16(pl.dA, desc_from(a_lo + 2u * k, d_hi), desc_from(b_a + 2u * k, d_hi), pl.iA, 1u);
           }
         } else {
+          umma_f16(pl.dB, desc_from(a_lo, d_hi), desc_from(b_b, d_hi), pl.iB, 1u);
+          if (ksteps == 4) {
 #pragma unroll
-          for (int k = 1; k < 3; ++k) {
-            if (k < ksteps) {
+            for (int k = 1; k < 4; ++k) {
               umma_f16(pl.dA, desc_from(a_lo + 2u * k, d_hi), desc_from(b_a + 2u * k, d_hi), pl.iA, 1u);
-              if (pl.iB) umma_f16(pl.dB, desc_from(a_lo + 2u * k, d_hi), desc_from(b_b + 2u * k, d_hi), pl.iB, 1u);
+              umma_f16(pl.dB, desc_from(a_lo + 2u * k, d_hi), desc_from(b_b + 2u * k, d_hi), pl.iB, 1u);
+            }
+          } else if (ksteps == 2) {
+            umma_f16(pl.dA, desc_from(a_lo + 2u, d_hi), desc_from(b_a + 2u, d_hi), pl.iA, 1u);
+            umma_f16(pl.dB, desc_from(a_lo + 2u, d_hi), desc_from(b_b + 2u, d_hi), pl.iB, 1u);
+          } else {
+            for (int k = 1; k < ksteps; ++k) {
+              umma_f16(pl.dA, desc_from(a_lo + 2u * k, d_hi), desc_from(b_a + 2u * k, d_hi), pl.iA, 1u);
+              umma_f16(pl.dB, desc_from(a_lo + 2u * k, d_hi), desc_from(b_b + 2u * k, d_hi), pl.iB, 1u);
             }
           }
         }
