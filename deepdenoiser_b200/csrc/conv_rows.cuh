@@ -656,21 +656,31 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
     const int eset = warp >> 2;                    // rows with q % n_sets == eset
     // A set may only wait for use u of an accumulator barrier after use u-1 completed (parity waits cannot tell
     // phases two apart): its previous row q - n_sets must be at least as late as row q - ring, i.e. n_sets <= ring.
-    const uint32_t n_sets = (p.ring < kRowsEpiSets) ? static_cast<uint32_t>(p.ring) : static_cast<uint32_t>(kRowsEpiSets);
+    const uint32_t scr = smem_u32(tmem_slot + 2 + warp);   // parameters of the row loop pinned in registers (see pin())
+    const int ring_i = pin(p.ring, scr);
+    const int n_sets = (ring_i < kRowsEpiSets) ? ring_i : kRowsEpiSets;
+    const uint32_t cpad_e = pin(static_cast<uint32_t>(p.cpad), scr);
+    const int epi_plain = pin(p.epi_plain, scr), e_ngroups = pin(p.ngroups, scr), e_group_c = pin(p.group_c, scr),
+              e_cout = pin(p.cout_store, scr), e_dbg = pin(p.dbg, scr), e_bf16 = pin(p.bf16, scr);
+    const uint32_t lo2 = pin(p.relu ? 0u : (p.bf16 ? 0xFF80FF80u : 0xFC00FC00u), scr);   // max(x, -inf) = x: ReLU as a constant
+    unsigned long long* const e_trace = (blockIdx.x == 0 && wq == 0 && lane == 0) ? pin(p.trace, scr) : nullptr;
+    const uint32_t bar_full_e = pin(smem_u32(acc_full), scr);
     uint8_t* stage = st_smem + static_cast<size_t>(warp) * 4096;   // one 4 KB staging row set per warp
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
     RowsWalker walk(p);
     RowsSegment sg;
-    uint32_t q = 0;
     int it = 0;
-    const uint32_t ring = static_cast<uint32_t>(p.ring);
+    // output row number q (running) lives in block ring-1-(q % ring), use q / ring, and belongs to set q % n_sets: maintained
+    // incrementally (three integer divisions per row otherwise)
+    int blk_next = ring_i - 1, set_next = 0; uint32_t par_next = 0;
     while (walk.next(sg)) {
-      for (int j = sg.y0; j < sg.y1; ++j, ++q, ++it) {
-        if (q % n_sets != static_cast<uint32_t>(eset)) continue;
-        const int blk = p.ring - 1 - static_cast<int>(q % ring);
-        const uint32_t use = q / ring;
-        const bool tr = p.trace && blockIdx.x == 0 && it < 64 && wq == 0 && lane == 0;
-        if (tr) p.trace[it * 8 + 4] = clock64();
+      for (int j = sg.y0; j < sg.y1; ++j, ++it) {
+        const int blk = blk_next; const uint32_t par = par_next; const bool mine = (set_next == eset);
+        if (--blk_next < 0) { blk_next = ring_i - 1; par_next ^= 1u; }
+        if (++set_next == n_sets) set_next = 0;
+        if (!mine) continue;
+        const bool tr = e_trace && it < 64;
+        if (tr) e_trace[it * 8 + 4] = clock64();
         const int x_in = sg.x0 + wq * 32 + lane;              // input-grid pixel of this thread (TMEM lane)
         const int x_warp = sg.x0 + wq * 32;
         // residual of a narrow layer (<= 32 channels): fetched before the accumulator wait so that its HBM latency
@@ -684,10 +694,10 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
           for (int i = 0; i < 4; ++i)
             rv0[i] = (i * 8 < p.cout_store) ? __ldg(reinterpret_cast<const uint4*>(rp + i * 8)) : make_uint4(0, 0, 0, 0);
         }
-        mbar_wait(&acc_full[blk], use & 1u);
+        mbar_wait_addr(bar_full_e + 8u * blk, par);
         tc_fence_after();
-        if (tr) p.trace[it * 8 + 5] = clock64();
-        const uint32_t t_blk = t_lane + static_cast<uint32_t>(blk * p.cpad);
+        if (tr) e_trace[it * 8 + 5] = clock64();
+        const uint32_t t_blk = t_lane + static_cast<uint32_t>(blk) * cpad_e;
         uint8_t* row = stage + lane * 128;
         // the single staging set may be rewritten once the previous store of this warp has finished reading it
         auto begin_rows = [&]() {
@@ -702,24 +712,23 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
             tma_store_commit();
           }
         };
-        if (p.epi_plain) {
+        if (epi_plain) {
           // The common layer: one 16-bit output, optional ReLU, nothing else.  Kept small on purpose - an epilogue warp shares
           // the ~6 KB L0 instruction cache of its SM sub-partition with the UMMA-issuing thread, and the general path below
           // (residual / mask / relu copy / fp32 / split outputs) spreads one row over ~5 KB of code.
-          const uint32_t lo2 = p.relu ? 0u : (p.bf16 ? 0xFF80FF80u : 0xFC00FC00u);       // max(x, -inf) = x: ReLU as a constant
-          for (int g = 0; g < p.ngroups; ++g) {
+          for (int g = 0; g < e_ngroups; ++g) {
 #pragma unroll 1
-            for (int cb = 0; cb < p.cout_store; cb += 32) {
+            for (int cb = 0; cb < e_cout; cb += 32) {
               uint32_t v[32];
               __syncwarp();
-              const bool last = (g == p.ngroups - 1 && cb + 32 >= p.cout_store);
-              if (!(p.dbg & 2)) { tmem_ld_32x32(t_blk + static_cast<uint32_t>(g * p.group_c + cb), v); tmem_ld_wait(); }
+              const bool last = (g == e_ngroups - 1 && cb + 32 >= e_cout);
+              if (!(e_dbg & 2)) { tmem_ld_32x32(t_blk + static_cast<uint32_t>(g * e_group_c + cb), v); tmem_ld_wait(); }
               if (last) {   // the accumulator block is free as soon as its last column chunk sits in registers
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[blk]);
               }
-              if (p.dbg & 3) continue;
+              if (e_dbg & 3) continue;
               const int sub = (cb >> 5) & 1;
               if (sub == 0) begin_rows();
               const float4* b4 = reinterpret_cast<const float4*>(bias_smem + cb);
@@ -731,7 +740,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
                             f2 = __uint_as_float(v[8 * i + 2]) + ba.z, f3 = __uint_as_float(v[8 * i + 3]) + ba.w,
                             f4 = __uint_as_float(v[8 * i + 4]) + bb.x, f5 = __uint_as_float(v[8 * i + 5]) + bb.y,
                             f6 = __uint_as_float(v[8 * i + 6]) + bb.z, f7 = __uint_as_float(v[8 * i + 7]) + bb.w;
-                if (p.bf16) {
+                if (e_bf16) {
                   const __nv_bfloat162 l = *reinterpret_cast<const __nv_bfloat162*>(&lo2);
                   __nv_bfloat162 h;
                   h = __hmax2(__floats2bfloat162_rn(f0, f1), l); pw[0] = *reinterpret_cast<uint32_t*>(&h);
@@ -748,11 +757,11 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
                 }
                 *reinterpret_cast<uint4*>(row + (((sub * 4 + i) ^ (lane & 7)) << 4)) = pk;
               }
-              if (sub == 1 || cb + 32 >= p.cout_store) end_rows(&maps.out[g], cb & ~63);
+              if (sub == 1 || cb + 32 >= e_cout) end_rows(&maps.out[g], cb & ~63);
             }
           }
           __syncwarp();
-          if (tr) p.trace[it * 8 + 6] = clock64();
+          if (tr) e_trace[it * 8 + 6] = clock64();
           continue;
         }
         // pass 0: primary output; then (optional) the fp16 relu(primary) copy; then (split mode) the low halves of the primary:
@@ -860,7 +869,7 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
           }
         }
         __syncwarp();
-        if (tr) p.trace[it * 8 + 6] = clock64();
+        if (tr) e_trace[it * 8 + 6] = clock64();
       }
     }
     if (lane == 0) tma_store_wait_all();
