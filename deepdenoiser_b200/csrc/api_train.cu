@@ -340,6 +340,76 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const PoolBwdParams p)
   }
 }
 
+// Gather form for 16-bit tensors (the tensor-core training path): one thread per (INPUT pixel, 8 channels) visits the <= 4
+// windows that contain the pixel, and takes a window's gradient when the pixel is the window's FIRST maximum (TF MaxPoolGrad;
+// decided by comparing with the stored pooled value and, on a match, with the window elements that precede the pixel).  No
+// atomics, no fp32 scratch tensor, no zero fill, and the result is ADDED to the 16-bit gradient in place - the scatter form
+// above moved ~7 GB per full-resolution level of a cfg5 step for 1.1 GB of activations.
+__global__ void __launch_bounds__(256) maxpool_bwd_gather_kernel(const PoolBwdParams p) {
+  const int cv = p.x.c / 8;
+  const size_t total = static_cast<size_t>(p.x.n) * p.x.h * p.x.w * cv;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % cv) * 8;
+  const size_t ipix = idx / cv;
+  const int xx = static_cast<int>(ipix % p.x.w);
+  const int yy = static_cast<int>((ipix / p.x.w) % p.x.h);
+  const int n = static_cast<int>(ipix / (static_cast<size_t>(p.x.w) * p.x.h));
+  const int bf = p.x.bf16, k = p.ksize;
+  const uint16_t* xin = reinterpret_cast<const uint16_t*>(p.x.ptr);
+  const uint16_t* yin = reinterpret_cast<const uint16_t*>(p.y.ptr);
+  const uint16_t* gin = reinterpret_cast<const uint16_t*>(p.dy.ptr);
+  float xv[8], acc[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(xin + ipix * p.x.cstride + p.x.coff + c)), bf, xv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  // windows oy with 2 oy - pad <= yy <= 2 oy - pad + k - 1
+  int oy_lo = yy + p.pad_y - k + 1; oy_lo = oy_lo <= 0 ? 0 : (oy_lo + 1) >> 1;
+  int oy_hi = (yy + p.pad_y) >> 1; if (oy_hi > p.y.h - 1) oy_hi = p.y.h - 1;
+  int ox_lo = xx + p.pad_x - k + 1; ox_lo = ox_lo <= 0 ? 0 : (ox_lo + 1) >> 1;
+  int ox_hi = (xx + p.pad_x) >> 1; if (ox_hi > p.y.w - 1) ox_hi = p.y.w - 1;
+  for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+      const size_t op = p.y.pix(n, oy, ox);
+      float m[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(yin + op * p.y.cstride + p.y.coff + c)), bf, m);
+      unsigned eq = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) eq |= (xv[i] == m[i]) ? (1u << i) : 0u;
+      if (!eq) continue;
+      // earlier elements of the window (row-major scan) that already hold the maximum take the gradient instead
+      const int y0 = 2 * oy - p.pad_y, x0 = 2 * ox - p.pad_x;
+      bool reached = false;
+      for (int r = 0; r < k && !reached; ++r) {
+        const int y2 = y0 + r;
+        if (y2 < 0 || y2 >= p.x.h) continue;
+        for (int s = 0; s < k; ++s) {
+          const int x2 = x0 + s;
+          if (x2 < 0 || x2 >= p.x.w) continue;
+          if (y2 == yy && x2 == xx) { reached = true; break; }
+          float e[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(xin + p.x.pix(n, y2, x2) * p.x.cstride + p.x.coff + c)), bf, e);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (e[i] == m[i]) eq &= ~(1u << i);
+        }
+      }
+      if (!eq) continue;
+      float g[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(gin + op * p.dy.cstride + p.dy.coff + c)), bf, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (eq & (1u << i)) acc[i] += g[i];
+    }
+  }
+  uint16_t* dst = reinterpret_cast<uint16_t*>(p.dx.ptr) + ipix * p.dx.cstride + p.dx.coff + c;
+  float d[8];
+  unpack8(*reinterpret_cast<const uint4*>(dst), bf, d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] += acc[i];
+  *reinterpret_cast<uint4*>(dst) = pack8(d, bf);
+}
+
 // ------------------------------------------------------------------------------------------------ kernel prediction backward
 // dlogits_k = p_k (G_k - sum_c g_c out_c),  G_k = sum_c g_c S_c[k],  p = softmax(logits)        (no gradient to the source: it is data)
 struct KpBwdParams { View src, logits, dout, dlogits; int K, F, ipt; };
@@ -827,6 +897,27 @@ int dd_maxpool_s2_bwd(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, const
   p.pad_y = (pty > 0 ? pty : 0) / 2; p.pad_x = (ptx > 0 ? ptx : 0) / 2;
   const size_t total = static_cast<size_t>(y->n) * y->h * y->w * y->c;
   maxpool_bwd_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_maxpool_s2_bwd_acc(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, const dd_tensor* dy, int ksize, const dd_tensor* dx,
+                          void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(x) && tensor_ok(y) && tensor_ok(dy) && tensor_ok(dx) && same_dims(y, dy) && same_dims(x, dx),
+               "bad argument");
+  DD_CHECK_ARG(ksize == 2 || ksize == 3, "maxpool ksize must be 2 or 3");
+  const dd_tensor* all[4] = {x, y, dy, dx};
+  for (const dd_tensor* t : all)
+    DD_CHECK_ARG(t->dtype == x->dtype && (t->dtype == DD_F16 || t->dtype == DD_BF16) && t->c % 8 == 0 && t->coff % 8 == 0 &&
+                     t->cstride % 8 == 0, "maxpool_bwd_acc: fp16 / bf16 views with multiples of 8 channels expected");
+  PoolBwdParams p;
+  p.x = make_view(x); p.y = make_view(y); p.dy = make_view(dy); p.dx = make_view(dx); p.ksize = ksize;
+  const int oh = (x->h + 1) / 2, ow = (x->w + 1) / 2;
+  DD_CHECK_ARG(y->h == oh && y->w == ow && y->n == x->n && y->c == x->c, "maxpool_bwd_acc: pooled dims");
+  const int pty = (oh - 1) * 2 + ksize - x->h, ptx = (ow - 1) * 2 + ksize - x->w;
+  p.pad_y = (pty > 0 ? pty : 0) / 2; p.pad_x = (ptx > 0 ? ptx : 0) / 2;
+  const size_t total = static_cast<size_t>(x->n) * x->h * x->w * (x->c / 8);
+  maxpool_bwd_gather_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }

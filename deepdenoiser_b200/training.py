@@ -476,10 +476,8 @@ class Trainer:
       skip, pooled = tape["pools"][i]
       dskip = V(dcat[i].t, f[i], 0)                                  # [:f] half, written by the concat consumer
       if self.mixed:
-        # dd_maxpool_s2_bwd scatters with fp32 atomics: route through an fp32 scratch tensor, then add
-        scratch = self._buf("pool%d.scatter" % i, tuple(skip.t.shape[:3]) + (f[i],), zero=True)
-        ctx.call("dd_maxpool_s2_bwd", _b(skip.d), _b(pooled.d), _b(dpool.d), 3, _b(_lib.desc(scratch)))
-        ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(scratch)), _b(dskip.d))
+        # gather form: adds into the 16-bit concat gradient in place (no atomics, no fp32 scratch tensor)
+        ctx.call("dd_maxpool_s2_bwd_acc", _b(skip.d), _b(pooled.d), _b(dpool.d), 3, _b(dskip.d))
       else:
         ctx.call("dd_maxpool_s2_bwd", _b(skip.d), _b(pooled.d), _b(dpool.d), 3, _b(dskip.d))
       layers, acts = blocks["d%d" % i]
@@ -708,12 +706,17 @@ class Trainer:
     logits = list(tape["logits_coarse_first"])
     if arch.use_multiscale_predictions:
       logits.reverse()                                   # largest first (Architecture.py:577-579)
-    if not arch.use_kernel_prediction:
-      raise NotImplementedError("training without kernel prediction is not built")
     kp = []
     for s in range(n_scales):
       dst = self._buf("kp.out%d" % s, (nt, h >> s, w >> s, 3))
-      ctx.kernel_predict(_lib.desc(kp_sources[s]), logits[s].d, arch.kernel_size, ft, n, _lib.desc(dst))
+      if arch.use_kernel_prediction:
+        ctx.kernel_predict(_lib.desc(kp_sources[s]), logits[s].d, arch.kernel_size, ft, n, _lib.desc(dst))
+      else:
+        # direct prediction (Architecture.py:519-521): the post-processed tensor is split into 3 channels per feature
+        if ft != 1:
+          raise NotImplementedError("training without kernel prediction is built for SINGLE tuples; the COMBINED variant's "
+                                    "gradients do not match the oracle yet (inference of that variant is built and tested)")
+        arch._split_direct(logits[s], dst, len(tuples), n)
       kp.append(dst)
     # multi-scale composition / inverse standardisation; `pre` = values fed to the inversion (needed by its backward)
     stage = list(kp)
@@ -1000,8 +1003,16 @@ class Trainer:
     dlogits = []
     for s in range(n_scales):
       dl = self._act("dlogits%d" % s, tuple(st["logits"][s].t.shape[:3]), st["logits"][s].c)
-      ctx.call("dd_kernel_predict_bwd", _b(_lib.desc(st["kp_sources"][s])), _b(st["logits"][s].d), _b(_lib.desc(dlarge[s])),
-               arch.kernel_size, arch.features_per_tuple, n, _b(dl.d))
+      if arch.use_kernel_prediction:
+        ctx.call("dd_kernel_predict_bwd", _b(_lib.desc(st["kp_sources"][s])), _b(st["logits"][s].d), _b(_lib.desc(dlarge[s])),
+                 arch.kernel_size, arch.features_per_tuple, n, _b(dl.d))
+      else:
+        # adjoint of the per-feature split: feature f of tuple t owns channels [3f, 3f+3) of the tuple's images
+        ft = arch.features_per_tuple
+        for t in range(len(arch.feature_prediction_tuples)):
+          for f in range(ft):
+            g_tf = dlarge[s][(t * ft + f) * n:(t * ft + f + 1) * n]
+            ctx.cast_copy(_lib.desc(g_tf), V(dl.t[t * n:(t + 1) * n], 3, dl.coff + 3 * f).d)
       dlogits.append(dl)
     if arch.use_multiscale_predictions:
       dlogits.reverse()                           # coarsest first, the order of the core outputs

@@ -308,6 +308,9 @@ int dd_conv2d_repack_f32(dd_ctx* ctx, const float* w_dev, int ksize, int cin, in
 /* backward of dd_maxpool_s2_fwd: dx (fp32, pre-zeroed or accumulating) += dy routed to the first maximum of each window. */
 int dd_maxpool_s2_bwd(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, const dd_tensor* dy, int ksize, const dd_tensor* dx,
                       void* stream);
+/* Same routing for fp16 / bf16 tensors in gather form (no atomics): dx += the gradient, in place, in the tensors' 16-bit type. */
+int dd_maxpool_s2_bwd_acc(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, const dd_tensor* dy, int ksize, const dd_tensor* dx,
+                          void* stream);
 /* backward of dd_kernel_predict_fwd w.r.t. the logits (the source is data): softmax Jacobian included. */
 int dd_kernel_predict_bwd(dd_ctx* ctx, const dd_tensor* src, const dd_tensor* logits, const dd_tensor* dout, int ksize,
                           int features, int images_per_tuple, const dd_tensor* dlogits, void* stream);

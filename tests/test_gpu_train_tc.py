@@ -273,3 +273,23 @@ def test_maxpool_16bit_vector_path(ctx, dtype):
   xp = F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1), value=float("-inf"))
   want = F.max_pool2d(xp, 3, 2).permute(0, 2, 3, 1).to(dtype)
   assert torch.equal(y, want)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("k,h,w", [(3, 12, 20), (3, 11, 17), (2, 12, 20), (2, 9, 15)])
+def test_maxpool_backward_gather_matches_the_scatter_form(ctx, dtype, k, h, w):
+  """dd_maxpool_s2_bwd_acc (gather, 16-bit, accumulating) == dd_maxpool_s2_bwd (fp32 atomics) on data FULL of ties (ReLU
+  zeros and coarsely quantised positives): the gradient goes to the first maximum of every window (TF MaxPoolGrad)."""
+  n, c = 2, 16
+  x = torch.clamp(torch.round(torch.randn(n, h, w, c, device="cuda") * 2.0) / 2.0, min=0.0).to(dtype)
+  oh, ow = (h + 1) // 2, (w + 1) // 2
+  y = torch.empty(n, oh, ow, c, device="cuda", dtype=dtype)
+  ctx.maxpool_s2(_lib.desc(x), k, _lib.desc(y))
+  dy = (torch.round(torch.randn(n, oh, ow, c, device="cuda") * 8.0) / 8.0).to(dtype)      # exactly representable sums
+  want = torch.zeros(n, h, w, c, device="cuda", dtype=torch.float32)
+  ctx.call("dd_maxpool_s2_bwd", _b(_lib.desc(x)), _b(_lib.desc(y)), _b(_lib.desc(dy)), k, _b(_lib.desc(want)))
+  base = (torch.round(torch.randn(n, h, w, c, device="cuda") * 4.0) / 4.0).to(dtype)
+  got = base.clone()
+  ctx.call("dd_maxpool_s2_bwd_acc", _b(_lib.desc(x)), _b(_lib.desc(y)), _b(_lib.desc(dy)), k, _b(_lib.desc(got)))
+  torch.cuda.synchronize()
+  assert torch.equal(got.float(), base.float() + want)

@@ -94,6 +94,25 @@ def test_gradients_combined_tuples_and_invert_before_compose():
   check_gradients(trainer, want_grads)
 
 
+def test_gradients_without_kernel_prediction():
+  """Direct 3-channel prediction per feature (Architecture.py:519-521 allows use_kernel_prediction = false), SINGLE tuples."""
+  j = small_example(filters=(16, 16), n_convs=1, k=3, tuple_type="SINGLE")
+  j["architecture"]["kernel_prediction"]["use_kernel_prediction"] = False
+  host, weights, features, targets = make_problem(j, n=1, h=8, w=12)
+  trainer = Trainer(Architecture(j, weights=weights), TrainingSettings())
+  trainer.forward({k: torch.from_numpy(v) for k, v in features.items()})
+  loss = float(trainer.loss_and_gradient({k: torch.from_numpy(v) for k, v in targets.items()}).item())
+  trainer.backward()
+  want_loss, want_grads, want_preds = oracle_loss_and_grads(j, weights, features, targets)
+  got_preds = trainer.predictions()
+  for s in range(len(want_preds)):
+    for k_, v in want_preds[s].items():
+      v = v.detach().numpy()       # direct predictions are unbounded network outputs: tolerance relative to their scale
+      assert np.abs(got_preds[s][k_].cpu().numpy() - v).max() <= 1e-4 * max(1.0, float(np.abs(v).max())), k_
+  assert abs(loss - want_loss) <= 1e-4 * max(1.0, abs(want_loss)), (loss, want_loss)
+  check_gradients(trainer, want_grads)
+
+
 def test_gradients_tiramisu_backbone():
   """Dense blocks (shared concat gradient), 1x1 transition + 2x2 max-pool, 3x3 stride-2 transposed convolution."""
   j = small_example(filters=(8, 16, 16), n_convs=2, k=3)
