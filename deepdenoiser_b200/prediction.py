@@ -179,10 +179,11 @@ def cut_tiles(image, tiles, ctx=None):
   return torch.stack([image[t.y:t.y + t.size, t.x:t.x + t.size] for t in tiles], dim=0)
 
 
-def stitch_tiles(batch, tiles, height, width, ctx=None):
+def stitch_tiles(batch, tiles, height, width, ctx=None, out=None):
   """[T,size,size,C] predictions -> [H,W,C] image, keeping each tile's crop (Prediction.py:384-441).  CUDA batches are
-  pasted by one dd_tiles_scatter launch."""
-  out = torch.empty((height, width, batch.shape[3]), dtype=batch.dtype, device=batch.device)
+  pasted by one dd_tiles_scatter launch.  `out`: paste into this image instead of a new one (a rank's share of the tiles)."""
+  if out is None:
+    out = torch.empty((height, width, batch.shape[3]), dtype=batch.dtype, device=batch.device)
   if ctx is not None and batch.is_cuda:
     import ctypes
     from . import _lib
@@ -237,6 +238,22 @@ def predict_image(architecture, features, height, width, tile_size=128, tile_ove
       dev = v.device
   results = {k: torch.cat(v, dim=0) for k, v in results.items()}
   if world_size > 1:
+    import torch.distributed as dist
+    on_device = ctx is not None and dist.get_backend() == "nccl"
+    if on_device:
+      # every rank pastes ITS tiles into a zero frame; the kept crops partition the image, so a sum over the ranks (one NCCL
+      # reduce per pass over NVLink) is the stitched frame, bit for bit.  (The host-side gather below pickles ~3 GB at 4K.)
+      layout = [[(k, int(v.shape[3])) for k, v in results.items()]] if rank == 0 else [None]
+      dist.broadcast_object_list(layout, src=0)                  # a rank may own no tile at all
+      my_tiles = [tiles[i] for i in mine]
+      out = {}
+      for k, channels in layout[0]:
+        frame = torch.zeros((height, width, channels), dtype=torch.float32, device=ctx.device)
+        if my_tiles:
+          stitch_tiles(results[k].float(), my_tiles, height, width, ctx, out=frame)
+        dist.reduce(frame, dst=0)
+        out[k] = frame
+      return out if rank == 0 else None
     results = _gather_tiles(results, mine, len(tiles), rank, world_size, dev)
     if rank != 0:
       return None

@@ -28,6 +28,7 @@ def main():
   ap.add_argument("--width", type=int, default=3840)
   ap.add_argument("--tiles", default="128,256,512,0")
   ap.add_argument("--repeats", type=int, default=2)
+  ap.add_argument("--stream-frames", type=int, default=4, help="full frames streamed through FramePipeline per rank (0 = skip)")
   ap.add_argument("--out", default=None)
   args = ap.parse_args()
   rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
@@ -42,7 +43,7 @@ def main():
   feats = synthetic.synthetic_features(arch, 1, args.height, args.width, seed=99)
   feats = {k: torch.from_numpy(v[0]).pin_memory() for k, v in feats.items()}
   mp = args.height * args.width / 1e6
-  results, full = [], None
+  results, full, stream_rec = [], None, None
   pinned_out = {}
 
   def download(name, t):
@@ -52,7 +53,30 @@ def main():
       pinned_out[name] = buf
     buf.copy_(t, non_blocking=True)
     return buf
-  for tile in [int(t) for t in args.tiles.split(",")]:
+  # full frames as a STREAM (Prediction.py walks a directory of frames): FramePipeline overlaps the upload of frame i+1 and the
+  # download of frame i-1 with the kernels of frame i; every rank streams its own frames (no exchange)
+  if args.stream_frames > 0:
+    from deepdenoiser_b200.pipeline import FramePipeline
+    pipe = FramePipeline(arch)
+    frame = {k: v.unsqueeze(0).contiguous().pin_memory() for k, v in feats.items()}
+    pipe.run([frame] * 2)                                        # warm-up: buffers, weights, caches
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    t0 = time.perf_counter()
+    done = pipe.run([frame] * args.stream_frames)
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    dt = time.perf_counter() - t0
+    rec = {"tile": 0, "mode": "stream of %d full frames per rank through FramePipeline (copies overlapped)" % done,
+           "seconds_per_frame": dt / done, "megapixels_per_s": world * done * mp / dt}
+    if rank == 0:
+      stream_rec = rec
+      print(json.dumps(rec), flush=True)
+    arch.network.release_buffers()
+    torch.cuda.empty_cache()
+  for tile in [int(t) for t in args.tiles.split(",") if t != ""]:
     overlap = max(2, int(round(tile * 14 / 128))) if tile else 0
     times = []
     out = None
@@ -83,11 +107,11 @@ def main():
     torch.cuda.empty_cache()
   if rank == 0:
     summary = {"metric": "tiled inference, %dx%d, U-Net KPCN 32-ch (cfg4)" % (args.width, args.height), "n_gpus": world,
-               "results": [r for r, _ in results]}
+               "results": [r for r, _ in results], "stream": stream_rec}
     if full is not None:
       for rec, out in results:
         if rec["tile"]:
-          rec["max_abs_diff_vs_full_frame"] = max(float((out[k] - full[k]).abs().max()) for k in out)
+          rec["max_abs_diff_vs_full_frame"] = max(float((out[k].cpu() - full[k].cpu()).abs().max()) for k in out)
     print(json.dumps(summary))
     if args.out:
       with open(args.out, "w") as f:
