@@ -143,14 +143,35 @@ __global__ void __launch_bounds__(kPkThreads) post_kp_fused_kernel(const PostKpP
     src_f[it] = (i < SRC_ELEMS) ? f : -1; src_ly[it] = r / TWs - PAD; src_lx[it] = r % TWs - PAD;
   }
 
+  // interior tiles (no clipping, no symmetric padding) take a path without per-element index arithmetic: all per-thread offsets
+  // are fixed for the whole kernel
+  const int im_h = p.h, im_w = p.w, x_cs = p.xcs;
+  const int w_xcs = im_w * x_cs;
+  const bool rows_step = (px_step & 15) == 0;                     // a thread keeps its tile column from load to load
+  const int thr_x_off = (ld_px0 >> 4) * w_xcs + (ld_px0 & 15) * x_cs + p.xoff + ld_c * 8;
+  const int step_x_off = (px_step >> 4) * w_xcs;
+  const int src_cs = p.src.cstride;
+  int src_off[SRC_ITERS];
+#pragma unroll
+  for (int it = 0; it < SRC_ITERS; ++it) src_off[it] = (src_ly[it] * im_w + src_lx[it]) * src_cs + p.src.coff;
+  const float* src_base = reinterpret_cast<const float*>(p.src.ptr);
+
   auto issue_loads = [&](const Coord& c, int buf) {
     const int y0 = c.ty * kPkTileH, x0 = c.tx * kPkTileW;
-    if (ld_c < cchunks) {
+    const bool inside = (y0 + kPkTileH <= im_h) && (x0 + kPkTileW <= im_w);
+    if (ld_c < cchunks && inside && rows_step && ld_c < valid_chunks) {
+      uint32_t dst = xs_u + static_cast<uint32_t>(buf * x_bytes + ld_c * 16 + ld_px0 * xrow);
+      const uint32_t dst_step = static_cast<uint32_t>(px_step * xrow);
+      const __half* src = p.x + ((static_cast<size_t>(c.b) * im_h + y0) * im_w + x0) * x_cs + thr_x_off;
+      for (int px = ld_px0; px < 128; px += px_step) {
+        pk_cp_async_16(dst, src);
+        dst += dst_step; src += step_x_off;
+      }
+    } else if (ld_c < cchunks) {
       uint32_t dst = xs_u + static_cast<uint32_t>(buf * x_bytes + ld_c * 16 + ld_px0 * xrow);
       const uint32_t dst_step = static_cast<uint32_t>(px_step * xrow);
       const __half* tile_base = p.x + ((static_cast<size_t>(c.b) * p.h + y0) * p.w + x0) * p.xcs + p.xoff + ld_c * 8;
       const bool chunk_ok = ld_c < valid_chunks;
-      const int w_xcs = p.w * p.xcs;
       for (int px = ld_px0; px < 128; px += px_step) {
         const int r = px >> 4, xx = px & 15;
         if (chunk_ok && y0 + r < p.h && x0 + xx < p.w) {
@@ -163,6 +184,18 @@ __global__ void __launch_bounds__(kPkThreads) post_kp_fused_kernel(const PostKpP
     }
     // source halo tiles (symmetric padding, KernelPrediction.py:30 via Conv2dUtilities.pad_equally)
     const int img0 = first_image(c.b);
+    if (y0 >= PAD && x0 >= PAD && y0 + kPkTileH + PAD <= im_h && x0 + kPkTileW + PAD <= im_w) {
+#pragma unroll
+      for (int it = 0; it < SRC_ITERS; ++it) {
+        if (src_f[it] >= 0) {
+          const float* sp = src_base + ((static_cast<size_t>(img0 + src_f[it] * p.ipt) * im_h + y0) * im_w + x0) * src_cs + src_off[it];
+          const uint32_t dst = src_u + static_cast<uint32_t>((buf * SRC_ELEMS + tid + it * kPkThreads) * 16);
+          pk_cp_async_4(dst, sp); pk_cp_async_4(dst + 4, sp + 1); pk_cp_async_4(dst + 8, sp + 2);
+        }
+      }
+      pk_cp_async_commit();
+      return;
+    }
 #pragma unroll
     for (int it = 0; it < SRC_ITERS; ++it) {
       if (src_f[it] >= 0) {
