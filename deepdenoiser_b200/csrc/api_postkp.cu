@@ -320,7 +320,13 @@ static int launch_post_kp(dd_ctx* ctx, const PostKpParams& p, cudaStream_t s) {
                       2 * static_cast<size_t>(T) * (kPkTileH + 2 * PAD) * (kPkTileW + 2 * PAD) * sizeof(float4);
   DD_CHECK_ARG(smem <= ctx->max_smem_optin, "post_kp: tile does not fit shared memory");
   DD_CUDA(cudaFuncSetAttribute(post_kp_fused_kernel<K, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  int grid = ctx->sm_count * 4;
+  // persistent grid = exactly the CTAs that are resident at once (4 per SM at C = 64, 3 at 96, 2 at 128): a 4th CTA per SM that
+  // has to wait for a slot would run its whole tile share after the others have finished
+  int per_sm = 0;
+  DD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, post_kp_fused_kernel<K, T>, kPkThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  int grid = ctx->sm_count * per_sm;
   if (grid > p.total_tiles) grid = p.total_tiles;
   post_kp_fused_kernel<K, T><<<static_cast<unsigned>(grid), kPkThreads, smem, s>>>(p);
   DD_LAUNCH_CHECK(ctx);

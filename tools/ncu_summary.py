@@ -32,7 +32,7 @@ def main():
         continue
       i = cols[0]
       w.writerow([key, units[i]] + [d[i] for d in data])
-  # roofline.traffic of bench.py: dram bytes of the LAST captured conv_rows_kernel launch (profiles/ncu_traffic.json)
+  # roofline.traffic of bench.py: dram bytes of the longest captured conv_rows_kernel launch (profiles/ncu_traffic.json)
   def col(name):
     c = [i for i, h in enumerate(header) if h == name]
     return c[0] if c else None
@@ -42,12 +42,12 @@ def main():
     import json
     import os
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    d = convs[-1]
+    d = max(convs, key=lambda r: float(r[dur].replace(",", "")) if dur is not None else 0.0)    # the longest captured launch
     total = float(d[rd].replace(",", "")) * scale.get(units[rd], 1.0) + float(d[wr].replace(",", "")) * scale.get(units[wr], 1.0)
     path = os.path.join(os.path.dirname(os.path.abspath(out)), "ncu_traffic.json")
     known = json.load(open(path)) if os.path.exists(path) else {}
     known["conv_rows_kernel"] = {"bytes": total, "launch": "launch %d of %s (%s %s under ncu --set full)" %
-                                 (len(convs), os.path.basename(rep), d[dur] if dur is not None else "?", units[dur] if dur is not None else "")}
+                                 (convs.index(d) + 1, os.path.basename(rep), d[dur] if dur is not None else "?", units[dur] if dur is not None else "")}
     json.dump(known, open(path, "w"), indent=1)
 
 
