@@ -189,9 +189,13 @@ def test_conv_epilogue_relu_mask(ctx, cin, cout):
   assert torch.equal(fused, plain * (mask > 0))
 
 
-@pytest.mark.parametrize("k,features,ipt,h,w,ldtype", [(5, 1, 1, 9, 14, torch.float32), (21, 1, 2, 12, 10, torch.float32),
-                                                        (3, 3, 1, 8, 11, torch.float32), (5, 3, 2, 7, 9, torch.float16)])
-def test_kernel_predict_bwd_matches_autograd(ctx, k, features, ipt, h, w, ldtype):
+@pytest.mark.parametrize("k,features,ipt,h,w,ldtype,gdtype", [
+    (5, 1, 1, 9, 14, torch.float32, None), (21, 1, 2, 12, 10, torch.float32, None), (3, 3, 1, 8, 11, torch.float32, None),
+    (5, 3, 2, 7, 9, torch.float16, None),
+    # the tiled kernel (one feature per tuple, K = 3 / 5, fp32 logits): tiles cut by the image border, 16-bit gradient rows
+    (5, 1, 2, 19, 45, torch.float32, None), (5, 1, 1, 19, 45, torch.float32, torch.bfloat16),
+    (3, 1, 1, 10, 70, torch.float32, torch.float16)])
+def test_kernel_predict_bwd_matches_autograd(ctx, k, features, ipt, h, w, ldtype, gdtype):
   """dd_kernel_predict_bwd against torch autograd of softmax + symmetric-padded KxK gather (KernelPrediction.py:11-63)."""
   tuples = 2
   b, k2, pad = tuples * ipt, k * k, (k - 1) // 2
@@ -202,7 +206,7 @@ def test_kernel_predict_bwd_matches_autograd(ctx, k, features, ipt, h, w, ldtype
   logits = logits.to(ldtype)
   src = torch.randn(features * b, h, w, 3, device="cuda", generator=g)
   dout = torch.randn(features * b, h, w, 3, device="cuda", generator=g)
-  dl = torch.zeros(b, h, w, cs, device="cuda", dtype=ldtype)
+  dl = torch.zeros(b, h, w, cs, device="cuda", dtype=gdtype or ldtype)
   ctx.call("dd_kernel_predict_bwd", _b(_lib.desc(src)), _b(_lib.desc(logits, features * k2, 0)), _b(_lib.desc(dout)), k, features,
            ipt, _b(_lib.desc(dl, features * k2, 0)))
   lg = logits.float()[..., :features * k2].clone().requires_grad_(True)
@@ -219,7 +223,7 @@ def test_kernel_predict_bwd_matches_autograd(ctx, k, features, ipt, h, w, ldtype
       out = sum(wts[..., i * k + j, None] * padded[i:i + h, j:j + w] for i in range(k) for j in range(k))
       loss = loss + (out * dout[o]).sum()
   loss.backward()
-  tol = 2e-3 if ldtype == torch.float16 else 2e-5
+  tol = {torch.float16: 2e-3, torch.bfloat16: 1e-2, torch.float32: 2e-5}[gdtype or ldtype]
   assert rel_err(dl.float()[..., :features * k2], lg.grad) <= tol
 
 
