@@ -92,6 +92,73 @@ __global__ void __launch_bounds__(256) ewise_vec_kernel(const Ewise p) {
   *reinterpret_cast<uint4*>(at(p.out)) = pack8(o, p.out.bf16);
 }
 
+// Flat fp32 form: every operand is a dense fp32 tensor (no channel window), so the op runs over a flat array with 32-bit
+// indices and four elements per thread.  The image-space gradient plumbing of a training step (axpy / lighting products /
+// inverse-standardisation backward on [B,h,w,3] fp32 tensors) is ~140 launches per step; the generic kernel spends a 64-bit
+// division and a modulo per element on them.
+struct EwiseFlat { const float* a; const float* b; const float* c; float* out; float* out2; float* out3; int op; float alpha; unsigned n4; };
+__device__ __forceinline__ float4 f4_fma(float s, float4 a, float4 o) { return make_float4(fmaf(s, a.x, o.x), fmaf(s, a.y, o.y), fmaf(s, a.z, o.z), fmaf(s, a.w, o.w)); }
+__global__ void __launch_bounds__(256) ewise_flat_kernel(const EwiseFlat p, const EwiseInv q) {
+  const unsigned i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= p.n4) return;
+  const float4* a4 = reinterpret_cast<const float4*>(p.a);
+  const float4* b4 = reinterpret_cast<const float4*>(p.b);
+  const float4* c4 = reinterpret_cast<const float4*>(p.c);
+  float4* o4 = reinterpret_cast<float4*>(p.out);
+  switch (p.op) {
+    case EW_AXPY: o4[i] = f4_fma(p.alpha, a4[i], o4[i]); break;
+    case EW_FILL: o4[i] = make_float4(p.alpha, p.alpha, p.alpha, p.alpha); break;
+    case EW_MULADD: {
+      const float4 a = a4[i], b = b4[i], c = c4[i];
+      o4[i] = make_float4(a.x * (b.x + c.x), a.y * (b.y + c.y), a.z * (b.z + c.z), a.w * (b.w + c.w));
+      break;
+    }
+    case EW_MULADD_BWD: {
+      const float4 g = o4[i], a = a4[i], b = b4[i], c = c4[i];
+      float4* d2 = reinterpret_cast<float4*>(p.out2);
+      const float4 o = d2[i];
+      d2[i] = make_float4(o.x + g.x * (b.x + c.x), o.y + g.y * (b.y + c.y), o.z + g.z * (b.z + c.z), o.w + g.w * (b.w + c.w));
+      reinterpret_cast<float4*>(p.out3)[i] = make_float4(g.x * a.x, g.y * a.y, g.z * a.z, g.w * a.w);
+      break;
+    }
+    case EW_RELU_MASK: {
+      const float4 a = a4[i], b = b4[i];
+      o4[i] = make_float4(b.x > 0.f ? a.x : 0.f, b.y > 0.f ? a.y : 0.f, b.z > 0.f ? a.z : 0.f, b.w > 0.f ? a.w : 0.f);
+      break;
+    }
+    case EW_INVERT_BWD: {
+      const float4 a = a4[i], b = b4[i];
+      const float xs[4] = {b.x, b.y, b.z, b.w};
+      float d[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float x = xs[k]; d[k] = 1.f;
+        if (q.variance != 1.f) { x *= q.sqrt_var; d[k] *= q.sqrt_var; }
+        if (q.mean != 0.f) x += q.mean;
+        if (q.use_log1p) d[k] *= expf(fabsf(x));
+      }
+      o4[i] = make_float4(a.x * d[0], a.y * d[1], a.z * d[2], a.w * d[3]);
+      break;
+    }
+    default: break;
+  }
+}
+inline bool flat_ok(const View& v) { return v.ptr && !v.f16 && !v.bf16 && v.coff == 0 && v.cstride == v.c && (reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0; }
+// launches the flat kernel when the op's operands allow it (mask bits: 1 a, 2 b, 4 c, 8 out2, 16 out3; `out` always)
+inline bool try_ewise_flat(const Ewise& p, const EwiseInv& q, unsigned uses, cudaStream_t s) {
+  if (p.op == EW_RELU_MASK_ACC) return false;
+  const size_t total = static_cast<size_t>(p.out.n) * p.out.h * p.out.w * p.out.c;
+  if ((total & 3) || total / 4 >= 0xffffff00u || !flat_ok(p.out)) return false;
+  if (((uses & 1) && !flat_ok(p.a)) || ((uses & 2) && !flat_ok(p.b)) || ((uses & 4) && !flat_ok(p.c)) ||
+      ((uses & 8) && !flat_ok(p.out2)) || ((uses & 16) && !flat_ok(p.out3))) return false;
+  EwiseFlat f;
+  f.a = reinterpret_cast<const float*>(p.a.ptr); f.b = reinterpret_cast<const float*>(p.b.ptr); f.c = reinterpret_cast<const float*>(p.c.ptr);
+  f.out = reinterpret_cast<float*>(p.out.ptr); f.out2 = reinterpret_cast<float*>(p.out2.ptr); f.out3 = reinterpret_cast<float*>(p.out3.ptr);
+  f.op = p.op; f.alpha = p.alpha; f.n4 = static_cast<unsigned>(total / 4);
+  ewise_flat_kernel<<<(f.n4 + 255) / 256, 256, 0, s>>>(f, q);
+  return true;
+}
+
 inline bool vec_ok(const View& v) { return vec16_ok(v); }
 // launches the vectorised kernel when every operand allows it; returns false otherwise
 inline bool try_ewise_vec(const Ewise& p, bool uses_b, cudaStream_t s) {
@@ -773,7 +840,7 @@ int dd_relu_bwd(dd_ctx* ctx, const dd_tensor* dy, const dd_tensor* y, const dd_t
   Ewise p; memset(&p, 0, sizeof(p)); EwiseInv q; memset(&q, 0, sizeof(q));
   p.a = make_view(dy); p.b = make_view(y); p.out = make_view(dz); p.op = EW_RELU_MASK;
   const size_t total = static_cast<size_t>(dy->n) * dy->h * dy->w * dy->c;
-  if (!try_ewise_vec(p, true, static_cast<cudaStream_t>(stream)))
+  if (!try_ewise_vec(p, true, static_cast<cudaStream_t>(stream)) && !try_ewise_flat(p, q, 3, static_cast<cudaStream_t>(stream)))
     ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
@@ -796,7 +863,8 @@ int dd_muladd_fwd(dd_ctx* ctx, const dd_tensor* a, const dd_tensor* b, const dd_
   Ewise p; memset(&p, 0, sizeof(p)); EwiseInv q; memset(&q, 0, sizeof(q));
   p.a = make_view(a); p.b = make_view(b); p.c = make_view(c); p.out = make_view(out); p.op = EW_MULADD;
   const size_t total = static_cast<size_t>(a->n) * a->h * a->w * a->c;
-  ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
+  if (!try_ewise_flat(p, q, 7, static_cast<cudaStream_t>(stream)))
+    ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }
@@ -810,7 +878,8 @@ int dd_muladd_bwd(dd_ctx* ctx, const dd_tensor* a, const dd_tensor* b, const dd_
   p.a = make_view(a); p.b = make_view(b); p.c = make_view(c); p.out = make_view(g); p.out2 = make_view(da_acc);
   p.out3 = make_view(dbc_inc); p.op = EW_MULADD_BWD;
   const size_t total = static_cast<size_t>(a->n) * a->h * a->w * a->c;
-  ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
+  if (!try_ewise_flat(p, q, 31, static_cast<cudaStream_t>(stream)))
+    ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }
@@ -820,7 +889,7 @@ int dd_axpy(dd_ctx* ctx, float alpha, const dd_tensor* x, const dd_tensor* y, vo
   Ewise p; memset(&p, 0, sizeof(p)); EwiseInv q; memset(&q, 0, sizeof(q));
   p.a = make_view(x); p.out = make_view(y); p.op = EW_AXPY; p.alpha = alpha;
   const size_t total = static_cast<size_t>(x->n) * x->h * x->w * x->c;
-  if (!try_ewise_vec(p, false, static_cast<cudaStream_t>(stream)))
+  if (!try_ewise_vec(p, false, static_cast<cudaStream_t>(stream)) && !try_ewise_flat(p, q, 1, static_cast<cudaStream_t>(stream)))
     ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
@@ -831,7 +900,8 @@ int dd_fill(dd_ctx* ctx, float value, const dd_tensor* y, void* stream) {
   Ewise p; memset(&p, 0, sizeof(p)); EwiseInv q; memset(&q, 0, sizeof(q));
   p.out = make_view(y); p.op = EW_FILL; p.alpha = value;
   const size_t total = static_cast<size_t>(y->n) * y->h * y->w * y->c;
-  ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
+  if (!try_ewise_flat(p, q, 0, static_cast<cudaStream_t>(stream)))
+    ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }
@@ -843,7 +913,8 @@ int dd_invert_standardization_bwd(dd_ctx* ctx, const dd_tensor* dy, const dd_ten
   q.use_log1p = inv->use_log1p; q.mean = inv->mean; q.variance = inv->variance; q.sqrt_var = sqrtf(inv->variance);
   p.a = make_view(dy); p.b = make_view(x); p.out = make_view(dx); p.op = EW_INVERT_BWD;
   const size_t total = static_cast<size_t>(dy->n) * dy->h * dy->w * dy->c;
-  ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
+  if (!try_ewise_flat(p, q, 3, static_cast<cudaStream_t>(stream)))
+    ewise_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }
