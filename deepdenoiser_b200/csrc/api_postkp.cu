@@ -312,6 +312,241 @@ __global__ void __launch_bounds__(kPkThreads) post_kp_fused_kernel(const PostKpP
   pk_cp_async_wait_all();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// One feature per tuple (SINGLE tuples, the benchmarked configuration): same GEMMs, but the softmax / filter stage runs with ONE
+// THREAD PER PIXEL.  A warp owns two tile rows (M = 32 as two m16 blocks: the weight fragments are shared), stages its 32 x K*K
+// logits through the x rows it has just consumed ([column][32 pixels + 1] floats: conflict free both ways) and every lane then
+// walks the K*K taps of its own pixel with compile-time offsets - no quad shuffles, no padded tap slots, no per-tap address
+// arithmetic.  Measured on the quad form (ncu source counters, profiles/r02_ncu_postkp_compose_full.csv): 41.6 warp-instructions
+// per pixel, 18 of them in the softmax / filter stage and 14 in the tile loads.
+constexpr int kPxThreads = 128, kPxLgPitch = 33;
+
+template <int K>
+__global__ void __launch_bounds__(kPxThreads) post_kp_pixel_kernel(const PostKpParams p) {
+  constexpr int K2 = K * K, O16 = (K2 + 15) / 16 * 16, NT = O16 / 8, PAD = (K - 1) / 2;
+  constexpr int TWs = kPkTileW + 2 * PAD, THs = kPkTileH + 2 * PAD, SRC_ELEMS = THs * TWs;
+  extern __shared__ __align__(16) uint8_t pk_smem[];
+  const int xrow = p.Cpad * 2 + 16;                       // bytes per staged pixel (odd multiple of 16: conflict-free ldmatrix)
+  const int w1row = p.Cpad * 2 + 16, w2row = O16 * 2 + 16;
+  const int x_bytes = 128 * xrow;
+  uint8_t* xs = pk_smem;                                  // [2][128][xrow]
+  uint8_t* w1s = xs + 2 * x_bytes;                        // [O16][w1row]
+  uint8_t* w2s = w1s + O16 * w1row;                       // [O16][w2row]
+  float* b1s = reinterpret_cast<float*>(w2s + O16 * w2row);
+  float* b2s = b1s + O16;
+  float4* s_src = reinterpret_cast<float4*>(b2s + O16);   // [2][THs][TWs]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int cchunks = p.Cpad / 8;
+  for (int i = tid; i < O16 * cchunks; i += kPxThreads) {
+    const int n = i / cchunks, c = i % cchunks;
+    *reinterpret_cast<uint4*>(w1s + n * w1row + c * 16) = *reinterpret_cast<const uint4*>(p.w1t + static_cast<size_t>(n) * p.Cpad + c * 8);
+  }
+  for (int i = tid; i < O16 * (O16 / 8); i += kPxThreads) {
+    const int n = i / (O16 / 8), c = i % (O16 / 8);
+    *reinterpret_cast<uint4*>(w2s + n * w2row + c * 16) = *reinterpret_cast<const uint4*>(p.w2t + static_cast<size_t>(n) * O16 + c * 8);
+  }
+  for (int i = tid; i < O16; i += kPxThreads) { b1s[i] = p.b1[i]; b2s[i] = p.b2[i] * 1.4426950408889634f; }   // logits in log2 units
+
+  const uint32_t xs_u = smem_u32(xs), w1_u = smem_u32(w1s), w2_u = smem_u32(w2s), src_u = smem_u32(s_src);
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_kof = (lane >> 4) * 16;
+  const int b_row = (lane & 7) + (lane >> 4) * 8, b_kof = ((lane >> 3) & 1) * 16;
+  const int valid_chunks = p.C / 8;
+  const int cp_shift = p.cp_shift, cp_mask = (1 << cp_shift) - 1, px_step = kPxThreads >> cp_shift;
+  const int ld_c = tid & cp_mask, ld_px0 = tid >> cp_shift;
+  const int im_h = p.h, im_w = p.w, x_cs = p.xcs, w_xcs = im_w * x_cs, src_cs = p.src.cstride;
+  const float* src_base = reinterpret_cast<const float*>(p.src.ptr) + p.src.coff;
+  float* out_base = reinterpret_cast<float*>(p.out.ptr) + p.out.coff;
+  const int out_cs = p.out.cstride;
+
+  struct Coord { int b, ty, tx; };
+  const int tiles_per_image = p.tiles_x * p.tiles_y;
+  Coord delta;
+  delta.b = static_cast<int>(gridDim.x) / tiles_per_image;
+  { const int rem = static_cast<int>(gridDim.x) - delta.b * tiles_per_image; delta.ty = rem / p.tiles_x; delta.tx = rem - delta.ty * p.tiles_x; }
+  auto advance = [&](Coord& c) {
+    c.tx += delta.tx; if (c.tx >= p.tiles_x) { c.tx -= p.tiles_x; ++c.ty; }
+    c.ty += delta.ty; if (c.ty >= p.tiles_y) { c.ty -= p.tiles_y; ++c.b; }
+    c.b += delta.b;
+  };
+  constexpr int SRC_ITERS = (SRC_ELEMS + kPxThreads - 1) / kPxThreads;
+  int src_ly[SRC_ITERS], src_lx[SRC_ITERS];
+#pragma unroll
+  for (int it = 0; it < SRC_ITERS; ++it) {
+    const int i = tid + it * kPxThreads;
+    src_ly[it] = (i < SRC_ELEMS) ? i / TWs - PAD : -1000; src_lx[it] = i % TWs - PAD;
+  }
+
+  auto issue_loads = [&](const Coord& c, int buf) {
+    const int y0 = c.ty * kPkTileH, x0 = c.tx * kPkTileW;
+    if (ld_c < cchunks) {
+      const bool inside = (y0 + kPkTileH <= im_h) && (x0 + kPkTileW <= im_w) && ld_c < valid_chunks;
+      uint32_t dst = xs_u + static_cast<uint32_t>(buf * x_bytes + ld_c * 16 + ld_px0 * xrow);
+      const uint32_t dst_step = static_cast<uint32_t>(px_step * xrow);
+      const __half* tile_base = p.x + ((static_cast<size_t>(c.b) * im_h + y0) * im_w + x0) * x_cs + p.xoff + ld_c * 8;
+      for (int px = ld_px0; px < 128; px += px_step) {
+        const int r = px >> 4, xx = px & 15;
+        if (inside || (ld_c < valid_chunks && y0 + r < im_h && x0 + xx < im_w)) {
+          pk_cp_async_16(dst, tile_base + r * w_xcs + xx * x_cs);
+        } else {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");
+        }
+        dst += dst_step;
+      }
+    }
+    const bool src_inside = y0 >= PAD && x0 >= PAD && y0 + kPkTileH + PAD <= im_h && x0 + kPkTileW + PAD <= im_w;
+    const float* img = src_base + static_cast<size_t>(c.b) * im_h * im_w * src_cs;
+#pragma unroll
+    for (int it = 0; it < SRC_ITERS; ++it) {
+      if (src_ly[it] > -1000) {
+        int yy = y0 + src_ly[it], xx = x0 + src_lx[it];
+        if (!src_inside) { yy = pk_sym(yy, im_h); xx = pk_sym(xx, im_w); }
+        const float* sp = img + (static_cast<size_t>(yy) * im_w + xx) * src_cs;
+        const uint32_t dst = src_u + static_cast<uint32_t>((buf * SRC_ELEMS + tid + it * kPxThreads) * 16);
+        pk_cp_async_4(dst, sp); pk_cp_async_4(dst + 4, sp + 1); pk_cp_async_4(dst + 8, sp + 2);
+      }
+    }
+    pk_cp_async_commit();
+  };
+
+  int tile = blockIdx.x;
+  int buf = 0;
+  Coord cur;
+  cur.b = tile / tiles_per_image;
+  { const int rem = tile - cur.b * tiles_per_image; cur.ty = rem / p.tiles_x; cur.tx = rem - cur.ty * p.tiles_x; }
+  if (tile < p.total_tiles) issue_loads(cur, 0);
+  for (; tile < p.total_tiles; tile += gridDim.x, buf ^= 1) {
+    const int b = cur.b;
+    const int y0 = cur.ty * kPkTileH, x0 = cur.tx * kPkTileW;
+    advance(cur);                                          // cur = the NEXT tile of this CTA from here on
+    pk_cp_async_wait_all();
+    __syncthreads();                                       // this tile's data (and the weights) visible; the other buffer is free
+    if (tile + static_cast<int>(gridDim.x) < p.total_tiles) issue_loads(cur, buf ^ 1);   // in flight during the math below
+
+    // ---------------------------------------------------------------- GEMM 1: hidden = relu(x W1 + b1), two row blocks per warp
+    float acc[2][NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const float bl = b1s[j * 8 + 2 * t4], bh = b1s[j * 8 + 2 * t4 + 1];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) { acc[m][j][0] = bl; acc[m][j][1] = bh; acc[m][j][2] = bl; acc[m][j][3] = bh; }
+    }
+    const uint32_t a_base = xs_u + static_cast<uint32_t>(buf * x_bytes + (warp * 32 + a_row) * xrow + a_kof);
+    const uint32_t a_blk = static_cast<uint32_t>(16 * xrow);
+    for (int ks = 0; ks < p.Cpad / 16; ++ks) {
+      uint32_t a0[4], a1[4];
+      pk_ldmatrix_x4(a0, a_base + ks * 32);
+      pk_ldmatrix_x4(a1, a_base + a_blk + ks * 32);
+#pragma unroll
+      for (int j = 0; j < NT; j += 2) {
+        uint32_t bf[4];
+        pk_ldmatrix_x4(bf, w1_u + static_cast<uint32_t>((j * 8 + b_row) * w1row + ks * 32 + b_kof));
+        pk_mma(acc[0][j], a0, bf[0], bf[1]);
+        pk_mma(acc[0][j + 1], a0, bf[2], bf[3]);
+        pk_mma(acc[1][j], a1, bf[0], bf[1]);
+        pk_mma(acc[1][j + 1], a1, bf[2], bf[3]);
+      }
+    }
+    // ---------------------------------------------------------------- GEMM 2: logits = hidden W2 + b2 (then * log2 e)
+    float lg[2][NT][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) lg[m][j][e] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        a[m][0] = pk_pack_relu(acc[m][2 * kk][0], acc[m][2 * kk][1]);
+        a[m][1] = pk_pack_relu(acc[m][2 * kk][2], acc[m][2 * kk][3]);
+        a[m][2] = pk_pack_relu(acc[m][2 * kk + 1][0], acc[m][2 * kk + 1][1]);
+        a[m][3] = pk_pack_relu(acc[m][2 * kk + 1][2], acc[m][2 * kk + 1][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < NT; j += 2) {
+        uint32_t bf[4];
+        pk_ldmatrix_x4(bf, w2_u + static_cast<uint32_t>((j * 8 + b_row) * w2row + kk * 32 + b_kof));
+        pk_mma(lg[0][j], a[0], bf[0], bf[1]);
+        pk_mma(lg[0][j + 1], a[0], bf[2], bf[3]);
+        pk_mma(lg[1][j], a[1], bf[0], bf[1]);
+        pk_mma(lg[1][j + 1], a[1], bf[2], bf[3]);
+      }
+    }
+    // ---------------------------------------------------------------- logits -> [column][pixel] in the warp's own (consumed) x rows
+    __syncwarp();
+    float* st = reinterpret_cast<float*>(xs + buf * x_bytes + warp * 32 * xrow);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int c0 = j * 8 + 2 * t4;
+      const float bl = b2s[c0], bh = b2s[c0 + 1];            // already scaled by log2 e
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const int px = m * 16 + g;
+        st[c0 * kPxLgPitch + px] = fmaf(lg[m][j][0], 1.4426950408889634f, bl);
+        st[(c0 + 1) * kPxLgPitch + px] = fmaf(lg[m][j][1], 1.4426950408889634f, bh);
+        st[c0 * kPxLgPitch + px + 8] = fmaf(lg[m][j][2], 1.4426950408889634f, bl);
+        st[(c0 + 1) * kPxLgPitch + px + 8] = fmaf(lg[m][j][3], 1.4426950408889634f, bh);
+      }
+    }
+    __syncwarp();
+    // ---------------------------------------------------------------- softmax over K*K + filter apply: lane = pixel
+    {
+      const int r = warp * 2 + (lane >> 4), cx = lane & 15;
+      // three interleaved accumulator sets: one thread per pixel means 25-deep dependent chains otherwise
+      float l[K2];
+      float m3[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int k = 0; k < K2; ++k) { l[k] = st[k * kPxLgPitch + lane]; m3[k % 3] = fmaxf(m3[k % 3], l[k]); }
+      const float mx = fmaxf(fmaxf(m3[0], m3[1]), m3[2]);
+      const float4* tile_f = s_src + buf * SRC_ELEMS + r * TWs + cx;
+      float sum[3] = {0.f, 0.f, 0.f}, rr[3] = {0.f, 0.f, 0.f}, gg[3] = {0.f, 0.f, 0.f}, bb[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < K2; ++k) {
+        const float ev = pk_ex2(l[k] - mx);
+        const float4 sv = tile_f[(k / K) * TWs + (k % K)];
+        sum[k % 3] += ev;
+        rr[k % 3] = fmaf(ev, sv.x, rr[k % 3]); gg[k % 3] = fmaf(ev, sv.y, gg[k % 3]); bb[k % 3] = fmaf(ev, sv.z, bb[k % 3]);
+      }
+      const int y = y0 + r, x = x0 + cx;
+      if (y < im_h && x < im_w) {
+        const float inv = 1.f / (sum[0] + sum[1] + sum[2]);
+        float* o = out_base + ((static_cast<size_t>(b) * im_h + y) * im_w + x) * out_cs;
+        o[0] = (rr[0] + rr[1] + rr[2]) * inv; o[1] = (gg[0] + gg[1] + gg[2]) * inv; o[2] = (bb[0] + bb[1] + bb[2]) * inv;
+      }
+    }
+  }
+  pk_cp_async_wait_all();
+}
+
+// logits staged in the consumed x rows: 32 pixels x xrow bytes per warp must hold [O16][33] floats
+static bool post_kp_pixel_form(int cin, int ksize, int features) {
+  if (features != 1 || !(ksize == 3 || ksize == 5)) return false;
+  const int o16 = round_up(ksize * ksize, 16), cpad = round_up(cin, 16);
+  return 32 * (cpad * 2 + 16) >= o16 * kPxLgPitch * 4;
+}
+
+template <int K>
+static int launch_post_kp_pixel(dd_ctx* ctx, const PostKpParams& p, cudaStream_t s) {
+  constexpr int K2 = K * K, O16 = (K2 + 15) / 16 * 16, PAD = (K - 1) / 2;
+  const size_t smem = 2 * 128ull * (p.Cpad * 2 + 16) + static_cast<size_t>(O16) * (p.Cpad * 2 + 16) +
+                      static_cast<size_t>(O16) * (O16 * 2 + 16) + 2ull * O16 * sizeof(float) +
+                      2 * static_cast<size_t>(kPkTileH + 2 * PAD) * (kPkTileW + 2 * PAD) * sizeof(float4);
+  DD_CHECK_ARG(smem <= ctx->max_smem_optin, "post_kp: tile does not fit shared memory");
+  DD_CUDA(cudaFuncSetAttribute(post_kp_pixel_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  DD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, post_kp_pixel_kernel<K>, kPxThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  int grid = ctx->sm_count * per_sm;
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  post_kp_pixel_kernel<K><<<static_cast<unsigned>(grid), kPxThreads, smem, s>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
 template <int K, int T>
 static int launch_post_kp(dd_ctx* ctx, const PostKpParams& p, cudaStream_t s) {
   constexpr int K2 = K * K, O16 = T * ((K2 + 15) / 16 * 16), PAD = (K - 1) / 2;
@@ -367,9 +602,10 @@ int dd_post_kp_pack_weights(const float* w1, const float* b1, const float* w2, c
   // hidden unit c -> row (c / K2) * KP + c % K2;  logit c = (feature f, tap k) -> column f * KP + 8j + 2*t4 + e with
   // k = 4 * (2j + e) + t4 (the kernel's quad layout); padded logit columns get a bias of -inf (softmax weight 0)
   auto hid = [&](int c) { return (c / k2) * kp + c % k2; };
+  const bool pixel_form = post_kp_pixel_form(cin, ksize, features);     // one thread per pixel: logit column = tap
   auto col = [&](int c) {
     const int f = c / k2, k = c % k2, slot = k / 4, t4 = k % 4;
-    return f * kp + 8 * (slot / 2) + 2 * t4 + (slot % 2);
+    return pixel_form ? f * kp + k : f * kp + 8 * (slot / 2) + 2 * t4 + (slot % 2);
   };
   for (int c = 0; c < cin; ++c)
     for (int n = 0; n < o; ++n) w1t[static_cast<size_t>(hid(n)) * cpad + c] = __float2half_rn(w1[static_cast<size_t>(c) * o + n]);
@@ -405,6 +641,8 @@ int dd_post_kp_fwd(dd_ctx* ctx, const dd_tensor* x, const void* blob_dev, const 
   while ((1 << p.cp_shift) < p.Cpad / 8) ++p.cp_shift;
   DD_CHECK_ARG(p.cp_shift <= 7, "post_kp: at most 1024 input channels");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (post_kp_pixel_form(x->c, ksize, features))       // must mirror dd_post_kp_pack_weights (the column order of W2 differs)
+    return ksize == 5 ? launch_post_kp_pixel<5>(ctx, p, s) : launch_post_kp_pixel<3>(ctx, p, s);
   if (ksize == 5 && features == 1) return launch_post_kp<5, 1>(ctx, p, s);
   if (ksize == 5 && features == 3) return launch_post_kp<5, 3>(ctx, p, s);
   if (ksize == 3 && features == 1) return launch_post_kp<3, 1>(ctx, p, s);
