@@ -205,7 +205,7 @@ def l1_of(out, want):
 def hbm_rooflines(arch, pk):
   """HBM-bound kernels of the kernel-prediction apply at 1080p (KernelPrediction.py:22-61), timed alone with CUDA events,
   L2 flushed between repetitions (inputs of one launch are > 126 MB anyway):
-    post_kp_fused_kernel<5>   fused 1x1 post-process x2 + softmax + 5x5 apply of 8 x 1080p tuple passes; algorithmic bytes/px
+    post_kp_pixel_kernel<5>   fused 1x1 post-process x2 + softmax + 5x5 apply of 8 x 1080p tuple passes; algorithmic bytes/px
                               = 2*64 (fp16 backbone features) + 12 (source) + 12 (prediction) = 152
     kernel_predict_tma_kernel K = 21 apply on materialised fp32 logits (the cfg3 / Tiramisu head): 441*4 + 12 + 12 B/px"""
   from deepdenoiser_b200 import _lib
@@ -235,7 +235,7 @@ def hbm_rooflines(arch, pk):
     fn()
     ms = timed(fn)
     b = n * HEIGHT * WIDTH * 152.0
-    out["post_kp_fused_k5"] = {"bound": "hbm", "kernel": "post_kp_fused_kernel<5,1> (1x1 post-process x2 + softmax + 5x5 apply), 8 x 1080p",
+    out["post_kp_fused_k5"] = {"bound": "hbm", "kernel": "post_kp_pixel_kernel<5> (1x1 post-process x2 + softmax + 5x5 apply, dd_post_kp_fwd), 8 x 1080p",
                                "bytes": b, "ms": ms, "achieved": b / ms / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                "frac": b / ms / 1e6 / pk["hbm_gbs"]}
     del feat

@@ -20,7 +20,7 @@ if [[ $what == all || $what == ncu ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_rows -s 2 -c 3 \
       -o gpurun_out/prof_conv -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-train > gpurun_out/ncu_full.log 2>&1
   tail -2 gpurun_out/ncu_full.log
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"post_kp_fused|compose_rows" -s 6 -c 4 \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"post_kp_|compose_rows" -s 6 -c 4 \
       -o gpurun_out/prof_image -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-train > gpurun_out/ncu_full2.log 2>&1
   tail -2 gpurun_out/ncu_full2.log
   ls -la gpurun_out
