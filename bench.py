@@ -203,8 +203,8 @@ def l1_of(out, want):
 
 
 def hbm_rooflines(arch, pk):
-  """HBM-bound kernels of the kernel-prediction apply at 1080p (KernelPrediction.py:22-61), timed alone with CUDA events,
-  L2 flushed between repetitions (inputs of one launch are > 126 MB anyway):
+  """HBM-bound kernels of the kernel-prediction apply at 1080p (KernelPrediction.py:22-61), timed alone with CUDA events
+  (inputs of one launch are 2-7 GB, far larger than L2):
     post_kp_pixel_kernel<5>   fused 1x1 post-process x2 + softmax + 5x5 apply of 8 x 1080p tuple passes; algorithmic bytes/px
                               = 2*64 (fp16 backbone features) + 12 (source) + 12 (prediction) = 152
     kernel_predict_tma_kernel K = 21 apply on materialised fp32 logits (the cfg3 / Tiramisu head): 441*4 + 12 + 12 B/px"""
@@ -215,14 +215,19 @@ def hbm_rooflines(arch, pk):
   flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
   def timed(fn, reps=5):
-    ms = []
-    for _ in range(reps + 1):
-      ctx.l2_flush(flush)
-      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-      e0.record(); fn(); e1.record()
-      torch.cuda.synchronize()
-      ms.append(e0.elapsed_time(e1))
-    return float(np.mean(ms[1:]))
+    # `reps` launches back to back between one pair of events: every launch streams 2-7 GB, far more than the 126 MB L2, so
+    # nothing is reused between repetitions; a single launch between events would also time the host's launch path (~0.1-0.2 ms
+    # of Python / ctypes per call against a ~1 ms kernel)
+    fn()
+    ctx.l2_flush(flush)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+      fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
 
   n = 8
   g = torch.Generator(device=dev).manual_seed(5)
@@ -534,6 +539,9 @@ def main():
     config = {"workload": "configs[2] network, inference: Tiramisu [64,96,128]x4 KPCN K=21, 32-ch render-pass stack, 1920x1080 "
                           "frame, batch 1, SINGLE tuples (17 passes/frame), 3 scales", "height": HEIGHT, "width": WIDTH,
               "input_channels": 32, "kernel_size": 21}
+  # timing rule: no L2 flush between timed frames - one frame streams 514 MB of inputs and ~15 GB of intermediates through a
+  # 126 MB L2, nothing of frame i survives into frame i+1 (same key in both arms so that the configs stay identical)
+  config["l2"] = "inputs larger than L2 (514 MB of sources, ~15 GB of intermediates per frame vs 126 MB); no flush between frames"
   if args.impl == "reference":
     run_reference(args, arch_json, weights, config)
   else:

@@ -61,6 +61,7 @@ SIGNATURES = {
     "dd_conv2d_fwd": (_i, [_vp, _T, _vp, _vp, _i, _u32, _T, _T, _T, _vp]),
     "dd_conv2d_transpose2x2_fwd": (_i, [_vp, _T, _vp, _vp, _u32, _T, _vp]),
     "dd_conv2d_fwd_split": (_i, [_vp, _T, _T, _vp, _vp, _i, _u32, _T, _T, _vp]),
+    "dd_conv2d_fwd_colsum": (_i, [_vp, _T, _vp, _vp, _i, _u32, _T, _T, _vp, _vp]),
     "dd_conv2d_transpose2x2_fwd_split": (_i, [_vp, _T, _T, _vp, _vp, _u32, _T, _T, _vp]),
     "dd_maxpool_s2_fwd_split": (_i, [_vp, _T, _T, _i, _T, _T, _vp]),
     "dd_assemble_input_split": (_i, [_vp, _vp, _i, _i, _T, _T, _vp]),
@@ -227,9 +228,15 @@ class Context:
                                                 packed.data_ptr(), self._stream()))
     return packed
 
-  def conv2d(self, x, w_packed, bias, ksize, y, relu=False, residual=None, y_relu=None, residual_is_mask=False):
+  def conv2d(self, x, w_packed, bias, ksize, y, relu=False, residual=None, y_relu=None, residual_is_mask=False, colsum=None):
     flags = ((DD_CONV_RELU if relu else 0) | (DD_CONV_RELU_COPY if y_relu is not None else 0) |
              (DD_CONV_RESIDUAL_MASK if residual_is_mask else 0))
+    if colsum is not None:       # fp32 device tensor: column sums of y are accumulated into it (fused BiasAddGrad)
+      assert y_relu is None
+      self._check(self.lib.dd_conv2d_fwd_colsum(
+          self.handle, ctypes.byref(x), w_packed.data_ptr(), bias.data_ptr() if bias is not None else None, ksize, flags,
+          ctypes.byref(residual) if residual is not None else None, ctypes.byref(y), colsum.data_ptr(), self._stream()))
+      return
     self._check(self.lib.dd_conv2d_fwd(
         self.handle, ctypes.byref(x), w_packed.data_ptr(), bias.data_ptr() if bias is not None else None, ksize,
         flags, ctypes.byref(residual) if residual is not None else None, ctypes.byref(y),

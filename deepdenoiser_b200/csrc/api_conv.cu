@@ -130,6 +130,7 @@ struct TcLaunch {
   int s_mask, rm_lo, rm_hi; // tap subset (3x3 only); s_mask == 0 -> all
   const dd_tensor* x_lo;    // split-fp16 mode: low halves of the input (same shape as x) / of the 16-bit output
   const dd_tensor* y_lo;
+  float* colsum;            // optional column sums of the output (device, fp32, accumulated), see ConvRowsParams
 };
 
 // view of `t` seen through a stride-`ups` sub-pixel lattice starting at (ay, ax)
@@ -212,7 +213,8 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
   p.b_tile_bytes = static_cast<uint32_t>(n_r * p.cpad) * 128u;
   p.b_tx_bytes = p.b_tile_bytes;
   const size_t stage_bytes = static_cast<size_t>(kRowsEpiWarps) * 4096;   // one 4 KB staging row set per epilogue warp
-  const size_t fixed = stage_bytes + 1024 /*bias*/ + 3072 /*barriers + MMA plans*/;
+  const size_t colsum_bytes = L.colsum ? static_cast<size_t>(kRowsEpiWarps) * 128 * sizeof(float) : 0;   // per-warp column sums
+  const size_t fixed = stage_bytes + 1024 /*bias*/ + 3072 /*barriers + MMA plans*/ + colsum_bytes;
   const size_t avail = ctx->max_smem_optin - 1024 /*alignment slack*/ - fixed;
   const size_t w_total = static_cast<size_t>(w_chunks) * p.n_s * p.b_tile_bytes;
   size_t b_bytes;
@@ -251,7 +253,7 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
   p.stage_off = p.b_off + static_cast<uint32_t>(round_up(static_cast<int>(b_bytes), 1024));
   p.bias_off = p.stage_off + static_cast<uint32_t>(stage_bytes);
   p.bar_off = p.bias_off + 1024;
-  const size_t smem = 1024 + p.bar_off + 3072;
+  const size_t smem = 1024 + p.bar_off + 3072 + colsum_bytes;
 
   // epilogue
   p.ngroups = L.ngroups; p.group_c = L.group_c; p.cout_store = L.cout; p.ups = L.ups;
@@ -322,7 +324,11 @@ static int launch_conv_rows(dd_ctx* ctx, const TcLaunch& L, cudaStream_t stream)
     if (rc) return rc;
   }
 
-  p.epi_plain = (!p.out_f32 && !p.residual && !p.has_relu_copy && !p.split_out) ? 1 : 0;
+  if (L.colsum) {
+    DD_CHECK_ARG(L.ngroups == 1 && L.cout <= 128 && !p.split, "column sums: plain convolution slices of at most 128 channels");
+    p.colsum = L.colsum;
+  }
+  p.epi_plain = (!p.out_f32 && !p.residual && !p.has_relu_copy && !p.split_out && !p.colsum) ? 1 : 0;
 
   int grid = ctx->sm_count;
   if (p.total_rows < grid) grid = static_cast<int>(p.total_rows);
@@ -497,7 +503,7 @@ int dd_conv2d_pack_weights(dd_ctx* ctx, const float* w, int ksize, int cin, int 
 
 static int conv2d_fwd_impl(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* x_lo, const void* w_packed, const float* bias,
                            int ksize, uint32_t flags, const dd_tensor* residual, const dd_tensor* y, const dd_tensor* y_lo,
-                           const dd_tensor* y_relu, void* stream) {
+                           const dd_tensor* y_relu, void* stream, float* colsum = nullptr) {
   DD_CHECK_ARG(ctx && w_packed, "NULL argument");
   DD_CHECK_ARG(tensor_ok(x) && tensor_ok(y), "bad tensor descriptor");
   DD_CHECK_ARG(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
@@ -509,6 +515,7 @@ static int conv2d_fwd_impl(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* x_l
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (x->dtype == DD_F32) {
     DD_CHECK_ARG(y->dtype == DD_F32, "exact path writes fp32");
+    DD_CHECK_ARG(!colsum, "column sums are fused on the 16-bit tensor-core path only");
     return launch_conv_simt(ctx, x, reinterpret_cast<const float*>(w_packed), bias, ksize, y->c, flags, residual, y,
                             y_relu, 1, 0, 0, s);
   }
@@ -535,6 +542,7 @@ static int conv2d_fwd_impl(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* x_l
     L.flags = flags; L.residual = residual ? &rs : nullptr; L.y = &ys; L.y_relu = y_relu ? &yr : nullptr;
     L.ups = 1; L.sp0 = 0; L.s_mask = 0; L.rm_lo = 0; L.rm_hi = 2;
     L.x_lo = x_lo; L.y_lo = y_lo ? &yl : nullptr;
+    L.colsum = colsum ? colsum + row0 : nullptr;
     int rc = launch_conv_rows(ctx, L, s);
     if (rc) return rc;
   }
@@ -544,6 +552,12 @@ static int conv2d_fwd_impl(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* x_l
 int dd_conv2d_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const float* bias, int ksize, uint32_t flags,
                   const dd_tensor* residual, const dd_tensor* y, const dd_tensor* y_relu, void* stream) {
   return conv2d_fwd_impl(ctx, x, nullptr, w_packed, bias, ksize, flags, residual, y, nullptr, y_relu, stream);
+}
+
+int dd_conv2d_fwd_colsum(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const float* bias, int ksize, uint32_t flags,
+                         const dd_tensor* residual, const dd_tensor* y, float* colsum_dev, void* stream) {
+  DD_CHECK_ARG(colsum_dev, "colsum_dev is NULL");
+  return conv2d_fwd_impl(ctx, x, nullptr, w_packed, bias, ksize, flags, residual, y, nullptr, nullptr, stream, colsum_dev);
 }
 
 int dd_conv2d_fwd_split(dd_ctx* ctx, const dd_tensor* x_hi, const dd_tensor* x_lo, const void* w_packed, const float* bias,

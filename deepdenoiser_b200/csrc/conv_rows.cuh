@@ -87,6 +87,8 @@ struct ConvRowsParams {
   // store, 2 epilogue skips the TMEM load too, 4 no UMMAs are issued, 8 every A load fetches input row 0 of image 0 (L2 hits),
   // 16 only the first k-step of every (chunk, shift) is issued
   int dbg;
+  float* colsum;          // optional: colsum[c] += sum over all pixels of the primary output (fp32, before the 16-bit rounding):
+                          // BiasAddGrad fused into the input-gradient convolution of the tensor-core training path
   int epi_plain;          // one 16-bit output, optional ReLU, no residual / mask / relu copy / split output: the compact epilogue
 };
 
@@ -673,6 +675,15 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
     // output row number q (running) lives in block ring-1-(q % ring), use q / ring, and belongs to set q % n_sets: maintained
     // incrementally (three integer divisions per row otherwise)
     int blk_next = ring_i - 1, set_next = 0; uint32_t par_next = 0;
+    // fused column sums (BiasAddGrad): a private [128] accumulator per epilogue warp in shared memory (behind the barrier /
+    // plan area, allocated by the host only when p.colsum is set): no registers are held across rows for it
+    float* const cs_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 3072) + warp * 128;
+    const bool has_colsum = !SPLIT && pin(p.colsum != nullptr ? 1 : 0, scr) != 0;
+    if (has_colsum) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cs_smem[i * 32 + lane] = 0.f;
+      __syncwarp();
+    }
     while (walk.next(sg)) {
       for (int j = sg.y0; j < sg.y1; ++j, ++it) {
         const int blk = blk_next; const uint32_t par = par_next; const bool mine = (set_next == eset);
@@ -865,6 +876,26 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
                 }
                 if (sub == 1 || cb + 32 >= p.cout_store) end_rows(omap, cb & ~63);
               }
+              if (has_colsum && pass == 0) {
+                // column sums of this 32-pixel x 32-channel block: a transpose-reduce over the warp (31 shuffles: in round
+                // `half` a lane keeps the half of its values whose channel bit matches its lane bit and receives the partner's
+                // partial sums for them), lane L ends with the sum of channel cb + L
+                // (in place, after the block has been staged for the store: f is dead afterwards)
+                const bool live = x_in < p.W;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = live ? f[i] : 0.f;
+#pragma unroll
+                for (int half = 16; half >= 1; half >>= 1) {
+                  const bool up = (lane & half) != 0;
+#pragma unroll
+                  for (int i = 0; i < half; ++i) {
+                    const float send = up ? f[i] : f[i + half];
+                    const float keep = up ? f[i + half] : f[i];
+                    f[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+                  }
+                }
+                cs_smem[cb + lane] += f[0];
+              }
             }
           }
         }
@@ -874,6 +905,12 @@ conv_rows_kernel(const __grid_constant__ ConvRowsMaps maps, const ConvRowsParams
     }
     if (lane == 0) tma_store_wait_all();
     __syncwarp();
+    if (has_colsum) {
+      const int cout = p.cout_store;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i * 32 + lane < cout) atomicAdd(p.colsum + i * 32 + lane, cs_smem[i * 32 + lane]);
+    }
   }
 
   tc_fence_before();

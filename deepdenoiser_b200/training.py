@@ -423,8 +423,9 @@ class Trainer:
       ctx.call("dd_conv2d_wgrad_tc", _b(x.d), _b(dz.d), var.ksize, 0, _fp(self.param_grad(var.kernel_name)), ctypes.c_float(1.0))
       if i > 0:
         dz_prev = self._act("%s.dz%d" % (key, i - 1), tuple(x.t.shape[:3]), var.cin)
-        ctx.conv2d(dz.d, self.bwd[var.name], None, var.ksize, dz_prev.d, residual=x.d, residual_is_mask=True)
-        ctx.call("dd_relu_bwd_bias", _b(dz_prev.d), None, None, _fp(self.param_grad(layers[i - 1].bias_name)), ctypes.c_float(1.0))
+        # input gradient + ReLU mask of layer i-1 + its bias gradient (column sums of dz_prev) in one launch
+        ctx.conv2d(dz.d, self.bwd[var.name], None, var.ksize, dz_prev.d, residual=x.d, residual_is_mask=True,
+                   colsum=self.param_grad(layers[i - 1].bias_name))
         dz = dz_prev
       else:
         dx = self._act("%s.dx0" % key, tuple(x.t.shape[:3]), var.cin)

@@ -93,6 +93,13 @@ int dd_conv2d_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const f
                   uint32_t flags, const dd_tensor* residual, const dd_tensor* y, const dd_tensor* y_relu,
                   void* stream);
 
+/* dd_conv2d_fwd on the 16-bit tensor-core path that also accumulates colsum_dev[c] += sum over all pixels of y[.., c] (fp32,
+ * from the values before the 16-bit rounding).  With DD_CONV_RESIDUAL_MASK this is the input-gradient convolution of layer i
+ * fused with the ReLU backward AND the BiasAddGrad of layer i-1 (Training.py:700-702 delegates both to TensorFlow's autodiff):
+ * the separate read-only pass over the gradient tensor disappears. */
+int dd_conv2d_fwd_colsum(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const float* bias, int ksize,
+                         uint32_t flags, const dd_tensor* residual, const dd_tensor* y, float* colsum_dev, void* stream);
+
 /* y = relu?(conv2d_transpose(x, W, k=2, stride=2, 'same') + b): y[2i+a,2j+b,o] = sum_c x[i,j,c] W[a,b,o,c].
  * Replaces tf.layers.conv2d_transpose at UNet.py:56-58. */
 int dd_conv2d_transpose2x2_fwd(dd_ctx* ctx, const dd_tensor* x, const void* w_packed, const float* bias,

@@ -297,3 +297,26 @@ def test_maxpool_backward_gather_matches_the_scatter_form(ctx, dtype, k, h, w):
   ctx.call("dd_maxpool_s2_bwd_acc", _b(_lib.desc(x)), _b(_lib.desc(y)), _b(_lib.desc(dy)), k, _b(_lib.desc(got)))
   torch.cuda.synchronize()
   assert torch.equal(got.float(), base.float() + want)
+
+
+@pytest.mark.parametrize("cin,cout,n,h,w", [(64, 64, 2, 13, 300), (96, 128, 1, 9, 130), (128, 24, 1, 10, 64)])
+def test_dgrad_conv_with_fused_mask_and_bias_gradient(ctx, cin, cout, n, h, w):
+  """dd_conv2d_fwd_colsum with DD_CONV_RESIDUAL_MASK: the masked output equals the plain fused-mask launch bit for bit and the
+  accumulated column sums equal the sum over all pixels of that output (the BiasAddGrad of the layer below)."""
+  x = torch.randn(n, h, w, cin, device="cuda").bfloat16()
+  mask = torch.randn(n, h, w, cout, device="cuda").bfloat16()
+  wt = torch.randn(3, 3, cin, cout, device="cuda") * 0.1
+  pb = torch.zeros(ctx.lib.dd_conv2d_packed_bytes(3, cin, cout, _lib.DD_BF16, 0), dtype=torch.uint8, device="cuda")
+  ctx.call("dd_conv2d_pack_weights_dev", _fp(wt), 3, cin, cout, 0 | _lib.DD_PACK_BF16, _fp(pb))
+  plain = torch.empty(n, h, w, cout, device="cuda", dtype=torch.bfloat16)
+  fused = torch.empty_like(plain)
+  ctx.conv2d(_lib.desc(x), pb, None, 3, _lib.desc(plain), residual=_lib.desc(mask), residual_is_mask=True)
+  base = torch.randn(cout, device="cuda")
+  db = base.clone()
+  ctx.conv2d(_lib.desc(x), pb, None, 3, _lib.desc(fused), residual=_lib.desc(mask), residual_is_mask=True, colsum=db)
+  torch.cuda.synchronize()
+  assert torch.equal(fused, plain)
+  # reference sum from fp32 arithmetic on the same bf16 operands (the kernel sums before the 16-bit rounding)
+  ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.bfloat16().float().permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)
+  want = (ref * (mask.float() > 0)).sum(dim=(0, 1, 2))
+  assert rel_err(db - base, want) <= 2e-3
