@@ -103,6 +103,8 @@ SIGNATURES = {
     "dd_conv2d_repack_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "dd_maxpool_s2_bwd": (_i, [_vp, _T, _T, _T, _i, _T, _vp]),
     "dd_maxpool_s2_bwd_acc": (_i, [_vp, _T, _T, _T, _i, _T, _vp]),
+    "dd_maxpool_s2_fwd_index": (_i, [_vp, _T, _i, _T, _vp, _vp]),
+    "dd_maxpool_s2_bwd_index": (_i, [_vp, _vp, _T, _i, _T, _vp]),
     "dd_kernel_predict_bwd": (_i, [_vp, _T, _T, _T, _i, _i, _i, _T, _vp]),
     "dd_compose_tail_bwd": (_i, [_vp, _T, _vp, _vp, _i, _T, _T, _T, _T, _T, _T, _vp, _vp, _vp]),
     "dd_compose_head_bwd": (_i, [_vp, _T, _T, _vp, _i, _T, _T, _T, _T, _vp, _vp, _vp]),

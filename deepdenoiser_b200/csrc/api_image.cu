@@ -85,6 +85,44 @@ __global__ void __launch_bounds__(256) maxpool_h8_kernel(const PoolParams p) {
   *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.y.ptr) + opix * p.y.cstride + p.y.coff + c) = o;
 }
 
+// Training form: also records WHICH element of the window is the (first) maximum - one byte per (window, channel), r * k + s -
+// so that the backward pass is a pure gather (maxpool_bwd_index_kernel in api_train.cu) instead of re-deriving the first maximum
+// of up to four windows per input pixel.
+__global__ void __launch_bounds__(256) maxpool_h8_index_kernel(const PoolParams p, uint8_t* __restrict__ index) {
+  const int cv = p.y.c / 8;
+  const size_t total = static_cast<size_t>(p.y.n) * p.y.h * p.y.w * cv;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % cv) * 8;
+  const size_t opix = idx / cv;
+  const int ox = static_cast<int>(opix % p.y.w);
+  const int oy = static_cast<int>((opix / p.y.w) % p.y.h);
+  const int n = static_cast<int>(opix / (static_cast<size_t>(p.y.w) * p.y.h));
+  const uint16_t* xin = reinterpret_cast<const uint16_t*>(p.x.ptr);
+  float m[8]; uint32_t arg[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { m[i] = -INFINITY; arg[i] = 255u; }
+  for (int r = 0; r < p.ksize; ++r) {
+    const int yy = 2 * oy - p.pad_y + r;
+    if (yy < 0 || yy >= p.x.h) continue;
+    for (int s = 0; s < p.ksize; ++s) {
+      const int xx = 2 * ox - p.pad_x + s;
+      if (xx < 0 || xx >= p.x.w) continue;
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(xin + p.x.pix(n, yy, xx) * p.x.cstride + p.x.coff + c)), p.x.bf16, v);
+      const uint32_t code = static_cast<uint32_t>(r * p.ksize + s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (arg[i] == 255u || v[i] > m[i]) { m[i] = v[i]; arg[i] = code; }     // first maximum in scan order (TF MaxPoolGrad)
+    }
+  }
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.y.ptr) + opix * p.y.cstride + p.y.coff + c) = pack8(m, p.y.bf16);
+  uint2 packed;
+  packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+  packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+  *reinterpret_cast<uint2*>(index + opix * p.y.c + c) = packed;
+}
+
 // split-fp16 pairs (x = hi + lo, the "float16x2" mode): the maximum is taken on the fp32 sums and re-split exactly
 __global__ void __launch_bounds__(256) maxpool_split_kernel(const PoolParams p, const View xlo, const View ylo) {
   const int cv = p.y.c / 8;
@@ -392,6 +430,23 @@ int dd_maxpool_s2_fwd(dd_ctx* ctx, const dd_tensor* x, int ksize, const dd_tenso
     const size_t total = static_cast<size_t>(y->n) * y->h * y->w * y->c;
     maxpool_generic_kernel<<<blocks_for(total, 256), 256, 0, s>>>(p);
   }
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_maxpool_s2_fwd_index(dd_ctx* ctx, const dd_tensor* x, int ksize, const dd_tensor* y, uint8_t* index_dev, void* stream) {
+  DD_CHECK_ARG(ctx && tensor_ok(x) && tensor_ok(y) && index_dev, "bad argument");
+  DD_CHECK_ARG(ksize == 2 || ksize == 3, "maxpool ksize must be 2 or 3");
+  const int oh = (x->h + 1) / 2, ow = (x->w + 1) / 2;
+  DD_CHECK_ARG(y->n == x->n && y->h == oh && y->w == ow && y->c == x->c, "maxpool: bad output dims");
+  DD_CHECK_ARG(is_half_type(x->dtype) && y->dtype == x->dtype && x->c % 8 == 0 && x->coff % 8 == 0 && x->cstride % 8 == 0 &&
+                   y->coff % 8 == 0 && y->cstride % 8 == 0, "maxpool_index: fp16 / bf16 views with multiples of 8 channels expected");
+  PoolParams p;
+  p.x = make_view(x); p.y = make_view(y); p.ksize = ksize;
+  const int pty = (oh - 1) * 2 + ksize - x->h, ptx = (ow - 1) * 2 + ksize - x->w;
+  p.pad_y = (pty > 0 ? pty : 0) / 2; p.pad_x = (ptx > 0 ? ptx : 0) / 2;
+  const size_t total = static_cast<size_t>(y->n) * y->h * y->w * (y->c / 8);
+  maxpool_h8_index_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, index_dev);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }

@@ -477,6 +477,54 @@ __global__ void __launch_bounds__(256) maxpool_bwd_gather_kernel(const PoolBwdPa
   *reinterpret_cast<uint4*>(dst) = pack8(d, bf);
 }
 
+// Index form: the forward pass (dd_maxpool_s2_fwd_index) recorded the first maximum of every window, so an input pixel only
+// compares its position inside each of its <= 4 windows with the recorded byte: 8 + 16 bytes per window instead of up to nine
+// 16-byte activation loads (the gather form above spent 3.2 ms per full-resolution level of a cfg5 step on its tie-break scans).
+__global__ void __launch_bounds__(256) maxpool_bwd_index_kernel(const PoolBwdParams p, const uint8_t* __restrict__ index) {
+  const int cv = p.dx.c / 8;
+  const size_t total = static_cast<size_t>(p.dx.n) * p.dx.h * p.dx.w * cv;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % cv) * 8;
+  const size_t ipix = idx / cv;
+  const int xx = static_cast<int>(ipix % p.dx.w);
+  const int yy = static_cast<int>((ipix / p.dx.w) % p.dx.h);
+  const int n = static_cast<int>(ipix / (static_cast<size_t>(p.dx.w) * p.dx.h));
+  const int bf = p.dx.bf16, k = p.ksize;
+  const uint16_t* gin = reinterpret_cast<const uint16_t*>(p.dy.ptr);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  int oy_lo = yy + p.pad_y - k + 1; oy_lo = oy_lo <= 0 ? 0 : (oy_lo + 1) >> 1;
+  int oy_hi = (yy + p.pad_y) >> 1; if (oy_hi > p.dy.h - 1) oy_hi = p.dy.h - 1;
+  int ox_lo = xx + p.pad_x - k + 1; ox_lo = ox_lo <= 0 ? 0 : (ox_lo + 1) >> 1;
+  int ox_hi = (xx + p.pad_x) >> 1; if (ox_hi > p.dy.w - 1) ox_hi = p.dy.w - 1;
+  for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+      const size_t op = p.dy.pix(n, oy, ox);
+      const uint32_t code = static_cast<uint32_t>((yy - (2 * oy - p.pad_y)) * k + (xx - (2 * ox - p.pad_x)));
+      const uint2 a = __ldg(reinterpret_cast<const uint2*>(index + op * p.dy.c + c));
+      const uint32_t want = code * 0x01010101u;
+      const uint32_t e0 = a.x ^ want, e1 = a.y ^ want;               // a zero byte = this pixel is the window's first maximum
+      if ((((e0 - 0x01010101u) & ~e0) | ((e1 - 0x01010101u) & ~e1)) & 0x80808080u) {
+        float g[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(gin + op * p.dy.cstride + p.dy.coff + c)), bf, g);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (((e0 >> (8 * i)) & 255u) == 0u) acc[i] += g[i];
+          if (((e1 >> (8 * i)) & 255u) == 0u) acc[4 + i] += g[4 + i];
+        }
+      }
+    }
+  }
+  uint16_t* dst = reinterpret_cast<uint16_t*>(p.dx.ptr) + ipix * p.dx.cstride + p.dx.coff + c;
+  float d[8];
+  unpack8(*reinterpret_cast<const uint4*>(dst), bf, d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] += acc[i];
+  *reinterpret_cast<uint4*>(dst) = pack8(d, bf);
+}
+
 // ------------------------------------------------------------------------------------------------ kernel prediction backward
 // dlogits_k = p_k (G_k - sum_c g_c out_c),  G_k = sum_c g_c S_c[k],  p = softmax(logits)        (no gradient to the source: it is data)
 struct KpBwdParams { View src, logits, dout, dlogits; int K, F, ipt; };
@@ -1055,6 +1103,25 @@ int dd_maxpool_s2_bwd_acc(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, c
   p.pad_y = (pty > 0 ? pty : 0) / 2; p.pad_x = (ptx > 0 ? ptx : 0) / 2;
   const size_t total = static_cast<size_t>(x->n) * x->h * x->w * (x->c / 8);
   maxpool_bwd_gather_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+int dd_maxpool_s2_bwd_index(dd_ctx* ctx, const uint8_t* index_dev, const dd_tensor* dy, int ksize, const dd_tensor* dx, void* stream) {
+  DD_CHECK_ARG(ctx && index_dev && tensor_ok(dy) && tensor_ok(dx), "bad argument");
+  DD_CHECK_ARG(ksize == 2 || ksize == 3, "maxpool ksize must be 2 or 3");
+  const dd_tensor* both[2] = {dy, dx};
+  for (const dd_tensor* t : both)
+    DD_CHECK_ARG(t->dtype == dx->dtype && is_half_type(t->dtype) && t->c % 8 == 0 && t->coff % 8 == 0 && t->cstride % 8 == 0,
+                 "maxpool_bwd_index: fp16 / bf16 views with multiples of 8 channels expected");
+  const int oh = (dx->h + 1) / 2, ow = (dx->w + 1) / 2;
+  DD_CHECK_ARG(dy->h == oh && dy->w == ow && dy->n == dx->n && dy->c == dx->c, "maxpool_bwd_index: pooled dims");
+  PoolBwdParams p;
+  p.x = make_view(dx); p.y = make_view(dy); p.dy = make_view(dy); p.dx = make_view(dx); p.ksize = ksize;
+  const int pty = (oh - 1) * 2 + ksize - dx->h, ptx = (ow - 1) * 2 + ksize - dx->w;
+  p.pad_y = (pty > 0 ? pty : 0) / 2; p.pad_x = (ptx > 0 ? ptx : 0) / 2;
+  const size_t total = static_cast<size_t>(dx->n) * dx->h * dx->w * (dx->c / 8);
+  maxpool_bwd_index_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, index_dev);
   DD_LAUNCH_CHECK(ctx);
   return DD_OK;
 }

@@ -344,8 +344,14 @@ class Trainer:
       skip = V(cat, f[i], 0)
       block("d%d" % i, spec.down[i], x, skip)
       pooled = self._act("pool%d" % i, (b, dims[i + 1][0], dims[i + 1][1]), f[i])
-      ctx.maxpool_s2(skip.d, 3, pooled.d)
-      tape["pools"].append((skip, pooled))
+      if self.mixed and f[i] % 8 == 0:
+        # the forward pass records the first maximum of every window (one byte per window and channel): pure-gather backward
+        idx = self._buf("pool%d.index" % i, (b, dims[i + 1][0], dims[i + 1][1], f[i]), dtype=torch.uint8)
+        ctx.call("dd_maxpool_s2_fwd_index", _b(skip.d), 3, _b(pooled.d), _fp(idx))
+      else:
+        idx = None
+        ctx.maxpool_s2(skip.d, 3, pooled.d)
+      tape["pools"].append((skip, pooled, idx))
       x = pooled
     results = []
     for i in range(steps):
@@ -474,10 +480,12 @@ class Trainer:
         dcat[index] = dx                                             # block u_index consumed cat_index
     # encoder: pooling + down blocks from coarse to fine
     for i in reversed(range(steps)):
-      skip, pooled = tape["pools"][i]
+      skip, pooled, idx = tape["pools"][i]
       dskip = V(dcat[i].t, f[i], 0)                                  # [:f] half, written by the concat consumer
-      if self.mixed:
-        # gather form: adds into the 16-bit concat gradient in place (no atomics, no fp32 scratch tensor)
+      if idx is not None:
+        # gather by the recorded index: adds into the 16-bit concat gradient in place (no atomics, no fp32 scratch tensor)
+        ctx.call("dd_maxpool_s2_bwd_index", _fp(idx), _b(dpool.d), 3, _b(dskip.d))
+      elif self.mixed:
         ctx.call("dd_maxpool_s2_bwd_acc", _b(skip.d), _b(pooled.d), _b(dpool.d), 3, _b(dskip.d))
       else:
         ctx.call("dd_maxpool_s2_bwd", _b(skip.d), _b(pooled.d), _b(dpool.d), 3, _b(dskip.d))

@@ -315,6 +315,11 @@ int dd_conv2d_repack_f32(dd_ctx* ctx, const float* w_dev, int ksize, int cin, in
 /* backward of dd_maxpool_s2_fwd: dx (fp32, pre-zeroed or accumulating) += dy routed to the first maximum of each window. */
 int dd_maxpool_s2_bwd(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, const dd_tensor* dy, int ksize, const dd_tensor* dx,
                       void* stream);
+/* Training pair for 16-bit tensors: the forward pass also records the first maximum of every window (index_dev: one byte per
+ * (window, channel), [n, oh, ow, c] dense, value r * ksize + s), the backward pass adds dy to dx (in place, 16-bit) where a pixel
+ * is the recorded maximum of a window - a pure gather.  tf.layers.max_pooling2d's gradient (UNet.py:42-44 under Training.py:700). */
+int dd_maxpool_s2_fwd_index(dd_ctx* ctx, const dd_tensor* x, int ksize, const dd_tensor* y, uint8_t* index_dev, void* stream);
+int dd_maxpool_s2_bwd_index(dd_ctx* ctx, const uint8_t* index_dev, const dd_tensor* dy, int ksize, const dd_tensor* dx, void* stream);
 /* Same routing for fp16 / bf16 tensors in gather form (no atomics): dx += the gradient, in place, in the tensors' 16-bit type. */
 int dd_maxpool_s2_bwd_acc(dd_ctx* ctx, const dd_tensor* x, const dd_tensor* y, const dd_tensor* dy, int ksize, const dd_tensor* dx,
                           void* stream);

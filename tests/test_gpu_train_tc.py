@@ -320,3 +320,27 @@ def test_dgrad_conv_with_fused_mask_and_bias_gradient(ctx, cin, cout, n, h, w):
   ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.bfloat16().float().permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)
   want = (ref * (mask.float() > 0)).sum(dim=(0, 1, 2))
   assert rel_err(db - base, want) <= 2e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("k,h,w", [(3, 12, 20), (3, 11, 17), (2, 12, 20), (2, 9, 15)])
+def test_maxpool_index_pair_matches_the_scatter_form(ctx, dtype, k, h, w):
+  """dd_maxpool_s2_fwd_index / dd_maxpool_s2_bwd_index (recorded first maximum, pure-gather backward) == dd_maxpool_s2_fwd +
+  dd_maxpool_s2_bwd (fp32 atomics) on tie-heavy data."""
+  n, c = 2, 16
+  x = torch.clamp(torch.round(torch.randn(n, h, w, c, device="cuda") * 2.0) / 2.0, min=0.0).to(dtype)
+  oh, ow = (h + 1) // 2, (w + 1) // 2
+  y_ref = torch.empty(n, oh, ow, c, device="cuda", dtype=dtype)
+  ctx.maxpool_s2(_lib.desc(x), k, _lib.desc(y_ref))
+  y = torch.empty_like(y_ref)
+  idx = torch.empty(n, oh, ow, c, device="cuda", dtype=torch.uint8)
+  ctx.call("dd_maxpool_s2_fwd_index", _b(_lib.desc(x)), k, _b(_lib.desc(y)), _fp(idx))
+  assert torch.equal(y, y_ref)
+  dy = (torch.round(torch.randn(n, oh, ow, c, device="cuda") * 8.0) / 8.0).to(dtype)
+  want = torch.zeros(n, h, w, c, device="cuda", dtype=torch.float32)
+  ctx.call("dd_maxpool_s2_bwd", _b(_lib.desc(x)), _b(_lib.desc(y_ref)), _b(_lib.desc(dy)), k, _b(_lib.desc(want)))
+  base = (torch.round(torch.randn(n, h, w, c, device="cuda") * 4.0) / 4.0).to(dtype)
+  got = base.clone()
+  ctx.call("dd_maxpool_s2_bwd_index", _fp(idx), _b(_lib.desc(dy)), k, _b(_lib.desc(got)))
+  torch.cuda.synchronize()
+  assert torch.equal(got.float(), base.float() + want)
