@@ -359,14 +359,21 @@ class Architecture:
     std_bank = net._buf("bank.std", (len(every) * n, h, w, 3), torch.float32)
     var_bank = net._buf("bank.var", (len(every) * n, h, w, max(var_width, 1)), torch.float32)
     raw_bank = net._buf("bank.raw", (len(targets) * n, h, w, 3), torch.float32) if self._preserve_source else None
+    jobs = []                                    # every pass in ONE launch (dd_standardize_variance_batch)
     for fp, s in zip(every, sources):
       lo, hi = fp.bank_index * n, (fp.bank_index + 1) * n
       vc = fp.feature_variance.channels(fp.number_of_channels)
-      ctx.standardize_variance(_lib.desc(s), self._std_params(fp), _lib.desc(std_bank[lo:hi]),
-                               _lib.desc(var_bank[lo:hi], vc, 0) if vc else None)
+      jobs.append((_lib.desc(s), self._std_params(fp), _lib.desc(std_bank[lo:hi]),
+                   _lib.desc(var_bank[lo:hi], vc, 0) if vc else None))
       if self._preserve_source and fp.is_target:
         identity = _lib.dd_standardize_params(0, 0.0, 1.0, 0, 0, 0, 0, 0, 1e-4)
-        ctx.standardize_variance(_lib.desc(s), identity, _lib.desc(raw_bank[lo:hi]), None)
+        jobs.append((_lib.desc(s), identity, _lib.desc(raw_bank[lo:hi]), None))
+    if len(jobs) * n <= 65535:
+      job_table = net._buf("std.jobs", (len(jobs) * int(ctx.lib.dd_standardize_variance_job_bytes()),), torch.uint8)
+      ctx.standardize_variance_batch(jobs, job_table)
+    else:
+      for job in jobs:
+        ctx.standardize_variance(*job)
 
     # kernel-prediction sources per scale: avg-pool by 2^s of the full-resolution source (Architecture.py:280-283)
     nt = len(targets) * n

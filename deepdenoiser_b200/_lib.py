@@ -69,6 +69,8 @@ SIGNATURES = {
     "dd_maxpool_s2_fwd": (_i, [_vp, _T, _i, _T, _vp]),
     "dd_avgpool_fwd": (_i, [_vp, _T, _i, _T, _vp]),
     "dd_standardize_variance": (_i, [_vp, _T, _P(dd_standardize_params), _T, _T, _vp]),
+    "dd_standardize_variance_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
+    "dd_standardize_variance_job_bytes": (ctypes.c_size_t, []),
     "dd_assemble_input": (_i, [_vp, _vp, _i, _i, _T, _vp]),
     "dd_kernel_predict_fwd": (_i, [_vp, _T, _T, _i, _i, _i, _T, _vp]),
     "dd_compose_head_fwd": (_i, [_vp, _T, _T, _vp, _vp, _i, _T, _vp]),
@@ -283,6 +285,18 @@ class Context:
     self._check(self.lib.dd_avgpool_fwd(self.handle, ctypes.byref(x), factor, ctypes.byref(y), self._stream()))
 
   # -- encoder
+  def standardize_variance_batch(self, jobs, table):
+    """jobs: list of (src desc, dd_standardize_params, std_out desc | None, var_out desc | None) with identical [n,h,w];
+    table: uint8 device tensor of at least len(jobs) * dd_standardize_variance_job_bytes() bytes."""
+    count = len(jobs)
+    ptr_t = ctypes.POINTER(dd_tensor)
+    src = (ptr_t * count)(*[ctypes.pointer(j[0]) for j in jobs])
+    prm = (dd_standardize_params * count)(*[j[1] for j in jobs])
+    so = (ptr_t * count)(*[ctypes.pointer(j[2]) if j[2] is not None else ptr_t() for j in jobs])
+    vo = (ptr_t * count)(*[ctypes.pointer(j[3]) if j[3] is not None else ptr_t() for j in jobs])
+    self._check(self.lib.dd_standardize_variance_batch(self.handle, count, src, prm, so, vo, table.data_ptr(),
+                                                       table.numel(), self._stream()))
+
   def standardize_variance(self, src, params, std_out, var_out):
     self._check(self.lib.dd_standardize_variance(
         self.handle, ctypes.byref(src), ctypes.byref(params), ctypes.byref(std_out) if std_out is not None else None,

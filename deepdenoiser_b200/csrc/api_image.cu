@@ -2,6 +2,8 @@
 // variance, network-input assembly, the kernel-prediction apply and the multi-scale composition.
 #include <string.h>
 
+#include <vector>
+
 #include "dd_internal.h"
 
 namespace dd {
@@ -263,9 +265,26 @@ __device__ __forceinline__ float standardize_value(float v, const dd_standardize
 // its one-pixel symmetric halo are computed ONCE into shared memory (log1p is the expensive part), then every thread
 // forms the 3x3 / plus-shaped local mean and second moment of its pixel from shared memory.
 constexpr int kStdTileW = 32, kStdTileH = 8, kStdHaloW = kStdTileW + 2, kStdHaloH = kStdTileH + 2;
+__device__ __forceinline__ void standardize_variance_tile(const StdParams& p, int n, float (*s_val)[kStdHaloH * kStdHaloW]);
+
 __global__ void __launch_bounds__(256) standardize_variance_kernel(const StdParams p) {
   __shared__ float s_val[3][kStdHaloH * kStdHaloW];
-  const int n = blockIdx.z;
+  standardize_variance_tile(p, blockIdx.z, s_val);
+}
+
+// every pass of a predict() call in ONE launch: job = blockIdx.z / n_images (44 launches of ~58 MB each ran at a third of the
+// HBM rate: a 1080p pass is too small to fill the machine between its ramp-up and its tail)
+__global__ void __launch_bounds__(256) standardize_variance_batch_kernel(const StdParams* __restrict__ jobs, int n_images) {
+  __shared__ float s_val[3][kStdHaloH * kStdHaloW];
+  __shared__ StdParams job;
+  const int j = blockIdx.z / n_images;
+  if (threadIdx.x < sizeof(StdParams) / 4)
+    reinterpret_cast<uint32_t*>(&job)[threadIdx.x] = reinterpret_cast<const uint32_t*>(jobs + j)[threadIdx.x];
+  __syncthreads();
+  standardize_variance_tile(job, blockIdx.z - j * n_images, s_val);
+}
+
+__device__ __forceinline__ void standardize_variance_tile(const StdParams& p, int n, float (*s_val)[kStdHaloH * kStdHaloW]) {
   const int ty0 = blockIdx.y * kStdTileH, tx0 = blockIdx.x * kStdTileW;
   const int h = p.src.h, w = p.src.w, C = p.src.c;
   if (p.has_v) {
@@ -542,6 +561,54 @@ int dd_avgpool_fwd(dd_ctx* ctx, const dd_tensor* x, int factor, const dd_tensor*
   const size_t total = static_cast<size_t>(y->n) * y->h * y->w;
   avgpool_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+static int make_std_params(const dd_tensor* src, const dd_standardize_params* prm, const dd_tensor* std_out,
+                           const dd_tensor* var_out, StdParams& p);
+
+int dd_standardize_variance_batch(dd_ctx* ctx, int count, const dd_tensor* const* src, const dd_standardize_params* prm,
+                                  const dd_tensor* const* std_out, const dd_tensor* const* var_out, void* table_dev,
+                                  size_t table_bytes, void* stream) {
+  DD_CHECK_ARG(ctx && count > 0 && src && prm && std_out && var_out && table_dev, "bad argument");
+  DD_CHECK_ARG(table_bytes >= static_cast<size_t>(count) * sizeof(StdParams), "table_dev too small (%zu bytes per job)", sizeof(StdParams));
+  static_assert(sizeof(StdParams) % 4 == 0 && sizeof(StdParams) / 4 <= 256, "job record is copied by one block");
+  std::vector<StdParams> jobs(static_cast<size_t>(count));
+  for (int i = 0; i < count; ++i) {
+    int rc = make_std_params(src[i], prm + i, std_out[i], var_out[i], jobs[i]);
+    if (rc) return rc;
+    DD_CHECK_ARG(src[i]->n == src[0]->n && src[i]->h == src[0]->h && src[i]->w == src[0]->w, "batched passes must share [n,h,w]");
+  }
+  const dd_tensor* s0 = src[0];
+  DD_CHECK_ARG(static_cast<long long>(s0->n) * count <= 65535 && (s0->h + kStdTileH - 1) / kStdTileH <= 65535, "standardize: grid too large");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // pageable source: the runtime stages it before returning, the vector may die with this call
+  DD_CUDA(cudaMemcpyAsync(table_dev, jobs.data(), jobs.size() * sizeof(StdParams), cudaMemcpyHostToDevice, s));
+  dim3 grid((s0->w + kStdTileW - 1) / kStdTileW, (s0->h + kStdTileH - 1) / kStdTileH, s0->n * count);
+  standardize_variance_batch_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const StdParams*>(table_dev), s0->n);
+  DD_LAUNCH_CHECK(ctx);
+  return DD_OK;
+}
+
+size_t dd_standardize_variance_job_bytes(void) { return sizeof(StdParams); }
+
+static int make_std_params(const dd_tensor* src, const dd_standardize_params* prm, const dd_tensor* std_out,
+                           const dd_tensor* var_out, StdParams& p) {
+  DD_CHECK_ARG(prm && src && tensor_ok(src), "bad argument");
+  DD_CHECK_ARG(src->c == 1 || src->c == 3, "source must have 1 or 3 channels");
+  DD_CHECK_ARG(std_out || var_out, "nothing to compute");
+  memset(&p, 0, sizeof(p));
+  p.src = make_view(src); p.q = *prm;
+  p.inv_sqrt_var = 1.f / sqrtf(prm->variance);
+  if (std_out) {
+    DD_CHECK_ARG(tensor_ok(std_out) && same_spatial(src, std_out) && std_out->c == 3, "std_out must be [n,h,w,3]");
+    p.sout = make_view(std_out); p.has_s = 1;
+  }
+  if (var_out && prm->use_variance) {
+    const int vc = prm->compress_to_one_channel ? 1 : src->c;
+    DD_CHECK_ARG(tensor_ok(var_out) && same_spatial(src, var_out) && var_out->c == vc, "var_out has wrong dims");
+    p.vout = make_view(var_out); p.has_v = 1;
+  }
   return DD_OK;
 }
 

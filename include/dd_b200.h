@@ -155,6 +155,13 @@ typedef struct dd_standardize_params {
 } dd_standardize_params;
 int dd_standardize_variance(dd_ctx* ctx, const dd_tensor* src, const dd_standardize_params* prm,
                             const dd_tensor* std_out, const dd_tensor* var_out, void* stream);
+/* The same for `count` passes of identical [n,h,w] in ONE launch (Architecture.py:549-555 loops over every pass): arrays of
+ * `count` descriptor pointers (std_out[i] / var_out[i] may be NULL) and `count` parameter blocks.  table_dev: device scratch of
+ * at least count * dd_standardize_variance_job_bytes() bytes (filled by this call on `stream`). */
+int dd_standardize_variance_batch(dd_ctx* ctx, int count, const dd_tensor* const* src, const dd_standardize_params* prm,
+                                  const dd_tensor* const* std_out, const dd_tensor* const* var_out, void* table_dev,
+                                  size_t table_bytes, void* stream);
+size_t dd_standardize_variance_job_bytes(void);
 
 /* SourceEncoder.prepare_neural_network_input (SourceEncoder.py:29-79) for ALL tuples at once:
  * out[t*n + i, y, x, ch] = table[t][ch].ptr ? ptr[((i*h + y)*w + x)*cstride + cidx] : table[t][ch].constant
