@@ -194,7 +194,11 @@ __device__ __forceinline__ void loss_elem(int kind, float p, float t, float eps,
       val = a / den;
       const float sd = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
       const float sp = (p > 0.f) ? 1.f : ((p < 0.f) ? -1.f : 0.f);
-      grad = sd / den - a * sp / (den * den);
+      // d/dp = sd/den - a sp/den^2.  Written without den^2 (overflows fp32 from |p| ~ 1.8e19: direct predictions reach
+      // exp(46)) and, where p lies beyond t on its own side (sd == sp), without the cancellation den - a:
+      // den - a = |t| + sp t + eps exactly.
+      if (sd == sp && sd != 0.f) grad = sp * ((fabsf(t) + sp * t + eps) / den) / den;
+      else grad = (sd - val * sp) / den;
       break;
     }
   }
@@ -695,7 +699,10 @@ __global__ void __launch_bounds__(256) compose_tail_bwd_kernel(const ComposeTail
       atomicAdd(dl + p.large.pix(n, yb + 1, xb + 1) * p.dlarge.cstride + p.dlarge.coff + c, dlow);
       atomicAdd(ds + spix * p.dsmall.cstride + p.dsmall.coff + c, wgt * g);
     }
-    const float da = (a > 0.f) ? dwgt * wgt * (1.f - wgt) : 0.f;
+    // sigmoid'(ar) = e / (1 + e)^2 with e = exp(-ar): `wgt * (1 - wgt)` cancels catastrophically once the gate saturates (ar > ~10
+    // in fp32), which direct predictions (no kernel prediction: unbounded inputs of the compose net) reach routinely
+    const float en = expf(-ar);
+    const float da = (a > 0.f) ? dwgt * en / ((1.f + en) * (1.f + en)) : 0.f;
 #pragma unroll
     for (int c = 0; c < kCmpC; ++c) {
       if (c < p.c_mid) {

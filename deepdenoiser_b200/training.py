@@ -722,9 +722,6 @@ class Trainer:
         ctx.kernel_predict(_lib.desc(kp_sources[s]), logits[s].d, arch.kernel_size, ft, n, _lib.desc(dst))
       else:
         # direct prediction (Architecture.py:519-521): the post-processed tensor is split into 3 channels per feature
-        if ft != 1:
-          raise NotImplementedError("training without kernel prediction is built for SINGLE tuples; the COMBINED variant's "
-                                    "gradients do not match the oracle yet (inference of that variant is built and tested)")
         arch._split_direct(logits[s], dst, len(tuples), n)
       kp.append(dst)
     # multi-scale composition / inverse standardisation; `pre` = values fed to the inversion (needed by its backward)

@@ -94,9 +94,12 @@ def test_gradients_combined_tuples_and_invert_before_compose():
   check_gradients(trainer, want_grads)
 
 
-def test_gradients_without_kernel_prediction():
-  """Direct 3-channel prediction per feature (Architecture.py:519-521 allows use_kernel_prediction = false), SINGLE tuples."""
-  j = small_example(filters=(16, 16), n_convs=1, k=3, tuple_type="SINGLE")
+@pytest.mark.parametrize("tuple_type", ["SINGLE", "COMBINED"])
+def test_gradients_without_kernel_prediction(tuple_type):
+  """Direct 3-channel prediction per feature (Architecture.py:519-521 allows use_kernel_prediction = false).  The
+  predictions are unbounded network outputs fed to signed_expm1 (up to ~1e20 here): the SMAPE gradient has to survive
+  |p|^2 beyond the fp32 range."""
+  j = small_example(filters=(16, 16), n_convs=1, k=3, tuple_type=tuple_type)
   j["architecture"]["kernel_prediction"]["use_kernel_prediction"] = False
   host, weights, features, targets = make_problem(j, n=1, h=8, w=12)
   trainer = Trainer(Architecture(j, weights=weights), TrainingSettings())
