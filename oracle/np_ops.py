@@ -1,10 +1,15 @@
 """ORACLE (test infrastructure, not product code) - numpy restatement of the TensorFlow-1.x operators the
 DeepDenoiser hot path calls.
 
-PARITY UNPINNED: the reference ships no tests / golden vectors and TensorFlow 1.x cannot be installed in
-this environment, so these functions are pinned only by (a) the TF semantics written down in SURVEY.md
-Appendix A, (b) the known-answer/property tests in tests/test_oracle_ops.py and (c) agreement with the
-independent torch-CPU formulation in oracle/torch_ops.py.
+PARITY: the functions that restate REFERENCE code (kernel_prediction, variance_feature, loss_difference,
+signed_log1p / signed_expm1, and - through oracle/reference_model.py - compose_scales and the whole predict path)
+are pinned against that code itself, executed in this container over oracle/tf_shim
+(tests/golden/refshim_components.npz, tests/test_reference_golden.py: 1e-12).  The functions that restate
+TENSORFLOW kernels (conv2d_same, conv2d_transpose_same_s2, max_pool_same_s2, avg_pool_same, pad_symmetric,
+resize_nearest_x2) remain PARITY UNPINNED: the reference ships no tests / golden vectors and TensorFlow 1.x cannot
+be installed here, so they are held only by (a) the TF semantics written down in SURVEY.md Appendix A, (b) the
+known-answer / property tests in tests/test_oracle_ops.py, (c) agreement with the independent torch-CPU formulation
+in oracle/torch_ops.py and with the shim's third formulation.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
 package.  All tensors are NHWC numpy arrays; `dtype` of the inputs is preserved (float64 for the oracle

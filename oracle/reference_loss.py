@@ -5,7 +5,10 @@ Follows Training.py: model_fn loss assembly :611-660, BaseFeatureTraining.loss :
 mean :126-129, FeatureTraining / CombinedFeatureTraining / CombinedImageFeatureTraining.initialize :374-495 and
 LossDifference.difference (LossDifference.py:15-36), variation_mean :139-186 + :304-346 and masked_mean :131-137 with the
 masks of FeatureTraining / CombinedFeatureTraining.initialize :374-392, :434-437, and ms_ssim :188-204 with
-tf.image.ssim_multiscale restated from TensorFlow's image_ops_impl.py [external].  PARITY UNPINNED (see oracle/np_ops.py).
+tf.image.ssim_multiscale restated from TensorFlow's image_ops_impl.py [external].  PARITY: loss and every parameter gradient
+are pinned against the reference's own Training.main() + model_fn executed over oracle/tf_shim
+(tests/golden/refshim_training_example.npz: equal to the last bit for the loss); MS-SSIM is not part of that pin (the shim
+does not restate tf.image.ssim_multiscale) and TensorFlow's kernels stay unpinned (see oracle/np_ops.py).
 """
 import torch
 

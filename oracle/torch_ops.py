@@ -7,7 +7,7 @@ oracle/reference_model.py can run on either backend:
   * torch_ops + float32 -> the "restated reference on CPU" that bench.py times as cpu_baseline / --impl reference
     (oneDNN kernels on all host threads; the closest thing to the reference's TF-CPU path that can run here)
 
-PARITY UNPINNED (see np_ops.py).  tests/test_oracle_ops.py requires the two backends to agree.
+PARITY: see np_ops.py (reference code pinned through oracle/tf_shim; TensorFlow's kernels unpinned).  tests/test_oracle_ops.py requires the two backends to agree.
 Reference call sites are cited per function (file:line under /root/reference/TensorFlow).
 """
 import numpy as np

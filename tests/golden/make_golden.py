@@ -1,9 +1,9 @@
 """Generates tests/golden/<case>.npz: outputs of the float64 numpy oracle (oracle/reference_model.py) on the
 seeded synthetic inputs / weights of tests/cases.py.
 
-PARITY UNPINNED: the reference cannot run here (TensorFlow 1.x) and ships no golden vectors, so these are
-regression pins of the restated oracle, not outputs of the reference itself.  Re-run after an intentional
-oracle change:  python tests/golden/make_golden.py
+These are regression pins of the restated oracle; the outputs of the reference's own code for the same cases are
+tests/golden/refshim_<case>.npz (tests/golden/make_reference_golden.py), which the oracle reproduces to 1e-10.
+Re-run after an intentional oracle change:  python tests/golden/make_golden.py
 """
 import hashlib
 import os

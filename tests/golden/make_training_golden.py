@@ -3,7 +3,8 @@
 block, K = 3, the passes / tuples / flags of ArchitectureExample.json) with the loss weights of TrainingExample.json plus
 non-zero variation / masked-mean weights.
 
-PARITY UNPINNED (see make_golden.py): a regression pin of the restated reference, not TensorFlow output.
+A regression pin of the restated reference; the same problem through the reference's own Training.main() / model_fn is
+tests/golden/refshim_training_example.npz (make_reference_golden.py) - the losses agree to the last bit.
 Re-run after an intentional oracle change:  python tests/golden/make_training_golden.py"""
 import os
 import sys

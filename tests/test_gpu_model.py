@@ -98,6 +98,29 @@ def test_predict_float32_matches_committed_golden(name):
   assert checked > 0
 
 
+@pytest.mark.parametrize("name", cases.GOLDEN_CASES)
+@pytest.mark.parametrize("dtype,bound", [("float32", 1e-4), ("float16x2", 1e-4)])
+def test_predict_matches_the_reference_code_fixtures(name, dtype, bound):
+  """The CUDA path against tests/golden/refshim_<case>.npz: outputs of the reference's OWN Python modules (float64) executed
+  over oracle/tf_shim (tests/golden/make_reference_golden.py) - the exact SIMT path and the high-accuracy tensor-core mode,
+  north-star tolerance."""
+  if dtype == "float16x2" and name not in ("example", "combined_onehot", "variants"):
+    pytest.skip("float16x2 is built for the U-Net with kernel prediction")
+  arch, out, _ = run_case(name, dtype)
+  z = np.load(os.path.join(GOLDEN, "refshim_" + name + ".npz"))
+  checked = 0
+  for key in z.files:
+    if "|" not in key:
+      continue
+    s, k = key.split("|", 1)
+    want = z[key]
+    got = out[int(s)][k].float().cpu().numpy()
+    assert got.shape == want.shape, key
+    assert np.abs(got - want).max() <= bound * max(1.0, np.abs(want).max()), key
+    checked += 1
+  assert checked > 0
+
+
 def test_tuple_chunking_does_not_change_results():
   j, host_arch, weights, features = cases.build("example")
   outs = []

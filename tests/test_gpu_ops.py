@@ -2,6 +2,8 @@
 the C ABI (ctypes) exactly like the product does.  fp32 paths: <= 2e-5 relative to the output scale (fp32
 reassociation); fp16 tensor-core convolution: compared with the oracle run on the SAME fp16-rounded operands,
 tolerance 2e-3 * output scale (one fp16 rounding of the result + fp32 accumulation order)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -418,6 +420,66 @@ def test_compose_scales_fused(ctx, n, h, w, inv, dtype):
   print("compose %s %dx%dx%d: max %.2e mean %.2e" % (dtype, n, h, w, err.max() / max(1.0, np.abs(want).max()), err.mean()))
   close(out, want, 2e-3 if dtype == "f16" else 2e-2, "fused compose")
   assert err.mean() < (2e-4 if dtype == "f16" else 2e-3)
+
+
+def _reference_components():
+  """(inputs, outputs) of tests/golden/refshim_components.npz: the reference's own building blocks executed over
+  oracle/tf_shim by tests/golden/make_reference_golden.py (inputs are a closed form, regenerated here)."""
+  import importlib.util
+  golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+  spec = importlib.util.spec_from_file_location("make_reference_golden", os.path.join(golden, "make_reference_golden.py"))
+  m = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(m)
+  return m.component_inputs(), np.load(os.path.join(golden, "refshim_components.npz"))
+
+
+@pytest.mark.parametrize("k", [3, 5, 7, 21])
+def test_kernel_predict_matches_the_reference_code_fixture(ctx, k):
+  """dd_kernel_predict_fwd (fp32 logits) against KernelPrediction.kernel_prediction of the reference itself."""
+  inp, z = _reference_components()
+  src, logits = inp["kp%d|src" % k].astype(np.float32), inp["kp%d|logits" % k].astype(np.float32)
+  k2 = k * k
+  cpad = (k2 + 7) // 8 * 8
+  padded = np.zeros(logits.shape[:3] + (cpad,), np.float32)
+  padded[..., :k2] = logits
+  out = torch.empty(src.shape, device="cuda")
+  ctx.kernel_predict(_lib.desc(dev(src)), _lib.desc(dev(padded), k2, 0), k, 1, src.shape[0], _lib.desc(out))
+  close(out, z["kp%d|out" % k], 5e-6, "kernel prediction vs reference code")
+
+
+def test_compose_scales_matches_the_reference_code_fixture(ctx):
+  """dd_compose_scales_fwd against MultiScalePrediction.compose_scales of the reference itself (fp16 activations between the
+  layers: the bound of test_compose_scales_fused)."""
+  inp, z = _reference_components()
+  f32 = lambda key: inp["compose|" + key].astype(np.float32)      # noqa: E731
+  names = ["conv2d"] + ["conv2d_%d" % i for i in range(1, 6)]
+  blob, floats, code = _lib.pack_compose_weights(f32(names[0] + "/kernel"), f32(names[0] + "/bias"),
+                                                 [f32(n + "/kernel") for n in names[1:5]], [f32(n + "/bias") for n in names[1:5]],
+                                                 f32(names[5] + "/kernel"), f32(names[5] + "/bias"))
+  out = torch.full(inp["compose|large"].shape, float("nan"), device="cuda")
+  ctx.compose_scales(_lib.desc(dev(f32("small"))), _lib.desc(dev(f32("large"))), (torch.from_numpy(blob).cuda(), floats, code), None,
+                     _lib.desc(out))
+  close(out, z["compose|out"], 2e-3, "compose vs reference code")
+
+
+def test_variance_and_standardisation_match_the_reference_code_fixture(ctx):
+  """dd_standardize_variance against FeatureEngineering.variance / Utilities.signed_log1p of the reference itself."""
+  inp, z = _reference_components()
+  x = inp["var|x"].astype(np.float32)
+  for mode in ("uniform", "neighbor"):
+    for rel in (False, True):
+      for one in (False, True):
+        want = z["var|%s|%d|%d" % (mode, rel, one)]
+        std = torch.empty(x.shape, device="cuda")
+        var = torch.empty(want.shape, device="cuda")
+        params = _lib.dd_standardize_params(0, 0.0, 1.0, 1, 1 if mode == "neighbor" else 0, int(rel), 0, int(one), 1e-4)
+        ctx.standardize_variance(_lib.desc(dev(x)), params, _lib.desc(std), _lib.desc(var))
+        tol = 3e-2 if rel else 1e-5       # relative variance divides by a squared mean that is clamped at 1e-4
+        close(var, want, tol, "variance %s rel %d one %d" % (mode, rel, one))
+  u = inp["util|x"].astype(np.float32).reshape(1, 8, 8, 1)
+  std = torch.empty(1, 8, 8, 3, device="cuda")            # a 1-channel pass is replicated to 3 channels
+  ctx.standardize_variance(_lib.desc(dev(u)), _lib.dd_standardize_params(1, 0.0, 1.0, 0, 0, 0, 0, 0, 1e-4), _lib.desc(std), None)
+  close(std, np.repeat(z["util|log1p"].reshape(1, 8, 8, 1), 3, axis=3), 2e-6, "signed_log1p vs reference code")
 
 
 def test_compose_scales_at_benchmark_shape(ctx):

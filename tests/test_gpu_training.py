@@ -440,9 +440,12 @@ def test_bfloat16_training_and_inference():
   assert losses[-1] < losses[0] - 0.3
 
 
-def test_exact_training_path_matches_committed_golden():
-  """The exact CUDA training path against the COMMITTED fixture tests/golden/training_example.npz (float64 oracle autograd;
-  loss weights of TrainingExample.json + variation / masked-mean terms): loss to 1e-5, every gradient to 2e-3 of its scale."""
+@pytest.mark.parametrize("fixture", ["training_example.npz", "refshim_training_example.npz"])
+def test_exact_training_path_matches_committed_golden(fixture):
+  """The exact CUDA training path against the COMMITTED fixtures: tests/golden/training_example.npz (float64 oracle autograd)
+  and tests/golden/refshim_training_example.npz (loss of the REFERENCE'S OWN Training.main() / model_fn executed over
+  oracle/tf_shim, gradients by autograd through it; tests/golden/make_reference_golden.py).  Loss weights of
+  TrainingExample.json + variation / masked-mean terms: loss to 1e-5, every gradient to 2e-3 of its scale."""
   import importlib.util, os
   here = os.path.dirname(os.path.abspath(__file__))
   spec = importlib.util.spec_from_file_location("make_training_golden", os.path.join(here, "golden", "make_training_golden.py"))
@@ -460,7 +463,7 @@ def test_exact_training_path_matches_committed_golden():
   trainer.forward({k: torch.from_numpy(v) for k, v in features.items()})
   loss = float(trainer.loss_and_gradient({k: torch.from_numpy(v) for k, v in targets.items()}).item())
   trainer.backward()
-  z = np.load(os.path.join(here, "golden", "training_example.npz"))
+  z = np.load(os.path.join(here, "golden", fixture))
   assert abs(loss - float(z["loss"])) <= 1e-5 * max(1.0, abs(float(z["loss"]))), (loss, float(z["loss"]))
   want = {k[len("grad|"):]: z[k].astype(np.float64) for k in z.files if k.startswith("grad|")}
   check_gradients(trainer, want)

@@ -1,0 +1,283 @@
+"""The oracle against the reference's own code.
+
+tests/golden/refshim_<case>.npz hold float64 outputs of the UNMODIFIED reference modules (/root/reference/TensorFlow/
+Architecture.py and everything it imports) executed over oracle/tf_shim - a torch-backed stand-in for the TensorFlow 1.x
+symbols they use - by tests/golden/make_reference_golden.py.  Here:
+  * oracle/reference_model.py (numpy float64 and torch float32 backends) must reproduce them,
+  * the variable names the reference requested, in its creation order, must be the oracle's and the product's,
+  * the shim's restatements of TensorFlow kernels are checked against independent definitions (torch's own 'same' padding,
+    numpy.pad, autograd of the forward convolution for conv2d_transpose, a literal loop for SAME pooling),
+  * when the reference sources are present (this container, not the GPU box) the fixtures are regenerated and compared.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import np_ops, reference_model, torch_ops
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+
+
+def _maker():
+  spec = importlib.util.spec_from_file_location("make_reference_golden", os.path.join(GOLDEN, "make_reference_golden.py"))
+  m = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(m)
+  return m
+
+
+def _shim():
+  """The shim under a private module name (so that `tensorflow` stays unclaimed in this process)."""
+  spec = importlib.util.spec_from_file_location("dd_tf_shim", os.path.join(os.path.dirname(HERE), "oracle", "tf_shim", "tensorflow",
+                                                                          "__init__.py"))
+  m = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(m)
+  return m
+
+
+def _fixture(name):
+  z = np.load(os.path.join(GOLDEN, "refshim_" + name + ".npz"))
+  out = {}
+  for k in z.files:
+    if "|" in k:
+      s, key = k.split("|", 1)
+      out.setdefault(int(s), {})[key] = z[k]
+  return [out[s] for s in sorted(out)], z
+
+
+@pytest.mark.parametrize("name", cases.GOLDEN_CASES)
+def test_numpy_oracle_reproduces_the_reference_code(name):
+  from golden.make_golden import digest
+  j, arch, weights, features = cases.build(name)
+  want, z = _fixture(name)
+  assert digest(features) == str(z["inputs_sha256"]) and digest(weights) == str(z["weights_sha256"]), \
+      "synthetic inputs / weights changed: regenerate with tests/golden/make_reference_golden.py"
+  got = reference_model.Architecture(j, ops=np_ops, dtype=np.float64, weights=weights).predict_numpy(features)
+  assert len(got) == len(want)
+  for s in range(len(want)):
+    assert set(got[s]) == set(want[s])
+    for k in want[s]:
+      assert got[s][k].shape == want[s][k].shape, (s, k)
+      scale = max(1.0, float(np.abs(want[s][k]).max()))
+      assert np.abs(got[s][k] - want[s][k]).max() <= 1e-8 * scale, (s, k)       # float64 against float64 (measured: 1e-10, summation order)
+
+
+@pytest.mark.parametrize("name", cases.GOLDEN_CASES)
+def test_torch_float32_oracle_matches_the_reference_code(name):
+  j, arch, weights, features = cases.build(name)
+  want, _ = _fixture(name)
+  got = reference_model.Architecture(j, ops=torch_ops, dtype=torch.float32, weights=weights).predict_numpy(features)
+  for s in range(len(want)):
+    for k in want[s]:
+      scale = max(1.0, float(np.abs(want[s][k]).max()))
+      assert np.abs(got[s][k] - want[s][k]).max() <= 2e-5 * scale, (s, k)
+
+
+@pytest.mark.parametrize("name", ["example", "tiramisu"])
+def test_variable_names_and_creation_order_are_the_references(name):
+  j, arch, weights, features = cases.build(name)
+  _, z = _fixture(name)
+  requested = str(z["variables_in_creation_order"]).split("\n")
+  oracle = reference_model.Architecture(j, weights={})
+  oracle.predict(features)
+  assert oracle.store.created == requested
+  assert [n for n, _ in arch.spec.variable_shapes()] == requested
+
+
+# ------------------------------------------------------------------------------------------------ building blocks
+def _components():
+  m = _maker()
+  z = np.load(os.path.join(GOLDEN, "refshim_components.npz"))
+  return m.component_inputs(), z
+
+
+@pytest.mark.parametrize("k", [3, 5, 7, 21])
+def test_kernel_prediction_oracle_matches_the_reference_code(k):
+  inp, z = _components()
+  got = np_ops.kernel_prediction(inp["kp%d|src" % k], inp["kp%d|logits" % k], k)
+  assert np.abs(got - z["kp%d|out" % k]).max() <= 1e-12
+
+
+def test_variance_loss_difference_and_log_transforms_match_the_reference_code():
+  inp, z = _components()
+  for mode in ("uniform", "neighbor"):
+    for rel in (False, True):
+      for one in (False, True):
+        got = np_ops.variance_feature(inp["var|x"], mode, rel, one)
+        want = z["var|%s|%d|%d" % (mode, rel, one)]
+        assert got.shape == want.shape and np.abs(got - want).max() <= 1e-9 * max(1.0, np.abs(want).max()), (mode, rel, one)
+  for kind in ("DIFFERENCE", "ABSOLUTE", "SMOOTH_ABSOLUTE", "SQUARED", "SMAPE"):
+    got = np_ops.loss_difference(inp["loss|p"], inp["loss|t"], kind)
+    assert np.abs(got - z["loss|" + kind]).max() <= 1e-12, kind
+    got = torch_ops.loss_difference(torch.from_numpy(inp["loss|p"]), torch.from_numpy(inp["loss|t"]), kind).numpy()
+    assert np.abs(got - z["loss|" + kind]).max() <= 1e-12, kind
+  assert np.abs(np_ops.signed_log1p(inp["util|x"]) - z["util|log1p"]).max() <= 1e-13
+  assert np.abs(np_ops.signed_expm1(inp["util|x"]) - z["util|expm1"]).max() <= 1e-12 * np.abs(z["util|expm1"]).max()
+
+
+def test_compose_scales_oracle_matches_the_reference_code():
+  inp, z = _components()
+  weights = {"reused_compose_scales/" + k.split("|", 1)[1]: v for k, v in inp.items() if k.startswith("compose|conv2d")}
+  store = reference_model.VariableStore(weights)
+  store.enter_scope("reused_compose_scales")
+  got = reference_model.compose_scales(np_ops, store, inp["compose|small"], inp["compose|large"])
+  store.exit_scope()
+  assert np.abs(got - z["compose|out"]).max() <= 1e-12
+  assert np.abs(np_ops.avg_pool_same(inp["compose|large"], 4) - z["compose|down4"]).max() <= 1e-13
+  assert np.array_equal(np_ops.resize_nearest_x2(inp["compose|small"]), z["compose|up"])
+
+
+def test_oracle_loss_and_gradients_match_the_references_model_fn():
+  """tests/golden/refshim_training_example.npz: the reference's Training.main() built its loss objects from the training JSON,
+  its model_fn (Training.py:607-725) produced the loss, torch autograd through the shim the gradients."""
+  spec = importlib.util.spec_from_file_location("make_training_golden", os.path.join(GOLDEN, "make_training_golden.py"))
+  mtg = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mtg)
+  j, arch, weights, features, targets = mtg.problem()
+  loss, grads = mtg.oracle_loss_and_gradients(j, weights, features, targets)
+  z = np.load(os.path.join(GOLDEN, "refshim_training_example.npz"))
+  assert abs(loss - float(z["loss"])) <= 1e-12 * abs(float(z["loss"]))
+  checked = 0
+  for key in z.files:
+    if key.startswith("grad|"):
+      want = z[key]
+      got = grads[key[5:]]
+      assert np.abs(got - want).max() <= 1e-9 * max(1e-6, np.abs(want).max()), key
+      checked += 1
+  assert checked == len(weights)
+  # the reference tracked a mean metric for every loaded pass, every combined light and the combined image at every scale
+  metrics = str(z["metrics"]).split("\n")
+  assert "combined_mean/1" in metrics and "combined_diffuse_mean/2" in metrics and "alpha_mean/1" in metrics
+
+
+# ------------------------------------------------------------------------------------------------ the shim's kernels
+def test_shim_conv2d_same_is_torchs_same_padding_and_valid_is_unpadded():
+  tf = _shim()
+  g = torch.Generator().manual_seed(3)
+  x = torch.randn(2, 9, 7, 5, generator=g, dtype=torch.float64)
+  for k in (1, 3, 5):
+    w = torch.randn(k, k, 5, 4, generator=g, dtype=torch.float64)
+    tf.reset({"conv2d/kernel": w, "conv2d/bias": torch.zeros(4, dtype=torch.float64)})
+    got = tf.layers.conv2d(x, 4, (k, k), padding="same", data_format="channels_last")
+    want = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding="same").permute(0, 2, 3, 1)
+    assert torch.allclose(got, want, atol=1e-12)
+    got = tf.nn.conv2d(x, filter=w, strides=[1, 1, 1, 1], padding="VALID", data_format="NHWC")
+    assert got.shape == (2, 9 - k + 1, 7 - k + 1, 4)
+  # NCHW entry point == NHWC entry point
+  tf.reset({"conv2d/kernel": w, "conv2d/bias": torch.ones(4, dtype=torch.float64)})
+  a = tf.layers.conv2d(x, 4, (5, 5), padding="same", activation=tf.nn.relu, data_format="channels_last")
+  tf.reset({"conv2d/kernel": w, "conv2d/bias": torch.ones(4, dtype=torch.float64)})
+  b = tf.layers.conv2d(x.permute(0, 3, 1, 2), 4, (5, 5), padding="same", activation=tf.nn.relu, data_format="channels_first")
+  assert torch.allclose(a, b.permute(0, 2, 3, 1), atol=1e-12)
+
+
+@pytest.mark.parametrize("k,s", [(2, 2), (3, 2)])
+def test_shim_conv2d_transpose_is_the_gradient_of_the_same_padded_forward_convolution(k, s):
+  """tf.layers.conv2d_transpose is DEFINED as conv2d's input gradient: for a forward convolution `y = conv(u, W)` (SAME,
+  stride s, u of the upsampled size), conv2d_transpose(x, W) = d<y, x>/du."""
+  tf = _shim()
+  g = torch.Generator().manual_seed(5)
+  cin, cout, h, w = 3, 4, 5, 6
+  x = torch.randn(1, h, w, cin, generator=g, dtype=torch.float64)
+  kernel = torch.randn(k, k, cout, cin, generator=g, dtype=torch.float64)       # TF layout of the transposed layer
+  tf.reset({"conv2d_transpose/kernel": kernel, "conv2d_transpose/bias": torch.zeros(cout, dtype=torch.float64)})
+  got = tf.layers.conv2d_transpose(x, cout, (k, k), strides=(s, s), padding="same", data_format="channels_last")
+  assert got.shape == (1, h * s, w * s, cout)
+  u = torch.zeros(1, h * s, w * s, cout, dtype=torch.float64, requires_grad=True)
+  y = tf.nn.conv2d(u, filter=kernel, strides=[1, s, s, 1], padding="SAME", data_format="NHWC")   # [k,k,in=cout,out=cin]
+  assert y.shape == x.shape
+  (y * x).sum().backward()
+  assert torch.allclose(got, u.grad, atol=1e-12)
+
+
+def test_shim_same_pooling_pads_the_tail_and_excludes_padding():
+  tf = _shim()
+  g = torch.Generator().manual_seed(7)
+  x = torch.randn(1, 6, 8, 2, generator=g, dtype=torch.float64)
+  got = tf.layers.max_pooling2d(x, (3, 3), (2, 2), padding="same", data_format="channels_last")
+  want = torch.empty(1, 3, 4, 2, dtype=torch.float64)
+  for i in range(3):
+    for j in range(4):          # SAME, k 3, s 2, even size: one padded row / column at the END (pad_before = 0)
+      want[0, i, j] = x[0, 2 * i:min(6, 2 * i + 3), 2 * j:min(8, 2 * j + 3)].amax(dim=(0, 1))
+  assert torch.equal(got, want)
+  odd = torch.randn(1, 5, 5, 1, generator=g, dtype=torch.float64)
+  got = tf.layers.average_pooling2d(odd, 2, 2, padding="same", data_format="channels_last")
+  assert got.shape == (1, 3, 3, 1)
+  assert torch.allclose(got[0, 2, 2, 0], odd[0, 4, 4, 0]) and torch.allclose(got[0, 0, 2, 0], odd[0, 0:2, 4, 0].mean())
+  assert torch.allclose(got[0, 0, 0, 0], odd[0, 0:2, 0:2, 0].mean())
+
+
+def test_shim_pad_modes_are_numpys_and_resize_is_pixel_replication():
+  tf = _shim()
+  x = torch.arange(2 * 4 * 5 * 3, dtype=torch.float64).reshape(2, 4, 5, 3)
+  for mode in ("symmetric", "REFLECT", "constant"):
+    got = tf.pad(x, [[0, 0], [2, 2], [1, 3], [0, 0]], mode)
+    want = np.pad(x.numpy(), [(0, 0), (2, 2), (1, 3), (0, 0)], mode=mode.lower())
+    assert np.array_equal(got.numpy(), want), mode
+  up = tf.image.resize_images(x, (8, 10), method=tf.image.ResizeMethod.NEAREST_NEIGHBOR)
+  assert np.array_equal(up.numpy(), np.repeat(np.repeat(x.numpy(), 2, axis=1), 2, axis=2))
+
+
+def test_shim_variable_scopes_number_default_names_like_tf1():
+  tf = _shim()
+  zeros = {n: torch.zeros(1, 1, 1, 1) for n in ("a/conv2d/kernel", "a/conv2d_1/kernel", "a/b/conv2d/kernel", "conv2d/kernel")}
+  zeros.update({n.replace("kernel", "bias"): torch.zeros(1) for n in list(zeros)})
+  tf.reset(zeros)
+  x = torch.zeros(1, 2, 2, 1)
+  for reuse in (False, True):                       # re-entering 'a' restarts the numbering: reuse finds the same variables
+    with tf.variable_scope("a", reuse=reuse):
+      tf.layers.conv2d(x, 1, (1, 1))
+      tf.layers.conv2d(x, 1, (1, 1))
+      with tf.variable_scope("b"):
+        tf.layers.conv2d(x, 1, (1, 1))
+  tf.layers.conv2d(x, 1, (1, 1))
+  assert tf.created == ["a/conv2d/kernel", "a/conv2d/bias", "a/conv2d_1/kernel", "a/conv2d_1/bias", "a/b/conv2d/kernel",
+                        "a/b/conv2d/bias", "conv2d/kernel", "conv2d/bias"]
+  with pytest.raises(KeyError):
+    with tf.variable_scope("a"):
+      for _ in range(3):
+        tf.layers.conv2d(x, 1, (1, 1))              # a/conv2d_2 was never provided
+
+
+# ------------------------------------------------------------------------------------------------ live, where the reference is
+@pytest.mark.skipif(not os.path.isdir("/root/reference/TensorFlow"), reason="reference sources are not on this machine")
+def test_reference_building_blocks_over_the_shim_reproduce_the_committed_fixture():
+  m = _maker()
+  saved_path, saved_mods = list(sys.path), dict(sys.modules)
+  try:
+    tf, mods = m.load_reference()
+    got = m.reference_components(tf, mods)
+  finally:
+    sys.path[:] = saved_path
+    for k in list(sys.modules):
+      if k not in saved_mods:
+        del sys.modules[k]
+  z = np.load(os.path.join(GOLDEN, "refshim_components.npz"))
+  assert sorted(z.files) == sorted(got)
+  for k in got:
+    assert np.abs(got[k] - z[k]).max() <= 1e-12 * max(1.0, float(np.abs(z[k]).max())), k
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/TensorFlow"), reason="reference sources are not on this machine")
+@pytest.mark.parametrize("name", ["direct", "variants"])
+def test_reference_code_over_the_shim_reproduces_the_committed_fixtures(name):
+  m = _maker()
+  saved_path, saved_mods = list(sys.path), dict(sys.modules)
+  try:
+    tf, mods = m.load_reference()
+    j, arch, weights, features = cases.build(name)
+    got, _ = m.run_reference(tf, mods, j, weights, features, "channels_first")
+  finally:
+    sys.path[:] = saved_path
+    for k in list(sys.modules):
+      if k not in saved_mods:
+        del sys.modules[k]
+  want, _ = _fixture(name)
+  for s in range(len(want)):
+    for k in want[s]:
+      assert np.abs(got[s][k] - want[s][k]).max() <= 1e-12 * max(1.0, float(np.abs(want[s][k]).max())), (s, k)
