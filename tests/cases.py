@@ -52,9 +52,14 @@ def case(name):
     return j, 2, 8, 12
   if name == "rgb9":                          # BASELINE cfg1: 9 source channels, one 64x64 tile
     return synthetic.baseline_architecture_json("rgb9"), 1, 64, 64
+  if name == "unet32_small":                  # BASELINE cfg2 / cfg4 / cfg5 architecture (the benchmarked network) on one small tile
+    return synthetic.baseline_architecture_json("unet32"), 1, 16, 16
+  if name == "tiramisu32_small":              # BASELINE cfg3 architecture: K = 21 needs >= 10 pixels at the coarsest scale
+    return synthetic.baseline_architecture_json("tiramisu32"), 1, 40, 40
   raise KeyError(name)
 
 
+BASELINE_CASES = ("rgb9", "unet32_small", "tiramisu32_small")     # reference-code fixtures only (tests/golden/refshim_*.npz)
 GOLDEN_CASES = ("example", "combined_onehot", "tiramisu", "variants", "direct")
 
 

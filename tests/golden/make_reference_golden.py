@@ -30,6 +30,10 @@ REFERENCE_MODULES = ("RenderPasses", "Naming", "Conv2dUtilities", "Utilities", "
                      "MultiScalePrediction", "SourceEncoder", "UNet", "Tiramisu", "LossDifference", "Architecture")
 
 
+STORED_PASSES = ("prediction/Alpha", "prediction/Diffuse Color", "prediction/Glossy Direct", "prediction/Emission",
+                 "prediction/Volume Indirect")
+
+
 def load_reference():
   """The reference modules (by their own top-level names) with the shim as `tensorflow`; returns (tf shim, modules)."""
   if not os.path.isdir(REFERENCE):
@@ -221,7 +225,7 @@ def main():
   from golden.make_golden import digest
   check = "--check" in sys.argv
   tf, mods = load_reference()
-  for name in cases.GOLDEN_CASES:
+  for name in cases.GOLDEN_CASES + cases.BASELINE_CASES:
     j, arch, weights, features = cases.build(name)
     last, names_last = run_reference(tf, mods, j, weights, features, "channels_last")
     first, names_first = run_reference(tf, mods, j, weights, features, "channels_first")
@@ -235,9 +239,12 @@ def main():
     assert worst < 1e-12, "channels_last and channels_first runs of the reference disagree: %g" % worst
     payload = {"inputs_sha256": np.array(digest(features)), "weights_sha256": np.array(digest(weights)),
                "variables_in_creation_order": np.array("\n".join(names_last))}
+    baseline = name in cases.BASELINE_CASES       # the BASELINE.json architectures: float32 storage, and a subset of the 17 passes
+    keep = None if name != "tiramisu32_small" else STORED_PASSES
     for s, d in enumerate(last):
       for k, v in d.items():
-        payload["%d|%s" % (s, k)] = v.astype(np.float64)
+        if keep is None or k in keep:
+          payload["%d|%s" % (s, k)] = v.astype(np.float32 if baseline else np.float64)
     path = os.path.join(HERE, "refshim_" + name + ".npz")
     if check:
       z = np.load(path)

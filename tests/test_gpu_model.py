@@ -98,13 +98,13 @@ def test_predict_float32_matches_committed_golden(name):
   assert checked > 0
 
 
-@pytest.mark.parametrize("name", cases.GOLDEN_CASES)
+@pytest.mark.parametrize("name", cases.GOLDEN_CASES + cases.BASELINE_CASES)
 @pytest.mark.parametrize("dtype,bound", [("float32", 1e-4), ("float16x2", 1e-4)])
 def test_predict_matches_the_reference_code_fixtures(name, dtype, bound):
   """The CUDA path against tests/golden/refshim_<case>.npz: outputs of the reference's OWN Python modules (float64) executed
   over oracle/tf_shim (tests/golden/make_reference_golden.py) - the exact SIMT path and the high-accuracy tensor-core mode,
   north-star tolerance."""
-  if dtype == "float16x2" and name not in ("example", "combined_onehot", "variants"):
+  if dtype == "float16x2" and name not in ("example", "combined_onehot", "variants", "rgb9", "unet32_small"):
     pytest.skip("float16x2 is built for the U-Net with kernel prediction")
   arch, out, _ = run_case(name, dtype)
   z = np.load(os.path.join(GOLDEN, "refshim_" + name + ".npz"))

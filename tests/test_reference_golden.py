@@ -78,6 +78,23 @@ def test_torch_float32_oracle_matches_the_reference_code(name):
       assert np.abs(got[s][k] - want[s][k]).max() <= 2e-5 * scale, (s, k)
 
 
+@pytest.mark.parametrize("name", cases.BASELINE_CASES)
+def test_oracle_reproduces_the_reference_code_on_the_baseline_architectures(name):
+  """BASELINE.json's own networks (U-Net [64,96,128]x4 K=5 with 32 input channels - the benchmarked one -, the Tiramisu K=21,
+  the 9-channel cfg1) on one small tile; the fixtures are stored in float32."""
+  j, arch, weights, features = cases.build(name)
+  want, z = _fixture(name)
+  got = reference_model.Architecture(j, ops=np_ops, dtype=np.float64, weights=weights).predict_numpy(features)
+  assert len(got) == len(want) == 3
+  for s in range(len(want)):
+    assert set(want[s]) <= set(got[s])
+    for k in want[s]:
+      scale = max(1.0, float(np.abs(want[s][k]).max()))
+      assert np.abs(got[s][k] - want[s][k]).max() <= 2e-7 * scale, (s, k)       # float32 rounding of the stored fixture
+  requested = str(z["variables_in_creation_order"]).split("\n")
+  assert [n for n, _ in arch.spec.variable_shapes()] == requested
+
+
 @pytest.mark.parametrize("name", ["example", "tiramisu"])
 def test_variable_names_and_creation_order_are_the_references(name):
   j, arch, weights, features = cases.build(name)
