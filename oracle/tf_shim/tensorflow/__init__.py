@@ -130,6 +130,11 @@ def exp(x, name=None): return torch.exp(x)
 def sigmoid(x, name=None): return torch.sigmoid(x)
 def minimum(x, y, name=None): return torch.minimum(_t(x, y), _t(y, x).to(_t(x, y).dtype))
 def maximum(x, y, name=None): return torch.maximum(_t(x, y), _t(y, x).to(_t(x, y).dtype))
+def negative(x, name=None): return -x
+def sin(x, name=None): return torch.sin(_t(x).to(COMPUTE_DTYPE) if not isinstance(x, torch.Tensor) else x)
+def cos(x, name=None): return torch.cos(_t(x).to(COMPUTE_DTYPE) if not isinstance(x, torch.Tensor) else x)
+def matmul(a, b, name=None): return torch.matmul(a, b.to(a.dtype))
+def equal(x, y, name=None): return _t(x) == _t(y)
 def less(x, y, name=None): return _t(x, y) < _t(y, x)
 def greater(x, y, name=None): return _t(x, y) > _t(y, x)
 def where(condition, x=None, y=None, name=None): return torch.where(condition, x, y)
@@ -162,6 +167,8 @@ def constant(value, dtype=None, shape=None, name=None):             # noqa: A002
 def ones(shape, dtype=float32, name=None): return torch.ones([int(s) for s in shape], dtype=_f(dtype))     # noqa: A002
 def zeros(shape, dtype=float32, name=None): return torch.zeros([int(s) for s in shape], dtype=_f(dtype))   # noqa: A002
 def reshape(tensor, shape, name=None):                               # noqa: A002
+  if isinstance(tensor, (list, tuple)) and any(isinstance(v, torch.Tensor) for v in tensor):
+    tensor = torch.stack([_t(v).to(COMPUTE_DTYPE) for v in tensor])
   t = tensor if isinstance(tensor, torch.Tensor) else torch.tensor(tensor, dtype=COMPUTE_DTYPE)
   return t.reshape([int(s) for s in shape])
 def transpose(a, perm=None, name=None): return a.permute(*perm) if perm is not None else a.t()
@@ -230,6 +237,13 @@ def map_fn(fn, elems, dtype=None, name=None):
 
 def cond(pred, true_fn=None, false_fn=None, name=None):
   return true_fn() if bool(pred) else false_fn()
+
+
+def case(pred_fn_pairs, default=None, exclusive=False, name=None):
+  hits = [fn for pred, fn in pred_fn_pairs if bool(pred)]
+  if exclusive and len(hits) > 1:
+    raise ValueError("tf.case(exclusive=True): more than one predicate is true")
+  return hits[0]() if hits else default()
 
 
 # ------------------------------------------------------------------------------------------------ SAME padding (TF)
@@ -400,6 +414,16 @@ class _Image(object):
     xs = torch.tensor([min(iw - 1, (c * iw) // ow) for c in range(ow)], dtype=torch.long)
     y = x.index_select(1, ys).index_select(2, xs)
     return y if batched else y[0]
+
+  @staticmethod
+  def flip_left_right(image):
+    """Reverses the width axis ([h, w, c] or [n, h, w, c])."""
+    return torch.flip(image, dims=[image.dim() - 2])
+
+  @staticmethod
+  def rot90(image, k=1, name=None):
+    """k counter-clockwise quarter turns of the (height, width) plane."""
+    return torch.rot90(image, k=int(k) % 4, dims=(image.dim() - 3, image.dim() - 2))
 
   @staticmethod
   def ssim_multiscale(*a, **k):

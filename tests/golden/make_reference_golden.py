@@ -218,6 +218,37 @@ def reference_components(tf, mods, dtype=torch.float64):
   return out
 
 
+AUGMENT_VECTORS = ((0.0, 0.0, 0.0), (0.25, 0.5, 0.75), (0.9, 0.1, 0.3))
+
+
+def reference_augmentation(tf):
+  """DataAugmentation.py on one [h, w, 3] example (the reference augments per example, Training.py:803-815): outputs only."""
+  sys.path.insert(0, REFERENCE)
+  sys.path.insert(0, SHIM)
+  try:
+    da = importlib.import_module("DataAugmentation").DataAugmentation
+  finally:
+    sys.path.remove(SHIM)
+    sys.path.remove(REFERENCE)
+  image = torch.as_tensor(det((5, 7, 3), 77), dtype=torch.float64)
+  out = {}
+  for name in ("Diffuse Color", "Screen Space Normal"):
+    tag = name.replace(" ", "")
+    for flip in (0, 1):
+      out["flip|%s|%d" % (tag, flip)] = da.flip_left_right(image, name, flip).numpy()
+    for k in range(4):
+      out["rot|%s|%d" % (tag, k)] = da.rotate_90(image, k, name).numpy()
+      first = da.rotate_90(image.permute(2, 0, 1), k, name, data_format="channels_first").permute(1, 2, 0)
+      assert torch.equal(first, torch.as_tensor(out["rot|%s|%d" % (tag, k)]))
+  for permute in range(6):
+    out["perm|%d" % permute] = da.permute_rgb(image, permute).numpy()
+  for i, vec in enumerate(AUGMENT_VECTORS):
+    r = da.random_rotation_matrix([torch.tensor(v, dtype=torch.float64) for v in vec])
+    out["matrix|%d" % i] = r.numpy()
+    out["normal|%d" % i] = da.rotate_normal(image, r).numpy()
+  return out
+
+
 def main():
   sys.path.insert(0, ROOT)
   sys.path.insert(0, os.path.dirname(HERE))
@@ -257,6 +288,7 @@ def main():
       print(name, len(last), "scales", len(last[0]), "passes, NHWC vs NCHW max rel diff %.1e" % worst, "->", os.path.basename(path))
   main_training(tf, mods, check)
   comp = reference_components(tf, mods)
+  comp.update({"augment|" + k: v for k, v in reference_augmentation(tf).items()})
   path = os.path.join(HERE, "refshim_components.npz")
   if check:
     z = np.load(path)

@@ -149,6 +149,30 @@ def test_compose_scales_oracle_matches_the_reference_code():
   assert np.array_equal(np_ops.resize_nearest_x2(inp["compose|small"]), z["compose|up"])
 
 
+def test_augmentation_oracle_and_host_matrix_match_the_reference_code():
+  """oracle/np_augment.py and the product's host-side rotation matrix (deepdenoiser_b200/augmentation.py) against
+  DataAugmentation.py itself (flip / rot90 incl. the screen-space-normal sign rules, the five RGB permutations,
+  random_rotation_matrix, rotate_normal)."""
+  from deepdenoiser_b200 import augmentation
+  from oracle import np_augment
+  m = _maker()
+  z = np.load(os.path.join(GOLDEN, "refshim_components.npz"))
+  image = m.det((5, 7, 3), 77)
+  for name in ("Diffuse Color", "Screen Space Normal"):
+    tag = name.replace(" ", "")
+    for flip in (0, 1):
+      assert np.array_equal(np_augment.flip_left_right(image, name, flip), z["augment|flip|%s|%d" % (tag, flip)]), (name, flip)
+    for k in range(4):
+      assert np.array_equal(np_augment.rotate_90(image, k, name), z["augment|rot|%s|%d" % (tag, k)]), (name, k)
+  for permute in range(6):
+    assert np.array_equal(np_augment.permute_rgb(image, permute), z["augment|perm|%d" % permute]), permute
+  for i, vec in enumerate(m.AUGMENT_VECTORS):
+    want = z["augment|matrix|%d" % i]
+    got = augmentation.random_rotation_matrix(vec)
+    assert np.abs(np.asarray(got, dtype=np.float64) - want).max() <= 1e-6, vec          # the product builds it in float32
+    assert np.abs(np_augment.rotate_normal(image, want) - z["augment|normal|%d" % i]).max() <= 1e-13
+
+
 def test_oracle_loss_and_gradients_match_the_references_model_fn():
   """tests/golden/refshim_training_example.npz: the reference's Training.main() built its loss objects from the training JSON,
   its model_fn (Training.py:607-725) produced the loss, torch autograd through the shim the gradients."""
@@ -269,6 +293,7 @@ def test_reference_building_blocks_over_the_shim_reproduce_the_committed_fixture
   try:
     tf, mods = m.load_reference()
     got = m.reference_components(tf, mods)
+    got.update({"augment|" + k: v for k, v in m.reference_augmentation(tf).items()})
   finally:
     sys.path[:] = saved_path
     for k in list(sys.modules):
