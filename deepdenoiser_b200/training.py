@@ -956,6 +956,74 @@ class Trainer:
                  _b(pred_view(st["finals"][s], i)), _b(_lib.desc(gc)), _b(pred_view(dfin[s], c)), _b(_lib.desc(inc)))
         ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(inc)), _b(pred_view(dfin[s], d)))
         ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(inc)), _b(pred_view(dfin[s], i)))
+      # COMBINED tuples: Training.main() builds a CombinedFeatureTraining for EVERY tuple (Training.py:1142-1171), also for the
+      # ones with generated members (Alpha, Emission, Environment: generated Direct / Indirect; Volume: generated Color).  A
+      # generated member's "prediction" is the top-left crop of its standardised source (Architecture.py:151-157), its target
+      # the loader's constant (Training.py:538-549: 1 for Color, 0.5 for Direct / Indirect); no gradient flows into it.
+      if use_combined and arch.feature_prediction_tuple_type == FeaturePredictionTupleType.COMBINED:
+        hs, ws = h >> s, w >> s
+        for tup in arch.feature_prediction_tuples:
+          members = list(tup.feature_predictions)
+          if len(members) != 3 or all(m.load_data for m in members) or not any(m.load_data for m in members):
+            continue                                     # fully loaded tuples are the lights above
+          tag = "%s.%d" % (tup.name, s)
+          P, T, G = [], [], []                           # 3-channel predictions / targets / gradient accumulators per member
+          for index, m in enumerate(members):
+            pb = self._buf("ctup.p%d.%s" % (index, tag), shape)
+            tb = self._buf("ctup.t%d.%s" % (index, tag), shape)
+            if m.load_data:
+              pv, tv = pred_view(st["finals"][s], m), _lib.desc(tgt[m.name][s])
+              if m.number_of_channels == 3:
+                ctx.cast_copy(pv, _lib.desc(pb)); ctx.cast_copy(tv, _lib.desc(tb))
+              else:                                      # Alpha: one channel broadcast against the 3-channel generated members
+                for ch in range(3):
+                  ctx.cast_copy(pv, _lib.desc(pb, 1, ch)); ctx.cast_copy(tv, _lib.desc(tb, 1, ch))
+            else:
+              lo = m.bank_index * n
+              pb.copy_(st["std_bank"][lo:lo + n, :hs, :ws, :])
+              ctx.call("dd_fill", ctypes.c_float(1.0 if index == 0 else 0.5), _b(_lib.desc(tb)))
+            P.append(pb); T.append(tb)
+            G.append(self._buf("ctup.g%d.%s" % (index, tag), shape, zero=True))
+          cp = self._buf("ctup.cp.%s" % tag, shape)
+          ct = self._buf("ctup.ct.%s" % tag, shape)
+          gc = self._buf("ctup.gc.%s" % tag, shape, zero=True)
+          ctx.call("dd_muladd_fwd", _b(_lib.desc(P[0])), _b(_lib.desc(P[1])), _b(_lib.desc(P[2])), _b(_lib.desc(cp)))
+          ctx.call("dd_muladd_fwd", _b(_lib.desc(T[0])), _b(_lib.desc(T[1])), _b(_lib.desc(T[2])), _b(_lib.desc(ct)))
+          if cfg.combined_feature_weight > 0:
+            ctx.call("dd_loss_fwd_bwd", _b(_lib.desc(cp)), _b(_lib.desc(ct)), kind,
+                     ctypes.c_float(S * cfg.combined_feature_weight * factor / px), ctypes.c_float(1e-2), _fp(self.loss_value),
+                     _b(_lib.desc(gc)), 1)
+          if cfg.combined_feature_variation_weight > 0 or cfg.combined_feature_masked_weight > 0:
+            # mask = non-zero mask of the tuple's colour target (RenderPasses.combined_to_color_render_pass)
+            color_pass = tup.name if tup.name in (RenderPasses.ALPHA, RenderPasses.EMISSION, RenderPasses.ENVIRONMENT) else tup.name + " Color"
+            mask_t = next((T[i] for i, m in enumerate(members) if m.name == color_pass), None)
+            if cfg.combined_feature_variation_weight > 0:
+              count = float(n * (hs * (ws - 1) + (hs - 1) * ws))
+              ctx.call("dd_loss_variation_fwd_bwd", _b(_lib.desc(cp)), _b(_lib.desc(ct)), kind,
+                       ctypes.c_float(S * cfg.combined_feature_variation_weight * factor / count), ctypes.c_float(1e-2),
+                       _fp(self.loss_value), _b(_lib.desc(gc)))
+            if cfg.combined_feature_masked_weight > 0:
+              if mask_t is None:
+                raise Exception("Masking is not supported for '%s': no corresponding colour target" % tup.name)
+              msum = self._buf("mask.sum.ctup.%s" % tag, (1,), zero=True)
+              ctx.call("dd_mask_sum", _b(_lib.desc(mask_t)), _fp(msum))
+              ctx.call("dd_loss_masked_fwd_bwd", _b(_lib.desc(cp)), _b(_lib.desc(ct)), _b(_lib.desc(mask_t)), _fp(msum), kind,
+                       ctypes.c_float(S * cfg.combined_feature_masked_weight * factor), ctypes.c_float(1e-2), _fp(self.loss_value),
+                       _b(_lib.desc(gc)))
+          if cfg.combined_feature_ms_ssim_weight > 0 and s == 0:
+            ms_ssim_term(_lib.desc(cp), _lib.desc(ct), _lib.desc(gc), cfg.combined_feature_ms_ssim_weight, tup.name)
+          inc = self._buf("ctup.inc.%s" % tag, shape)
+          ctx.call("dd_muladd_bwd", _b(_lib.desc(P[0])), _b(_lib.desc(P[1])), _b(_lib.desc(P[2])), _b(_lib.desc(gc)),
+                   _b(_lib.desc(G[0])), _b(_lib.desc(inc)))
+          for index, m in enumerate(members):
+            if not m.load_data:
+              continue
+            g_m = G[0] if index == 0 else inc
+            if m.number_of_channels == 3:
+              ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(g_m)), _b(pred_view(dfin[s], m)))
+            else:
+              for ch in range(3):
+                ctx.call("dd_axpy", ctypes.c_float(1.0), _b(_lib.desc(g_m, 1, ch)), _b(pred_view(dfin[s], m)))
     self._dfinal = dfin
     if S != 1.0:
       self.loss_value.div_(S)

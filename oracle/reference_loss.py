@@ -117,11 +117,38 @@ def mask_pass(name):
   return None
 
 
+def combined_tuples_of(model):
+  """[(tuple name, [(member name, load_data, is Color) x 3])] of a COMBINED-tuple architecture (any object with
+  .feature_prediction_tuples whose members have .name / .load_data / .kind or .feature_prediction_type), None for SINGLE tuples."""
+  tuples = getattr(model, "feature_prediction_tuples", None) or []
+  out = []
+  for tup in tuples:
+    members = list(tup.feature_predictions)
+    if len(members) != 3:
+      return None
+    rows = []
+    for index, fp in enumerate(members):
+      rows.append((fp.name, bool(fp.load_data), index == 0))
+    out.append((tup.name, rows))
+  return out or None
+
+
+def combined_to_color_pass(name):
+  """RenderPasses.combined_to_color_render_pass (RenderPasses.py:106-122): the pass whose target masks a combined feature."""
+  return name if name in ("Alpha", "Emission", "Environment", "Ambient Occlusion", "Shadow") else name + " Color"
+
+
 def total_loss(predictions, labels, loaded_names, kind="SMAPE", feature_weight=1.0, combined_feature_weight=5.0,
                combined_image_weight=10.0, use_multiscale_loss=True, feature_variation_weight=0.0, feature_masked_weight=0.0,
                combined_feature_variation_weight=0.0, combined_feature_masked_weight=0.0, combined_image_variation_weight=0.0,
-               feature_ms_ssim_weight=0.0, combined_feature_ms_ssim_weight=0.0, combined_image_ms_ssim_weight=0.0):
-  """predictions: list over scales of {'prediction/<Pass>': tensor}; labels: {'target_image/<Pass>': tensor}."""
+               feature_ms_ssim_weight=0.0, combined_feature_ms_ssim_weight=0.0, combined_image_ms_ssim_weight=0.0,
+               combined_tuples=None):
+  """predictions: list over scales of {'prediction/<Pass>': tensor}; labels: {'target_image/<Pass>': tensor}.
+
+  combined_tuples (combined_tuples_of(model)): COMBINED tuple type.  Training.main() then builds a CombinedFeatureTraining for
+  EVERY tuple (Training.py:1142-1171), also for those whose Direct / Indirect (or Color) members are generated: their
+  'prediction' is the standardised generated source (Architecture.py:151-157), their target the raw constant of
+  FeatureTrainingLoader.add_to_targets_dictionary (Training.py:538-549: 1 for Color, 0.5 for Direct / Indirect)."""
   targets = multiscale_targets(labels, len(predictions))
   p = lambda name: [d["prediction/" + name] for d in predictions]     # noqa: E731
   t = lambda name: [d["target_image/" + name] for d in targets]       # noqa: E731
@@ -131,15 +158,35 @@ def total_loss(predictions, labels, loaded_names, kind="SMAPE", feature_weight=1
       mask = t(mask_pass(name)) if (feature_masked_weight > 0 and mask_pass(name) is not None) else None
       loss = loss + feature_loss(p(name), t(name), kind, feature_weight, use_multiscale_loss, feature_variation_weight,
                                  feature_masked_weight if mask is not None else 0.0, mask, feature_ms_ssim_weight)
+  use_combined = (combined_feature_weight > 0 or combined_feature_variation_weight > 0 or combined_feature_masked_weight > 0 or
+                  combined_feature_ms_ssim_weight > 0)
   lights = [l for l in LIGHTS if all((l + k) in loaded_names for k in (" Color", " Direct", " Indirect"))]
   comb_p, comb_t = {}, {}
-  for l in lights:
-    comb_p[l] = [c * (d + i) for c, d, i in zip(p(l + " Color"), p(l + " Direct"), p(l + " Indirect"))]
-    comb_t[l] = [c * (d + i) for c, d, i in zip(t(l + " Color"), t(l + " Direct"), t(l + " Indirect"))]
-    if (combined_feature_weight > 0 or combined_feature_variation_weight > 0 or combined_feature_masked_weight > 0 or
-        combined_feature_ms_ssim_weight > 0):
-      loss = loss + feature_loss(comb_p[l], comb_t[l], kind, combined_feature_weight, use_multiscale_loss,
-                                 combined_feature_variation_weight, combined_feature_masked_weight, t(l + " Color"),
+  if combined_tuples is None:
+    groups = [(l, [(l + " Color", True, True), (l + " Direct", True, False), (l + " Indirect", True, False)]) for l in lights]
+  else:
+    groups = list(combined_tuples)
+  for name, members in groups:
+    def member_target(member, s):
+      m_name, loaded, is_color = member
+      if loaded:
+        return t(m_name)[s]
+      like = predictions[s]["prediction/" + m_name]
+      return torch.full_like(like, 1.0 if is_color else 0.5)
+    n_scales = len(predictions)
+    preds = [[p(m[0])[s] for m in members] for s in range(n_scales)]
+    tgts = [[member_target(m, s) for m in members] for s in range(n_scales)]
+    comb_p[name] = [c * (d + i) for c, d, i in preds]
+    comb_t[name] = [c * (d + i) for c, d, i in tgts]
+    if use_combined:
+      color_pass = combined_to_color_pass(name)
+      if combined_feature_masked_weight > 0:
+        source = next((m for m in members if m[0] == color_pass), None)
+        mask = [member_target(source, s) for s in range(n_scales)] if source is not None else t(color_pass)
+      else:
+        mask = None
+      loss = loss + feature_loss(comb_p[name], comb_t[name], kind, combined_feature_weight, use_multiscale_loss,
+                                 combined_feature_variation_weight, combined_feature_masked_weight, mask,
                                  combined_feature_ms_ssim_weight)
   terms = [x for x in IMAGE_TERMS if x in loaded_names]
   if ((combined_image_weight > 0 or combined_image_variation_weight > 0 or combined_image_ms_ssim_weight > 0) and

@@ -145,15 +145,32 @@ def main_training(tf, mods, check):
   payload = {"loss": np.array(loss), "metrics": np.array("\n".join(metrics))}
   for k, g in grads.items():
     payload["grad|" + k] = g.astype(np.float64)
-  path = os.path.join(HERE, "refshim_training_example.npz")
+  _write_training(os.path.join(HERE, "refshim_training_example.npz"), payload, check)
+  # COMBINED tuples: the reference's loader also feeds constant targets for the generated members (Training.py:538-549)
+  j, arch, weights, features, targets = mtg.problem_combined()
+  full_targets = dict(targets)
+  n, h, w = next(iter(targets.values())).shape[:3]
+  for tup in arch.feature_prediction_tuples:
+    for index, fp in enumerate(tup.feature_predictions):
+      if not fp.load_data:
+        full_targets["target_image/" + fp.name] = np.full((n, h, w, fp.number_of_channels), 1.0 if index == 0 else 0.5, np.float32)
+  loss, grads, metrics = run_reference_training(tf, mods, j, training_json_for(mtg.COMBINED_LOSS_ARGS), weights, features,
+                                                full_targets)
+  payload = {"loss": np.array(loss), "metrics": np.array("\n".join(metrics))}
+  for k, g in grads.items():
+    payload["grad|" + k] = g.astype(np.float32)
+  _write_training(os.path.join(HERE, "refshim_training_combined.npz"), payload, check)
+
+
+def _write_training(path, payload, check):
   if check:
     z = np.load(path)
-    assert float(z["loss"]) == loss
-    print("training_example matches the committed fixture")
+    assert float(z["loss"]) == float(payload["loss"])
+    print(os.path.basename(path), "matches the committed fixture")
   else:
     np.savez_compressed(path, **payload)
-    print("training_example: loss %.9f, %d gradient tensors, %d tracked metrics -> %s" % (loss, len(grads), len(metrics),
-                                                                                         os.path.basename(path)))
+    print("%s: loss %.9f, %d gradient tensors" % (os.path.basename(path), float(payload["loss"]),
+                                                  sum(k.startswith("grad|") for k in payload)))
 
 
 def det(shape, seed, scale=1.0):

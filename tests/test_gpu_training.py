@@ -43,7 +43,7 @@ def oracle_loss_and_grads(j, weights, features, targets, **loss_args):
   preds = [{k: v for k, v in d.items()} for d in preds]
   labels = {k: torch.as_tensor(v, dtype=torch.float64) for k, v in targets.items()}
   loaded = [fp.name for fp in model.feature_predictions if fp.load_data]
-  loss = reference_loss.total_loss(preds, labels, loaded, **loss_args)
+  loss = reference_loss.total_loss(preds, labels, loaded, combined_tuples=reference_loss.combined_tuples_of(model), **loss_args)
   loss.backward()
   grads = {k: (v.grad.numpy() if v.grad is not None else np.zeros_like(weights[k], dtype=np.float64)) for k, v in params.items()}
   return float(loss.detach()), grads, preds
@@ -438,6 +438,30 @@ def test_bfloat16_training_and_inference():
   losses = [float(tr.train_step(f, t).item()) for _ in range(10)]
   print("bf16 losses", ["%.4f" % l for l in losses])
   assert losses[-1] < losses[0] - 0.3
+
+
+def test_combined_tuple_training_matches_the_reference_code_fixture():
+  """COMBINED tuples against tests/golden/refshim_training_combined.npz (the reference's own Training.main() / model_fn over
+  oracle/tf_shim): the combined-feature loss of EVERY tuple, generated members included; ABSOLUTE differences + variation terms."""
+  import importlib.util, os
+  here = os.path.dirname(os.path.abspath(__file__))
+  spec = importlib.util.spec_from_file_location("make_training_golden", os.path.join(here, "golden", "make_training_golden.py"))
+  gen = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(gen)
+  j, arch, weights, features, targets = gen.problem_combined()
+  tj = {"loss_difference": "ABSOLUTE",
+        "features_training_settings": {"loss_weights": {"mean": 1.0, "variation": 0.25, "ms_ssim": 0.0}},
+        "combined_features_training_settings": {"loss_weights": {"mean": 5.0, "variation": 0.5, "ms_ssim": 0.0}},
+        "combined_image_training_settings": {"loss_weights": {"mean": 10.0, "variation": 0.0, "ms_ssim": 0.0}}}
+  jj = dict(j)
+  jj["b200"] = {"dtype": "float32"}
+  trainer = Trainer(Architecture(jj, weights=weights), TrainingSettings(tj))
+  trainer.forward({k: torch.from_numpy(v) for k, v in features.items()})
+  loss = float(trainer.loss_and_gradient({k: torch.from_numpy(v) for k, v in targets.items()}).item())
+  trainer.backward()
+  z = np.load(os.path.join(here, "golden", "refshim_training_combined.npz"))
+  assert abs(loss - float(z["loss"])) <= 1e-5 * max(1.0, abs(float(z["loss"]))), (loss, float(z["loss"]))
+  check_gradients(trainer, {k[len("grad|"):]: z[k].astype(np.float64) for k in z.files if k.startswith("grad|")})
 
 
 @pytest.mark.parametrize("fixture", ["training_example.npz", "refshim_training_example.npz"])

@@ -196,6 +196,23 @@ def test_oracle_loss_and_gradients_match_the_references_model_fn():
   assert "combined_mean/1" in metrics and "combined_diffuse_mean/2" in metrics and "alpha_mean/1" in metrics
 
 
+def test_oracle_loss_for_combined_tuples_matches_the_references_model_fn():
+  """COMBINED tuples: Training.main() builds a combined-feature loss for EVERY tuple, also for Alpha / Emission / Environment /
+  Volume whose generated members 'predict' their standardised source against the loader's constant targets
+  (tests/golden/refshim_training_combined.npz; ABSOLUTE differences, variation terms)."""
+  spec = importlib.util.spec_from_file_location("make_training_golden", os.path.join(GOLDEN, "make_training_golden.py"))
+  mtg = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mtg)
+  j, arch, weights, features, targets = mtg.problem_combined()
+  loss, grads = mtg.oracle_loss_and_gradients(j, weights, features, targets, mtg.COMBINED_LOSS_ARGS)
+  z = np.load(os.path.join(GOLDEN, "refshim_training_combined.npz"))
+  assert abs(loss - float(z["loss"])) <= 1e-12 * abs(float(z["loss"])), (loss, float(z["loss"]))
+  for key in z.files:
+    if key.startswith("grad|"):
+      want = z[key].astype(np.float64)
+      assert np.abs(grads[key[5:]] - want).max() <= 1e-6 * max(1e-6, np.abs(want).max()), key     # float32-stored fixture
+
+
 # ------------------------------------------------------------------------------------------------ the shim's kernels
 def test_shim_conv2d_same_is_torchs_same_padding_and_valid_is_unpadded():
   tf = _shim()
