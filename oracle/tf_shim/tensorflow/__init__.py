@@ -122,7 +122,8 @@ def squared_difference(x, y, name=None): return (x - y) * (x - y)
 def abs(x, name=None): return torch.abs(x)                      # noqa: A001
 def sign(x, name=None): return torch.sign(x)
 def square(x, name=None): return x * x
-def sqrt(x, name=None): return torch.sqrt(_t(x).to(torch.float64)) if not isinstance(x, torch.Tensor) else torch.sqrt(x)
+def _c(x): return x if isinstance(x, torch.Tensor) else torch.as_tensor(x, dtype=COMPUTE_DTYPE)     # python scalars: compute dtype
+def sqrt(x, name=None): return torch.sqrt(_c(x))
 def log(x, name=None): return torch.log(x)
 def log1p(x, name=None): return torch.log1p(x)
 def expm1(x, name=None): return torch.expm1(x)
@@ -131,8 +132,8 @@ def sigmoid(x, name=None): return torch.sigmoid(x)
 def minimum(x, y, name=None): return torch.minimum(_t(x, y), _t(y, x).to(_t(x, y).dtype))
 def maximum(x, y, name=None): return torch.maximum(_t(x, y), _t(y, x).to(_t(x, y).dtype))
 def negative(x, name=None): return -x
-def sin(x, name=None): return torch.sin(_t(x).to(COMPUTE_DTYPE) if not isinstance(x, torch.Tensor) else x)
-def cos(x, name=None): return torch.cos(_t(x).to(COMPUTE_DTYPE) if not isinstance(x, torch.Tensor) else x)
+def sin(x, name=None): return torch.sin(_c(x))
+def cos(x, name=None): return torch.cos(_c(x))
 def matmul(a, b, name=None): return torch.matmul(a, b.to(a.dtype))
 def equal(x, y, name=None): return _t(x) == _t(y)
 def less(x, y, name=None): return _t(x, y) < _t(y, x)

@@ -79,3 +79,49 @@ def build(name, seed=4321):
       planes[..., i] = 1.0
       features["feature_flag/" + nm] = planes
   return j, arch, weights, features
+
+
+def random_case(trial):
+  """Seeded random point of the architecture JSON space the reference accepts (backbone, filters, convolutions per block,
+  K 3 / 5 / 7, SINGLE / COMBINED tuples, NONE / ONE_HOT / EMBEDDING flags, kernel prediction on / off with standardised or raw
+  source, multi-scale on / off, inversion before / after, pass and auxiliary subsets, variance mode / relative / before /
+  compressed, log1p / mean / variance) -> (json, product-side Architecture, weights, features)."""
+  import random
+  import numpy as np
+  from deepdenoiser_b200.Architecture import Architecture
+  rnd = random.Random(1000 + trial)
+  ex = synthetic.example_architecture_json()
+  j = _small(ex, rnd.choice([[8, 8], [8, 16, 8], [16, 8, 8, 8]]), rnd.choice([1, 2, 3]), rnd.choice([3, 5, 7]))
+  a = j["architecture"]
+  a["core_architecture"]["name"] = rnd.choice(["U-Net", "Tiramisu"])
+  a["source_encoder"] = {"feature_prediction_tuple_type": rnd.choice(["SINGLE", "COMBINED"]),
+                         "feature_flag_mode": rnd.choice(["NONE", "ONE_HOT_ENCODING", "EMBEDDING"])}
+  a["kernel_prediction"]["use_kernel_prediction"] = rnd.random() < 0.8
+  a["kernel_prediction"]["use_standardized_source_for_kernel_prediction"] = rnd.random() < 0.5
+  a["multiscale_prediction"]["use_multiscale_predictions"] = rnd.random() < 0.8
+  a["multiscale_prediction"]["invert_standardization_after_multiscale_predictions"] = rnd.random() < 0.5
+  names = rnd.sample(sorted(ex["combined_features"]), rnd.choice([2, 3, 8]))
+  j["combined_features"] = {k: ex["combined_features"][k] for k in names}
+  aux = sorted(ex["auxiliary_features"])             # the reference needs at least one (Architecture.py:404 reads a leaked name)
+  j["auxiliary_features"] = {k: copy.deepcopy(ex["auxiliary_features"][k]) for k in rnd.sample(aux, rnd.randint(1, len(aux)))}
+  one = rnd.random() < 0.5 or "Alpha" in names       # every tuple must feed the same number of input channels
+  for kind in ("Color", "Direct", "Indirect"):
+    hnd = j["combined_features_handling"][kind]
+    hnd["feature_variance"].update(use_variance=True, variance_mode=rnd.choice(["uniform", "neighbor"]),
+                                   relative_variance=rnd.random() < 0.5, compute_before_standardization=rnd.random() < 0.5,
+                                   compress_to_one_channel=one)
+    hnd["standardization"].update(use_log1p=rnd.random() < 0.7, mean=rnd.choice([0.0, 0.3]), variance=rnd.choice([1.0, 1.7]))
+    hnd["invert_standardization"] = rnd.random() < 0.8
+  arch = Architecture(j, seed=100 + trial)
+  weights = synthetic.randomize_biases(arch.weights)
+  arch.weights = weights
+  steps = len(a["core_architecture"]["number_of_filters_for_convolution_blocks"]) - 1
+  h = w = (8 << steps) if a["kernel_prediction"]["kernel_size"] < 7 else (16 << steps)
+  features = synthetic.synthetic_features(arch, 1, h, w, seed=trial)
+  if arch.feature_flag_mode.name == "ONE_HOT_ENCODING":
+    tuple_names = sorted(t.name for t in arch.feature_prediction_tuples)
+    for i, nm in enumerate(tuple_names):
+      planes = np.zeros((1, h, w, len(tuple_names)), dtype=np.float32)
+      planes[..., i] = 1.0
+      features["feature_flag/" + nm] = planes
+  return j, arch, weights, features

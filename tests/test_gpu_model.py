@@ -121,6 +121,23 @@ def test_predict_matches_the_reference_code_fixtures(name, dtype, bound):
   assert checked > 0
 
 
+@pytest.mark.parametrize("trial", range(16))
+def test_random_architectures_exact_path_matches_the_oracle(trial):
+  """cases.random_case: seeded random points of the architecture JSON space (the same sweep tests/test_reference_golden.py runs
+  through the reference's own code): the exact CUDA path against the float64 oracle, north-star tolerance."""
+  j, host_arch, weights, features = cases.random_case(trial)
+  j = dict(j)
+  j["b200"] = {"dtype": "float32"}
+  arch = Architecture(j, weights=weights)
+  out = arch.predict({k: torch.from_numpy(v) for k, v in features.items()}, ModeKeys.PREDICT)
+  torch.cuda.synchronize()
+  oracle = reference_model.Architecture(j, ops=np_ops, dtype=np.float64, weights=weights).predict_numpy(features)
+  if max(float(np.abs(v).max()) for d in oracle for v in d.values()) > 1e30:
+    pytest.skip("signed_expm1 of a raw-source prediction leaves the fp32 range (the reference's float32 graph overflows too)")
+  mx, mean = errors(out, oracle)
+  assert mx <= 1e-4, (trial, mx)
+
+
 def test_tuple_chunking_does_not_change_results():
   j, host_arch, weights, features = cases.build("example")
   outs = []

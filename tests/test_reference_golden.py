@@ -340,3 +340,29 @@ def test_reference_code_over_the_shim_reproduces_the_committed_fixtures(name):
   for s in range(len(want)):
     for k in want[s]:
       assert np.abs(got[s][k] - want[s][k]).max() <= 1e-12 * max(1.0, float(np.abs(want[s][k]).max())), (s, k)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/TensorFlow"), reason="reference sources are not on this machine")
+def test_random_architectures_oracle_matches_the_reference_code_live():
+  """cases.random_case: a seeded sweep over the architecture JSON - the reference's Architecture.predict over the shim against
+  the oracle (float64), and the product's variable list against the variables the reference requested."""
+  m = _maker()
+  saved_path, saved_mods = list(sys.path), dict(sys.modules)
+  try:
+    tf, mods = m.load_reference()
+    for trial in range(16):
+      j, arch, weights, features = cases.random_case(trial)
+      want, requested = m.run_reference(tf, mods, j, weights, features, "channels_first" if trial % 2 else "channels_last")
+      got = reference_model.Architecture(j, ops=np_ops, dtype=np.float64, weights=weights).predict_numpy(features)
+      assert [n for n, _ in arch.spec.variable_shapes()] == requested, trial
+      assert len(got) == len(want), trial
+      for s in range(len(want)):
+        assert set(got[s]) == set(want[s]), trial
+        for k in want[s]:
+          assert got[s][k].shape == want[s][k].shape, (trial, s, k)
+          assert np.abs(got[s][k] - want[s][k]).max() <= 1e-9 * max(1.0, float(np.abs(want[s][k]).max())), (trial, s, k)
+  finally:
+    sys.path[:] = saved_path
+    for k in list(sys.modules):
+      if k not in saved_mods:
+        del sys.modules[k]
