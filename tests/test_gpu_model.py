@@ -138,6 +138,26 @@ def test_random_architectures_exact_path_matches_the_oracle(trial):
   assert mx <= 1e-4, (trial, mx)
 
 
+@pytest.mark.parametrize("trial", range(0, 24, 2))
+@pytest.mark.parametrize("dtype,bound", [("float16", 3e-2), ("bfloat16", 2.5e-1)])
+def test_random_architectures_run_on_the_tensor_core_path(trial, dtype, bound):
+  """The same sweep through the 16-bit tensor-core modes: every configuration must run (odd channel counts, 2- to 4-level
+  backbones, K 3 / 5 / 7 fused or stand-alone heads, with and without kernel prediction / multi-scale) and stay finite; the
+  bound only catches structural errors (a wrong channel mapping is O(1)) - the tiny random-weight nets push 16-bit rounding
+  through signed_expm1 (measured: float16 <= 1.6e-2, bfloat16 <= 1.9e-1 where the outputs stay below 1e4)."""
+  j, host_arch, weights, features = cases.random_case(trial)
+  j = dict(j)
+  j["b200"] = {"dtype": dtype}
+  oracle = reference_model.Architecture(j, ops=np_ops, dtype=np.float64, weights=weights).predict_numpy(features)
+  arch = Architecture(j, weights=weights)
+  out = arch.predict({k: torch.from_numpy(v) for k, v in features.items()}, ModeKeys.PREDICT)
+  torch.cuda.synchronize()
+  if max(float(np.abs(v).max()) for d in oracle for v in d.values()) > 1e4:
+    return                                  # ran; exp-amplified outputs are not a meaningful yardstick for 16-bit rounding
+  mx, mean = errors(out, oracle)
+  assert mx <= bound, (trial, mx)
+
+
 def test_tuple_chunking_does_not_change_results():
   j, host_arch, weights, features = cases.build("example")
   outs = []
