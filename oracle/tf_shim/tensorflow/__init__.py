@@ -499,3 +499,97 @@ def _estimator(model_fn=None, model_dir=None, config=None, params=None, **unused
 
 
 estimator.Estimator = _estimator
+
+
+# ------------------------------------------------------------------------------------------------ Prediction.main() plumbing
+# Prediction.py writes its tiles into a temporary TFRecord file and reads them back through tf.data (Prediction.py:85-155, 316-372).
+# Here the "file" is a list of {feature name: bytes} kept in memory (an empty file is created so that main()'s os.remove works),
+# and `Estimator.predict` (ESTIMATOR_MODE = "predict") feeds every record, as a batch of one [tile, tile, 3] float32 example per
+# feature, to the reference's model_fn and yields its prediction dictionary without the batch axis - what
+# tf.estimator.Estimator.predict yields.  The tile grid, the crop / stitch arithmetic and the combination of the passes are
+# the reference's own statements.
+ESTIMATOR_MODE = "capture"
+RECORDS = {}
+
+
+def enable_eager_execution(*a, **k):
+  return None
+
+
+class _Compat(object):
+  as_bytes = staticmethod(lambda b: bytes(b))
+
+
+compat = _Compat()
+
+
+class _Train(object):
+  class BytesList(object):
+    def __init__(self, value=None):
+      self.value = list(value or [])
+
+  class Feature(object):
+    def __init__(self, bytes_list=None):
+      self.bytes_list = bytes_list
+
+  class Features(object):
+    def __init__(self, feature=None):
+      self.feature = dict(feature or {})
+
+  class Example(object):
+    def __init__(self, features=None):
+      self.features = features
+
+    def SerializeToString(self):
+      return self
+
+
+train = _Train()
+
+
+class _TFRecordWriter(object):
+  def __init__(self, path):
+    import os
+    self.key = os.path.abspath(path)
+    RECORDS[self.key] = []
+    open(path, "wb").close()
+
+  def write(self, example):
+    RECORDS[self.key].append({k: v.bytes_list.value[0] for k, v in example.features.feature.items()})
+
+  def close(self):
+    pass
+
+
+class _PythonIO(object):
+  TFRecordWriter = _TFRecordWriter
+
+
+python_io = _PythonIO()
+
+
+class _PredictingEstimator(object):
+  def __init__(self, model_fn=None, model_dir=None, config=None, params=None, **unused):
+    self.model_fn, self.params = model_fn, params
+
+  def predict(self, input_fn=None, **unused):
+    import numpy as np
+    records = list(RECORDS.values())[-1]
+    for record in records:
+      features = {}
+      for name, raw in record.items():
+        flat = np.frombuffer(raw, dtype=np.float32)
+        side = int(round((flat.size // 3) ** 0.5))
+        assert side * side * 3 == flat.size, "Prediction.py reshapes every source to [tile, tile, 3] (Prediction.py:70)"
+        features[name] = torch.as_tensor(flat.reshape(1, side, side, 3).copy(), dtype=COMPUTE_DTYPE)
+      spec = self.model_fn(features, None, _ModeKeys.PREDICT, self.params)
+      yield {k: v[0].detach().numpy() for k, v in spec.predictions.items()}
+
+
+def _estimator(model_fn=None, model_dir=None, config=None, params=None, **unused):      # noqa: F811
+  if ESTIMATOR_MODE == "predict":
+    return _PredictingEstimator(model_fn, model_dir, config, params)
+  raise SetupCaptured(model_fn, params)
+
+
+estimator.Estimator = _estimator

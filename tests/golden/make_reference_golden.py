@@ -235,6 +235,72 @@ def reference_components(tf, mods, dtype=torch.float64):
   return out
 
 
+def prediction_problem():
+  """A small all-passes network (ArchitectureExample.json with [8, 8] filters, one convolution per block, K = 3, without the
+  'Screen Space Normal' auxiliary: Prediction.py matches files by SUBSTRING, 'Normal' would also match that file) and a
+  40 x 72 frame cut into 32-pixel tiles with 4 pixels of overlap: 2 x 3 tiles, first / interior / last in the width."""
+  sys.path.insert(0, ROOT)
+  sys.path.insert(0, os.path.dirname(HERE))
+  import cases
+  from deepdenoiser_b200 import synthetic
+  from deepdenoiser_b200.Architecture import Architecture
+  j = cases._small(synthetic.example_architecture_json(), [8, 8], 1, 3)
+  j["auxiliary_features"] = {k: v for k, v in j["auxiliary_features"].items() if k != "Screen Space Normal"}
+  arch = Architecture(j, seed=777)
+  weights = synthetic.randomize_biases(arch.weights)
+  arch.weights = weights
+  h, w = 40, 72
+  features = synthetic.synthetic_features(arch, 1, h, w, seed=99)
+  frame = {}
+  for fp in arch.required_features():
+    if fp.load_data:
+      img = features["source_image/0/" + fp.name][0]
+      frame[fp.name] = np.repeat(img, 3, axis=2) if img.shape[2] == 1 else img        # an EXR always decodes to 3 channels
+  return j, arch, weights, frame, h, w, 32, 4
+
+
+def reference_prediction(tf):
+  """Prediction.main() of the reference (Prediction.py:188-519) on a scratch directory: returns {file stem: array} of the
+  .npy files it saved (every pass + 'Combined')."""
+  import argparse
+  import json
+  import tempfile
+  j, arch, weights, frame, h, w, tile, overlap = prediction_problem()
+  for name in ("Prediction", "OpenEXRDirectory", "cv2"):
+    sys.modules.pop(name, None)
+  sys.path.insert(0, REFERENCE)
+  sys.path.insert(0, SHIM)
+  try:
+    prediction = importlib.import_module("Prediction")
+    assert os.path.abspath(prediction.__file__).startswith(os.path.abspath(REFERENCE)), prediction.__file__
+  finally:
+    sys.path.remove(SHIM)
+    sys.path.remove(REFERENCE)
+  tf.reset({k: torch.as_tensor(np.asarray(v), dtype=torch.float64) for k, v in weights.items()})
+  tf.ESTIMATOR_MODE = "predict"
+  cwd = os.getcwd()
+  out = {}
+  try:
+    with tempfile.TemporaryDirectory() as scratch:
+      frame_dir = os.path.join(scratch, "frame")
+      os.makedirs(frame_dir)
+      for name, img in frame.items():
+        with open(os.path.join(frame_dir, name + ".exr"), "wb") as f:
+          np.save(f, np.ascontiguousarray(img[..., ::-1]).astype(np.float32))           # BGR, as OpenCV decodes
+      with open(os.path.join(scratch, "architecture.json"), "w") as f:
+        json.dump(j, f)
+      os.chdir(scratch)                                                                 # main() writes ./tmp.tfrecords
+      prediction.main(argparse.Namespace(json_filename=os.path.join(scratch, "architecture.json"), input=frame_dir, tile_size=tile,
+                                         tile_overlap_size=overlap, threads=1, data_format="channels_last"))
+      for file in sorted(os.listdir(frame_dir)):
+        if file.endswith(".npy"):
+          out[file[:-4]] = np.load(os.path.join(frame_dir, file))
+  finally:
+    os.chdir(cwd)
+    tf.ESTIMATOR_MODE = "capture"
+  return out
+
+
 AUGMENT_VECTORS = ((0.0, 0.0, 0.0), (0.25, 0.5, 0.75), (0.9, 0.1, 0.3))
 
 
@@ -304,6 +370,16 @@ def main():
       np.savez_compressed(path, **payload)
       print(name, len(last), "scales", len(last[0]), "passes, NHWC vs NCHW max rel diff %.1e" % worst, "->", os.path.basename(path))
   main_training(tf, mods, check)
+  pred = reference_prediction(tf)
+  path = os.path.join(HERE, "refshim_prediction.npz")
+  if check:
+    z = np.load(path)
+    for k in pred:
+      assert np.array_equal(z[k], pred[k].astype(np.float32)), k
+    print("tiled prediction matches the committed fixture")
+  else:
+    np.savez_compressed(path, **{k: v.astype(np.float32) for k, v in pred.items()})
+    print("tiled prediction:", len(pred), "images", next(iter(pred.values())).shape, "->", os.path.basename(path))
   comp = reference_components(tf, mods)
   comp.update({"augment|" + k: v for k, v in reference_augmentation(tf).items()})
   path = os.path.join(HERE, "refshim_components.npz")

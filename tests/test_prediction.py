@@ -172,6 +172,30 @@ def test_prediction_cli_matches_tiled_oracle(tmp_path):
   assert err <= 1e-4, err
 
 
+@pytest.mark.gpu
+def test_tiled_prediction_on_the_device_matches_the_references_prediction_main():
+  """The product path (frame resident on the device, tiles cut / pasted by dd_tiles_gather / dd_tiles_scatter, exact fp32
+  network, lighting combination in libdd_b200) against tests/golden/refshim_prediction.npz - the output files of the
+  reference's own Prediction.main() executed over oracle/tf_shim (tests/golden/make_reference_golden.py)."""
+  import importlib.util
+  golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+  spec = importlib.util.spec_from_file_location("make_reference_golden", os.path.join(golden, "make_reference_golden.py"))
+  m = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(m)
+  j, arch_host, weights, frame, h, w, tile, overlap = m.prediction_problem()
+  j = dict(j)
+  j["b200"] = {"dtype": "float32"}
+  arch = Architecture(j, weights=weights)
+  feats = {"source_image/0/" + name: img for name, img in frame.items()}
+  got = prediction.predict_image(arch, feats, h, w, tile, overlap)
+  image, combined = prediction.combine_passes(got, arch.ctx)
+  z = np.load(os.path.join(golden, "refshim_prediction.npz"))
+  for key in z.files:
+    mine = image if key == "Combined" else got["prediction/" + key]
+    assert tuple(mine.shape) == z[key].shape, key
+    assert np.abs(mine.float().cpu().numpy() - z[key]).max() <= 1e-4 * max(1.0, float(np.abs(z[key]).max())), key
+
+
 def test_tile_grid_partitions_any_image_exactly():
   """Property (ragged sizes): for any image at least 16 pixels wide the kept crops of the reference's tile grid
   (Prediction.py:259-310, 396-427) cover every pixel exactly once and every tile lies inside the image."""

@@ -213,6 +213,31 @@ def test_oracle_loss_for_combined_tuples_matches_the_references_model_fn():
       assert np.abs(grads[key[5:]] - want).max() <= 1e-6 * max(1e-6, np.abs(want).max()), key     # float32-stored fixture
 
 
+def test_tiled_prediction_matches_the_references_prediction_main():
+  """tests/golden/refshim_prediction.npz: the reference's Prediction.main() (Prediction.py:188-519 - tile grid, per-tile
+  prediction, crop / stitch, lighting = colour x (direct + indirect), combined image) on a 40 x 72 frame with 32-pixel tiles and
+  4 pixels of overlap.  Here: the product's tile grid / stitch / combine (deepdenoiser_b200/prediction.py) around the ORACLE
+  as the per-tile network."""
+  from deepdenoiser_b200 import prediction
+  m = _maker()
+  j, arch, weights, frame, h, w, tile, overlap = m.prediction_problem()
+  z = np.load(os.path.join(GOLDEN, "refshim_prediction.npz"))
+  oracle = reference_model.Architecture(j, ops=np_ops, dtype=np.float64, weights=weights)
+  feats = {"source_image/0/" + name: img for name, img in frame.items()}
+  got = prediction.predict_image(
+      None, feats, h, w, tile, overlap, tiles_per_batch=1,
+      predict_fn=lambda f: {k: torch.from_numpy(v) for k, v in oracle.predict_numpy({kk: vv.numpy() for kk, vv in f.items()})[0].items()})
+  image, combined = prediction.combine_passes(got)
+  assert sorted(z.files) == sorted(["Combined"] + [k[len("prediction/"):] for k in got])
+  for key in z.files:
+    mine = image if key == "Combined" else got["prediction/" + key]
+    assert tuple(mine.shape) == z[key].shape, (key, tuple(mine.shape), z[key].shape)
+    assert np.abs(mine.numpy() - z[key]).max() <= 2e-6 * max(1.0, float(np.abs(z[key]).max())), key    # float32-stored fixture
+  assert z["Alpha"].shape == (h, w, 1) and z["Combined"].shape == (h, w, 3)
+  tiles, _, _ = prediction.tile_grid(h, w, tile, overlap)
+  assert len(tiles) == 6                                   # 2 x 3: first / interior / last column
+
+
 # ------------------------------------------------------------------------------------------------ the shim's kernels
 def test_shim_conv2d_same_is_torchs_same_padding_and_valid_is_unpadded():
   tf = _shim()
@@ -303,6 +328,24 @@ def test_shim_variable_scopes_number_default_names_like_tf1():
 
 
 # ------------------------------------------------------------------------------------------------ live, where the reference is
+@pytest.mark.skipif(not os.path.isdir("/root/reference/TensorFlow"), reason="reference sources are not on this machine")
+def test_reference_prediction_main_over_the_shim_reproduces_the_committed_fixture():
+  m = _maker()
+  saved_path, saved_mods = list(sys.path), dict(sys.modules)
+  try:
+    tf, mods = m.load_reference()
+    got = m.reference_prediction(tf)
+  finally:
+    sys.path[:] = saved_path
+    for k in list(sys.modules):
+      if k not in saved_mods:
+        del sys.modules[k]
+  z = np.load(os.path.join(GOLDEN, "refshim_prediction.npz"))
+  assert sorted(z.files) == sorted(got)
+  for k in got:
+    assert np.array_equal(got[k].astype(np.float32), z[k]), k
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/TensorFlow"), reason="reference sources are not on this machine")
 def test_reference_building_blocks_over_the_shim_reproduce_the_committed_fixture():
   m = _maker()
