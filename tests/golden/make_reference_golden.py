@@ -302,6 +302,11 @@ def reference_prediction(tf):
 
 
 AUGMENT_VECTORS = ((0.0, 0.0, 0.0), (0.25, 0.5, 0.75), (0.9, 0.1, 0.3))
+# (tag, [(pass, channels, is target)], flip, rot90 k, RGB permutation, rotation vector); the reference refuses to flip 'Normal'
+AUGMENT_PIPELINES = (
+    ("rotate", [("Diffuse Color", 3, True), ("Normal", 3, False), ("Screen Space Normal", 3, False), ("Depth", 1, False),
+                ("Alpha", 1, True)], None, 3, 4, (0.25, 0.5, 0.75)),
+    ("flip", [("Glossy Direct", 3, True), ("Screen Space Normal", 3, False), ("Depth", 1, False)], 1, 1, 2, None))
 
 
 def reference_augmentation(tf):
@@ -329,6 +334,32 @@ def reference_augmentation(tf):
     r = da.random_rotation_matrix([torch.tensor(v, dtype=torch.float64) for v in vec])
     out["matrix|%d" % i] = r.numpy()
     out["normal|%d" % i] = da.rotate_normal(image, r).numpy()
+  # the whole per-example pipeline in the reference's order (FeatureTrainingAugmentation, Training.py:551-605, driven as
+  # input_fn_tfrecords does, :803-819): flip -> rot90 -> RGB permutation -> normal rotation
+  sys.path.insert(0, REFERENCE)
+  sys.path.insert(0, SHIM)
+  try:
+    training = importlib.import_module("Training")
+  finally:
+    sys.path.remove(SHIM)
+    sys.path.remove(REFERENCE)
+  for tag, passes, flip, rot, perm, vec in AUGMENT_PIPELINES:
+    sources = {"source_image/0/" + n: torch.as_tensor(det((6, 6, c), 300 + i), dtype=torch.float64) for i, (n, c, _) in enumerate(passes)}
+    targets = {"target_image/" + n: torch.as_tensor(det((6, 6, c), 400 + i), dtype=torch.float64) for i, (n, c, t) in enumerate(passes) if t}
+    matrix = da.random_rotation_matrix([torch.tensor(v, dtype=torch.float64) for v in vec]) if vec is not None else None
+    for n, c, is_target in passes:
+      fta = training.FeatureTrainingAugmentation(1, is_target, c, n)
+      fta.intialize_from_dictionaries(sources, targets)
+      if flip is not None:
+        fta.flip_left_right(flip, "channels_last")
+      fta.rotate_90(rot, "channels_last")
+      fta.permute_rgb(perm, "channels_last")
+      if matrix is not None:
+        fta.rotate_normal(matrix, "channels_last")
+      fta.add_to_sources_dictionary(sources)
+      fta.add_to_targets_dictionary(targets)
+    for k, v in list(sources.items()) + list(targets.items()):
+      out["pipeline|%s|%s" % (tag, k)] = v.numpy()
   return out
 
 

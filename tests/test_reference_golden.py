@@ -173,6 +173,26 @@ def test_augmentation_oracle_and_host_matrix_match_the_reference_code():
     assert np.abs(np_augment.rotate_normal(image, want) - z["augment|normal|%d" % i]).max() <= 1e-13
 
 
+def test_augmentation_pipeline_order_matches_the_references_feature_training_augmentation():
+  """FeatureTrainingAugmentation driven as input_fn_tfrecords drives it (Training.py:551-605, 803-819) against
+  oracle/np_augment.augment_example: flip -> rot90 -> RGB permutation (colour passes only) -> normal rotation ('Normal' only),
+  sources and targets, 1- and 3-channel passes."""
+  from deepdenoiser_b200.RenderPasses import RenderPasses
+  from oracle import np_augment
+  m = _maker()
+  z = np.load(os.path.join(GOLDEN, "refshim_components.npz"))
+  for tag, passes, flip, rot, perm, vec in m.AUGMENT_PIPELINES:
+    matrix = z["augment|matrix|%d" % m.AUGMENT_VECTORS.index(vec)] if vec is not None else None
+    for i, (name, c, is_target) in enumerate(passes):
+      for kind, seed in (("source_image/0/", 300 + i), ("target_image/", 400 + i)):
+        if kind == "target_image/" and not is_target:
+          continue
+        got = np_augment.augment_example(m.det((6, 6, c), seed), name, RenderPasses.is_rgb_color_render_pass(name), flip=flip, rot=rot,
+                                         perm=perm, rotation=matrix)
+        want = z["augment|pipeline|%s|%s%s" % (tag, kind, name)]
+        assert got.shape == want.shape and np.abs(got - want).max() <= 1e-13, (tag, kind, name)
+
+
 def test_oracle_loss_and_gradients_match_the_references_model_fn():
   """tests/golden/refshim_training_example.npz: the reference's Training.main() built its loss objects from the training JSON,
   its model_fn (Training.py:607-725) produced the loss, torch autograd through the shim the gradients."""
