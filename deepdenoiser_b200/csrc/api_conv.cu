@@ -424,6 +424,7 @@ int dd_ctx_set_option(dd_ctx* ctx, const char* name, int value) {
   DD_CHECK_ARG(ctx && name, "NULL argument");
   if (!strcmp(name, "conv_rows")) { ctx->conv_rows = value; return DD_OK; }               // cap on G (rows per weight pass)
   if (!strcmp(name, "conv_b_stages")) { ctx->conv_b_stages = value; return DD_OK; }       // weight stages when streaming (0 = auto)
+  if (!strcmp(name, "std_generic")) { ctx->std_generic = value; return DD_OK; }           // generic standardisation tile kernel (A/B)
   if (!strcmp(name, "conv_dbg")) { ctx->conv_dbg = value; return DD_OK; }                 // ablation switches (wrong results)
   if (!strcmp(name, "conv_force_stream")) { ctx->conv_force_stream = value; return DD_OK; } // never keep weights resident
   set_error("unknown option '%s'", name);

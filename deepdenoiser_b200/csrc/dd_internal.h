@@ -19,6 +19,7 @@ struct dd_ctx {
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through the runtime
   int conv_rows = 0;             // cap on input rows per weight pass (0 = auto), see conv_rows.cuh
   int conv_b_stages = 0;         // debug: weight stages of the streaming configuration (0 = auto)
+  int std_generic = 0;           // dd_standardize_variance_batch: force the generic tile kernel (A/B switch of the fp32 fast path)
   int conv_dbg = 0;              // debug: ablation switches of conv_rows_kernel (ConvRowsParams::dbg)
   int conv_force_stream = 0;     // debug: stream weights even when they would fit in shared memory
   unsigned long long* conv_trace = nullptr;  // debug: device buffer [64][8] of clock64 stamps (CTA 0)

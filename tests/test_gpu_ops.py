@@ -261,6 +261,42 @@ def test_standardize_variance(ctx, c, mode, rel, before, comp, log1p, mean, var)
   close(v, want_v, tol, "variance")
 
 
+@pytest.mark.parametrize("n,h,w", [(1, 8, 8), (2, 37, 71), (1, 16, 130)])
+@pytest.mark.parametrize("generic", [0, 1])
+def test_standardize_variance_batch_all_variants_in_one_launch(ctx, n, h, w, generic):
+  """dd_standardize_variance_batch: every parametrisation as one job of ONE launch (fp32 fast path: 64 x 16 tiles, four pixels per
+  thread; generic=1 forces the generic tile kernel), 1- and 3-channel sources, tiles cut by the image border on both axes."""
+  jobs, wants = [], []
+  keep = []
+  for c in (3, 1):
+    for mode in ("uniform", "neighbor"):
+      for rel in (False, True):
+        for before in (False, True):
+          for comp in (False, True):
+            log1p, mean, var = (not before), (0.3 if rel else 0.0), (1.7 if comp else 1.0)
+            x = (RNG.standard_normal((n, h, w, c)) * 3).astype(np.float32)
+            x[0, :3, :4] = 0.0
+            prm = _lib.dd_standardize_params(int(log1p), mean, var, 1, 0 if mode == "uniform" else 1, int(rel), int(before), int(comp), 1e-4)
+            sd = torch.full((n, h, w, 3), float("nan"), device="cuda")
+            vd = torch.full((n, h, w, 1 if comp else c), float("nan"), device="cuda")
+            xd = dev(x)
+            keep.append((xd, sd, vd))
+            jobs.append((_lib.desc(xd), prm, _lib.desc(sd), _lib.desc(vd)))
+            x64 = x.astype(np.float64)
+            std = np_ops.signed_log1p(x64) if log1p else x64
+            std = (std - mean) / np.sqrt(var)
+            wants.append((np.repeat(std, 3, axis=3) if c == 1 else std, np_ops.variance_feature(x64 if before else std, mode, rel, comp), rel))
+  table = torch.empty(len(jobs) * int(ctx.lib.dd_standardize_variance_job_bytes()), dtype=torch.uint8, device="cuda")
+  ctx.set_option("std_generic", generic)
+  try:
+    ctx.standardize_variance_batch(jobs, table)
+  finally:
+    ctx.set_option("std_generic", 0)
+  for (xd, sd, vd), (want_s, want_v, rel) in zip(keep, wants):
+    close(sd, want_s, 2e-6, "standardize (batch)")
+    close(vd, want_v, 3e-2 if rel else 2e-5, "variance (batch)")
+
+
 def test_assemble_input_gathers_channels(ctx):
   n, h, w, tuples, c = 2, 5, 7, 3, 16
   a = RNG.standard_normal((n, h, w, 3)).astype(np.float32)
