@@ -1,9 +1,9 @@
 """TEST INFRASTRUCTURE - not part of the product, never imported by deepdenoiser_b200/.
 
-A minimal EAGER stand-in for the ~60 TensorFlow 1.x symbols that the reference's prediction and loss code touches
-(/root/reference/TensorFlow/{Architecture,UNet,Tiramisu,KernelPrediction,MultiScalePrediction,FeatureEngineering,
-Conv2dUtilities,SourceEncoder,FeatureFlags,Utilities,LossDifference}.py and the loss classes of Training.py), backed by
-torch CPU tensors.  With this directory first on sys.path, `import tensorflow as tf` inside the UNMODIFIED reference
+A minimal EAGER stand-in for the ~100 TensorFlow 1.x symbols that the reference's prediction, loss, augmentation and tiling
+code touches (/root/reference/TensorFlow/{Architecture,UNet,Tiramisu,KernelPrediction,MultiScalePrediction,FeatureEngineering,
+Conv2dUtilities,SourceEncoder,FeatureFlags,Utilities,LossDifference,DataAugmentation}.py, Training.py up to its Estimator and its
+model_fn, Prediction.py's main()), backed by torch CPU tensors.  With this directory first on sys.path, `import tensorflow as tf` inside the UNMODIFIED reference
 modules resolves to this file, so the reference's own Python - its control flow, slicing arithmetic, scope / variable
 naming, data-format conversions - executes here and produces the vectors of tests/golden/refshim_*.npz
 (tests/golden/make_reference_golden.py).  TensorFlow itself cannot be installed in this image.

@@ -2,7 +2,7 @@
 /root/reference/TensorFlow, imported from where they lie) for the seeded synthetic inputs / weights of tests/cases.py.
 
 TensorFlow 1.x cannot be installed in this image, so `import tensorflow` inside the reference modules resolves to
-oracle/tf_shim/tensorflow - a torch-backed eager stand-in for the ~60 TF symbols this path uses (its header states what
+oracle/tf_shim/tensorflow - a torch-backed eager stand-in for the ~100 TF symbols these paths use (its header states what
 that leaves unverified: TF's kernels are restated, the reference's code is executed as written).  Both data formats of
 the reference ('channels_last', its CPU mode, and 'channels_first', its GPU default with the NHWC <-> NCHW conversions of
 Conv2dUtilities.convert_to_data_format) are run in float64 and must agree before anything is written.
