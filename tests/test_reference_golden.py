@@ -315,6 +315,33 @@ def test_shim_same_pooling_pads_the_tail_and_excludes_padding():
   assert torch.allclose(got[0, 0, 0, 0], odd[0, 0:2, 0:2, 0].mean())
 
 
+def test_same_padding_rule_is_the_one_hugging_face_uses_to_run_tensorflow_checkpoints():
+  """An outside witness for TensorFlow's SAME rule: transformers' `apply_tf_padding` (MobileNet ports, validated against real
+  TensorFlow checkpoints) pads exactly like the shim's `_same_pad` and the oracle's `np_ops.same_padding` for every
+  (size, kernel, stride) the path uses and more; torch's 'nearest' interpolation is the shim's resize for any ratio."""
+  mobilenet = pytest.importorskip("transformers.models.mobilenet_v2.modeling_mobilenet_v2")
+  tf = _shim()
+  for k in (1, 2, 3, 5, 7):
+    for stride in (1, 2, 3):
+      conv = torch.nn.Conv2d(1, 1, k, stride=stride)
+      for size in range(1, 20):
+        x = torch.zeros(1, 1, size, size + 3)
+        padded = mobilenet.apply_tf_padding(x, conv)
+        top, bottom = tf._same_pad(size, k, stride)
+        left, right = tf._same_pad(size + 3, k, stride)
+        assert tuple(padded.shape[-2:]) == (size + top + bottom, size + 3 + left + right), (k, stride, size)
+        probe = torch.zeros(1, 1, size, size + 3)
+        probe[0, 0, 0, 0] = 1.0
+        where = torch.nonzero(mobilenet.apply_tf_padding(probe, conv)[0, 0])[0].tolist()
+        assert where == [top, left], (k, stride, size)                     # the smaller half goes in front
+        assert tuple(np_ops.same_padding(size, k, stride)[1:]) == (top, bottom), (k, stride, size)
+  x = torch.arange(2 * 5 * 7 * 3, dtype=torch.float64).reshape(2, 5, 7, 3)
+  for oh, ow in ((10, 14), (8, 9), (3, 4)):
+    got = tf.image.resize_images(x, (oh, ow), method=tf.image.ResizeMethod.NEAREST_NEIGHBOR)
+    want = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2), size=(oh, ow), mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(got, want), (oh, ow)
+
+
 def test_shim_pad_modes_are_numpys_and_resize_is_pixel_replication():
   tf = _shim()
   x = torch.arange(2 * 4 * 5 * 3, dtype=torch.float64).reshape(2, 4, 5, 3)
