@@ -63,6 +63,16 @@ def run_reference(tf, mods, j, weights, features, data_format, dtype=torch.float
   return [{k: v.detach().numpy() for k, v in d.items()} for d in out], list(tf.created)
 
 
+def describe_reference(mods, j):
+  """Bookkeeping of the reference's Architecture object (Architecture.py:367-473): passes, tuples, auxiliaries."""
+  arch = mods["Architecture"].Architecture(j, source_data_format="channels_last", data_format="channels_last")
+  row = lambda fp: (fp.name, bool(fp.load_data), bool(fp.is_target), int(fp.number_of_channels), int(fp.number_of_sources),     # noqa: E731
+                    bool(fp.preserve_source), bool(fp.invert_standardization) if fp.is_target else None)
+  return {"feature_predictions": [row(fp) for fp in arch.feature_predictions],
+          "auxiliary_features": [row(fp) for fp in arch.auxiliary_features],
+          "tuples": [(t.name, [fp.name for fp in t.feature_predictions]) for t in arch.feature_prediction_tuples]}
+
+
 def reference_training_setup(tf, j, training_json, data_format="channels_last"):
   """Runs the reference's Training.main() (Training.py:944-1232) on JSON files written to a scratch directory until it
   constructs its tf.estimator.Estimator; returns (Training module, model_fn, params) - the loss objects in `params` were

@@ -445,12 +445,96 @@ def test_random_architectures_oracle_matches_the_reference_code_live():
       want, requested = m.run_reference(tf, mods, j, weights, features, "channels_first" if trial % 2 else "channels_last")
       got = reference_model.Architecture(j, ops=np_ops, dtype=np.float64, weights=weights).predict_numpy(features)
       assert [n for n, _ in arch.spec.variable_shapes()] == requested, trial
+      # the product's host-side bookkeeping (deepdenoiser_b200/Architecture.py) against the reference's objects
+      book = m.describe_reference(mods, j)
+      row = lambda fp: (fp.name, bool(fp.load_data), bool(fp.is_target), int(fp.number_of_channels), int(fp.number_of_sources),     # noqa: E731
+                        bool(fp.preserve_source), bool(fp.invert_standardization) if fp.is_target else None)
+      assert [row(fp) for fp in arch.feature_predictions] == book["feature_predictions"], trial
+      assert [row(fp) for fp in arch.auxiliary_features] == book["auxiliary_features"], trial
+      assert [(t.name, [fp.name for fp in t.feature_predictions]) for t in arch.feature_prediction_tuples] == book["tuples"], trial
       assert len(got) == len(want), trial
       for s in range(len(want)):
         assert set(got[s]) == set(want[s]), trial
         for k in want[s]:
           assert got[s][k].shape == want[s][k].shape, (trial, s, k)
           assert np.abs(got[s][k] - want[s][k]).max() <= 1e-9 * max(1.0, float(np.abs(want[s][k]).max())), (trial, s, k)
+  finally:
+    sys.path[:] = saved_path
+    for k in list(sys.modules):
+      if k not in saved_mods:
+        del sys.modules[k]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/TensorFlow"), reason="reference sources are not on this machine")
+def test_source_index_tuples_draw_like_the_references_live():
+  """Training.source_index_tuples (Training.py:879-913) under the same `random` seed: same tuples, same required indices."""
+  import random
+  from deepdenoiser_b200 import tfrecords
+  m = _maker()
+  saved_path, saved_mods = list(sys.path), dict(sys.modules)
+  try:
+    tf, mods = m.load_reference()
+    sys.path.insert(0, m.REFERENCE)
+    sys.path.insert(0, m.SHIM)
+    import importlib
+    training = importlib.import_module("Training")
+    for per_example, tuples, per_target in ((4, 8, 1), (4, 10, 1), (3, 2, 1), (5, 7, 2), (2, 6, 2)):
+      for seed in (0, 1, 2):
+        random.seed(seed)
+        want = training.source_index_tuples(per_example, tuples, per_target)
+        random.seed(seed)
+        got = tfrecords.source_index_tuples(per_example, tuples, per_target)
+        assert (list(got[0]), list(got[1])) == (list(want[0]), list(want[1])), (per_example, tuples, per_target, seed)
+    for bad in ((1, 4, 2), (4, 4, 3)):
+      with pytest.raises(Exception):
+        training.source_index_tuples(*bad)
+      with pytest.raises(Exception):
+        tfrecords.source_index_tuples(*bad)
+  finally:
+    sys.path[:] = saved_path
+    for k in list(sys.modules):
+      if k not in saved_mods:
+        del sys.modules[k]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/TensorFlow"), reason="reference sources are not on this machine")
+def test_render_passes_and_naming_agree_with_the_references_live():
+  """The pure-Python helpers of the drop-in boundary (RenderPasses.py, Naming.py - dictionary keys, pass classification, mask
+  lookups incl. the ' Inirect' typo) against the reference's own functions, over every pass constant of both trees, every
+  combined feature name and every flag combination."""
+  import itertools
+  from deepdenoiser_b200.Naming import Naming
+  from deepdenoiser_b200.RenderPasses import RenderPasses
+  m = _maker()
+  saved_path, saved_mods = list(sys.path), dict(sys.modules)
+  try:
+    tf, mods = m.load_reference()
+    ref_rp, ref_nm = mods["RenderPasses"].RenderPasses, mods["Naming"].Naming
+    constants = {k: v for k, v in vars(ref_rp).items() if k.isupper() and isinstance(v, str)}
+    assert constants, "no pass constants found in the reference"
+    for key, value in constants.items():
+      assert getattr(RenderPasses, key) == value, key
+    names = sorted(set(constants.values()) | {"Alpha Direct", "Volume Color", "Foo", "Foo Direct", "Foo Indirect", "Foo Color", ""})
+    for name in names:
+      for fn in ("number_of_channels", "is_combined_feature_render_pass", "is_volume_render_pass", "is_direct_or_indirect_render_pass",
+                 "is_color_render_pass", "is_rgb_color_render_pass", "combined_to_color_render_pass", "combined_to_direct_render_pass",
+                 "combined_to_indirect_render_pass"):
+        assert getattr(RenderPasses, fn)(name) == getattr(ref_rp, fn)(name), (fn, name)
+      if ref_rp.is_direct_or_indirect_render_pass(name):
+        assert RenderPasses.direct_or_indirect_to_color_render_pass(name) == ref_rp.direct_or_indirect_to_color_render_pass(name), name
+      assert Naming.feature_prediction_name(name) == ref_nm.feature_prediction_name(name)
+      assert Naming.feature_flags_name(name) == ref_nm.feature_flags_name(name)
+      assert Naming.tensorboard_name(name) == ref_nm.tensorboard_name(name)
+      for masked in (False, True):
+        assert Naming.target_feature_name(name, masked=masked) == ref_nm.target_feature_name(name, masked=masked)
+        for spp, index in itertools.product((None, 16), (None, 0, 3)):
+          assert (Naming.source_feature_name(name, samples_per_pixel=spp, index=index, masked=masked) ==
+                  ref_nm.source_feature_name(name, samples_per_pixel=spp, index=index, masked=masked)), (name, spp, index, masked)
+        for internal, scale in itertools.product((False, True), (None, 0, 2)):
+          for fn in ("difference_name", "mean_name", "variation_difference_name", "variation_mean_name"):
+            assert (getattr(Naming, fn)(name, masked=masked, internal=internal, scale_index=scale) ==
+                    getattr(ref_nm, fn)(name, masked=masked, internal=internal, scale_index=scale)), (fn, name, masked, internal, scale)
+          assert Naming.ms_ssim_name(name, masked=masked, internal=internal) == ref_nm.ms_ssim_name(name, masked=masked, internal=internal)
   finally:
     sys.path[:] = saved_path
     for k in list(sys.modules):
